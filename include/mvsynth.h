@@ -37,7 +37,7 @@ typedef struct mvs_params {
     int32_t  mean_coeffs_x10;   /* mean TotalCoeff of a coded 4x4 block, times 10        */
     int32_t  level_scale_x10;   /* Laplacian scale of |level|-1, times 10                */
     int32_t  max_level;         /* |level| <= max_level (AC); DC limited to 4*max_level  */
-    int32_t  poc_type;          /* 0 or 2                                                 */
+    int32_t  poc_type;          /* must be 0 (the reference mis-parses types 1 and 2)     */
     int32_t  crop_bottom;       /* frame_crop_bottom_offset in luma rows/2 (signalled only) */
     int32_t  force_mode;        /* -1 random; else use this pred mode wherever legal      */
     int32_t  force_kind;        /* -1 random; else 0/1/2                                  */

@@ -562,6 +562,9 @@ int mvs_generate(const mvs_params *p, mvs_output *out)
     if (p->profile_idc != 66 && p->profile_idc != 77 && p->profile_idc != 100) return 0;
     if (p->qp_min < 0 || p->qp_max > 51 || p->qp_min > p->qp_max) return 0;
     if (p->init_qp < p->qp_min || p->init_qp > p->qp_max) return 0;
+    /* The reference parses the pic_order_cnt_type 1 fields for EVERY non-zero type
+     * (h264_parameterset.c:314-331), so a conformant type-2 SPS desynchronises it. */
+    if (p->poc_type != 0) return 0;
 
     enc_t e;
     memset(&e, 0, sizeof e);
