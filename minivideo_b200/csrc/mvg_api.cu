@@ -1,0 +1,593 @@
+/*
+ * mvg_api.cu -- host side of libmvgpu.so: the C ABI of include/mvgpu.h.
+ * Device memory, streams, table upload, kernel launches, pinned-copy pipeline.
+ * There is no CPU fallback anywhere in this file: without a CUDA device every
+ * entry point fails with MVG_FAILURE.
+ */
+#include "mvgpu.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "mvg_internal.h"
+#include "mvg_kernels.cuh"
+
+/* ------------------------------------------------------------------------- */
+
+static char g_create_error[512] = "";
+
+#define MVG_PIPE_DEPTH 3       /* slot regions used by mvg_decode_host */
+#define MVG_WORK_RING  64      /* work counters, one per kernel-2 launch in flight */
+
+struct mvg_ctx {
+    int device = -1, sm_count = 0;
+    int max_w = 0, max_h = 0, max_pics = 0;
+    int w_mbs = 0, h_mbs = 0;
+    bool have_sps = false;
+    char err[512] = "";
+
+    cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_h2d[MVG_PIPE_DEPTH] = {}, ev_comp[MVG_PIPE_DEPTH] = {}, ev_d2h[MVG_PIPE_DEPTH] = {};
+    bool ran_k3 = false;
+    int launches = 0, last_scale = 0;
+
+    /* inputs (SoA), slot-major */
+    uint8_t *d_kind = nullptr, *d_i16 = nullptr, *d_cm = nullptr, *d_cbp = nullptr, *d_modes = nullptr;
+    int8_t *d_qp = nullptr;
+    int16_t *d_coeff = nullptr;
+    /* intermediates / outputs */
+    int16_t *d_resid = nullptr;
+    MvgMbCtl *d_ctl = nullptr;
+    uint8_t *d_yuv = nullptr, *d_rgb = nullptr;
+    int *d_progress = nullptr, *d_work = nullptr;
+    int work_next = 0;
+    MvgTables *d_tab = nullptr;
+    MvgLuts *d_luts = nullptr;
+
+    size_t n_mb_max() const { return (size_t)max_w * max_h; }
+    size_t n_mb() const { return (size_t)w_mbs * h_mbs; }
+};
+
+static int fail(mvg_ctx *ctx, const char *fmt, ...)
+{
+    char *dst = ctx ? ctx->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return MVG_FAILURE;
+}
+
+#define CK(ctx, call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+/* ------------------------------------------------------------------------- */
+/* tables                                                                      */
+
+static void zigzag(int n, uint8_t *zz)      /* zz[k] = row*n + col, spec 8.5.6 / 8.5.7 */
+{
+    int r = 0, c = 0;
+    bool up = true;
+    for (int k = 0; k < n * n; k++) {
+        zz[k] = (uint8_t)(r * n + c);
+        if (up) {
+            if (c == n - 1) { r++; up = false; }
+            else if (r == 0) { c++; up = false; }
+            else { r--; c++; }
+        } else {
+            if (r == n - 1) { c++; up = true; }
+            else if (c == 0) { r++; up = true; }
+            else { r++; c--; }
+        }
+    }
+}
+
+extern "C" int mvg_build_level_scale(const uint8_t *lists4x4, const uint8_t *list8x8,
+                                     int32_t ls4[3 * 6 * 16], int32_t ls8[6 * 64])
+{
+    /* normAdjust: h264.c:428-446, spec 8.5.9 */
+    static const int v4[6][3] = {{10,16,13},{11,18,14},{13,20,16},{14,23,18},{16,25,20},{18,29,23}};
+    static const int v8[6][6] = {{20,18,32,19,25,24},{22,19,35,21,28,26},{26,23,42,24,33,31},
+                                 {28,25,45,26,35,33},{32,28,51,30,40,38},{36,32,58,34,46,43}};
+    if (!ls4 || !ls8) return MVG_FAILURE;
+    uint8_t zz4[16], zz8[64];
+    zigzag(4, zz4); zigzag(8, zz8);
+    for (int c = 0; c < 3; c++) {
+        int m[16];
+        for (int k = 0; k < 16; k++) m[zz4[k]] = lists4x4 ? lists4x4[c * 16 + k] : 16;
+        for (int q = 0; q < 6; q++)
+            for (int i = 0; i < 4; i++)
+                for (int j = 0; j < 4; j++) {
+                    const int cls = (i % 2 == 0 && j % 2 == 0) ? 0 : (i % 2 == 1 && j % 2 == 1) ? 1 : 2;
+                    ls4[(c * 6 + q) * 16 + i * 4 + j] = m[i * 4 + j] * v4[q][cls];
+                }
+    }
+    int m8[64];
+    for (int k = 0; k < 64; k++) m8[zz8[k]] = list8x8 ? list8x8[k] : 16;
+    for (int q = 0; q < 6; q++)
+        for (int i = 0; i < 8; i++)
+            for (int j = 0; j < 8; j++) {
+                int cls;
+                if (i % 4 == 0 && j % 4 == 0) cls = 0;
+                else if (i % 2 == 1 && j % 2 == 1) cls = 1;
+                else if (i % 4 == 2 && j % 4 == 2) cls = 2;
+                else if ((i % 4 == 0 && j % 2 == 1) || (i % 2 == 1 && j % 4 == 0)) cls = 3;
+                else if ((i % 4 == 0 && j % 4 == 2) || (i % 4 == 2 && j % 4 == 0)) cls = 4;
+                else cls = 5;
+                ls8[q * 64 + i * 8 + j] = m8[i * 8 + j] * v8[q][cls];
+            }
+    return MVG_SUCCESS;
+}
+
+/* A neighbour reference of a directional predictor: top row p[i,-1] (i = -1 is the
+ * corner) or left column p[-1,i]. */
+struct Ref { bool left; int i; };
+static Ref T(int i) { return {false, i}; }
+static Ref L(int i) { return i < 0 ? Ref{false, -1} : Ref{true, i}; }
+
+struct Taps { Ref r[4]; };
+static Taps tap3(Ref p, Ref q, Ref r) { return {{p, q, q, r}}; }   /* (p + 2q + r + 2) >> 2 */
+static Taps tap2(Ref p, Ref q) { return {{p, p, q, q}}; }          /* (p + q + 1) >> 1      */
+static Taps tap1(Ref p) { return {{p, p, p, p}}; }                 /* p                     */
+static Taps tapend(Ref p, Ref q) { return {{p, q, q, q}}; }        /* (p + 3q + 2) >> 2     */
+
+/* spec 8.3.1.2.x (n = 4) and 8.3.2.2.x (n = 8); same formulas the reference codes at
+ * h264_intra_prediction.c:496-926 and :1366-1793.  Mode 2 (DC) has no taps. */
+static Taps nxn_taps(int n, int mode, int x, int y)
+{
+    switch (mode) {
+    case 0: return tap1(T(x));
+    case 1: return tap1(L(y));
+    case 3: return (x == n - 1 && y == n - 1) ? tapend(T(2 * n - 2), T(2 * n - 1))
+                                              : tap3(T(x + y), T(x + y + 1), T(x + y + 2));
+    case 4:
+        if (x > y) return tap3(T(x - y - 2), T(x - y - 1), T(x - y));
+        if (x < y) return tap3(L(y - x - 2), L(y - x - 1), L(y - x));
+        return tap3(T(0), T(-1), L(0));
+    case 5: {
+        const int z = 2 * x - y, i = x - (y >> 1);
+        if (z >= 0 && !(z & 1)) return tap2(T(i - 1), T(i));
+        if (z >= 0) return tap3(T(i - 2), T(i - 1), T(i));
+        if (z == -1) return tap3(L(0), T(-1), T(0));
+        return tap3(L(y - 2 * x - 1), L(y - 2 * x - 2), L(y - 2 * x - 3));
+    }
+    case 6: {
+        const int z = 2 * y - x, i = y - (x >> 1);
+        if (z >= 0 && !(z & 1)) return tap2(L(i - 1), L(i));
+        if (z >= 0) return tap3(L(i - 2), L(i - 1), L(i));
+        if (z == -1) return tap3(L(0), T(-1), T(0));
+        return tap3(T(x - 2 * y - 1), T(x - 2 * y - 2), T(x - 2 * y - 3));
+    }
+    case 7: {
+        const int i = x + (y >> 1);
+        return (y & 1) ? tap3(T(i), T(i + 1), T(i + 2)) : tap2(T(i), T(i + 1));
+    }
+    case 8: {
+        const int z = x + 2 * y, i = y + (x >> 1), zmax = 2 * n - 3;
+        if (z > zmax) return tap1(L(n - 1));
+        if (z == zmax) return tapend(L(n - 2), L(n - 1));
+        return (z & 1) ? tap3(L(i), L(i + 1), L(i + 2)) : tap2(L(i), L(i + 1));
+    }
+    default: return tap1(T(0));
+    }
+}
+
+extern "C" void mvg_build_luts(MvgLuts *out)
+{
+    memset(out, 0, sizeof *out);
+    for (int tr = 0; tr < 2; tr++)
+        for (int mode = 0; mode < 9; mode++)
+            for (int y = 0; y < 4; y++)
+                for (int x = 0; x < 4; x++) {
+                    uint32_t word = 0;
+                    if (mode != 2) {
+                        Taps t = nxn_taps(4, mode, x, y);
+                        for (int k = 0; k < 4; k++) {
+                            int off;
+                            if (t.r[k].left) off = t.r[k].i * MVG_LT_STRIDE - 1;
+                            else {
+                                int i = t.r[k].i;
+                                if (!tr && i > 3) i = 3;     /* h264_intra_prediction.c:431-439 */
+                                off = -MVG_LT_STRIDE + i;
+                            }
+                            word |= (uint32_t)(uint8_t)(int8_t)off << (8 * k);
+                        }
+                    }
+                    out->lut4[tr][mode][y * 4 + x] = word;
+                }
+    for (int mode = 0; mode < 9; mode++)
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < 8; x++) {
+                uint32_t word = 0;
+                if (mode == 2) word = MVG_N8_DC * 0x01010101u;
+                else {
+                    Taps t = nxn_taps(8, mode, x, y);
+                    for (int k = 0; k < 4; k++) {
+                        const int idx = t.r[k].left ? MVG_N8_LEFT(t.r[k].i) : MVG_N8_TOP(t.r[k].i);
+                        word |= (uint32_t)idx << (8 * k);
+                    }
+                }
+                out->lut8[mode][y * 8 + x] = word;
+            }
+}
+
+/* ------------------------------------------------------------------------- */
+/* life cycle                                                                  */
+
+extern "C" const char *mvg_last_error(const mvg_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t count) { return cudaMalloc((void **)p, count * sizeof(T)); }
+
+extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mbs, int max_pics)
+{
+    if (!out) return fail(nullptr, "mvg_create: out is NULL");
+    *out = nullptr;
+    if (max_w_mbs < 1 || max_h_mbs < 1 || max_pics < 1) return fail(nullptr, "mvg_create: bad geometry");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, "mvg_create: no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return fail(nullptr, "mvg_create: device %d out of range (0..%d)", device, n_dev - 1);
+
+    mvg_ctx *ctx = new (std::nothrow) mvg_ctx;
+    if (!ctx) return fail(nullptr, "mvg_create: out of host memory");
+    ctx->device = device; ctx->max_w = max_w_mbs; ctx->max_h = max_h_mbs; ctx->max_pics = max_pics;
+
+    auto bail = [&](const char *what, cudaError_t err) {
+        fail(nullptr, "mvg_create: %s: %s", what, cudaGetErrorString(err));
+        mvg_destroy(ctx);
+        return MVG_FAILURE;
+    };
+#define TRY(what, call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) return bail(what, e2); } while (0)
+    TRY("cudaSetDevice", cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TRY("cudaGetDeviceProperties", cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    TRY("stream", cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    TRY("stream", cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    TRY("stream", cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    for (auto &ev : ctx->ev) TRY("event", cudaEventCreate(&ev));
+    for (int i = 0; i < MVG_PIPE_DEPTH; i++) {
+        TRY("event", cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+        TRY("event", cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+        TRY("event", cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+    }
+    const size_t n = ctx->n_mb_max() * (size_t)max_pics;
+    TRY("alloc mb_kind", dalloc(&ctx->d_kind, n));
+    TRY("alloc i16_mode", dalloc(&ctx->d_i16, n));
+    TRY("alloc chroma_mode", dalloc(&ctx->d_cm, n));
+    TRY("alloc qp", dalloc(&ctx->d_qp, n));
+    TRY("alloc cbp", dalloc(&ctx->d_cbp, n));
+    TRY("alloc luma_modes", dalloc(&ctx->d_modes, n * 16));
+    TRY("alloc coeff", dalloc(&ctx->d_coeff, n * 384));
+    TRY("alloc residual", dalloc(&ctx->d_resid, n * 384));
+    TRY("alloc ctl", dalloc(&ctx->d_ctl, n));
+    TRY("alloc yuv", dalloc(&ctx->d_yuv, n * 384));
+    TRY("alloc rgb", dalloc(&ctx->d_rgb, n * 768));
+    TRY("alloc progress", dalloc(&ctx->d_progress, (size_t)max_pics * max_h_mbs));
+    TRY("alloc work", dalloc(&ctx->d_work, MVG_WORK_RING));
+    TRY("alloc tables", dalloc(&ctx->d_tab, 1));
+    TRY("alloc luts", dalloc(&ctx->d_luts, 1));
+    MvgLuts luts;
+    mvg_build_luts(&luts);
+    TRY("upload luts", cudaMemcpy(ctx->d_luts, &luts, sizeof luts, cudaMemcpyHostToDevice));
+#undef TRY
+    *out = ctx;
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_destroy(mvg_ctx *ctx)
+{
+    if (!ctx) return MVG_FAILURE;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_kind); cudaFree(ctx->d_i16); cudaFree(ctx->d_cm); cudaFree(ctx->d_qp); cudaFree(ctx->d_cbp);
+    cudaFree(ctx->d_modes); cudaFree(ctx->d_coeff); cudaFree(ctx->d_resid); cudaFree(ctx->d_ctl);
+    cudaFree(ctx->d_yuv); cudaFree(ctx->d_rgb); cudaFree(ctx->d_progress); cudaFree(ctx->d_work);
+    cudaFree(ctx->d_tab); cudaFree(ctx->d_luts);
+    for (auto ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (int i = 0; i < MVG_PIPE_DEPTH; i++) {
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
+        if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    delete ctx;
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_set_sps(mvg_ctx *ctx, int width_mbs, int height_mbs,
+                           const int32_t level_scale4x4[3 * 6 * 16], const int32_t level_scale8x8[6 * 64],
+                           int cb_qp_offset, int cr_qp_offset)
+{
+    if (!ctx) return MVG_FAILURE;
+    if (!level_scale4x4 || !level_scale8x8) return fail(ctx, "mvg_set_sps: NULL table");
+    if (width_mbs < 1 || height_mbs < 1 || width_mbs > ctx->max_w || height_mbs > ctx->max_h)
+        return fail(ctx, "mvg_set_sps: %dx%d MBs exceeds the context capacity %dx%d",
+                    width_mbs, height_mbs, ctx->max_w, ctx->max_h);
+    CK(ctx, cudaSetDevice(ctx->device));
+    MvgTables t;
+    memset(&t, 0, sizeof t);
+    memcpy(t.ls4, level_scale4x4, sizeof t.ls4);
+    memcpy(t.ls8, level_scale8x8, sizeof t.ls8);
+    uint8_t zz8[64];
+    zigzag(8, zz8);
+    for (int k = 0; k < 64; k++) t.zz8inv[zz8[k]] = (uint8_t)k;
+    t.cb_qp_offset = cb_qp_offset; t.cr_qp_offset = cr_qp_offset;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaMemcpy(ctx->d_tab, &t, sizeof t, cudaMemcpyHostToDevice));
+    ctx->w_mbs = width_mbs; ctx->h_mbs = height_mbs; ctx->have_sps = true;
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_width(const mvg_ctx *ctx) { return ctx ? 16 * ctx->w_mbs : 0; }
+extern "C" int mvg_height(const mvg_ctx *ctx) { return ctx ? 16 * ctx->h_mbs : 0; }
+extern "C" int mvg_max_pics(const mvg_ctx *ctx) { return ctx ? ctx->max_pics : 0; }
+extern "C" int mvg_sm_count(const mvg_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" void *mvg_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void mvg_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+/* ------------------------------------------------------------------------- */
+/* uploads                                                                     */
+
+static int check_ready(mvg_ctx *ctx, int first_slot, int n_pics, const char *who)
+{
+    if (!ctx) return MVG_FAILURE;
+    if (!ctx->have_sps) return fail(ctx, "%s: mvg_set_sps() has not been called", who);
+    if (n_pics < 1 || first_slot < 0 || first_slot + n_pics > ctx->max_pics)
+        return fail(ctx, "%s: slots [%d,%d) outside [0,%d)", who, first_slot, first_slot + n_pics, ctx->max_pics);
+    return MVG_SUCCESS;
+}
+
+static int upload_async(mvg_ctx *ctx, const mvg_batch *b, int src_pic, int first_slot, int n_pics, cudaStream_t st)
+{
+    const size_t n = ctx->n_mb(), o = (size_t)first_slot * n, s = (size_t)src_pic * n, cnt = (size_t)n_pics * n;
+    CK(ctx, cudaMemcpyAsync(ctx->d_kind + o, b->mb_kind + s, cnt, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(ctx->d_i16 + o, b->i16_mode + s, cnt, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(ctx->d_cm + o, b->chroma_mode + s, cnt, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(ctx->d_qp + o, b->qp_y + s, cnt, cudaMemcpyHostToDevice, st));
+    if (b->cbp) CK(ctx, cudaMemcpyAsync(ctx->d_cbp + o, b->cbp + s, cnt, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(ctx->d_modes + o * 16, b->luma_modes + s * 16, cnt * 16, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(ctx->d_coeff + o * 384, b->coeff + s * 384, cnt * 768, cudaMemcpyHostToDevice, st));
+    return MVG_SUCCESS;
+}
+
+static int check_batch(mvg_ctx *ctx, const mvg_batch *b, const char *who)
+{
+    if (!b) return fail(ctx, "%s: batch is NULL", who);
+    if (!b->mb_kind || !b->i16_mode || !b->chroma_mode || !b->qp_y || !b->luma_modes || !b->coeff)
+        return fail(ctx, "%s: a required SoA pointer is NULL", who);
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_upload(mvg_ctx *ctx, const mvg_batch *b, int first_slot)
+{
+    if (!ctx) return MVG_FAILURE;
+    if (check_batch(ctx, b, "mvg_upload") != MVG_SUCCESS) return MVG_FAILURE;
+    if (check_ready(ctx, first_slot, b->n_pics, "mvg_upload") != MVG_SUCCESS) return MVG_FAILURE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (upload_async(ctx, b, 0, first_slot, b->n_pics, ctx->stream) != MVG_SUCCESS) return MVG_FAILURE;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_clone_slot(mvg_ctx *ctx, int src_slot, int dst_slot)
+{
+    if (check_ready(ctx, src_slot, 1, "mvg_clone_slot") != MVG_SUCCESS) return MVG_FAILURE;
+    if (check_ready(ctx, dst_slot, 1, "mvg_clone_slot") != MVG_SUCCESS) return MVG_FAILURE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t n = ctx->n_mb(), s = (size_t)src_slot * n, d = (size_t)dst_slot * n;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(ctx->d_kind + d, ctx->d_kind + s, n, cudaMemcpyDeviceToDevice, st));
+    CK(ctx, cudaMemcpyAsync(ctx->d_i16 + d, ctx->d_i16 + s, n, cudaMemcpyDeviceToDevice, st));
+    CK(ctx, cudaMemcpyAsync(ctx->d_cm + d, ctx->d_cm + s, n, cudaMemcpyDeviceToDevice, st));
+    CK(ctx, cudaMemcpyAsync(ctx->d_qp + d, ctx->d_qp + s, n, cudaMemcpyDeviceToDevice, st));
+    CK(ctx, cudaMemcpyAsync(ctx->d_cbp + d, ctx->d_cbp + s, n, cudaMemcpyDeviceToDevice, st));
+    CK(ctx, cudaMemcpyAsync(ctx->d_modes + d * 16, ctx->d_modes + s * 16, n * 16, cudaMemcpyDeviceToDevice, st));
+    CK(ctx, cudaMemcpyAsync(ctx->d_coeff + d * 384, ctx->d_coeff + s * 384, n * 768, cudaMemcpyDeviceToDevice, st));
+    return MVG_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------- */
+/* launches                                                                    */
+
+static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale, cudaStream_t st, bool timed)
+{
+    const int W = ctx->w_mbs, H = ctx->h_mbs;
+    const size_t n = ctx->n_mb();
+    const int width = 16 * W, height = 16 * H;
+    if (rgb_scale < 0 || (rgb_scale > 0 && (width % rgb_scale || height % rgb_scale)))
+        return fail(ctx, "rgb_scale %d does not divide %dx%d", rgb_scale, width, height);
+
+    int *work = ctx->d_work + ctx->work_next;
+    ctx->work_next = (ctx->work_next + 1) % MVG_WORK_RING;
+    CK(ctx, cudaMemsetAsync(work, 0, sizeof(int), st));
+    CK(ctx, cudaMemsetAsync(ctx->d_progress + (size_t)first_slot * H, 0, (size_t)n_pics * H * sizeof(int), st));
+
+    int launches = 0;
+    if (timed) CK(ctx, cudaEventRecord(ctx->ev[0], st));
+    {
+        K1Params p;
+        const size_t o = (size_t)first_slot * n;
+        p.mb_kind = ctx->d_kind + o; p.i16_mode = ctx->d_i16 + o; p.chroma_mode = ctx->d_cm + o;
+        p.luma_modes = ctx->d_modes + o * 16; p.qp_y = ctx->d_qp + o; p.coeff = ctx->d_coeff + o * 384;
+        p.resid = ctx->d_resid + o * 384; p.ctl = ctx->d_ctl + o; p.tab = ctx->d_tab;
+        p.n_mbs = (long long)n * n_pics;
+        const long long want = (p.n_mbs + K1_WARPS - 1) / K1_WARPS;
+        const int grid = (int)std::min<long long>(want, (long long)ctx->sm_count * 8 * 4);
+        k1_dequant_idct<<<grid, K1_WARPS * 32, 0, st>>>(p);
+        launches++;
+    }
+    if (timed) CK(ctx, cudaEventRecord(ctx->ev[1], st));
+    {
+        K2Params p;
+        p.resid = ctx->d_resid; p.ctl = ctx->d_ctl; p.yuv = ctx->d_yuv; p.progress = ctx->d_progress;
+        p.work = work; p.luts = ctx->d_luts; p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics;
+        const long long items = (long long)n_pics * H;
+        const int grid = (int)std::min<long long>((items + K2_WARPS - 1) / K2_WARPS, (long long)ctx->sm_count * 8);
+        k2_wavefront<<<grid, K2_WARPS * 32, 0, st>>>(p);
+        launches++;
+    }
+    if (timed) CK(ctx, cudaEventRecord(ctx->ev[2], st));
+    if (rgb_scale >= 1) {
+        K3Params p;
+        p.yuv = ctx->d_yuv; p.rgb = ctx->d_rgb; p.width = width; p.height = height; p.scale = rgb_scale;
+        p.first_slot = first_slot; p.n_pics = n_pics;
+        const long long threads = rgb_scale == 1 ? (long long)(width / 16) * height * n_pics
+                                                 : (long long)(width / rgb_scale) * (height / rgb_scale) * n_pics;
+        const int grid = (int)std::min<long long>((threads + 255) / 256, (long long)ctx->sm_count * 32);
+        if (rgb_scale == 1) k3_rgb_full<<<grid, 256, 0, st>>>(p);
+        else k3_rgb_scaled<<<grid, 256, 0, st>>>(p);
+        launches++;
+    }
+    if (timed) {
+        CK(ctx, cudaEventRecord(ctx->ev[3], st));
+        ctx->ran_k3 = rgb_scale >= 1;
+        ctx->launches = launches;
+    }
+    ctx->last_scale = rgb_scale;
+    CK(ctx, cudaGetLastError());
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_run(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale)
+{
+    if (check_ready(ctx, first_slot, n_pics, "mvg_run") != MVG_SUCCESS) return MVG_FAILURE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return launch_stages(ctx, first_slot, n_pics, rgb_scale, ctx->stream, true);
+}
+
+extern "C" int mvg_sync(mvg_ctx *ctx)
+{
+    if (!ctx) return MVG_FAILURE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->s_h2d));
+    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_get_timing(mvg_ctx *ctx, mvg_timing *out)
+{
+    if (!ctx || !out) return MVG_FAILURE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaEventSynchronize(ctx->ev[3]));
+    CK(ctx, cudaEventElapsedTime(&out->k1_dequant_idct_ms, ctx->ev[0], ctx->ev[1]));
+    CK(ctx, cudaEventElapsedTime(&out->k2_wavefront_ms, ctx->ev[1], ctx->ev[2]));
+    out->k3_rgb_ms = 0.f;
+    if (ctx->ran_k3) CK(ctx, cudaEventElapsedTime(&out->k3_rgb_ms, ctx->ev[2], ctx->ev[3]));
+    CK(ctx, cudaEventElapsedTime(&out->total_ms, ctx->ev[0], ctx->ev[3]));
+    out->launches = ctx->launches;
+    return MVG_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------- */
+/* downloads                                                                   */
+
+static size_t rgb_bytes(const mvg_ctx *ctx, int scale)
+{
+    return (size_t)(16 * ctx->w_mbs / scale) * (16 * ctx->h_mbs / scale) * 3;
+}
+
+extern "C" int mvg_download_yuv420(mvg_ctx *ctx, int slot, uint8_t *y, uint8_t *cb, uint8_t *cr)
+{
+    if (check_ready(ctx, slot, 1, "mvg_download_yuv420") != MVG_SUCCESS) return MVG_FAILURE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t n = ctx->n_mb();
+    const uint8_t *src = ctx->d_yuv + (size_t)slot * n * 384;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (y) CK(ctx, cudaMemcpy(y, src, n * 256, cudaMemcpyDeviceToHost));
+    if (cb) CK(ctx, cudaMemcpy(cb, src + n * 256, n * 64, cudaMemcpyDeviceToHost));
+    if (cr) CK(ctx, cudaMemcpy(cr, src + n * 320, n * 64, cudaMemcpyDeviceToHost));
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_download_rgb(mvg_ctx *ctx, int slot, uint8_t *rgb)
+{
+    if (check_ready(ctx, slot, 1, "mvg_download_rgb") != MVG_SUCCESS) return MVG_FAILURE;
+    if (!rgb || ctx->last_scale < 1) return fail(ctx, "mvg_download_rgb: no RGB output (last run had rgb_scale 0)");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t sz = rgb_bytes(ctx, ctx->last_scale);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaMemcpy(rgb, ctx->d_rgb + (size_t)slot * sz, sz, cudaMemcpyDeviceToHost));
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_download_residual(mvg_ctx *ctx, int slot, int16_t *residual)
+{
+    if (check_ready(ctx, slot, 1, "mvg_download_residual") != MVG_SUCCESS) return MVG_FAILURE;
+    if (!residual) return fail(ctx, "mvg_download_residual: NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t n = ctx->n_mb();
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaMemcpy(residual, ctx->d_resid + (size_t)slot * n * 384, n * 768, cudaMemcpyDeviceToHost));
+    return MVG_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------- */
+/* end-to-end: host SoA in, host pictures out, pipelined over slot regions     */
+
+extern "C" int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *b, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale)
+{
+    if (!ctx) return MVG_FAILURE;
+    if (check_batch(ctx, b, "mvg_decode_host") != MVG_SUCCESS) return MVG_FAILURE;
+    if (!ctx->have_sps) return fail(ctx, "mvg_decode_host: mvg_set_sps() has not been called");
+    if (b->n_pics < 1) return fail(ctx, "mvg_decode_host: empty batch");
+    if (rgb_out && rgb_scale < 1) return fail(ctx, "mvg_decode_host: rgb_out given but rgb_scale < 1");
+    CK(ctx, cudaSetDevice(ctx->device));
+
+    const int scale = rgb_out ? rgb_scale : 0;
+    const size_t n = ctx->n_mb();
+    const size_t yuv_sz = n * 384, rgb_sz = scale ? rgb_bytes(ctx, scale) : 0;
+    /* region size: a third of the context, but never more pictures than needed */
+    int depth = MVG_PIPE_DEPTH;
+    int chunk = std::max(1, ctx->max_pics / depth);
+    if (ctx->max_pics < depth) { depth = 1; chunk = ctx->max_pics; }
+    chunk = std::min(chunk, b->n_pics);
+
+    int idx = 0;
+    for (int done = 0; done < b->n_pics; done += chunk, idx++) {
+        const int cnt = std::min(chunk, b->n_pics - done);
+        const int r = idx % depth, slot0 = r * chunk;
+        /* inputs of region r were last read by the compute of chunk idx-depth */
+        if (idx >= depth) CK(ctx, cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[r], 0));
+        if (upload_async(ctx, b, done, slot0, cnt, ctx->s_h2d) != MVG_SUCCESS) return MVG_FAILURE;
+        CK(ctx, cudaEventRecord(ctx->ev_h2d[r], ctx->s_h2d));
+        /* outputs of region r were last read by the D2H of chunk idx-depth */
+        CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[r], 0));
+        if (idx >= depth) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[r], 0));
+        if (launch_stages(ctx, slot0, cnt, scale, ctx->stream, false) != MVG_SUCCESS) return MVG_FAILURE;
+        CK(ctx, cudaEventRecord(ctx->ev_comp[r], ctx->stream));
+        CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[r], 0));
+        if (yuv_out)
+            CK(ctx, cudaMemcpyAsync(yuv_out + (size_t)done * yuv_sz, ctx->d_yuv + (size_t)slot0 * yuv_sz,
+                                    (size_t)cnt * yuv_sz, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (rgb_out)
+            CK(ctx, cudaMemcpyAsync(rgb_out + (size_t)done * rgb_sz, ctx->d_rgb + (size_t)slot0 * rgb_sz,
+                                    (size_t)cnt * rgb_sz, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CK(ctx, cudaEventRecord(ctx->ev_d2h[r], ctx->s_d2h));
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return MVG_SUCCESS;
+}

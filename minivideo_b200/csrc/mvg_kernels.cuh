@@ -1,0 +1,743 @@
+/*
+ * mvg_kernels.cuh -- the three sm_100a kernels of the intra reconstruction path.
+ *
+ *   k1_dequant_idct   dequantisation + 4x4/8x8 inverse integer transforms,
+ *                     Intra16x16 luma-DC Hadamard, chroma-DC 2x2        (HBM-bound)
+ *   k2_wavefront      Intra4x4/8x8/16x16 + chroma prediction, residual add,
+ *                     macroblock-row wavefront batched over pictures    (dependency-bound)
+ *   k3_rgb            fused 4:2:0 -> RGB24 convert (+ box downscale)    (HBM-bound)
+ *
+ * Arithmetic follows the reference bit for bit (citations: minivideo/src/decoder/h264/
+ * in the reference tree, which is not part of this repository):
+ *   h264_transform.c        -> k1 (quant4x4 :1100, idct4x4 :1145, quant8x8 :1256,
+ *                              idct8x8 :1295, lumadc :756, chromadc :827-936)
+ *   h264_intra_prediction.c -> k2 (4x4 :315-926, 8x8 :1107-1793, 16x16 :1809-2141,
+ *                              chroma :2157-2564) + residual add h264_transform.c:152,219,267,393
+ *   export_utils.c:209-324  -> k3
+ * No tensor cores: none of this is a dense contraction.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mvg_internal.h"
+
+#define MVG_FULL 0xffffffffu
+
+/* ------------------------------------------------------------------------- */
+/* constant tables                                                             */
+
+struct MvgTables {
+    int32_t ls4[3][6][16];      /* LevelScale4x4[c][q][i*4+j] */
+    int32_t ls8[6][64];         /* LevelScale8x8[0][q][i*8+j] */
+    uint8_t zz8inv[64];         /* zz8inv[row*8+col] = zig-zag index k of that position */
+    int32_t cb_qp_offset, cr_qp_offset;
+};
+
+__device__ __forceinline__ int mvg_clip8(int v) { return min(max(v, 0), 255); }
+
+/* Table 8-15: QPC as a function of qPI >= 30 (h264_transform.c:71) */
+__constant__ unsigned char mvg_qpc_tab[22] = {29,30,31,32,32,33,34,34,35,35,36,36,37,37,37,38,38,38,39,39,39,39};
+
+/* h264_transform.c:598-637 (8-bit video: QpBdOffsetC = 0) */
+__device__ __forceinline__ int mvg_chroma_qp(int qp_y, int offset)
+{
+    const int qpi = min(max(qp_y + offset, 0), 51);
+    return qpi < 30 ? qpi : (int)mvg_qpc_tab[qpi - 30];
+}
+
+/* ========================================================================= */
+/* Kernel 1                                                                    */
+
+struct K1Params {
+    const uint8_t *mb_kind, *i16_mode, *chroma_mode, *luma_modes;
+    const int8_t  *qp_y;
+    const int16_t *coeff;       /* [n_mbs][384] */
+    int16_t       *resid;       /* [n_mbs][384] */
+    MvgMbCtl      *ctl;         /* [n_mbs]      */
+    const MvgTables *tab;
+    long long      n_mbs;
+};
+
+/* spec 8.5.12.2 / h264_transform.c:1145-1191, one 4-point butterfly */
+__device__ __forceinline__ void mvg_bfly4(int a, int b, int c, int d, int &o0, int &o1, int &o2, int &o3)
+{
+    int e0 = a + c, e1 = a - c, e2 = (b >> 1) - d, e3 = b + (d >> 1);
+    o0 = e0 + e3; o1 = e1 + e2; o2 = e1 - e2; o3 = e0 - e3;
+}
+
+/* spec 8.5.13.2 / h264_transform.c:1308-1378, one 8-point pass */
+__device__ __forceinline__ void mvg_idct8_1d(int (&v)[8])
+{
+    int a0 = v[0] + v[4];
+    int a1 = -v[3] + v[5] - v[7] - (v[7] >> 1);
+    int a2 = v[0] - v[4];
+    int a3 = v[1] + v[7] - v[3] - (v[3] >> 1);
+    int a4 = (v[2] >> 1) - v[6];
+    int a5 = -v[1] + v[7] + v[5] + (v[5] >> 1);
+    int a6 = v[2] + (v[6] >> 1);
+    int a7 = v[3] + v[5] + v[1] + (v[1] >> 1);
+    int b0 = a0 + a6, b1 = a1 + (a7 >> 2), b2 = a2 + a4, b3 = a3 + (a5 >> 2);
+    int b4 = a2 - a4, b5 = (a3 >> 2) - a5, b6 = a0 - a6, b7 = a7 - (a1 >> 2);
+    v[0] = b0 + b7; v[1] = b2 + b5; v[2] = b4 + b3; v[3] = b6 + b1;
+    v[4] = b6 - b1; v[5] = b4 - b3; v[6] = b2 - b5; v[7] = b0 - b7;
+}
+
+__device__ __forceinline__ int mvg_sat16(int v) { return min(max(v, -32768), 32767); }
+
+#define K1_WARPS 8
+
+/* One warp per macroblock.
+ *  4x4 path (Intra4x4 / Intra16x16 luma, all chroma): lane b < 24 owns 4x4 block b
+ *    (0..15 luma in decoding order, 16..19 Cb, 20..23 Cr): two 128-bit loads bring
+ *    its 16 levels, the zig-zag inverse is a compile-time register renaming, both
+ *    butterfly passes stay in registers.  The Intra16x16 DC Hadamard and the chroma
+ *    DC 2x2 are done across lanes with shuffles.
+ *  8x8 path (Intra8x8 luma): 8 lanes per block, one matrix row per lane, transposed
+ *    through shared memory between the row and the column pass.
+ *  The int16 residual is staged in shared memory in raster order and leaves with
+ *    coalesced 128-bit stores. */
+__global__ void __launch_bounds__(K1_WARPS * 32)
+k1_dequant_idct(K1Params p)
+{
+    __shared__ int32_t s_ls4[3 * 6 * 16];
+    __shared__ int32_t s_ls8[6 * 64];
+    __shared__ uint8_t s_zz8inv[64];
+    __shared__ __align__(16) int16_t s_in[K1_WARPS][256];      /* luma levels of an Intra8x8 MB */
+    __shared__ int32_t s_tr[K1_WARPS][4][8][9];                 /* 8x8 transpose, padded          */
+    __shared__ __align__(16) int16_t s_out[K1_WARPS][384];     /* residual, raster                */
+
+    for (int i = threadIdx.x; i < 3 * 6 * 16; i += blockDim.x) s_ls4[i] = (&p.tab->ls4[0][0][0])[i];
+    for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) s_ls8[i] = (&p.tab->ls8[0][0])[i];
+    if (threadIdx.x < 64) s_zz8inv[threadIdx.x] = p.tab->zz8inv[threadIdx.x];
+    const int cb_off = p.tab->cb_qp_offset, cr_off = p.tab->cr_qp_offset;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long n_warps = (long long)gridDim.x * K1_WARPS;
+
+    for (long long mb = (long long)blockIdx.x * K1_WARPS + w; mb < p.n_mbs; mb += n_warps) {
+        const int kind = p.mb_kind[mb];
+        const int qp = p.qp_y[mb];
+        const int16_t *cf = p.coeff + mb * 384;
+        int16_t *out = s_out[w];
+
+        /* ---------------- 4x4 blocks ---------------- */
+        const bool luma4 = (kind != MVG_MB_I8x8);
+        const bool is_chroma = lane >= 16;
+        const bool active = lane < 24 && (is_chroma || luma4);
+        int c[16];                              /* matrix, row-major, after inverse zig-zag */
+#pragma unroll
+        for (int k = 0; k < 16; k++) c[k] = 0;
+        if (active) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(cf + lane * 16);
+            uint4 a = __ldg(src), b = __ldg(src + 1);
+            int v[16];
+            v[0] = (short)(a.x & 0xffff); v[1] = (int)a.x >> 16; v[2] = (short)(a.y & 0xffff); v[3] = (int)a.y >> 16;
+            v[4] = (short)(a.z & 0xffff); v[5] = (int)a.z >> 16; v[6] = (short)(a.w & 0xffff); v[7] = (int)a.w >> 16;
+            v[8] = (short)(b.x & 0xffff); v[9] = (int)b.x >> 16; v[10] = (short)(b.y & 0xffff); v[11] = (int)b.y >> 16;
+            v[12] = (short)(b.z & 0xffff); v[13] = (int)b.z >> 16; v[14] = (short)(b.w & 0xffff); v[15] = (int)b.w >> 16;
+            /* zig-zag k -> (row,col): utils.h:64 / spec Table 8-13 */
+            c[0] = v[0];  c[1] = v[1];  c[4] = v[2];  c[8] = v[3];
+            c[5] = v[4];  c[2] = v[5];  c[3] = v[6];  c[6] = v[7];
+            c[9] = v[8];  c[12] = v[9]; c[13] = v[10]; c[10] = v[11];
+            c[7] = v[12]; c[11] = v[13]; c[14] = v[14]; c[15] = v[15];
+        }
+
+        /* component and quantiser of this lane's block */
+        const int comp = lane < 16 ? 0 : (lane < 20 ? 1 : 2);
+        int qpb = qp;
+        if (comp) qpb = mvg_chroma_qp(qp, comp == 1 ? cb_off : cr_off);
+        const int qm = qpb % 6, qd = qpb / 6;
+        const int32_t *ls = s_ls4 + (comp * 6 + qm) * 16;
+        const int ls00 = ls[0];
+        bool keep_dc = is_chroma;
+
+        /* Intra16x16 luma DC: f = H c H over the 16 lanes (h264_transform.c:783-808) */
+        if (kind == MVG_MB_I16x16) {            /* warp-uniform */
+            /* lane b sits at matrix position (i,j): i = by, j = bx */
+            const int bi = ((lane >> 1) & 1) | ((lane >> 3) << 1);
+            const int bj = (lane & 1) | (((lane >> 2) & 1) << 1);
+            /* rows of H (h264_transform.c:62-68) as sign masks over k */
+            const unsigned hs_i = (0xA6C0u >> (4 * bi)) & 0xF;   /* row0 0000,row1 1100,row2 0110,row3 1010 */
+            const unsigned hs_j = (0xA6C0u >> (4 * bj)) & 0xF;
+            int f = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int l = 0; l < 4; l++) {
+                    const int src = (l & 1) | ((k & 1) << 1) | ((l >> 1) << 2) | ((k >> 1) << 3);
+                    int v = __shfl_sync(MVG_FULL, c[0], src);
+                    const unsigned neg = ((hs_i >> k) ^ (hs_j >> l)) & 1u;
+                    f += neg ? -v : v;
+                }
+            int t = f * ls00;
+            int dcy = (qp >= 36) ? (int)((unsigned)t << (qd - 6)) : ((t + (1 << (5 - qd))) >> (6 - qd));
+            if (lane < 16) { c[0] = dcy; keep_dc = true; }
+        }
+        /* chroma DC 2x2 (h264_transform.c:988-1005, :924-936) over lane groups 16..19, 20..23 */
+        {
+            const int base = lane & ~3, r = (lane >> 1) & 1, cc = lane & 1;
+            int f = 0;
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                int v = __shfl_sync(MVG_FULL, c[0], base + s);
+                const int neg = (r & (s >> 1)) ^ (cc & (s & 1));
+                f += neg ? -v : v;
+            }
+            if (is_chroma && lane < 24) c[0] = (int)((unsigned)(f * ls00) << qd) >> 5;
+        }
+
+        if (active) {
+            /* quant4x4, h264_transform.c:1100-1134 */
+            const int dc_in = c[0];
+            if (qpb > 23) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) c[k] = (int)((unsigned)(c[k] * ls[k]) << (qd - 4));
+            } else {
+                const int rnd = 1 << (3 - qd), sh = 4 - qd;
+#pragma unroll
+                for (int k = 0; k < 16; k++) c[k] = (c[k] * ls[k] + rnd) >> sh;
+            }
+            if (keep_dc) c[0] = dc_in;
+            /* idct4x4: rows then columns */
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                mvg_bfly4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3], c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                mvg_bfly4(c[j], c[4 + j], c[8 + j], c[12 + j], c[j], c[4 + j], c[8 + j], c[12 + j]);
+            /* (h + 32) >> 6, saturate to int16, store raster */
+            int16_t *dst;
+            int stride;
+            if (lane < 16) {
+                const int bx = (lane & 1) | (((lane >> 2) & 1) << 1), by = ((lane >> 1) & 1) | ((lane >> 3) << 1);
+                dst = out + (by * 4) * 16 + bx * 4; stride = 16;
+            } else {
+                const int b = lane & 3, pl = (lane - 16) >> 2;
+                dst = out + 256 + pl * 64 + ((b >> 1) * 4) * 8 + (b & 1) * 4; stride = 8;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int r0 = mvg_sat16((c[4 * i] + 32) >> 6), r1 = mvg_sat16((c[4 * i + 1] + 32) >> 6);
+                int r2 = mvg_sat16((c[4 * i + 2] + 32) >> 6), r3 = mvg_sat16((c[4 * i + 3] + 32) >> 6);
+                uint2 pk;
+                pk.x = (unsigned)(r0 & 0xffff) | ((unsigned)r1 << 16);
+                pk.y = (unsigned)(r2 & 0xffff) | ((unsigned)r3 << 16);
+                *reinterpret_cast<uint2 *>(dst + i * stride) = pk;
+            }
+        }
+
+        /* ---------------- Intra8x8 luma ---------------- */
+        if (kind == MVG_MB_I8x8) {              /* warp-uniform */
+            reinterpret_cast<uint4 *>(s_in[w])[lane] = __ldg(reinterpret_cast<const uint4 *>(cf) + lane);
+            __syncwarp();
+            const int b8 = lane >> 3, row = lane & 7;
+            const int qm8 = qp % 6, qd8 = qp / 6;
+            const int32_t *l8 = s_ls8 + qm8 * 64 + row * 8;
+            int v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int lvl = s_in[w][b8 * 64 + s_zz8inv[row * 8 + j]];
+                int t = lvl * l8[j];                      /* quant8x8, h264_transform.c:1256-1284 */
+                v[j] = (qp > 35) ? (int)((unsigned)t << (qd8 - 6)) : ((t + (1 << (5 - qd8))) >> (6 - qd8));
+            }
+            mvg_idct8_1d(v);                              /* row pass */
+#pragma unroll
+            for (int j = 0; j < 8; j++) s_tr[w][b8][row][j] = v[j];
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = s_tr[w][b8][i][row];   /* this lane now owns column `row` */
+            mvg_idct8_1d(v);                              /* column pass */
+            const int xo = (b8 & 1) * 8 + row, yo = (b8 >> 1) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; i++) out[(yo + i) * 16 + xo] = (int16_t)mvg_sat16((v[i] + 32) >> 6);
+        }
+        __syncwarp();
+
+        /* ---------------- write residual + control record ---------------- */
+        uint4 *gout = reinterpret_cast<uint4 *>(p.resid + mb * 384);
+        const uint4 *sout = reinterpret_cast<const uint4 *>(out);
+        uint4 q0 = sout[lane];
+        uint4 q1 = make_uint4(0, 0, 0, 0);
+        if (lane < 16) q1 = sout[32 + lane];
+        gout[lane] = q0;
+        if (lane < 16) gout[32 + lane] = q1;
+
+        /* non-zero map: 8 shorts per uint4; lane's q0 covers luma row lane>>1, cols 8*(lane&1).. */
+        unsigned nz_lo = (q0.x | q0.y) != 0, nz_hi = (q0.z | q0.w) != 0;     /* two 4-sample groups */
+        /* luma 4x4 block of (row y, col group g): bx = g, by = y>>2 */
+        unsigned mask = 0;
+        {
+            const int y = lane >> 1, g0 = (lane & 1) * 2;
+            const int by = y >> 2;
+            const int b_lo = (g0 & 1) | ((by & 1) << 1) | ((g0 >> 1) << 2) | ((by >> 1) << 3);
+            const int g1 = g0 + 1;
+            const int b_hi = (g1 & 1) | ((by & 1) << 1) | ((g1 >> 1) << 2) | ((by >> 1) << 3);
+            mask |= nz_lo << b_lo;
+            mask |= nz_hi << b_hi;
+        }
+        if (lane < 16) {     /* chroma: q1 covers plane lane>>3, row lane&7, 8 samples = blocks (y>>2)*2 + {0,1} */
+            const int pl = lane >> 3, y = lane & 7;
+            unsigned c_lo = (q1.x | q1.y) != 0, c_hi = (q1.z | q1.w) != 0;
+            mask |= c_lo << (16 + pl * 4 + (y >> 2) * 2);
+            mask |= c_hi << (16 + pl * 4 + (y >> 2) * 2 + 1);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) mask |= __shfl_xor_sync(MVG_FULL, mask, s);
+
+        if (lane == 0) {
+            const uint4 m = __ldg(reinterpret_cast<const uint4 *>(p.luma_modes + mb * 16));
+            MvgMbCtl ctl;
+            ctl.w0 = (unsigned)kind | ((unsigned)p.i16_mode[mb] << 8) | ((unsigned)p.chroma_mode[mb] << 16);
+            /* pack 4 mode bytes -> 4 nibbles */
+            auto pack = [](unsigned x) {
+                return (x & 0xF) | ((x >> 4) & 0xF0) | ((x >> 8) & 0xF00) | ((x >> 12) & 0xF000);
+            };
+            ctl.w1 = pack(m.x) | (pack(m.y) << 16);
+            ctl.w2 = pack(m.z) | (pack(m.w) << 16);
+            ctl.w3 = mask;
+            *reinterpret_cast<uint4 *>(p.ctl + mb) = make_uint4(ctl.w0, ctl.w1, ctl.w2, ctl.w3);
+        }
+        __syncwarp();
+    }
+}
+
+/* ========================================================================= */
+/* Kernel 2                                                                    */
+
+struct K2Params {
+    const int16_t  *resid;      /* [slot][n_mb][384]                         */
+    const MvgMbCtl *ctl;        /* [slot][n_mb]                              */
+    uint8_t        *yuv;        /* [slot][1.5*W*H] planar I420               */
+    int            *progress;   /* [slot][h_mbs]: MBs finished in that row   */
+    int            *work;       /* work counter of this launch (starts at 0) */
+    const MvgLuts  *luts;
+    int w_mbs, h_mbs, first_slot, n_pics;
+};
+
+#define K2_WARPS 4
+
+struct K2WarpSmem {
+    __align__(16) int16_t  resid[384];
+    __align__(16) uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
+    __align__(16) uint8_t  ct[2][MVG_CT_ROWS * MVG_CT_STRIDE];
+    __align__(16) uint8_t  n8[32];
+};
+
+__device__ __forceinline__ int mvg_ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+/* byte sum of a 32-bit word */
+__device__ __forceinline__ int mvg_sum4(unsigned w) { return (int)__dp4a(w, 0x01010101u, 0u); }
+
+/* ---- Intra16x16 luma (h264_intra_prediction.c:1945-2141) ------------------- */
+__device__ __forceinline__ void k2_luma16(K2WarpSmem &s, int lane, int mode, bool left, bool up)
+{
+    uint8_t *lt = s.lt;
+    const int y = lane >> 1, x0 = (lane & 1) * 8;
+    int pred[8];
+    if (mode == 0) {            /* Vertical */
+        const uint2 t = *reinterpret_cast<const uint2 *>(lt + MVG_LT_XOFF + x0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { pred[i] = (t.x >> (8 * i)) & 255; pred[4 + i] = (t.y >> (8 * i)) & 255; }
+    } else if (mode == 1) {     /* Horizontal */
+        const int v = lt[(y + 1) * MVG_LT_STRIDE + MVG_LT_XOFF - 1];
+#pragma unroll
+        for (int i = 0; i < 8; i++) pred[i] = v;
+    } else if (mode == 2) {     /* DC */
+        int v = 0;
+        if (lane < 16) {
+            if (up) v += lt[MVG_LT_XOFF + lane];
+            if (left) v += lt[(lane + 1) * MVG_LT_STRIDE + MVG_LT_XOFF - 1];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MVG_FULL, v, o);
+        v = (left && up) ? (v + 16) >> 5 : (left || up) ? (v + 8) >> 4 : 128;
+#pragma unroll
+        for (int i = 0; i < 8; i++) pred[i] = v;
+    } else {                    /* Plane */
+        int term = 0;
+        const int i = lane & 7;
+        if (lane < 8)       term = (i + 1) * ((int)lt[MVG_LT_XOFF + 8 + i] - (int)lt[MVG_LT_XOFF + 6 - i]);
+        else if (lane < 16) term = (i + 1) * ((int)lt[(9 + i) * MVG_LT_STRIDE + MVG_LT_XOFF - 1] -
+                                              (int)lt[(7 - i) * MVG_LT_STRIDE + MVG_LT_XOFF - 1]);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) term += __shfl_xor_sync(MVG_FULL, term, o);
+        const int H = __shfl_sync(MVG_FULL, term, 0), V = __shfl_sync(MVG_FULL, term, 8);
+        const int a = 16 * ((int)lt[16 * MVG_LT_STRIDE + MVG_LT_XOFF - 1] + (int)lt[MVG_LT_XOFF + 15]);
+        const int b = (5 * H + 32) >> 6, c = (5 * V + 32) >> 6;
+        const int base = a + c * (y - 7) + 16;
+#pragma unroll
+        for (int k = 0; k < 8; k++) pred[k] = mvg_clip8((base + b * (x0 + k - 7)) >> 5);
+    }
+    const uint4 r = *reinterpret_cast<const uint4 *>(s.resid + y * 16 + x0);
+    const unsigned rr[4] = {r.x, r.y, r.z, r.w};
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int r0 = (short)(rr[k] & 0xffff), r1 = (int)rr[k] >> 16;
+        const unsigned p0 = (unsigned)mvg_clip8(pred[2 * k] + r0), p1 = (unsigned)mvg_clip8(pred[2 * k + 1] + r1);
+        const unsigned pk = p0 | (p1 << 8);
+        if (k < 2) lo |= pk << (16 * k); else hi |= pk << (16 * (k - 2));
+    }
+    __syncwarp();               /* every lane has read its neighbours */
+    *reinterpret_cast<uint2 *>(lt + (y + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + x0) = make_uint2(lo, hi);
+}
+
+/* ---- Intra4x4 luma: anti-diagonal schedule, two blocks per step ------------- */
+__device__ __forceinline__ void k2_luma4(K2WarpSmem &s, const uint32_t *lut4, int lane,
+                                         unsigned long long modes, bool availA, bool availB, bool availC)
+{
+    uint8_t *lt = s.lt;
+    const int half = lane >> 4, px = lane & 3, py = (lane >> 2) & 3;
+#pragma unroll 1
+    for (int t = 0; t < 10; t++) {
+        /* blocks with bx + 2*by == t: (t&1, t>>1) and ((t&1)+2, (t>>1)-1) */
+        const int bx = (t & 1) + 2 * half, by = (t >> 1) - half;
+        const bool valid = by >= 0 && by <= 3;
+        if (valid) {
+            const int blk = (bx & 1) | ((by & 1) << 1) | ((bx >> 1) << 2) | ((by >> 1) << 3);
+            const int mode = (int)((modes >> (4 * blk)) & 15);
+            const bool left = bx > 0 || availA, up = by > 0 || availB;
+            /* p[4..7,-1]: h264_intra_prediction.c:398-429 + h264_spatial.c:757-774 */
+            bool tr;
+            if (blk == 3 || blk == 11) tr = false;
+            else if (by > 0) tr = bx < 3;
+            else tr = bx < 3 ? availB : availC;
+            const int org = (by * 4 + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + bx * 4;
+            int pred;
+            if (mode == 2) {
+                int sum = 0;
+                if (up) sum += mvg_sum4(*reinterpret_cast<const unsigned *>(lt + org - MVG_LT_STRIDE));
+                if (left) sum += (int)lt[org - 1] + (int)lt[org + MVG_LT_STRIDE - 1] +
+                                 (int)lt[org + 2 * MVG_LT_STRIDE - 1] + (int)lt[org + 3 * MVG_LT_STRIDE - 1];
+                pred = (left && up) ? (sum + 4) >> 3 : (left || up) ? (sum + 2) >> 2 : 128;
+            } else {
+                const uint32_t taps = lut4[((tr ? 1 : 0) * 9 + mode) * 16 + py * 4 + px];
+                const int o0 = (int)(signed char)(taps & 255), o1 = (int)(signed char)((taps >> 8) & 255);
+                const int o2 = (int)(signed char)((taps >> 16) & 255), o3 = (int)(signed char)(taps >> 24);
+                pred = ((int)lt[org + o0] + (int)lt[org + o1] + (int)lt[org + o2] + (int)lt[org + o3] + 2) >> 2;
+            }
+            const int r = s.resid[(by * 4 + py) * 16 + bx * 4 + px];
+            lt[org + py * MVG_LT_STRIDE + px] = (uint8_t)mvg_clip8(pred + r);
+        }
+        __syncwarp();
+    }
+}
+
+/* ---- Intra8x8 luma: 4 blocks in order, reference sample filter + taps -------- */
+__device__ __forceinline__ void k2_luma8(K2WarpSmem &s, const uint32_t *lut8, int lane,
+                                         unsigned long long modes, bool availA, bool availB, bool availC, bool availD)
+{
+    uint8_t *lt = s.lt;
+#pragma unroll 1
+    for (int b8 = 0; b8 < 4; b8++) {
+        const int xo = (b8 & 1) * 8, yo = (b8 >> 1) * 8;
+        const int mode = (int)((modes >> (4 * b8)) & 15);
+        const bool left = xo > 0 || availA, up = yo > 0 || availB;
+        const bool upleft = b8 == 0 ? availD : (b8 == 1 ? availB : (b8 == 2 ? availA : true));
+        const bool tr = b8 == 0 ? availB : (b8 == 1 ? availC : (b8 == 2));
+        const int org = (yo + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + xo;
+
+        /* neighbour line: n = 0..7 left[7..0], 8 corner, 9..24 top[0..15] */
+        int raw = 0;
+        if (lane < 8)        raw = lt[org + (7 - lane) * MVG_LT_STRIDE - 1];
+        else if (lane == 8)  raw = lt[org - MVG_LT_STRIDE - 1];
+        else if (lane < 25) {
+            int i = lane - 9;
+            if (i > 7 && !tr) i = 7;             /* h264_intra_prediction.c:1230-1236 */
+            raw = lt[org - MVG_LT_STRIDE + i];
+        }
+        int prev = __shfl_up_sync(MVG_FULL, raw, 1), next = __shfl_down_sync(MVG_FULL, raw, 1);
+        /* h264_intra_prediction.c:1295-1353 */
+        if (lane == 0) prev = raw;                              /* p'[-1,7] = (p[-1,6] + 3 p[-1,7] + 2) >> 2 */
+        if (lane == 24) next = raw;                             /* p'[15,-1] */
+        if (lane == 7 && !upleft) next = raw;                   /* p'[-1,0] without corner */
+        if (lane == 9 && !upleft) prev = raw;                   /* p'[0,-1] without corner */
+        if (lane == 8) { if (!left) prev = raw; if (!up) next = raw; }
+        const int filt = (prev + 2 * raw + next + 2) >> 2;
+        if (lane < 25) s.n8[lane] = (uint8_t)filt;
+        if (mode == 2) {                                        /* warp-uniform */
+            int v = 0;
+            if (lane < 8 && left) v = filt;
+            if (lane >= 9 && lane < 17 && up) v = filt;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MVG_FULL, v, o);
+            v = (left && up) ? (v + 8) >> 4 : (left || up) ? (v + 4) >> 3 : 128;
+            if (lane == 0) s.n8[MVG_N8_DC] = (uint8_t)v;
+        }
+        __syncwarp();
+        const int px = lane & 7, py = lane >> 3;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int y = py + 4 * h;
+            const uint32_t taps = lut8[mode * 64 + y * 8 + px];
+            const int pred = ((int)s.n8[taps & 255] + (int)s.n8[(taps >> 8) & 255] +
+                              (int)s.n8[(taps >> 16) & 255] + (int)s.n8[taps >> 24] + 2) >> 2;
+            const int r = s.resid[(yo + y) * 16 + xo + px];
+            lt[org + y * MVG_LT_STRIDE + px] = (uint8_t)mvg_clip8(pred + r);
+        }
+        __syncwarp();
+    }
+}
+
+/* ---- chroma, both planes at once (h264_intra_prediction.c:2338-2564) --------- */
+__device__ __forceinline__ void k2_chroma(K2WarpSmem &s, int lane, int mode, bool left, bool up)
+{
+    const int pl = lane >> 4, y = (lane & 15) >> 1, x0 = (lane & 1) * 4;
+    uint8_t *ct = s.ct[pl];
+    const int top = MVG_CT_XOFF, lcol = MVG_CT_XOFF - 1;
+    int pred[4];
+    if (mode == 0) {            /* DC, per 4x4 block */
+        const int yo = y & 4;
+        int st = 0, sl = 0;
+        if (up) st = mvg_sum4(*reinterpret_cast<const unsigned *>(ct + top + x0));
+        if (left) sl = (int)ct[(yo + 1) * MVG_CT_STRIDE + lcol] + (int)ct[(yo + 2) * MVG_CT_STRIDE + lcol] +
+                       (int)ct[(yo + 3) * MVG_CT_STRIDE + lcol] + (int)ct[(yo + 4) * MVG_CT_STRIDE + lcol];
+        int v;
+        if (!left && !up) v = 128;
+        else if ((x0 == 0) == (yo == 0))       /* blocks (0,0) and (4,4) */
+            v = (left && up) ? (st + sl + 4) >> 3 : left ? (sl + 2) >> 2 : (st + 2) >> 2;
+        else if (x0 > 0) v = up ? (st + 2) >> 2 : (sl + 2) >> 2;          /* (4,0): top first  */
+        else v = left ? (sl + 2) >> 2 : (st + 2) >> 2;                    /* (0,4): left first */
+        pred[0] = pred[1] = pred[2] = pred[3] = v;
+    } else if (mode == 1) {     /* Horizontal */
+        const int v = ct[(y + 1) * MVG_CT_STRIDE + lcol];
+        pred[0] = pred[1] = pred[2] = pred[3] = v;
+    } else if (mode == 2) {     /* Vertical */
+        const unsigned t = *reinterpret_cast<const unsigned *>(ct + top + x0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) pred[i] = (t >> (8 * i)) & 255;
+    } else {                    /* Plane */
+        int H = 0, V = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            H += (i + 1) * ((int)ct[top + 4 + i] - (int)ct[top + 2 - i]);
+            V += (i + 1) * ((int)ct[(5 + i) * MVG_CT_STRIDE + lcol] - (int)ct[(3 - i) * MVG_CT_STRIDE + lcol]);
+        }
+        const int a = 16 * ((int)ct[8 * MVG_CT_STRIDE + lcol] + (int)ct[top + 7]);
+        const int b = (34 * H + 32) >> 6, c = (34 * V + 32) >> 6;
+        const int base = a + c * (y - 3) + 16;
+#pragma unroll
+        for (int k = 0; k < 4; k++) pred[k] = mvg_clip8((base + b * (x0 + k - 3)) >> 5);
+    }
+    const uint2 r = *reinterpret_cast<const uint2 *>(s.resid + 256 + pl * 64 + y * 8 + x0);
+    const unsigned p0 = (unsigned)mvg_clip8(pred[0] + (short)(r.x & 0xffff));
+    const unsigned p1 = (unsigned)mvg_clip8(pred[1] + ((int)r.x >> 16));
+    const unsigned p2 = (unsigned)mvg_clip8(pred[2] + (short)(r.y & 0xffff));
+    const unsigned p3 = (unsigned)mvg_clip8(pred[3] + ((int)r.y >> 16));
+    __syncwarp();
+    *reinterpret_cast<unsigned *>(ct + (y + 1) * MVG_CT_STRIDE + MVG_CT_XOFF + x0) = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+}
+
+/* Persistent warps; each warp claims (picture, macroblock row) items in order from
+ * an atomic counter and walks the row left to right.  Row r may process macroblock
+ * x once row r-1 has finished macroblock x+1 (its up-right neighbour C,
+ * h264_spatial.c:371-382): progress[] carries that count with release/acquire.
+ * Because items are claimed in order, the row a warp waits for was always claimed
+ * earlier by a warp that is already running, so the wait cannot deadlock. */
+__global__ void __launch_bounds__(K2_WARPS * 32, 8)
+k2_wavefront(K2Params p)
+{
+    __shared__ uint32_t s_lut4[2 * 9 * 16];
+    __shared__ uint32_t s_lut8[9 * 64];
+    __shared__ K2WarpSmem s_warp[K2_WARPS];
+
+    for (int i = threadIdx.x; i < 2 * 9 * 16; i += blockDim.x) s_lut4[i] = (&p.luts->lut4[0][0][0])[i];
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) s_lut8[i] = (&p.luts->lut8[0][0])[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    K2WarpSmem &s = s_warp[threadIdx.x >> 5];
+    const int W = p.w_mbs, H = p.h_mbs, n_mb = W * H;
+    const int ystride = W * 16, cstride = W * 8;
+    const size_t pic_bytes = (size_t)n_mb * 384;
+    const int total = p.n_pics * H;
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(p.work, 1);
+        item = __shfl_sync(MVG_FULL, item, 0);
+        if (item >= total) break;
+        const int slot = p.first_slot + item / H, row = item % H;
+        uint8_t *ybase = p.yuv + (size_t)slot * pic_bytes;
+        uint8_t *cbbase = ybase + (size_t)n_mb * 256, *crbase = cbbase + (size_t)n_mb * 64;
+        const int16_t *resid = p.resid + ((size_t)slot * n_mb + (size_t)row * W) * 384;
+        const MvgMbCtl *ctl = p.ctl + (size_t)slot * n_mb + (size_t)row * W;
+        const int *above = p.progress + (size_t)slot * H + row - 1;
+        int *mine = p.progress + (size_t)slot * H + row;
+        const bool availB = row > 0;
+
+        /* prefetch the first macroblock's inputs */
+        uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(resid) + lane);
+        uint4 r1 = make_uint4(0, 0, 0, 0);
+        if (lane < 16) r1 = __ldg(reinterpret_cast<const uint4 *>(resid) + 32 + lane);
+        uint4 c4 = __ldg(reinterpret_cast<const uint4 *>(ctl));
+        int seen = 0;
+
+        for (int mx = 0; mx < W; mx++) {
+            reinterpret_cast<uint4 *>(s.resid)[lane] = r0;
+            if (lane < 16) reinterpret_cast<uint4 *>(s.resid)[32 + lane] = r1;
+            const uint4 cur = c4;
+            if (mx + 1 < W) {       /* software pipeline: next macroblock's loads fly during this one */
+                const uint4 *nr = reinterpret_cast<const uint4 *>(resid + (size_t)(mx + 1) * 384);
+                r0 = __ldg(nr + lane);
+                if (lane < 16) r1 = __ldg(nr + 32 + lane);
+                c4 = __ldg(reinterpret_cast<const uint4 *>(ctl + mx + 1));
+            }
+            const bool availA = mx > 0, availC = availB && mx < W - 1, availD = availA && availB;
+
+            if (availB) {
+                const int need = min(mx + 2, W);
+                while (seen < need) {
+                    seen = mvg_ld_acquire(above);
+                    if (seen < need) __nanosleep(100);
+                }
+                /* row -1 of the tiles: samples written by the warp that owns row-1 */
+                const uint8_t *ytop = ybase + (size_t)(row * 16 - 1) * ystride + mx * 16;
+                if (lane < 25) {
+                    const int x = lane - 1;
+                    if ((x >= 0 || availA) && (x < 16 || availC))
+                        s.lt[MVG_LT_XOFF + x] = __ldcg(ytop + x);
+                }
+                const int cl = lane & 15;
+                if (cl < 9) {
+                    const int x = cl - 1;
+                    const uint8_t *ctop = (lane < 16 ? cbbase : crbase) + (size_t)(row * 8 - 1) * cstride + mx * 8;
+                    if (x >= 0 || availA) s.ct[lane >> 4][MVG_CT_XOFF + x] = __ldcg(ctop + x);
+                }
+            }
+            __syncwarp();
+
+            const int kind = cur.x & 255, i16 = (cur.x >> 8) & 255, cmode = (cur.x >> 16) & 255;
+            const unsigned long long modes = (unsigned long long)cur.y | ((unsigned long long)cur.z << 32);
+            if (kind == MVG_MB_I16x16)    k2_luma16(s, lane, i16, availA, availB);
+            else if (kind == MVG_MB_I4x4) k2_luma4(s, s_lut4, lane, modes, availA, availB, availC);
+            else                          k2_luma8(s, s_lut8, lane, modes, availA, availB, availC, availD);
+            k2_chroma(s, lane, cmode, availA, availB);
+            __syncwarp();
+
+            /* write the macroblock to the planar picture */
+            if (lane < 16) {
+                const uint2 a = *reinterpret_cast<const uint2 *>(s.lt + (lane + 1) * MVG_LT_STRIDE + MVG_LT_XOFF);
+                const uint2 b = *reinterpret_cast<const uint2 *>(s.lt + (lane + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + 8);
+                *reinterpret_cast<uint4 *>(ybase + (size_t)(row * 16 + lane) * ystride + mx * 16) = make_uint4(a.x, a.y, b.x, b.y);
+            } else {
+                const int pl = (lane >> 3) & 1, y = lane & 7;
+                const uint2 a = *reinterpret_cast<const uint2 *>(s.ct[pl] + (y + 1) * MVG_CT_STRIDE + MVG_CT_XOFF);
+                *reinterpret_cast<uint2 *>((pl ? crbase : cbbase) + (size_t)(row * 8 + y) * cstride + mx * 8) = a;
+            }
+            /* left column for the next macroblock: x = 15 -> x = -1 (rows 0..15; chroma x = 7) */
+            if (lane < 16) s.lt[(lane + 1) * MVG_LT_STRIDE + MVG_LT_XOFF - 1] = s.lt[(lane + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + 15];
+            else {
+                const int pl = (lane >> 3) & 1, y = lane & 7;
+                s.ct[pl][(y + 1) * MVG_CT_STRIDE + MVG_CT_XOFF - 1] = s.ct[pl][(y + 1) * MVG_CT_STRIDE + MVG_CT_XOFF + 7];
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile int *>(mine) = mx + 1;
+        }
+    }
+}
+
+/* ========================================================================= */
+/* Kernel 3                                                                    */
+
+struct K3Params {
+    const uint8_t *yuv;     /* [slot][1.5*W*H] */
+    uint8_t       *rgb;     /* [slot][3*(W/s)*(H/s)] */
+    int width, height, scale, first_slot, n_pics;
+};
+
+/* export_utils.c:300-302 */
+__device__ __forceinline__ void mvg_ycc_to_rgb(int Y, int Cb, int Cr, int &R, int &G, int &B)
+{
+    const int t = (298 * Y) >> 8;
+    R = mvg_clip8(t + ((408 * Cr) >> 8) - 222);
+    G = mvg_clip8(t - ((100 * Cb) >> 8) - ((208 * Cr) >> 8) + 135);
+    B = mvg_clip8(t + ((516 * Cb) >> 8) - 276);
+}
+
+/* scale 1: one thread converts 16 horizontally adjacent samples: 16 B of Y, 8 B of Cb
+ * and Cr in, 48 B of RGB24 out as three 128-bit stores. */
+__global__ void __launch_bounds__(256)
+k3_rgb_full(K3Params p)
+{
+    const int groups_per_row = p.width >> 4;
+    const long long per_pic = (long long)groups_per_row * p.height;
+    const long long total = per_pic * p.n_pics;
+    const size_t ysz = (size_t)p.width * p.height;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const int pic = (int)(g / per_pic);
+        const long long rem = g - (long long)pic * per_pic;
+        const int y = (int)(rem / groups_per_row), gx = (int)(rem - (long long)y * groups_per_row);
+        const size_t slot = (size_t)(p.first_slot + pic);
+        const uint8_t *Y = p.yuv + slot * (ysz * 3 / 2);
+        const uint8_t *Cb = Y + ysz, *Cr = Cb + ysz / 4;
+        const uint4 yy = __ldg(reinterpret_cast<const uint4 *>(Y + (size_t)y * p.width + gx * 16));
+        const size_t coff = (size_t)(y >> 1) * (p.width >> 1) + gx * 8;
+        const uint2 cb = __ldg(reinterpret_cast<const uint2 *>(Cb + coff));
+        const uint2 cr = __ldg(reinterpret_cast<const uint2 *>(Cr + coff));
+        const unsigned yw[4] = {yy.x, yy.y, yy.z, yy.w};
+        const unsigned cbw[2] = {cb.x, cb.y}, crw[2] = {cr.x, cr.y};
+        unsigned out[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) out[k] = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int Yv = (yw[i >> 2] >> (8 * (i & 3))) & 255;
+            const int ci = i >> 1;                      /* 2x2 replication, export_utils.c:278-279 */
+            const int Cbv = (cbw[ci >> 2] >> (8 * (ci & 3))) & 255, Crv = (crw[ci >> 2] >> (8 * (ci & 3))) & 255;
+            int R, G, B;
+            mvg_ycc_to_rgb(Yv, Cbv, Crv, R, G, B);
+            const int b0 = 3 * i, b1 = 3 * i + 1, b2 = 3 * i + 2;
+            out[b0 >> 2] |= (unsigned)R << (8 * (b0 & 3));
+            out[b1 >> 2] |= (unsigned)G << (8 * (b1 & 3));
+            out[b2 >> 2] |= (unsigned)B << (8 * (b2 & 3));
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(p.rgb + slot * (ysz * 3) + ((size_t)y * p.width + gx * 16) * 3);
+        dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+        dst[2] = make_uint4(out[8], out[9], out[10], out[11]);
+    }
+}
+
+/* scale s > 1: one thread per output pixel, rounded s x s box average of the
+ * full-resolution RGB picture. */
+__global__ void __launch_bounds__(256)
+k3_rgb_scaled(K3Params p)
+{
+    const int s = p.scale, ow = p.width / s, oh = p.height / s;
+    const long long per_pic = (long long)ow * oh, total = per_pic * p.n_pics;
+    const size_t ysz = (size_t)p.width * p.height;
+    const int area = s * s;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const int pic = (int)(g / per_pic);
+        const long long rem = g - (long long)pic * per_pic;
+        const int oy = (int)(rem / ow), ox = (int)(rem - (long long)oy * ow);
+        const size_t slot = (size_t)(p.first_slot + pic);
+        const uint8_t *Y = p.yuv + slot * (ysz * 3 / 2);
+        const uint8_t *Cb = Y + ysz, *Cr = Cb + ysz / 4;
+        int aR = 0, aG = 0, aB = 0;
+        for (int dy = 0; dy < s; dy++) {
+            const int py = oy * s + dy;
+            for (int dx = 0; dx < s; dx++) {
+                const int px = ox * s + dx;
+                const size_t co = (size_t)(py >> 1) * (p.width >> 1) + (px >> 1);
+                int R, G, B;
+                mvg_ycc_to_rgb(__ldg(Y + (size_t)py * p.width + px), __ldg(Cb + co), __ldg(Cr + co), R, G, B);
+                aR += R; aG += G; aB += B;
+            }
+        }
+        uint8_t *o = p.rgb + slot * ((size_t)ow * oh * 3) + ((size_t)oy * ow + ox) * 3;
+        o[0] = (uint8_t)((aR + area / 2) / area);
+        o[1] = (uint8_t)((aG + area / 2) / area);
+        o[2] = (uint8_t)((aB + area / 2) / area);
+    }
+}
