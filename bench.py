@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the H.264 intra reconstruction hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--frames F] [--distinct G] [--rgb-scale S] [--e2e-frames E]
+
+One "step" = one pass of the hot path (kernel 1 dequant/IDCT, kernel 2 wavefront
+prediction, kernel 3 RGB) over one batch of F synthetic 1920x1088 High-profile
+IDR pictures (BASELINE.json configs[2]) that are already resident in HBM.
+Rank 0 prints ONE JSON line.  Multi-GPU: one process per GPU (torchrun), disjoint
+pictures per GPU, no collective on the data path ("scaling": "weak").
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, the
+unmodified reference compiled by oracle/Makefile) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "1080p_idr_frames_per_s_recon_rgb"
+UNIT = "frames/s"
+WORKLOAD = "configs[2]: 1920x1080 High-profile CAVLC, 8x8 transform + custom scaling lists, 1000 IDR frames on 1 B200"
+
+
+# ----------------------------------------------------------------------------
+# helpers
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples = index, threading.Event(), []
+        self.max_mhz, self.reasons, self.err = None, set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                "hw_power_brake_slowdown": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+            }
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons",
+                                  getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+            while not self.stop_flag.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                if get_reasons:
+                    mask = get_reasons(h)
+                    for k, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(k)
+                time.sleep(0.02)
+        except Exception as e:  # pragma: no cover - depends on the box
+            self.err = repr(e)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "error": self.err}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def algorithmic_bytes(n_mb: int, width: int, height: int, scale: int):
+    """SURVEY.md section 8(d), per picture; kernel 2 reads the 16-byte control record
+    kernel 1 writes instead of the 32 B/MB the survey budgeted (stated in DESIGN.md)."""
+    meta_in = 21                      # mb_kind, i16_mode, chroma_mode, qp_y, cbp, 16 luma modes
+    k1 = n_mb * (768 + meta_in) + n_mb * (768 + 16)
+    k2 = n_mb * (768 + 16) + width * height * 3 // 2
+    k3 = width * height * 3 // 2 + 3 * (width // scale) * (height // scale) if scale >= 1 else 0
+    return {"k1": k1, "k2": k2, "k3": k3}
+
+
+# ----------------------------------------------------------------------------
+# reference arm: the unmodified reference decoder on the host cores
+
+def reference_sample(n_procs: int, pics_per_proc: int, rgb: bool = True):
+    """Every core decodes the same `pics_per_proc` 1080p pictures with the reference
+    (CAVLC parse + reconstruction + mb_to_rgb, no file output).  Returns
+    (frames_per_s, wall_s)."""
+    from minivideo_b200 import synth
+    from oracle import ref
+    if not ref.available():
+        raise RuntimeError("oracle/_ref/ref_decode is missing (run `make -C oracle ref` where the reference is mounted)")
+    stream, _ = synth.generate(pics_per_proc, "1080p", want_soa=False)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    with tempfile.TemporaryDirectory(dir=base, prefix="mvbench_") as d:
+        path = os.path.join(d, "sample.264")
+        Path(path).write_bytes(stream)
+        ref.time_decode(path, 1, rgb=rgb, cwd=d)            # warm the page cache / binary
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=n_procs) as ex:
+            secs = list(ex.map(lambda _: ref.time_decode(path, pics_per_proc, rgb=rgb, cwd=d), range(n_procs)))
+        wall = time.perf_counter() - t0
+    return n_procs * pics_per_proc / max(secs), wall
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    per = args.ref_pics
+    vals, walls = [], []
+    for i in range(args.warmup + args.steps):
+        fps, wall = reference_sample(cores, per)
+        if i >= args.warmup:
+            vals.append(fps); walls.append(wall)
+    value = float(np.mean(vals))
+    sample = f"{per} pictures per process x {cores} processes (one per host core), same 1080p stream, in-process minivideo_decode() time"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(walls)) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------
+# our arm
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    if args.gpus > 1 and world == 1:
+        # not launched by torchrun: re-exec under it (one process per GPU)
+        port = 29500 + (os.getpid() % 1000)
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                                   "--master-port", str(port), str(Path(__file__).resolve())] + sys.argv[1:])
+    import torch
+    import torch.distributed as dist
+    from minivideo_b200 import api, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- synthetic input: G distinct pictures per rank, replicated on the device to F
+    F, G, scale = args.frames, min(args.distinct, args.frames), args.rgb_scale
+    _, soa = synth.generate(G, "1080p", want_stream=False, seed=0xC0FFEE + 2 + 1000 * rank)
+    W, H, N = soa.width, soa.height, soa.n_mbs
+    ctx = api.Context(local, soa.width_mbs, soa.height_mbs, F)
+    ctx.set_sps_from(soa)
+    ctx.upload(soa, 0)
+    for s in range(G, F):
+        ctx.clone_slot(s % G, s)
+    ctx.sync()
+
+    # ---- timed region: K steps over the resident batch
+    for _ in range(args.warmup):
+        ctx.run(0, F, scale)
+    ctx.sync()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    k_ms = {"k1": [], "k2": [], "k3": []}
+    launches = 0
+    t_wall0 = time.perf_counter()
+    ctx.mark(0)
+    for _ in range(args.steps):
+        ctx.run(0, F, scale)
+        t = ctx.timing()                      # waits for the step; per-kernel CUDA-event times
+        k_ms["k1"].append(t.k1_dequant_idct_ms); k_ms["k2"].append(t.k2_wavefront_ms); k_ms["k3"].append(t.k3_rgb_ms)
+        launches += t.launches
+    ctx.mark(1)
+    dev_ms = ctx.mark_elapsed_ms()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    clocks = sampler.result()
+
+    # ---- end to end: pinned host SoA -> H2D -> kernels -> D2H RGB in pinned host memory
+    E = min(args.e2e_frames, F)
+    reps = -(-E // G)
+    pin = {
+        "mb_kind": api.PinnedArray((E * N,), np.uint8), "i16_mode": api.PinnedArray((E * N,), np.uint8),
+        "chroma_mode": api.PinnedArray((E * N,), np.uint8), "qp_y": api.PinnedArray((E * N,), np.int8),
+        "cbp": api.PinnedArray((E * N,), np.uint8), "luma_modes": api.PinnedArray((E * N, 16), np.uint8),
+        "coeff": api.PinnedArray((E * N, 384), np.int16),
+    }
+    for name, pa in pin.items():
+        src = getattr(soa, name)
+        pa.array[...] = np.concatenate([src] * reps)[: E * N]
+    rgb_px = (W // scale) * (H // scale) * 3
+    rgb_out = api.PinnedArray((E, rgb_px), np.uint8)
+    batch = api.Batch()
+    batch.n_pics = E
+    for name, pa in pin.items():
+        setattr(batch, name, pa.ptr)
+    h2d = sum(pa.nbytes for pa in pin.values())
+    d2h = rgb_out.nbytes
+    for _ in range(max(1, args.warmup // 2)):
+        ctx.decode_host(None, None, rgb_out.array, scale, batch=batch)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.decode_host(None, None, rgb_out.array, scale, batch=batch)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks (max time), rank 0 reports
+    times = torch.tensor([dev_ms, wall_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms, e2e_ms = (float(x) for x in times.tolist())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ab = algorithmic_bytes(N, W, H, scale)
+        mean_ms = {k: float(np.mean(v)) for k, v in k_ms.items()}
+        dom = max(mean_ms, key=mean_ms.get)
+        achieved = ab[dom] * F / (mean_ms[dom] * 1e-3) / 1e9
+        traffic = None
+        tfile = ROOT / "profiles" / "ncu_traffic.json"
+        if tfile.exists():
+            try:
+                traffic = json.loads(tfile.read_text()).get(dom, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        kernels = {k: {"ms_per_launch": mean_ms[k], "algorithmic_bytes": ab[k] * F,
+                       "achieved_gbs": ab[k] * F / (mean_ms[k] * 1e-3) / 1e9 if mean_ms[k] > 0 else None,
+                       "frac": ab[k] * F / (mean_ms[k] * 1e-3) / 1e9 / peak if mean_ms[k] > 0 else None}
+                   for k in mean_ms}
+        line = {
+            "metric": METRIC, "value": world * F * args.steps / (dev_ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pictures_per_step_per_gpu": F, "distinct_pictures": G,
+                       "coded_size": f"{W}x{H}", "rgb_scale": scale, "pipeline": "3 kernels (k1 dequant/idct, k2 wavefront, k3 rgb)",
+                       "l2": f"inputs {F * N * 789 / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
+                       "timing": "CUDA events on the launch stream, max over ranks", "wall_ms_per_step": wall_ms / args.steps},
+            "clocks": clocks,
+            "e2e": {"value": world * E * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "pictures_per_step_per_gpu": E,
+                    "path": "mvg_decode_host: pinned host SoA -> H2D -> k1,k2,k3 -> D2H RGB24"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": {"k1": "k1_dequant_idct", "k2": "k2_wavefront", "k3": "k3_rgb"}[dom],
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src},
+            "kernels": kernels,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cores = os.cpu_count() or 1
+                fps, _ = reference_sample(cores, args.ref_pics)
+                line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": f"{args.ref_pics} pictures per process x {cores} processes of the same 1080p "
+                                                  "stream through the unmodified reference (parse + recon + mb_to_rgb)"}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1000, help="pictures per step per GPU (resident in HBM)")
+    ap.add_argument("--distinct", type=int, default=32, help="distinct pictures generated on the host per GPU")
+    ap.add_argument("--rgb-scale", type=int, default=1, help="RGB thumbnail downscale factor (1 = the reference's mb_to_rgb)")
+    ap.add_argument("--e2e-frames", type=int, default=96, help="pictures per end-to-end step per GPU")
+    ap.add_argument("--ref-pics", type=int, default=6, help="pictures each host core decodes in the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

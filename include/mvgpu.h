@@ -151,6 +151,12 @@ int mvg_run(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale);
 int mvg_sync(mvg_ctx *ctx);
 int mvg_get_timing(mvg_ctx *ctx, mvg_timing *out);
 
+/* Bracket a region of several mvg_run() calls with two CUDA events on the context
+ * stream: mvg_mark(ctx, 0) before, mvg_mark(ctx, 1) after; mvg_mark_elapsed() waits
+ * for the second event and returns the device time between them (milliseconds). */
+int mvg_mark(mvg_ctx *ctx, int which);
+int mvg_mark_elapsed(mvg_ctx *ctx, float *ms);
+
 /* Copy results of picture slot `slot` to HOST memory.
  * yuv420: planar I420, (16*width_mbs) x (16*height_mbs), uncropped -- exactly the
  * bytes export_idr_yuv420() writes (export.c:100-151).

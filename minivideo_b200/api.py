@@ -17,7 +17,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libmvgpu.so"
 # every symbol include/mvgpu.h declares
 EXPORTS = (
     "mvg_create", "mvg_destroy", "mvg_last_error", "mvg_set_sps", "mvg_build_level_scale",
-    "mvg_upload", "mvg_clone_slot", "mvg_run", "mvg_sync", "mvg_get_timing",
+    "mvg_upload", "mvg_clone_slot", "mvg_run", "mvg_sync", "mvg_get_timing", "mvg_mark", "mvg_mark_elapsed",
     "mvg_download_yuv420", "mvg_download_rgb", "mvg_download_residual", "mvg_decode_host",
     "mvg_host_alloc", "mvg_host_free", "mvg_width", "mvg_height", "mvg_max_pics", "mvg_sm_count",
 )
@@ -62,6 +62,8 @@ def load_library() -> C.CDLL:
     lib.mvg_run.argtypes = [vp, i32, i32, i32]
     lib.mvg_sync.argtypes = [vp]
     lib.mvg_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    lib.mvg_mark.argtypes = [vp, i32]
+    lib.mvg_mark_elapsed.argtypes = [vp, C.POINTER(C.c_float)]
     lib.mvg_download_yuv420.argtypes = [vp, i32, vp, vp, vp]
     lib.mvg_download_rgb.argtypes = [vp, i32, vp]
     lib.mvg_download_residual.argtypes = [vp, i32, vp]
@@ -198,6 +200,14 @@ class Context:
         t = Timing()
         self._ck(self.lib.mvg_get_timing(self.handle, C.byref(t)))
         return t
+
+    def mark(self, which: int):
+        self._ck(self.lib.mvg_mark(self.handle, which))
+
+    def mark_elapsed_ms(self) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.mvg_mark_elapsed(self.handle, C.byref(ms)))
+        return float(ms.value)
 
     def download_yuv420(self, slot) -> np.ndarray:
         w, h = self.width, self.height

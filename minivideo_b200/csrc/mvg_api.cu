@@ -33,6 +33,7 @@ struct mvg_ctx {
 
     cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_mark[2] = {nullptr, nullptr};
     cudaEvent_t ev_h2d[MVG_PIPE_DEPTH] = {}, ev_comp[MVG_PIPE_DEPTH] = {}, ev_d2h[MVG_PIPE_DEPTH] = {};
     bool ran_k3 = false;
     int launches = 0, last_scale = 0;
@@ -259,6 +260,7 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     TRY("stream", cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     TRY("stream", cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     for (auto &ev : ctx->ev) TRY("event", cudaEventCreate(&ev));
+    for (auto &ev : ctx->ev_mark) TRY("event", cudaEventCreate(&ev));
     for (int i = 0; i < MVG_PIPE_DEPTH; i++) {
         TRY("event", cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
         TRY("event", cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
@@ -298,6 +300,7 @@ extern "C" int mvg_destroy(mvg_ctx *ctx)
     cudaFree(ctx->d_yuv); cudaFree(ctx->d_rgb); cudaFree(ctx->d_progress); cudaFree(ctx->d_work);
     cudaFree(ctx->d_tab); cudaFree(ctx->d_luts);
     for (auto ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto ev : ctx->ev_mark) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < MVG_PIPE_DEPTH; i++) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
@@ -498,6 +501,23 @@ extern "C" int mvg_get_timing(mvg_ctx *ctx, mvg_timing *out)
     if (ctx->ran_k3) CK(ctx, cudaEventElapsedTime(&out->k3_rgb_ms, ctx->ev[2], ctx->ev[3]));
     CK(ctx, cudaEventElapsedTime(&out->total_ms, ctx->ev[0], ctx->ev[3]));
     out->launches = ctx->launches;
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_mark(mvg_ctx *ctx, int which)
+{
+    if (!ctx || which < 0 || which > 1) return MVG_FAILURE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaEventRecord(ctx->ev_mark[which], ctx->stream));
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_mark_elapsed(mvg_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return MVG_FAILURE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaEventSynchronize(ctx->ev_mark[1]));
+    CK(ctx, cudaEventElapsedTime(ms, ctx->ev_mark[0], ctx->ev_mark[1]));
     return MVG_SUCCESS;
 }
 

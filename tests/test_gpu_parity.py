@@ -1,0 +1,155 @@
+"""Parity of the CUDA path (through the C ABI of libmvgpu.so) against the oracle and the golden
+vectors of the reference.  Bit-exact: integer/byte work, no tolerance."""
+import numpy as np
+import pytest
+
+from helpers import golden_names, large_digests, load_golden, sha
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx_for(soa, n_slots, ls4=None, ls8=None):
+    from minivideo_b200 import api
+    ctx = api.Context(0, soa.width_mbs, soa.height_mbs, n_slots)
+    if ls4 is None:
+        ctx.set_sps_from(soa)
+    else:
+        ctx.set_sps(soa.width_mbs, soa.height_mbs, ls4, ls8, soa.cb_qp_offset, soa.cr_qp_offset)
+    return ctx
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_gpu_matches_reference_golden_vectors(name):
+    """Input = the reference's own parsed macroblocks and LevelScale tables; expected output = the
+    reference's own YUV and mb_to_rgb() bytes."""
+    soa, z = load_golden(name)
+    ctx = _ctx_for(soa, soa.n_pics, z["ls4"], z["ls8"])
+    ctx.upload(soa, 0)
+    ctx.run(0, soa.n_pics, 1)
+    ctx.sync()
+    for i in range(soa.n_pics):
+        assert np.array_equal(ctx.download_yuv420(i), z["yuv"][i]), f"{name} pic {i} YUV"
+        assert np.array_equal(ctx.download_rgb(i), z["rgb"][i]), f"{name} pic {i} RGB"
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", sorted(large_digests()))
+def test_gpu_large_digests(name):
+    from minivideo_b200 import api, synth
+    d = large_digests()[name]
+    _, soa = synth.generate(d["n_pics"], want_stream=False, **d["params"])
+    out = api.reconstruct(soa, rgb_scale=1)
+    assert [sha(out["yuv"][i]) for i in range(d["n_pics"])] == d["yuv_sha256"]
+    assert [sha(out["rgb"][i]) for i in range(d["n_pics"])] == d["rgb_sha256"]
+
+
+CASES = {
+    "cif_30": (30, dict(config="cif")),
+    "720p": (3, dict(config="720p", seed=61)),
+    "1080p": (4, dict(config="1080p", seed=62)),
+    "qp_extremes": (2, dict(width_mbs=12, height_mbs=9, profile_idc=100, transform8x8=1, scaling_lists=1, seed=63, qp_min=0, qp_max=51)),
+    "big_levels": (2, dict(width_mbs=12, height_mbs=9, profile_idc=100, transform8x8=1, seed=64, level_scale_x10=300, max_level=255, qp_min=0, qp_max=51, luma_cbp_percent=95)),
+    "hostile_levels": (1, dict(width_mbs=8, height_mbs=8, profile_idc=100, transform8x8=1, scaling_lists=1, seed=65, level_scale_x10=30000, max_level=8191, qp_min=40, qp_max=51, init_qp=45, luma_cbp_percent=100)),
+    "one_mb": (5, dict(width_mbs=1, height_mbs=1, profile_idc=100, transform8x8=1, seed=66)),
+    "one_row": (2, dict(width_mbs=33, height_mbs=1, profile_idc=100, transform8x8=1, seed=67)),
+    "one_col": (2, dict(width_mbs=1, height_mbs=33, profile_idc=100, transform8x8=1, seed=68)),
+    "two_cols": (2, dict(width_mbs=2, height_mbs=17, profile_idc=100, transform8x8=1, seed=69)),
+    "2160p": (1, dict(config="2160p", seed=70)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_gpu_matches_oracle(name):
+    """Same seeded SoA through the oracle and the CUDA path: residual (kernel 1), YUV (kernel 2)
+    and RGB (kernel 3) must be identical, including int32 wrap-around on hostile levels."""
+    from minivideo_b200 import api, synth
+    from oracle import cpu
+    n, kw = CASES[name]
+    _, soa = synth.generate(n, want_stream=False, **kw)
+    want_yuv, want_res = cpu.reconstruct(soa, want_residual=True)
+    got = api.reconstruct(soa, rgb_scale=1, want_residual=True)
+    assert np.array_equal(got["residual"], want_res)
+    assert np.array_equal(got["yuv"], want_yuv)
+    assert np.array_equal(got["rgb"], cpu.yuv_to_rgb(want_yuv, soa.width, soa.height, 1))
+
+
+@pytest.mark.parametrize("scale", [2, 4, 8, 16])
+def test_gpu_rgb_downscale_matches_oracle_box_filter(scale):
+    from minivideo_b200 import api, synth
+    from oracle import cpu
+    _, soa = synth.generate(2, want_stream=False, width_mbs=12, height_mbs=8, profile_idc=100, transform8x8=1, seed=71)
+    want_yuv, _ = cpu.reconstruct(soa)
+    got = api.reconstruct(soa, rgb_scale=scale)
+    assert np.array_equal(got["rgb"], cpu.yuv_to_rgb(want_yuv, soa.width, soa.height, scale))
+
+
+def test_full_size_batch_properties_1080p():
+    """BASELINE-size property checks (the oracle would take minutes on this many pictures):
+    a batch built from 4 distinct pictures cloned into 96 slots reconstructs every clone to the
+    same bytes as its source, whatever wave of the persistent kernel processed it; a second run is
+    bit-identical (no race); RGB at scale 4 equals the box average of the scale-1 RGB."""
+    from minivideo_b200 import api, synth
+    from oracle import cpu
+    G, F = 4, 96
+    _, soa = synth.generate(G, want_stream=False, config="1080p", seed=81)
+    ctx = _ctx_for(soa, F)
+    ctx.upload(soa, 0)
+    for s in range(G, F):
+        ctx.clone_slot(s % G, s)
+    ctx.run(0, F, 1)
+    ctx.sync()
+    want_yuv, _ = cpu.reconstruct(soa.pictures(0, 2))
+    base = [ctx.download_yuv420(i) for i in range(G)]
+    base_rgb = [ctx.download_rgb(i) for i in range(G)]
+    assert np.array_equal(base[0], want_yuv[0]) and np.array_equal(base[1], want_yuv[1])
+    for s in (G, G + 1, 37, 50, F - 2, F - 1):
+        assert np.array_equal(ctx.download_yuv420(s), base[s % G]), s
+        assert np.array_equal(ctx.download_rgb(s), base_rgb[s % G]), s
+    ctx.run(0, F, 4)
+    ctx.sync()
+    for s in (0, 1, F - 1):
+        assert np.array_equal(ctx.download_yuv420(s), base[s % G])
+        full = base_rgb[s % G].astype(np.uint32)
+        h, w = full.shape[:2]
+        box = (full.reshape(h // 4, 4, w // 4, 4, 3).sum(axis=(1, 3)) + 8) // 16
+        assert np.array_equal(ctx.download_rgb(s, 4), box.astype(np.uint8))
+    t = ctx.timing()
+    assert t.launches == 3 and t.k2_wavefront_ms > 0
+    ctx.close()
+
+
+def test_decode_host_equals_resident_path_and_handles_ragged_batches():
+    """mvg_decode_host (pinned H2D/D2H pipeline over slot regions) with batch sizes that do not
+    divide the region size, including a batch larger than the context."""
+    from minivideo_b200 import api, synth
+    from oracle import cpu
+    _, soa = synth.generate(11, want_stream=False, width_mbs=10, height_mbs=7, profile_idc=100, transform8x8=1,
+                            scaling_lists=1, seed=91)
+    want_yuv, _ = cpu.reconstruct(soa)
+    want_rgb = cpu.yuv_to_rgb(want_yuv, soa.width, soa.height, 1)
+    for slots in (1, 2, 4, 6, 16):
+        ctx = _ctx_for(soa, slots)
+        yuv = np.zeros_like(want_yuv)
+        rgb = np.zeros((soa.n_pics, soa.height * soa.width * 3), np.uint8)
+        ctx.decode_host(soa, yuv, rgb, 1)
+        assert np.array_equal(yuv, want_yuv), slots
+        assert np.array_equal(rgb.reshape(want_rgb.shape), want_rgb), slots
+        ctx.close()
+
+
+def test_error_paths():
+    from minivideo_b200 import api, synth
+    _, soa = synth.generate(1, want_stream=False, width_mbs=4, height_mbs=4, profile_idc=66)
+    ctx = api.Context(0, 4, 4, 2)
+    with pytest.raises(api.MvgError, match="mvg_set_sps"):
+        ctx.run(0, 1, 1)
+    ctx.set_sps_from(soa)
+    with pytest.raises(api.MvgError, match="slots"):
+        ctx.run(1, 2, 1)
+    with pytest.raises(api.MvgError, match="rgb_scale"):
+        ctx.upload(soa, 0); ctx.run(0, 1, 3)
+    with pytest.raises(api.MvgError, match="capacity"):
+        ctx.set_sps(5, 4, *api.build_level_scale(None, None))
+    ctx.close()
+    with pytest.raises(api.MvgError, match="out of range"):
+        api.Context(99, 4, 4, 1)
