@@ -23,6 +23,7 @@ static char g_create_error[512] = "";
 
 #define MVG_PIPE_DEPTH 3       /* slot regions used by mvg_decode_host */
 #define MVG_WORK_RING  64      /* work counters, one per kernel-2 launch in flight */
+#define MVG_K2_GROUP   512     /* pictures interleaved row by row in kernel 2's claim order */
 
 struct mvg_ctx {
     int device = -1, sm_count = 0;
@@ -46,8 +47,10 @@ struct mvg_ctx {
     int16_t *d_resid = nullptr;
     MvgMbCtl *d_ctl = nullptr;
     uint8_t *d_yuv = nullptr, *d_rgb = nullptr;
-    int *d_progress = nullptr, *d_work = nullptr;
+    uint2 *d_halo = nullptr;         /* [slot][n_mb][8] flag-in-data bottom lines (kernel 2) */
+    int *d_work = nullptr;
     int work_next = 0;
+    unsigned epoch = 0;              /* bumped per kernel-2 launch; halo words carry it       */
     MvgTables *d_tab = nullptr;
     MvgLuts *d_luts = nullptr;
 
@@ -201,7 +204,7 @@ extern "C" void mvg_build_luts(MvgLuts *out)
                                 if (!tr && i > 3) i = 3;     /* h264_intra_prediction.c:431-439 */
                                 off = -MVG_LT_STRIDE + i;
                             }
-                            word |= (uint32_t)(uint8_t)(int8_t)off << (8 * k);
+                            word |= (uint32_t)(off + MVG_LUT4_BIAS) << (8 * k);
                         }
                     }
                     out->lut4[tr][mode][y * 4 + x] = word;
@@ -278,7 +281,8 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     TRY("alloc ctl", dalloc(&ctx->d_ctl, n));
     TRY("alloc yuv", dalloc(&ctx->d_yuv, n * 384));
     TRY("alloc rgb", dalloc(&ctx->d_rgb, n * 768));
-    TRY("alloc progress", dalloc(&ctx->d_progress, (size_t)max_pics * max_h_mbs));
+    TRY("alloc halo", dalloc(&ctx->d_halo, n * 8));
+    TRY("clear halo", cudaMemset(ctx->d_halo, 0, n * 8 * sizeof(uint2)));
     TRY("alloc work", dalloc(&ctx->d_work, MVG_WORK_RING));
     TRY("alloc tables", dalloc(&ctx->d_tab, 1));
     TRY("alloc luts", dalloc(&ctx->d_luts, 1));
@@ -297,7 +301,7 @@ extern "C" int mvg_destroy(mvg_ctx *ctx)
     cudaDeviceSynchronize();
     cudaFree(ctx->d_kind); cudaFree(ctx->d_i16); cudaFree(ctx->d_cm); cudaFree(ctx->d_qp); cudaFree(ctx->d_cbp);
     cudaFree(ctx->d_modes); cudaFree(ctx->d_coeff); cudaFree(ctx->d_resid); cudaFree(ctx->d_ctl);
-    cudaFree(ctx->d_yuv); cudaFree(ctx->d_rgb); cudaFree(ctx->d_progress); cudaFree(ctx->d_work);
+    cudaFree(ctx->d_yuv); cudaFree(ctx->d_rgb); cudaFree(ctx->d_halo); cudaFree(ctx->d_work);
     cudaFree(ctx->d_tab); cudaFree(ctx->d_luts);
     for (auto ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : ctx->ev_mark) if (ev) cudaEventDestroy(ev);
@@ -425,7 +429,6 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
     int *work = ctx->d_work + ctx->work_next;
     ctx->work_next = (ctx->work_next + 1) % MVG_WORK_RING;
     CK(ctx, cudaMemsetAsync(work, 0, sizeof(int), st));
-    CK(ctx, cudaMemsetAsync(ctx->d_progress + (size_t)first_slot * H, 0, (size_t)n_pics * H * sizeof(int), st));
 
     int launches = 0;
     if (timed) CK(ctx, cudaEventRecord(ctx->ev[0], st));
@@ -444,7 +447,9 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
     if (timed) CK(ctx, cudaEventRecord(ctx->ev[1], st));
     {
         K2Params p;
-        p.resid = ctx->d_resid; p.ctl = ctx->d_ctl; p.yuv = ctx->d_yuv; p.progress = ctx->d_progress;
+        p.resid = ctx->d_resid; p.ctl = ctx->d_ctl; p.yuv = ctx->d_yuv; p.halo = ctx->d_halo;
+        if (++ctx->epoch == 0) ctx->epoch = 1;      /* 0 is the value of never-written words */
+        p.epoch = ctx->epoch; p.group = MVG_K2_GROUP;
         p.work = work; p.luts = ctx->d_luts; p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics;
         const long long items = (long long)n_pics * H;
         const int grid = (int)std::min<long long>((items + K2_WARPS - 1) / K2_WARPS, (long long)ctx->sm_count * 8);
@@ -579,12 +584,13 @@ extern "C" int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *b, uint8_t *yuv_ou
     const int scale = rgb_out ? rgb_scale : 0;
     const size_t n = ctx->n_mb();
     const size_t yuv_sz = n * 384, rgb_sz = scale ? rgb_bytes(ctx, scale) : 0;
-    /* region size: a third of the context, but never more pictures than needed */
+    /* slot regions: MVG_PIPE_DEPTH of them; a region holds at most a third of the context
+     * and at most an eighth of the batch, so that H2D, kernels and D2H of neighbouring
+     * chunks overlap even when the whole batch would fit in one region. */
     int depth = MVG_PIPE_DEPTH;
     int chunk = std::max(1, ctx->max_pics / depth);
     if (ctx->max_pics < depth) { depth = 1; chunk = ctx->max_pics; }
-    chunk = std::min(chunk, b->n_pics);
-
+    chunk = std::min(chunk, std::max(1, (b->n_pics + 7) / 8));
     int idx = 0;
     for (int done = 0; done < b->n_pics; done += chunk, idx++) {
         const int cnt = std::min(chunk, b->n_pics - done);

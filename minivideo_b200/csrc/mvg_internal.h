@@ -35,12 +35,14 @@ struct MvgMbCtl { uint32_t w0, w1, w2, w3; };
  *   2-tap (p + q + 1) >> 1       -> {p,p,q,q}
  *   copy  p                      -> {p,p,p,p}
  *   end   (p + 3q + 2) >> 2      -> {p,q,q,q}
- * lut4[tr][mode][y*4+x]: four int8 byte offsets into the luma tile relative to
- *   the block's top-left sample; tr = 1 when p[4..7,-1] are available, else they
- *   alias p[3,-1] (h264_intra_prediction.c:431-439).  Mode 2 (DC) is unused.
+ * lut4[tr][mode][y*4+x]: four uint8 byte offsets into the luma tile relative to
+ *   (the block's top-left sample - MVG_LUT4_BIAS); tr = 1 when p[4..7,-1] are
+ *   available, else they alias p[3,-1] (h264_intra_prediction.c:431-439).
+ *   Mode 2 (DC) is unused.
  * lut8[mode][y*8+x]: four uint8 indices into the 26-entry filtered neighbour
  *   line of an 8x8 block: 0..7 = p'[-1,7..0], 8 = p'[-1,-1], 9..24 = p'[0..15,-1],
  *   25 = the DC value (mode 2 points all four taps there).                      */
+#define MVG_LUT4_BIAS    (MVG_LT_STRIDE + 1)   /* p[-1,-1] is the lowest address */
 #define MVG_N8_LEFT(y)  (7 - (y))
 #define MVG_N8_CORNER   8
 #define MVG_N8_TOP(x)   (9 + (x))

@@ -84,24 +84,34 @@ __device__ __forceinline__ void mvg_idct8_1d(int (&v)[8])
     v[4] = b6 - b1; v[5] = b4 - b3; v[6] = b2 - b5; v[7] = b0 - b7;
 }
 
-__device__ __forceinline__ int mvg_sat16(int v) { return min(max(v, -32768), 32767); }
+/* two int32 -> saturated int16 pair (hi:lo) in one instruction */
+__device__ __forceinline__ unsigned mvg_pack_sat16(int hi, int lo)
+{
+    unsigned d;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+    return d;
+}
 
 #define K1_WARPS 8
 
-/* One warp per macroblock.
+/* One warp per macroblock, grid-stride, the next macroblock's loads in flight while the
+ * current one is transformed.
  *  4x4 path (Intra4x4 / Intra16x16 luma, all chroma): lane b < 24 owns 4x4 block b
  *    (0..15 luma in decoding order, 16..19 Cb, 20..23 Cr): two 128-bit loads bring
  *    its 16 levels, the zig-zag inverse is a compile-time register renaming, both
  *    butterfly passes stay in registers.  The Intra16x16 DC Hadamard and the chroma
- *    DC 2x2 are done across lanes with shuffles.
+ *    DC 2x2 run across lanes with shuffles.
  *  8x8 path (Intra8x8 luma): 8 lanes per block, one matrix row per lane, transposed
  *    through shared memory between the row and the column pass.
- *  The int16 residual is staged in shared memory in raster order and leaves with
- *    coalesced 128-bit stores. */
-__global__ void __launch_bounds__(K1_WARPS * 32)
+ *  The dequantisation scale (LevelScale << (qP/6 - 4)) is tabulated per qP in shared
+ *  memory; the rounding constant 32 of the final >> 6 is added to the DC term before the
+ *  butterflies (it reaches every output with weight one).  The int16 residual is staged
+ *  in shared memory in raster order and leaves with coalesced 128-bit stores. */
+__global__ void __launch_bounds__(K1_WARPS * 32, 3)
 k1_dequant_idct(K1Params p)
 {
     __shared__ int32_t s_ls4[3 * 6 * 16];
+    __shared__ int32_t s_ls4q[3 * 52 * 16];                     /* qP >= 24: LevelScale << (qP/6-4) */
     __shared__ int32_t s_ls8[6 * 64];
     __shared__ uint8_t s_zz8inv[64];
     __shared__ __align__(16) int16_t s_in[K1_WARPS][256];      /* luma levels of an Intra8x8 MB */
@@ -109,6 +119,11 @@ k1_dequant_idct(K1Params p)
     __shared__ __align__(16) int16_t s_out[K1_WARPS][384];     /* residual, raster                */
 
     for (int i = threadIdx.x; i < 3 * 6 * 16; i += blockDim.x) s_ls4[i] = (&p.tab->ls4[0][0][0])[i];
+    for (int i = threadIdx.x; i < 3 * 52 * 16; i += blockDim.x) {
+        const int k = i & 15, qp = (i >> 4) % 52, c = (i >> 4) / 52;
+        const int v = p.tab->ls4[c][qp % 6][k];
+        s_ls4q[i] = qp > 23 ? (int)((unsigned)v << (qp / 6 - 4)) : v;
+    }
     for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) s_ls8[i] = (&p.tab->ls8[0][0])[i];
     if (threadIdx.x < 64) s_zz8inv[threadIdx.x] = p.tab->zz8inv[threadIdx.x];
     const int cb_off = p.tab->cb_qp_offset, cr_off = p.tab->cr_qp_offset;
@@ -116,51 +131,78 @@ k1_dequant_idct(K1Params p)
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long n_warps = (long long)gridDim.x * K1_WARPS;
+    const bool is_chroma = lane >= 16;
+    const int comp = lane < 16 ? 0 : (lane < 20 ? 1 : 2);
+    int16_t *out = s_out[w];
+    /* where this lane's 4x4 block lands in the raster residual */
+    int16_t *dst;
+    int dst_stride;
+    if (lane < 16) {
+        const int bx = (lane & 1) | (((lane >> 2) & 1) << 1), by = ((lane >> 1) & 1) | ((lane >> 3) << 1);
+        dst = out + (by * 4) * 16 + bx * 4; dst_stride = 16;
+    } else {
+        const int b = lane & 3, pl = (lane >> 2) & 1;
+        dst = out + 256 + pl * 64 + ((b >> 1) * 4) * 8 + (b & 1) * 4; dst_stride = 8;
+    }
 
-    for (long long mb = (long long)blockIdx.x * K1_WARPS + w; mb < p.n_mbs; mb += n_warps) {
-        const int kind = p.mb_kind[mb];
-        const int qp = p.qp_y[mb];
-        const int16_t *cf = p.coeff + mb * 384;
-        int16_t *out = s_out[w];
+    long long mb = (long long)blockIdx.x * K1_WARPS + w;
+    uint4 na = make_uint4(0, 0, 0, 0), nb = na;
+    int nkind = 0, nqp = 0;
+    if (mb < p.n_mbs) {
+        if (lane < 24) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.coeff + mb * 384 + lane * 16);
+            na = __ldg(src); nb = __ldg(src + 1);
+        }
+        nkind = p.mb_kind[mb]; nqp = p.qp_y[mb];
+    }
+
+    for (; mb < p.n_mbs; mb += n_warps) {
+        const uint4 a = na, b = nb;
+        const int kind = nkind, qp = nqp;
+        const int mode_byte = lane < 16 ? p.luma_modes[mb * 16 + lane] : 0;
+        const unsigned w0 = (unsigned)kind | ((unsigned)p.i16_mode[mb] << 8) | ((unsigned)p.chroma_mode[mb] << 16);
+        {   /* prefetch the next macroblock of this warp */
+            const long long nx = mb + n_warps;
+            if (nx < p.n_mbs) {
+                if (lane < 24) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(p.coeff + nx * 384 + lane * 16);
+                    na = __ldg(src); nb = __ldg(src + 1);
+                }
+                nkind = p.mb_kind[nx]; nqp = p.qp_y[nx];
+            }
+        }
 
         /* ---------------- 4x4 blocks ---------------- */
         const bool luma4 = (kind != MVG_MB_I8x8);
-        const bool is_chroma = lane >= 16;
         const bool active = lane < 24 && (is_chroma || luma4);
         int c[16];                              /* matrix, row-major, after inverse zig-zag */
-#pragma unroll
-        for (int k = 0; k < 16; k++) c[k] = 0;
-        if (active) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(cf + lane * 16);
-            uint4 a = __ldg(src), b = __ldg(src + 1);
-            int v[16];
-            v[0] = (short)(a.x & 0xffff); v[1] = (int)a.x >> 16; v[2] = (short)(a.y & 0xffff); v[3] = (int)a.y >> 16;
-            v[4] = (short)(a.z & 0xffff); v[5] = (int)a.z >> 16; v[6] = (short)(a.w & 0xffff); v[7] = (int)a.w >> 16;
-            v[8] = (short)(b.x & 0xffff); v[9] = (int)b.x >> 16; v[10] = (short)(b.y & 0xffff); v[11] = (int)b.y >> 16;
-            v[12] = (short)(b.z & 0xffff); v[13] = (int)b.z >> 16; v[14] = (short)(b.w & 0xffff); v[15] = (int)b.w >> 16;
+        {
             /* zig-zag k -> (row,col): utils.h:64 / spec Table 8-13 */
-            c[0] = v[0];  c[1] = v[1];  c[4] = v[2];  c[8] = v[3];
-            c[5] = v[4];  c[2] = v[5];  c[3] = v[6];  c[6] = v[7];
-            c[9] = v[8];  c[12] = v[9]; c[13] = v[10]; c[10] = v[11];
-            c[7] = v[12]; c[11] = v[13]; c[14] = v[14]; c[15] = v[15];
+            c[0] = (short)(a.x & 0xffff); c[1] = (int)a.x >> 16; c[4] = (short)(a.y & 0xffff); c[8] = (int)a.y >> 16;
+            c[5] = (short)(a.z & 0xffff); c[2] = (int)a.z >> 16; c[3] = (short)(a.w & 0xffff); c[6] = (int)a.w >> 16;
+            c[9] = (short)(b.x & 0xffff); c[12] = (int)b.x >> 16; c[13] = (short)(b.y & 0xffff); c[10] = (int)b.y >> 16;
+            c[7] = (short)(b.z & 0xffff); c[11] = (int)b.z >> 16; c[14] = (short)(b.w & 0xffff); c[15] = (int)b.w >> 16;
+        }
+        if (kind == MVG_MB_I8x8) {              /* warp-uniform: stage the luma levels for the 8x8 path */
+            if (lane < 16) {
+                reinterpret_cast<uint4 *>(s_in[w])[2 * lane] = a;
+                reinterpret_cast<uint4 *>(s_in[w])[2 * lane + 1] = b;
+            }
         }
 
-        /* component and quantiser of this lane's block */
-        const int comp = lane < 16 ? 0 : (lane < 20 ? 1 : 2);
+        /* quantiser of this lane's block */
         int qpb = qp;
         if (comp) qpb = mvg_chroma_qp(qp, comp == 1 ? cb_off : cr_off);
-        const int qm = qpb % 6, qd = qpb / 6;
-        const int32_t *ls = s_ls4 + (comp * 6 + qm) * 16;
-        const int ls00 = ls[0];
+        const int qd = qpb / 6, qm = qpb - 6 * qd;
+        const int ls00 = s_ls4[(comp * 6 + qm) * 16];
         bool keep_dc = is_chroma;
 
         /* Intra16x16 luma DC: f = H c H over the 16 lanes (h264_transform.c:783-808) */
         if (kind == MVG_MB_I16x16) {            /* warp-uniform */
-            /* lane b sits at matrix position (i,j): i = by, j = bx */
-            const int bi = ((lane >> 1) & 1) | ((lane >> 3) << 1);
+            const int bi = ((lane >> 1) & 1) | (((lane >> 3) & 1) << 1);
             const int bj = (lane & 1) | (((lane >> 2) & 1) << 1);
-            /* rows of H (h264_transform.c:62-68) as sign masks over k */
-            const unsigned hs_i = (0xA6C0u >> (4 * bi)) & 0xF;   /* row0 0000,row1 1100,row2 0110,row3 1010 */
+            /* rows of H (h264_transform.c:62-68) as sign masks over k: 0000, 1100, 0110, 1010 */
+            const unsigned hs_i = (0xA6C0u >> (4 * bi)) & 0xF;
             const unsigned hs_j = (0xA6C0u >> (4 * bj)) & 0xF;
             int f = 0;
 #pragma unroll
@@ -168,12 +210,12 @@ k1_dequant_idct(K1Params p)
 #pragma unroll
                 for (int l = 0; l < 4; l++) {
                     const int src = (l & 1) | ((k & 1) << 1) | ((l >> 1) << 2) | ((k >> 1) << 3);
-                    int v = __shfl_sync(MVG_FULL, c[0], src);
+                    const int v = __shfl_sync(MVG_FULL, c[0], src);
                     const unsigned neg = ((hs_i >> k) ^ (hs_j >> l)) & 1u;
                     f += neg ? -v : v;
                 }
-            int t = f * ls00;
-            int dcy = (qp >= 36) ? (int)((unsigned)t << (qd - 6)) : ((t + (1 << (5 - qd))) >> (6 - qd));
+            const int t = f * ls00;
+            const int dcy = (qp >= 36) ? (int)((unsigned)t << (qd - 6)) : ((t + (1 << (5 - qd))) >> (6 - qd));
             if (lane < 16) { c[0] = dcy; keep_dc = true; }
         }
         /* chroma DC 2x2 (h264_transform.c:988-1005, :924-936) over lane groups 16..19, 20..23 */
@@ -182,25 +224,30 @@ k1_dequant_idct(K1Params p)
             int f = 0;
 #pragma unroll
             for (int s = 0; s < 4; s++) {
-                int v = __shfl_sync(MVG_FULL, c[0], base + s);
+                const int v = __shfl_sync(MVG_FULL, c[0], base + s);
                 const int neg = (r & (s >> 1)) ^ (cc & (s & 1));
                 f += neg ? -v : v;
             }
             if (is_chroma && lane < 24) c[0] = (int)((unsigned)(f * ls00) << qd) >> 5;
         }
 
+        unsigned nz_any = 0;
         if (active) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) nz_any |= (unsigned)c[k];
             /* quant4x4, h264_transform.c:1100-1134 */
             const int dc_in = c[0];
+            const int32_t *lq = s_ls4q + (comp * 52 + qpb) * 16;
             if (qpb > 23) {
 #pragma unroll
-                for (int k = 0; k < 16; k++) c[k] = (int)((unsigned)(c[k] * ls[k]) << (qd - 4));
+                for (int k = 0; k < 16; k++) c[k] = c[k] * lq[k];
             } else {
                 const int rnd = 1 << (3 - qd), sh = 4 - qd;
 #pragma unroll
-                for (int k = 0; k < 16; k++) c[k] = (c[k] * ls[k] + rnd) >> sh;
+                for (int k = 0; k < 16; k++) c[k] = (c[k] * lq[k] + rnd) >> sh;
             }
             if (keep_dc) c[0] = dc_in;
+            c[0] += 32;                         /* rounding of the final >> 6 (h264_transform.c:1190) */
             /* idct4x4: rows then columns */
 #pragma unroll
             for (int i = 0; i < 4; i++)
@@ -208,41 +255,32 @@ k1_dequant_idct(K1Params p)
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 mvg_bfly4(c[j], c[4 + j], c[8 + j], c[12 + j], c[j], c[4 + j], c[8 + j], c[12 + j]);
-            /* (h + 32) >> 6, saturate to int16, store raster */
-            int16_t *dst;
-            int stride;
-            if (lane < 16) {
-                const int bx = (lane & 1) | (((lane >> 2) & 1) << 1), by = ((lane >> 1) & 1) | ((lane >> 3) << 1);
-                dst = out + (by * 4) * 16 + bx * 4; stride = 16;
-            } else {
-                const int b = lane & 3, pl = (lane - 16) >> 2;
-                dst = out + 256 + pl * 64 + ((b >> 1) * 4) * 8 + (b & 1) * 4; stride = 8;
-            }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                int r0 = mvg_sat16((c[4 * i] + 32) >> 6), r1 = mvg_sat16((c[4 * i + 1] + 32) >> 6);
-                int r2 = mvg_sat16((c[4 * i + 2] + 32) >> 6), r3 = mvg_sat16((c[4 * i + 3] + 32) >> 6);
                 uint2 pk;
-                pk.x = (unsigned)(r0 & 0xffff) | ((unsigned)r1 << 16);
-                pk.y = (unsigned)(r2 & 0xffff) | ((unsigned)r3 << 16);
-                *reinterpret_cast<uint2 *>(dst + i * stride) = pk;
+                pk.x = mvg_pack_sat16(c[4 * i + 1] >> 6, c[4 * i] >> 6);
+                pk.y = mvg_pack_sat16(c[4 * i + 3] >> 6, c[4 * i + 2] >> 6);
+                *reinterpret_cast<uint2 *>(dst + i * dst_stride) = pk;
             }
         }
+        unsigned nzmask = __ballot_sync(MVG_FULL, nz_any != 0) & (luma4 ? 0x00FFFFFFu : 0x00FF0000u);
 
         /* ---------------- Intra8x8 luma ---------------- */
         if (kind == MVG_MB_I8x8) {              /* warp-uniform */
-            reinterpret_cast<uint4 *>(s_in[w])[lane] = __ldg(reinterpret_cast<const uint4 *>(cf) + lane);
             __syncwarp();
             const int b8 = lane >> 3, row = lane & 7;
-            const int qm8 = qp % 6, qd8 = qp / 6;
+            const int qd8 = qp / 6, qm8 = qp - 6 * qd8;
             const int32_t *l8 = s_ls8 + qm8 * 64 + row * 8;
             int v[8];
+            unsigned any8 = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                int lvl = s_in[w][b8 * 64 + s_zz8inv[row * 8 + j]];
-                int t = lvl * l8[j];                      /* quant8x8, h264_transform.c:1256-1284 */
+                const int lvl = s_in[w][b8 * 64 + s_zz8inv[row * 8 + j]];
+                any8 |= (unsigned)lvl;
+                const int t = lvl * l8[j];                /* quant8x8, h264_transform.c:1256-1284 */
                 v[j] = (qp > 35) ? (int)((unsigned)t << (qd8 - 6)) : ((t + (1 << (5 - qd8))) >> (6 - qd8));
             }
+            if (row == 0) v[0] += 32;                     /* rounding of the final >> 6 (:1382) */
             mvg_idct8_1d(v);                              /* row pass */
 #pragma unroll
             for (int j = 0; j < 8; j++) s_tr[w][b8][row][j] = v[j];
@@ -252,54 +290,26 @@ k1_dequant_idct(K1Params p)
             mvg_idct8_1d(v);                              /* column pass */
             const int xo = (b8 & 1) * 8 + row, yo = (b8 >> 1) * 8;
 #pragma unroll
-            for (int i = 0; i < 8; i++) out[(yo + i) * 16 + xo] = (int16_t)mvg_sat16((v[i] + 32) >> 6);
+            for (int i = 0; i < 8; i++) out[(yo + i) * 16 + xo] = (int16_t)min(max(v[i] >> 6, -32768), 32767);
+            const unsigned bal = __ballot_sync(MVG_FULL, any8 != 0);
+#pragma unroll
+            for (int q = 0; q < 4; q++) if ((bal >> (8 * q)) & 0xFFu) nzmask |= 0xFu << (4 * q);
         }
         __syncwarp();
 
         /* ---------------- write residual + control record ---------------- */
         uint4 *gout = reinterpret_cast<uint4 *>(p.resid + mb * 384);
         const uint4 *sout = reinterpret_cast<const uint4 *>(out);
-        uint4 q0 = sout[lane];
-        uint4 q1 = make_uint4(0, 0, 0, 0);
-        if (lane < 16) q1 = sout[32 + lane];
-        gout[lane] = q0;
-        if (lane < 16) gout[32 + lane] = q1;
+        gout[lane] = sout[lane];
+        if (lane < 16) gout[32 + lane] = sout[32 + lane];
 
-        /* non-zero map: 8 shorts per uint4; lane's q0 covers luma row lane>>1, cols 8*(lane&1).. */
-        unsigned nz_lo = (q0.x | q0.y) != 0, nz_hi = (q0.z | q0.w) != 0;     /* two 4-sample groups */
-        /* luma 4x4 block of (row y, col group g): bx = g, by = y>>2 */
-        unsigned mask = 0;
-        {
-            const int y = lane >> 1, g0 = (lane & 1) * 2;
-            const int by = y >> 2;
-            const int b_lo = (g0 & 1) | ((by & 1) << 1) | ((g0 >> 1) << 2) | ((by >> 1) << 3);
-            const int g1 = g0 + 1;
-            const int b_hi = (g1 & 1) | ((by & 1) << 1) | ((g1 >> 1) << 2) | ((by >> 1) << 3);
-            mask |= nz_lo << b_lo;
-            mask |= nz_hi << b_hi;
-        }
-        if (lane < 16) {     /* chroma: q1 covers plane lane>>3, row lane&7, 8 samples = blocks (y>>2)*2 + {0,1} */
-            const int pl = lane >> 3, y = lane & 7;
-            unsigned c_lo = (q1.x | q1.y) != 0, c_hi = (q1.z | q1.w) != 0;
-            mask |= c_lo << (16 + pl * 4 + (y >> 2) * 2);
-            mask |= c_hi << (16 + pl * 4 + (y >> 2) * 2 + 1);
-        }
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) mask |= __shfl_xor_sync(MVG_FULL, mask, s);
-
-        if (lane == 0) {
-            const uint4 m = __ldg(reinterpret_cast<const uint4 *>(p.luma_modes + mb * 16));
-            MvgMbCtl ctl;
-            ctl.w0 = (unsigned)kind | ((unsigned)p.i16_mode[mb] << 8) | ((unsigned)p.chroma_mode[mb] << 16);
-            /* pack 4 mode bytes -> 4 nibbles */
-            auto pack = [](unsigned x) {
-                return (x & 0xF) | ((x >> 4) & 0xF0) | ((x >> 8) & 0xF00) | ((x >> 12) & 0xF000);
-            };
-            ctl.w1 = pack(m.x) | (pack(m.y) << 16);
-            ctl.w2 = pack(m.z) | (pack(m.w) << 16);
-            ctl.w3 = mask;
-            *reinterpret_cast<uint4 *>(p.ctl + mb) = make_uint4(ctl.w0, ctl.w1, ctl.w2, ctl.w3);
-        }
+        /* 16 prediction modes -> 16 nibbles: OR-reduce inside each group of 8 lanes */
+        unsigned nib = (unsigned)(mode_byte & 15) << (4 * (lane & 7));
+        nib |= __shfl_xor_sync(MVG_FULL, nib, 1);
+        nib |= __shfl_xor_sync(MVG_FULL, nib, 2);
+        nib |= __shfl_xor_sync(MVG_FULL, nib, 4);
+        const unsigned w2 = __shfl_sync(MVG_FULL, nib, 8);
+        if (lane == 0) *reinterpret_cast<uint4 *>(p.ctl + mb) = make_uint4(w0, nib, w2, nzmask);
         __syncwarp();
     }
 }
@@ -308,13 +318,15 @@ k1_dequant_idct(K1Params p)
 /* Kernel 2                                                                    */
 
 struct K2Params {
-    const int16_t  *resid;      /* [slot][n_mb][384]                         */
-    const MvgMbCtl *ctl;        /* [slot][n_mb]                              */
-    uint8_t        *yuv;        /* [slot][1.5*W*H] planar I420               */
-    int            *progress;   /* [slot][h_mbs]: MBs finished in that row   */
-    int            *work;       /* work counter of this launch (starts at 0) */
+    const int16_t  *resid;      /* [slot][n_mb][384]                          */
+    const MvgMbCtl *ctl;        /* [slot][n_mb]                               */
+    uint8_t        *yuv;        /* [slot][1.5*W*H] planar I420                */
+    uint2          *halo;       /* [slot][h_mbs][w_mbs][8]: bottom sample row of every MB,
+                                   4 data bytes + 4 flag bytes per 64-bit word  */
+    int            *work;       /* work counter of this launch (starts at 0)  */
     const MvgLuts  *luts;
-    int w_mbs, h_mbs, first_slot, n_pics;
+    unsigned        epoch;      /* flag value that marks halo words of THIS launch */
+    int w_mbs, h_mbs, first_slot, n_pics, group;
 };
 
 #define K2_WARPS 4
@@ -326,15 +338,22 @@ struct K2WarpSmem {
     __align__(16) uint8_t  n8[32];
 };
 
-__device__ __forceinline__ int mvg_ld_acquire(const int *p)
+__device__ __forceinline__ uint2 mvg_ld_relaxed_u64(const uint2 *p)
 {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return make_uint2((unsigned)v, (unsigned)(v >> 32));
+}
+__device__ __forceinline__ void mvg_st_relaxed_u64(uint2 *p, unsigned lo, unsigned hi)
+{
+    const unsigned long long v = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
 /* byte sum of a 32-bit word */
 __device__ __forceinline__ int mvg_sum4(unsigned w) { return (int)__dp4a(w, 0x01010101u, 0u); }
+/* Clip1(pred + r): one VIADDMNMX */
+__device__ __forceinline__ int mvg_add_clip8(int pred, int r) { return __viaddmin_s32_relu(pred, r, 255); }
 
 /* ---- Intra16x16 luma (h264_intra_prediction.c:1945-2141) ------------------- */
 __device__ __forceinline__ void k2_luma16(K2WarpSmem &s, int lane, int mode, bool left, bool up)
@@ -382,64 +401,83 @@ __device__ __forceinline__ void k2_luma16(K2WarpSmem &s, int lane, int mode, boo
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int r0 = (short)(rr[k] & 0xffff), r1 = (int)rr[k] >> 16;
-        const unsigned p0 = (unsigned)mvg_clip8(pred[2 * k] + r0), p1 = (unsigned)mvg_clip8(pred[2 * k + 1] + r1);
+        const unsigned p0 = (unsigned)mvg_add_clip8(pred[2 * k], r0), p1 = (unsigned)mvg_add_clip8(pred[2 * k + 1], r1);
         const unsigned pk = p0 | (p1 << 8);
         if (k < 2) lo |= pk << (16 * k); else hi |= pk << (16 * (k - 2));
     }
-    __syncwarp();               /* every lane has read its neighbours */
     *reinterpret_cast<uint2 *>(lt + (y + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + x0) = make_uint2(lo, hi);
 }
 
 /* ---- Intra4x4 luma: anti-diagonal schedule, two blocks per step ------------- */
-__device__ __forceinline__ void k2_luma4(K2WarpSmem &s, const uint32_t *lut4, int lane,
-                                         unsigned long long modes, bool availA, bool availB, bool availC)
+/* Blocks with bx + 2*by == t can be predicted together: their left, up, up-left and
+ * up-right neighbours all belong to earlier steps.  Lanes 0..15 take block
+ * (t&1, t>>1), lanes 16..31 block ((t&1)+2, (t>>1)-1), one sample per lane. */
+template <int T>
+__device__ __forceinline__ void k2_luma4_step(K2WarpSmem &s, const uint32_t *lut4, int half, int pix, int pxy,
+                                              unsigned mlo, unsigned mhi, bool availA, bool availB, bool availC)
 {
+    constexpr int bx0 = (T & 1), by0 = (T >> 1), bx1 = (T & 1) + 2, by1 = (T >> 1) - 1;
+    constexpr bool v0 = by0 <= 3, v1 = by1 >= 0 && by1 <= 3;
+    constexpr int blk0 = (bx0 & 1) | ((by0 & 1) << 1) | ((bx0 >> 1) << 2) | ((by0 >> 1) << 3);
+    constexpr int blk1 = (bx1 & 1) | ((by1 & 1) << 1) | ((bx1 >> 1) << 2) | (((by1 >> 1) & 1) << 3);
     uint8_t *lt = s.lt;
-    const int half = lane >> 4, px = lane & 3, py = (lane >> 2) & 3;
-#pragma unroll 1
-    for (int t = 0; t < 10; t++) {
-        /* blocks with bx + 2*by == t: (t&1, t>>1) and ((t&1)+2, (t>>1)-1) */
-        const int bx = (t & 1) + 2 * half, by = (t >> 1) - half;
-        const bool valid = by >= 0 && by <= 3;
-        if (valid) {
-            const int blk = (bx & 1) | ((by & 1) << 1) | ((bx >> 1) << 2) | ((by >> 1) << 3);
-            const int mode = (int)((modes >> (4 * blk)) & 15);
-            const bool left = bx > 0 || availA, up = by > 0 || availB;
-            /* p[4..7,-1]: h264_intra_prediction.c:398-429 + h264_spatial.c:757-774 */
-            bool tr;
-            if (blk == 3 || blk == 11) tr = false;
-            else if (by > 0) tr = bx < 3;
-            else tr = bx < 3 ? availB : availC;
-            const int org = (by * 4 + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + bx * 4;
-            int pred;
-            if (mode == 2) {
-                int sum = 0;
-                if (up) sum += mvg_sum4(*reinterpret_cast<const unsigned *>(lt + org - MVG_LT_STRIDE));
-                if (left) sum += (int)lt[org - 1] + (int)lt[org + MVG_LT_STRIDE - 1] +
-                                 (int)lt[org + 2 * MVG_LT_STRIDE - 1] + (int)lt[org + 3 * MVG_LT_STRIDE - 1];
-                pred = (left && up) ? (sum + 4) >> 3 : (left || up) ? (sum + 2) >> 2 : 128;
-            } else {
-                const uint32_t taps = lut4[((tr ? 1 : 0) * 9 + mode) * 16 + py * 4 + px];
-                const int o0 = (int)(signed char)(taps & 255), o1 = (int)(signed char)((taps >> 8) & 255);
-                const int o2 = (int)(signed char)((taps >> 16) & 255), o3 = (int)(signed char)(taps >> 24);
-                pred = ((int)lt[org + o0] + (int)lt[org + o1] + (int)lt[org + o2] + (int)lt[org + o3] + 2) >> 2;
-            }
-            const int r = s.resid[(by * 4 + py) * 16 + bx * 4 + px];
-            lt[org + py * MVG_LT_STRIDE + px] = (uint8_t)mvg_clip8(pred + r);
+    const bool valid = half ? v1 : v0;
+    if (valid) {
+        const int bx = half ? bx1 : bx0, by = half ? by1 : by0, blk = half ? blk1 : blk0;
+        const unsigned mw = blk < 8 ? mlo : mhi;
+        const int mode = (mw >> (4 * (blk & 7))) & 15;
+        const bool left = bx > 0 || availA, up = by > 0 || availB;
+        /* p[4..7,-1]: h264_intra_prediction.c:398-429 + h264_spatial.c:757-774 */
+        bool tr;
+        if (blk == 3 || blk == 11) tr = false;
+        else if (by > 0) tr = bx < 3;
+        else tr = bx < 3 ? availB : availC;
+        const int org = (by * 4 + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + bx * 4;
+        int pred;
+        if (mode == 2) {
+            int sum = 0;
+            if (up) sum += mvg_sum4(*reinterpret_cast<const unsigned *>(lt + org - MVG_LT_STRIDE));
+            if (left) sum += (int)lt[org - 1] + (int)lt[org + MVG_LT_STRIDE - 1] +
+                             (int)lt[org + 2 * MVG_LT_STRIDE - 1] + (int)lt[org + 3 * MVG_LT_STRIDE - 1];
+            pred = (left && up) ? (sum + 4) >> 3 : (left || up) ? (sum + 2) >> 2 : 128;
+        } else {
+            const uint32_t taps = lut4[((tr ? 9 : 0) + mode) * 16 + pix];
+            const uint8_t *nb = lt + org - MVG_LUT4_BIAS;
+            pred = ((int)nb[taps & 255] + (int)nb[(taps >> 8) & 255] + (int)nb[(taps >> 16) & 255] +
+                    (int)nb[taps >> 24] + 2) >> 2;
         }
-        __syncwarp();
+        const int r = s.resid[by * 64 + bx * 4 + pxy];
+        lt[org + (pxy >> 4) * MVG_LT_STRIDE + (pxy & 3)] = (uint8_t)mvg_add_clip8(pred, r);
     }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void k2_luma4(K2WarpSmem &s, const uint32_t *lut4, int lane,
+                                         unsigned mlo, unsigned mhi, bool availA, bool availB, bool availC)
+{
+    const int half = lane >> 4, pix = lane & 15;
+    const int pxy = ((lane >> 2) & 3) * 16 + (lane & 3);      /* py*16 + px */
+    k2_luma4_step<0>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
+    k2_luma4_step<1>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
+    k2_luma4_step<2>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
+    k2_luma4_step<3>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
+    k2_luma4_step<4>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
+    k2_luma4_step<5>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
+    k2_luma4_step<6>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
+    k2_luma4_step<7>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
+    k2_luma4_step<8>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
+    k2_luma4_step<9>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
 }
 
 /* ---- Intra8x8 luma: 4 blocks in order, reference sample filter + taps -------- */
 __device__ __forceinline__ void k2_luma8(K2WarpSmem &s, const uint32_t *lut8, int lane,
-                                         unsigned long long modes, bool availA, bool availB, bool availC, bool availD)
+                                         unsigned mlo, bool availA, bool availB, bool availC, bool availD)
 {
     uint8_t *lt = s.lt;
 #pragma unroll 1
     for (int b8 = 0; b8 < 4; b8++) {
         const int xo = (b8 & 1) * 8, yo = (b8 >> 1) * 8;
-        const int mode = (int)((modes >> (4 * b8)) & 15);
+        const int mode = (int)((mlo >> (4 * b8)) & 15);
         const bool left = xo > 0 || availA, up = yo > 0 || availB;
         const bool upleft = b8 == 0 ? availD : (b8 == 1 ? availB : (b8 == 2 ? availA : true));
         const bool tr = b8 == 0 ? availB : (b8 == 1 ? availC : (b8 == 2));
@@ -481,7 +519,7 @@ __device__ __forceinline__ void k2_luma8(K2WarpSmem &s, const uint32_t *lut8, in
             const int pred = ((int)s.n8[taps & 255] + (int)s.n8[(taps >> 8) & 255] +
                               (int)s.n8[(taps >> 16) & 255] + (int)s.n8[taps >> 24] + 2) >> 2;
             const int r = s.resid[(yo + y) * 16 + xo + px];
-            lt[org + y * MVG_LT_STRIDE + px] = (uint8_t)mvg_clip8(pred + r);
+            lt[org + y * MVG_LT_STRIDE + px] = (uint8_t)mvg_add_clip8(pred, r);
         }
         __syncwarp();
     }
@@ -528,20 +566,27 @@ __device__ __forceinline__ void k2_chroma(K2WarpSmem &s, int lane, int mode, boo
         for (int k = 0; k < 4; k++) pred[k] = mvg_clip8((base + b * (x0 + k - 3)) >> 5);
     }
     const uint2 r = *reinterpret_cast<const uint2 *>(s.resid + 256 + pl * 64 + y * 8 + x0);
-    const unsigned p0 = (unsigned)mvg_clip8(pred[0] + (short)(r.x & 0xffff));
-    const unsigned p1 = (unsigned)mvg_clip8(pred[1] + ((int)r.x >> 16));
-    const unsigned p2 = (unsigned)mvg_clip8(pred[2] + (short)(r.y & 0xffff));
-    const unsigned p3 = (unsigned)mvg_clip8(pred[3] + ((int)r.y >> 16));
-    __syncwarp();
+    const unsigned p0 = (unsigned)mvg_add_clip8(pred[0], (short)(r.x & 0xffff));
+    const unsigned p1 = (unsigned)mvg_add_clip8(pred[1], (int)r.x >> 16);
+    const unsigned p2 = (unsigned)mvg_add_clip8(pred[2], (short)(r.y & 0xffff));
+    const unsigned p3 = (unsigned)mvg_add_clip8(pred[3], (int)r.y >> 16);
     *reinterpret_cast<unsigned *>(ct + (y + 1) * MVG_CT_STRIDE + MVG_CT_XOFF + x0) = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
 }
 
-/* Persistent warps; each warp claims (picture, macroblock row) items in order from
- * an atomic counter and walks the row left to right.  Row r may process macroblock
- * x once row r-1 has finished macroblock x+1 (its up-right neighbour C,
- * h264_spatial.c:371-382): progress[] carries that count with release/acquire.
- * Because items are claimed in order, the row a warp waits for was always claimed
- * earlier by a warp that is already running, so the wait cannot deadlock. */
+/* Persistent warps.  A work item is one macroblock row of one picture; a warp claims items
+ * from an atomic counter and walks its row left to right.
+ *
+ * Wavefront dependency: row r may process macroblock x once row r-1 has finished macroblock
+ * x+1 (its up-right neighbour C, h264_spatial.c:371-382).  The only samples that cross rows are
+ * the bottom sample line of the macroblocks above, so a finished macroblock publishes that
+ * line (16 Y + 8 Cb + 8 Cr bytes) as eight 64-bit words {4 data bytes, launch epoch} -- the
+ * flag travels with the data, every word validates itself, and neither side needs a fence or
+ * a separate progress counter.  The row below spins only on words whose epoch is stale.
+ *
+ * Claim order: pictures are taken in groups of `group`; inside a group items are ordered
+ * row-major over (row, picture).  Row r-1 of a picture is therefore always claimed before row
+ * r (no deadlock: it runs on a resident warp), and `group` items earlier, so in steady state
+ * it is many macroblocks ahead and the spin is rarely entered. */
 __global__ void __launch_bounds__(K2_WARPS * 32, 8)
 k2_wavefront(K2Params p)
 {
@@ -559,32 +604,53 @@ k2_wavefront(K2Params p)
     const int ystride = W * 16, cstride = W * 8;
     const size_t pic_bytes = (size_t)n_mb * 384;
     const int total = p.n_pics * H;
+    const unsigned epoch = p.epoch;
+
+    /* byte offset inside the tiles of the halo word this lane carries (lanes 0..7) */
+    const int halo_pl = lane < 4 ? -1 : ((lane - 4) >> 1);
+    const int halo_x = lane < 4 ? lane * 4 : ((lane - 4) & 1) * 4;
 
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(p.work, 1);
         item = __shfl_sync(MVG_FULL, item, 0);
         if (item >= total) break;
-        const int slot = p.first_slot + item / H, row = item % H;
+        const int g = item / (p.group * H);
+        const int gsize = min(p.group, p.n_pics - g * p.group);
+        const int within = item - g * p.group * H;
+        const int row = within / gsize;
+        const int slot = p.first_slot + g * p.group + (within - row * gsize);
+
         uint8_t *ybase = p.yuv + (size_t)slot * pic_bytes;
         uint8_t *cbbase = ybase + (size_t)n_mb * 256, *crbase = cbbase + (size_t)n_mb * 64;
         const int16_t *resid = p.resid + ((size_t)slot * n_mb + (size_t)row * W) * 384;
         const MvgMbCtl *ctl = p.ctl + (size_t)slot * n_mb + (size_t)row * W;
-        const int *above = p.progress + (size_t)slot * H + row - 1;
-        int *mine = p.progress + (size_t)slot * H + row;
-        const bool availB = row > 0;
+        const bool availB = row > 0, publish = row < H - 1;
+        const uint2 *habove = p.halo + ((size_t)slot * n_mb + (size_t)(row - 1) * W) * 8 + lane;
+        uint2 *hmine = p.halo + ((size_t)slot * n_mb + (size_t)row * W) * 8 + lane;
 
         /* prefetch the first macroblock's inputs */
         uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(resid) + lane);
         uint4 r1 = make_uint4(0, 0, 0, 0);
         if (lane < 16) r1 = __ldg(reinterpret_cast<const uint4 *>(resid) + 32 + lane);
         uint4 c4 = __ldg(reinterpret_cast<const uint4 *>(ctl));
-        int seen = 0;
+        /* halo words of the row above: cur = macroblock mx, nxt = macroblock mx+1 */
+        uint2 cur = make_uint2(0, 0), nxt = make_uint2(0, 0);
+        if (availB && lane < 8) {
+            cur = mvg_ld_relaxed_u64(habove);
+            if (W > 1) nxt = mvg_ld_relaxed_u64(habove + 8);
+        }
+        if (availB) {
+            while (!__all_sync(MVG_FULL, lane >= 8 || cur.y == epoch)) {
+                __nanosleep(200);
+                if (lane < 8) cur = mvg_ld_relaxed_u64(habove);
+            }
+        }
 
         for (int mx = 0; mx < W; mx++) {
             reinterpret_cast<uint4 *>(s.resid)[lane] = r0;
             if (lane < 16) reinterpret_cast<uint4 *>(s.resid)[32 + lane] = r1;
-            const uint4 cur = c4;
+            const uint4 ctlw = c4;
             if (mx + 1 < W) {       /* software pipeline: next macroblock's loads fly during this one */
                 const uint4 *nr = reinterpret_cast<const uint4 *>(resid + (size_t)(mx + 1) * 384);
                 r0 = __ldg(nr + lane);
@@ -594,32 +660,28 @@ k2_wavefront(K2Params p)
             const bool availA = mx > 0, availC = availB && mx < W - 1, availD = availA && availB;
 
             if (availB) {
-                const int need = min(mx + 2, W);
-                while (seen < need) {
-                    seen = mvg_ld_acquire(above);
-                    if (seen < need) __nanosleep(100);
+                if (availC) {       /* the up-right macroblock must have been published */
+                    while (!__all_sync(MVG_FULL, lane >= 8 || nxt.y == epoch)) {
+                        __nanosleep(200);
+                        if (lane < 8) nxt = mvg_ld_relaxed_u64(habove + (size_t)(mx + 1) * 8);
+                    }
                 }
-                /* row -1 of the tiles: samples written by the warp that owns row-1 */
-                const uint8_t *ytop = ybase + (size_t)(row * 16 - 1) * ystride + mx * 16;
-                if (lane < 25) {
-                    const int x = lane - 1;
-                    if ((x >= 0 || availA) && (x < 16 || availC))
-                        s.lt[MVG_LT_XOFF + x] = __ldcg(ytop + x);
+                /* sample row -1 of the tiles: x = 0..15 from cur, x = 16..23 from nxt */
+                if (lane < 4) {
+                    *reinterpret_cast<unsigned *>(s.lt + MVG_LT_XOFF + halo_x) = cur.x;
+                    if (lane < 2) *reinterpret_cast<unsigned *>(s.lt + MVG_LT_XOFF + 16 + halo_x) = nxt.x;
+                } else if (lane < 8) {
+                    *reinterpret_cast<unsigned *>(s.ct[halo_pl] + MVG_CT_XOFF + halo_x) = cur.x;
                 }
-                const int cl = lane & 15;
-                if (cl < 9) {
-                    const int x = cl - 1;
-                    const uint8_t *ctop = (lane < 16 ? cbbase : crbase) + (size_t)(row * 8 - 1) * cstride + mx * 8;
-                    if (x >= 0 || availA) s.ct[lane >> 4][MVG_CT_XOFF + x] = __ldcg(ctop + x);
-                }
+                cur = nxt;
+                if (mx + 2 < W && lane < 8) nxt = mvg_ld_relaxed_u64(habove + (size_t)(mx + 2) * 8);
             }
             __syncwarp();
 
-            const int kind = cur.x & 255, i16 = (cur.x >> 8) & 255, cmode = (cur.x >> 16) & 255;
-            const unsigned long long modes = (unsigned long long)cur.y | ((unsigned long long)cur.z << 32);
+            const int kind = ctlw.x & 255, i16 = (ctlw.x >> 8) & 255, cmode = (ctlw.x >> 16) & 255;
             if (kind == MVG_MB_I16x16)    k2_luma16(s, lane, i16, availA, availB);
-            else if (kind == MVG_MB_I4x4) k2_luma4(s, s_lut4, lane, modes, availA, availB, availC);
-            else                          k2_luma8(s, s_lut8, lane, modes, availA, availB, availC, availD);
+            else if (kind == MVG_MB_I4x4) k2_luma4(s, s_lut4, lane, ctlw.y, ctlw.z, availA, availB, availC);
+            else                          k2_luma8(s, s_lut8, lane, ctlw.y, availA, availB, availC, availD);
             k2_chroma(s, lane, cmode, availA, availB);
             __syncwarp();
 
@@ -633,15 +695,18 @@ k2_wavefront(K2Params p)
                 const uint2 a = *reinterpret_cast<const uint2 *>(s.ct[pl] + (y + 1) * MVG_CT_STRIDE + MVG_CT_XOFF);
                 *reinterpret_cast<uint2 *>((pl ? crbase : cbbase) + (size_t)(row * 8 + y) * cstride + mx * 8) = a;
             }
-            /* left column for the next macroblock: x = 15 -> x = -1 (rows 0..15; chroma x = 7) */
-            if (lane < 16) s.lt[(lane + 1) * MVG_LT_STRIDE + MVG_LT_XOFF - 1] = s.lt[(lane + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + 15];
-            else {
-                const int pl = (lane >> 3) & 1, y = lane & 7;
-                s.ct[pl][(y + 1) * MVG_CT_STRIDE + MVG_CT_XOFF - 1] = s.ct[pl][(y + 1) * MVG_CT_STRIDE + MVG_CT_XOFF + 7];
+            /* publish the bottom sample line for the row below */
+            if (publish && lane < 8) {
+                const unsigned d = lane < 4
+                    ? *reinterpret_cast<const unsigned *>(s.lt + 16 * MVG_LT_STRIDE + MVG_LT_XOFF + halo_x)
+                    : *reinterpret_cast<const unsigned *>(s.ct[halo_pl] + 8 * MVG_CT_STRIDE + MVG_CT_XOFF + halo_x);
+                mvg_st_relaxed_u64(hmine + (size_t)mx * 8, d, epoch);
             }
-            __threadfence();
+            /* next macroblock: x = 15 becomes x = -1 (luma rows -1..15, chroma x = 7, rows -1..7) */
+            if (lane < 17) s.lt[lane * MVG_LT_STRIDE + MVG_LT_XOFF - 1] = s.lt[lane * MVG_LT_STRIDE + MVG_LT_XOFF + 15];
+            else if (lane < 26) s.ct[0][(lane - 17) * MVG_CT_STRIDE + MVG_CT_XOFF - 1] = s.ct[0][(lane - 17) * MVG_CT_STRIDE + MVG_CT_XOFF + 7];
+            if (lane < 9) s.ct[1][lane * MVG_CT_STRIDE + MVG_CT_XOFF - 1] = s.ct[1][lane * MVG_CT_STRIDE + MVG_CT_XOFF + 7];
             __syncwarp();
-            if (lane == 0) *reinterpret_cast<volatile int *>(mine) = mx + 1;
         }
     }
 }
