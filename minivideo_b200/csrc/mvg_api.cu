@@ -23,7 +23,7 @@ static char g_create_error[512] = "";
 
 #define MVG_PIPE_DEPTH 3       /* slot regions used by mvg_decode_host */
 #define MVG_WORK_RING  64      /* work counters, one per kernel-2 launch in flight */
-#define MVG_K2_GROUP   512     /* pictures interleaved row by row in kernel 2's claim order */
+#define MVG_K2_GROUP   1024    /* pictures interleaved row by row in kernel 2's claim order */
 
 struct mvg_ctx {
     int device = -1, sm_count = 0;
@@ -331,6 +331,12 @@ extern "C" int mvg_set_sps(mvg_ctx *ctx, int width_mbs, int height_mbs,
     memset(&t, 0, sizeof t);
     memcpy(t.ls4, level_scale4x4, sizeof t.ls4);
     memcpy(t.ls8, level_scale8x8, sizeof t.ls8);
+    for (int c = 0; c < 3; c++)
+        for (int qp = 0; qp < 52; qp++)
+            for (int k = 0; k < 16; k++) {
+                const int32_t v = t.ls4[c][qp % 6][k];
+                t.ls4q[c][qp][k] = qp > 23 ? (int32_t)((uint32_t)v << (qp / 6 - 4)) : v;
+            }
     uint8_t zz8[64];
     zigzag(8, zz8);
     for (int k = 0; k < 64; k++) t.zz8inv[zz8[k]] = (uint8_t)k;
@@ -461,7 +467,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         K3Params p;
         p.yuv = ctx->d_yuv; p.rgb = ctx->d_rgb; p.width = width; p.height = height; p.scale = rgb_scale;
         p.first_slot = first_slot; p.n_pics = n_pics;
-        const long long threads = rgb_scale == 1 ? (long long)(width / 16) * height * n_pics
+        const long long threads = rgb_scale == 1 ? (long long)(width / 16) * (height / 2) * n_pics
                                                  : (long long)(width / rgb_scale) * (height / rgb_scale) * n_pics;
         const int grid = (int)std::min<long long>((threads + 255) / 256, (long long)ctx->sm_count * 32);
         if (rgb_scale == 1) k3_rgb_full<<<grid, 256, 0, st>>>(p);

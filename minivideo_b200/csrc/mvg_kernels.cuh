@@ -30,6 +30,7 @@
 
 struct MvgTables {
     int32_t ls4[3][6][16];      /* LevelScale4x4[c][q][i*4+j] */
+    int32_t ls4q[3][52][16];    /* per qP: LevelScale4x4[c][qP%6] << (qP/6-4) when qP >= 24, else unshifted */
     int32_t ls8[6][64];         /* LevelScale8x8[0][q][i*8+j] */
     uint8_t zz8inv[64];         /* zz8inv[row*8+col] = zig-zag index k of that position */
     int32_t cb_qp_offset, cr_qp_offset;
@@ -119,11 +120,7 @@ k1_dequant_idct(K1Params p)
     __shared__ __align__(16) int16_t s_out[K1_WARPS][384];     /* residual, raster                */
 
     for (int i = threadIdx.x; i < 3 * 6 * 16; i += blockDim.x) s_ls4[i] = (&p.tab->ls4[0][0][0])[i];
-    for (int i = threadIdx.x; i < 3 * 52 * 16; i += blockDim.x) {
-        const int k = i & 15, qp = (i >> 4) % 52, c = (i >> 4) / 52;
-        const int v = p.tab->ls4[c][qp % 6][k];
-        s_ls4q[i] = qp > 23 ? (int)((unsigned)v << (qp / 6 - 4)) : v;
-    }
+    for (int i = threadIdx.x; i < 3 * 52 * 16; i += blockDim.x) s_ls4q[i] = (&p.tab->ls4q[0][0][0])[i];
     for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) s_ls8[i] = (&p.tab->ls8[0][0])[i];
     if (threadIdx.x < 64) s_zz8inv[threadIdx.x] = p.tab->zz8inv[threadIdx.x];
     const int cb_off = p.tab->cb_qp_offset, cr_off = p.tab->cr_qp_offset;
@@ -145,22 +142,30 @@ k1_dequant_idct(K1Params p)
         dst = out + 256 + pl * 64 + ((b >> 1) * 4) * 8 + (b & 1) * 4; dst_stride = 8;
     }
 
+    /* per-MB side information, one byte per lane: lanes 0..15 luma modes, 16 mb_kind,
+     * 17 Intra16x16PredMode, 18 intra_chroma_pred_mode, 19 QPY */
+    const uint8_t *meta_src = lane < 16 ? p.luma_modes + lane
+                            : lane == 16 ? p.mb_kind : lane == 17 ? p.i16_mode
+                            : lane == 18 ? p.chroma_mode : reinterpret_cast<const uint8_t *>(p.qp_y);
+    const long long meta_stride = lane < 16 ? 16 : 1;
     long long mb = (long long)blockIdx.x * K1_WARPS + w;
     uint4 na = make_uint4(0, 0, 0, 0), nb = na;
-    int nkind = 0, nqp = 0;
+    int nmeta = 0;
     if (mb < p.n_mbs) {
         if (lane < 24) {
             const uint4 *src = reinterpret_cast<const uint4 *>(p.coeff + mb * 384 + lane * 16);
             na = __ldg(src); nb = __ldg(src + 1);
         }
-        nkind = p.mb_kind[mb]; nqp = p.qp_y[mb];
+        if (lane < 20) nmeta = __ldg(meta_src + mb * meta_stride);
     }
 
     for (; mb < p.n_mbs; mb += n_warps) {
         const uint4 a = na, b = nb;
-        const int kind = nkind, qp = nqp;
-        const int mode_byte = lane < 16 ? p.luma_modes[mb * 16 + lane] : 0;
-        const unsigned w0 = (unsigned)kind | ((unsigned)p.i16_mode[mb] << 8) | ((unsigned)p.chroma_mode[mb] << 16);
+        const int mode_byte = nmeta;
+        const int kind = __shfl_sync(MVG_FULL, nmeta, 16);
+        const int qp = (signed char)__shfl_sync(MVG_FULL, nmeta, 19);
+        const unsigned w0 = (unsigned)kind | ((unsigned)__shfl_sync(MVG_FULL, nmeta, 17) << 8) |
+                            ((unsigned)__shfl_sync(MVG_FULL, nmeta, 18) << 16);
         {   /* prefetch the next macroblock of this warp */
             const long long nx = mb + n_warps;
             if (nx < p.n_mbs) {
@@ -168,7 +173,7 @@ k1_dequant_idct(K1Params p)
                     const uint4 *src = reinterpret_cast<const uint4 *>(p.coeff + nx * 384 + lane * 16);
                     na = __ldg(src); nb = __ldg(src + 1);
                 }
-                nkind = p.mb_kind[nx]; nqp = p.qp_y[nx];
+                if (lane < 20) nmeta = __ldg(meta_src + nx * meta_stride);
             }
         }
 
@@ -304,7 +309,7 @@ k1_dequant_idct(K1Params p)
         if (lane < 16) gout[32 + lane] = sout[32 + lane];
 
         /* 16 prediction modes -> 16 nibbles: OR-reduce inside each group of 8 lanes */
-        unsigned nib = (unsigned)(mode_byte & 15) << (4 * (lane & 7));
+        unsigned nib = lane < 16 ? (unsigned)(mode_byte & 15) << (4 * (lane & 7)) : 0u;
         nib |= __shfl_xor_sync(MVG_FULL, nib, 1);
         nib |= __shfl_xor_sync(MVG_FULL, nib, 2);
         nib |= __shfl_xor_sync(MVG_FULL, nib, 4);
@@ -641,8 +646,10 @@ k2_wavefront(K2Params p)
             if (W > 1) nxt = mvg_ld_relaxed_u64(habove + 8);
         }
         if (availB) {
+            unsigned ns = 64;
             while (!__all_sync(MVG_FULL, lane >= 8 || cur.y == epoch)) {
-                __nanosleep(200);
+                __nanosleep(ns);
+                if (ns < 2048) ns *= 2;
                 if (lane < 8) cur = mvg_ld_relaxed_u64(habove);
             }
         }
@@ -661,8 +668,10 @@ k2_wavefront(K2Params p)
 
             if (availB) {
                 if (availC) {       /* the up-right macroblock must have been published */
+                    unsigned ns = 64;
                     while (!__all_sync(MVG_FULL, lane >= 8 || nxt.y == epoch)) {
-                        __nanosleep(200);
+                        __nanosleep(ns);
+                        if (ns < 2048) ns *= 2;
                         if (lane < 8) nxt = mvg_ld_relaxed_u64(habove + (size_t)(mx + 1) * 8);
                     }
                 }
@@ -729,47 +738,66 @@ __device__ __forceinline__ void mvg_ycc_to_rgb(int Y, int Cb, int Cr, int &R, in
     B = mvg_clip8(t + ((516 * Cb) >> 8) - 276);
 }
 
-/* scale 1: one thread converts 16 horizontally adjacent samples: 16 B of Y, 8 B of Cb
- * and Cr in, 48 B of RGB24 out as three 128-bit stores. */
+/* scale 1: one thread converts a 16 x 2 sample patch: 2 x 16 B of Y, 8 B of Cb and of Cr in
+ * (each chroma sample covers a 2 x 2 patch, export_utils.c:278-279), 2 x 48 B of RGB24 out as
+ * 128-bit stores.  The chroma contributions are computed once per chroma sample. */
 __global__ void __launch_bounds__(256)
 k3_rgb_full(K3Params p)
 {
-    const int groups_per_row = p.width >> 4;
-    const long long per_pic = (long long)groups_per_row * p.height;
+    const int groups_per_row = p.width >> 4, row_pairs = p.height >> 1;
+    const long long per_pic = (long long)groups_per_row * row_pairs;
     const long long total = per_pic * p.n_pics;
     const size_t ysz = (size_t)p.width * p.height;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
         const int pic = (int)(g / per_pic);
-        const long long rem = g - (long long)pic * per_pic;
-        const int y = (int)(rem / groups_per_row), gx = (int)(rem - (long long)y * groups_per_row);
+        const int rem = (int)(g - (long long)pic * per_pic);
+        const int yp = rem / groups_per_row, gx = rem - yp * groups_per_row;
         const size_t slot = (size_t)(p.first_slot + pic);
         const uint8_t *Y = p.yuv + slot * (ysz * 3 / 2);
         const uint8_t *Cb = Y + ysz, *Cr = Cb + ysz / 4;
-        const uint4 yy = __ldg(reinterpret_cast<const uint4 *>(Y + (size_t)y * p.width + gx * 16));
-        const size_t coff = (size_t)(y >> 1) * (p.width >> 1) + gx * 8;
+        const uint8_t *yrow = Y + (size_t)(2 * yp) * p.width + gx * 16;
+        const uint4 y0 = __ldg(reinterpret_cast<const uint4 *>(yrow));
+        const uint4 y1 = __ldg(reinterpret_cast<const uint4 *>(yrow + p.width));
+        const size_t coff = (size_t)yp * (p.width >> 1) + gx * 8;
         const uint2 cb = __ldg(reinterpret_cast<const uint2 *>(Cb + coff));
         const uint2 cr = __ldg(reinterpret_cast<const uint2 *>(Cr + coff));
-        const unsigned yw[4] = {yy.x, yy.y, yy.z, yy.w};
+        const unsigned yw[2][4] = {{y0.x, y0.y, y0.z, y0.w}, {y1.x, y1.y, y1.z, y1.w}};
         const unsigned cbw[2] = {cb.x, cb.y}, crw[2] = {cr.x, cr.y};
-        unsigned out[12];
+        unsigned out[2][12];
 #pragma unroll
-        for (int k = 0; k < 12; k++) out[k] = 0;
+        for (int r = 0; r < 2; r++)
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const int Yv = (yw[i >> 2] >> (8 * (i & 3))) & 255;
-            const int ci = i >> 1;                      /* 2x2 replication, export_utils.c:278-279 */
+            for (int k = 0; k < 12; k++) out[r][k] = 0;
+#pragma unroll
+        for (int ci = 0; ci < 8; ci++) {
             const int Cbv = (cbw[ci >> 2] >> (8 * (ci & 3))) & 255, Crv = (crw[ci >> 2] >> (8 * (ci & 3))) & 255;
-            int R, G, B;
-            mvg_ycc_to_rgb(Yv, Cbv, Crv, R, G, B);
-            const int b0 = 3 * i, b1 = 3 * i + 1, b2 = 3 * i + 2;
-            out[b0 >> 2] |= (unsigned)R << (8 * (b0 & 3));
-            out[b1 >> 2] |= (unsigned)G << (8 * (b1 & 3));
-            out[b2 >> 2] |= (unsigned)B << (8 * (b2 & 3));
+            /* export_utils.c:300-302, the terms that do not depend on Y */
+            const int rC = ((408 * Crv) >> 8) - 222;
+            const int gC = 135 - ((100 * Cbv) >> 8) - ((208 * Crv) >> 8);
+            const int bC = ((516 * Cbv) >> 8) - 276;
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int i = 2 * ci + h;
+                    const int Yv = (yw[r][i >> 2] >> (8 * (i & 3))) & 255;
+                    const int t = (298 * Yv) >> 8;
+                    const unsigned R = (unsigned)__viaddmin_s32_relu(t, rC, 255);
+                    const unsigned G = (unsigned)__viaddmin_s32_relu(t, gC, 255);
+                    const unsigned B = (unsigned)__viaddmin_s32_relu(t, bC, 255);
+                    const int b0 = 3 * i, b1 = 3 * i + 1, b2 = 3 * i + 2;
+                    out[r][b0 >> 2] |= R << (8 * (b0 & 3));
+                    out[r][b1 >> 2] |= G << (8 * (b1 & 3));
+                    out[r][b2 >> 2] |= B << (8 * (b2 & 3));
+                }
         }
-        uint4 *dst = reinterpret_cast<uint4 *>(p.rgb + slot * (ysz * 3) + ((size_t)y * p.width + gx * 16) * 3);
-        dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
-        dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
-        dst[2] = make_uint4(out[8], out[9], out[10], out[11]);
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            uint4 *dst = reinterpret_cast<uint4 *>(p.rgb + slot * (ysz * 3) + ((size_t)(2 * yp + r) * p.width + gx * 16) * 3);
+            dst[0] = make_uint4(out[r][0], out[r][1], out[r][2], out[r][3]);
+            dst[1] = make_uint4(out[r][4], out[r][5], out[r][6], out[r][7]);
+            dst[2] = make_uint4(out[r][8], out[r][9], out[r][10], out[r][11]);
+        }
     }
 }
 
