@@ -261,7 +261,7 @@ def run_ours(args):
         tfile = ROOT / "profiles" / "ncu_traffic.json"
         if tfile.exists():
             try:
-                traffic = json.loads(tfile.read_text()).get(dom, {}).get("dram_bytes_per_launch")
+                traffic = json.loads(tfile.read_text())["per_picture_dram_bytes"][dom] * F
             except Exception:
                 traffic = None
         kernels = {k: {"ms_per_launch": mean_ms[k], "algorithmic_bytes": ab[k] * F,
