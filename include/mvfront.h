@@ -1,0 +1,80 @@
+/*
+ * mvfront.h -- host front end of the intra reconstruction path (libmvfront.so).
+ *
+ * Written from scratch in C: Annex-B elementary-stream scan, NAL unescape, SPS / PPS /
+ * slice header, CAVLC macroblock parsing -> the structure-of-arrays of mvgpu.h, one IDR
+ * slice per thread.  It replaces, for this path only, what the reference does on the way
+ * to its per-macroblock hot-path call (citations relative to minivideo/src/):
+ *
+ *   es_fileParse()            demuxer/esparser/esparser.c:40     -> mvf_open_annexb()
+ *   idr_filtering()           demuxer/filter.c:52                -> mvf_select_idr()
+ *   nalu_clean_sample()       decoder/h264/h264_nalu.c:195       -> (inside) NAL unescape
+ *   decodeSPS()/decodePPS()   decoder/h264/h264_parameterset.c:123,:812
+ *   decodeSliceHeader()       decoder/h264/h264_slice.c:156
+ *   macroblock_layer() parse half, mb_pred(), residual_luma/chroma()
+ *                             decoder/h264/h264_macroblock.c:75-313,:393,:1102,:1222
+ *   residual_block_cavlc()    decoder/h264/h264_cavlc.c:79
+ *   Intra_4x4/8x8_deriv_PredMode()  decoder/h264/h264_intra_prediction.c:196,:977
+ *
+ * Return codes as in mvgpu.h (MVG_SUCCESS 1 / MVG_FAILURE 0 / MVG_UNSUPPORTED -1); never
+ * exits.  Supported: what the reference supports for this path -- Baseline/Main/High 4:2:0
+ * 8-bit, frame_mbs_only, CAVLC, one I slice per IDR picture, SPS scaling lists.
+ * Unsupported (MVG_UNSUPPORTED): CABAC, I_PCM, FMO/ASO, interlace, PPS scaling lists.
+ */
+#ifndef MVFRONT_H
+#define MVFRONT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "mvgpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mvf_stream mvf_stream;
+
+typedef struct mvf_info {
+    int32_t width_mbs, height_mbs;      /* PicWidthInMbs, PicHeightInMapUnits (frame_mbs_only) */
+    int32_t profile_idc, level_idc;
+    int32_t n_idr;                      /* IDR slice NAL units found                            */
+    int32_t transform_8x8_mode;
+    int32_t cb_qp_offset, cr_qp_offset; /* chroma_qp_index_offset, second_chroma_qp_index_offset */
+    int32_t pic_init_qp;
+    int32_t crop_left, crop_right, crop_top, crop_bottom;   /* parsed, never applied (export.c:80-81) */
+    int32_t level_scale4x4[3 * 6 * 16]; /* ready for mvg_set_sps()                              */
+    int32_t level_scale8x8[6 * 64];
+} mvf_info;
+
+/* Writable twin of mvg_batch: the caller allocates the arrays (pinned memory from
+ * mvg_host_alloc() for full PCIe speed) for `n_pics` pictures. */
+typedef struct mvf_batch {
+    int32_t  n_pics;
+    uint8_t *mb_kind, *i16_mode, *chroma_mode;
+    int8_t  *qp_y;
+    uint8_t *cbp, *luma_modes;
+    int16_t *coeff;
+} mvf_batch;
+
+/* Scan an Annex-B byte stream held in memory (it must stay valid until mvf_close), parse the
+ * first SPS and PPS, index the IDR slices. */
+int mvf_open_annexb(const uint8_t *data, size_t len, mvf_stream **out);
+int mvf_close(mvf_stream *s);
+const char *mvf_last_error(const mvf_stream *s);      /* s may be NULL after a failed open */
+int mvf_get_info(const mvf_stream *s, mvf_info *out);
+
+/* Frame selection, the work-list builder for the GPUs: mirrors idr_filtering()
+ * (demuxer/filter.c:52-215).  mode 0 = unfiltered (first n), 1 = ordered, 2 = distributed.
+ * Writes at most `n_wanted` IDR indices (0-based among the IDR slices) and returns how many. */
+int mvf_select_idr(const mvf_stream *s, int n_wanted, int mode, int32_t *indices);
+
+/* CAVLC-parse `count` IDR pictures given by `indices` (NULL = first, first+1, ...) into `out`
+ * using up to `n_threads` host threads (one slice per thread). */
+int mvf_parse_pictures(mvf_stream *s, const int32_t *indices, int first, int count,
+                       mvf_batch *out, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -49,20 +49,20 @@ def _run(cmd: list[str], log: Path | None = None) -> None:
 
 def build_synth(force: bool = False) -> Path:
     out = PKG / "libmvsynth.so"
-    src = [CSRC / "h264_synth.c", INC / "mvsynth.h"]
+    src = [CSRC / "h264_synth.c", INC / "mvsynth.h", CSRC / "h264_cavlc_tables.h"]
     if force or _stale(out, src):
-        _run(["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", f"-I{INC}",
+        _run(["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", f"-I{INC}", f"-I{CSRC}",
               "-o", str(out), str(src[0]), "-lm"])
     return out
 
 
 def build_front(force: bool = False) -> Path | None:
     out = PKG / "libmvfront.so"
-    src = [CSRC / "h264_front.c", INC / "mvfront.h", INC / "mvgpu.h"]
+    src = [CSRC / "h264_front.c", INC / "mvfront.h", INC / "mvgpu.h", CSRC / "h264_cavlc_tables.h"]
     if not src[0].exists():
         return None
     if force or _stale(out, src):
-        _run(["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", f"-I{INC}",
+        _run(["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", f"-I{INC}", f"-I{CSRC}",
               "-o", str(out), str(src[0]), "-lm", "-lpthread"])
     return out
 

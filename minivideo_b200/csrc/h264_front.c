@@ -1,0 +1,734 @@
+/*
+ * h264_front.c -- host front end: Annex-B / SPS / PPS / slice header / CAVLC -> mvgpu.h SoA.
+ * See include/mvfront.h for the interface and the reference functions it stands in for.
+ * Written from ITU-T H.264 (clauses 7.3, 7.4, 8.3.1.1, 8.3.2.1, 9.1, 9.2); comments name the
+ * reference lines whose observable behaviour matters for drop-in parity.
+ */
+#define _GNU_SOURCE
+#include "mvfront.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "h264_cavlc_tables.h"
+
+/* ------------------------------------------------------------------------ */
+/* CAVLC decode look-up tables, built once from the (length, code) tables     */
+
+static uint16_t lut_ct[3][1 << 16];      /* len<<7 | TotalCoeff<<2 | TrailingOnes, indexed by next 16 bits */
+static uint16_t lut_ctc[1 << 8];         /* chroma DC coeff_token, next 8 bits                             */
+static uint8_t  lut_tz4[15][1 << 9];     /* len<<4 | total_zeros, next 9 bits                              */
+static uint8_t  lut_tz2[3][1 << 3];
+static uint8_t  lut_run[7][1 << 11];     /* len<<4 | run_before, next 11 bits                              */
+static uint8_t  cbp_from_codenum[48];
+static uint8_t  zz4[16], zz8[64];
+static pthread_once_t lut_once = PTHREAD_ONCE_INIT;
+
+static void fill16(uint16_t *lut, int bits, int len, unsigned code, uint16_t val)
+{
+    if (!len) return;
+    unsigned lo = code << (bits - len), n = 1u << (bits - len);
+    for (unsigned i = 0; i < n; i++) lut[lo + i] = val;
+}
+static void fill8s(uint8_t *lut, int bits, const char *str, int sym)
+{
+    int len = (int)strlen(str);
+    unsigned code = 0;
+    for (int i = 0; i < len; i++) code = (code << 1) | (unsigned)(str[i] == '1');
+    unsigned lo = code << (bits - len), n = 1u << (bits - len);
+    for (unsigned i = 0; i < n; i++) lut[lo + i] = (uint8_t)(len << 4 | sym);
+}
+static void zigzag_build(int n, uint8_t *zz)
+{
+    int r = 0, c = 0, up = 1;
+    for (int k = 0; k < n * n; k++) {
+        zz[k] = (uint8_t)(r * n + c);
+        if (up) { if (c == n - 1) { r++; up = 0; } else if (r == 0) { c++; up = 0; } else { r--; c++; } }
+        else    { if (r == n - 1) { c++; up = 1; } else if (c == 0) { r++; up = 1; } else { r++; c--; } }
+    }
+}
+static void build_luts(void)
+{
+    for (int t = 0; t < 3; t++)
+        for (int t1 = 0; t1 < 4; t1++)
+            for (int tc = t1; tc <= 16; tc++)
+                fill16(lut_ct[t], 16, ct_len[t][t1][tc], ct_code[t][t1][tc], (uint16_t)(ct_len[t][t1][tc] << 7 | tc << 2 | t1));
+    for (int t1 = 0; t1 < 4; t1++)
+        for (int tc = t1; tc <= 4; tc++)
+            fill16(lut_ctc, 8, ctc_len[t1][tc], ctc_code[t1][tc], (uint16_t)(ctc_len[t1][tc] << 7 | tc << 2 | t1));
+    for (int tc = 1; tc <= 15; tc++)
+        for (int tz = 0; tz <= 16 - tc; tz++) fill8s(lut_tz4[tc - 1], 9, tz4x4[tc - 1][tz], tz);
+    for (int tc = 1; tc <= 3; tc++)
+        for (int tz = 0; tz <= 4 - tc; tz++) fill8s(lut_tz2[tc - 1], 3, tz2x2[tc - 1][tz], tz);
+    for (int zl = 1; zl <= 7; zl++)
+        for (int run = 0; run <= (zl < 7 ? zl : 14); run++) fill8s(lut_run[zl - 1], 11, runb[zl - 1][run], run);
+    for (int k = 0; k < 48; k++) cbp_from_codenum[k] = cbp_intra_by_codenum[k];
+    zigzag_build(4, zz4); zigzag_build(8, zz8);
+}
+
+/* ------------------------------------------------------------------------ */
+/* bit reader over an unescaped RBSP (8 zero bytes of padding behind it)      */
+
+typedef struct { const uint8_t *p; size_t pos, nbits; } br_t;
+
+static inline uint32_t br_peek(const br_t *b, int n)      /* n <= 25 */
+{
+    const uint8_t *q = b->p + (b->pos >> 3);
+    uint32_t w = (uint32_t)q[0] << 24 | (uint32_t)q[1] << 16 | (uint32_t)q[2] << 8 | q[3];
+    return (w << (b->pos & 7)) >> (32 - n);
+}
+static inline void br_skip(br_t *b, int n) { b->pos += (size_t)n; }
+static inline uint32_t br_get(br_t *b, int n)
+{
+    if (n == 0) return 0;
+    uint32_t v;
+    if (n <= 25) { v = br_peek(b, n); b->pos += (size_t)n; return v; }
+    v = br_peek(b, 16); b->pos += 16;
+    v = (v << (n - 16)) | br_peek(b, n - 16); b->pos += (size_t)(n - 16);
+    return v;
+}
+static inline int br_bit(br_t *b) { return (int)br_get(b, 1); }
+static uint32_t br_ue(br_t *b)
+{
+    int z = 0;
+    while (z < 32 && b->pos < b->nbits + 64 && br_peek(b, 1) == 0) { z++; b->pos++; }
+    b->pos++;
+    if (z == 0) return 0;
+    if (z >= 32) return 0xffffffffu;
+    return (1u << z) - 1 + br_get(b, z);
+}
+static int br_se(br_t *b)
+{
+    uint32_t k = br_ue(b);
+    return (k & 1) ? (int)((k + 1) >> 1) : -(int)(k >> 1);
+}
+static inline int br_overrun(const br_t *b) { return b->pos > b->nbits; }
+
+/* ------------------------------------------------------------------------ */
+
+typedef struct { size_t off, size; int type; } nal_t;     /* off: NAL header byte */
+
+typedef struct {
+    int valid, profile_idc, level_idc, chroma_format_idc;
+    int log2_max_frame_num, poc_type, log2_max_poc_lsb, delta_pic_order_always_zero;
+    int width_mbs, height_mbs, frame_mbs_only;
+    int crop[4];
+    uint8_t list4[6][16], list8[2][64];                     /* zig-zag order */
+} sps_t;
+
+typedef struct {
+    int valid, entropy_cabac, bottom_field_poc_present, init_qp, cb_off, cr_off;
+    int deblocking_control, constrained_intra, redundant_pic_cnt, transform8x8;
+} pps_t;
+
+struct mvf_stream {
+    const uint8_t *data; size_t len;
+    nal_t *nals; int n_nals;
+    int *idr; int n_idr;                                    /* indices into nals[] */
+    int n_param_nals;
+    sps_t sps; pps_t pps;
+    char err[256];
+};
+
+static char g_open_error[256];
+
+static int sfail(mvf_stream *s, int code, const char *fmt, ...)
+{
+    char *dst = s ? s->err : g_open_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 256, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+/* NAL payload (after the header byte) -> RBSP; returns the RBSP length (7.4.1.1) */
+static size_t unescape(const uint8_t *src, size_t n, uint8_t *dst)
+{
+    size_t o = 0;
+    int zeros = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (zeros >= 2 && src[i] == 3) { zeros = 0; continue; }
+        dst[o++] = src[i];
+        zeros = src[i] == 0 ? zeros + 1 : 0;
+    }
+    memset(dst + o, 0, 8);
+    return o;
+}
+
+/* bits before the rbsp_stop_one_bit (7.3.2.11) */
+static size_t rbsp_payload_bits(const uint8_t *rbsp, size_t n)
+{
+    while (n > 0 && rbsp[n - 1] == 0) n--;                  /* trailing zero bytes (cabac_zero_words, padding) */
+    if (n == 0) return 0;
+    int b = 0;
+    while (!((rbsp[n - 1] >> b) & 1)) b++;
+    return (n - 1) * 8 + (size_t)(7 - b);
+}
+
+static const uint8_t default4_intra[16] = {6,13,13,20,20,20,28,28,28,28,32,32,32,37,37,42};
+static const uint8_t default4_inter[16] = {10,14,14,20,20,20,24,24,24,24,27,27,27,30,30,34};
+static const uint8_t default8_intra[64] = {6,10,10,13,11,13,16,16,16,16,18,18,18,18,18,23,23,23,23,23,23,25,25,25,25,25,25,25,
+    27,27,27,27,27,27,27,27,29,29,29,29,29,29,29,31,31,31,31,31,31,33,33,33,33,33,36,36,36,36,38,38,38,40,40,42};
+static const uint8_t default8_inter[64] = {9,13,13,15,13,15,17,17,17,17,19,19,19,19,19,21,21,21,21,21,21,22,22,22,22,22,22,22,
+    24,24,24,24,24,24,24,24,25,25,25,25,25,25,25,27,27,27,27,27,27,28,28,28,28,28,30,30,30,30,32,32,32,33,33,35};
+
+/* 7.3.2.1.1.1; returns 1 when the list says "use default" */
+static int parse_scaling_list(br_t *b, uint8_t *list, int n)
+{
+    int last = 8, next = 8, use_default = 0;
+    for (int j = 0; j < n; j++) {
+        if (next != 0) {
+            int delta = br_se(b);
+            next = (last + delta + 256) % 256;
+            use_default = (j == 0 && next == 0);
+        }
+        list[j] = (uint8_t)(next == 0 ? last : next);
+        last = list[j];
+    }
+    return use_default;
+}
+
+static int parse_sps(mvf_stream *s, const uint8_t *rbsp, size_t n)
+{
+    br_t b = { rbsp, 0, n * 8 };
+    sps_t v;
+    memset(&v, 0, sizeof v);
+    v.profile_idc = (int)br_get(&b, 8);
+    br_get(&b, 8);                                          /* constraint_set flags + reserved */
+    v.level_idc = (int)br_get(&b, 8);
+    br_ue(&b);                                              /* seq_parameter_set_id */
+    v.chroma_format_idc = 1;
+    for (int i = 0; i < 6; i++) memset(v.list4[i], 16, 16);
+    for (int i = 0; i < 2; i++) memset(v.list8[i], 16, 64);
+    int p = v.profile_idc;
+    if (p == 100 || p == 110 || p == 122 || p == 244 || p == 44 || p == 83 || p == 86 || p == 118 || p == 128) {
+        v.chroma_format_idc = (int)br_ue(&b);
+        if (v.chroma_format_idc != 1)                       /* h264_parameterset.c:175-199 */
+            return sfail(s, MVG_UNSUPPORTED, "chroma_format_idc %d (only 4:2:0 is supported)", v.chroma_format_idc);
+        if (br_ue(&b) != 0 || br_ue(&b) != 0) return sfail(s, MVG_UNSUPPORTED, "bit depth > 8");
+        if (br_bit(&b)) return sfail(s, MVG_UNSUPPORTED, "qpprime_y_zero_transform_bypass_flag");
+        if (br_bit(&b)) {                                   /* seq_scaling_matrix_present_flag */
+            for (int i = 0; i < 8; i++) {
+                uint8_t *dst = i < 6 ? v.list4[i] : v.list8[i - 6];
+                int len = i < 6 ? 16 : 64;
+                int present = br_bit(&b), use_default = 0;
+                if (present) use_default = parse_scaling_list(&b, dst, len);
+                if (!present || use_default) {              /* fall-back rule A / default (Table 7-2) */
+                    if (!present && (i == 1 || i == 2 || i == 4 || i == 5)) memcpy(dst, v.list4[i - 1], 16);
+                    else if (i == 0 || i == 1 || i == 2) memcpy(dst, default4_intra, 16);
+                    else if (i < 6) memcpy(dst, default4_inter, 16);
+                    else memcpy(dst, i == 6 ? default8_intra : default8_inter, 64);
+                }
+            }
+        }
+    }
+    v.log2_max_frame_num = (int)br_ue(&b) + 4;
+    v.poc_type = (int)br_ue(&b);
+    if (v.poc_type == 0) v.log2_max_poc_lsb = (int)br_ue(&b) + 4;
+    else if (v.poc_type == 1) {
+        v.delta_pic_order_always_zero = br_bit(&b);
+        br_se(&b); br_se(&b);
+        uint32_t cyc = br_ue(&b);
+        if (cyc > 255) return sfail(s, MVG_FAILURE, "bad SPS");
+        for (uint32_t i = 0; i < cyc; i++) br_se(&b);
+    } else if (v.poc_type != 2) return sfail(s, MVG_FAILURE, "pic_order_cnt_type %d", v.poc_type);
+    br_ue(&b);                                              /* max_num_ref_frames */
+    br_bit(&b);                                             /* gaps_in_frame_num_value_allowed_flag */
+    v.width_mbs = (int)br_ue(&b) + 1;
+    v.height_mbs = (int)br_ue(&b) + 1;
+    v.frame_mbs_only = br_bit(&b);
+    if (!v.frame_mbs_only) return sfail(s, MVG_UNSUPPORTED, "interlaced (frame_mbs_only_flag = 0)");
+    br_bit(&b);                                             /* direct_8x8_inference_flag */
+    if (br_bit(&b)) for (int i = 0; i < 4; i++) v.crop[i] = (int)br_ue(&b);
+    if (br_overrun(&b) || v.width_mbs > 1024 || v.height_mbs > 1024) return sfail(s, MVG_FAILURE, "truncated or bad SPS");
+    v.valid = 1;
+    s->sps = v;
+    return MVG_SUCCESS;
+}
+
+static int parse_pps(mvf_stream *s, const uint8_t *rbsp, size_t n)
+{
+    br_t b = { rbsp, 0, rbsp_payload_bits(rbsp, n) };
+    pps_t v;
+    memset(&v, 0, sizeof v);
+    br_ue(&b); br_ue(&b);                                   /* pps id, sps id */
+    v.entropy_cabac = br_bit(&b);
+    v.bottom_field_poc_present = br_bit(&b);
+    if (br_ue(&b) != 0) return sfail(s, MVG_UNSUPPORTED, "FMO (num_slice_groups_minus1 > 0)");
+    br_ue(&b); br_ue(&b);                                   /* num_ref_idx defaults */
+    br_bit(&b); br_get(&b, 2);                              /* weighted prediction */
+    v.init_qp = 26 + br_se(&b);
+    br_se(&b);                                              /* pic_init_qs */
+    v.cb_off = br_se(&b);
+    v.deblocking_control = br_bit(&b);
+    v.constrained_intra = br_bit(&b);
+    v.redundant_pic_cnt = br_bit(&b);
+    v.cr_off = v.cb_off;
+    if (b.pos < b.nbits) {                                  /* more_rbsp_data() */
+        v.transform8x8 = br_bit(&b);
+        if (br_bit(&b)) return sfail(s, MVG_UNSUPPORTED, "PPS scaling lists (h264_parameterset.c:904-921)");
+        v.cr_off = br_se(&b);
+    }
+    if (v.entropy_cabac) return sfail(s, MVG_UNSUPPORTED, "CABAC (entropy_coding_mode_flag = 1)");
+    if (b.pos > b.nbits + 1) return sfail(s, MVG_FAILURE, "truncated PPS");
+    v.valid = 1;
+    s->pps = v;
+    return MVG_SUCCESS;
+}
+
+int mvf_open_annexb(const uint8_t *data, size_t len, mvf_stream **out)
+{
+    if (!out) return MVG_FAILURE;
+    *out = NULL;
+    if (!data || len < 5) return sfail(NULL, MVG_FAILURE, "mvf_open_annexb: empty stream");
+    pthread_once(&lut_once, build_luts);
+    mvf_stream *s = calloc(1, sizeof *s);
+    if (!s) return sfail(NULL, MVG_FAILURE, "out of memory");
+    s->data = data; s->len = len;
+
+    /* start codes 00 00 01 (a 4-byte start code is the same with one more leading zero) */
+    int cap = 1024;
+    s->nals = malloc(sizeof(nal_t) * (size_t)cap);
+    for (size_t i = 0; i + 3 < len; i++) {
+        if (data[i] == 0 && data[i + 1] == 0 && data[i + 2] == 1) {
+            if (s->n_nals == cap) { cap *= 2; s->nals = realloc(s->nals, sizeof(nal_t) * (size_t)cap); }
+            s->nals[s->n_nals].off = i + 3;
+            s->nals[s->n_nals].type = data[i + 3] & 31;
+            s->n_nals++;
+            i += 2;
+        }
+    }
+    for (int k = 0; k < s->n_nals; k++) {
+        size_t end = k + 1 < s->n_nals ? s->nals[k + 1].off - 3 : len;
+        while (end > s->nals[k].off && data[end - 1] == 0) end--;          /* trailing_zero_8bits */
+        s->nals[k].size = end - s->nals[k].off;
+    }
+    s->idr = malloc(sizeof(int) * (size_t)(s->n_nals + 1));
+    int rc = MVG_SUCCESS;
+    uint8_t *tmp = NULL;
+    for (int k = 0; k < s->n_nals && rc == MVG_SUCCESS; k++) {
+        const nal_t *nl = &s->nals[k];
+        if (nl->type == 5) { s->idr[s->n_idr++] = k; continue; }
+        if (nl->type != 7 && nl->type != 8) continue;
+        if (s->n_idr == 0) s->n_param_nals++;
+        if ((nl->type == 7 && s->sps.valid) || (nl->type == 8 && s->pps.valid)) continue;   /* first ones win */
+        tmp = realloc(tmp, nl->size + 16);
+        size_t n = unescape(data + nl->off + 1, nl->size - 1, tmp);
+        rc = nl->type == 7 ? parse_sps(s, tmp, n) : parse_pps(s, tmp, n);
+    }
+    free(tmp);
+    if (rc == MVG_SUCCESS && (!s->sps.valid || !s->pps.valid)) rc = sfail(s, MVG_FAILURE, "no SPS/PPS in the stream");
+    if (rc == MVG_SUCCESS && s->pps.transform8x8 && s->sps.profile_idc < 100) s->pps.transform8x8 = 0;
+    if (rc != MVG_SUCCESS) {
+        memcpy(g_open_error, s->err, sizeof g_open_error);
+        mvf_close(s);
+        return rc;
+    }
+    *out = s;
+    return MVG_SUCCESS;
+}
+
+int mvf_close(mvf_stream *s)
+{
+    if (!s) return MVG_FAILURE;
+    free(s->nals); free(s->idr); free(s);
+    return MVG_SUCCESS;
+}
+
+const char *mvf_last_error(const mvf_stream *s) { return s ? s->err : g_open_error; }
+
+/* normAdjust x scaling matrix (spec 8.5.9; h264.c:419-493, h264_transform.c:645-741); the same
+ * tables mvg_build_level_scale() produces, rebuilt here so that libmvfront.so has no CUDA dependency */
+static void build_level_scale(const uint8_t l4[3][16], const uint8_t l8[64], int32_t *ls4, int32_t *ls8)
+{
+    static const int v4[6][3] = {{10,16,13},{11,18,14},{13,20,16},{14,23,18},{16,25,20},{18,29,23}};
+    static const int v8[6][6] = {{20,18,32,19,25,24},{22,19,35,21,28,26},{26,23,42,24,33,31},
+                                 {28,25,45,26,35,33},{32,28,51,30,40,38},{36,32,58,34,46,43}};
+    for (int c = 0; c < 3; c++) {
+        int m[16];
+        for (int k = 0; k < 16; k++) m[zz4[k]] = l4[c][k];
+        for (int q = 0; q < 6; q++)
+            for (int i = 0; i < 4; i++)
+                for (int j = 0; j < 4; j++) {
+                    int cls = (!(i & 1) && !(j & 1)) ? 0 : ((i & 1) && (j & 1)) ? 1 : 2;
+                    ls4[(c * 6 + q) * 16 + i * 4 + j] = m[i * 4 + j] * v4[q][cls];
+                }
+    }
+    int m8[64];
+    for (int k = 0; k < 64; k++) m8[zz8[k]] = l8[k];
+    for (int q = 0; q < 6; q++)
+        for (int i = 0; i < 8; i++)
+            for (int j = 0; j < 8; j++) {
+                int cls;
+                if (i % 4 == 0 && j % 4 == 0) cls = 0;
+                else if (i % 2 == 1 && j % 2 == 1) cls = 1;
+                else if (i % 4 == 2 && j % 4 == 2) cls = 2;
+                else if ((i % 4 == 0 && j % 2 == 1) || (i % 2 == 1 && j % 4 == 0)) cls = 3;
+                else if ((i % 4 == 0 && j % 4 == 2) || (i % 4 == 2 && j % 4 == 0)) cls = 4;
+                else cls = 5;
+                ls8[q * 64 + i * 8 + j] = m8[i * 8 + j] * v8[q][cls];
+            }
+}
+
+int mvf_get_info(const mvf_stream *s, mvf_info *o)
+{
+    if (!s || !o) return MVG_FAILURE;
+    memset(o, 0, sizeof *o);
+    o->width_mbs = s->sps.width_mbs; o->height_mbs = s->sps.height_mbs;
+    o->profile_idc = s->sps.profile_idc; o->level_idc = s->sps.level_idc;
+    o->n_idr = s->n_idr; o->transform_8x8_mode = s->pps.transform8x8;
+    o->cb_qp_offset = s->pps.cb_off; o->cr_qp_offset = s->pps.cr_off; o->pic_init_qp = s->pps.init_qp;
+    o->crop_left = s->sps.crop[0]; o->crop_right = s->sps.crop[1]; o->crop_top = s->sps.crop[2]; o->crop_bottom = s->sps.crop[3];
+    uint8_t l4[3][16];
+    for (int c = 0; c < 3; c++) memcpy(l4[c], s->sps.list4[c], 16);           /* intra Y, Cb, Cr */
+    build_level_scale(l4, s->sps.list8[0], o->level_scale4x4, o->level_scale8x8);
+    return MVG_SUCCESS;
+}
+
+/* demuxer/filter.c:52-215, on IDR indices instead of bitstream-map samples */
+int mvf_select_idr(const mvf_stream *s, int n_wanted, int mode, int32_t *indices)
+{
+    if (!s || !indices || n_wanted < 0) return 0;
+    int n_idr = s->n_idr;
+    if (n_wanted > n_idr) n_wanted = n_idr;                 /* filter.c:79-87 */
+    if (mode == 0) {                                        /* PICTURE_UNFILTERED, filter.c:88-92 */
+        for (int i = 0; i < n_wanted; i++) indices[i] = i;
+        return n_wanted;
+    }
+    if (n_idr == 0) return 0;
+    /* sample size = distance between NAL header bytes (esparser.c:91,:130) */
+    long long payload = 0;
+    long long *size = malloc(sizeof(long long) * (size_t)n_idr);
+    for (int i = 0; i < n_idr; i++) {
+        int k = s->idr[i];
+        size_t next = k + 1 < s->n_nals ? s->nals[k + 1].off : s->len;
+        size[i] = (long long)(next - s->nals[k].off);
+        payload += size[i];
+    }
+    int threshold = (int)(((double)payload / (double)n_idr) / 1.66);          /* filter.c:109 */
+    int borders = n_idr > 48 ? (int)ceil(n_idr * 0.03) : 0;                   /* filter.c:114-118 */
+    int *cand = malloc(sizeof(int) * (size_t)n_idr), n_cand = 0;
+    for (int i = borders; i < n_idr - borders; i++)
+        if (size[i] > threshold) cand[n_cand++] = i;                          /* filter.c:120-131 */
+    if (n_wanted > n_cand) n_wanted = n_cand;
+    int n_out = 0;
+    if (mode == 1) {                                        /* PICTURE_ORDERED */
+        for (int i = 0; i < n_wanted; i++) indices[n_out++] = cand[i];
+    } else if (n_wanted == 1) {
+        indices[n_out++] = cand[0];                         /* the reference divides by zero here (filter.c:140) */
+    } else if (n_wanted > 1) {
+        int jump = n_cand / (n_wanted - 1);                 /* filter.c:140: ceil() of an integer quotient */
+        for (int i = 0; i < n_wanted; i++) {
+            int j = i * jump;
+            if (j >= n_cand) break;                         /* the reference reads one past the end there */
+            indices[n_out++] = cand[j];
+        }
+    }
+    free(size); free(cand);
+    return n_out;
+}
+
+/* ------------------------------------------------------------------------ */
+/* slice + macroblock parsing                                                 */
+
+typedef struct {
+    const mvf_stream *s;
+    uint8_t *rbsp; size_t rbsp_cap;
+    uint8_t *tot_luma, *tot_chroma[2];
+    int8_t *mode_grid;
+    char err[200];
+} worker_t;
+
+static inline int blk_x(int blk) { return (blk & 1) + 2 * ((blk >> 2) & 1); }
+static inline int blk_y(int blk) { return ((blk >> 1) & 1) + 2 * (blk >> 3); }
+
+static int nC_of(const uint8_t *tot, int stride, int X, int Y)
+{
+    int a = X > 0, b = Y > 0;
+    int nA = a ? tot[Y * stride + X - 1] : 0, nB = b ? tot[(Y - 1) * stride + X] : 0;
+    if (a && b) return (nA + nB + 1) >> 1;
+    return a ? nA : (b ? nB : 0);
+}
+
+/* 9.2: one residual block; coef[] in scan order, max_num 16 / 15 / 4.  Returns TotalCoeff or -1. */
+static int read_residual_block(br_t *b, int *coef, int max_num, int nC)
+{
+    int tc, t1;
+    memset(coef, 0, sizeof(int) * (size_t)max_num);
+    if (nC == -1) {
+        uint16_t e = lut_ctc[br_peek(b, 8)];
+        if (!e) return -1;
+        br_skip(b, e >> 7); tc = (e >> 2) & 31; t1 = e & 3;
+    } else if (nC >= 8) {
+        uint32_t v = br_get(b, 6);
+        if (v == 3) { tc = 0; t1 = 0; } else { tc = (int)(v >> 2) + 1; t1 = (int)(v & 3); if (t1 > tc) return -1; }
+    } else {
+        uint16_t e = lut_ct[nC < 2 ? 0 : (nC < 4 ? 1 : 2)][br_peek(b, 16)];
+        if (!e) return -1;
+        br_skip(b, e >> 7); tc = (e >> 2) & 31; t1 = e & 3;
+    }
+    if (tc == 0) return 0;
+    if (tc > max_num) return -1;
+
+    int level[16];
+    int suffix_len = (tc > 10 && t1 < 3) ? 1 : 0;
+    for (int i = 0; i < tc; i++) {
+        if (i < t1) { level[i] = br_bit(b) ? -1 : 1; continue; }
+        int prefix = 0;
+        while (prefix < 32 && br_peek(b, 1) == 0) { prefix++; br_skip(b, 1); }
+        br_skip(b, 1);
+        if (prefix >= 32) return -1;
+        int code = (prefix < 15 ? prefix : 15) << suffix_len;           /* 9.2.2.1 */
+        int ssize = suffix_len;
+        if (prefix == 14 && suffix_len == 0) ssize = 4;
+        else if (prefix >= 15) ssize = prefix - 3;
+        if (ssize > 0) code += (int)br_get(b, ssize);
+        if (prefix >= 15 && suffix_len == 0) code += 15;
+        if (prefix >= 16) code += (1 << (prefix - 3)) - 4096;
+        if (i == t1 && t1 < 3) code += 2;
+        level[i] = (code & 1) ? (-code - 1) >> 1 : (code + 2) >> 1;
+        if (suffix_len == 0) suffix_len = 1;
+        if (abs(level[i]) > (3 << (suffix_len - 1)) && suffix_len < 6) suffix_len++;
+    }
+    int zeros_left = 0;
+    if (tc < max_num) {
+        uint8_t e = max_num == 4 ? lut_tz2[tc - 1][br_peek(b, 3)] : lut_tz4[tc - 1][br_peek(b, 9)];
+        if (!e) return -1;
+        br_skip(b, e >> 4); zeros_left = e & 15;
+    }
+    int pos = zeros_left + tc - 1;                                      /* scan index of the first (highest) level */
+    if (pos >= max_num) return -1;
+    for (int i = 0; i < tc; i++) {
+        coef[pos] = level[i];
+        int run = 0;
+        if (i < tc - 1 && zeros_left > 0) {
+            uint8_t e = lut_run[(zeros_left > 7 ? 7 : zeros_left) - 1][br_peek(b, 11)];
+            if (!e) return -1;
+            br_skip(b, e >> 4); run = e & 15;
+            if (run > zeros_left) return -1;
+            zeros_left -= run;
+        }
+        pos -= 1 + run;
+        if (i < tc - 1 && pos < 0) return -1;
+    }
+    return tc;
+}
+
+static inline int16_t clamp16(int v) { return (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
+
+static int wfail(worker_t *w, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(w->err, sizeof w->err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_t pic_slot)
+{
+    const mvf_stream *s = w->s;
+    const sps_t *sps = &s->sps; const pps_t *pps = &s->pps;
+    const nal_t *nl = &s->nals[s->idr[idr_index]];
+    if (nl->size + 16 > w->rbsp_cap) { w->rbsp_cap = nl->size * 2 + 64; w->rbsp = realloc(w->rbsp, w->rbsp_cap); }
+    size_t n = unescape(s->data + nl->off + 1, nl->size - 1, w->rbsp);
+    br_t b = { w->rbsp, 0, rbsp_payload_bits(w->rbsp, n) };
+    int nal_ref_idc = (s->data[nl->off] >> 5) & 3;
+
+    /* ---- slice header, 7.3.3 (h264_slice.c:156-334) ---- */
+    if (br_ue(&b) != 0) return wfail(w, MVG_UNSUPPORTED, "picture %d: first_mb_in_slice != 0 (one slice per picture only)", idr_index);
+    uint32_t slice_type = br_ue(&b);
+    if (slice_type != 2 && slice_type != 7) return wfail(w, MVG_UNSUPPORTED, "picture %d: slice_type %u is not I", idr_index, slice_type);
+    br_ue(&b);                                              /* pic_parameter_set_id */
+    br_get(&b, sps->log2_max_frame_num);                    /* frame_num */
+    br_ue(&b);                                              /* idr_pic_id */
+    if (sps->poc_type == 0) {
+        br_get(&b, sps->log2_max_poc_lsb);
+        if (pps->bottom_field_poc_present) br_se(&b);
+    } else if (sps->poc_type == 1 && !sps->delta_pic_order_always_zero) {
+        br_se(&b);
+        if (pps->bottom_field_poc_present) br_se(&b);
+    }
+    if (pps->redundant_pic_cnt) br_ue(&b);
+    if (nal_ref_idc) { br_bit(&b); br_bit(&b); }            /* dec_ref_pic_marking of an IDR picture */
+    int qp = pps->init_qp + br_se(&b);                      /* SliceQPY */
+    if (pps->deblocking_control) {
+        if (br_ue(&b) != 1) { br_se(&b); br_se(&b); }
+    }
+    if (qp < 0 || qp > 51) return wfail(w, MVG_FAILURE, "picture %d: SliceQPY %d out of range", idr_index, qp);
+
+    /* ---- slice data, 7.3.4 / 7.3.5 ---- */
+    const int W = sps->width_mbs, H = sps->height_mbs, W4 = W * 4, W2 = W * 2;
+    const size_t N = (size_t)W * H;
+    memset(w->tot_luma, 0, N * 16);
+    memset(w->tot_chroma[0], 0, N * 4);
+    memset(w->tot_chroma[1], 0, N * 4);
+    int coef[64], sub[16];
+
+    for (int my = 0; my < H; my++)
+        for (int mx = 0; mx < W; mx++) {
+            const size_t mbi = pic_slot * N + (size_t)my * W + mx;
+            int16_t *cf = out->coeff + mbi * 384;
+            uint8_t *modes = out->luma_modes + mbi * 16;
+            memset(cf, 0, 768);
+            memset(modes, 0, 16);
+            uint32_t mb_type = br_ue(&b);
+            if (mb_type == 25) return wfail(w, MVG_UNSUPPORTED, "picture %d: I_PCM macroblock (h264_macroblock.c:151-154)", idr_index);
+            if (mb_type > 25) return wfail(w, MVG_FAILURE, "picture %d mb %d: bad mb_type %u", idr_index, my * W + mx, mb_type);
+            int kind, i16_mode = 0, cbp_l, cbp_c;
+            if (mb_type == 0) {
+                kind = (pps->transform8x8 && br_bit(&b)) ? MVG_MB_I8x8 : MVG_MB_I4x4;
+                int nb = kind == MVG_MB_I4x4 ? 16 : 4;
+                for (int i = 0; i < nb; i++) {
+                    int X4 = mx * 4 + (kind == MVG_MB_I4x4 ? blk_x(i) : (i & 1) * 2);
+                    int Y4 = my * 4 + (kind == MVG_MB_I4x4 ? blk_y(i) : (i >> 1) * 2);
+                    int pred = 2;                           /* 8.3.1.1 / 8.3.2.1 */
+                    if (X4 > 0 && Y4 > 0) {
+                        int a = w->mode_grid[Y4 * W4 + X4 - 1], bb = w->mode_grid[(Y4 - 1) * W4 + X4];
+                        pred = a < bb ? a : bb;
+                    }
+                    int mode = pred;
+                    if (!br_bit(&b)) { int rem = (int)br_get(&b, 3); mode = rem < pred ? rem : rem + 1; }
+                    modes[i] = (uint8_t)mode;
+                    int span = kind == MVG_MB_I4x4 ? 1 : 2;
+                    for (int dy = 0; dy < span; dy++)
+                        for (int dx = 0; dx < span; dx++) w->mode_grid[(Y4 + dy) * W4 + X4 + dx] = (int8_t)mode;
+                }
+            } else {
+                kind = MVG_MB_I16x16;
+                int t = (int)mb_type - 1;
+                i16_mode = t & 3; cbp_c = (t >> 2) % 3; cbp_l = t >= 12 ? 15 : 0;
+                for (int blk = 0; blk < 16; blk++) w->mode_grid[(my * 4 + blk_y(blk)) * W4 + mx * 4 + blk_x(blk)] = 2;
+            }
+            uint32_t chroma_mode = br_ue(&b);
+            if (chroma_mode > 3) return wfail(w, MVG_FAILURE, "picture %d mb %d: intra_chroma_pred_mode %u", idr_index, my * W + mx, chroma_mode);
+            if (kind != MVG_MB_I16x16) {
+                uint32_t cn = br_ue(&b);
+                if (cn > 47) return wfail(w, MVG_FAILURE, "picture %d mb %d: coded_block_pattern codeNum %u", idr_index, my * W + mx, cn);
+                int cbp = cbp_from_codenum[cn];
+                cbp_l = cbp & 15; cbp_c = cbp >> 4;
+            }
+            if (cbp_l || cbp_c || kind == MVG_MB_I16x16) {
+                int delta = br_se(&b);
+                if (delta) qp = (qp + delta + 52) % 52;     /* h264_macroblock.c:263-266 */
+                /* residual_luma, 7.3.5.3.1 */
+                if (kind == MVG_MB_I16x16) {
+                    if (read_residual_block(&b, coef, 16, nC_of(w->tot_luma, W4, mx * 4, my * 4)) < 0) goto bad_block;
+                    for (int k = 0; k < 16; k++) {
+                        int r = zz4[k] >> 2, c = zz4[k] & 3;
+                        cf[((r & 1) * 2 + (r >> 1) * 8 + (c & 1) + (c >> 1) * 4) * 16] = clamp16(coef[k]);
+                    }
+                }
+                for (int b8 = 0; b8 < 4; b8++)
+                    for (int i4 = 0; i4 < 4; i4++) {
+                        int blk = b8 * 4 + i4, X4 = mx * 4 + blk_x(blk), Y4 = my * 4 + blk_y(blk), tc = 0;
+                        if ((cbp_l >> b8) & 1) {
+                            int maxn = kind == MVG_MB_I16x16 ? 15 : 16;
+                            tc = read_residual_block(&b, sub, maxn, nC_of(w->tot_luma, W4, X4, Y4));
+                            if (tc < 0) goto bad_block;
+                            if (kind == MVG_MB_I4x4) for (int k = 0; k < 16; k++) cf[blk * 16 + k] = clamp16(sub[k]);
+                            else if (kind == MVG_MB_I8x8) for (int k = 0; k < 16; k++) cf[b8 * 64 + 4 * k + i4] = clamp16(sub[k]);   /* h264_macroblock.c:1182 */
+                            else for (int k = 0; k < 15; k++) cf[blk * 16 + 1 + k] = clamp16(sub[k]);
+                        }
+                        w->tot_luma[Y4 * W4 + X4] = (uint8_t)tc;
+                    }
+                /* residual chroma: DC of both planes, then AC of both planes (h264_macroblock.c:1222-1292) */
+                for (int c = 0; c < 2; c++)
+                    if (cbp_c & 3) {
+                        if (read_residual_block(&b, sub, 4, -1) < 0) goto bad_block;
+                        for (int k = 0; k < 4; k++) cf[256 + c * 64 + k * 16] = clamp16(sub[k]);
+                    }
+                for (int c = 0; c < 2; c++)
+                    for (int blk = 0; blk < 4; blk++) {
+                        int X2 = mx * 2 + (blk & 1), Y2 = my * 2 + (blk >> 1), tc = 0;
+                        if (cbp_c & 2) {
+                            tc = read_residual_block(&b, sub, 15, nC_of(w->tot_chroma[c], W2, X2, Y2));
+                            if (tc < 0) goto bad_block;
+                            for (int k = 0; k < 15; k++) cf[256 + c * 64 + blk * 16 + 1 + k] = clamp16(sub[k]);
+                        }
+                        w->tot_chroma[c][Y2 * W2 + X2] = (uint8_t)tc;
+                    }
+            } else {
+                for (int blk = 0; blk < 16; blk++) w->tot_luma[(my * 4 + blk_y(blk)) * W4 + mx * 4 + blk_x(blk)] = 0;
+                for (int c = 0; c < 2; c++)
+                    for (int blk = 0; blk < 4; blk++) w->tot_chroma[c][(my * 2 + (blk >> 1)) * W2 + mx * 2 + (blk & 1)] = 0;
+            }
+            out->mb_kind[mbi] = (uint8_t)kind;
+            out->i16_mode[mbi] = (uint8_t)i16_mode;
+            out->chroma_mode[mbi] = (uint8_t)chroma_mode;
+            out->qp_y[mbi] = (int8_t)qp;
+            out->cbp[mbi] = (uint8_t)(cbp_c << 4 | cbp_l);
+            if (br_overrun(&b)) return wfail(w, MVG_FAILURE, "picture %d: slice data ends at macroblock %d of %zu", idr_index, my * W + mx, N);
+            continue;
+        bad_block:
+            return wfail(w, MVG_FAILURE, "picture %d mb %d: invalid CAVLC code", idr_index, my * W + mx);
+        }
+    return MVG_SUCCESS;
+}
+
+typedef struct {
+    mvf_stream *s; const int32_t *indices; int first, count; const mvf_batch *out;
+    int next; int rc; char err[200];
+    pthread_mutex_t mu;
+} job_t;
+
+static void *worker_main(void *arg)
+{
+    job_t *j = arg;
+    const mvf_stream *s = j->s;
+    size_t N = (size_t)s->sps.width_mbs * s->sps.height_mbs;
+    worker_t w;
+    memset(&w, 0, sizeof w);
+    w.s = s;
+    w.tot_luma = malloc(N * 16); w.tot_chroma[0] = malloc(N * 4); w.tot_chroma[1] = malloc(N * 4);
+    w.mode_grid = malloc(N * 16);
+    for (;;) {
+        pthread_mutex_lock(&j->mu);
+        int i = j->rc == MVG_SUCCESS ? j->next++ : j->count;
+        pthread_mutex_unlock(&j->mu);
+        if (i >= j->count) break;
+        int idx = j->indices ? j->indices[i] : j->first + i;
+        int rc = (idx < 0 || idx >= s->n_idr) ? wfail(&w, MVG_FAILURE, "IDR index %d out of range (0..%d)", idx, s->n_idr - 1)
+                                              : parse_picture(&w, idx, j->out, (size_t)i);
+        if (rc != MVG_SUCCESS) {
+            pthread_mutex_lock(&j->mu);
+            if (j->rc == MVG_SUCCESS) { j->rc = rc; memcpy(j->err, w.err, sizeof j->err); }
+            pthread_mutex_unlock(&j->mu);
+        }
+    }
+    free(w.rbsp); free(w.tot_luma); free(w.tot_chroma[0]); free(w.tot_chroma[1]); free(w.mode_grid);
+    return NULL;
+}
+
+int mvf_parse_pictures(mvf_stream *s, const int32_t *indices, int first, int count, mvf_batch *out, int n_threads)
+{
+    if (!s || !out || count < 0) return MVG_FAILURE;
+    if (!out->mb_kind || !out->i16_mode || !out->chroma_mode || !out->qp_y || !out->cbp || !out->luma_modes || !out->coeff)
+        return sfail(s, MVG_FAILURE, "mvf_parse_pictures: a batch pointer is NULL");
+    out->n_pics = count;
+    if (count == 0) return MVG_SUCCESS;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > count) n_threads = count;
+    if (n_threads > 256) n_threads = 256;
+    job_t j;
+    memset(&j, 0, sizeof j);
+    j.s = s; j.indices = indices; j.first = first; j.count = count; j.out = out; j.rc = MVG_SUCCESS;
+    pthread_mutex_init(&j.mu, NULL);
+    if (n_threads == 1) worker_main(&j);
+    else {
+        pthread_t th[256];
+        int started = 0;
+        for (int t = 0; t < n_threads; t++)
+            if (pthread_create(&th[started], NULL, worker_main, &j) == 0) started++;
+        if (started == 0) worker_main(&j);
+        for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+    }
+    pthread_mutex_destroy(&j.mu);
+    if (j.rc != MVG_SUCCESS) memcpy(s->err, j.err, sizeof j.err);
+    return j.rc;
+}

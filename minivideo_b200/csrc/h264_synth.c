@@ -90,85 +90,12 @@ static void emit_nal(sink_t *s, uint8_t header, const bw_t *rbsp)
     }
 }
 
-/* ------------------------------------------------------------------------ */
-/* CAVLC tables (H.264 Tables 9-5, 9-7, 9-9, 9-10) as (length, code) pairs   */
-
-/* coeff_token, [table for 0<=nC<2, 2<=nC<4, 4<=nC<8][TrailingOnes][TotalCoeff] */
-static const uint8_t ct_len[3][4][17] = {
-    {{ 1, 6, 8, 9,10,11,13,13,13,14,14,15,15,16,16,16,16},
-     { 0, 2, 6, 8, 9,10,11,13,13,14,14,15,15,15,16,16,16},
-     { 0, 0, 3, 7, 8, 9,10,11,13,13,14,14,15,15,16,16,16},
-     { 0, 0, 0, 5, 6, 7, 8, 9,10,11,13,14,14,15,15,16,16}},
-    {{ 2, 6, 6, 7, 8, 8, 9,11,11,12,12,12,13,13,13,14,14},
-     { 0, 2, 5, 6, 6, 7, 8, 9,11,11,12,12,13,13,14,14,14},
-     { 0, 0, 3, 6, 6, 7, 8, 9,11,11,12,12,13,13,13,14,14},
-     { 0, 0, 0, 4, 4, 5, 6, 6, 7, 9,11,11,12,13,13,13,14}},
-    {{ 4, 6, 6, 6, 7, 7, 7, 7, 8, 8, 9, 9, 9,10,10,10,10},
-     { 0, 4, 5, 5, 5, 5, 6, 6, 7, 8, 8, 9, 9, 9,10,10,10},
-     { 0, 0, 4, 5, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9,10,10,10},
-     { 0, 0, 0, 4, 4, 4, 4, 4, 5, 6, 7, 8, 8, 9,10,10,10}},
-};
-static const uint8_t ct_code[3][4][17] = {
-    {{ 1, 5, 7, 7, 7, 7,15,11, 8,15,11,15,11,15,11, 7, 4},
-     { 0, 1, 4, 6, 6, 6, 6,14,10,14,10,14,10, 1,14,10, 6},
-     { 0, 0, 1, 5, 5, 5, 5, 5,13, 9,13, 9,13, 9,13, 9, 5},
-     { 0, 0, 0, 3, 3, 4, 4, 4, 4, 4,12,12, 8,12, 8,12, 8}},
-    {{ 3,11, 7, 7, 7, 4, 7,15,11,15,11, 8,15,11, 7, 9, 7},
-     { 0, 2, 7,10, 6, 6, 6, 6,14,10,14,10,14,10,11, 8, 6},
-     { 0, 0, 3, 9, 5, 5, 5, 5,13, 9,13, 9,13, 9, 6,10, 5},
-     { 0, 0, 0, 5, 4, 6, 8, 4, 4, 4,12, 8,12,12, 8, 1, 4}},
-    {{15,15,11, 8,15,11, 9, 8,15,11,15,11, 8,13, 9, 5, 1},
-     { 0,14,15,12,10, 8,14,10,14,14,10,14,10, 7,12, 8, 4},
-     { 0, 0,13,14,11, 9,13, 9,13,10,13, 9,13, 9,11, 7, 3},
-     { 0, 0, 0,12,11,10, 9, 8,13,12,12,12, 8,12,10, 6, 2}},
-};
-/* coeff_token for chroma DC (nC == -1), [TrailingOnes][TotalCoeff] */
-static const uint8_t ctc_len[4][5]  = {{2,6,6,6,6},{0,1,6,7,8},{0,0,3,7,8},{0,0,0,6,7}};
-static const uint8_t ctc_code[4][5] = {{1,7,4,3,2},{0,1,6,3,3},{0,0,1,2,2},{0,0,0,5,0}};
-
-/* total_zeros for 4x4 blocks, row = TotalCoeff-1, written as bit strings */
-static const char *const tz4x4[15][16] = {
-    {"1","011","010","0011","0010","00011","00010","000011","000010","0000011","0000010","00000011","00000010","000000011","000000010","000000001"},
-    {"111","110","101","100","011","0101","0100","0011","0010","00011","00010","000011","000010","000001","000000"},
-    {"0101","111","110","101","0100","0011","100","011","0010","00011","00010","000001","00001","000000"},
-    {"00011","111","0101","0100","110","101","100","0011","011","0010","00010","00001","00000"},
-    {"0101","0100","0011","111","110","101","100","011","0010","00001","0001","00000"},
-    {"000001","00001","111","110","101","100","011","010","0001","001","000000"},
-    {"000001","00001","101","100","011","11","010","0001","001","000000"},
-    {"000001","0001","00001","011","11","10","010","001","000000"},
-    {"000001","000000","0001","11","10","001","01","00001"},
-    {"00001","00000","001","11","10","01","0001"},
-    {"0000","0001","001","010","1","011"},
-    {"0000","0001","01","1","001"},
-    {"000","001","1","01"},
-    {"00","01","1"},
-    {"0","1"},
-};
-/* total_zeros for chroma DC 2x2, row = TotalCoeff-1 */
-static const char *const tz2x2[3][4] = {
-    {"1","01","001","000"}, {"1","01","00"}, {"1","0"},
-};
-/* run_before, row = min(zerosLeft,7)-1 */
-static const char *const runb[7][15] = {
-    {"1","0"},
-    {"1","01","00"},
-    {"11","10","01","00"},
-    {"11","10","01","001","000"},
-    {"11","10","011","010","001","000"},
-    {"11","000","001","011","010","101","100"},
-    {"111","110","101","100","011","010","001","0001","00001","000001","0000001","00000001","000000001","0000000001","00000000001"},
-};
+#include "h264_cavlc_tables.h"
 
 static void bw_str(bw_t *b, const char *s)
 {
     for (; *s; s++) bw_put(b, 1, *s == '1');
 }
-
-/* coded_block_pattern -> codeNum for me(v), Intra, ChromaArrayType 1 (Table 9-4) */
-static const uint8_t cbp_intra_by_codenum[48] = {
-    47,31,15, 0,23,27,29,30, 7,11,13,14,39,43,45,46,16, 3, 5,10,12,19,21,26,
-    28,35,37,42,44, 1, 2, 4, 8,17,18,20,24, 6, 9,22,25,32,33,34,36,40,38,41
-};
 
 /* frame zig-zag scans generated from the definition (8.5.6, 8.5.7):
  * zz[k] = row*n + col of the k-th coefficient */
