@@ -196,6 +196,9 @@ def run_ours(args):
     # ---- timed region: K steps over the resident batch
     sampler = ClockSampler(local)
     sampler.start()
+    t_wait = time.perf_counter()
+    while not sampler.samples and sampler.err is None and time.perf_counter() - t_wait < 10.0:
+        time.sleep(0.01)                      # NVML initialisation can take longer than the warm-up
     for _ in range(args.warmup):
         ctx.run(0, F, scale)
     ctx.sync()

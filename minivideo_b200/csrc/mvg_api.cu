@@ -27,6 +27,7 @@ static char g_create_error[512] = "";
 
 struct mvg_ctx {
     int device = -1, sm_count = 0;
+    int k1_ctas_per_sm = 1, k2_ctas_per_sm = 1;
     int max_w = 0, max_h = 0, max_pics = 0;
     int w_mbs = 0, h_mbs = 0;
     bool have_sps = false;
@@ -259,6 +260,9 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     cudaDeviceProp prop;
     TRY("cudaGetDeviceProperties", cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
+    TRY("occupancy k1", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_ctas_per_sm, k1_dequant_idct, K1_WARPS * 32, 0));
+    TRY("occupancy k2", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2_ctas_per_sm, k2_wavefront, K2_WARPS * 32, 0));
+    if (ctx->k1_ctas_per_sm < 1 || ctx->k2_ctas_per_sm < 1) return bail("kernel does not fit on an SM", cudaErrorLaunchOutOfResources);
     TRY("stream", cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     TRY("stream", cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     TRY("stream", cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
@@ -445,8 +449,9 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         p.luma_modes = ctx->d_modes + o * 16; p.qp_y = ctx->d_qp + o; p.coeff = ctx->d_coeff + o * 384;
         p.resid = ctx->d_resid + o * 384; p.ctl = ctx->d_ctl + o; p.tab = ctx->d_tab;
         p.n_mbs = (long long)n * n_pics;
-        const long long want = (p.n_mbs + K1_WARPS - 1) / K1_WARPS;
-        const int grid = (int)std::min<long long>(want, (long long)ctx->sm_count * 8 * 4);
+        const long long groups = (p.n_mbs + K1_GROUP - 1) / K1_GROUP;
+        const long long want = (groups + K1_WARPS - 1) / K1_WARPS;
+        const int grid = (int)std::min<long long>(want, (long long)ctx->sm_count * ctx->k1_ctas_per_sm);
         k1_dequant_idct<<<grid, K1_WARPS * 32, 0, st>>>(p);
         launches++;
     }
@@ -458,7 +463,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         p.epoch = ctx->epoch; p.group = MVG_K2_GROUP;
         p.work = work; p.luts = ctx->d_luts; p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics;
         const long long items = (long long)n_pics * H;
-        const int grid = (int)std::min<long long>((items + K2_WARPS - 1) / K2_WARPS, (long long)ctx->sm_count * 8);
+        const int grid = (int)std::min<long long>((items + K2_WARPS - 1) / K2_WARPS, (long long)ctx->sm_count * ctx->k2_ctas_per_sm);
         k2_wavefront<<<grid, K2_WARPS * 32, 0, st>>>(p);
         launches++;
     }
@@ -571,7 +576,26 @@ extern "C" int mvg_download_residual(mvg_ctx *ctx, int slot, int16_t *residual)
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t n = ctx->n_mb();
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    CK(ctx, cudaMemcpy(residual, ctx->d_resid + (size_t)slot * n * 384, n * 768, cudaMemcpyDeviceToHost));
+    int16_t *tmp = new (std::nothrow) int16_t[n * 384];
+    if (!tmp) return fail(ctx, "mvg_download_residual: out of host memory");
+    cudaError_t e = cudaMemcpy(tmp, ctx->d_resid + (size_t)slot * n * 384, n * 768, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { delete[] tmp; return fail(ctx, "cudaMemcpy failed: %s", cudaGetErrorString(e)); }
+    /* device layout is block-major (4x4 block b at [b*16, b*16+16)); the ABI promises rasters */
+    for (size_t mb = 0; mb < n; mb++) {
+        const int16_t *src = tmp + mb * 384;
+        int16_t *dst = residual + mb * 384;
+        for (int b = 0; b < 16; b++) {
+            const int bx = (b & 1) | (((b >> 2) & 1) << 1), by = ((b >> 1) & 1) | ((b >> 3) << 1);
+            for (int i = 0; i < 4; i++)
+                for (int j = 0; j < 4; j++) dst[(by * 4 + i) * 16 + bx * 4 + j] = src[b * 16 + i * 4 + j];
+        }
+        for (int p = 0; p < 2; p++)
+            for (int b = 0; b < 4; b++)
+                for (int i = 0; i < 4; i++)
+                    for (int j = 0; j < 4; j++)
+                        dst[256 + p * 64 + ((b >> 1) * 4 + i) * 8 + (b & 1) * 4 + j] = src[256 + p * 64 + b * 16 + i * 4 + j];
+    }
+    delete[] tmp;
     return MVG_SUCCESS;
 }
 

@@ -93,230 +93,325 @@ __device__ __forceinline__ unsigned mvg_pack_sat16(int hi, int lo)
     return d;
 }
 
-#define K1_WARPS 8
+#define K1_WARPS 4          /* warps per CTA                      */
+#define K1_GROUP 4          /* macroblocks per warp iteration     */
+#define K1_TILE  (K1_GROUP * 384)
 
-/* One warp per macroblock, grid-stride, the next macroblock's loads in flight while the
- * current one is transformed.
- *  4x4 path (Intra4x4 / Intra16x16 luma, all chroma): lane b < 24 owns 4x4 block b
- *    (0..15 luma in decoding order, 16..19 Cb, 20..23 Cr): two 128-bit loads bring
- *    its 16 levels, the zig-zag inverse is a compile-time register renaming, both
- *    butterfly passes stay in registers.  The Intra16x16 DC Hadamard and the chroma
- *    DC 2x2 run across lanes with shuffles.
- *  8x8 path (Intra8x8 luma): 8 lanes per block, one matrix row per lane, transposed
- *    through shared memory between the row and the column pass.
- *  The dequantisation scale (LevelScale << (qP/6 - 4)) is tabulated per qP in shared
- *  memory; the rounding constant 32 of the final >> 6 is added to the DC term before the
- *  butterflies (it reaches every output with weight one).  The int16 residual is staged
- *  in shared memory in raster order and leaves with coalesced 128-bit stores. */
-__global__ void __launch_bounds__(K1_WARPS * 32, 3)
+/* ---- bulk asynchronous copies (TMA, 1-D) and their mbarrier ------------------- */
+__device__ __forceinline__ uint32_t mvg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mvg_mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mvg_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mvg_mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mvg_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mvg_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mvg_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mvg_bulk_load(void *dst_smem, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(mvg_smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(mvg_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mvg_bulk_store(void *dst, const void *src_smem, unsigned bytes)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst), "r"(mvg_smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void mvg_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+struct K1WarpSmem {
+    __align__(128) int16_t tile[2][K1_TILE];    /* levels in, residual out (in place), double buffered */
+    int32_t  dc[K1_GROUP][24];                  /* dequantised DC of Intra16x16 luma / chroma blocks   */
+    int32_t  f1[K1_GROUP][16];                  /* first stage of the luma DC Hadamard                 */
+    int32_t  tr[4][8][9];                       /* 8x8 transpose, padded                               */
+    uint32_t meta[K1_GROUP];                    /* mb_kind | QPY << 8                                  */
+    uint8_t  list4[K1_GROUP * 24 + 8];          /* 4x4 blocks that need the full transform             */
+    uint8_t  list8[K1_GROUP * 4 + 4];           /* 8x8 blocks with non-zero levels                     */
+    __align__(8) uint64_t mbar[2];
+};
+
+/* position (bx,by) -> luma4x4BlkIdx (h264_spatial.c:210-225 inverted) */
+__device__ __forceinline__ int mvg_blk_of(int bx, int by) { return (bx & 1) | ((by & 1) << 1) | ((bx >> 1) << 2) | ((by >> 1) << 3); }
+
+/* One warp transforms K1_GROUP macroblocks per iteration, in place in shared memory:
+ *   - the 3 KB of levels arrive with ONE bulk asynchronous copy (cp.async.bulk + mbarrier), the
+ *     next group's copy is in flight while this one is processed, and the residual leaves with
+ *     one bulk store -- no per-thread global loads/stores for the payload;
+ *   - Intra16x16 luma DC (4x4 Hadamard, h264_transform.c:756-812) and chroma DC (2x2, :827-936)
+ *     are done first, separably, a few lanes per macroblock;
+ *   - every 4x4 block is classified: all-zero (nothing to do), DC-only (every residual sample is
+ *     (d00 + 32) >> 6, spec 8.5.12.2 with a single non-zero input) or general; the general blocks
+ *     of the whole group are compacted with ballots and run through quant4x4 + idct4x4
+ *     (h264_transform.c:1100-1191) 32 at a time, one block per lane, entirely in registers;
+ *   - non-zero 8x8 blocks (Intra8x8 luma, quant8x8/idct8x8 :1256-1383) are compacted the same
+ *     way and transformed 4 per pass, 8 lanes per block, transposed through shared memory.
+ * Residual layout out: per macroblock 24 blocks x 16 int16, block-major (see MvgMbCtl). */
+__global__ void __launch_bounds__(K1_WARPS * 32, 5)
 k1_dequant_idct(K1Params p)
 {
     __shared__ int32_t s_ls4[3 * 6 * 16];
-    __shared__ int32_t s_ls4q[3 * 52 * 16];                     /* qP >= 24: LevelScale << (qP/6-4) */
+    __shared__ int32_t s_ls4q[3 * 52 * 16];                     /* per qP; << (qP/6-4) folded in when qP >= 24 */
     __shared__ int32_t s_ls8[6 * 64];
     __shared__ uint8_t s_zz8inv[64];
-    __shared__ __align__(16) int16_t s_in[K1_WARPS][256];      /* luma levels of an Intra8x8 MB */
-    __shared__ int32_t s_tr[K1_WARPS][4][8][9];                 /* 8x8 transpose, padded          */
-    __shared__ __align__(16) int16_t s_out[K1_WARPS][384];     /* residual, raster                */
+    __shared__ K1WarpSmem s_warp[K1_WARPS];
 
     for (int i = threadIdx.x; i < 3 * 6 * 16; i += blockDim.x) s_ls4[i] = (&p.tab->ls4[0][0][0])[i];
     for (int i = threadIdx.x; i < 3 * 52 * 16; i += blockDim.x) s_ls4q[i] = (&p.tab->ls4q[0][0][0])[i];
     for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) s_ls8[i] = (&p.tab->ls8[0][0])[i];
     if (threadIdx.x < 64) s_zz8inv[threadIdx.x] = p.tab->zz8inv[threadIdx.x];
     const int cb_off = p.tab->cb_qp_offset, cr_off = p.tab->cr_qp_offset;
+
+    const int lane = threadIdx.x & 31;
+    K1WarpSmem &s = s_warp[threadIdx.x >> 5];
+    if (lane == 0) { mvg_mbar_init(&s.mbar[0], 1); mvg_mbar_init(&s.mbar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long n_warps = (long long)gridDim.x * K1_WARPS;
-    const bool is_chroma = lane >= 16;
-    const int comp = lane < 16 ? 0 : (lane < 20 ? 1 : 2);
-    int16_t *out = s_out[w];
-    /* where this lane's 4x4 block lands in the raster residual */
-    int16_t *dst;
-    int dst_stride;
-    if (lane < 16) {
-        const int bx = (lane & 1) | (((lane >> 2) & 1) << 1), by = ((lane >> 1) & 1) | ((lane >> 3) << 1);
-        dst = out + (by * 4) * 16 + bx * 4; dst_stride = 16;
-    } else {
-        const int b = lane & 3, pl = (lane >> 2) & 1;
-        dst = out + 256 + pl * 64 + ((b >> 1) * 4) * 8 + (b & 1) * 4; dst_stride = 8;
+    const long long n_groups = (p.n_mbs + K1_GROUP - 1) / K1_GROUP;
+    const long long stride = (long long)gridDim.x * K1_WARPS;
+    long long g = (long long)blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
+
+    /* side information of a group, one 32-bit word per lane: lane = 8*j + t for macroblock j;
+     * t = 0..3 luma modes 4t..4t+3, t = 4 mb_kind, 5 QPY, 6 Intra16x16PredMode, 7 intra_chroma_pred_mode */
+    const int mj = lane >> 3, mt = lane & 7;
+    auto load_meta = [&](long long grp) -> unsigned {
+        const long long mb = grp * K1_GROUP + mj;
+        if (mb >= p.n_mbs) return 0u;
+        if (mt < 4) return __ldg(reinterpret_cast<const unsigned *>(p.luma_modes + mb * 16) + mt);
+        const uint8_t *src = mt == 4 ? p.mb_kind : mt == 5 ? reinterpret_cast<const uint8_t *>(p.qp_y)
+                           : mt == 6 ? p.i16_mode : p.chroma_mode;
+        return (unsigned)__ldg(src + mb);
+    };
+    auto issue_load = [&](int buf, long long grp) {
+        const long long mb0 = grp * K1_GROUP;
+        const unsigned bytes = (unsigned)min((long long)K1_GROUP, p.n_mbs - mb0) * 768u;
+        mvg_mbar_expect_tx(&s.mbar[buf], bytes);
+        mvg_bulk_load(s.tile[buf], p.coeff + mb0 * 384, bytes, &s.mbar[buf]);
+    };
+
+    unsigned nmeta = 0;
+    if (g < n_groups) {
+        if (lane == 0) issue_load(0, g);
+        nmeta = load_meta(g);
     }
+    unsigned parity = 0;            /* bit b: phase parity of mbar[b] */
 
-    /* per-MB side information, one byte per lane: lanes 0..15 luma modes, 16 mb_kind,
-     * 17 Intra16x16PredMode, 18 intra_chroma_pred_mode, 19 QPY */
-    const uint8_t *meta_src = lane < 16 ? p.luma_modes + lane
-                            : lane == 16 ? p.mb_kind : lane == 17 ? p.i16_mode
-                            : lane == 18 ? p.chroma_mode : reinterpret_cast<const uint8_t *>(p.qp_y);
-    const long long meta_stride = lane < 16 ? 16 : 1;
-    long long mb = (long long)blockIdx.x * K1_WARPS + w;
-    uint4 na = make_uint4(0, 0, 0, 0), nb = na;
-    int nmeta = 0;
-    if (mb < p.n_mbs) {
-        if (lane < 24) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.coeff + mb * 384 + lane * 16);
-            na = __ldg(src); nb = __ldg(src + 1);
-        }
-        if (lane < 20) nmeta = __ldg(meta_src + mb * meta_stride);
-    }
-
-    for (; mb < p.n_mbs; mb += n_warps) {
-        const uint4 a = na, b = nb;
-        const int mode_byte = nmeta;
-        const int kind = __shfl_sync(MVG_FULL, nmeta, 16);
-        const int qp = (signed char)__shfl_sync(MVG_FULL, nmeta, 19);
-        const unsigned w0 = (unsigned)kind | ((unsigned)__shfl_sync(MVG_FULL, nmeta, 17) << 8) |
-                            ((unsigned)__shfl_sync(MVG_FULL, nmeta, 18) << 16);
-        {   /* prefetch the next macroblock of this warp */
-            const long long nx = mb + n_warps;
-            if (nx < p.n_mbs) {
-                if (lane < 24) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(p.coeff + nx * 384 + lane * 16);
-                    na = __ldg(src); nb = __ldg(src + 1);
-                }
-                if (lane < 20) nmeta = __ldg(meta_src + nx * meta_stride);
+    for (int it = 0; g < n_groups; g += stride, it++) {
+        const int buf = it & 1;
+        const unsigned meta = nmeta;
+        {   /* next group: its buffer was the source of the previous bulk store */
+            const long long gn = g + stride;
+            if (gn < n_groups) {
+                if (lane == 0) { mvg_bulk_wait_read(); issue_load(buf ^ 1, gn); }
+                nmeta = load_meta(gn);
             }
         }
+        const long long mb0 = g * K1_GROUP;
+        const int nmb = (int)min((long long)K1_GROUP, p.n_mbs - mb0);
+        int16_t *tile = s.tile[buf];
 
-        /* ---------------- 4x4 blocks ---------------- */
-        const bool luma4 = (kind != MVG_MB_I8x8);
-        const bool active = lane < 24 && (is_chroma || luma4);
-        int c[16];                              /* matrix, row-major, after inverse zig-zag */
-        {
-            /* zig-zag k -> (row,col): utils.h:64 / spec Table 8-13 */
-            c[0] = (short)(a.x & 0xffff); c[1] = (int)a.x >> 16; c[4] = (short)(a.y & 0xffff); c[8] = (int)a.y >> 16;
-            c[5] = (short)(a.z & 0xffff); c[2] = (int)a.z >> 16; c[3] = (short)(a.w & 0xffff); c[6] = (int)a.w >> 16;
-            c[9] = (short)(b.x & 0xffff); c[12] = (int)b.x >> 16; c[13] = (short)(b.y & 0xffff); c[10] = (int)b.y >> 16;
-            c[7] = (short)(b.z & 0xffff); c[11] = (int)b.z >> 16; c[14] = (short)(b.w & 0xffff); c[15] = (int)b.w >> 16;
-        }
-        if (kind == MVG_MB_I8x8) {              /* warp-uniform: stage the luma levels for the 8x8 path */
-            if (lane < 16) {
-                reinterpret_cast<uint4 *>(s_in[w])[2 * lane] = a;
-                reinterpret_cast<uint4 *>(s_in[w])[2 * lane + 1] = b;
+        /* per-lane view of "my" macroblock j = lane >> 3 */
+        const int kind_j = (int)__shfl_sync(MVG_FULL, meta, (lane & ~7) + 4);
+        const int qp_j = (signed char)__shfl_sync(MVG_FULL, meta, (lane & ~7) + 5);
+        if (mt == 0) s.meta[mj] = (unsigned)kind_j | ((unsigned)(qp_j & 255) << 8);
+
+        mvg_mbar_wait(&s.mbar[buf], (parity >> buf) & 1u);
+        parity ^= 1u << buf;
+
+        /* ---------------- DC transforms ---------------- */
+        if (mj < nmb) {
+            const int16_t *cf = tile + mj * 384;
+            if (kind_j == MVG_MB_I16x16 && mt < 4) {         /* row mt of c: t = c * H */
+                const int a = cf[mvg_blk_of(0, mt) * 16], b = cf[mvg_blk_of(1, mt) * 16];
+                const int c = cf[mvg_blk_of(2, mt) * 16], d = cf[mvg_blk_of(3, mt) * 16];
+                int32_t *f1 = s.f1[mj] + mt * 4;
+                f1[0] = a + b + c + d; f1[1] = a + b - c - d; f1[2] = a - b - c + d; f1[3] = a - b + c - d;
+            } else if (mt == 4 || mt == 5) {                 /* chroma plane mt-4: f = A c A, then scale */
+                const int pl = mt - 4;
+                const int16_t *cc = cf + 256 + pl * 64;
+                const int c00 = cc[0], c01 = cc[16], c10 = cc[32], c11 = cc[48];
+                const int qpc = mvg_chroma_qp(qp_j, pl ? cr_off : cb_off);
+                const int qd = qpc / 6, ls00 = s_ls4[((pl + 1) * 6 + (qpc - 6 * qd)) * 16];
+                const int f[4] = {c00 + c01 + c10 + c11, c00 - c01 + c10 - c11, c00 + c01 - c10 - c11, c00 - c01 - c10 + c11};
+#pragma unroll
+                for (int k = 0; k < 4; k++) s.dc[mj][16 + pl * 4 + k] = (int)((unsigned)(f[k] * ls00) << qd) >> 5;
             }
         }
-
-        /* quantiser of this lane's block */
-        int qpb = qp;
-        if (comp) qpb = mvg_chroma_qp(qp, comp == 1 ? cb_off : cr_off);
-        const int qd = qpb / 6, qm = qpb - 6 * qd;
-        const int ls00 = s_ls4[(comp * 6 + qm) * 16];
-        bool keep_dc = is_chroma;
-
-        /* Intra16x16 luma DC: f = H c H over the 16 lanes (h264_transform.c:783-808) */
-        if (kind == MVG_MB_I16x16) {            /* warp-uniform */
-            const int bi = ((lane >> 1) & 1) | (((lane >> 3) & 1) << 1);
-            const int bj = (lane & 1) | (((lane >> 2) & 1) << 1);
-            /* rows of H (h264_transform.c:62-68) as sign masks over k: 0000, 1100, 0110, 1010 */
-            const unsigned hs_i = (0xA6C0u >> (4 * bi)) & 0xF;
-            const unsigned hs_j = (0xA6C0u >> (4 * bj)) & 0xF;
-            int f = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-#pragma unroll
-                for (int l = 0; l < 4; l++) {
-                    const int src = (l & 1) | ((k & 1) << 1) | ((l >> 1) << 2) | ((k >> 1) << 3);
-                    const int v = __shfl_sync(MVG_FULL, c[0], src);
-                    const unsigned neg = ((hs_i >> k) ^ (hs_j >> l)) & 1u;
-                    f += neg ? -v : v;
-                }
-            const int t = f * ls00;
-            const int dcy = (qp >= 36) ? (int)((unsigned)t << (qd - 6)) : ((t + (1 << (5 - qd))) >> (6 - qd));
-            if (lane < 16) { c[0] = dcy; keep_dc = true; }
-        }
-        /* chroma DC 2x2 (h264_transform.c:988-1005, :924-936) over lane groups 16..19, 20..23 */
-        {
-            const int base = lane & ~3, r = (lane >> 1) & 1, cc = lane & 1;
-            int f = 0;
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-                const int v = __shfl_sync(MVG_FULL, c[0], base + s);
-                const int neg = (r & (s >> 1)) ^ (cc & (s & 1));
-                f += neg ? -v : v;
-            }
-            if (is_chroma && lane < 24) c[0] = (int)((unsigned)(f * ls00) << qd) >> 5;
-        }
-
-        unsigned nz_any = 0;
-        if (active) {
-#pragma unroll
-            for (int k = 0; k < 16; k++) nz_any |= (unsigned)c[k];
-            /* quant4x4, h264_transform.c:1100-1134 */
-            const int dc_in = c[0];
-            const int32_t *lq = s_ls4q + (comp * 52 + qpb) * 16;
-            if (qpb > 23) {
-#pragma unroll
-                for (int k = 0; k < 16; k++) c[k] = c[k] * lq[k];
-            } else {
-                const int rnd = 1 << (3 - qd), sh = 4 - qd;
-#pragma unroll
-                for (int k = 0; k < 16; k++) c[k] = (c[k] * lq[k] + rnd) >> sh;
-            }
-            if (keep_dc) c[0] = dc_in;
-            c[0] += 32;                         /* rounding of the final >> 6 (h264_transform.c:1190) */
-            /* idct4x4: rows then columns */
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                mvg_bfly4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3], c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                mvg_bfly4(c[j], c[4 + j], c[8 + j], c[12 + j], c[j], c[4 + j], c[8 + j], c[12 + j]);
+        __syncwarp();
+        if (mj < nmb && kind_j == MVG_MB_I16x16 && mt < 4) { /* column mt: f = H * t, then scale */
+            const int32_t *f1 = s.f1[mj];
+            const int a = f1[mt], b = f1[4 + mt], c = f1[8 + mt], d = f1[12 + mt];
+            const int f[4] = {a + b + c + d, a + b - c - d, a - b - c + d, a - b + c - d};
+            const int qd = qp_j / 6, ls00 = s_ls4[(qp_j - 6 * qd) * 16];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                uint2 pk;
-                pk.x = mvg_pack_sat16(c[4 * i + 1] >> 6, c[4 * i] >> 6);
-                pk.y = mvg_pack_sat16(c[4 * i + 3] >> 6, c[4 * i + 2] >> 6);
-                *reinterpret_cast<uint2 *>(dst + i * dst_stride) = pk;
+                const int t = f[i] * ls00;
+                s.dc[mj][mvg_blk_of(mt, i)] = (qp_j >= 36) ? (int)((unsigned)t << (qd - 6)) : ((t + (1 << (5 - qd))) >> (6 - qd));
             }
-        }
-        unsigned nzmask = __ballot_sync(MVG_FULL, nz_any != 0) & (luma4 ? 0x00FFFFFFu : 0x00FF0000u);
-
-        /* ---------------- Intra8x8 luma ---------------- */
-        if (kind == MVG_MB_I8x8) {              /* warp-uniform */
-            __syncwarp();
-            const int b8 = lane >> 3, row = lane & 7;
-            const int qd8 = qp / 6, qm8 = qp - 6 * qd8;
-            const int32_t *l8 = s_ls8 + qm8 * 64 + row * 8;
-            int v[8];
-            unsigned any8 = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int lvl = s_in[w][b8 * 64 + s_zz8inv[row * 8 + j]];
-                any8 |= (unsigned)lvl;
-                const int t = lvl * l8[j];                /* quant8x8, h264_transform.c:1256-1284 */
-                v[j] = (qp > 35) ? (int)((unsigned)t << (qd8 - 6)) : ((t + (1 << (5 - qd8))) >> (6 - qd8));
-            }
-            if (row == 0) v[0] += 32;                     /* rounding of the final >> 6 (:1382) */
-            mvg_idct8_1d(v);                              /* row pass */
-#pragma unroll
-            for (int j = 0; j < 8; j++) s_tr[w][b8][row][j] = v[j];
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = s_tr[w][b8][i][row];   /* this lane now owns column `row` */
-            mvg_idct8_1d(v);                              /* column pass */
-            const int xo = (b8 & 1) * 8 + row, yo = (b8 >> 1) * 8;
-#pragma unroll
-            for (int i = 0; i < 8; i++) out[(yo + i) * 16 + xo] = (int16_t)min(max(v[i] >> 6, -32768), 32767);
-            const unsigned bal = __ballot_sync(MVG_FULL, any8 != 0);
-#pragma unroll
-            for (int q = 0; q < 4; q++) if ((bal >> (8 * q)) & 0xFFu) nzmask |= 0xFu << (4 * q);
         }
         __syncwarp();
 
-        /* ---------------- write residual + control record ---------------- */
-        uint4 *gout = reinterpret_cast<uint4 *>(p.resid + mb * 384);
-        const uint4 *sout = reinterpret_cast<const uint4 *>(out);
-        gout[lane] = sout[lane];
-        if (lane < 16) gout[32 + lane] = sout[32 + lane];
+        /* ---------------- classify the 4x4 blocks, compact the general ones ---------------- */
+        int n4 = 0, n8 = 0;
+        unsigned nzbal[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int u = lane + 32 * r, j = u / 24, b = u - 24 * j;
+            bool general = false, nonzero = false, nz8q = false;
+            const unsigned mw = j < nmb ? s.meta[j] : 0u;
+            const int kind = mw & 255, qp = (signed char)(mw >> 8);
+            const bool is8 = kind == MVG_MB_I8x8 && b < 16;
+            if (j < nmb) {
+                uint4 *blk = reinterpret_cast<uint4 *>(tile + j * 384 + b * 16);
+                const uint4 w0 = blk[0], w1 = blk[1];
+                const unsigned rest = (w0.x & 0xffff0000u) | w0.y | w0.z | w0.w | w1.x | w1.y | w1.z | w1.w;
+                const int dcraw = (short)(w0.x & 0xffff);
+                if (is8) nz8q = (rest | (unsigned)dcraw) != 0;
+                else if (rest) general = nonzero = true;
+                else {
+                    const bool has_dc = b >= 16 || kind == MVG_MB_I16x16;
+                    int rv = 0;
+                    if (has_dc) rv = (s.dc[j][b] + 32) >> 6;          /* d00 = c00 (h264_transform.c:1126-1129) */
+                    else if (dcraw) {
+                        const int qd = qp / 6, lq = s_ls4q[qp * 16];
+                        const int d = qp > 23 ? dcraw * lq : (dcraw * lq + (1 << (3 - qd))) >> (4 - qd);
+                        rv = (d + 32) >> 6;
+                    }
+                    rv = min(max(rv, -32768), 32767);
+                    nonzero = rv != 0;
+                    if (nonzero || dcraw) {
+                        const unsigned pk = (unsigned)(rv & 0xffff) * 0x10001u;
+                        blk[0] = make_uint4(pk, pk, pk, pk); blk[1] = make_uint4(pk, pk, pk, pk);
+                    }
+                }
+            }
+            const unsigned gb = __ballot_sync(MVG_FULL, general);
+            if (general) s.list4[n4 + __popc(gb & ((1u << lane) - 1))] = (uint8_t)u;
+            n4 += __popc(gb);
+            /* Intra8x8: slots 4*b8..4*b8+3 are the four quarters of 8x8 block b8 (aligned lane quads) */
+            const unsigned qb = __ballot_sync(MVG_FULL, nz8q);
+            const bool any8 = is8 && ((qb >> (lane & ~3)) & 0xFu) != 0;
+            const bool lead8 = any8 && (lane & 3) == 0;
+            const unsigned lb = __ballot_sync(MVG_FULL, lead8);
+            if (lead8) s.list8[n8 + __popc(lb & ((1u << lane) - 1))] = (uint8_t)(j * 4 + (b >> 2));
+            n8 += __popc(lb);
+            nzbal[r] = __ballot_sync(MVG_FULL, nonzero || any8);
+        }
+        __syncwarp();
 
-        /* 16 prediction modes -> 16 nibbles: OR-reduce inside each group of 8 lanes */
-        unsigned nib = lane < 16 ? (unsigned)(mode_byte & 15) << (4 * (lane & 7)) : 0u;
-        nib |= __shfl_xor_sync(MVG_FULL, nib, 1);
-        nib |= __shfl_xor_sync(MVG_FULL, nib, 2);
-        nib |= __shfl_xor_sync(MVG_FULL, nib, 4);
-        const unsigned w2 = __shfl_sync(MVG_FULL, nib, 8);
-        if (lane == 0) *reinterpret_cast<uint4 *>(p.ctl + mb) = make_uint4(w0, nib, w2, nzmask);
+        /* ---------------- general 4x4 blocks, 32 per pass ---------------- */
+        for (int base = 0; base < n4; base += 32) {
+            if (base + lane < n4) {
+                const int u = s.list4[base + lane], j = u / 24, b = u - 24 * j;
+                const unsigned mw = s.meta[j];
+                const int kind = mw & 255, qp = (signed char)(mw >> 8);
+                const int comp = b < 16 ? 0 : (b < 20 ? 1 : 2);
+                const int qpb = comp ? mvg_chroma_qp(qp, comp == 1 ? cb_off : cr_off) : qp;
+                uint4 *blk = reinterpret_cast<uint4 *>(tile + j * 384 + b * 16);
+                const uint4 a = blk[0], bb = blk[1];
+                int c[16];                      /* zig-zag k -> (row,col): utils.h:64 / spec Table 8-13 */
+                c[0] = (short)(a.x & 0xffff); c[1] = (int)a.x >> 16; c[4] = (short)(a.y & 0xffff); c[8] = (int)a.y >> 16;
+                c[5] = (short)(a.z & 0xffff); c[2] = (int)a.z >> 16; c[3] = (short)(a.w & 0xffff); c[6] = (int)a.w >> 16;
+                c[9] = (short)(bb.x & 0xffff); c[12] = (int)bb.x >> 16; c[13] = (short)(bb.y & 0xffff); c[10] = (int)bb.y >> 16;
+                c[7] = (short)(bb.z & 0xffff); c[11] = (int)bb.z >> 16; c[14] = (short)(bb.w & 0xffff); c[15] = (int)bb.w >> 16;
+                const bool keep_dc = comp != 0 || kind == MVG_MB_I16x16;
+                const int dc_in = keep_dc ? s.dc[j][b] : 0;
+                /* quant4x4, h264_transform.c:1100-1134 */
+                const int4 *lq = reinterpret_cast<const int4 *>(s_ls4q + (comp * 52 + qpb) * 16);
+                const int4 l0 = lq[0], l1 = lq[1], l2 = lq[2], l3 = lq[3];
+                const int ls[16] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w, l2.x, l2.y, l2.z, l2.w, l3.x, l3.y, l3.z, l3.w};
+                if (qpb > 23) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) c[k] = c[k] * ls[k];
+                } else {
+                    const int qd = qpb / 6, rnd = 1 << (3 - qd), sh = 4 - qd;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) c[k] = (c[k] * ls[k] + rnd) >> sh;
+                }
+                if (keep_dc) c[0] = dc_in;
+                c[0] += 32;                     /* rounding of the final >> 6 (h264_transform.c:1190) */
+#pragma unroll
+                for (int i = 0; i < 4; i++)     /* idct4x4: rows, then columns */
+                    mvg_bfly4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3], c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    mvg_bfly4(c[q], c[4 + q], c[8 + q], c[12 + q], c[q], c[4 + q], c[8 + q], c[12 + q]);
+                uint4 o0, o1;
+                o0.x = mvg_pack_sat16(c[1] >> 6, c[0] >> 6);   o0.y = mvg_pack_sat16(c[3] >> 6, c[2] >> 6);
+                o0.z = mvg_pack_sat16(c[5] >> 6, c[4] >> 6);   o0.w = mvg_pack_sat16(c[7] >> 6, c[6] >> 6);
+                o1.x = mvg_pack_sat16(c[9] >> 6, c[8] >> 6);   o1.y = mvg_pack_sat16(c[11] >> 6, c[10] >> 6);
+                o1.z = mvg_pack_sat16(c[13] >> 6, c[12] >> 6); o1.w = mvg_pack_sat16(c[15] >> 6, c[14] >> 6);
+                blk[0] = o0; blk[1] = o1;
+            }
+        }
+
+        /* ---------------- non-zero 8x8 blocks, 4 per pass ---------------- */
+        for (int base = 0; base < n8; base += 4) {
+            const int slot = base + (lane >> 3), row = lane & 7;
+            const bool act = slot < n8;
+            int v[8];
+            int16_t *o8 = tile;
+            if (act) {
+                const int id = s.list8[slot], j = id >> 2, b8 = id & 3;
+                const int qp = (signed char)(s.meta[j] >> 8);
+                const int qd8 = qp / 6;
+                const int32_t *l8 = s_ls8 + (qp - 6 * qd8) * 64 + row * 8;
+                const int16_t *in = tile + j * 384 + b8 * 64;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int t = (int)in[s_zz8inv[row * 8 + q]] * l8[q];       /* quant8x8, h264_transform.c:1256-1284 */
+                    v[q] = (qp > 35) ? (int)((unsigned)t << (qd8 - 6)) : ((t + (1 << (5 - qd8))) >> (6 - qd8));
+                }
+                if (row == 0) v[0] += 32;                                       /* rounding of the final >> 6 (:1382) */
+                mvg_idct8_1d(v);                                                /* row pass */
+#pragma unroll
+                for (int q = 0; q < 8; q++) s.tr[lane >> 3][row][q] = v[q];
+                o8 = tile + j * 384 + (b8 * 4 + (row >> 2)) * 16 + (row & 3);
+            }
+            __syncwarp();
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = s.tr[lane >> 3][i][row];     /* this lane now owns column `row` */
+                mvg_idct8_1d(v);                                                /* column pass */
+#pragma unroll
+                for (int i = 0; i < 8; i++) o8[(i >> 2) * 32 + (i & 3) * 4] = (int16_t)min(max(v[i] >> 6, -32768), 32767);
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+
+        /* ---------------- residual out (one bulk store) + control records ---------------- */
+        if (lane == 0) mvg_bulk_store(p.resid + mb0 * 384, tile, (unsigned)nmb * 768u);
+        {
+            /* 96-bit non-zero map -> 24 bits per macroblock */
+            const unsigned long long lo = (unsigned long long)nzbal[0] | ((unsigned long long)nzbal[1] << 32);
+            const unsigned hi = nzbal[2];
+            const unsigned nz = mj == 0 ? nzbal[0] : mj == 1 ? (unsigned)(lo >> 24)
+                              : mj == 2 ? ((unsigned)(lo >> 48) | (hi << 16)) : (hi >> 8);
+            /* 4 mode bytes -> 4 nibbles; lane 8j collects its macroblock's record */
+            unsigned nib = (meta & 0xF) | ((meta >> 4) & 0xF0) | ((meta >> 8) & 0xF00) | ((meta >> 12) & 0xF000);
+            const unsigned n1 = __shfl_down_sync(MVG_FULL, nib, 1), n2 = __shfl_down_sync(MVG_FULL, nib, 2);
+            const unsigned n3 = __shfl_down_sync(MVG_FULL, nib, 3);
+            const unsigned k4 = __shfl_down_sync(MVG_FULL, meta, 4), k6 = __shfl_down_sync(MVG_FULL, meta, 6);
+            const unsigned k7 = __shfl_down_sync(MVG_FULL, meta, 7);
+            if (mt == 0 && mj < nmb)
+                *reinterpret_cast<uint4 *>(p.ctl + mb0 + mj) =
+                    make_uint4((k4 & 255) | ((k6 & 255) << 8) | ((k7 & 255) << 16), nib | (n1 << 16), n2 | (n3 << 16), nz & 0x00FFFFFFu);
+        }
         __syncwarp();
     }
+    if (lane == 0) mvg_bulk_wait_read();
 }
 
 /* ========================================================================= */
@@ -400,8 +495,12 @@ __device__ __forceinline__ void k2_luma16(K2WarpSmem &s, int lane, int mode, boo
 #pragma unroll
         for (int k = 0; k < 8; k++) pred[k] = mvg_clip8((base + b * (x0 + k - 7)) >> 5);
     }
-    const uint4 r = *reinterpret_cast<const uint4 *>(s.resid + y * 16 + x0);
-    const unsigned rr[4] = {r.x, r.y, r.z, r.w};
+    /* row y, samples x0..x0+7: 4x4 blocks (x0/4, y/4) and (x0/4+1, y/4), row y&3 of each */
+    const int bcol = x0 >> 2, brow = y >> 2;
+    const int blkA = (bcol & 1) | ((brow & 1) << 1) | ((bcol >> 1) << 2) | ((brow >> 1) << 3);
+    const uint2 ra = *reinterpret_cast<const uint2 *>(s.resid + blkA * 16 + (y & 3) * 4);
+    const uint2 rb = *reinterpret_cast<const uint2 *>(s.resid + (blkA + 1) * 16 + (y & 3) * 4);
+    const unsigned rr[4] = {ra.x, ra.y, rb.x, rb.y};
     unsigned lo = 0, hi = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -451,7 +550,7 @@ __device__ __forceinline__ void k2_luma4_step(K2WarpSmem &s, const uint32_t *lut
             pred = ((int)nb[taps & 255] + (int)nb[(taps >> 8) & 255] + (int)nb[(taps >> 16) & 255] +
                     (int)nb[taps >> 24] + 2) >> 2;
         }
-        const int r = s.resid[by * 64 + bx * 4 + pxy];
+        const int r = s.resid[blk * 16 + pix];
         lt[org + (pxy >> 4) * MVG_LT_STRIDE + (pxy & 3)] = (uint8_t)mvg_add_clip8(pred, r);
     }
     __syncwarp();
@@ -523,7 +622,7 @@ __device__ __forceinline__ void k2_luma8(K2WarpSmem &s, const uint32_t *lut8, in
             const uint32_t taps = lut8[mode * 64 + y * 8 + px];
             const int pred = ((int)s.n8[taps & 255] + (int)s.n8[(taps >> 8) & 255] +
                               (int)s.n8[(taps >> 16) & 255] + (int)s.n8[taps >> 24] + 2) >> 2;
-            const int r = s.resid[(yo + y) * 16 + xo + px];
+            const int r = s.resid[(b8 * 4 + (y >> 2) * 2 + (px >> 2)) * 16 + (y & 3) * 4 + (px & 3)];
             lt[org + y * MVG_LT_STRIDE + px] = (uint8_t)mvg_add_clip8(pred, r);
         }
         __syncwarp();
@@ -570,7 +669,7 @@ __device__ __forceinline__ void k2_chroma(K2WarpSmem &s, int lane, int mode, boo
 #pragma unroll
         for (int k = 0; k < 4; k++) pred[k] = mvg_clip8((base + b * (x0 + k - 3)) >> 5);
     }
-    const uint2 r = *reinterpret_cast<const uint2 *>(s.resid + 256 + pl * 64 + y * 8 + x0);
+    const uint2 r = *reinterpret_cast<const uint2 *>(s.resid + 256 + pl * 64 + ((y >> 2) * 2 + (x0 >> 2)) * 16 + (y & 3) * 4);
     const unsigned p0 = (unsigned)mvg_add_clip8(pred[0], (short)(r.x & 0xffff));
     const unsigned p1 = (unsigned)mvg_add_clip8(pred[1], (int)r.x >> 16);
     const unsigned p2 = (unsigned)mvg_add_clip8(pred[2], (short)(r.y & 0xffff));
