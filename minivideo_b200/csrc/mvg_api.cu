@@ -140,11 +140,11 @@ struct Ref { bool left; int i; };
 static Ref T(int i) { return {false, i}; }
 static Ref L(int i) { return i < 0 ? Ref{false, -1} : Ref{true, i}; }
 
-struct Taps { Ref r[4]; };
-static Taps tap3(Ref p, Ref q, Ref r) { return {{p, q, q, r}}; }   /* (p + 2q + r + 2) >> 2 */
-static Taps tap2(Ref p, Ref q) { return {{p, p, q, q}}; }          /* (p + q + 1) >> 1      */
-static Taps tap1(Ref p) { return {{p, p, p, p}}; }                 /* p                     */
-static Taps tapend(Ref p, Ref q) { return {{p, q, q, q}}; }        /* (p + 3q + 2) >> 2     */
+struct Taps { Ref r[4]; int form; };                                    /* form: 1 copy, 2 two-tap, 3 three-tap, 4 end */
+static Taps tap3(Ref p, Ref q, Ref r) { return {{p, q, q, r}, 3}; }   /* (p + 2q + r + 2) >> 2 */
+static Taps tap2(Ref p, Ref q) { return {{p, p, q, q}, 2}; }          /* (p + q + 1) >> 1      */
+static Taps tap1(Ref p) { return {{p, p, p, p}, 1}; }                 /* p                     */
+static Taps tapend(Ref p, Ref q) { return {{p, q, q, q}, 4}; }        /* (p + 3q + 2) >> 2     */
 
 /* spec 8.3.1.2.x (n = 4) and 8.3.2.2.x (n = 8); same formulas the reference codes at
  * h264_intra_prediction.c:496-926 and :1366-1793.  Mode 2 (DC) has no taps. */
@@ -210,19 +210,20 @@ extern "C" void mvg_build_luts(MvgLuts *out)
                     }
                     out->lut4[tr][mode][y * 4 + x] = word;
                 }
+    auto line8 = [](Ref r) { return r.left ? MVG_N8_LEFT(r.i) : MVG_N8_TOP(r.i); };
     for (int mode = 0; mode < 9; mode++)
         for (int y = 0; y < 8; y++)
             for (int x = 0; x < 8; x++) {
-                uint32_t word = 0;
-                if (mode == 2) word = MVG_N8_DC * 0x01010101u;
-                else {
-                    Taps t = nxn_taps(8, mode, x, y);
-                    for (int k = 0; k < 4; k++) {
-                        const int idx = t.r[k].left ? MVG_N8_LEFT(t.r[k].i) : MVG_N8_TOP(t.r[k].i);
-                        word |= (uint32_t)idx << (8 * k);
-                    }
+                int idx = MVG_N8_DC, shift = 0;
+                if (mode != 2) {
+                    const Taps t = nxn_taps(8, mode, x, y);
+                    if (t.form == 1) { idx = line8(t.r[0]); shift = 0; }
+                    else if (t.form == 2) {                       /* adjacent pair -> f2 of the lower index */
+                        const int a = line8(t.r[0]), b = line8(t.r[3]);
+                        idx = a < b ? a : b; shift = 8;
+                    } else { idx = line8(t.r[1]); shift = 16; }   /* centre (or the line end of an end tap) */
                 }
-                out->lut8[mode][y * 8 + x] = word;
+                out->lut8[mode][y * 8 + x] = (uint16_t)(idx * 4 | shift << 8);
             }
 }
 

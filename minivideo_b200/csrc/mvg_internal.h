@@ -39,9 +39,12 @@ struct MvgMbCtl { uint32_t w0, w1, w2, w3; };
  *   (the block's top-left sample - MVG_LUT4_BIAS); tr = 1 when p[4..7,-1] are
  *   available, else they alias p[3,-1] (h264_intra_prediction.c:431-439).
  *   Mode 2 (DC) is unused.
- * lut8[mode][y*8+x]: four uint8 indices into the 26-entry filtered neighbour
- *   line of an 8x8 block: 0..7 = p'[-1,7..0], 8 = p'[-1,-1], 9..24 = p'[0..15,-1],
- *   25 = the DC value (mode 2 points all four taps there).                      */
+ * lut8[mode][y*8+x]: the Intra8x8 predictors read a 26-entry filtered neighbour line
+ *   (0..7 = p'[-1,7..0], 8 = p'[-1,-1], 9..24 = p'[0..15,-1], 25 = the DC value), each
+ *   entry a 32-bit word {p', f2 = (p'[n]+p'[n+1]+1)>>1, f3 = (p'[n-1]+2p'[n]+p'[n+1]+2)>>2};
+ *   a sample is one byte of one word: low byte = 4*n (byte offset of the word), high byte =
+ *   bit shift (0 copy, 8 two-tap, 16 three-tap).  The 3- and 2-tap forms of the spec always
+ *   involve adjacent line entries, and the two "end" taps (p+3q) are f3 at a line end.      */
 #define MVG_LUT4_BIAS    (MVG_LT_STRIDE + 1)   /* p[-1,-1] is the lowest address */
 #define MVG_N8_LEFT(y)  (7 - (y))
 #define MVG_N8_CORNER   8
@@ -50,7 +53,7 @@ struct MvgMbCtl { uint32_t w0, w1, w2, w3; };
 
 struct MvgLuts {
     uint32_t lut4[2][9][16];
-    uint32_t lut8[9][64];
+    uint16_t lut8[9][64];
 };
 
 #ifdef __cplusplus

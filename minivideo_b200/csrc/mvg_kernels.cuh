@@ -435,7 +435,7 @@ struct K2WarpSmem {
     __align__(16) int16_t  resid[384];
     __align__(16) uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
     __align__(16) uint8_t  ct[2][MVG_CT_ROWS * MVG_CT_STRIDE];
-    __align__(16) uint8_t  n8[32];
+    __align__(16) uint32_t n8[32];      /* Intra8x8 neighbour line: p' | f2 << 8 | f3 << 16 per entry */
 };
 
 __device__ __forceinline__ uint2 mvg_ld_relaxed_u64(const uint2 *p)
@@ -573,60 +573,72 @@ __device__ __forceinline__ void k2_luma4(K2WarpSmem &s, const uint32_t *lut4, in
     k2_luma4_step<9>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
 }
 
-/* ---- Intra8x8 luma: 4 blocks in order, reference sample filter + taps -------- */
-__device__ __forceinline__ void k2_luma8(K2WarpSmem &s, const uint32_t *lut8, int lane,
-                                         unsigned mlo, bool availA, bool availB, bool availC, bool availD)
+/* ---- Intra8x8 luma: 4 blocks in order ------------------------------------------ */
+/* The 25 neighbours of a block form one line: n = 0..7 p[-1,7..0], 8 p[-1,-1], 9..24 p[0..15,-1].
+ * Lane n filters its entry (reference sample filter, h264_intra_prediction.c:1295-1353) and then
+ * derives, again with shuffles, the two smoothings every directional mode is built from:
+ *   f2[n] = (p'[n] + p'[n+1] + 1) >> 1,  f3[n] = (p'[n-1] + 2 p'[n] + p'[n+1] + 2) >> 2
+ * (line ends replicate).  Each predicted sample is then ONE of p'[i], f2[i], f3[i] -- the
+ * table lut8 says which (byte offset of entry i, bit shift of the variant). */
+struct K2Lane8 {            /* per-lane constants of the neighbour gather */
+    int off_tr, off_notr;   /* tile offset of this lane's neighbour relative to the block origin */
+};
+
+template <int B8>
+__device__ __forceinline__ void k2_luma8_block(K2WarpSmem &s, const uint16_t *lut8, int lane, const K2Lane8 &k,
+                                               unsigned mlo, bool availA, bool availB, bool availC, bool availD)
 {
     uint8_t *lt = s.lt;
-#pragma unroll 1
-    for (int b8 = 0; b8 < 4; b8++) {
-        const int xo = (b8 & 1) * 8, yo = (b8 >> 1) * 8;
-        const int mode = (int)((mlo >> (4 * b8)) & 15);
-        const bool left = xo > 0 || availA, up = yo > 0 || availB;
-        const bool upleft = b8 == 0 ? availD : (b8 == 1 ? availB : (b8 == 2 ? availA : true));
-        const bool tr = b8 == 0 ? availB : (b8 == 1 ? availC : (b8 == 2));
-        const int org = (yo + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + xo;
+    constexpr int xo = (B8 & 1) * 8, yo = (B8 >> 1) * 8;
+    constexpr int org = (yo + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + xo;
+    const int mode = (int)((mlo >> (4 * B8)) & 15);
+    const bool left = B8 & 1 ? true : availA, up = B8 & 2 ? true : availB;
+    const bool upleft = B8 == 0 ? availD : (B8 == 1 ? availB : (B8 == 2 ? availA : true));
+    const bool tr = B8 == 0 ? availB : (B8 == 1 ? availC : (B8 == 2));
 
-        /* neighbour line: n = 0..7 left[7..0], 8 corner, 9..24 top[0..15] */
-        int raw = 0;
-        if (lane < 8)        raw = lt[org + (7 - lane) * MVG_LT_STRIDE - 1];
-        else if (lane == 8)  raw = lt[org - MVG_LT_STRIDE - 1];
-        else if (lane < 25) {
-            int i = lane - 9;
-            if (i > 7 && !tr) i = 7;             /* h264_intra_prediction.c:1230-1236 */
-            raw = lt[org - MVG_LT_STRIDE + i];
-        }
-        int prev = __shfl_up_sync(MVG_FULL, raw, 1), next = __shfl_down_sync(MVG_FULL, raw, 1);
-        /* h264_intra_prediction.c:1295-1353 */
-        if (lane == 0) prev = raw;                              /* p'[-1,7] = (p[-1,6] + 3 p[-1,7] + 2) >> 2 */
-        if (lane == 24) next = raw;                             /* p'[15,-1] */
-        if (lane == 7 && !upleft) next = raw;                   /* p'[-1,0] without corner */
-        if (lane == 9 && !upleft) prev = raw;                   /* p'[0,-1] without corner */
-        if (lane == 8) { if (!left) prev = raw; if (!up) next = raw; }
-        const int filt = (prev + 2 * raw + next + 2) >> 2;
-        if (lane < 25) s.n8[lane] = (uint8_t)filt;
-        if (mode == 2) {                                        /* warp-uniform */
-            int v = 0;
-            if (lane < 8 && left) v = filt;
-            if (lane >= 9 && lane < 17 && up) v = filt;
+    const int raw = lt[org + (tr ? k.off_tr : k.off_notr)];
+    int prev = __shfl_up_sync(MVG_FULL, raw, 1), next = __shfl_down_sync(MVG_FULL, raw, 1);
+    if (lane == 0) prev = raw;                              /* p'[-1,7] = (p[-1,6] + 3 p[-1,7] + 2) >> 2 */
+    if (lane == 24) next = raw;                             /* p'[15,-1] */
+    if (!upleft) { if (lane == 7) next = raw; if (lane == 9) prev = raw; }
+    if (lane == 8) { if (!left) prev = raw; if (!up) next = raw; }
+    const int filt = (prev + 2 * raw + next + 2) >> 2;
+    int fp = __shfl_up_sync(MVG_FULL, filt, 1), fn = __shfl_down_sync(MVG_FULL, filt, 1);
+    if (lane == 0) fp = filt;
+    if (lane == 24) fn = filt;
+    const int f2 = (filt + fn + 1) >> 1, f3 = (fp + 2 * filt + fn + 2) >> 2;
+    if (lane < 25) s.n8[lane] = (unsigned)filt | ((unsigned)f2 << 8) | ((unsigned)f3 << 16);
+    if (mode == 2) {                                        /* warp-uniform */
+        int v = 0;
+        if (lane < 8 && left) v = filt;
+        if (lane >= 9 && lane < 17 && up) v = filt;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MVG_FULL, v, o);
-            v = (left && up) ? (v + 8) >> 4 : (left || up) ? (v + 4) >> 3 : 128;
-            if (lane == 0) s.n8[MVG_N8_DC] = (uint8_t)v;
-        }
-        __syncwarp();
-        const int px = lane & 7, py = lane >> 3;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int y = py + 4 * h;
-            const uint32_t taps = lut8[mode * 64 + y * 8 + px];
-            const int pred = ((int)s.n8[taps & 255] + (int)s.n8[(taps >> 8) & 255] +
-                              (int)s.n8[(taps >> 16) & 255] + (int)s.n8[taps >> 24] + 2) >> 2;
-            const int r = s.resid[(b8 * 4 + (y >> 2) * 2 + (px >> 2)) * 16 + (y & 3) * 4 + (px & 3)];
-            lt[org + y * MVG_LT_STRIDE + px] = (uint8_t)mvg_add_clip8(pred, r);
-        }
-        __syncwarp();
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MVG_FULL, v, o);
+        v = (left && up) ? (v + 8) >> 4 : (left || up) ? (v + 4) >> 3 : 128;
+        if (lane == 0) s.n8[MVG_N8_DC] = (unsigned)v;
     }
+    __syncwarp();
+    const int px = lane & 7, py = lane >> 3;
+    const uint16_t *lrow = lut8 + mode * 64 + lane;         /* sample (px, py), then (px, py + 4) */
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int y = py + 4 * h;
+        const unsigned e = lrow[32 * h];
+        const unsigned w = *reinterpret_cast<const unsigned *>(reinterpret_cast<const uint8_t *>(s.n8) + (e & 255));
+        const int pred = (w >> (e >> 8)) & 255;
+        const int r = s.resid[(B8 * 4 + (y >> 2) * 2 + (px >> 2)) * 16 + (y & 3) * 4 + (px & 3)];
+        lt[org + y * MVG_LT_STRIDE + px] = (uint8_t)mvg_add_clip8(pred, r);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void k2_luma8(K2WarpSmem &s, const uint16_t *lut8, int lane, const K2Lane8 &k,
+                                         unsigned mlo, bool availA, bool availB, bool availC, bool availD)
+{
+    k2_luma8_block<0>(s, lut8, lane, k, mlo, availA, availB, availC, availD);
+    k2_luma8_block<1>(s, lut8, lane, k, mlo, availA, availB, availC, availD);
+    k2_luma8_block<2>(s, lut8, lane, k, mlo, availA, availB, availC, availD);
+    k2_luma8_block<3>(s, lut8, lane, k, mlo, availA, availB, availC, availD);
 }
 
 /* ---- chroma, both planes at once (h264_intra_prediction.c:2338-2564) --------- */
@@ -695,11 +707,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 8)
 k2_wavefront(K2Params p)
 {
     __shared__ uint32_t s_lut4[2 * 9 * 16];
-    __shared__ uint32_t s_lut8[9 * 64];
+    __shared__ uint16_t s_lut8[9 * 64];
     __shared__ K2WarpSmem s_warp[K2_WARPS];
 
     for (int i = threadIdx.x; i < 2 * 9 * 16; i += blockDim.x) s_lut4[i] = (&p.luts->lut4[0][0][0])[i];
-    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) s_lut8[i] = (&p.luts->lut8[0][0])[i];
+    for (int i = threadIdx.x; i < 9 * 64 / 2; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(s_lut8)[i] = reinterpret_cast<const uint32_t *>(&p.luts->lut8[0][0])[i];
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -710,9 +723,27 @@ k2_wavefront(K2Params p)
     const int total = p.n_pics * H;
     const unsigned epoch = p.epoch;
 
-    /* byte offset inside the tiles of the halo word this lane carries (lanes 0..7) */
-    const int halo_pl = lane < 4 ? -1 : ((lane - 4) >> 1);
-    const int halo_x = lane < 4 ? lane * 4 : ((lane - 4) & 1) * 4;
+    /* per-lane constants --------------------------------------------------------------- */
+    /* halo word carried by lanes 0..7: 0..3 luma x = 4*lane, 4,5 Cb, 6,7 Cr */
+    uint8_t *const halo_top = lane < 4 ? s.lt + MVG_LT_XOFF + lane * 4
+                                       : s.ct[(lane >> 1) & 1] + MVG_CT_XOFF + (lane & 1) * 4;      /* sample row -1 */
+    const uint8_t *const halo_bot = lane < 4 ? halo_top + 16 * MVG_LT_STRIDE : halo_top + 8 * MVG_CT_STRIDE;
+    /* column x = 15 -> x = -1 hand-over: lanes 0..16 luma rows -1..15, lanes 17..25 Cb rows -1..7, and a
+     * second move by lanes 0..8 for Cr */
+    uint8_t *const lc_dst = lane < 17 ? s.lt + lane * MVG_LT_STRIDE + MVG_LT_XOFF - 1
+                                      : s.ct[0] + (lane < 26 ? lane - 17 : 0) * MVG_CT_STRIDE + MVG_CT_XOFF - 1;
+    const int lc_span = lane < 17 ? 16 : 8;
+    uint8_t *const lc_dst2 = s.ct[1] + (lane < 9 ? lane : 0) * MVG_CT_STRIDE + MVG_CT_XOFF - 1;
+    /* picture write-out: lanes 0..15 one luma row (16 B), lanes 16..23 Cb rows, 24..31 Cr rows (8 B) */
+    const uint8_t *const wo_src = lane < 16 ? s.lt + (lane + 1) * MVG_LT_STRIDE + MVG_LT_XOFF
+                                            : s.ct[(lane >> 3) & 1] + ((lane & 7) + 1) * MVG_CT_STRIDE + MVG_CT_XOFF;
+    /* Intra8x8 neighbour gather */
+    K2Lane8 k8;
+    if (lane < 8)       k8.off_tr = (7 - lane) * MVG_LT_STRIDE - 1;
+    else if (lane == 8) k8.off_tr = -MVG_LT_STRIDE - 1;
+    else if (lane < 25) k8.off_tr = -MVG_LT_STRIDE + (lane - 9);
+    else                k8.off_tr = 0;
+    k8.off_notr = (lane > 16 && lane < 25) ? -MVG_LT_STRIDE + 7 : k8.off_tr;     /* p[8..15,-1] := p[7,-1] */
 
     for (;;) {
         int item = 0;
@@ -726,7 +757,10 @@ k2_wavefront(K2Params p)
         const int slot = p.first_slot + g * p.group + (within - row * gsize);
 
         uint8_t *ybase = p.yuv + (size_t)slot * pic_bytes;
-        uint8_t *cbbase = ybase + (size_t)n_mb * 256, *crbase = cbbase + (size_t)n_mb * 64;
+        /* where this lane writes its row of every macroblock of this macroblock row */
+        uint8_t *wo_dst = lane < 16 ? ybase + (size_t)(row * 16 + lane) * ystride
+                                    : ybase + (size_t)n_mb * (lane < 24 ? 256 : 320) + (size_t)(row * 8 + (lane & 7)) * cstride;
+        const int wo_step = lane < 16 ? 16 : 8;
         const int16_t *resid = p.resid + ((size_t)slot * n_mb + (size_t)row * W) * 384;
         const MvgMbCtl *ctl = p.ctl + (size_t)slot * n_mb + (size_t)row * W;
         const bool availB = row > 0, publish = row < H - 1;
@@ -775,12 +809,8 @@ k2_wavefront(K2Params p)
                     }
                 }
                 /* sample row -1 of the tiles: x = 0..15 from cur, x = 16..23 from nxt */
-                if (lane < 4) {
-                    *reinterpret_cast<unsigned *>(s.lt + MVG_LT_XOFF + halo_x) = cur.x;
-                    if (lane < 2) *reinterpret_cast<unsigned *>(s.lt + MVG_LT_XOFF + 16 + halo_x) = nxt.x;
-                } else if (lane < 8) {
-                    *reinterpret_cast<unsigned *>(s.ct[halo_pl] + MVG_CT_XOFF + halo_x) = cur.x;
-                }
+                if (lane < 8) *reinterpret_cast<unsigned *>(halo_top) = cur.x;
+                if (lane < 2) *reinterpret_cast<unsigned *>(halo_top + 16) = nxt.x;
                 cur = nxt;
                 if (mx + 2 < W && lane < 8) nxt = mvg_ld_relaxed_u64(habove + (size_t)(mx + 2) * 8);
             }
@@ -789,31 +819,25 @@ k2_wavefront(K2Params p)
             const int kind = ctlw.x & 255, i16 = (ctlw.x >> 8) & 255, cmode = (ctlw.x >> 16) & 255;
             if (kind == MVG_MB_I16x16)    k2_luma16(s, lane, i16, availA, availB);
             else if (kind == MVG_MB_I4x4) k2_luma4(s, s_lut4, lane, ctlw.y, ctlw.z, availA, availB, availC);
-            else                          k2_luma8(s, s_lut8, lane, ctlw.y, availA, availB, availC, availD);
+            else                          k2_luma8(s, s_lut8, lane, k8, ctlw.y, availA, availB, availC, availD);
             k2_chroma(s, lane, cmode, availA, availB);
             __syncwarp();
 
             /* write the macroblock to the planar picture */
             if (lane < 16) {
-                const uint2 a = *reinterpret_cast<const uint2 *>(s.lt + (lane + 1) * MVG_LT_STRIDE + MVG_LT_XOFF);
-                const uint2 b = *reinterpret_cast<const uint2 *>(s.lt + (lane + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + 8);
-                *reinterpret_cast<uint4 *>(ybase + (size_t)(row * 16 + lane) * ystride + mx * 16) = make_uint4(a.x, a.y, b.x, b.y);
+                const uint2 a = *reinterpret_cast<const uint2 *>(wo_src);
+                const uint2 b = *reinterpret_cast<const uint2 *>(wo_src + 8);
+                *reinterpret_cast<uint4 *>(wo_dst) = make_uint4(a.x, a.y, b.x, b.y);
             } else {
-                const int pl = (lane >> 3) & 1, y = lane & 7;
-                const uint2 a = *reinterpret_cast<const uint2 *>(s.ct[pl] + (y + 1) * MVG_CT_STRIDE + MVG_CT_XOFF);
-                *reinterpret_cast<uint2 *>((pl ? crbase : cbbase) + (size_t)(row * 8 + y) * cstride + mx * 8) = a;
+                *reinterpret_cast<uint2 *>(wo_dst) = *reinterpret_cast<const uint2 *>(wo_src);
             }
+            wo_dst += wo_step;
             /* publish the bottom sample line for the row below */
-            if (publish && lane < 8) {
-                const unsigned d = lane < 4
-                    ? *reinterpret_cast<const unsigned *>(s.lt + 16 * MVG_LT_STRIDE + MVG_LT_XOFF + halo_x)
-                    : *reinterpret_cast<const unsigned *>(s.ct[halo_pl] + 8 * MVG_CT_STRIDE + MVG_CT_XOFF + halo_x);
-                mvg_st_relaxed_u64(hmine + (size_t)mx * 8, d, epoch);
-            }
+            if (publish && lane < 8)
+                mvg_st_relaxed_u64(hmine + (size_t)mx * 8, *reinterpret_cast<const unsigned *>(halo_bot), epoch);
             /* next macroblock: x = 15 becomes x = -1 (luma rows -1..15, chroma x = 7, rows -1..7) */
-            if (lane < 17) s.lt[lane * MVG_LT_STRIDE + MVG_LT_XOFF - 1] = s.lt[lane * MVG_LT_STRIDE + MVG_LT_XOFF + 15];
-            else if (lane < 26) s.ct[0][(lane - 17) * MVG_CT_STRIDE + MVG_CT_XOFF - 1] = s.ct[0][(lane - 17) * MVG_CT_STRIDE + MVG_CT_XOFF + 7];
-            if (lane < 9) s.ct[1][lane * MVG_CT_STRIDE + MVG_CT_XOFF - 1] = s.ct[1][lane * MVG_CT_STRIDE + MVG_CT_XOFF + 7];
+            if (lane < 26) *lc_dst = lc_dst[lc_span];
+            if (lane < 9) *lc_dst2 = lc_dst2[8];
             __syncwarp();
         }
     }

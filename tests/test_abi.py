@@ -66,12 +66,12 @@ def test_pred_tap_tables_reproduce_the_oracle_predictors():
     from oracle import cpu
 
     class Luts(C.Structure):
-        _fields_ = [("lut4", C.c_uint32 * (2 * 9 * 16)), ("lut8", C.c_uint32 * (9 * 64))]
+        _fields_ = [("lut4", C.c_uint32 * (2 * 9 * 16)), ("lut8", C.c_uint16 * (9 * 64))]
     lib = api.load_library()
     luts = Luts()
     lib.mvg_build_luts(C.byref(luts))
     lut4 = np.frombuffer(luts.lut4, np.uint32).reshape(2, 9, 16)
-    lut8 = np.frombuffer(luts.lut8, np.uint32).reshape(9, 64)
+    lut8 = np.frombuffer(luts.lut8, np.uint16).reshape(9, 64)
     rng = np.random.default_rng(1)
 
     # 2x2-MB picture: MBs 0,1,2 are I16x16 with random DC so that MB 3 sees random neighbours;
@@ -100,8 +100,7 @@ def test_pred_tap_tables_reproduce_the_oracle_predictors():
                         w = int(lut4[1, mode, y * 4 + x])
                         s = 0
                         for k in range(4):
-                            off = (w >> (8 * k)) & 255
-                            off = off - 256 if off > 127 else off
+                            off = ((w >> (8 * k)) & 255) - 33     # biased by MVG_LUT4_BIAS = stride + 1
                             dy, dx = divmod(off + 32 + 8, 32)     # stride 32, offsets relative to block origin
                             s += Y[y0 + dy - 1, x0 + dx - 8]
                         pred[y, x] = (s + 2) >> 2
@@ -118,10 +117,12 @@ def test_pred_tap_tables_reproduce_the_oracle_predictors():
                     fl[i] = (left[i - 1] + 2 * left[i] + left[i + 1] + 2) >> 2
                 fl[7] = (left[6] + 3 * left[7] + 2) >> 2
                 ftl = (top[0] + 2 * tl + left[0] + 2) >> 2
-                line = np.concatenate([fl[::-1], [ftl], ft, [0]])
+                line = np.concatenate([fl[::-1], [ftl], ft])
+                nxt = np.concatenate([line[1:], line[-1:]]); prv = np.concatenate([line[:1], line[:-1]])
+                variants = {0: line, 8: (line + nxt + 1) >> 1, 16: (prv + 2 * line + nxt + 2) >> 2}
                 pred = np.zeros((8, 8), np.int32)
                 for y in range(8):
                     for x in range(8):
                         w = int(lut8[mode, y * 8 + x])
-                        pred[y, x] = (sum(line[(w >> (8 * k)) & 255] for k in range(4)) + 2) >> 2
+                        pred[y, x] = variants[w >> 8][(w & 255) // 4]
                 assert np.array_equal(pred, Y[y0:y0 + 8, x0:x0 + 8]), (kind, mode)
