@@ -315,7 +315,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1000, help="pictures per step per GPU (resident in HBM)")
     ap.add_argument("--distinct", type=int, default=32, help="distinct pictures generated on the host per GPU")
     ap.add_argument("--rgb-scale", type=int, default=1, help="RGB thumbnail downscale factor (1 = the reference's mb_to_rgb)")
-    ap.add_argument("--e2e-frames", type=int, default=96, help="pictures per end-to-end step per GPU")
+    ap.add_argument("--e2e-frames", type=int, default=384, help="pictures per end-to-end step per GPU")
     ap.add_argument("--ref-pics", type=int, default=6, help="pictures each host core decodes in the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

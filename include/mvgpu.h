@@ -180,6 +180,11 @@ int mvg_download_residual(mvg_ctx *ctx, int slot, int16_t *residual);
 int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *host_batch,
                     uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale);
 
+/* Pictures per pipeline chunk of mvg_decode_host() (0 = automatic: an eighth of the batch, at
+ * most a third of the context).  Larger chunks fill the GPU better, smaller ones overlap the
+ * PCIe copies of neighbouring chunks better. */
+int mvg_set_pipeline(mvg_ctx *ctx, int chunk_pics);
+
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
 void *mvg_host_alloc(size_t bytes);
 void  mvg_host_free(void *p);

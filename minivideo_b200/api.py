@@ -19,7 +19,7 @@ EXPORTS = (
     "mvg_create", "mvg_destroy", "mvg_last_error", "mvg_set_sps", "mvg_build_level_scale",
     "mvg_upload", "mvg_clone_slot", "mvg_run", "mvg_sync", "mvg_get_timing", "mvg_mark", "mvg_mark_elapsed",
     "mvg_download_yuv420", "mvg_download_rgb", "mvg_download_residual", "mvg_decode_host",
-    "mvg_host_alloc", "mvg_host_free", "mvg_width", "mvg_height", "mvg_max_pics", "mvg_sm_count",
+    "mvg_set_pipeline", "mvg_host_alloc", "mvg_host_free", "mvg_width", "mvg_height", "mvg_max_pics", "mvg_sm_count",
 )
 
 
@@ -68,6 +68,7 @@ def load_library() -> C.CDLL:
     lib.mvg_download_rgb.argtypes = [vp, i32, vp]
     lib.mvg_download_residual.argtypes = [vp, i32, vp]
     lib.mvg_decode_host.argtypes = [vp, C.POINTER(Batch), vp, vp, i32]
+    lib.mvg_set_pipeline.argtypes = [vp, i32]
     lib.mvg_host_alloc.argtypes = [C.c_size_t]
     lib.mvg_host_alloc.restype = vp
     lib.mvg_host_free.argtypes = [vp]
@@ -226,6 +227,9 @@ class Context:
         out = np.empty((self.width_mbs * self.height_mbs, 384), np.int16)
         self._ck(self.lib.mvg_download_residual(self.handle, slot, out.ctypes.data))
         return out
+
+    def set_pipeline(self, chunk_pics: int):
+        self._ck(self.lib.mvg_set_pipeline(self.handle, chunk_pics))
 
     # -- end-to-end path -------------------------------------------------------
     def decode_host(self, soa, yuv_out: np.ndarray | None, rgb_out: np.ndarray | None, rgb_scale=1,

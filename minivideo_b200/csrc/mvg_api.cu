@@ -52,6 +52,7 @@ struct mvg_ctx {
     int *d_work = nullptr;
     int work_next = 0;
     unsigned epoch = 0;              /* bumped per kernel-2 launch; halo words carry it       */
+    int pipe_chunk = 0;              /* pictures per mvg_decode_host() chunk, 0 = automatic    */
     MvgTables *d_tab = nullptr;
     MvgLuts *d_luts = nullptr;
 
@@ -352,6 +353,13 @@ extern "C" int mvg_set_sps(mvg_ctx *ctx, int width_mbs, int height_mbs,
     return MVG_SUCCESS;
 }
 
+extern "C" int mvg_set_pipeline(mvg_ctx *ctx, int chunk_pics)
+{
+    if (!ctx || chunk_pics < 0) return MVG_FAILURE;
+    ctx->pipe_chunk = chunk_pics;
+    return MVG_SUCCESS;
+}
+
 extern "C" int mvg_width(const mvg_ctx *ctx) { return ctx ? 16 * ctx->w_mbs : 0; }
 extern "C" int mvg_height(const mvg_ctx *ctx) { return ctx ? 16 * ctx->h_mbs : 0; }
 extern "C" int mvg_max_pics(const mvg_ctx *ctx) { return ctx ? ctx->max_pics : 0; }
@@ -622,6 +630,7 @@ extern "C" int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *b, uint8_t *yuv_ou
     int chunk = std::max(1, ctx->max_pics / depth);
     if (ctx->max_pics < depth) { depth = 1; chunk = ctx->max_pics; }
     chunk = std::min(chunk, std::max(1, (b->n_pics + 7) / 8));
+    if (ctx->pipe_chunk > 0) chunk = std::min(ctx->pipe_chunk, std::max(1, ctx->max_pics / depth));
     int idx = 0;
     for (int done = 0; done < b->n_pics; done += chunk, idx++) {
         const int cnt = std::min(chunk, b->n_pics - done);

@@ -801,10 +801,12 @@ k2_wavefront(K2Params p)
 
             if (availB) {
                 if (availC) {       /* the up-right macroblock must have been published */
-                    unsigned ns = 64;
+                    /* rarely entered; when it is, this row has caught up with the row above, so sleep
+                     * for about a macroblock time instead of polling at full rate */
+                    unsigned ns = 400;
                     while (!__all_sync(MVG_FULL, lane >= 8 || nxt.y == epoch)) {
                         __nanosleep(ns);
-                        if (ns < 2048) ns *= 2;
+                        if (ns < 3200) ns *= 2;
                         if (lane < 8) nxt = mvg_ld_relaxed_u64(habove + (size_t)(mx + 1) * 8);
                     }
                 }
