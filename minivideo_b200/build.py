@@ -78,6 +78,16 @@ def build_gpu(force: bool = False) -> Path:
     return out
 
 
+def build_thumbnailer(force: bool = False) -> Path:
+    """mv_thumbnailer: the CLI over libmvfront.so + libmvgpu.so (mini_thumbnailer-compatible arguments)."""
+    out = PKG / "mv_thumbnailer"
+    src = [CSRC / "mv_thumbnailer.c", INC / "mvfront.h", INC / "mvgpu.h", PKG / "libmvfront.so", PKG / "libmvgpu.so"]
+    if force or _stale(out, src):
+        _run(["gcc", "-O2", "-Wall", "-Wextra", f"-I{INC}", "-o", str(out), str(src[0]), f"-L{PKG}",
+              "-Wl,-rpath,$ORIGIN", "-lmvfront", "-lmvgpu", "-lstdc++", "-lm", "-lpthread", "-ldl", "-lrt"])
+    return out
+
+
 def build_oracle(force: bool = False) -> Path:
     out = ROOT / "oracle" / "librecon_oracle.so"
     src = [ROOT / "oracle" / "recon_oracle.c", ROOT / "oracle" / "recon_oracle.h"]
@@ -103,6 +113,7 @@ def build_all(force: bool = False) -> dict:
         "oracle": build_oracle(force),
         "reference": build_reference(force),
         "gpu": build_gpu(force),
+        "thumbnailer": build_thumbnailer(force),
     }
 
 

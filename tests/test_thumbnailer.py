@@ -1,0 +1,88 @@
+"""mv_thumbnailer (bitstream -> front end -> C ABI -> picture files) against the files the unmodified
+reference CLI (oracle/_ref/mini_thumbnailer) writes for the same stream and arguments: byte for byte."""
+import os
+import subprocess
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import ref
+
+ROOT = Path(__file__).resolve().parent.parent
+MV = ROOT / "minivideo_b200" / "mv_thumbnailer"
+
+
+@pytest.fixture(scope="module")
+def cli():
+    from minivideo_b200 import build
+    return build.build_thumbnailer()
+
+
+def test_cli_builds_and_rejects_bad_arguments(cli):
+    assert os.access(cli, os.X_OK)
+    assert subprocess.run([str(cli)], capture_output=True).returncode == 2
+    assert subprocess.run([str(cli), "-i", "x.264", "-f", "webp"], capture_output=True).returncode == 2
+    r = subprocess.run([str(cli), "-i", "/nonexistent.264"], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr
+
+
+def _run_both(stream: bytes, args: list[str]):
+    """Run both CLIs in separate scratch directories on the same stream; return {file name: bytes} each."""
+    out = []
+    for exe, extra in ((ref.MINI_THUMBNAILER, []), (MV, ["-o", "."])):
+        with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+            (Path(d) / "in.264").write_bytes(stream)
+            r = subprocess.run([str(exe), "-i", str(Path(d) / "in.264")] + args + extra, capture_output=True, text=True, cwd=d)
+            assert r.returncode == 0, (exe, r.stdout[-1500:], r.stderr[-1500:])
+            out.append({p.name: p.read_bytes() for p in Path(d).iterdir() if p.name != "in.264"})
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["yuv420", "bmp", "tga"])
+@pytest.mark.parametrize("mode,n", [("unfiltered", 1), ("unfiltered", 5), ("ordered", 4), ("distributed", 4)])
+def test_cli_files_equal_the_reference_cli(cli, fmt, mode, n):
+    from minivideo_b200 import synth
+    if not ref.MINI_THUMBNAILER.exists():
+        pytest.skip("reference CLI not built")
+    stream, _ = synth.generate(12, "cif", seed=901)
+    want, got = _run_both(stream, ["-f", fmt, "-n", str(n), "-e", mode])
+    assert sorted(want) == sorted(got)
+    for name in want:
+        assert want[name] == got[name], name
+
+
+@pytest.mark.gpu
+def test_cli_high_profile_stream_and_small_batches(cli):
+    from minivideo_b200 import synth
+    if not ref.MINI_THUMBNAILER.exists():
+        pytest.skip("reference CLI not built")
+    stream, _ = synth.generate(7, width_mbs=20, height_mbs=12, profile_idc=100, transform8x8=1, scaling_lists=1,
+                               cb_qp_offset=3, cr_qp_offset=-1, seed=902)
+    want, _ = _run_both(stream, ["-f", "bmp", "-n", "7"])
+    for batch in ("1", "3", "64"):
+        _, got = _run_both(stream, ["-f", "bmp", "-n", "7", "-b", batch])
+        assert want == got, batch
+
+
+@pytest.mark.gpu
+def test_cli_scaled_thumbnail_is_the_box_average(cli):
+    """-s has no reference counterpart: defined as the rounded box average of the scale-1 RGB picture."""
+    from minivideo_b200 import synth
+    stream, _ = synth.generate(1, "cif", seed=903)
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "in.264").write_bytes(stream)
+        for s in (1, 4):
+            r = subprocess.run([str(MV), "-i", str(Path(d) / "in.264"), "-f", "bmp", "-s", str(s), "-o", d], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            os.rename(Path(d) / "in.bmp", Path(d) / f"s{s}.bmp")
+
+        def bmp(p):
+            raw = np.fromfile(p, np.uint8)
+            w, h = int(raw[18:22].view("<u4")[0]), int(raw[22:26].view("<u4")[0])
+            return raw[54:].reshape(h, w * 3)[::-1].reshape(h, w, 3).astype(np.uint32)
+        full, small = bmp(Path(d) / "s1.bmp"), bmp(Path(d) / "s4.bmp")
+        h, w = full.shape[:2]
+        assert np.array_equal(small, (full.reshape(h // 4, 4, w // 4, 4, 3).sum(axis=(1, 3)) + 8) // 16)
