@@ -191,40 +191,43 @@ static Taps nxn_taps(int n, int mode, int x, int y)
 extern "C" void mvg_build_luts(MvgLuts *out)
 {
     memset(out, 0, sizeof *out);
-    for (int tr = 0; tr < 2; tr++)
-        for (int mode = 0; mode < 9; mode++)
+    for (int half = 0; half < 2; half++)
+        for (int row = 0; row < 16; row++) {
+            const int mode = row == 11 ? 3 : row == 15 ? 7 : row;
+            if (mode > 8 || mode == 2) continue;
+            const bool tr = row < 9;
             for (int y = 0; y < 4; y++)
                 for (int x = 0; x < 4; x++) {
-                    uint32_t word = 0;
-                    if (mode != 2) {
-                        Taps t = nxn_taps(4, mode, x, y);
-                        for (int k = 0; k < 4; k++) {
-                            int off;
-                            if (t.r[k].left) off = t.r[k].i * MVG_LT_STRIDE - 1;
-                            else {
-                                int i = t.r[k].i;
-                                if (!tr && i > 3) i = 3;     /* h264_intra_prediction.c:431-439 */
-                                off = -MVG_LT_STRIDE + i;
-                            }
-                            word |= (uint32_t)(off + MVG_LUT4_BIAS) << (8 * k);
+                    const Taps t = nxn_taps(4, mode, x, y);
+                    for (int k = 0; k < 4; k++) {
+                        int off;
+                        if (t.r[k].left) off = t.r[k].i * MVG_LT_STRIDE - 1;
+                        else {
+                            int i = t.r[k].i;
+                            if (!tr && i > 3) i = 3;         /* h264_intra_prediction.c:431-439 */
+                            off = -MVG_LT_STRIDE + i;
                         }
+                        out->lut4[half][row][y * 4 + x][k] = off + (half ? 8 - 4 * MVG_LT_STRIDE : 0) + MVG_LUT4_BIAS;
                     }
-                    out->lut4[tr][mode][y * 4 + x] = word;
                 }
+        }
     auto line8 = [](Ref r) { return r.left ? MVG_N8_LEFT(r.i) : MVG_N8_TOP(r.i); };
     for (int mode = 0; mode < 9; mode++)
-        for (int y = 0; y < 8; y++)
-            for (int x = 0; x < 8; x++) {
-                int idx = MVG_N8_DC, shift = 0;
+        for (int lane = 0; lane < 32; lane++)
+            for (int s = 0; s < 2; s++) {
+                const int x = 2 * (lane & 3) + s, y = lane >> 2;
+                int idx = MVG_N8_DC, variant = 0;
                 if (mode != 2) {
                     const Taps t = nxn_taps(8, mode, x, y);
-                    if (t.form == 1) { idx = line8(t.r[0]); shift = 0; }
+                    if (t.form == 1) { idx = line8(t.r[0]); variant = 0; }
                     else if (t.form == 2) {                       /* adjacent pair -> f2 of the lower index */
                         const int a = line8(t.r[0]), b = line8(t.r[3]);
-                        idx = a < b ? a : b; shift = 8;
-                    } else { idx = line8(t.r[1]); shift = 16; }   /* centre (or the line end of an end tap) */
+                        idx = a < b ? a : b; variant = 1;
+                    } else { idx = line8(t.r[1]); variant = 2; }  /* centre (or the line end of an end tap) */
                 }
-                out->lut8[mode][y * 8 + x] = (uint16_t)(idx * 4 | shift << 8);
+                out->lut8[mode][lane][2 * s] = (uint32_t)idx * 4;
+                out->lut8[mode][lane][2 * s + 1] = s == 0 ? 0x4440u | (uint32_t)variant
+                                                          : 0x5054u | ((uint32_t)variant << 8);
             }
 }
 
@@ -263,7 +266,8 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     TRY("cudaGetDeviceProperties", cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     TRY("occupancy k1", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_ctas_per_sm, k1_dequant_idct, K1_WARPS * 32, 0));
-    TRY("occupancy k2", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2_ctas_per_sm, k2_wavefront, K2_WARPS * 32, 0));
+    TRY("k2 shared memory", cudaFuncSetAttribute(k2_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM_BYTES));
+    TRY("occupancy k2", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2_ctas_per_sm, k2_wavefront, K2_WARPS * 32, K2_SMEM_BYTES));
     if (ctx->k1_ctas_per_sm < 1 || ctx->k2_ctas_per_sm < 1) return bail("kernel does not fit on an SM", cudaErrorLaunchOutOfResources);
     TRY("stream", cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     TRY("stream", cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
@@ -473,7 +477,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         p.work = work; p.luts = ctx->d_luts; p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics;
         const long long items = (long long)n_pics * H;
         const int grid = (int)std::min<long long>((items + K2_WARPS - 1) / K2_WARPS, (long long)ctx->sm_count * ctx->k2_ctas_per_sm);
-        k2_wavefront<<<grid, K2_WARPS * 32, 0, st>>>(p);
+        k2_wavefront<<<grid, K2_WARPS * 32, K2_SMEM_BYTES, st>>>(p);
         launches++;
     }
     if (timed) CK(ctx, cudaEventRecord(ctx->ev[2], st));

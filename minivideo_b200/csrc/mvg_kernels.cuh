@@ -92,6 +92,16 @@ __device__ __forceinline__ unsigned mvg_pack_sat16(int hi, int lo)
     asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
     return d;
 }
+/* {clamp(hi >> 6, -512, 511), clamp(lo >> 6, -512, 511)} as an int16 pair: saturate to int16 first
+ * (>> is monotonic, so clamp and shift commute), then shift both halves at once and sign-extend the two
+ * 10-bit fields with a packed subtract.  The residual is clamped because kernel 2 adds it to the
+ * prediction with packed 16-bit arithmetic: Clip1(pred + r) does not change for any clamp range that
+ * contains [-255, 255], and 255 + 511 cannot wrap. */
+__device__ __forceinline__ unsigned mvg_pack_shr6(int hi, int lo)
+{
+    const unsigned t = ((mvg_pack_sat16(hi, lo) >> 6) & 0x03ff03ffu) ^ 0x02000200u;
+    return __vsub2(t, 0x02000200u);
+}
 
 #define K1_WARPS 4          /* warps per CTA                      */
 #define K1_GROUP 4          /* macroblocks per warp iteration     */
@@ -288,7 +298,7 @@ k1_dequant_idct(K1Params p)
                         const int d = qp > 23 ? dcraw * lq : (dcraw * lq + (1 << (3 - qd))) >> (4 - qd);
                         rv = (d + 32) >> 6;
                     }
-                    rv = min(max(rv, -32768), 32767);
+                    rv = min(max(rv, -512), 511);
                     nonzero = rv != 0;
                     if (nonzero || dcraw) {
                         const unsigned pk = (unsigned)(rv & 0xffff) * 0x10001u;
@@ -348,10 +358,10 @@ k1_dequant_idct(K1Params p)
                 for (int q = 0; q < 4; q++)
                     mvg_bfly4(c[q], c[4 + q], c[8 + q], c[12 + q], c[q], c[4 + q], c[8 + q], c[12 + q]);
                 uint4 o0, o1;
-                o0.x = mvg_pack_sat16(c[1] >> 6, c[0] >> 6);   o0.y = mvg_pack_sat16(c[3] >> 6, c[2] >> 6);
-                o0.z = mvg_pack_sat16(c[5] >> 6, c[4] >> 6);   o0.w = mvg_pack_sat16(c[7] >> 6, c[6] >> 6);
-                o1.x = mvg_pack_sat16(c[9] >> 6, c[8] >> 6);   o1.y = mvg_pack_sat16(c[11] >> 6, c[10] >> 6);
-                o1.z = mvg_pack_sat16(c[13] >> 6, c[12] >> 6); o1.w = mvg_pack_sat16(c[15] >> 6, c[14] >> 6);
+                o0.x = mvg_pack_shr6(c[1], c[0]);   o0.y = mvg_pack_shr6(c[3], c[2]);
+                o0.z = mvg_pack_shr6(c[5], c[4]);   o0.w = mvg_pack_shr6(c[7], c[6]);
+                o1.x = mvg_pack_shr6(c[9], c[8]);   o1.y = mvg_pack_shr6(c[11], c[10]);
+                o1.z = mvg_pack_shr6(c[13], c[12]); o1.w = mvg_pack_shr6(c[15], c[14]);
                 blk[0] = o0; blk[1] = o1;
             }
         }
@@ -385,7 +395,7 @@ k1_dequant_idct(K1Params p)
                 for (int i = 0; i < 8; i++) v[i] = s.tr[lane >> 3][i][row];     /* this lane now owns column `row` */
                 mvg_idct8_1d(v);                                                /* column pass */
 #pragma unroll
-                for (int i = 0; i < 8; i++) o8[(i >> 2) * 32 + (i & 3) * 4] = (int16_t)min(max(v[i] >> 6, -32768), 32767);
+                for (int i = 0; i < 8; i++) o8[(i >> 2) * 32 + (i & 3) * 4] = (int16_t)min(max(v[i] >> 6, -512), 511);
             }
             __syncwarp();
         }
@@ -407,7 +417,8 @@ k1_dequant_idct(K1Params p)
             const unsigned k7 = __shfl_down_sync(MVG_FULL, meta, 7);
             if (mt == 0 && mj < nmb)
                 *reinterpret_cast<uint4 *>(p.ctl + mb0 + mj) =
-                    make_uint4((k4 & 255) | ((k6 & 255) << 8) | ((k7 & 255) << 16), nib | (n1 << 16), n2 | (n3 << 16), nz & 0x00FFFFFFu);
+                    make_uint4((k4 & 255) | ((k6 & 255) << 8) | ((k7 & 255) << 16), nib | (n2 << 16),
+                               __funnelshift_l(n1 | (n3 << 16), n1 | (n3 << 16), 8), nz & 0x00FFFFFFu);
         }
         __syncwarp();
     }
@@ -429,14 +440,23 @@ struct K2Params {
     int w_mbs, h_mbs, first_slot, n_pics, group;
 };
 
-#define K2_WARPS 4
+#define K2_WARPS     16         /* warps per CTA; two CTAs per SM                              */
+#define K2_CTL_CHUNK 128        /* control records staged in shared memory per bulk copy       */
+#define K2_TO(x, y)  (((y) + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + (x))    /* luma tile offset of sample (x, y)   */
+#define K2_CO(x, y)  (((y) + 1) * MVG_CT_STRIDE + MVG_CT_XOFF + (x))    /* chroma tile offset of sample (x, y) */
 
 struct K2WarpSmem {
-    __align__(16) int16_t  resid[384];
-    __align__(16) uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
-    __align__(16) uint8_t  ct[2][MVG_CT_ROWS * MVG_CT_STRIDE];
-    __align__(16) uint32_t n8[32];      /* Intra8x8 neighbour line: p' | f2 << 8 | f3 << 16 per entry */
+    __align__(128) int16_t  resid[2][384];      /* residual of this and of the next macroblock (bulk async copies) */
+    __align__(16)  MvgMbCtl ctl[K2_CTL_CHUNK];  /* control records of the macroblock row                          */
+    __align__(16)  uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
+    __align__(16)  uint8_t  ct[2][MVG_CT_ROWS * MVG_CT_STRIDE];
+    __align__(16)  uint32_t n8[36];             /* Intra8x8 neighbour line: p' | f2 << 8 | f3 << 16; [32] = DC     */
+    __align__(8)   uint64_t mbar[3];            /* resid[0], resid[1], ctl                                         */
 };
+
+/* dynamic shared memory: [K2WarpSmem x K2_WARPS][pad to 8 KB][MvgLuts]; the Intra4x4 tap table must sit on
+ * an 8 KB boundary so that (mode << 8) can be OR-ed into a lane's table address */
+#define K2_SMEM_BYTES (sizeof(K2WarpSmem) * K2_WARPS + 8192 + sizeof(MvgLuts))
 
 __device__ __forceinline__ uint2 mvg_ld_relaxed_u64(const uint2 *p)
 {
@@ -454,123 +474,141 @@ __device__ __forceinline__ void mvg_st_relaxed_u64(uint2 *p, unsigned lo, unsign
 __device__ __forceinline__ int mvg_sum4(unsigned w) { return (int)__dp4a(w, 0x01010101u, 0u); }
 /* Clip1(pred + r): one VIADDMNMX */
 __device__ __forceinline__ int mvg_add_clip8(int pred, int r) { return __viaddmin_s32_relu(pred, r, 255); }
+/* Clip1(pred + r) on two samples held as int16 pairs: one VIADDMNMX.S16x2.RELU.  The 16-bit add wraps,
+ * which is why kernel 1 clamps the residual to [-512, 511]. */
+__device__ __forceinline__ unsigned mvg_add_clip8x2(unsigned pred2, unsigned r2) { return __viaddmin_s16x2_relu(pred2, r2, 0x00ff00ffu); }
+/* bytes 0,1 / 2,3 of a word as int16 pairs */
+__device__ __forceinline__ unsigned mvg_pair_lo(unsigned w) { return __byte_perm(w, 0, 0x4140); }
+__device__ __forceinline__ unsigned mvg_pair_hi(unsigned w) { return __byte_perm(w, 0, 0x4342); }
+/* low bytes of two int16 pairs -> 4 bytes */
+__device__ __forceinline__ unsigned mvg_pairs_to_bytes(unsigned a, unsigned b) { return __byte_perm(a, b, 0x6420); }
+
+/* everything a lane needs to know about its warp's shared memory and its own role; the pointers are
+ * warp-uniform (they come from a lane-0 broadcast, so they live in uniform registers and shared-memory
+ * accesses take the form [lane register + uniform base + immediate]) */
+struct K2Ctx {
+    uint8_t *lt, *ct;           /* luma tile, chroma tiles (plane stride MVG_CT_ROWS * MVG_CT_STRIDE) */
+    uint32_t *n8;
+    const uint8_t *resid;       /* residual buffer of the current macroblock */
+    const uint8_t *lut8;        /* MvgLuts::lut8 in shared memory */
+    int lane;
+    /* Intra4x4: lane = 16 * half + 4 * py + px */
+    unsigned lut4;              /* shared-memory address of lut4[half][0][pix] */
+    int s4;                     /* tile offset of my sample relative to the origin of the half-0 block */
+    int r4odd, r4even;          /* residual byte offset relative to the half-0 block, by0 odd / even */
+    int h4;                     /* tile offset of my block relative to the half-0 block */
+    unsigned m4c, m4b, m4cc;    /* nibbles (bit 0) whose block has no up-right neighbour: always / if !availB / if !availC */
+    /* Intra8x8: lane n = entry n of the neighbour line; samples (2*(lane&3) + {0,1}, lane>>2) */
+    int n8tr, n8notr;           /* tile offset of my neighbour sample relative to the block origin */
+    int s8, r8;
+    unsigned fixA, fixB, fixD;  /* bit 2b: next := raw, bit 2b+1: prev := raw in block b when A / B / D is unavailable */
+};
 
 /* ---- Intra16x16 luma (h264_intra_prediction.c:1945-2141) ------------------- */
-__device__ __forceinline__ void k2_luma16(K2WarpSmem &s, int lane, int mode, bool left, bool up)
+/* lane = 2 * y + (x0 / 8): eight samples of one row, handled as four int16 pairs */
+__device__ __forceinline__ void k2_luma16(const K2Ctx &c, int mode, bool left, bool up)
 {
-    uint8_t *lt = s.lt;
-    const int y = lane >> 1, x0 = (lane & 1) * 8;
-    int pred[8];
+    uint8_t *lt = c.lt;
+    const int lane = c.lane, y = lane >> 1, x0 = (lane & 1) * 8;
+    unsigned pp[4];
     if (mode == 0) {            /* Vertical */
-        const uint2 t = *reinterpret_cast<const uint2 *>(lt + MVG_LT_XOFF + x0);
-#pragma unroll
-        for (int i = 0; i < 4; i++) { pred[i] = (t.x >> (8 * i)) & 255; pred[4 + i] = (t.y >> (8 * i)) & 255; }
+        const uint2 t = *reinterpret_cast<const uint2 *>(lt + K2_TO(0, -1) + x0);
+        pp[0] = mvg_pair_lo(t.x); pp[1] = mvg_pair_hi(t.x); pp[2] = mvg_pair_lo(t.y); pp[3] = mvg_pair_hi(t.y);
     } else if (mode == 1) {     /* Horizontal */
-        const int v = lt[(y + 1) * MVG_LT_STRIDE + MVG_LT_XOFF - 1];
-#pragma unroll
-        for (int i = 0; i < 8; i++) pred[i] = v;
+        pp[0] = pp[1] = pp[2] = pp[3] = (unsigned)lt[K2_TO(-1, 0) + y * MVG_LT_STRIDE] * 0x10001u;
     } else if (mode == 2) {     /* DC */
         int v = 0;
-        if (lane < 16) {
-            if (up) v += lt[MVG_LT_XOFF + lane];
-            if (left) v += lt[(lane + 1) * MVG_LT_STRIDE + MVG_LT_XOFF - 1];
-        }
+        if (lane < 16) { if (left) v = lt[K2_TO(-1, 0) + lane * MVG_LT_STRIDE]; }
+        else if (lane < 20) { if (up) v = mvg_sum4(*reinterpret_cast<const unsigned *>(lt + K2_TO(0, -1) + (lane - 16) * 4)); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MVG_FULL, v, o);
         v = (left && up) ? (v + 16) >> 5 : (left || up) ? (v + 8) >> 4 : 128;
-#pragma unroll
-        for (int i = 0; i < 8; i++) pred[i] = v;
+        pp[0] = pp[1] = pp[2] = pp[3] = (unsigned)v * 0x10001u;
     } else {                    /* Plane */
         int term = 0;
         const int i = lane & 7;
-        if (lane < 8)       term = (i + 1) * ((int)lt[MVG_LT_XOFF + 8 + i] - (int)lt[MVG_LT_XOFF + 6 - i]);
-        else if (lane < 16) term = (i + 1) * ((int)lt[(9 + i) * MVG_LT_STRIDE + MVG_LT_XOFF - 1] -
-                                              (int)lt[(7 - i) * MVG_LT_STRIDE + MVG_LT_XOFF - 1]);
+        if (lane < 8)       term = (i + 1) * ((int)lt[K2_TO(8 + i, -1)] - (int)lt[K2_TO(6 - i, -1)]);
+        else if (lane < 16) term = (i + 1) * ((int)lt[K2_TO(-1, 8 + i)] - (int)lt[K2_TO(-1, 6 - i)]);
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) term += __shfl_xor_sync(MVG_FULL, term, o);
         const int H = __shfl_sync(MVG_FULL, term, 0), V = __shfl_sync(MVG_FULL, term, 8);
-        const int a = 16 * ((int)lt[16 * MVG_LT_STRIDE + MVG_LT_XOFF - 1] + (int)lt[MVG_LT_XOFF + 15]);
-        const int b = (5 * H + 32) >> 6, c = (5 * V + 32) >> 6;
-        const int base = a + c * (y - 7) + 16;
+        const int a = 16 * ((int)lt[K2_TO(-1, 15)] + (int)lt[K2_TO(15, -1)]);
+        const int b = (5 * H + 32) >> 6, cc = (5 * V + 32) >> 6;
+        /* v(x) = a + b (x - 7) + c (y - 7) + 16 fits int16 (|v| < 20000); Clip1(v >> 5) = clamp(v, 0, 8191) >> 5 */
+        const int v0 = a + cc * (y - 7) + 16 + b * (x0 - 7);
+        unsigned pair = __vadd2((unsigned)(v0 & 0xffff) * 0x10001u, (unsigned)b << 16);
+        const unsigned step = (unsigned)((2 * b) & 0xffff) * 0x10001u;
 #pragma unroll
-        for (int k = 0; k < 8; k++) pred[k] = mvg_clip8((base + b * (x0 + k - 7)) >> 5);
+        for (int k = 0; k < 4; k++) {
+            pp[k] = (__vimin_s16x2_relu(pair, 0x1fff1fffu) >> 5) & 0x00ff00ffu;
+            pair = __vadd2(pair, step);
+        }
     }
     /* row y, samples x0..x0+7: 4x4 blocks (x0/4, y/4) and (x0/4+1, y/4), row y&3 of each */
     const int bcol = x0 >> 2, brow = y >> 2;
     const int blkA = (bcol & 1) | ((brow & 1) << 1) | ((bcol >> 1) << 2) | ((brow >> 1) << 3);
-    const uint2 ra = *reinterpret_cast<const uint2 *>(s.resid + blkA * 16 + (y & 3) * 4);
-    const uint2 rb = *reinterpret_cast<const uint2 *>(s.resid + (blkA + 1) * 16 + (y & 3) * 4);
-    const unsigned rr[4] = {ra.x, ra.y, rb.x, rb.y};
-    unsigned lo = 0, hi = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int r0 = (short)(rr[k] & 0xffff), r1 = (int)rr[k] >> 16;
-        const unsigned p0 = (unsigned)mvg_add_clip8(pred[2 * k], r0), p1 = (unsigned)mvg_add_clip8(pred[2 * k + 1], r1);
-        const unsigned pk = p0 | (p1 << 8);
-        if (k < 2) lo |= pk << (16 * k); else hi |= pk << (16 * (k - 2));
-    }
-    *reinterpret_cast<uint2 *>(lt + (y + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + x0) = make_uint2(lo, hi);
+    const uint2 ra = *reinterpret_cast<const uint2 *>(c.resid + blkA * 32 + (y & 3) * 8);
+    const uint2 rb = *reinterpret_cast<const uint2 *>(c.resid + (blkA + 1) * 32 + (y & 3) * 8);
+    const unsigned lo = mvg_pairs_to_bytes(mvg_add_clip8x2(pp[0], ra.x), mvg_add_clip8x2(pp[1], ra.y));
+    const unsigned hi = mvg_pairs_to_bytes(mvg_add_clip8x2(pp[2], rb.x), mvg_add_clip8x2(pp[3], rb.y));
+    *reinterpret_cast<uint2 *>(lt + K2_TO(0, 0) + y * MVG_LT_STRIDE + x0) = make_uint2(lo, hi);
 }
 
 /* ---- Intra4x4 luma: anti-diagonal schedule, two blocks per step ------------- */
-/* Blocks with bx + 2*by == t can be predicted together: their left, up, up-left and
- * up-right neighbours all belong to earlier steps.  Lanes 0..15 take block
- * (t&1, t>>1), lanes 16..31 block ((t&1)+2, (t>>1)-1), one sample per lane. */
+/* Blocks with bx + 2*by == t can be predicted together: their left, up, up-left and up-right neighbours
+ * all belong to earlier steps.  Lanes 0..15 take block (t&1, t>>1), lanes 16..31 block ((t&1)+2, (t>>1)-1),
+ * one sample per lane.  Every directional predictor is (n[a]+n[b]+n[c]+n[d]+2)>>2 over four (repeated)
+ * neighbour samples; the table row of (half, mode, sample) holds the four tile offsets as ready 32-bit
+ * values, so a sample costs one 128-bit table load, four byte loads at [offset + uniform tile base +
+ * immediate] and three adds.  Modes 3 and 7 without an up-right neighbour use rows 11 and 15, whose
+ * taps stop at p[3,-1] (h264_intra_prediction.c:431-439). */
 template <int T>
-__device__ __forceinline__ void k2_luma4_step(K2WarpSmem &s, const uint32_t *lut4, int half, int pix, int pxy,
-                                              unsigned mlo, unsigned mhi, bool availA, bool availB, bool availC)
+__device__ __forceinline__ void k2_luma4_step(const K2Ctx &c, unsigned seq, bool availA, bool availB)
 {
-    constexpr int bx0 = (T & 1), by0 = (T >> 1), bx1 = (T & 1) + 2, by1 = (T >> 1) - 1;
-    constexpr bool v0 = by0 <= 3, v1 = by1 >= 0 && by1 <= 3;
+    constexpr int bx0 = T & 1, by0 = T >> 1;
+    constexpr bool v0 = T <= 7, v1 = T >= 2;
+    constexpr int org0 = K2_TO(bx0 * 4, by0 * 4);
     constexpr int blk0 = (bx0 & 1) | ((by0 & 1) << 1) | ((bx0 >> 1) << 2) | ((by0 >> 1) << 3);
-    constexpr int blk1 = (bx1 & 1) | ((by1 & 1) << 1) | ((bx1 >> 1) << 2) | (((by1 >> 1) & 1) << 3);
-    uint8_t *lt = s.lt;
-    const bool valid = half ? v1 : v0;
-    if (valid) {
-        const int bx = half ? bx1 : bx0, by = half ? by1 : by0, blk = half ? blk1 : blk0;
-        const unsigned mw = blk < 8 ? mlo : mhi;
-        const int mode = (mw >> (4 * (blk & 7))) & 15;
-        const bool left = bx > 0 || availA, up = by > 0 || availB;
-        /* p[4..7,-1]: h264_intra_prediction.c:398-429 + h264_spatial.c:757-774 */
-        bool tr;
-        if (blk == 3 || blk == 11) tr = false;
-        else if (by > 0) tr = bx < 3;
-        else tr = bx < 3 ? availB : availC;
-        const int org = (by * 4 + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + bx * 4;
+    constexpr int sh = 4 * (T & 7);
+    const bool half = c.lane >= 16;
+    if ((v0 && v1) || (half ? v1 : v0)) {
+        const unsigned m = (sh >= 8 ? (seq >> (sh >= 8 ? sh - 8 : 0)) : (seq << (sh >= 8 ? 0 : 8 - sh))) & 0xF00u;
         int pred;
-        if (mode == 2) {
+        if (m == 0x200u) {          /* DC (h264_intra_prediction.c:554-600) */
+            const bool left = half ? true : (bx0 > 0 || availA);
+            const bool up = (half ? by0 - 1 > 0 : by0 > 0) || availB;
+            const uint8_t *o = c.lt + org0 + c.h4;
             int sum = 0;
-            if (up) sum += mvg_sum4(*reinterpret_cast<const unsigned *>(lt + org - MVG_LT_STRIDE));
-            if (left) sum += (int)lt[org - 1] + (int)lt[org + MVG_LT_STRIDE - 1] +
-                             (int)lt[org + 2 * MVG_LT_STRIDE - 1] + (int)lt[org + 3 * MVG_LT_STRIDE - 1];
+            if (up) sum = mvg_sum4(*reinterpret_cast<const unsigned *>(o - MVG_LT_STRIDE));
+            if (left) sum += (int)o[-1] + (int)o[MVG_LT_STRIDE - 1] + (int)o[2 * MVG_LT_STRIDE - 1] + (int)o[3 * MVG_LT_STRIDE - 1];
             pred = (left && up) ? (sum + 4) >> 3 : (left || up) ? (sum + 2) >> 2 : 128;
         } else {
-            const uint32_t taps = lut4[((tr ? 9 : 0) + mode) * 16 + pix];
-            const uint8_t *nb = lt + org - MVG_LUT4_BIAS;
-            pred = ((int)nb[taps & 255] + (int)nb[(taps >> 8) & 255] + (int)nb[(taps >> 16) & 255] +
-                    (int)nb[taps >> 24] + 2) >> 2;
+            uint4 tp;
+            asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(tp.x), "=r"(tp.y), "=r"(tp.z), "=r"(tp.w) : "r"(m | c.lut4));
+            const uint8_t *nb = c.lt + (org0 - MVG_LUT4_BIAS);
+            pred = ((int)nb[tp.x] + (int)nb[tp.y] + (int)nb[tp.z] + (int)nb[tp.w] + 2) >> 2;
         }
-        const int r = s.resid[blk * 16 + pix];
-        lt[org + (pxy >> 4) * MVG_LT_STRIDE + (pxy & 3)] = (uint8_t)mvg_add_clip8(pred, r);
+        const int r = *reinterpret_cast<const int16_t *>(c.resid + blk0 * 32 + ((by0 & 1) ? c.r4odd : c.r4even));
+        c.lt[org0 + c.s4] = (uint8_t)mvg_add_clip8(pred, r);
     }
     __syncwarp();
 }
 
-__device__ __forceinline__ void k2_luma4(K2WarpSmem &s, const uint32_t *lut4, int lane,
-                                         unsigned mlo, unsigned mhi, bool availA, bool availB, bool availC)
+__device__ __forceinline__ void k2_luma4(const K2Ctx &c, unsigned w1, unsigned w2, bool availA, bool availB, bool availC)
 {
-    const int half = lane >> 4, pix = lane & 15;
-    const int pxy = ((lane >> 2) & 3) * 16 + (lane & 3);      /* py*16 + px */
-    k2_luma4_step<0>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
-    k2_luma4_step<1>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
-    k2_luma4_step<2>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
-    k2_luma4_step<3>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
-    k2_luma4_step<4>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
-    k2_luma4_step<5>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
-    k2_luma4_step<6>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
-    k2_luma4_step<7>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
-    k2_luma4_step<8>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
-    k2_luma4_step<9>(s, lut4, half, pix, pxy, mlo, mhi, availA, availB, availC);
+    unsigned seq = c.lane >= 16 ? w2 : w1;
+    const unsigned notr = c.m4c | (availB ? 0u : c.m4b) | (availC ? 0u : c.m4cc);
+    seq |= (seq & (seq >> 1) & notr) << 3;          /* modes 3, 7 -> 11, 15 where p[4..7,-1] are not available */
+    k2_luma4_step<0>(c, seq, availA, availB);
+    k2_luma4_step<1>(c, seq, availA, availB);
+    k2_luma4_step<2>(c, seq, availA, availB);
+    k2_luma4_step<3>(c, seq, availA, availB);
+    k2_luma4_step<4>(c, seq, availA, availB);
+    k2_luma4_step<5>(c, seq, availA, availB);
+    k2_luma4_step<6>(c, seq, availA, availB);
+    k2_luma4_step<7>(c, seq, availA, availB);
+    k2_luma4_step<8>(c, seq, availA, availB);
+    k2_luma4_step<9>(c, seq, availA, availB);
 }
 
 /* ---- Intra8x8 luma: 4 blocks in order ------------------------------------------ */
@@ -578,36 +616,34 @@ __device__ __forceinline__ void k2_luma4(K2WarpSmem &s, const uint32_t *lut4, in
  * Lane n filters its entry (reference sample filter, h264_intra_prediction.c:1295-1353) and then
  * derives, again with shuffles, the two smoothings every directional mode is built from:
  *   f2[n] = (p'[n] + p'[n+1] + 1) >> 1,  f3[n] = (p'[n-1] + 2 p'[n] + p'[n+1] + 2) >> 2
- * (line ends replicate).  Each predicted sample is then ONE of p'[i], f2[i], f3[i] -- the
- * table lut8 says which (byte offset of entry i, bit shift of the variant). */
-struct K2Lane8 {            /* per-lane constants of the neighbour gather */
-    int off_tr, off_notr;   /* tile offset of this lane's neighbour relative to the block origin */
-};
-
+ * (line ends replicate).  Each predicted sample is then ONE of p'[i], f2[i], f3[i]; the table gives,
+ * for the two horizontally adjacent samples of a lane, the word to load and the byte-permute selector
+ * that drops the right byte into an int16 pair. */
 template <int B8>
-__device__ __forceinline__ void k2_luma8_block(K2WarpSmem &s, const uint16_t *lut8, int lane, const K2Lane8 &k,
-                                               unsigned mlo, bool availA, bool availB, bool availC, bool availD)
+__device__ __forceinline__ void k2_luma8_block(const K2Ctx &c, unsigned modes, unsigned fix, bool availA, bool availB, bool availC)
 {
-    uint8_t *lt = s.lt;
+    uint8_t *lt = c.lt;
+    const int lane = c.lane;
     constexpr int xo = (B8 & 1) * 8, yo = (B8 >> 1) * 8;
-    constexpr int org = (yo + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + xo;
-    const int mode = (int)((mlo >> (4 * B8)) & 15);
-    const bool left = B8 & 1 ? true : availA, up = B8 & 2 ? true : availB;
-    const bool upleft = B8 == 0 ? availD : (B8 == 1 ? availB : (B8 == 2 ? availA : true));
+    constexpr int org = K2_TO(xo, yo);
+    const unsigned mode = (modes >> (4 * B8)) & 15u;
+    const bool left = (B8 & 1) ? true : availA, up = (B8 & 2) ? true : availB;
     const bool tr = B8 == 0 ? availB : (B8 == 1 ? availC : (B8 == 2));
 
-    const int raw = lt[org + (tr ? k.off_tr : k.off_notr)];
+    const int raw = lt[org + (tr ? c.n8tr : c.n8notr)];
     int prev = __shfl_up_sync(MVG_FULL, raw, 1), next = __shfl_down_sync(MVG_FULL, raw, 1);
-    if (lane == 0) prev = raw;                              /* p'[-1,7] = (p[-1,6] + 3 p[-1,7] + 2) >> 2 */
-    if (lane == 24) next = raw;                             /* p'[15,-1] */
-    if (!upleft) { if (lane == 7) next = raw; if (lane == 9) prev = raw; }
-    if (lane == 8) { if (!left) prev = raw; if (!up) next = raw; }
+    /* lane 0 gets its own value back (p'[-1,7] = (p[-1,6] + 3 p[-1,7] + 2) >> 2); lane 25 loads what lane 24
+     * loads (p'[15,-1]); the corner and its neighbours replicate when a side is missing */
+    if (B8 != 3) {
+        if (fix & (1u << (2 * B8))) next = raw;
+        if (fix & (2u << (2 * B8))) prev = raw;
+    }
     const int filt = (prev + 2 * raw + next + 2) >> 2;
-    int fp = __shfl_up_sync(MVG_FULL, filt, 1), fn = __shfl_down_sync(MVG_FULL, filt, 1);
-    if (lane == 0) fp = filt;
+    const int fp = __shfl_up_sync(MVG_FULL, filt, 1);
+    int fn = __shfl_down_sync(MVG_FULL, filt, 1);
     if (lane == 24) fn = filt;
     const int f2 = (filt + fn + 1) >> 1, f3 = (fp + 2 * filt + fn + 2) >> 2;
-    if (lane < 25) s.n8[lane] = (unsigned)filt | ((unsigned)f2 << 8) | ((unsigned)f3 << 16);
+    c.n8[lane] = (unsigned)filt | ((unsigned)f2 << 8) | ((unsigned)f3 << 16);
     if (mode == 2) {                                        /* warp-uniform */
         int v = 0;
         if (lane < 8 && left) v = filt;
@@ -615,78 +651,69 @@ __device__ __forceinline__ void k2_luma8_block(K2WarpSmem &s, const uint16_t *lu
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MVG_FULL, v, o);
         v = (left && up) ? (v + 8) >> 4 : (left || up) ? (v + 4) >> 3 : 128;
-        if (lane == 0) s.n8[MVG_N8_DC] = (unsigned)v;
+        if (lane == 0) c.n8[MVG_N8_DC] = (unsigned)v;
     }
     __syncwarp();
-    const int px = lane & 7, py = lane >> 3;
-    const uint16_t *lrow = lut8 + mode * 64 + lane;         /* sample (px, py), then (px, py + 4) */
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int y = py + 4 * h;
-        const unsigned e = lrow[32 * h];
-        const unsigned w = *reinterpret_cast<const unsigned *>(reinterpret_cast<const uint8_t *>(s.n8) + (e & 255));
-        const int pred = (w >> (e >> 8)) & 255;
-        const int r = s.resid[(B8 * 4 + (y >> 2) * 2 + (px >> 2)) * 16 + (y & 3) * 4 + (px & 3)];
-        lt[org + y * MVG_LT_STRIDE + px] = (uint8_t)mvg_add_clip8(pred, r);
-    }
+    const uint4 e = *reinterpret_cast<const uint4 *>(c.lut8 + mode * 512 + lane * 16);
+    const unsigned p0 = __byte_perm(*reinterpret_cast<const unsigned *>(reinterpret_cast<const uint8_t *>(c.n8) + e.x), 0, e.y);
+    const unsigned pp = __byte_perm(*reinterpret_cast<const unsigned *>(reinterpret_cast<const uint8_t *>(c.n8) + e.z), p0, e.w);
+    const unsigned r2 = *reinterpret_cast<const unsigned *>(c.resid + B8 * 128 + c.r8);
+    *reinterpret_cast<uint16_t *>(lt + org + c.s8) = (uint16_t)__byte_perm(mvg_add_clip8x2(pp, r2), 0, 0x4420);
     __syncwarp();
 }
 
-__device__ __forceinline__ void k2_luma8(K2WarpSmem &s, const uint16_t *lut8, int lane, const K2Lane8 &k,
-                                         unsigned mlo, bool availA, bool availB, bool availC, bool availD)
+__device__ __forceinline__ void k2_luma8(const K2Ctx &c, unsigned modes, bool availA, bool availB, bool availC, bool availD)
 {
-    k2_luma8_block<0>(s, lut8, lane, k, mlo, availA, availB, availC, availD);
-    k2_luma8_block<1>(s, lut8, lane, k, mlo, availA, availB, availC, availD);
-    k2_luma8_block<2>(s, lut8, lane, k, mlo, availA, availB, availC, availD);
-    k2_luma8_block<3>(s, lut8, lane, k, mlo, availA, availB, availC, availD);
+    const unsigned fix = (availA ? 0u : c.fixA) | (availB ? 0u : c.fixB) | (availD ? 0u : c.fixD);
+    k2_luma8_block<0>(c, modes, fix, availA, availB, availC);
+    k2_luma8_block<1>(c, modes, fix, availA, availB, availC);
+    k2_luma8_block<2>(c, modes, fix, availA, availB, availC);
+    k2_luma8_block<3>(c, modes, fix, availA, availB, availC);
 }
 
 /* ---- chroma, both planes at once (h264_intra_prediction.c:2338-2564) --------- */
-__device__ __forceinline__ void k2_chroma(K2WarpSmem &s, int lane, int mode, bool left, bool up)
+/* lane = 16 * plane + 2 * y + (x0 / 4): four samples of one row as two int16 pairs */
+__device__ __forceinline__ void k2_chroma(const K2Ctx &c, int mode, bool left, bool up)
 {
-    const int pl = lane >> 4, y = (lane & 15) >> 1, x0 = (lane & 1) * 4;
-    uint8_t *ct = s.ct[pl];
-    const int top = MVG_CT_XOFF, lcol = MVG_CT_XOFF - 1;
-    int pred[4];
+    const int lane = c.lane, pl = lane >> 4, y = (lane >> 1) & 7, x0 = (lane & 1) * 4;
+    uint8_t *ct = c.ct + pl * (MVG_CT_ROWS * MVG_CT_STRIDE);
+    unsigned p0, p1;
     if (mode == 0) {            /* DC, per 4x4 block */
         const int yo = y & 4;
         int st = 0, sl = 0;
-        if (up) st = mvg_sum4(*reinterpret_cast<const unsigned *>(ct + top + x0));
-        if (left) sl = (int)ct[(yo + 1) * MVG_CT_STRIDE + lcol] + (int)ct[(yo + 2) * MVG_CT_STRIDE + lcol] +
-                       (int)ct[(yo + 3) * MVG_CT_STRIDE + lcol] + (int)ct[(yo + 4) * MVG_CT_STRIDE + lcol];
+        if (up) st = mvg_sum4(*reinterpret_cast<const unsigned *>(ct + K2_CO(0, -1) + x0));
+        if (left) sl = (int)ct[K2_CO(-1, 0) + yo * MVG_CT_STRIDE] + (int)ct[K2_CO(-1, 1) + yo * MVG_CT_STRIDE] +
+                       (int)ct[K2_CO(-1, 2) + yo * MVG_CT_STRIDE] + (int)ct[K2_CO(-1, 3) + yo * MVG_CT_STRIDE];
         int v;
         if (!left && !up) v = 128;
         else if ((x0 == 0) == (yo == 0))       /* blocks (0,0) and (4,4) */
             v = (left && up) ? (st + sl + 4) >> 3 : left ? (sl + 2) >> 2 : (st + 2) >> 2;
         else if (x0 > 0) v = up ? (st + 2) >> 2 : (sl + 2) >> 2;          /* (4,0): top first  */
         else v = left ? (sl + 2) >> 2 : (st + 2) >> 2;                    /* (0,4): left first */
-        pred[0] = pred[1] = pred[2] = pred[3] = v;
+        p0 = p1 = (unsigned)v * 0x10001u;
     } else if (mode == 1) {     /* Horizontal */
-        const int v = ct[(y + 1) * MVG_CT_STRIDE + lcol];
-        pred[0] = pred[1] = pred[2] = pred[3] = v;
+        p0 = p1 = (unsigned)ct[K2_CO(-1, 0) + y * MVG_CT_STRIDE] * 0x10001u;
     } else if (mode == 2) {     /* Vertical */
-        const unsigned t = *reinterpret_cast<const unsigned *>(ct + top + x0);
-#pragma unroll
-        for (int i = 0; i < 4; i++) pred[i] = (t >> (8 * i)) & 255;
+        const unsigned t = *reinterpret_cast<const unsigned *>(ct + K2_CO(0, -1) + x0);
+        p0 = mvg_pair_lo(t); p1 = mvg_pair_hi(t);
     } else {                    /* Plane */
         int H = 0, V = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            H += (i + 1) * ((int)ct[top + 4 + i] - (int)ct[top + 2 - i]);
-            V += (i + 1) * ((int)ct[(5 + i) * MVG_CT_STRIDE + lcol] - (int)ct[(3 - i) * MVG_CT_STRIDE + lcol]);
+            H += (i + 1) * ((int)ct[K2_CO(4 + i, -1)] - (int)ct[K2_CO(2 - i, -1)]);
+            V += (i + 1) * ((int)ct[K2_CO(-1, 4 + i)] - (int)ct[K2_CO(-1, 2 - i)]);
         }
-        const int a = 16 * ((int)ct[8 * MVG_CT_STRIDE + lcol] + (int)ct[top + 7]);
-        const int b = (34 * H + 32) >> 6, c = (34 * V + 32) >> 6;
-        const int base = a + c * (y - 3) + 16;
-#pragma unroll
-        for (int k = 0; k < 4; k++) pred[k] = mvg_clip8((base + b * (x0 + k - 3)) >> 5);
+        const int a = 16 * ((int)ct[K2_CO(-1, 7)] + (int)ct[K2_CO(7, -1)]);
+        const int b = (34 * H + 32) >> 6, cc = (34 * V + 32) >> 6;
+        /* |a + b (x - 3) + c (y - 3) + 16| < 2^15: int16 pairs as in the luma plane predictor */
+        const int v0 = a + cc * (y - 3) + 16 + b * (x0 - 3);
+        const unsigned pair = __vadd2((unsigned)(v0 & 0xffff) * 0x10001u, (unsigned)b << 16);
+        p0 = (__vimin_s16x2_relu(pair, 0x1fff1fffu) >> 5) & 0x00ff00ffu;
+        p1 = (__vimin_s16x2_relu(__vadd2(pair, (unsigned)((2 * b) & 0xffff) * 0x10001u), 0x1fff1fffu) >> 5) & 0x00ff00ffu;
     }
-    const uint2 r = *reinterpret_cast<const uint2 *>(s.resid + 256 + pl * 64 + ((y >> 2) * 2 + (x0 >> 2)) * 16 + (y & 3) * 4);
-    const unsigned p0 = (unsigned)mvg_add_clip8(pred[0], (short)(r.x & 0xffff));
-    const unsigned p1 = (unsigned)mvg_add_clip8(pred[1], (int)r.x >> 16);
-    const unsigned p2 = (unsigned)mvg_add_clip8(pred[2], (short)(r.y & 0xffff));
-    const unsigned p3 = (unsigned)mvg_add_clip8(pred[3], (int)r.y >> 16);
-    *reinterpret_cast<unsigned *>(ct + (y + 1) * MVG_CT_STRIDE + MVG_CT_XOFF + x0) = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+    const uint2 r = *reinterpret_cast<const uint2 *>(c.resid + (256 + pl * 64 + ((y >> 2) * 2 + (x0 >> 2)) * 16 + (y & 3) * 4) * 2);
+    *reinterpret_cast<unsigned *>(ct + K2_CO(0, 0) + y * MVG_CT_STRIDE + x0) =
+        mvg_pairs_to_bytes(mvg_add_clip8x2(p0, r.x), mvg_add_clip8x2(p1, r.y));
 }
 
 /* Persistent warps.  A work item is one macroblock row of one picture; a warp claims items
@@ -701,22 +728,30 @@ __device__ __forceinline__ void k2_chroma(K2WarpSmem &s, int lane, int mode, boo
  *
  * Claim order: pictures are taken in groups of `group`; inside a group items are ordered
  * row-major over (row, picture).  Row r-1 of a picture is therefore always claimed before row
- * r (no deadlock: it runs on a resident warp), and `group` items earlier, so in steady state
- * it is many macroblocks ahead and the spin is rarely entered. */
-__global__ void __launch_bounds__(K2_WARPS * 32, 8)
+ * r (no deadlock: it runs on a resident warp).
+ *
+ * Inputs arrive by bulk asynchronous copies (one elected lane, mbarrier completion): the control
+ * records of the whole row once per row, the 768-byte residual of macroblock x+1 while x is being
+ * predicted.  The kernel is bound by instruction issue, not by HBM, so everything in the loop is
+ * organised to cost as few warp instructions as possible: shared-memory addresses are
+ * [lane constant + uniform base + immediate], tables hold ready-to-use offsets and byte-permute
+ * selectors, residual adds run on int16 pairs. */
+__global__ void __launch_bounds__(K2_WARPS * 32, 2)
 k2_wavefront(K2Params p)
 {
-    __shared__ uint32_t s_lut4[2 * 9 * 16];
-    __shared__ uint16_t s_lut8[9 * 64];
-    __shared__ K2WarpSmem s_warp[K2_WARPS];
-
-    for (int i = threadIdx.x; i < 2 * 9 * 16; i += blockDim.x) s_lut4[i] = (&p.luts->lut4[0][0][0])[i];
-    for (int i = threadIdx.x; i < 9 * 64 / 2; i += blockDim.x)
-        reinterpret_cast<uint32_t *>(s_lut8)[i] = reinterpret_cast<const uint32_t *>(&p.luts->lut8[0][0])[i];
+    extern __shared__ __align__(128) uint8_t k2_smem[];
+    const int lane = threadIdx.x & 31;
+    const unsigned wid = __shfl_sync(MVG_FULL, threadIdx.x >> 5, 0);       /* warp-uniform by construction */
+    K2WarpSmem &s = reinterpret_cast<K2WarpSmem *>(k2_smem)[wid];
+    const unsigned lut_addr = (mvg_smem_u32(k2_smem) + (unsigned)(sizeof(K2WarpSmem) * K2_WARPS) + 8191u) & ~8191u;
+    MvgLuts *luts = reinterpret_cast<MvgLuts *>(k2_smem + (lut_addr - mvg_smem_u32(k2_smem)));
+    for (int i = threadIdx.x; i < (int)(sizeof(MvgLuts) / 16); i += blockDim.x)
+        reinterpret_cast<uint4 *>(luts)[i] = __ldg(reinterpret_cast<const uint4 *>(p.luts) + i);
+    if (lane == 0) { mvg_mbar_init(&s.mbar[0], 1); mvg_mbar_init(&s.mbar[1], 1); mvg_mbar_init(&s.mbar[2], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    K2WarpSmem &s = s_warp[threadIdx.x >> 5];
     const int W = p.w_mbs, H = p.h_mbs, n_mb = W * H;
     const int ystride = W * 16, cstride = W * 8;
     const size_t pic_bytes = (size_t)n_mb * 384;
@@ -724,26 +759,52 @@ k2_wavefront(K2Params p)
     const unsigned epoch = p.epoch;
 
     /* per-lane constants --------------------------------------------------------------- */
+    K2Ctx c;
+    c.lt = s.lt; c.ct = &s.ct[0][0]; c.n8 = s.n8; c.lut8 = reinterpret_cast<const uint8_t *>(&luts->lut8[0][0][0]);
+    c.lane = lane;
+    c.resid = reinterpret_cast<const uint8_t *>(s.resid[0]);
+    {
+        const int half = lane >> 4, pix = lane & 15, px = pix & 3, py = pix >> 2;
+        c.lut4 = lut_addr + (unsigned)((half * 256 + pix) * 16);
+        c.h4 = half ? 8 - 4 * MVG_LT_STRIDE : 0;
+        c.s4 = py * MVG_LT_STRIDE + px + c.h4;
+        c.r4odd = pix * 2 + (half ? 64 : 0);
+        c.r4even = pix * 2 + (half ? -64 : 0);
+        c.m4c = half ? 0x10100010u : 0x10001000u;
+        c.m4b = half ? 0x00000100u : 0x00000011u;
+        c.m4cc = half ? 0x00001000u : 0u;
+        /* Intra8x8 neighbour gather, relative to the block origin */
+        const int n = lane < 25 ? lane : 24;
+        if (n < 8)       c.n8tr = (7 - n) * MVG_LT_STRIDE - 1;
+        else if (n == 8) c.n8tr = -MVG_LT_STRIDE - 1;
+        else             c.n8tr = -MVG_LT_STRIDE + (n - 9);
+        c.n8notr = n > 16 ? -MVG_LT_STRIDE + 7 : c.n8tr;                    /* p[8..15,-1] := p[7,-1] */
+        const int y8 = lane >> 2, x8 = 2 * (lane & 3);
+        c.s8 = y8 * MVG_LT_STRIDE + x8;
+        c.r8 = (((y8 >> 2) * 2 + (x8 >> 2)) * 16 + (y8 & 3) * 4 + (x8 & 3)) * 2;
+        /* replicate at the corner: block 0 sees A, B, D of the macroblock; block 1: left = block 0, up and
+         * up-left from B; block 2: up = block 0, left and up-left from A */
+        c.fixA = lane == 7 ? 0x10u : lane == 8 ? 0x22u : lane == 9 ? 0x20u : 0u;
+        c.fixB = lane == 7 ? 0x04u : lane == 8 ? 0x05u : lane == 9 ? 0x08u : 0u;
+        c.fixD = lane == 7 ? 0x01u : lane == 9 ? 0x02u : 0u;
+    }
     /* halo word carried by lanes 0..7: 0..3 luma x = 4*lane, 4,5 Cb, 6,7 Cr */
-    uint8_t *const halo_top = lane < 4 ? s.lt + MVG_LT_XOFF + lane * 4
-                                       : s.ct[(lane >> 1) & 1] + MVG_CT_XOFF + (lane & 1) * 4;      /* sample row -1 */
+    uint8_t *const halo_top = lane < 4 ? s.lt + K2_TO(lane * 4, -1)
+                                       : s.ct[(lane >> 1) & 1] + K2_CO((lane & 1) * 4, -1);          /* sample row -1 */
     const uint8_t *const halo_bot = lane < 4 ? halo_top + 16 * MVG_LT_STRIDE : halo_top + 8 * MVG_CT_STRIDE;
-    /* column x = 15 -> x = -1 hand-over: lanes 0..16 luma rows -1..15, lanes 17..25 Cb rows -1..7, and a
-     * second move by lanes 0..8 for Cr */
-    uint8_t *const lc_dst = lane < 17 ? s.lt + lane * MVG_LT_STRIDE + MVG_LT_XOFF - 1
-                                      : s.ct[0] + (lane < 26 ? lane - 17 : 0) * MVG_CT_STRIDE + MVG_CT_XOFF - 1;
-    const int lc_span = lane < 17 ? 16 : 8;
-    uint8_t *const lc_dst2 = s.ct[1] + (lane < 9 ? lane : 0) * MVG_CT_STRIDE + MVG_CT_XOFF - 1;
+    /* column x = 15 -> x = -1 hand-over: lanes 0..16 luma rows -1..15, lanes 17..31 and, in a second move,
+     * lanes 0..2 the 2 x 9 chroma rows */
+    const int cj = lane >= 17 ? lane - 17 : min(lane + 15, 17);                      /* chroma hand-over item 0..17 */
+    uint8_t *const lc_src = lane < 17 ? s.lt + K2_TO(15, lane - 1)
+                                      : s.ct[cj / 9] + K2_CO(7, cj % 9 - 1);
+    const int lc_back = lane < 17 ? 16 : 8;
+    uint8_t *const lc_src2 = s.ct[cj / 9] + K2_CO(7, cj % 9 - 1);              /* used by lanes 0..2 */
     /* picture write-out: lanes 0..15 one luma row (16 B), lanes 16..23 Cb rows, 24..31 Cr rows (8 B) */
-    const uint8_t *const wo_src = lane < 16 ? s.lt + (lane + 1) * MVG_LT_STRIDE + MVG_LT_XOFF
-                                            : s.ct[(lane >> 3) & 1] + ((lane & 7) + 1) * MVG_CT_STRIDE + MVG_CT_XOFF;
-    /* Intra8x8 neighbour gather */
-    K2Lane8 k8;
-    if (lane < 8)       k8.off_tr = (7 - lane) * MVG_LT_STRIDE - 1;
-    else if (lane == 8) k8.off_tr = -MVG_LT_STRIDE - 1;
-    else if (lane < 25) k8.off_tr = -MVG_LT_STRIDE + (lane - 9);
-    else                k8.off_tr = 0;
-    k8.off_notr = (lane > 16 && lane < 25) ? -MVG_LT_STRIDE + 7 : k8.off_tr;     /* p[8..15,-1] := p[7,-1] */
+    const uint8_t *const wo_src = lane < 16 ? s.lt + K2_TO(0, lane)
+                                            : s.ct[(lane >> 3) & 1] + K2_CO(0, lane & 7);
+
+    unsigned parity = 0;            /* bit b: phase parity of mbar[b] */
+    unsigned nload = 0;             /* residual buffer the next bulk copy goes to */
 
     for (;;) {
         int item = 0;
@@ -756,22 +817,27 @@ k2_wavefront(K2Params p)
         const int row = within / gsize;
         const int slot = p.first_slot + g * p.group + (within - row * gsize);
 
+        const int16_t *resid = p.resid + ((size_t)slot * n_mb + (size_t)row * W) * 384;
+        const MvgMbCtl *ctl = p.ctl + (size_t)slot * n_mb + (size_t)row * W;
+        if (lane == 0) {            /* control records of the row (first chunk) and the first residual */
+            const unsigned cb = (unsigned)min(W, K2_CTL_CHUNK) * 16u;
+            mvg_mbar_expect_tx(&s.mbar[2], cb);
+            mvg_bulk_load(s.ctl, ctl, cb, &s.mbar[2]);
+            mvg_mbar_expect_tx(&s.mbar[nload], 768u);
+            mvg_bulk_load(s.resid[nload], resid, 768u, &s.mbar[nload]);
+        }
+        unsigned cur_buf = nload;
+        nload ^= 1u;
+
         uint8_t *ybase = p.yuv + (size_t)slot * pic_bytes;
         /* where this lane writes its row of every macroblock of this macroblock row */
         uint8_t *wo_dst = lane < 16 ? ybase + (size_t)(row * 16 + lane) * ystride
                                     : ybase + (size_t)n_mb * (lane < 24 ? 256 : 320) + (size_t)(row * 8 + (lane & 7)) * cstride;
         const int wo_step = lane < 16 ? 16 : 8;
-        const int16_t *resid = p.resid + ((size_t)slot * n_mb + (size_t)row * W) * 384;
-        const MvgMbCtl *ctl = p.ctl + (size_t)slot * n_mb + (size_t)row * W;
         const bool availB = row > 0, publish = row < H - 1;
         const uint2 *habove = p.halo + ((size_t)slot * n_mb + (size_t)(row - 1) * W) * 8 + lane;
         uint2 *hmine = p.halo + ((size_t)slot * n_mb + (size_t)row * W) * 8 + lane;
 
-        /* prefetch the first macroblock's inputs */
-        uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(resid) + lane);
-        uint4 r1 = make_uint4(0, 0, 0, 0);
-        if (lane < 16) r1 = __ldg(reinterpret_cast<const uint4 *>(resid) + 32 + lane);
-        uint4 c4 = __ldg(reinterpret_cast<const uint4 *>(ctl));
         /* halo words of the row above: cur = macroblock mx, nxt = macroblock mx+1 */
         uint2 cur = make_uint2(0, 0), nxt = make_uint2(0, 0);
         if (availB && lane < 8) {
@@ -786,23 +852,30 @@ k2_wavefront(K2Params p)
                 if (lane < 8) cur = mvg_ld_relaxed_u64(habove);
             }
         }
+        mvg_mbar_wait(&s.mbar[2], (parity >> 2) & 1u);
+        parity ^= 4u;
 
         for (int mx = 0; mx < W; mx++) {
-            reinterpret_cast<uint4 *>(s.resid)[lane] = r0;
-            if (lane < 16) reinterpret_cast<uint4 *>(s.resid)[32 + lane] = r1;
-            const uint4 ctlw = c4;
-            if (mx + 1 < W) {       /* software pipeline: next macroblock's loads fly during this one */
-                const uint4 *nr = reinterpret_cast<const uint4 *>(resid + (size_t)(mx + 1) * 384);
-                r0 = __ldg(nr + lane);
-                if (lane < 16) r1 = __ldg(nr + 32 + lane);
-                c4 = __ldg(reinterpret_cast<const uint4 *>(ctl + mx + 1));
+            if (mx && (mx & (K2_CTL_CHUNK - 1)) == 0) {     /* next chunk of control records */
+                if (lane == 0) {
+                    const unsigned cb = (unsigned)min(W - mx, K2_CTL_CHUNK) * 16u;
+                    mvg_mbar_expect_tx(&s.mbar[2], cb);
+                    mvg_bulk_load(s.ctl, ctl + mx, cb, &s.mbar[2]);
+                }
+                mvg_mbar_wait(&s.mbar[2], (parity >> 2) & 1u);
+                parity ^= 4u;
             }
+            /* the residual of macroblock mx+1 flies while mx is predicted; its buffer was last read
+             * before the __syncwarp() that closed macroblock mx-1 */
+            if (mx + 1 < W && lane == 0) {
+                mvg_mbar_expect_tx(&s.mbar[cur_buf ^ 1u], 768u);
+                mvg_bulk_load(s.resid[cur_buf ^ 1u], resid + (size_t)(mx + 1) * 384, 768u, &s.mbar[cur_buf ^ 1u]);
+            }
+            const uint4 ctlw = *reinterpret_cast<const uint4 *>(&s.ctl[mx & (K2_CTL_CHUNK - 1)]);
             const bool availA = mx > 0, availC = availB && mx < W - 1, availD = availA && availB;
 
             if (availB) {
                 if (availC) {       /* the up-right macroblock must have been published */
-                    /* rarely entered; when it is, this row has caught up with the row above, so sleep
-                     * for about a macroblock time instead of polling at full rate */
                     unsigned ns = 400;
                     while (!__all_sync(MVG_FULL, lane >= 8 || nxt.y == epoch)) {
                         __nanosleep(ns);
@@ -816,32 +889,35 @@ k2_wavefront(K2Params p)
                 cur = nxt;
                 if (mx + 2 < W && lane < 8) nxt = mvg_ld_relaxed_u64(habove + (size_t)(mx + 2) * 8);
             }
+            c.resid = reinterpret_cast<const uint8_t *>(s.resid[cur_buf]);
+            mvg_mbar_wait(&s.mbar[cur_buf], (parity >> cur_buf) & 1u);
+            parity ^= 1u << cur_buf;
             __syncwarp();
 
             const int kind = ctlw.x & 255, i16 = (ctlw.x >> 8) & 255, cmode = (ctlw.x >> 16) & 255;
-            if (kind == MVG_MB_I16x16)    k2_luma16(s, lane, i16, availA, availB);
-            else if (kind == MVG_MB_I4x4) k2_luma4(s, s_lut4, lane, ctlw.y, ctlw.z, availA, availB, availC);
-            else                          k2_luma8(s, s_lut8, lane, k8, ctlw.y, availA, availB, availC, availD);
-            k2_chroma(s, lane, cmode, availA, availB);
+            if (kind == MVG_MB_I16x16)    k2_luma16(c, i16, availA, availB);
+            else if (kind == MVG_MB_I4x4) k2_luma4(c, ctlw.y, ctlw.z, availA, availB, availC);
+            else                          k2_luma8(c, ctlw.y, availA, availB, availC, availD);
+            k2_chroma(c, cmode, availA, availB);
             __syncwarp();
 
             /* write the macroblock to the planar picture */
-            if (lane < 16) {
-                const uint2 a = *reinterpret_cast<const uint2 *>(wo_src);
-                const uint2 b = *reinterpret_cast<const uint2 *>(wo_src + 8);
-                *reinterpret_cast<uint4 *>(wo_dst) = make_uint4(a.x, a.y, b.x, b.y);
-            } else {
-                *reinterpret_cast<uint2 *>(wo_dst) = *reinterpret_cast<const uint2 *>(wo_src);
+            {
+                const uint4 v = *reinterpret_cast<const uint4 *>(wo_src);
+                if (lane < 16) *reinterpret_cast<uint4 *>(wo_dst) = v;
+                else *reinterpret_cast<uint2 *>(wo_dst) = make_uint2(v.x, v.y);
+                wo_dst += wo_step;
             }
-            wo_dst += wo_step;
             /* publish the bottom sample line for the row below */
             if (publish && lane < 8)
                 mvg_st_relaxed_u64(hmine + (size_t)mx * 8, *reinterpret_cast<const unsigned *>(halo_bot), epoch);
             /* next macroblock: x = 15 becomes x = -1 (luma rows -1..15, chroma x = 7, rows -1..7) */
-            if (lane < 26) *lc_dst = lc_dst[lc_span];
-            if (lane < 9) *lc_dst2 = lc_dst2[8];
+            lc_src[-lc_back] = lc_src[0];
+            if (lane < 3) lc_src2[-8] = lc_src2[0];
+            cur_buf ^= 1u;
             __syncwarp();
         }
+        nload = cur_buf;            /* the buffer after the last one used */
     }
 }
 

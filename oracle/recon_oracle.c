@@ -427,7 +427,9 @@ static void predict_chroma(const uint8_t *pix, int stride, int mode, int have_le
 }
 #undef PX
 
-static inline int16_t sat16(int32_t v) { return (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
+/* kernel 1 hands the residual on as int16 clamped to [-512, 511]: Clip1(pred + r) is the same for any
+ * clamp range that contains [-255, 255], and 255 + 511 stays inside a packed 16-bit add */
+static inline int16_t sat16(int32_t v) { return (int16_t)(v < -512 ? -512 : (v > 511 ? 511 : v)); }
 
 void oracle_reconstruct_picture(const oracle_sps *sps,
                                 const uint8_t *mb_kind, const uint8_t *i16_mode,

@@ -45,7 +45,7 @@ void oracle_mb_residual(const oracle_sps *sps, int mb_kind, int qp_y,
 
 /* Reconstruct one picture (kernels 1+2).  Arrays are indexed by mbAddr as in
  * mvgpu.h.  y: W*H, cb/cr: (W/2)*(H/2).  residual_out (optional): [N][384]
- * int16, saturated. */
+ * int16, clamped to [-512, 511] (the intermediate kernel 1 hands to kernel 2). */
 void oracle_reconstruct_picture(const oracle_sps *sps,
                                 const uint8_t *mb_kind, const uint8_t *i16_mode,
                                 const uint8_t *chroma_mode, const int8_t *qp_y,

@@ -66,12 +66,23 @@ def test_pred_tap_tables_reproduce_the_oracle_predictors():
     from oracle import cpu
 
     class Luts(C.Structure):
-        _fields_ = [("lut4", C.c_uint32 * (2 * 9 * 16)), ("lut8", C.c_uint16 * (9 * 64))]
+        _fields_ = [("lut4", C.c_int32 * (2 * 16 * 16 * 4)), ("lut8", C.c_uint32 * (9 * 32 * 4))]
     lib = api.load_library()
     luts = Luts()
     lib.mvg_build_luts(C.byref(luts))
-    lut4 = np.frombuffer(luts.lut4, np.uint32).reshape(2, 9, 16)
-    lut8 = np.frombuffer(luts.lut8, np.uint16).reshape(9, 64)
+    lut4 = np.frombuffer(luts.lut4, np.int32).reshape(2, 16, 16, 4)
+    lut8 = np.frombuffer(luts.lut8, np.uint32).reshape(9, 32, 4)
+    STRIDE, BIAS = 48, 240                                  # MVG_LT_STRIDE, MVG_LUT4_BIAS
+    # lanes 16..31 predict the block 8 samples to the right and 4 rows up of the block of lanes 0..15
+    used = [m for m in range(16) if m in (0, 1, 3, 4, 5, 6, 7, 8, 11, 15)]
+    assert np.array_equal(lut4[1][used], lut4[0][used] + 8 - 4 * STRIDE)
+    assert lut4.min() >= 0
+    # rows 11 / 15: modes 3 / 7 with the taps on p[4..7,-1] moved to p[3,-1]
+    for row, mode in ((11, 3), (15, 7)):
+        off = lut4[0, mode] - BIAS
+        top = (off + 1) // STRIDE == -1
+        clamped = np.where(top & (off + STRIDE > 3), -STRIDE + 3, off)
+        assert np.array_equal(lut4[0, row] - BIAS, clamped)
     rng = np.random.default_rng(1)
 
     # 2x2-MB picture: MBs 0,1,2 are I16x16 with random DC so that MB 3 sees random neighbours;
@@ -97,12 +108,12 @@ def test_pred_tap_tables_reproduce_the_oracle_predictors():
                 pred = np.zeros((4, 4), np.int32)
                 for y in range(4):
                     for x in range(4):
-                        w = int(lut4[1, mode, y * 4 + x])
                         s = 0
                         for k in range(4):
-                            off = ((w >> (8 * k)) & 255) - 33     # biased by MVG_LUT4_BIAS = stride + 1
-                            dy, dx = divmod(off + 32 + 8, 32)     # stride 32, offsets relative to block origin
-                            s += Y[y0 + dy - 1, x0 + dx - 8]
+                            off = int(lut4[0, mode, y * 4 + x, k]) - BIAS   # relative to the block origin
+                            dy = (off + 1) // STRIDE
+                            dx = off - dy * STRIDE
+                            s += Y[y0 + dy, x0 + dx]
                         pred[y, x] = (s + 2) >> 2
                 assert np.array_equal(pred, Y[y0:y0 + 4, x0:x0 + 4]), (kind, mode)
             else:
@@ -123,6 +134,12 @@ def test_pred_tap_tables_reproduce_the_oracle_predictors():
                 pred = np.zeros((8, 8), np.int32)
                 for y in range(8):
                     for x in range(8):
-                        w = int(lut8[mode, y * 8 + x])
-                        pred[y, x] = variants[w >> 8][(w & 255) // 4]
+                        e = lut8[mode, y * 4 + x // 2]
+                        if x % 2 == 0:
+                            assert int(e[1]) >> 4 == 0x444
+                            idx, var = int(e[0]) // 4, int(e[1]) & 15
+                        else:
+                            assert int(e[3]) & 0xF0FF == 0x5054
+                            idx, var = int(e[2]) // 4, (int(e[3]) >> 8) & 15
+                        pred[y, x] = variants[8 * var][idx]
                 assert np.array_equal(pred, Y[y0:y0 + 8, x0:x0 + 8]), (kind, mode)

@@ -28,14 +28,15 @@ def test_cli_builds_and_rejects_bad_arguments(cli):
     assert r.returncode == 1 and "cannot open" in r.stderr
 
 
-def _run_both(stream: bytes, args: list[str]):
+def _run_both(stream: bytes, args: list[str], ref_may_crash: bool = False):
     """Run both CLIs in separate scratch directories on the same stream; return {file name: bytes} each."""
     out = []
     for exe, extra in ((ref.MINI_THUMBNAILER, []), (MV, ["-o", "."])):
         with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
             (Path(d) / "in.264").write_bytes(stream)
             r = subprocess.run([str(exe), "-i", str(Path(d) / "in.264")] + args + extra, capture_output=True, text=True, cwd=d)
-            assert r.returncode == 0, (exe, r.stdout[-1500:], r.stderr[-1500:])
+            if not (ref_may_crash and exe == ref.MINI_THUMBNAILER):
+                assert r.returncode == 0, (exe, r.stdout[-1500:], r.stderr[-1500:])
             out.append({p.name: p.read_bytes() for p in Path(d).iterdir() if p.name != "in.264"})
     return out
 
@@ -48,8 +49,16 @@ def test_cli_files_equal_the_reference_cli(cli, fmt, mode, n):
     if not ref.MINI_THUMBNAILER.exists():
         pytest.skip("reference CLI not built")
     stream, _ = synth.generate(12, "cif", seed=901)
-    want, got = _run_both(stream, ["-f", fmt, "-n", str(n), "-e", mode])
-    assert sorted(want) == sorted(got)
+    # 'distributed' indexes one past its candidate list in the reference (demuxer/filter.c:179-186) and
+    # can abort after writing some of the pictures: compare what it did write
+    crashy = mode == "distributed"
+    want, got = _run_both(stream, ["-f", fmt, "-n", str(n), "-e", mode], ref_may_crash=crashy)
+    want = {k: v for k, v in want.items() if not k.startswith("core")}
+    if crashy:
+        assert set(want) <= set(got) and len(want) >= n - 1
+        want.pop(sorted(want)[-1])          # the last file may be cut short by the abort
+    else:
+        assert sorted(want) == sorted(got)
     for name in want:
         assert want[name] == got[name], name
 
