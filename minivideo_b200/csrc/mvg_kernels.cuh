@@ -438,25 +438,28 @@ struct K2Params {
     const MvgLuts  *luts;
     unsigned        epoch;      /* flag value that marks halo words of THIS launch */
     int w_mbs, h_mbs, first_slot, n_pics, group;
+    int stagger;                /* a row starts once the row above has published this many macroblocks */
 };
 
 #define K2_WARPS     16         /* warps per CTA; two CTAs per SM                              */
-#define K2_CTL_CHUNK 128        /* control records staged in shared memory per bulk copy       */
+#define K2_CTL_CHUNK 32         /* control records per bulk copy (two buffers)                 */
+#define K2_RING      4          /* residual ring slots (power of two)                          */
 #define K2_TO(x, y)  (((y) + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + (x))    /* luma tile offset of sample (x, y)   */
 #define K2_CO(x, y)  (((y) + 1) * MVG_CT_STRIDE + MVG_CT_XOFF + (x))    /* chroma tile offset of sample (x, y) */
 
 struct K2WarpSmem {
-    __align__(128) int16_t  resid[2][384];      /* residual of this and of the next macroblock (bulk async copies) */
-    __align__(16)  MvgMbCtl ctl[K2_CTL_CHUNK];  /* control records of the macroblock row                          */
+    __align__(128) int16_t  resid[K2_RING][384];        /* residual ring, filled by bulk async copies K2_RING-1 macroblocks ahead */
+    __align__(16)  MvgMbCtl ctl[2][K2_CTL_CHUNK];       /* control records, double buffered                                   */
     __align__(16)  uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
     __align__(16)  uint8_t  ct[2][MVG_CT_ROWS * MVG_CT_STRIDE];
-    __align__(16)  uint32_t n8[36];             /* Intra8x8 neighbour line: p' | f2 << 8 | f3 << 16; [32] = DC     */
-    __align__(8)   uint64_t mbar[3];            /* resid[0], resid[1], ctl                                         */
+    __align__(16)  uint32_t n8[36];                     /* Intra8x8 neighbour line: p' | f2 << 8 | f3 << 16; [32] = DC */
+    __align__(8)   uint64_t mbar[K2_RING + 2];          /* residual ring slots, then the two control buffers */
 };
 
-/* dynamic shared memory: [K2WarpSmem x K2_WARPS][pad to 8 KB][MvgLuts]; the Intra4x4 tap table must sit on
- * an 8 KB boundary so that (mode << 8) can be OR-ed into a lane's table address */
-#define K2_SMEM_BYTES (sizeof(K2WarpSmem) * K2_WARPS + 8192 + sizeof(MvgLuts))
+/* dynamic shared memory: warp records, with the tap tables on the first 8 KB boundary (so that (mode << 8) can be
+ * OR-ed into a lane's table address); one spare record covers the worst placement */
+#define K2_LUT_BYTES  sizeof(MvgLuts)
+#define K2_SMEM_BYTES (sizeof(K2WarpSmem) * (K2_WARPS + 1) + K2_LUT_BYTES)
 
 __device__ __forceinline__ uint2 mvg_ld_relaxed_u64(const uint2 *p)
 {
@@ -742,12 +745,18 @@ k2_wavefront(K2Params p)
     extern __shared__ __align__(128) uint8_t k2_smem[];
     const int lane = threadIdx.x & 31;
     const unsigned wid = __shfl_sync(MVG_FULL, threadIdx.x >> 5, 0);       /* warp-uniform by construction */
-    K2WarpSmem &s = reinterpret_cast<K2WarpSmem *>(k2_smem)[wid];
-    const unsigned lut_addr = (mvg_smem_u32(k2_smem) + (unsigned)(sizeof(K2WarpSmem) * K2_WARPS) + 8191u) & ~8191u;
-    MvgLuts *luts = reinterpret_cast<MvgLuts *>(k2_smem + (lut_addr - mvg_smem_u32(k2_smem)));
+    /* layout: the tap tables sit on the first 8 KB boundary; warp records fill the space before it, the
+     * others follow the tables */
+    const unsigned base = mvg_smem_u32(k2_smem);
+    const unsigned lut_addr = (base + 8191u) & ~8191u;
+    const unsigned n_before = (lut_addr - base) / (unsigned)sizeof(K2WarpSmem);
+    MvgLuts *luts = reinterpret_cast<MvgLuts *>(k2_smem + (lut_addr - base));
+    K2WarpSmem &s = *reinterpret_cast<K2WarpSmem *>(
+        wid < n_before ? k2_smem + wid * sizeof(K2WarpSmem)
+                       : k2_smem + (lut_addr - base) + K2_LUT_BYTES + (wid - n_before) * sizeof(K2WarpSmem));
     for (int i = threadIdx.x; i < (int)(sizeof(MvgLuts) / 16); i += blockDim.x)
         reinterpret_cast<uint4 *>(luts)[i] = __ldg(reinterpret_cast<const uint4 *>(p.luts) + i);
-    if (lane == 0) { mvg_mbar_init(&s.mbar[0], 1); mvg_mbar_init(&s.mbar[1], 1); mvg_mbar_init(&s.mbar[2], 1); }
+    if (lane < K2_RING + 2) mvg_mbar_init(&s.mbar[lane], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -788,13 +797,15 @@ k2_wavefront(K2Params p)
         c.fixB = lane == 7 ? 0x04u : lane == 8 ? 0x05u : lane == 9 ? 0x08u : 0u;
         c.fixD = lane == 7 ? 0x01u : lane == 9 ? 0x02u : 0u;
     }
-    /* halo word carried by lanes 0..7: 0..3 luma x = 4*lane, 4,5 Cb, 6,7 Cr */
+    /* sample row -1 of the tiles comes from the halo words of the row above: lanes 0..3 luma x = 4*lane,
+     * 4,5 Cb, 6,7 Cr of the macroblock above, lanes 8,9 luma x = 16..23 of the macroblock above-right */
     uint8_t *const halo_top = lane < 4 ? s.lt + K2_TO(lane * 4, -1)
-                                       : s.ct[(lane >> 1) & 1] + K2_CO((lane & 1) * 4, -1);          /* sample row -1 */
+                            : lane < 8 ? s.ct[(lane >> 1) & 1] + K2_CO((lane & 1) * 4, -1)
+                                       : s.lt + K2_TO(16 + (lane & 1) * 4, -1);
     const uint8_t *const halo_bot = lane < 4 ? halo_top + 16 * MVG_LT_STRIDE : halo_top + 8 * MVG_CT_STRIDE;
     /* column x = 15 -> x = -1 hand-over: lanes 0..16 luma rows -1..15, lanes 17..31 and, in a second move,
      * lanes 0..2 the 2 x 9 chroma rows */
-    const int cj = lane >= 17 ? lane - 17 : min(lane + 15, 17);                      /* chroma hand-over item 0..17 */
+    const int cj = lane >= 17 ? lane - 17 : min(lane + 15, 17);            /* chroma hand-over item 0..17 */
     uint8_t *const lc_src = lane < 17 ? s.lt + K2_TO(15, lane - 1)
                                       : s.ct[cj / 9] + K2_CO(7, cj % 9 - 1);
     const int lc_back = lane < 17 ? 16 : 8;
@@ -803,8 +814,8 @@ k2_wavefront(K2Params p)
     const uint8_t *const wo_src = lane < 16 ? s.lt + K2_TO(0, lane)
                                             : s.ct[(lane >> 3) & 1] + K2_CO(0, lane & 7);
 
-    unsigned parity = 0;            /* bit b: phase parity of mbar[b] */
-    unsigned nload = 0;             /* residual buffer the next bulk copy goes to */
+    unsigned parity = 0;            /* bit b: phase parity of mbar[b] (0..K2_RING-1 residual ring, then 2 control buffers) */
+    unsigned rb = 0;                /* ring slot of the current macroblock's residual */
 
     for (;;) {
         int item = 0;
@@ -819,15 +830,16 @@ k2_wavefront(K2Params p)
 
         const int16_t *resid = p.resid + ((size_t)slot * n_mb + (size_t)row * W) * 384;
         const MvgMbCtl *ctl = p.ctl + (size_t)slot * n_mb + (size_t)row * W;
-        if (lane == 0) {            /* control records of the row (first chunk) and the first residual */
+        if (lane == 0) {            /* first chunk of control records, first residuals of the row */
             const unsigned cb = (unsigned)min(W, K2_CTL_CHUNK) * 16u;
-            mvg_mbar_expect_tx(&s.mbar[2], cb);
-            mvg_bulk_load(s.ctl, ctl, cb, &s.mbar[2]);
-            mvg_mbar_expect_tx(&s.mbar[nload], 768u);
-            mvg_bulk_load(s.resid[nload], resid, 768u, &s.mbar[nload]);
+            mvg_mbar_expect_tx(&s.mbar[K2_RING], cb);
+            mvg_bulk_load(s.ctl[0], ctl, cb, &s.mbar[K2_RING]);
+            for (int i = 0; i < K2_RING - 1 && i < W; i++) {
+                const unsigned b = (rb + i) & (K2_RING - 1);
+                mvg_mbar_expect_tx(&s.mbar[b], 768u);
+                mvg_bulk_load(s.resid[b], resid + (size_t)i * 384, 768u, &s.mbar[b]);
+            }
         }
-        unsigned cur_buf = nload;
-        nload ^= 1u;
 
         uint8_t *ybase = p.yuv + (size_t)slot * pic_bytes;
         /* where this lane writes its row of every macroblock of this macroblock row */
@@ -835,63 +847,90 @@ k2_wavefront(K2Params p)
                                     : ybase + (size_t)n_mb * (lane < 24 ? 256 : 320) + (size_t)(row * 8 + (lane & 7)) * cstride;
         const int wo_step = lane < 16 ? 16 : 8;
         const bool availB = row > 0, publish = row < H - 1;
+        /* halo words of the row above, four macroblocks per coalesced load: lane = 8 * (mx & 3) + word */
         const uint2 *habove = p.halo + ((size_t)slot * n_mb + (size_t)(row - 1) * W) * 8 + lane;
         uint2 *hmine = p.halo + ((size_t)slot * n_mb + (size_t)row * W) * 8 + lane;
-
-        /* halo words of the row above: cur = macroblock mx, nxt = macroblock mx+1 */
-        uint2 cur = make_uint2(0, 0), nxt = make_uint2(0, 0);
-        if (availB && lane < 8) {
-            cur = mvg_ld_relaxed_u64(habove);
-            if (W > 1) nxt = mvg_ld_relaxed_u64(habove + 8);
-        }
+        const int hwords = W * 8;                               /* halo words of a macroblock row */
+        uint2 qa = make_uint2(0, epoch), qb = make_uint2(0, epoch);
         if (availB) {
-            unsigned ns = 64;
-            while (!__all_sync(MVG_FULL, lane >= 8 || cur.y == epoch)) {
-                __nanosleep(ns);
-                if (ns < 2048) ns *= 2;
-                if (lane < 8) cur = mvg_ld_relaxed_u64(habove);
+            if (p.stagger > 1) {
+                /* keep rows of one picture apart: a row that runs two macroblocks behind the row above waits
+                 * on every macroblock and inherits all of its stalls */
+                const uint2 *far = habove + (size_t)(min(p.stagger, W) - 1) * 8;
+                uint2 t = make_uint2(0, epoch);
+                if (lane < 8) t = mvg_ld_relaxed_u64(far);
+                unsigned ns = 256;
+                while (!__all_sync(MVG_FULL, t.y == epoch)) {
+                    __nanosleep(ns);
+                    if (ns < 4096) ns *= 2;
+                    if (lane < 8) t = mvg_ld_relaxed_u64(far);
+                }
             }
+            if (lane < hwords) qa = mvg_ld_relaxed_u64(habove);
+            if (lane + 32 < hwords) qb = mvg_ld_relaxed_u64(habove + 32);
         }
-        mvg_mbar_wait(&s.mbar[2], (parity >> 2) & 1u);
-        parity ^= 4u;
+        mvg_mbar_wait(&s.mbar[K2_RING], (parity >> K2_RING) & 1u);
+        parity ^= 1u << K2_RING;
 
         for (int mx = 0; mx < W; mx++) {
-            if (mx && (mx & (K2_CTL_CHUNK - 1)) == 0) {     /* next chunk of control records */
-                if (lane == 0) {
-                    const unsigned cb = (unsigned)min(W - mx, K2_CTL_CHUNK) * 16u;
-                    mvg_mbar_expect_tx(&s.mbar[2], cb);
-                    mvg_bulk_load(s.ctl, ctl + mx, cb, &s.mbar[2]);
+            const int j = mx & 3;
+            const unsigned cbuf = (unsigned)(mx / K2_CTL_CHUNK) & 1u;
+            if ((mx & (K2_CTL_CHUNK - 1)) == 0) {
+                /* this chunk of control records was requested one chunk ago (or in the row prologue);
+                 * request the next one into the other buffer, whose last reader finished a macroblock ago */
+                if (mx) {
+                    mvg_mbar_wait(&s.mbar[K2_RING + cbuf], (parity >> (K2_RING + cbuf)) & 1u);
+                    parity ^= 1u << (K2_RING + cbuf);
                 }
-                mvg_mbar_wait(&s.mbar[2], (parity >> 2) & 1u);
-                parity ^= 4u;
+                if (mx + K2_CTL_CHUNK < W && lane == 0) {
+                    const unsigned cb = (unsigned)min(W - mx - K2_CTL_CHUNK, K2_CTL_CHUNK) * 16u;
+                    mvg_mbar_expect_tx(&s.mbar[K2_RING + (cbuf ^ 1u)], cb);
+                    mvg_bulk_load(s.ctl[cbuf ^ 1u], ctl + mx + K2_CTL_CHUNK, cb, &s.mbar[K2_RING + (cbuf ^ 1u)]);
+                }
             }
-            /* the residual of macroblock mx+1 flies while mx is predicted; its buffer was last read
-             * before the __syncwarp() that closed macroblock mx-1 */
-            if (mx + 1 < W && lane == 0) {
-                mvg_mbar_expect_tx(&s.mbar[cur_buf ^ 1u], 768u);
-                mvg_bulk_load(s.resid[cur_buf ^ 1u], resid + (size_t)(mx + 1) * 384, 768u, &s.mbar[cur_buf ^ 1u]);
+            /* residual of macroblock mx + K2_RING - 1: its ring slot was last read before the __syncwarp()
+             * that closed macroblock mx - 1 */
+            if (mx + K2_RING - 1 < W && lane == 0) {
+                const unsigned b = (rb + K2_RING - 1) & (K2_RING - 1);
+                mvg_mbar_expect_tx(&s.mbar[b], 768u);
+                mvg_bulk_load(s.resid[b], resid + (size_t)(mx + K2_RING - 1) * 384, 768u, &s.mbar[b]);
             }
-            const uint4 ctlw = *reinterpret_cast<const uint4 *>(&s.ctl[mx & (K2_CTL_CHUNK - 1)]);
+            const uint4 ctlw = *reinterpret_cast<const uint4 *>(&s.ctl[cbuf][mx & (K2_CTL_CHUNK - 1)]);
             const bool availA = mx > 0, availC = availB && mx < W - 1, availD = availA && availB;
 
             if (availB) {
-                if (availC) {       /* the up-right macroblock must have been published */
-                    unsigned ns = 400;
-                    while (!__all_sync(MVG_FULL, lane >= 8 || nxt.y == epoch)) {
-                        __nanosleep(ns);
-                        if (ns < 3200) ns *= 2;
-                        if (lane < 8) nxt = mvg_ld_relaxed_u64(habove + (size_t)(mx + 1) * 8);
-                    }
+                if (j == 0 && mx) {             /* next group of four macroblocks above */
+                    qa = qb;
+                    qb = make_uint2(0, epoch);
+                    if (mx * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(habove + (size_t)mx * 8 + 32);
                 }
-                /* sample row -1 of the tiles: x = 0..15 from cur, x = 16..23 from nxt */
-                if (lane < 8) *reinterpret_cast<unsigned *>(halo_top) = cur.x;
-                if (lane < 2) *reinterpret_cast<unsigned *>(halo_top + 16) = nxt.x;
-                cur = nxt;
-                if (mx + 2 < W && lane < 8) nxt = mvg_ld_relaxed_u64(habove + (size_t)(mx + 2) * 8);
+                /* words needed now: the 8 of the macroblock above and, for the up-right neighbour, the
+                 * first two of the next one (in qb when this is the last macroblock of the group) */
+                const unsigned needA = (0xFFu << (8 * j)) | ((availC && j < 3) ? 0x300u << (8 * j) : 0u);
+                const unsigned needB = (availC && j == 3) ? 0x3u : 0u;
+                unsigned okA = __ballot_sync(MVG_FULL, qa.y == epoch);
+                unsigned okB = needB ? __ballot_sync(MVG_FULL, qb.y == epoch) : 0u;
+                if ((okA & needA) != needA || (okB & needB) != needB) {
+                    /* this row has caught up with the row above: poll, sleeping about a macroblock time */
+                    unsigned ns = 200;
+                    const size_t g0 = (size_t)(mx & ~3) * 8;
+                    do {
+                        __nanosleep(ns);
+                        if (ns < 1600) ns *= 2;
+                        if ((mx & ~3) * 8 + lane < hwords) qa = mvg_ld_relaxed_u64(habove + g0);
+                        if ((mx & ~3) * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(habove + g0 + 32);
+                        okA = __ballot_sync(MVG_FULL, qa.y == epoch);
+                        okB = __ballot_sync(MVG_FULL, qb.y == epoch);
+                    } while ((okA & needA) != needA || (okB & needB) != needB);
+                }
+                /* sample row -1 of the tiles: lanes 0..7 the macroblock above, lanes 8,9 x = 16..23 */
+                const unsigned src = (j == 3 && lane < 2) ? qb.x : qa.x;
+                const unsigned v = __shfl_sync(MVG_FULL, src, (8 * j + lane) & 31);
+                if (lane < 10) *reinterpret_cast<unsigned *>(halo_top) = v;
             }
-            c.resid = reinterpret_cast<const uint8_t *>(s.resid[cur_buf]);
-            mvg_mbar_wait(&s.mbar[cur_buf], (parity >> cur_buf) & 1u);
-            parity ^= 1u << cur_buf;
+            c.resid = reinterpret_cast<const uint8_t *>(s.resid[rb]);
+            mvg_mbar_wait(&s.mbar[rb], (parity >> rb) & 1u);
+            parity ^= 1u << rb;
             __syncwarp();
 
             const int kind = ctlw.x & 255, i16 = (ctlw.x >> 8) & 255, cmode = (ctlw.x >> 16) & 255;
@@ -914,10 +953,9 @@ k2_wavefront(K2Params p)
             /* next macroblock: x = 15 becomes x = -1 (luma rows -1..15, chroma x = 7, rows -1..7) */
             lc_src[-lc_back] = lc_src[0];
             if (lane < 3) lc_src2[-8] = lc_src2[0];
-            cur_buf ^= 1u;
+            rb = (rb + 1) & (K2_RING - 1);
             __syncwarp();
         }
-        nload = cur_buf;            /* the buffer after the last one used */
     }
 }
 
