@@ -48,6 +48,7 @@ struct mvg_ctx {
     /* intermediates / outputs */
     int16_t *d_resid = nullptr;
     MvgMbCtl *d_ctl = nullptr;
+    uint8_t *d_tiles = nullptr;      /* [slot][n_mb][384] reconstructed macroblocks (kernel 2 -> kernel 3 / 4) */
     uint8_t *d_yuv = nullptr, *d_rgb = nullptr;
     uint2 *d_halo = nullptr;         /* [slot][n_mb][8] flag-in-data bottom lines (kernel 2) */
     int *d_work = nullptr;
@@ -192,29 +193,31 @@ static Taps nxn_taps(int n, int mode, int x, int y)
 extern "C" void mvg_build_luts(MvgLuts *out)
 {
     memset(out, 0, sizeof *out);
-    for (int half = 0; half < 2; half++)
-        for (int row = 0; row < 16; row++) {
-            const int mode = row == 11 ? 3 : row == 15 ? 7 : row;
-            if (mode > 8 || mode == 2) continue;
-            const bool tr = row < 9;
-            for (int y = 0; y < 4; y++)
-                for (int x = 0; x < 4; x++) {
-                    const Taps t = nxn_taps(4, mode, x, y);
-                    for (int k = 0; k < 4; k++) {
-                        int off;
-                        if (t.r[k].left) off = t.r[k].i * MVG_LT_STRIDE - 1;
-                        else {
-                            int i = t.r[k].i;
-                            if (!tr && i > 3) i = 3;         /* h264_intra_prediction.c:431-439 */
-                            off = -MVG_LT_STRIDE + i;
-                        }
-                        out->lut4[half][row][y * 4 + x][k] = off + (half ? 8 - 4 * MVG_LT_STRIDE : 0) + MVG_LUT4_BIAS;
+    for (int row = 0; row < 16; row++) {
+        const int mode = row == 11 ? 3 : row == 15 ? 7 : row;
+        if (mode > 8 || mode == 2) continue;
+        const bool tr = row < 9;
+        for (int y = 0; y < 4; y++)
+            for (int x = 0; x < 4; x++) {
+                const Taps t = nxn_taps(4, mode, x, y);
+                uint32_t word = 0;
+                for (int k = 0; k < 4; k++) {
+                    int off;
+                    if (t.r[k].left) off = t.r[k].i * MVG_LT_STRIDE - 1;
+                    else {
+                        int i = t.r[k].i;
+                        if (!tr && i > 3) i = 3;             /* h264_intra_prediction.c:431-439 */
+                        off = -MVG_LT_STRIDE + i;
                     }
+                    word |= (uint32_t)(off + MVG_LUT4_BIAS) << (8 * k);
                 }
-        }
+                out->lut4[row][y * 4 + x] = out->lut4[row][16 + y * 4 + x] = word;
+            }
+    }
     auto line8 = [](Ref r) { return r.left ? MVG_N8_LEFT(r.i) : MVG_N8_TOP(r.i); };
     for (int mode = 0; mode < 9; mode++)
-        for (int lane = 0; lane < 32; lane++)
+        for (int lane = 0; lane < 32; lane++) {
+            uint32_t word = 0;
             for (int s = 0; s < 2; s++) {
                 const int x = 2 * (lane & 3) + s, y = lane >> 2;
                 int idx = MVG_N8_DC, variant = 0;
@@ -226,10 +229,10 @@ extern "C" void mvg_build_luts(MvgLuts *out)
                         idx = a < b ? a : b; variant = 1;
                     } else { idx = line8(t.r[1]); variant = 2; }  /* centre (or the line end of an end tap) */
                 }
-                out->lut8[mode][lane][2 * s] = (uint32_t)idx * 4;
-                out->lut8[mode][lane][2 * s + 1] = s == 0 ? 0x4440u | (uint32_t)variant
-                                                          : 0x5054u | ((uint32_t)variant << 8);
+                word |= ((uint32_t)idx * 4 | (uint32_t)variant * 8 << 8) << (16 * s);
             }
+            out->lut8[mode][lane] = word;
+        }
 }
 
 /* ------------------------------------------------------------------------- */
@@ -291,6 +294,7 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     TRY("alloc coeff", dalloc(&ctx->d_coeff, n * 384));
     TRY("alloc residual", dalloc(&ctx->d_resid, n * 384));
     TRY("alloc ctl", dalloc(&ctx->d_ctl, n));
+    TRY("alloc tiles", dalloc(&ctx->d_tiles, n * 384));
     TRY("alloc yuv", dalloc(&ctx->d_yuv, n * 384));
     TRY("alloc rgb", dalloc(&ctx->d_rgb, n * 768));
     TRY("alloc halo", dalloc(&ctx->d_halo, n * 8));
@@ -313,7 +317,7 @@ extern "C" int mvg_destroy(mvg_ctx *ctx)
     cudaDeviceSynchronize();
     cudaFree(ctx->d_kind); cudaFree(ctx->d_i16); cudaFree(ctx->d_cm); cudaFree(ctx->d_qp); cudaFree(ctx->d_cbp);
     cudaFree(ctx->d_modes); cudaFree(ctx->d_coeff); cudaFree(ctx->d_resid); cudaFree(ctx->d_ctl);
-    cudaFree(ctx->d_yuv); cudaFree(ctx->d_rgb); cudaFree(ctx->d_halo); cudaFree(ctx->d_work);
+    cudaFree(ctx->d_tiles); cudaFree(ctx->d_yuv); cudaFree(ctx->d_rgb); cudaFree(ctx->d_halo); cudaFree(ctx->d_work);
     cudaFree(ctx->d_tab); cudaFree(ctx->d_luts);
     for (auto ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : ctx->ev_mark) if (ev) cudaEventDestroy(ev);
@@ -443,6 +447,19 @@ extern "C" int mvg_clone_slot(mvg_ctx *ctx, int src_slot, int dst_slot)
 /* ------------------------------------------------------------------------- */
 /* launches                                                                    */
 
+/* planar I420 of slots [first_slot, first_slot + n_pics) from the macroblock tiles (kernel 4) */
+static int launch_planar(mvg_ctx *ctx, int first_slot, int n_pics, cudaStream_t st)
+{
+    K3Params p;
+    p.tiles = ctx->d_tiles; p.yuv = ctx->d_yuv; p.rgb = nullptr; p.width = 16 * ctx->w_mbs; p.height = 16 * ctx->h_mbs;
+    p.scale = 1; p.first_slot = first_slot; p.n_pics = n_pics;
+    const long long threads = (long long)ctx->n_mb() * 12 * n_pics;
+    const int grid = (int)std::min<long long>((threads + 255) / 256, (long long)ctx->sm_count * 32);
+    k4_yuv_planar<<<grid, 256, 0, st>>>(p);
+    CK(ctx, cudaGetLastError());
+    return MVG_SUCCESS;
+}
+
 static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale, cudaStream_t st, bool timed)
 {
     const int W = ctx->w_mbs, H = ctx->h_mbs;
@@ -473,7 +490,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
     if (timed) CK(ctx, cudaEventRecord(ctx->ev[1], st));
     {
         K2Params p;
-        p.resid = ctx->d_resid; p.ctl = ctx->d_ctl; p.yuv = ctx->d_yuv; p.halo = ctx->d_halo;
+        p.resid = ctx->d_resid; p.ctl = ctx->d_ctl; p.tiles = ctx->d_tiles; p.halo = ctx->d_halo;
         if (++ctx->epoch == 0) ctx->epoch = 1;      /* 0 is the value of never-written words */
         p.epoch = ctx->epoch; p.group = MVG_K2_GROUP; p.stagger = ctx->k2_stagger;
         p.work = work; p.luts = ctx->d_luts; p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics;
@@ -485,7 +502,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
     if (timed) CK(ctx, cudaEventRecord(ctx->ev[2], st));
     if (rgb_scale >= 1) {
         K3Params p;
-        p.yuv = ctx->d_yuv; p.rgb = ctx->d_rgb; p.width = width; p.height = height; p.scale = rgb_scale;
+        p.tiles = ctx->d_tiles; p.yuv = ctx->d_yuv; p.rgb = ctx->d_rgb; p.width = width; p.height = height; p.scale = rgb_scale;
         p.first_slot = first_slot; p.n_pics = n_pics;
         const long long threads = rgb_scale == 1 ? (long long)(width / 16) * (height / 2) * n_pics
                                                  : (long long)(width / rgb_scale) * (height / rgb_scale) * n_pics;
@@ -566,6 +583,7 @@ extern "C" int mvg_download_yuv420(mvg_ctx *ctx, int slot, uint8_t *y, uint8_t *
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t n = ctx->n_mb();
     const uint8_t *src = ctx->d_yuv + (size_t)slot * n * 384;
+    if (launch_planar(ctx, slot, 1, ctx->stream) != MVG_SUCCESS) return MVG_FAILURE;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     if (y) CK(ctx, cudaMemcpy(y, src, n * 256, cudaMemcpyDeviceToHost));
     if (cb) CK(ctx, cudaMemcpy(cb, src + n * 256, n * 64, cudaMemcpyDeviceToHost));
@@ -649,6 +667,7 @@ extern "C" int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *b, uint8_t *yuv_ou
         CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[r], 0));
         if (idx >= depth) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[r], 0));
         if (launch_stages(ctx, slot0, cnt, scale, ctx->stream, false) != MVG_SUCCESS) return MVG_FAILURE;
+        if (yuv_out && launch_planar(ctx, slot0, cnt, ctx->stream) != MVG_SUCCESS) return MVG_FAILURE;
         CK(ctx, cudaEventRecord(ctx->ev_comp[r], ctx->stream));
         CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[r], 0));
         if (yuv_out)

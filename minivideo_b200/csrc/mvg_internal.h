@@ -11,11 +11,11 @@
  * luma tile  : rows y = -1..15, row stride 48 B, sample x at byte (x + 16):
  *              x = -1 -> 15, x = 0..15 -> 16..31 (16-byte aligned rows for the write-out),
  *              x = 16..23 (macroblock C, top row only) -> 32..39
- * chroma tile: rows y = -1..7, row stride 32 B, sample x at byte (x + 16)       */
+ * chroma tile: rows y = -1..7, row stride 48 B (as luma: conflict-free row reads), sample x at byte (x + 16) */
 #define MVG_LT_STRIDE 48
 #define MVG_LT_XOFF   16
 #define MVG_LT_ROWS   17
-#define MVG_CT_STRIDE 32
+#define MVG_CT_STRIDE 48
 #define MVG_CT_XOFF   16
 #define MVG_CT_ROWS   9
 
@@ -42,26 +42,26 @@ struct MvgMbCtl { uint32_t w0, w1, w2, w3; };
  *   2-tap (p + q + 1) >> 1       -> {p,p,q,q}
  *   copy  p                      -> {p,p,p,p}
  *   end   (p + 3q + 2) >> 2      -> {p,q,q,q}
- * lut4[half][mode][y*4+x][k]: byte offset of tap k in the luma tile, relative to (origin of the block the
- *   lanes 0..15 predict in the same step) - MVG_LUT4_BIAS; half 1 is the block 8 samples to the right and
- *   4 rows up (kernel 2's anti-diagonal schedule), so one immediate per step serves both halves.
- *   Rows 0..8 are the nine modes with p[4..7,-1] available, rows 11 and 15 are modes 3 and 7 when they are
- *   not (taps stop at p[3,-1], h264_intra_prediction.c:431-439).  Row 2 (DC) is unused.
+ * lut4[mode][16*half + y*4+x]: the four taps as byte offsets into the luma tile (one byte each), relative
+ *   to (origin of the lane's block) - MVG_LUT4_BIAS; the two halves hold the same values (a lane reads
+ *   word `lane`: no bank conflicts).  Rows 0..8 are the nine modes with p[4..7,-1] available, rows 11 and
+ *   15 are modes 3 and 7 when they are not (taps stop at p[3,-1], h264_intra_prediction.c:431-439).
+ *   Row 2 (DC) is unused.
  * lut8[mode][lane]: the Intra8x8 predictors read a filtered neighbour line of 32-bit words
  *   {p', f2 = (p'[n]+p'[n+1]+1)>>1, f3 = (p'[n-1]+2p'[n]+p'[n+1]+2)>>2} (n = 0..7 p'[-1,7..0], 8 p'[-1,-1],
  *   9..24 p'[0..15,-1], MVG_N8_DC the DC value).  A lane predicts samples (2*(lane&3) + {0,1}, lane>>2):
- *   {byte offset of the word of sample 0, byte-permute selector that moves its byte into bits 0..7,
- *    byte offset for sample 1, selector that merges its byte into bits 16..23}.  The 3- and 2-tap forms
- *   of the spec always involve adjacent line entries, and the two "end" taps (p+3q) are f3 at a line end. */
-#define MVG_LUT4_BIAS    240
+ *   byte 0 = byte offset of the word of sample 0, byte 1 = its bit shift (0, 8, 16), bytes 2, 3 the same
+ *   for sample 1.  The 3- and 2-tap forms of the spec always involve adjacent line entries, and the two
+ *   "end" taps (p+3q) are f3 at a line end. */
+#define MVG_LUT4_BIAS    (MVG_LT_STRIDE + 1)   /* p[-1,-1] is the lowest address */
 #define MVG_N8_LEFT(y)  (7 - (y))
 #define MVG_N8_CORNER   8
 #define MVG_N8_TOP(x)   (9 + (x))
 #define MVG_N8_DC       32
 
 struct MvgLuts {
-    int32_t  lut4[2][16][16][4];
-    uint32_t lut8[9][32][4];
+    uint32_t lut4[16][32];
+    uint32_t lut8[9][32];
 };
 
 #ifdef __cplusplus
