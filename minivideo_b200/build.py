@@ -73,7 +73,8 @@ def build_gpu(force: bool = False) -> Path:
     deps = cu + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [INC / "mvgpu.h"]
     if force or _stale(out, deps):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-        _run([nvcc, *NVCC_FLAGS, f"-I{INC}", f"-I{CSRC}", "-o", str(out), *map(str, cu)],
+        extra = ["-DMVG_K2_PROFILE"] if os.environ.get("MVG_K2_PROFILE") else []     # dev: in-kernel cycle accounting
+        _run([nvcc, *NVCC_FLAGS, *extra, f"-I{INC}", f"-I{CSRC}", "-o", str(out), *map(str, cu)],
              log=PKG / "libmvgpu.build.log")
     return out
 

@@ -52,6 +52,7 @@ struct mvg_ctx {
     uint8_t *d_yuv = nullptr, *d_rgb = nullptr;
     uint2 *d_halo = nullptr;         /* [slot][n_mb][8] flag-in-data bottom lines (kernel 2) */
     int *d_work = nullptr;
+    unsigned long long *d_stats = nullptr;   /* DEV: kernel-2 cycle accounting (builds with -DMVG_K2_PROFILE) */
     int work_next = 0;
     unsigned epoch = 0;              /* bumped per kernel-2 launch; halo words carry it       */
     int pipe_chunk = 0;              /* pictures per mvg_decode_host() chunk, 0 = automatic    */
@@ -273,6 +274,7 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     TRY("k2 shared memory", cudaFuncSetAttribute(k2_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM_BYTES));
     TRY("occupancy k2", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2_ctas_per_sm, k2_wavefront, K2_WARPS * 32, K2_SMEM_BYTES));
     if (const char *e = getenv("MVG_K2_STAGGER")) ctx->k2_stagger = atoi(e);
+    if (const char *e = getenv("MVG_K2_CTAS")) { const int v = atoi(e); if (v >= 1 && v < ctx->k2_ctas_per_sm) ctx->k2_ctas_per_sm = v; }   /* dev */
     if (ctx->k1_ctas_per_sm < 1 || ctx->k2_ctas_per_sm < 1) return bail("kernel does not fit on an SM", cudaErrorLaunchOutOfResources);
     TRY("stream", cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     TRY("stream", cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
@@ -300,6 +302,8 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     TRY("alloc halo", dalloc(&ctx->d_halo, n * 8));
     TRY("clear halo", cudaMemset(ctx->d_halo, 0, n * 8 * sizeof(uint2)));
     TRY("alloc work", dalloc(&ctx->d_work, MVG_WORK_RING));
+    TRY("alloc stats", dalloc(&ctx->d_stats, 16));
+    TRY("clear stats", cudaMemset(ctx->d_stats, 0, 16 * sizeof(unsigned long long)));
     TRY("alloc tables", dalloc(&ctx->d_tab, 1));
     TRY("alloc luts", dalloc(&ctx->d_luts, 1));
     MvgLuts luts;
@@ -317,7 +321,7 @@ extern "C" int mvg_destroy(mvg_ctx *ctx)
     cudaDeviceSynchronize();
     cudaFree(ctx->d_kind); cudaFree(ctx->d_i16); cudaFree(ctx->d_cm); cudaFree(ctx->d_qp); cudaFree(ctx->d_cbp);
     cudaFree(ctx->d_modes); cudaFree(ctx->d_coeff); cudaFree(ctx->d_resid); cudaFree(ctx->d_ctl);
-    cudaFree(ctx->d_tiles); cudaFree(ctx->d_yuv); cudaFree(ctx->d_rgb); cudaFree(ctx->d_halo); cudaFree(ctx->d_work);
+    cudaFree(ctx->d_tiles); cudaFree(ctx->d_yuv); cudaFree(ctx->d_rgb); cudaFree(ctx->d_halo); cudaFree(ctx->d_work); cudaFree(ctx->d_stats);
     cudaFree(ctx->d_tab); cudaFree(ctx->d_luts);
     for (auto ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : ctx->ev_mark) if (ev) cudaEventDestroy(ev);
@@ -367,6 +371,17 @@ extern "C" int mvg_set_pipeline(mvg_ctx *ctx, int chunk_pics)
 {
     if (!ctx || chunk_pics < 0) return MVG_FAILURE;
     ctx->pipe_chunk = chunk_pics;
+    return MVG_SUCCESS;
+}
+
+/* DEV: read and clear the kernel-2 cycle counters (all zero unless built with -DMVG_K2_PROFILE) */
+extern "C" int mvg_dev_k2_stats(mvg_ctx *ctx, unsigned long long out[16])
+{
+    if (!ctx || !out) return MVG_FAILURE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaMemcpy(out, ctx->d_stats, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(ctx, cudaMemset(ctx->d_stats, 0, 16 * sizeof(unsigned long long)));
     return MVG_SUCCESS;
 }
 
@@ -492,7 +507,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         K2Params p;
         p.resid = ctx->d_resid; p.ctl = ctx->d_ctl; p.tiles = ctx->d_tiles; p.halo = ctx->d_halo;
         if (++ctx->epoch == 0) ctx->epoch = 1;      /* 0 is the value of never-written words */
-        p.epoch = ctx->epoch; p.group = MVG_K2_GROUP; p.stagger = ctx->k2_stagger;
+        p.epoch = ctx->epoch; p.group = MVG_K2_GROUP; p.stagger = ctx->k2_stagger; p.stats = ctx->d_stats;
         p.work = work; p.luts = ctx->d_luts; p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics;
         const long long items = (long long)n_pics * H;
         const int grid = (int)std::min<long long>((items + K2_WARPS - 1) / K2_WARPS, (long long)ctx->sm_count * ctx->k2_ctas_per_sm);

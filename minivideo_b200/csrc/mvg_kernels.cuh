@@ -439,8 +439,14 @@ struct K2Params {
     unsigned        epoch;      /* flag value that marks halo words of THIS launch */
     int w_mbs, h_mbs, first_slot, n_pics, group;
     int stagger;                /* a row starts once the row above has published this many macroblocks */
+    unsigned long long *stats;  /* DEV (-DMVG_K2_PROFILE): cycle accounting, 16 counters */
 };
 
+#ifdef MVG_K2_PROFILE
+#define K2_PROF(...) __VA_ARGS__
+#else
+#define K2_PROF(...)
+#endif
 #define K2_WARPS     16         /* warps per CTA; two CTAs per SM                              */
 #define K2_CTL_CHUNK 32         /* control records per bulk copy (two buffers)                 */
 #define K2_RING      4          /* residual ring slots (power of two)                          */
@@ -814,10 +820,12 @@ k2_wavefront(K2Params p)
     const uint8_t *const wo_src = lane < 16 ? s.lt + K2_TO(0, lane)
                                             : s.ct[(lane >> 3) & 1] + K2_CO(0, lane & 7);
 
+    K2_PROF(long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt0 = clock64();)
     unsigned parity = 0;            /* bit b: phase parity of mbar[b] (0..K2_RING-1 residual ring, then 2 control buffers) */
     unsigned rb = 0;                /* ring slot of the current macroblock's residual */
 
     for (;;) {
+        K2_PROF(const long long tr0 = clock64();)
         int item = 0;
         if (lane == 0) item = atomicAdd(p.work, 1);
         item = __shfl_sync(MVG_FULL, item, 0);
@@ -869,7 +877,9 @@ k2_wavefront(K2Params p)
         mvg_mbar_wait(&s.mbar[K2_RING], (parity >> K2_RING) & 1u);
         parity ^= 1u << K2_RING;
 
+        K2_PROF(pc[0] += clock64() - tr0;)
         for (int mx = 0; mx < W; mx++) {
+            K2_PROF(const long long t0 = clock64();)
             const int j = mx & 3;
             const unsigned cbuf = (unsigned)(mx / K2_CTL_CHUNK) & 1u;
             if ((mx & (K2_CTL_CHUNK - 1)) == 0) {
@@ -905,11 +915,14 @@ k2_wavefront(K2Params p)
                 const unsigned needA = (0xFFu << (8 * j)) | ((availC && j < 3) ? 0x300u << (8 * j) : 0u);
                 bool ok = (okA & needA) == needA;
                 if (availC && j == 3) ok = ok && (__ballot_sync(MVG_FULL, qb.y == epoch) & 3u) == 3u;
+                K2_PROF(const long long th = clock64();)
                 if (!ok) {
+                    K2_PROF(pc[5]++;)
                     /* this row has caught up with the row above: poll, sleeping a fraction of a macroblock time */
                     unsigned ns = 100;
                     const size_t g0 = (size_t)(mx & ~3) * 8;
                     do {
+                        K2_PROF(pc[6]++;)
                         __nanosleep(ns);
                         if (ns < 800) ns *= 2;
                         if ((mx & ~3) * 8 + lane < hwords) qa = mvg_ld_relaxed_u64(habove + g0);
@@ -921,6 +934,7 @@ k2_wavefront(K2Params p)
                         }
                     } while (!ok);
                 }
+                K2_PROF(pc[7] += clock64() - th;)
                 /* sample row -1 of the tiles: lanes 0..7 the macroblock above, lanes 8,9 x = 16..23 */
                 const unsigned src = (j == 3 && lane < 2) ? qb.x : qa.x;
                 const unsigned v = __shfl_sync(MVG_FULL, src, (8 * j + lane) & 31);
@@ -931,16 +945,20 @@ k2_wavefront(K2Params p)
                 }
             }
             c.resid = reinterpret_cast<const uint8_t *>(s.resid[rb]);
+            K2_PROF(const long long t1 = clock64();)
             mvg_mbar_wait(&s.mbar[rb], (parity >> rb) & 1u);
             parity ^= 1u << rb;
             __syncwarp();
+            K2_PROF(const long long t2 = clock64();)
 
             const int kind = ctlw.x & 255, i16 = (ctlw.x >> 8) & 255, cmode = (ctlw.x >> 16) & 255;
             if (kind == MVG_MB_I16x16)    k2_luma16(c, i16, availA, availB);
             else if (kind == MVG_MB_I4x4) k2_luma4(c, ctlw.y, ctlw.z, availA, availB, availC);
             else                          k2_luma8(c, ctlw.y, availA, availB, availC, availD);
+            K2_PROF(const long long t2b = clock64();)
             k2_chroma(c, cmode, availA, availB);
             __syncwarp();
+            K2_PROF(const long long t3 = clock64();)
 
             /* write the macroblock out as one 384-byte tile (coalesced; scattering 16-byte row pieces over a
              * planar picture costs more than the whole prediction: measured 4.5 ms vs 1.8 ms per 1000 pictures) */
@@ -958,8 +976,11 @@ k2_wavefront(K2Params p)
             if (lane < 3) lc_src2[-8] = lc_src2[0];
             rb = (rb + 1) & (K2_RING - 1);
             __syncwarp();
+            K2_PROF(const long long t4 = clock64(); pc[1] += t1 - t0; pc[2] += t2 - t1; pc[3] += t3 - t2; pc[4] += t4 - t3;
+                    if (kind == MVG_MB_I4x4) pc[0] += 0;)
         }
     }
+    K2_PROF(if (lane == 0 && p.stats) { for (int i = 0; i < 8; i++) atomicAdd(p.stats + i, (unsigned long long)pc[i]); atomicAdd(p.stats + 8, (unsigned long long)(clock64() - pt0)); })
 }
 
 /* ========================================================================= */
