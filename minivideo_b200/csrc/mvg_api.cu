@@ -519,7 +519,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         K3Params p;
         p.tiles = ctx->d_tiles; p.yuv = ctx->d_yuv; p.rgb = ctx->d_rgb; p.width = width; p.height = height; p.scale = rgb_scale;
         p.first_slot = first_slot; p.n_pics = n_pics;
-        const long long threads = rgb_scale == 1 ? (long long)(width / 16) * (height / 2) * n_pics
+        const long long threads = rgb_scale == 1 ? (long long)n * 8 * n_pics       /* 8 lanes per macroblock */
                                                  : (long long)(width / rgb_scale) * (height / rgb_scale) * n_pics;
         const int grid = (int)std::min<long long>((threads + 255) / 256, (long long)ctx->sm_count * 32);
         if (rgb_scale == 1) k3_rgb_full<<<grid, 256, 0, st>>>(p);
