@@ -180,6 +180,53 @@ int mvg_download_residual(mvg_ctx *ctx, int slot, int16_t *residual);
 int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *host_batch,
                     uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale);
 
+/* -- packed transfer format ---------------------------------------------------
+ * A parsed intra picture is mostly zero levels (a CAVLC block carries a handful of
+ * them), and the end-to-end path is bound by PCIe, so the levels can cross the bus
+ * packed.  The 384 levels of a macroblock are 24 chunks of 16 (chunk b =
+ * coeff[16 b .. 16 b + 15] of mvg_batch, i.e. one residual_block_cavlc() call,
+ * h264_cavlc.c:79, or a quarter of an 8x8 block):
+ *   nz_blocks[mb]  bit b set <=> chunk b holds a non-zero level
+ *   words          per macroblock: one uint16 mask per SET bit of nz_blocks in
+ *                  ascending b (bit k set <=> level k of the chunk is non-zero),
+ *                  followed by the non-zero levels (int16) of those chunks in the
+ *                  same order, ascending k
+ *   word_off[mb]   index (in uint16 units) of the macroblock's first word, counted
+ *                  from the first word of its picture
+ *   pic_off[i]     index of picture i's first word in `words`; pic_off[n_pics] =
+ *                  total number of words
+ * The other arrays are those of mvg_batch (cbp is not needed: nz_blocks says more).
+ * A front end can emit this directly (mvf_parse_pictures_packed); mvg_pack_batch()
+ * converts a dense batch.  On the device the levels are expanded to the dense
+ * layout before kernel 1, so results are identical by construction. */
+typedef struct mvg_packed_batch {
+    int32_t         n_pics;
+    const uint8_t  *mb_kind;      /* [P*N]    */
+    const uint8_t  *i16_mode;     /* [P*N]    */
+    const uint8_t  *chroma_mode;  /* [P*N]    */
+    const int8_t   *qp_y;         /* [P*N]    */
+    const uint8_t  *luma_modes;   /* [P*N*16] */
+    const uint32_t *nz_blocks;    /* [P*N]    */
+    const uint32_t *word_off;     /* [P*N]    */
+    const uint64_t *pic_off;      /* [P+1]    */
+    const uint16_t *words;        /* [pic_off[P]] */
+} mvg_packed_batch;
+
+/* Upper bound of the words one macroblock can need (24 masks + 384 levels). */
+#define MVG_PACKED_WORDS_PER_MB 408
+
+/* Pack `n_pics` pictures of `n_mbs` macroblocks each from dense levels (host code,
+ * `n_threads` host threads; <= 0: one per core).  The caller provides nz_blocks[P*N],
+ * word_off[P*N], pic_off[P+1] and words[words_capacity]; FAILURE when the capacity
+ * is too small (P*N*MVG_PACKED_WORDS_PER_MB always suffices). */
+int mvg_pack_batch(const int16_t *coeff, int n_pics, int n_mbs,
+                   uint32_t *nz_blocks, uint32_t *word_off, uint64_t *pic_off,
+                   uint16_t *words, size_t words_capacity, int n_threads);
+
+/* mvg_decode_host() for a packed batch: same pipeline, same outputs. */
+int mvg_decode_host_packed(mvg_ctx *ctx, const mvg_packed_batch *host_batch,
+                           uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale);
+
 /* Pictures per pipeline chunk of mvg_decode_host() (0 = automatic: an eighth of the batch, at
  * most a third of the context).  Larger chunks fill the GPU better, smaller ones overlap the
  * PCIe copies of neighbouring chunks better. */

@@ -19,12 +19,23 @@ EXPORTS = (
     "mvg_create", "mvg_destroy", "mvg_last_error", "mvg_set_sps", "mvg_build_level_scale",
     "mvg_upload", "mvg_clone_slot", "mvg_run", "mvg_sync", "mvg_get_timing", "mvg_mark", "mvg_mark_elapsed",
     "mvg_download_yuv420", "mvg_download_rgb", "mvg_download_residual", "mvg_decode_host",
+    "mvg_pack_batch", "mvg_decode_host_packed",
     "mvg_set_pipeline", "mvg_host_alloc", "mvg_host_free", "mvg_width", "mvg_height", "mvg_max_pics", "mvg_sm_count",
 )
 
 
 class MvgError(RuntimeError):
     pass
+
+
+class PackedBatch(C.Structure):
+    """mvg_packed_batch of include/mvgpu.h."""
+    _fields_ = [("n_pics", C.c_int32), ("mb_kind", C.c_void_p), ("i16_mode", C.c_void_p),
+                ("chroma_mode", C.c_void_p), ("qp_y", C.c_void_p), ("luma_modes", C.c_void_p),
+                ("nz_blocks", C.c_void_p), ("word_off", C.c_void_p), ("pic_off", C.c_void_p), ("words", C.c_void_p)]
+
+
+WORDS_PER_MB = 408      # MVG_PACKED_WORDS_PER_MB
 
 
 class Batch(C.Structure):
@@ -68,6 +79,8 @@ def load_library() -> C.CDLL:
     lib.mvg_download_rgb.argtypes = [vp, i32, vp]
     lib.mvg_download_residual.argtypes = [vp, i32, vp]
     lib.mvg_decode_host.argtypes = [vp, C.POINTER(Batch), vp, vp, i32]
+    lib.mvg_pack_batch.argtypes = [vp, i32, i32, vp, vp, vp, vp, C.c_size_t, i32]
+    lib.mvg_decode_host_packed.argtypes = [vp, C.POINTER(PackedBatch), vp, vp, i32]
     lib.mvg_set_pipeline.argtypes = [vp, i32]
     lib.mvg_host_alloc.argtypes = [C.c_size_t]
     lib.mvg_host_alloc.restype = vp
@@ -239,6 +252,79 @@ class Context:
         self._ck(self.lib.mvg_decode_host(self.handle, C.byref(b),
                                           yuv_out.ctypes.data if yuv_out is not None else None,
                                           rgb_out.ctypes.data if rgb_out is not None else None, rgb_scale))
+
+    def decode_host_packed(self, packed: "Packed", yuv_out: np.ndarray | None, rgb_out: np.ndarray | None, rgb_scale=1):
+        self._ck(self.lib.mvg_decode_host_packed(self.handle, C.byref(packed.struct),
+                                                 yuv_out.ctypes.data if yuv_out is not None else None,
+                                                 rgb_out.ctypes.data if rgb_out is not None else None, rgb_scale))
+
+
+class Packed:
+    """A batch in the packed transfer format (mvg_packed_batch), built from dense levels with mvg_pack_batch().
+    With pinned=True every array lives in cudaHostAlloc'ed memory (full PCIe speed)."""
+
+    def __init__(self, soa, n_pics=None, pinned=False, n_threads=0):
+        lib = load_library()
+        P = soa.n_pics if n_pics is None else n_pics
+        N = soa.n_mbs
+        reps = -(-P // soa.n_pics)
+        self._keep = []
+
+        def arr(shape, dt):
+            if pinned:
+                pa = PinnedArray(shape, dt)
+                self._keep.append(pa)
+                return pa.array
+            return np.empty(shape, dt)
+
+        def tiled(src):
+            out = arr((P * N,) + src.shape[1:], src.dtype)
+            out[...] = np.concatenate([src] * reps)[: P * N]
+            return out
+        self.n_pics, self.n_mbs = P, N
+        self.mb_kind, self.i16_mode, self.chroma_mode = tiled(soa.mb_kind), tiled(soa.i16_mode), tiled(soa.chroma_mode)
+        self.qp_y, self.luma_modes = tiled(soa.qp_y), tiled(soa.luma_modes)
+        coeff = np.ascontiguousarray(np.concatenate([soa.coeff] * reps)[: P * N])
+        self.nz_blocks, self.word_off = arr((P * N,), np.uint32), arr((P * N,), np.uint32)
+        self.pic_off = arr((P + 1,), np.uint64)
+        words = np.empty(P * N * WORDS_PER_MB, np.uint16)
+        rc = lib.mvg_pack_batch(coeff.ctypes.data, P, N, self.nz_blocks.ctypes.data, self.word_off.ctypes.data,
+                                self.pic_off.ctypes.data, words.ctypes.data, words.size, n_threads)
+        if rc != 1:
+            raise MvgError("mvg_pack_batch failed")
+        n_words = int(self.pic_off[P])
+        self.words = arr((max(n_words, 1),), np.uint16)
+        self.words[:n_words] = words[:n_words]
+        self.n_words = n_words
+        self.struct = PackedBatch(P, *(a.ctypes.data for a in (self.mb_kind, self.i16_mode, self.chroma_mode, self.qp_y,
+                                                               self.luma_modes, self.nz_blocks, self.word_off,
+                                                               self.pic_off, self.words)))
+
+    @property
+    def nbytes(self) -> int:
+        """Bytes that cross the bus for this batch."""
+        return (self.mb_kind.nbytes + self.i16_mode.nbytes + self.chroma_mode.nbytes + self.qp_y.nbytes +
+                self.luma_modes.nbytes + self.nz_blocks.nbytes + self.word_off.nbytes + 8 * self.n_pics + 2 * self.n_words)
+
+
+def unpack_levels(pk: "Packed") -> np.ndarray:
+    """Numpy restatement of the packed format (tests): packed -> dense levels [P*N, 384]."""
+    out = np.zeros((pk.n_pics * pk.n_mbs, 384), np.int16)
+    for p in range(pk.n_pics):
+        base = int(pk.pic_off[p])
+        for m in range(pk.n_mbs):
+            mb = p * pk.n_mbs + m
+            nzb = int(pk.nz_blocks[mb])
+            w = base + int(pk.word_off[mb])
+            blocks = [b for b in range(24) if (nzb >> b) & 1]
+            lv = w + len(blocks)
+            for i, b in enumerate(blocks):
+                mask = int(pk.words[w + i])
+                for k in range(16):
+                    if (mask >> k) & 1:
+                        out[mb, b * 16 + k] = pk.words[lv:lv + 1].view(np.int16)[0]
+                        lv += 1
+    return out
 
 
 def reconstruct(soa, device=0, rgb_scale=1, want_residual=False):

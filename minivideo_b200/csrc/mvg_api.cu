@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "mvg_internal.h"
 #include "mvg_kernels.cuh"
@@ -45,6 +47,11 @@ struct mvg_ctx {
     uint8_t *d_kind = nullptr, *d_i16 = nullptr, *d_cm = nullptr, *d_cbp = nullptr, *d_modes = nullptr;
     int8_t *d_qp = nullptr;
     int16_t *d_coeff = nullptr;
+    /* packed transfer format (allocated by the first mvg_decode_host_packed) */
+    uint32_t *d_nzb = nullptr, *d_woff = nullptr;
+    uint16_t *d_words = nullptr;
+    uint64_t *d_picbase = nullptr, *h_picbase = nullptr;
+    int h_picbase_cap = 0;
     /* intermediates / outputs */
     int16_t *d_resid = nullptr;
     MvgMbCtl *d_ctl = nullptr;
@@ -323,6 +330,8 @@ extern "C" int mvg_destroy(mvg_ctx *ctx)
     cudaFree(ctx->d_modes); cudaFree(ctx->d_coeff); cudaFree(ctx->d_resid); cudaFree(ctx->d_ctl);
     cudaFree(ctx->d_tiles); cudaFree(ctx->d_yuv); cudaFree(ctx->d_rgb); cudaFree(ctx->d_halo); cudaFree(ctx->d_work); cudaFree(ctx->d_stats);
     cudaFree(ctx->d_tab); cudaFree(ctx->d_luts);
+    cudaFree(ctx->d_nzb); cudaFree(ctx->d_woff); cudaFree(ctx->d_words); cudaFree(ctx->d_picbase);
+    if (ctx->h_picbase) cudaFreeHost(ctx->h_picbase);
     for (auto ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : ctx->ev_mark) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < MVG_PIPE_DEPTH; i++) {
@@ -650,15 +659,12 @@ extern "C" int mvg_download_residual(mvg_ctx *ctx, int slot, int16_t *residual)
 /* ------------------------------------------------------------------------- */
 /* end-to-end: host SoA in, host pictures out, pipelined over slot regions     */
 
-extern "C" int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *b, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale)
+/* chunk loop shared by the dense and the packed entry points: `upload(done, slot0, cnt)` enqueues the H2D
+ * copies of pictures [done, done+cnt) into slots [slot0, ..) on ctx->s_h2d, `expand(slot0, cnt)` enqueues
+ * whatever must run on ctx->stream before kernel 1 */
+template <typename Upload, typename Expand>
+static int decode_pipeline(mvg_ctx *ctx, int n_pics, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale, Upload upload, Expand expand)
 {
-    if (!ctx) return MVG_FAILURE;
-    if (check_batch(ctx, b, "mvg_decode_host") != MVG_SUCCESS) return MVG_FAILURE;
-    if (!ctx->have_sps) return fail(ctx, "mvg_decode_host: mvg_set_sps() has not been called");
-    if (b->n_pics < 1) return fail(ctx, "mvg_decode_host: empty batch");
-    if (rgb_out && rgb_scale < 1) return fail(ctx, "mvg_decode_host: rgb_out given but rgb_scale < 1");
-    CK(ctx, cudaSetDevice(ctx->device));
-
     const int scale = rgb_out ? rgb_scale : 0;
     const size_t n = ctx->n_mb();
     const size_t yuv_sz = n * 384, rgb_sz = scale ? rgb_bytes(ctx, scale) : 0;
@@ -668,19 +674,20 @@ extern "C" int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *b, uint8_t *yuv_ou
     int depth = MVG_PIPE_DEPTH;
     int chunk = std::max(1, ctx->max_pics / depth);
     if (ctx->max_pics < depth) { depth = 1; chunk = ctx->max_pics; }
-    chunk = std::min(chunk, std::max(1, (b->n_pics + 7) / 8));
+    chunk = std::min(chunk, std::max(1, (n_pics + 7) / 8));
     if (ctx->pipe_chunk > 0) chunk = std::min(ctx->pipe_chunk, std::max(1, ctx->max_pics / depth));
     int idx = 0;
-    for (int done = 0; done < b->n_pics; done += chunk, idx++) {
-        const int cnt = std::min(chunk, b->n_pics - done);
+    for (int done = 0; done < n_pics; done += chunk, idx++) {
+        const int cnt = std::min(chunk, n_pics - done);
         const int r = idx % depth, slot0 = r * chunk;
         /* inputs of region r were last read by the compute of chunk idx-depth */
         if (idx >= depth) CK(ctx, cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[r], 0));
-        if (upload_async(ctx, b, done, slot0, cnt, ctx->s_h2d) != MVG_SUCCESS) return MVG_FAILURE;
+        if (upload(done, slot0, cnt) != MVG_SUCCESS) return MVG_FAILURE;
         CK(ctx, cudaEventRecord(ctx->ev_h2d[r], ctx->s_h2d));
         /* outputs of region r were last read by the D2H of chunk idx-depth */
         CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[r], 0));
         if (idx >= depth) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[r], 0));
+        if (expand(slot0, cnt) != MVG_SUCCESS) return MVG_FAILURE;
         if (launch_stages(ctx, slot0, cnt, scale, ctx->stream, false) != MVG_SUCCESS) return MVG_FAILURE;
         if (yuv_out && launch_planar(ctx, slot0, cnt, ctx->stream) != MVG_SUCCESS) return MVG_FAILURE;
         CK(ctx, cudaEventRecord(ctx->ev_comp[r], ctx->stream));
@@ -697,3 +704,136 @@ extern "C" int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *b, uint8_t *yuv_ou
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return MVG_SUCCESS;
 }
+
+extern "C" int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *b, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale)
+{
+    if (!ctx) return MVG_FAILURE;
+    if (check_batch(ctx, b, "mvg_decode_host") != MVG_SUCCESS) return MVG_FAILURE;
+    if (!ctx->have_sps) return fail(ctx, "mvg_decode_host: mvg_set_sps() has not been called");
+    if (b->n_pics < 1) return fail(ctx, "mvg_decode_host: empty batch");
+    if (rgb_out && rgb_scale < 1) return fail(ctx, "mvg_decode_host: rgb_out given but rgb_scale < 1");
+    CK(ctx, cudaSetDevice(ctx->device));
+    return decode_pipeline(ctx, b->n_pics, yuv_out, rgb_out, rgb_scale,
+                           [&](int done, int slot0, int cnt) { return upload_async(ctx, b, done, slot0, cnt, ctx->s_h2d); },
+                           [&](int, int) { return (int)MVG_SUCCESS; });
+}
+
+/* ------------------------------------------------------------------------- */
+/* packed transfer format                                                      */
+
+extern "C" int mvg_pack_batch(const int16_t *coeff, int n_pics, int n_mbs, uint32_t *nz_blocks, uint32_t *word_off,
+                              uint64_t *pic_off, uint16_t *words, size_t words_capacity, int n_threads)
+{
+    if (!coeff || !nz_blocks || !word_off || !pic_off || !words || n_pics < 1 || n_mbs < 1) return MVG_FAILURE;
+    /* pass 1 (threaded over pictures): chunk bitmaps and per-macroblock sizes -> offsets inside the picture */
+    std::vector<uint64_t> pic_words((size_t)n_pics);
+    auto pass1 = [&](int p) {
+        uint64_t off = 0;
+        for (int m = 0; m < n_mbs; m++) {
+            const size_t mb = (size_t)p * n_mbs + m;
+            const int16_t *c = coeff + mb * 384;
+            uint32_t nzb = 0;
+            unsigned words_here = 0;
+            for (int b = 0; b < 24; b++) {
+                unsigned cnt = 0;
+                for (int k = 0; k < 16; k++) cnt += c[b * 16 + k] != 0;
+                if (cnt) { nzb |= 1u << b; words_here += 1 + cnt; }
+            }
+            nz_blocks[mb] = nzb;
+            word_off[mb] = (uint32_t)off;
+            off += words_here;
+        }
+        pic_words[(size_t)p] = off;
+    };
+    auto pass2 = [&](int p) {
+        for (int m = 0; m < n_mbs; m++) {
+            const size_t mb = (size_t)p * n_mbs + m;
+            const int16_t *c = coeff + mb * 384;
+            const uint32_t nzb = nz_blocks[mb];
+            uint16_t *w = words + pic_off[p] + word_off[mb];
+            uint16_t *lv = w + __builtin_popcount(nzb);
+            for (int b = 0; b < 24; b++) {
+                if (!((nzb >> b) & 1u)) continue;
+                unsigned mask = 0;
+                for (int k = 0; k < 16; k++)
+                    if (c[b * 16 + k]) { mask |= 1u << k; *lv++ = (uint16_t)c[b * 16 + k]; }
+                *w++ = (uint16_t)mask;
+            }
+        }
+    };
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, n_pics));
+    auto run = [&](auto &fn) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&, t] { for (int p = t; p < n_pics; p += nt) fn(p); });
+        for (auto &x : th) x.join();
+    };
+    run(pass1);
+    pic_off[0] = 0;
+    for (int p = 0; p < n_pics; p++) pic_off[p + 1] = pic_off[p] + pic_words[(size_t)p];
+    if (pic_off[n_pics] > words_capacity) return MVG_FAILURE;
+    run(pass2);
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_decode_host_packed(mvg_ctx *ctx, const mvg_packed_batch *b, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale)
+{
+    if (!ctx) return MVG_FAILURE;
+    if (!b) return fail(ctx, "mvg_decode_host_packed: batch is NULL");
+    if (!b->mb_kind || !b->i16_mode || !b->chroma_mode || !b->qp_y || !b->luma_modes || !b->nz_blocks || !b->word_off ||
+        !b->pic_off || !b->words)
+        return fail(ctx, "mvg_decode_host_packed: a required pointer is NULL");
+    if (!ctx->have_sps) return fail(ctx, "mvg_decode_host_packed: mvg_set_sps() has not been called");
+    if (b->n_pics < 1) return fail(ctx, "mvg_decode_host_packed: empty batch");
+    if (rgb_out && rgb_scale < 1) return fail(ctx, "mvg_decode_host_packed: rgb_out given but rgb_scale < 1");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t n = ctx->n_mb();
+    if (!ctx->d_words) {
+        const size_t cap = ctx->n_mb_max() * (size_t)ctx->max_pics;
+        CK(ctx, cudaMalloc((void **)&ctx->d_nzb, cap * sizeof(uint32_t)));
+        CK(ctx, cudaMalloc((void **)&ctx->d_woff, cap * sizeof(uint32_t)));
+        CK(ctx, cudaMalloc((void **)&ctx->d_words, cap * MVG_PACKED_WORDS_PER_MB * sizeof(uint16_t)));
+        CK(ctx, cudaMalloc((void **)&ctx->d_picbase, (size_t)ctx->max_pics * sizeof(uint64_t)));
+    }
+    if (b->n_pics > ctx->h_picbase_cap) {
+        if (ctx->h_picbase) cudaFreeHost(ctx->h_picbase);
+        ctx->h_picbase = nullptr; ctx->h_picbase_cap = 0;
+        CK(ctx, cudaHostAlloc((void **)&ctx->h_picbase, (size_t)b->n_pics * sizeof(uint64_t), cudaHostAllocDefault));
+        ctx->h_picbase_cap = b->n_pics;
+    }
+    for (int p = 0; p < b->n_pics; p++)
+        if (b->pic_off[p + 1] < b->pic_off[p] || b->pic_off[p + 1] - b->pic_off[p] > (uint64_t)n * MVG_PACKED_WORDS_PER_MB)
+            return fail(ctx, "mvg_decode_host_packed: picture %d has an impossible word count", p);
+    auto upload = [&](int done, int slot0, int cnt) -> int {
+        const size_t o = (size_t)slot0 * n, s = (size_t)done * n, c = (size_t)cnt * n;
+        cudaStream_t st = ctx->s_h2d;
+        CK(ctx, cudaMemcpyAsync(ctx->d_kind + o, b->mb_kind + s, c, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(ctx->d_i16 + o, b->i16_mode + s, c, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(ctx->d_cm + o, b->chroma_mode + s, c, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(ctx->d_qp + o, b->qp_y + s, c, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(ctx->d_modes + o * 16, b->luma_modes + s * 16, c * 16, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(ctx->d_nzb + o, b->nz_blocks + s, c * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(ctx->d_woff + o, b->word_off + s, c * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        const uint64_t w0 = b->pic_off[done], w1 = b->pic_off[done + cnt], base = (uint64_t)o * MVG_PACKED_WORDS_PER_MB;
+        if (w1 > w0)
+            CK(ctx, cudaMemcpyAsync(ctx->d_words + base, b->words + w0, (size_t)(w1 - w0) * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+        /* one staging entry per picture of the batch: nothing is reused before the final synchronisation */
+        for (int i = 0; i < cnt; i++) ctx->h_picbase[done + i] = base + (b->pic_off[done + i] - w0);
+        CK(ctx, cudaMemcpyAsync(ctx->d_picbase + slot0, ctx->h_picbase + done, (size_t)cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        return MVG_SUCCESS;
+    };
+    auto expand = [&](int slot0, int cnt) -> int {
+        K0Params p;
+        const size_t o = (size_t)slot0 * n;
+        p.nz_blocks = ctx->d_nzb + o; p.word_off = ctx->d_woff + o; p.pic_base = ctx->d_picbase + slot0;
+        p.words = ctx->d_words; p.coeff = ctx->d_coeff + o * 384; p.n_mbs = (long long)cnt * (long long)n; p.mbs_per_pic = (int)n;
+        const long long warps = p.n_mbs;
+        const int grid = (int)std::min<long long>((warps + 7) / 8, (long long)ctx->sm_count * 16);
+        k0_expand_levels<<<grid, 256, 0, ctx->stream>>>(p);
+        CK(ctx, cudaGetLastError());
+        return MVG_SUCCESS;
+    };
+    return decode_pipeline(ctx, b->n_pics, yuv_out, rgb_out, rgb_scale, upload, expand);
+}
+

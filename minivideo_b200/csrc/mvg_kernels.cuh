@@ -49,6 +49,56 @@ __device__ __forceinline__ int mvg_chroma_qp(int qp_y, int offset)
 }
 
 /* ========================================================================= */
+/* Kernel 0: packed levels -> dense levels (only on the end-to-end path; see mvgpu.h) */
+
+struct K0Params {
+    const uint32_t *nz_blocks, *word_off;   /* [n_mbs]                                    */
+    const uint64_t *pic_base;               /* [n_pics] first word of each picture in `words` */
+    const uint16_t *words;
+    int16_t        *coeff;                  /* [n_mbs][384]                               */
+    long long       n_mbs;
+    int             mbs_per_pic;
+};
+
+/* One warp per macroblock, lane b < 24 = chunk b: its mask sits at rank(b) among the coded chunks, its
+ * levels start after all masks plus the levels of the chunks before it (warp prefix sum of popcounts). */
+__global__ void __launch_bounds__(256)
+k0_expand_levels(K0Params p)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long mb = warp0; mb < p.n_mbs; mb += n_warps) {
+        const unsigned nzb = __ldg(p.nz_blocks + mb) & 0x00FFFFFFu;
+        const uint16_t *w = p.words + __ldg(p.pic_base + mb / p.mbs_per_pic) + __ldg(p.word_off + mb);
+        const bool coded = (nzb >> lane) & 1u;
+        const unsigned mask = coded ? (unsigned)__ldg(w + __popc(nzb & ((1u << lane) - 1u))) : 0u;
+        int pre = __popc(mask);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(MVG_FULL, pre, o);
+            if (lane >= o) pre += t;
+        }
+        const uint16_t *lv = w + __popc(nzb) + pre - __popc(mask);
+        unsigned out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned m = mask;
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned v = (unsigned)__ldg(lv++);
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if ((k >> 1) == q) out[q] |= v << (16 * (k & 1));
+        }
+        if (lane < 24) {
+            uint4 *dst = reinterpret_cast<uint4 *>(p.coeff + mb * 384 + lane * 16);
+            dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+            dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+        }
+    }
+}
+
+/* ========================================================================= */
 /* Kernel 1                                                                    */
 
 struct K1Params {
