@@ -15,7 +15,7 @@
 #define MVG_LT_STRIDE 48
 #define MVG_LT_XOFF   16
 #define MVG_LT_ROWS   17
-#define MVG_CT_STRIDE 48
+#define MVG_CT_STRIDE 32
 #define MVG_CT_XOFF   16
 #define MVG_CT_ROWS   9
 

@@ -498,23 +498,31 @@ struct K2Params {
 #define K2_PROF(...)
 #endif
 #define K2_WARPS     16         /* warps per CTA; two CTAs per SM                              */
-#define K2_CTL_CHUNK 32         /* control records per bulk copy (two buffers)                 */
-#define K2_RING      4          /* residual ring slots (power of two)                          */
+#define K2_CTL_CHUNK 32         /* control records per chunk (one 16-byte copy per lane)       */
+#define K2_RING      4          /* residual ring slots (power of two; three are live at a time)   */
 #define K2_TO(x, y)  (((y) + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + (x))    /* luma tile offset of sample (x, y)   */
 #define K2_CO(x, y)  (((y) + 1) * MVG_CT_STRIDE + MVG_CT_XOFF + (x))    /* chroma tile offset of sample (x, y) */
 
 struct K2WarpSmem {
-    __align__(128) int16_t  resid[K2_RING][384];        /* residual ring, filled by bulk async copies K2_RING-1 macroblocks ahead */
-    __align__(16)  MvgMbCtl ctl[2][K2_CTL_CHUNK];       /* control records, double buffered                                   */
-    __align__(16)  uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
-    __align__(16)  uint8_t  ct[2][MVG_CT_ROWS * MVG_CT_STRIDE];
-    __align__(16)  uint32_t n8[36];                     /* Intra8x8 neighbour line: p' | f2 << 8 | f3 << 16; [32] = DC */
-    __align__(8)   uint64_t mbar[K2_RING + 2];          /* residual ring slots, then the two control buffers */
+    __align__(16) int16_t  resid[K2_RING][384];         /* residual ring, filled by per-lane async copies two macroblocks ahead */
+    __align__(16) MvgMbCtl ctl[2 * K2_CTL_CHUNK];       /* control records, two chunks: record of macroblock mx at [mx & 63]      */
+    __align__(16) uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
+    __align__(16) uint8_t  ct[2][MVG_CT_ROWS * MVG_CT_STRIDE];
+    __align__(16) uint32_t n8[36];                      /* Intra8x8 neighbour line: p' | f2 << 8 | f3 << 16; [32] = DC */
 };
 
 /* dynamic shared memory: warp records and the tap tables (2 KB aligned, see the kernel) */
 #define K2_LUT_BYTES  ((sizeof(MvgLuts) + 127) / 128 * 128)
 #define K2_SMEM_BYTES (sizeof(K2WarpSmem) * K2_WARPS + 2048 + K2_LUT_BYTES)
+
+/* 16-byte asynchronous copy global -> shared (LDGSTS), completion by per-thread groups */
+__device__ __forceinline__ void mvg_cp_async16(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(mvg_smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void mvg_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void mvg_cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 __device__ __forceinline__ uint2 mvg_ld_relaxed_u64(const uint2 *p)
 {
@@ -563,11 +571,13 @@ struct K2Ctx {
 };
 
 /* ---- Intra16x16 luma (h264_intra_prediction.c:1945-2141) ------------------- */
-/* lane = 2 * y + (x0 / 8): eight samples of one row, handled as four int16 pairs */
+/* lane = 4 * p + row: row `row` of the horizontally adjacent 4x4 blocks 2p, 2p+1 (decoding order), i.e. eight
+ * samples whose residual is two 8-byte reads at lane-linear addresses; handled as four int16 pairs */
 __device__ __forceinline__ void k2_luma16(const K2Ctx &c, int mode, bool left, bool up)
 {
     uint8_t *lt = c.lt;
-    const int lane = c.lane, y = lane >> 1, x0 = (lane & 1) * 8;
+    const int lane = c.lane, p = lane >> 2;
+    const int x0 = (p & 2) * 4, y = ((p & 1) + (p >> 2) * 2) * 4 + (lane & 3);
     unsigned pp[4];
     if (mode == 0) {            /* Vertical */
         const uint2 t = *reinterpret_cast<const uint2 *>(lt + K2_TO(0, -1) + x0);
@@ -602,11 +612,9 @@ __device__ __forceinline__ void k2_luma16(const K2Ctx &c, int mode, bool left, b
             pair = __vadd2(pair, step);
         }
     }
-    /* row y, samples x0..x0+7: 4x4 blocks (x0/4, y/4) and (x0/4+1, y/4), row y&3 of each */
-    const int bcol = x0 >> 2, brow = y >> 2;
-    const int blkA = (bcol & 1) | ((brow & 1) << 1) | ((bcol >> 1) << 2) | ((brow >> 1) << 3);
-    const uint2 ra = *reinterpret_cast<const uint2 *>(c.resid + blkA * 32 + (y & 3) * 8);
-    const uint2 rb = *reinterpret_cast<const uint2 *>(c.resid + (blkA + 1) * 32 + (y & 3) * 8);
+    const uint8_t *r = c.resid + (lane >> 2) * 64 + (lane & 3) * 8;
+    const uint2 ra = *reinterpret_cast<const uint2 *>(r);
+    const uint2 rb = *reinterpret_cast<const uint2 *>(r + 32);
     const unsigned lo = mvg_pairs_to_bytes(mvg_add_clip8x2(pp[0], ra.x), mvg_add_clip8x2(pp[1], ra.y));
     const unsigned hi = mvg_pairs_to_bytes(mvg_add_clip8x2(pp[2], rb.x), mvg_add_clip8x2(pp[3], rb.y));
     *reinterpret_cast<uint2 *>(lt + K2_TO(0, 0) + y * MVG_LT_STRIDE + x0) = make_uint2(lo, hi);
@@ -733,14 +741,15 @@ __device__ __forceinline__ void k2_luma8(const K2Ctx &c, unsigned modes, bool av
 }
 
 /* ---- chroma, both planes at once (h264_intra_prediction.c:2338-2564) --------- */
-/* lane = 16 * plane + 2 * y + (x0 / 4): four samples of one row as two int16 pairs */
+/* lane = 16 * plane + 4 * block + row: four samples of one row of one 4x4 block as two int16 pairs; the
+ * residual of lane l is the 8 bytes at 512 + 8 l */
 __device__ __forceinline__ void k2_chroma(const K2Ctx &c, int mode, bool left, bool up)
 {
-    const int lane = c.lane, pl = lane >> 4, y = (lane >> 1) & 7, x0 = (lane & 1) * 4;
+    const int lane = c.lane, pl = lane >> 4;
+    const int x0 = (lane & 4), yo = (lane & 8) >> 1, y = yo + (lane & 3);
     uint8_t *ct = c.ct + pl * (MVG_CT_ROWS * MVG_CT_STRIDE);
     unsigned p0, p1;
     if (mode == 0) {            /* DC, per 4x4 block */
-        const int yo = y & 4;
         int st = 0, sl = 0;
         if (up) st = mvg_sum4(*reinterpret_cast<const unsigned *>(ct + K2_CO(0, -1) + x0));
         if (left) sl = (int)ct[K2_CO(-1, 0) + yo * MVG_CT_STRIDE] + (int)ct[K2_CO(-1, 1) + yo * MVG_CT_STRIDE] +
@@ -772,7 +781,7 @@ __device__ __forceinline__ void k2_chroma(const K2Ctx &c, int mode, bool left, b
         p0 = (__vimin_s16x2_relu(pair, 0x1fff1fffu) >> 5) & 0x00ff00ffu;
         p1 = (__vimin_s16x2_relu(__vadd2(pair, (unsigned)((2 * b) & 0xffff) * 0x10001u), 0x1fff1fffu) >> 5) & 0x00ff00ffu;
     }
-    const uint2 r = *reinterpret_cast<const uint2 *>(c.resid + (256 + pl * 64 + ((y >> 2) * 2 + (x0 >> 2)) * 16 + (y & 3) * 4) * 2);
+    const uint2 r = *reinterpret_cast<const uint2 *>(c.resid + 512 + lane * 8);
     *reinterpret_cast<unsigned *>(ct + K2_CO(0, 0) + y * MVG_CT_STRIDE + x0) =
         mvg_pairs_to_bytes(mvg_add_clip8x2(p0, r.x), mvg_add_clip8x2(p1, r.y));
 }
@@ -785,18 +794,20 @@ __device__ __forceinline__ void k2_chroma(const K2Ctx &c, int mode, bool left, b
  * the bottom sample line of the macroblocks above, so a finished macroblock publishes that
  * line (16 Y + 8 Cb + 8 Cr bytes) as eight 64-bit words {4 data bytes, launch epoch} -- the
  * flag travels with the data, every word validates itself, and neither side needs a fence or
- * a separate progress counter.  The row below spins only on words whose epoch is stale.
+ * a separate progress counter.  The row below reads them four macroblocks at a time (one coalesced
+ * load, a group ahead of use) and polls only when a word it needs is stale.
  *
  * Claim order: pictures are taken in groups of `group`; inside a group items are ordered
  * row-major over (row, picture).  Row r-1 of a picture is therefore always claimed before row
  * r (no deadlock: it runs on a resident warp).
  *
- * Inputs arrive by bulk asynchronous copies (one elected lane, mbarrier completion): the control
- * records of the whole row once per row, the 768-byte residual of macroblock x+1 while x is being
- * predicted.  The kernel is bound by instruction issue, not by HBM, so everything in the loop is
- * organised to cost as few warp instructions as possible: shared-memory addresses are
- * [lane constant + uniform base + immediate], tables hold ready-to-use offsets and byte-permute
- * selectors, residual adds run on int16 pairs. */
+ * Inputs arrive by per-lane asynchronous copies (LDGSTS, completion by per-thread groups, no barrier
+ * objects): the 768-byte residual of macroblock x+2 is requested while x is predicted, control records
+ * come 32 macroblocks at a time.  Output is one 384-byte tile per macroblock.
+ *
+ * What bounds the kernel (ncu, profiles/): instruction issue and the shared-memory data pipe, not HBM;
+ * hence tables with ready-to-use offsets, [lane constant + uniform base + immediate] addressing,
+ * int16-pair residual adds, and lane mappings that make addresses linear in the lane index. */
 __global__ void __launch_bounds__(K2_WARPS * 32, 2)
 k2_wavefront(K2Params p)
 {
@@ -814,9 +825,6 @@ k2_wavefront(K2Params p)
                        : k2_smem + (lut_addr - base) + K2_LUT_BYTES + (wid - n_before) * sizeof(K2WarpSmem));
     for (int i = threadIdx.x; i < (int)(sizeof(MvgLuts) / 16); i += blockDim.x)
         reinterpret_cast<uint4 *>(luts)[i] = __ldg(reinterpret_cast<const uint4 *>(p.luts) + i);
-    if (lane < K2_RING + 2) mvg_mbar_init(&s.mbar[lane], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     const int W = p.w_mbs, H = p.h_mbs, n_mb = W * H;
@@ -869,10 +877,11 @@ k2_wavefront(K2Params p)
     /* tile write-out: lanes 0..15 one luma row (16 B), lanes 16..23 Cb rows, 24..31 Cr rows (8 B) */
     const uint8_t *const wo_src = lane < 16 ? s.lt + K2_TO(0, lane)
                                             : s.ct[(lane >> 3) & 1] + K2_CO(0, lane & 7);
+    const int wo_off = lane < 16 ? lane * 16 : 256 + (lane - 16) * 8;
+    /* staging: lane l copies bytes [16 l, 16 l + 16) of a residual and, lanes 0..15, [512 + 16 l, ..) */
+    uint8_t *const st_dst = reinterpret_cast<uint8_t *>(s.resid[0]) + lane * 16;
 
     K2_PROF(long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt0 = clock64();)
-    unsigned parity = 0;            /* bit b: phase parity of mbar[b] (0..K2_RING-1 residual ring, then 2 control buffers) */
-    unsigned rb = 0;                /* ring slot of the current macroblock's residual */
 
     for (;;) {
         K2_PROF(const long long tr0 = clock64();)
@@ -885,26 +894,27 @@ k2_wavefront(K2Params p)
         const int within = item - g * p.group * H;
         const int row = within / gsize;
         const int slot = p.first_slot + g * p.group + (within - row * gsize);
+        const size_t mb0 = (size_t)slot * n_mb + (size_t)row * W;           /* first macroblock of the row */
 
-        const int16_t *resid = p.resid + ((size_t)slot * n_mb + (size_t)row * W) * 384;
-        const MvgMbCtl *ctl = p.ctl + (size_t)slot * n_mb + (size_t)row * W;
-        if (lane == 0) {            /* first chunk of control records, first residuals of the row */
-            const unsigned cb = (unsigned)min(W, K2_CTL_CHUNK) * 16u;
-            mvg_mbar_expect_tx(&s.mbar[K2_RING], cb);
-            mvg_bulk_load(s.ctl[0], ctl, cb, &s.mbar[K2_RING]);
-            for (int i = 0; i < K2_RING - 1 && i < W; i++) {
-                const unsigned b = (rb + i) & (K2_RING - 1);
-                mvg_mbar_expect_tx(&s.mbar[b], 768u);
-                mvg_bulk_load(s.resid[b], resid + (size_t)i * 384, 768u, &s.mbar[b]);
-            }
+        const uint8_t *st_src = reinterpret_cast<const uint8_t *>(p.resid + mb0 * 384) + lane * 16;
+        const MvgMbCtl *ctl = p.ctl + mb0;
+        /* group 0: control records 0..31 and residual 0; group 1: residual 1 */
+        if (lane < W) mvg_cp_async16(&s.ctl[lane], ctl + lane);
+        mvg_cp_async16(st_dst, st_src);
+        if (lane < 16) mvg_cp_async16(st_dst + 512, st_src + 512);
+        mvg_cp_async_commit();
+        if (W > 1) {
+            mvg_cp_async16(st_dst + 768, st_src + 768);
+            if (lane < 16) mvg_cp_async16(st_dst + 768 + 512, st_src + 768 + 512);
         }
+        mvg_cp_async_commit();
 
         /* where this lane writes its piece of every macroblock tile of this row */
-        uint8_t *wo_dst = p.tiles + ((size_t)slot * n_mb + (size_t)row * W) * 384 + (lane < 16 ? lane * 16 : 256 + (lane - 16) * 8);
+        uint8_t *const wo_dst = p.tiles + mb0 * 384 + wo_off;
         const bool availB = row > 0, publish = row < H - 1;
         /* halo words of the row above, four macroblocks per coalesced load: lane = 8 * (mx & 3) + word */
-        const uint2 *habove = p.halo + ((size_t)slot * n_mb + (size_t)(row - 1) * W) * 8 + lane;
-        uint2 *hmine = p.halo + ((size_t)slot * n_mb + (size_t)row * W) * 8 + lane;
+        const uint2 *const habove = p.halo + (mb0 - W) * 8 + lane;
+        uint2 *const hmine = p.halo + mb0 * 8 + lane;
         const int hwords = W * 8;                               /* halo words of a macroblock row */
         uint2 qa = make_uint2(0, epoch), qb = make_uint2(0, epoch);
         if (availB) {
@@ -924,35 +934,22 @@ k2_wavefront(K2Params p)
             if (lane < hwords) qa = mvg_ld_relaxed_u64(habove);
         }
         unsigned okA = 0;
-        mvg_mbar_wait(&s.mbar[K2_RING], (parity >> K2_RING) & 1u);
-        parity ^= 1u << K2_RING;
 
         K2_PROF(pc[0] += clock64() - tr0;)
         for (int mx = 0; mx < W; mx++) {
             K2_PROF(const long long t0 = clock64();)
             const int j = mx & 3;
-            const unsigned cbuf = (unsigned)(mx / K2_CTL_CHUNK) & 1u;
-            if ((mx & (K2_CTL_CHUNK - 1)) == 0) {
-                /* this chunk of control records was requested one chunk ago (or in the row prologue);
-                 * request the next one into the other buffer, whose last reader finished a macroblock ago */
-                if (mx) {
-                    mvg_mbar_wait(&s.mbar[K2_RING + cbuf], (parity >> (K2_RING + cbuf)) & 1u);
-                    parity ^= 1u << (K2_RING + cbuf);
-                }
-                if (mx + K2_CTL_CHUNK < W && lane == 0) {
-                    const unsigned cb = (unsigned)min(W - mx - K2_CTL_CHUNK, K2_CTL_CHUNK) * 16u;
-                    mvg_mbar_expect_tx(&s.mbar[K2_RING + (cbuf ^ 1u)], cb);
-                    mvg_bulk_load(s.ctl[cbuf ^ 1u], ctl + mx + K2_CTL_CHUNK, cb, &s.mbar[K2_RING + (cbuf ^ 1u)]);
-                }
+            /* requests for macroblock mx + 2 (its ring slot was last read before the __syncwarp() that closed
+             * macroblock mx - 2) and, at the start of a chunk, for the next chunk of control records */
+            if (mx + 2 < W) {
+                uint8_t *d = st_dst + ((mx + 2) & (K2_RING - 1)) * 768;
+                const uint8_t *src = st_src + (size_t)(mx + 2) * 768;
+                mvg_cp_async16(d, src);
+                if (lane < 16) mvg_cp_async16(d + 512, src + 512);
             }
-            /* residual of macroblock mx + K2_RING - 1: its ring slot was last read before the __syncwarp()
-             * that closed macroblock mx - 1 */
-            if (mx + K2_RING - 1 < W && lane == 0) {
-                const unsigned b = (rb + K2_RING - 1) & (K2_RING - 1);
-                mvg_mbar_expect_tx(&s.mbar[b], 768u);
-                mvg_bulk_load(s.resid[b], resid + (size_t)(mx + K2_RING - 1) * 384, 768u, &s.mbar[b]);
-            }
-            const uint4 ctlw = *reinterpret_cast<const uint4 *>(&s.ctl[cbuf][mx & (K2_CTL_CHUNK - 1)]);
+            if ((mx & (K2_CTL_CHUNK - 1)) == 0 && mx + K2_CTL_CHUNK + lane < W)
+                mvg_cp_async16(&s.ctl[(mx + K2_CTL_CHUNK + lane) & (2 * K2_CTL_CHUNK - 1)], ctl + mx + K2_CTL_CHUNK + lane);
+            mvg_cp_async_commit();
             const bool availA = mx > 0, availC = availB && mx < W - 1, availD = availA && availB;
 
             if (availB) {
@@ -962,7 +959,7 @@ k2_wavefront(K2Params p)
                 }
                 /* words needed now: the 8 of the macroblock above and, for the up-right neighbour, the
                  * first two of the next one (in qb when this is the last macroblock of the group) */
-                const unsigned needA = (0xFFu << (8 * j)) | ((availC && j < 3) ? 0x300u << (8 * j) : 0u);
+                const unsigned needA = (availC && j < 3 ? 0x3FFu : 0xFFu) << (8 * j);
                 bool ok = (okA & needA) == needA;
                 if (availC && j == 3) ok = ok && (__ballot_sync(MVG_FULL, qb.y == epoch) & 3u) == 3u;
                 K2_PROF(const long long th = clock64();)
@@ -994,18 +991,17 @@ k2_wavefront(K2Params p)
                     if (mx * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(habove + (size_t)mx * 8 + 32);
                 }
             }
-            c.resid = reinterpret_cast<const uint8_t *>(s.resid[rb]);
             K2_PROF(const long long t1 = clock64();)
-            mvg_mbar_wait(&s.mbar[rb], (parity >> rb) & 1u);
-            parity ^= 1u << rb;
+            mvg_cp_async_wait<2>();             /* all but the two youngest groups: macroblock mx has landed */
             __syncwarp();
             K2_PROF(const long long t2 = clock64();)
+            c.resid = reinterpret_cast<const uint8_t *>(s.resid[mx & (K2_RING - 1)]);
+            const uint4 ctlw = *reinterpret_cast<const uint4 *>(&s.ctl[mx & (2 * K2_CTL_CHUNK - 1)]);
 
             const int kind = ctlw.x & 255, i16 = (ctlw.x >> 8) & 255, cmode = (ctlw.x >> 16) & 255;
             if (kind == MVG_MB_I16x16)    k2_luma16(c, i16, availA, availB);
             else if (kind == MVG_MB_I4x4) k2_luma4(c, ctlw.y, ctlw.z, availA, availB, availC);
             else                          k2_luma8(c, ctlw.y, availA, availB, availC, availD);
-            K2_PROF(const long long t2b = clock64();)
             k2_chroma(c, cmode, availA, availB);
             __syncwarp();
             K2_PROF(const long long t3 = clock64();)
@@ -1014,9 +1010,9 @@ k2_wavefront(K2Params p)
              * planar picture costs more than the whole prediction: measured 4.5 ms vs 1.8 ms per 1000 pictures) */
             {
                 const uint4 v = *reinterpret_cast<const uint4 *>(wo_src);
-                if (lane < 16) *reinterpret_cast<uint4 *>(wo_dst) = v;
-                else *reinterpret_cast<uint2 *>(wo_dst) = make_uint2(v.x, v.y);
-                wo_dst += 384;
+                uint8_t *d = wo_dst + (size_t)mx * 384;
+                if (lane < 16) *reinterpret_cast<uint4 *>(d) = v;
+                else *reinterpret_cast<uint2 *>(d) = make_uint2(v.x, v.y);
             }
             /* publish the bottom sample line for the row below */
             if (publish && lane < 8)
@@ -1024,11 +1020,10 @@ k2_wavefront(K2Params p)
             /* next macroblock: x = 15 becomes x = -1 (luma rows -1..15, chroma x = 7, rows -1..7) */
             lc_src[-lc_back] = lc_src[0];
             if (lane < 3) lc_src2[-8] = lc_src2[0];
-            rb = (rb + 1) & (K2_RING - 1);
             __syncwarp();
-            K2_PROF(const long long t4 = clock64(); pc[1] += t1 - t0; pc[2] += t2 - t1; pc[3] += t3 - t2; pc[4] += t4 - t3;
-                    if (kind == MVG_MB_I4x4) pc[0] += 0;)
+            K2_PROF(const long long t4 = clock64(); pc[1] += t1 - t0; pc[2] += t2 - t1; pc[3] += t3 - t2; pc[4] += t4 - t3;)
         }
+        mvg_cp_async_wait<0>();
     }
     K2_PROF(if (lane == 0 && p.stats) { for (int i = 0; i < 8; i++) atomicAdd(p.stats + i, (unsigned long long)pc[i]); atomicAdd(p.stats + 8, (unsigned long long)(clock64() - pt0)); })
 }
