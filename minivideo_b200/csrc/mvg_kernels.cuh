@@ -909,19 +909,20 @@ k2_wavefront(K2Params p)
         }
         mvg_cp_async_commit();
 
-        /* where this lane writes its piece of every macroblock tile of this row */
-        uint8_t *const wo_dst = p.tiles + mb0 * 384 + wo_off;
+        /* running pointers: source of the residual requested next (macroblock mx + 2), this lane's piece of the
+         * tile of macroblock mx, its word of the published line, its word of the next group of the row above */
+        const uint8_t *st_run = st_src + 2 * 768;
+        uint8_t *wo_run = p.tiles + mb0 * 384 + wo_off;
+        uint2 *hm_run = p.halo + mb0 * 8 + lane;
+        const uint2 *ha_run = p.halo + (mb0 - W) * 8 + lane;           /* group of macroblock mx (at j == 0) */
         const bool availB = row > 0, publish = row < H - 1;
-        /* halo words of the row above, four macroblocks per coalesced load: lane = 8 * (mx & 3) + word */
-        const uint2 *const habove = p.halo + (mb0 - W) * 8 + lane;
-        uint2 *const hmine = p.halo + mb0 * 8 + lane;
         const int hwords = W * 8;                               /* halo words of a macroblock row */
         uint2 qa = make_uint2(0, epoch), qb = make_uint2(0, epoch);
         if (availB) {
             if (p.stagger > 1) {
                 /* keep rows of one picture apart: a row that runs two macroblocks behind the row above waits
                  * on every macroblock and inherits all of its stalls */
-                const uint2 *far = habove + (size_t)(min(p.stagger, W) - 1) * 8;
+                const uint2 *far = ha_run + (size_t)(min(p.stagger, W) - 1) * 8;
                 uint2 t = make_uint2(0, epoch);
                 if (lane < 8) t = mvg_ld_relaxed_u64(far);
                 unsigned ns = 256;
@@ -931,97 +932,95 @@ k2_wavefront(K2Params p)
                     if (lane < 8) t = mvg_ld_relaxed_u64(far);
                 }
             }
-            if (lane < hwords) qa = mvg_ld_relaxed_u64(habove);
+            if (lane < hwords) qb = mvg_ld_relaxed_u64(ha_run);     /* becomes qa at macroblock 0 */
         }
         unsigned okA = 0;
 
         K2_PROF(pc[0] += clock64() - tr0;)
-        for (int mx = 0; mx < W; mx++) {
-            K2_PROF(const long long t0 = clock64();)
-            const int j = mx & 3;
-            /* requests for macroblock mx + 2 (its ring slot was last read before the __syncwarp() that closed
-             * macroblock mx - 2) and, at the start of a chunk, for the next chunk of control records */
-            if (mx + 2 < W) {
-                uint8_t *d = st_dst + ((mx + 2) & (K2_RING - 1)) * 768;
-                const uint8_t *src = st_src + (size_t)(mx + 2) * 768;
-                mvg_cp_async16(d, src);
-                if (lane < 16) mvg_cp_async16(d + 512, src + 512);
-            }
-            if ((mx & (K2_CTL_CHUNK - 1)) == 0 && mx + K2_CTL_CHUNK + lane < W)
-                mvg_cp_async16(&s.ctl[(mx + K2_CTL_CHUNK + lane) & (2 * K2_CTL_CHUNK - 1)], ctl + mx + K2_CTL_CHUNK + lane);
-            mvg_cp_async_commit();
-            const bool availA = mx > 0, availC = availB && mx < W - 1, availD = availA && availB;
-
-            if (availB) {
-                if (j == 0) {                   /* next group of four macroblocks above (requested a group ago) */
-                    if (mx) qa = qb;
-                    okA = __ballot_sync(MVG_FULL, qa.y == epoch);
+        for (int c0 = 0; c0 < W; c0 += K2_CTL_CHUNK) {
+            /* next chunk of control records; joins the copy group of the first macroblock of this chunk */
+            if (c0 + K2_CTL_CHUNK + lane < W)
+                mvg_cp_async16(&s.ctl[(c0 + K2_CTL_CHUNK + lane) & (2 * K2_CTL_CHUNK - 1)], ctl + c0 + K2_CTL_CHUNK + lane);
+            const int cend = min(c0 + K2_CTL_CHUNK, W);
+            for (int mx = c0; mx < cend; mx++) {
+                K2_PROF(const long long t0 = clock64();)
+                const int j = mx & 3;
+                /* request macroblock mx + 2: its ring slot was last read before the __syncwarp() that closed mx - 2 */
+                if (mx + 2 < W) {
+                    uint8_t *d = st_dst + ((mx + 2) & (K2_RING - 1)) * 768;
+                    mvg_cp_async16(d, st_run);
+                    if (lane < 16) mvg_cp_async16(d + 512, st_run + 512);
                 }
-                /* words needed now: the 8 of the macroblock above and, for the up-right neighbour, the
-                 * first two of the next one (in qb when this is the last macroblock of the group) */
-                const unsigned needA = (availC && j < 3 ? 0x3FFu : 0xFFu) << (8 * j);
-                bool ok = (okA & needA) == needA;
-                if (availC && j == 3) ok = ok && (__ballot_sync(MVG_FULL, qb.y == epoch) & 3u) == 3u;
-                K2_PROF(const long long th = clock64();)
-                if (!ok) {
-                    K2_PROF(pc[5]++;)
-                    /* this row has caught up with the row above: poll, sleeping a fraction of a macroblock time */
-                    unsigned ns = 100;
-                    const size_t g0 = (size_t)(mx & ~3) * 8;
-                    do {
-                        K2_PROF(pc[6]++;)
-                        __nanosleep(ns);
-                        if (ns < 800) ns *= 2;
-                        if ((mx & ~3) * 8 + lane < hwords) qa = mvg_ld_relaxed_u64(habove + g0);
+                st_run += 768;
+                mvg_cp_async_commit();
+                const bool availA = mx > 0, availC = availB && mx < W - 1, availD = availA && availB;
+
+                if (availB) {
+                    if (j == 0) {               /* group of four macroblocks above: requested a group ago; request the next */
+                        qa = qb;
                         okA = __ballot_sync(MVG_FULL, qa.y == epoch);
-                        ok = (okA & needA) == needA;
-                        if (availC && j == 3) {
-                            if ((mx & ~3) * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(habove + g0 + 32);
-                            ok = ok && (__ballot_sync(MVG_FULL, qb.y == epoch) & 3u) == 3u;
-                        }
-                    } while (!ok);
+                        qb = make_uint2(0, epoch);
+                        if (mx * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(ha_run + 32);
+                    }
+                    /* words needed now: the 8 of the macroblock above and, for the up-right neighbour, the first
+                     * two of the next one, which sit in qb when this is the last macroblock of the group */
+                    const unsigned need = availC ? 0x3FFu : 0xFFu;
+                    unsigned have = __funnelshift_r(okA, j == 3 ? __ballot_sync(MVG_FULL, qb.y == epoch) : 0u, 8 * j);
+                    K2_PROF(const long long th = clock64();)
+                    if ((have & need) != need) {
+                        K2_PROF(pc[5]++;)
+                        /* this row has caught up with the row above: poll, sleeping a fraction of a macroblock time */
+                        unsigned ns = 100;
+                        do {
+                            K2_PROF(pc[6]++;)
+                            __nanosleep(ns);
+                            if (ns < 800) ns *= 2;
+                            if ((mx & ~3) * 8 + lane < hwords) qa = mvg_ld_relaxed_u64(ha_run);
+                            if ((mx & ~3) * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(ha_run + 32);
+                            okA = __ballot_sync(MVG_FULL, qa.y == epoch);
+                            have = __funnelshift_r(okA, __ballot_sync(MVG_FULL, qb.y == epoch), 8 * j);
+                        } while ((have & need) != need);
+                    }
+                    K2_PROF(pc[7] += clock64() - th;)
+                    /* sample row -1 of the tiles: lanes 0..7 the macroblock above, lanes 8,9 x = 16..23 */
+                    const unsigned src = (j == 3 && lane < 2) ? qb.x : qa.x;
+                    const unsigned v = __shfl_sync(MVG_FULL, src, (8 * j + lane) & 31);
+                    if (lane < 10) *reinterpret_cast<unsigned *>(halo_top) = v;
+                    if (j == 3) ha_run += 32;
                 }
-                K2_PROF(pc[7] += clock64() - th;)
-                /* sample row -1 of the tiles: lanes 0..7 the macroblock above, lanes 8,9 x = 16..23 */
-                const unsigned src = (j == 3 && lane < 2) ? qb.x : qa.x;
-                const unsigned v = __shfl_sync(MVG_FULL, src, (8 * j + lane) & 31);
-                if (lane < 10) *reinterpret_cast<unsigned *>(halo_top) = v;
-                if (j == 0) {                   /* request the group after this one; it is first looked at 3 macroblocks from now */
-                    qb = make_uint2(0, epoch);
-                    if (mx * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(habove + (size_t)mx * 8 + 32);
+                K2_PROF(const long long t1 = clock64();)
+                mvg_cp_async_wait<2>();         /* all but the two youngest groups: macroblock mx has landed */
+                __syncwarp();
+                K2_PROF(const long long t2 = clock64();)
+                c.resid = reinterpret_cast<const uint8_t *>(s.resid[mx & (K2_RING - 1)]);
+                const uint4 ctlw = *reinterpret_cast<const uint4 *>(&s.ctl[mx & (2 * K2_CTL_CHUNK - 1)]);
+
+                const int kind = ctlw.x & 255, i16 = (ctlw.x >> 8) & 255, cmode = (ctlw.x >> 16) & 255;
+                if (kind == MVG_MB_I16x16)    k2_luma16(c, i16, availA, availB);
+                else if (kind == MVG_MB_I4x4) k2_luma4(c, ctlw.y, ctlw.z, availA, availB, availC);
+                else                          k2_luma8(c, ctlw.y, availA, availB, availC, availD);
+                k2_chroma(c, cmode, availA, availB);
+                __syncwarp();
+                K2_PROF(const long long t3 = clock64();)
+
+                /* write the macroblock out as one 384-byte tile (coalesced; scattering 16-byte row pieces over a
+                 * planar picture costs more than the whole prediction: measured 4.5 ms vs 1.8 ms per 1000 pictures) */
+                {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(wo_src);
+                    if (lane < 16) *reinterpret_cast<uint4 *>(wo_run) = v;
+                    else *reinterpret_cast<uint2 *>(wo_run) = make_uint2(v.x, v.y);
+                    wo_run += 384;
                 }
+                /* publish the bottom sample line for the row below */
+                if (publish && lane < 8)
+                    mvg_st_relaxed_u64(hm_run, *reinterpret_cast<const unsigned *>(halo_bot), epoch);
+                hm_run += 8;
+                /* next macroblock: x = 15 becomes x = -1 (luma rows -1..15, chroma x = 7, rows -1..7) */
+                lc_src[-lc_back] = lc_src[0];
+                if (lane < 3) lc_src2[-8] = lc_src2[0];
+                __syncwarp();
+                K2_PROF(const long long t4 = clock64(); pc[1] += t1 - t0; pc[2] += t2 - t1; pc[3] += t3 - t2; pc[4] += t4 - t3;)
             }
-            K2_PROF(const long long t1 = clock64();)
-            mvg_cp_async_wait<2>();             /* all but the two youngest groups: macroblock mx has landed */
-            __syncwarp();
-            K2_PROF(const long long t2 = clock64();)
-            c.resid = reinterpret_cast<const uint8_t *>(s.resid[mx & (K2_RING - 1)]);
-            const uint4 ctlw = *reinterpret_cast<const uint4 *>(&s.ctl[mx & (2 * K2_CTL_CHUNK - 1)]);
-
-            const int kind = ctlw.x & 255, i16 = (ctlw.x >> 8) & 255, cmode = (ctlw.x >> 16) & 255;
-            if (kind == MVG_MB_I16x16)    k2_luma16(c, i16, availA, availB);
-            else if (kind == MVG_MB_I4x4) k2_luma4(c, ctlw.y, ctlw.z, availA, availB, availC);
-            else                          k2_luma8(c, ctlw.y, availA, availB, availC, availD);
-            k2_chroma(c, cmode, availA, availB);
-            __syncwarp();
-            K2_PROF(const long long t3 = clock64();)
-
-            /* write the macroblock out as one 384-byte tile (coalesced; scattering 16-byte row pieces over a
-             * planar picture costs more than the whole prediction: measured 4.5 ms vs 1.8 ms per 1000 pictures) */
-            {
-                const uint4 v = *reinterpret_cast<const uint4 *>(wo_src);
-                uint8_t *d = wo_dst + (size_t)mx * 384;
-                if (lane < 16) *reinterpret_cast<uint4 *>(d) = v;
-                else *reinterpret_cast<uint2 *>(d) = make_uint2(v.x, v.y);
-            }
-            /* publish the bottom sample line for the row below */
-            if (publish && lane < 8)
-                mvg_st_relaxed_u64(hmine + (size_t)mx * 8, *reinterpret_cast<const unsigned *>(halo_bot), epoch);
-            /* next macroblock: x = 15 becomes x = -1 (luma rows -1..15, chroma x = 7, rows -1..7) */
-            lc_src[-lc_back] = lc_src[0];
-            if (lane < 3) lc_src2[-8] = lc_src2[0];
-            __syncwarp();
-            K2_PROF(const long long t4 = clock64(); pc[1] += t1 - t0; pc[2] += t2 - t1; pc[3] += t3 - t2; pc[4] += t4 - t3;)
         }
         mvg_cp_async_wait<0>();
     }
