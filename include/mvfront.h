@@ -74,6 +74,25 @@ int mvf_select_idr(const mvf_stream *s, int n_wanted, int mode, int32_t *indices
 int mvf_parse_pictures(mvf_stream *s, const int32_t *indices, int first, int count,
                        mvf_batch *out, int n_threads);
 
+/* Writable twin of mvg_packed_batch (mvgpu.h): the caller allocates mb_kind .. word_off for `n_pics`
+ * pictures, pic_off[n_pics + 1] and `words_capacity` uint16 words (n_pics * N * MVG_PACKED_WORDS_PER_MB
+ * always suffices; a parsed picture typically needs a fifth of the dense levels). */
+typedef struct mvf_packed_batch {
+    int32_t   n_pics;
+    uint8_t  *mb_kind, *i16_mode, *chroma_mode;
+    int8_t   *qp_y;
+    uint8_t  *luma_modes;
+    uint32_t *nz_blocks, *word_off;
+    uint64_t *pic_off;
+    uint16_t *words;
+    size_t    words_capacity;
+} mvf_packed_batch;
+
+/* mvf_parse_pictures() emitting the packed transfer format directly: the levels of a picture never exist
+ * densely outside a per-thread scratch picture.  FAILURE (with a message) when `words` is too small. */
+int mvf_parse_pictures_packed(mvf_stream *s, const int32_t *indices, int first, int count,
+                              mvf_packed_batch *out, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -675,7 +675,51 @@ typedef struct {
     mvf_stream *s; const int32_t *indices; int first, count; const mvf_batch *out;
     int next; int rc; char err[200];
     pthread_mutex_t mu;
+    /* packed output (mvf_parse_pictures_packed): per picture, the words it needs */
+    const mvf_packed_batch *pk;
+    uint16_t **pic_words; uint64_t *pic_count;
 } job_t;
+
+/* one parsed picture (dense, in the worker's scratch) -> packed arrays of output slot i; the words go to a
+ * buffer of their own, stitched together once every picture's size is known */
+static int pack_picture(const mvf_batch *d, size_t N, const mvf_packed_batch *pk, size_t i, uint16_t **words_out, uint64_t *count_out)
+{
+    memcpy(pk->mb_kind + i * N, d->mb_kind, N);
+    memcpy(pk->i16_mode + i * N, d->i16_mode, N);
+    memcpy(pk->chroma_mode + i * N, d->chroma_mode, N);
+    memcpy(pk->qp_y + i * N, d->qp_y, N);
+    memcpy(pk->luma_modes + i * N * 16, d->luma_modes, N * 16);
+    size_t cap = N * 64, n = 0;
+    uint16_t *w = malloc(cap * sizeof *w);
+    if (!w) return 0;
+    for (size_t m = 0; m < N; m++) {
+        const int16_t *c = d->coeff + m * 384;
+        if (n + MVG_PACKED_WORDS_PER_MB > cap) {
+            cap = cap * 2 + MVG_PACKED_WORDS_PER_MB;
+            uint16_t *w2 = realloc(w, cap * sizeof *w);
+            if (!w2) { free(w); return 0; }
+            w = w2;
+        }
+        uint32_t nzb = 0;
+        uint16_t masks[24];
+        int n_coded = 0;
+        for (int b = 0; b < 24; b++) {
+            unsigned mask = 0;
+            for (int k = 0; k < 16; k++) mask |= (unsigned)(c[b * 16 + k] != 0) << k;
+            if (mask) { nzb |= 1u << b; masks[n_coded++] = (uint16_t)mask; }
+        }
+        pk->nz_blocks[i * N + m] = nzb;
+        pk->word_off[i * N + m] = (uint32_t)n;
+        memcpy(w + n, masks, (size_t)n_coded * sizeof *w);
+        n += (size_t)n_coded;
+        for (int b = 0; b < 24; b++)
+            if ((nzb >> b) & 1u)
+                for (int k = 0; k < 16; k++)
+                    if (c[b * 16 + k]) w[n++] = (uint16_t)c[b * 16 + k];
+    }
+    *words_out = w; *count_out = n;
+    return 1;
+}
 
 static void *worker_main(void *arg)
 {
@@ -687,6 +731,13 @@ static void *worker_main(void *arg)
     w.s = s;
     w.tot_luma = malloc(N * 16); w.tot_chroma[0] = malloc(N * 4); w.tot_chroma[1] = malloc(N * 4);
     w.mode_grid = malloc(N * 16);
+    mvf_batch scratch;                                      /* one dense picture, packed output only */
+    memset(&scratch, 0, sizeof scratch);
+    if (j->pk) {
+        scratch.mb_kind = malloc(N); scratch.i16_mode = malloc(N); scratch.chroma_mode = malloc(N);
+        scratch.qp_y = malloc(N); scratch.cbp = malloc(N); scratch.luma_modes = malloc(N * 16);
+        scratch.coeff = malloc(N * 768);
+    }
     for (;;) {
         pthread_mutex_lock(&j->mu);
         int i = j->rc == MVG_SUCCESS ? j->next++ : j->count;
@@ -694,7 +745,9 @@ static void *worker_main(void *arg)
         if (i >= j->count) break;
         int idx = j->indices ? j->indices[i] : j->first + i;
         int rc = (idx < 0 || idx >= s->n_idr) ? wfail(&w, MVG_FAILURE, "IDR index %d out of range (0..%d)", idx, s->n_idr - 1)
-                                              : parse_picture(&w, idx, j->out, (size_t)i);
+                                              : parse_picture(&w, idx, j->pk ? &scratch : j->out, j->pk ? 0 : (size_t)i);
+        if (rc == MVG_SUCCESS && j->pk && !pack_picture(&scratch, N, j->pk, (size_t)i, &j->pic_words[i], &j->pic_count[i]))
+            rc = wfail(&w, MVG_FAILURE, "picture %d: out of memory while packing", idx);
         if (rc != MVG_SUCCESS) {
             pthread_mutex_lock(&j->mu);
             if (j->rc == MVG_SUCCESS) { j->rc = rc; memcpy(j->err, w.err, sizeof j->err); }
@@ -702,7 +755,30 @@ static void *worker_main(void *arg)
         }
     }
     free(w.rbsp); free(w.tot_luma); free(w.tot_chroma[0]); free(w.tot_chroma[1]); free(w.mode_grid);
+    free(scratch.mb_kind); free(scratch.i16_mode); free(scratch.chroma_mode); free(scratch.qp_y); free(scratch.cbp);
+    free(scratch.luma_modes); free(scratch.coeff);
     return NULL;
+}
+
+static int run_job(mvf_stream *s, job_t *j, int n_threads)
+{
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > j->count) n_threads = j->count;
+    if (n_threads > 256) n_threads = 256;
+    j->rc = MVG_SUCCESS;
+    pthread_mutex_init(&j->mu, NULL);
+    if (n_threads == 1) worker_main(j);
+    else {
+        pthread_t th[256];
+        int started = 0;
+        for (int t = 0; t < n_threads; t++)
+            if (pthread_create(&th[started], NULL, worker_main, j) == 0) started++;
+        if (started == 0) worker_main(j);
+        for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+    }
+    pthread_mutex_destroy(&j->mu);
+    if (j->rc != MVG_SUCCESS) memcpy(s->err, j->err, sizeof j->err);
+    return j->rc;
 }
 
 int mvf_parse_pictures(mvf_stream *s, const int32_t *indices, int first, int count, mvf_batch *out, int n_threads)
@@ -712,23 +788,38 @@ int mvf_parse_pictures(mvf_stream *s, const int32_t *indices, int first, int cou
         return sfail(s, MVG_FAILURE, "mvf_parse_pictures: a batch pointer is NULL");
     out->n_pics = count;
     if (count == 0) return MVG_SUCCESS;
-    if (n_threads < 1) n_threads = 1;
-    if (n_threads > count) n_threads = count;
-    if (n_threads > 256) n_threads = 256;
     job_t j;
     memset(&j, 0, sizeof j);
-    j.s = s; j.indices = indices; j.first = first; j.count = count; j.out = out; j.rc = MVG_SUCCESS;
-    pthread_mutex_init(&j.mu, NULL);
-    if (n_threads == 1) worker_main(&j);
-    else {
-        pthread_t th[256];
-        int started = 0;
-        for (int t = 0; t < n_threads; t++)
-            if (pthread_create(&th[started], NULL, worker_main, &j) == 0) started++;
-        if (started == 0) worker_main(&j);
-        for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+    j.s = s; j.indices = indices; j.first = first; j.count = count; j.out = out;
+    return run_job(s, &j, n_threads);
+}
+
+int mvf_parse_pictures_packed(mvf_stream *s, const int32_t *indices, int first, int count, mvf_packed_batch *out, int n_threads)
+{
+    if (!s || !out || count < 0) return MVG_FAILURE;
+    if (!out->mb_kind || !out->i16_mode || !out->chroma_mode || !out->qp_y || !out->luma_modes || !out->nz_blocks ||
+        !out->word_off || !out->pic_off || !out->words)
+        return sfail(s, MVG_FAILURE, "mvf_parse_pictures_packed: a batch pointer is NULL");
+    out->n_pics = count;
+    out->pic_off[0] = 0;
+    if (count == 0) return MVG_SUCCESS;
+    job_t j;
+    memset(&j, 0, sizeof j);
+    j.s = s; j.indices = indices; j.first = first; j.count = count; j.pk = out;
+    j.pic_words = calloc((size_t)count, sizeof *j.pic_words);
+    j.pic_count = calloc((size_t)count, sizeof *j.pic_count);
+    if (!j.pic_words || !j.pic_count) { free(j.pic_words); free(j.pic_count); return sfail(s, MVG_FAILURE, "mvf_parse_pictures_packed: out of memory"); }
+    int rc = run_job(s, &j, n_threads);
+    if (rc == MVG_SUCCESS) {
+        for (int i = 0; i < count; i++) out->pic_off[i + 1] = out->pic_off[i] + j.pic_count[i];
+        if (out->pic_off[count] > out->words_capacity)
+            rc = sfail(s, MVG_FAILURE, "mvf_parse_pictures_packed: %llu words needed, capacity %zu",
+                       (unsigned long long)out->pic_off[count], out->words_capacity);
+        else
+            for (int i = 0; i < count; i++)
+                memcpy(out->words + out->pic_off[i], j.pic_words[i], (size_t)j.pic_count[i] * sizeof(uint16_t));
     }
-    pthread_mutex_destroy(&j.mu);
-    if (j.rc != MVG_SUCCESS) memcpy(s->err, j.err, sizeof j.err);
-    return j.rc;
+    for (int i = 0; i < count; i++) free(j.pic_words[i]);
+    free(j.pic_words); free(j.pic_count);
+    return rc;
 }

@@ -6,7 +6,8 @@
  *                  [-s scale] [-d device] [-t threads] [-b batch]
  *
  * Annex-B file -> mvf_open_annexb() -> mvf_select_idr() (demuxer/filter.c semantics) ->
- * mvf_parse_pictures() (threaded CAVLC) -> mvg_decode_host() (pinned copies + kernels 1-3) -> picture
+ * mvf_parse_pictures_packed() (threaded CAVLC, packed levels) -> mvg_decode_host_packed() (pinned copies +
+ * kernels 0-4) -> picture
  * files named like export_idr() names them (export.c:627-642,:704-705): <input base name>[_<k>].<ext>
  * with k counting exported pictures when more than one was requested.  File contents are byte-identical
  * to the reference's: planar I420 (export.c:100-151), 24-bit bottom-up BMP and run-length TGA as
@@ -182,15 +183,20 @@ int main(int argc, char **argv)
         return 1;
     }
     const size_t N = (size_t)info.width_mbs * info.height_mbs, nb = N * (size_t)batch;
-    mvf_batch pb;
+    /* parsed pictures travel in the packed transfer format (mvgpu.h): a fifth of the dense levels on the bus */
+    mvf_packed_batch pb;
     pb.n_pics = 0;
     pb.mb_kind = mvg_host_alloc(nb); pb.i16_mode = mvg_host_alloc(nb); pb.chroma_mode = mvg_host_alloc(nb);
-    pb.qp_y = mvg_host_alloc(nb); pb.cbp = mvg_host_alloc(nb); pb.luma_modes = mvg_host_alloc(nb * 16);
-    pb.coeff = mvg_host_alloc(nb * 768);
+    pb.qp_y = mvg_host_alloc(nb); pb.luma_modes = mvg_host_alloc(nb * 16);
+    pb.nz_blocks = mvg_host_alloc(nb * sizeof(uint32_t)); pb.word_off = mvg_host_alloc(nb * sizeof(uint32_t));
+    pb.pic_off = mvg_host_alloc(((size_t)batch + 1) * sizeof(uint64_t));
+    pb.words_capacity = nb * MVG_PACKED_WORDS_PER_MB;
+    pb.words = mvg_host_alloc(pb.words_capacity * sizeof(uint16_t));
     const int ow = W / scale, oh = H / scale;
     const size_t yuv_sz = (size_t)W * H * 3 / 2, rgb_sz = (size_t)ow * oh * 3;
     uint8_t *out = mvg_host_alloc((fmt == FMT_YUV420 ? yuv_sz : rgb_sz) * (size_t)batch);
-    if (!pb.mb_kind || !pb.i16_mode || !pb.chroma_mode || !pb.qp_y || !pb.cbp || !pb.luma_modes || !pb.coeff || !out) {
+    if (!pb.mb_kind || !pb.i16_mode || !pb.chroma_mode || !pb.qp_y || !pb.luma_modes || !pb.nz_blocks || !pb.word_off ||
+        !pb.pic_off || !pb.words || !out) {
         fprintf(stderr, "mv_thumbnailer: pinned host allocation failed\n");
         return 1;
     }
@@ -206,12 +212,13 @@ int main(int argc, char **argv)
     int exported = 0, rc = 0;
     for (int done = 0; done < n_sel && !rc; done += batch) {
         int cnt = n_sel - done < batch ? n_sel - done : batch;
-        if (mvf_parse_pictures(st, sel + done, 0, cnt, &pb, threads) != MVG_SUCCESS) {
+        if (mvf_parse_pictures_packed(st, sel + done, 0, cnt, &pb, threads) != MVG_SUCCESS) {
             fprintf(stderr, "mv_thumbnailer: %s\n", mvf_last_error(st));
             rc = 1; break;
         }
-        mvg_batch gb = { cnt, pb.mb_kind, pb.i16_mode, pb.chroma_mode, pb.qp_y, pb.cbp, pb.luma_modes, pb.coeff };
-        int ok = fmt == FMT_YUV420 ? mvg_decode_host(ctx, &gb, out, NULL, 0) : mvg_decode_host(ctx, &gb, NULL, out, scale);
+        mvg_packed_batch gb = { cnt, pb.mb_kind, pb.i16_mode, pb.chroma_mode, pb.qp_y, pb.luma_modes,
+                                pb.nz_blocks, pb.word_off, pb.pic_off, pb.words };
+        int ok = fmt == FMT_YUV420 ? mvg_decode_host_packed(ctx, &gb, out, NULL, 0) : mvg_decode_host_packed(ctx, &gb, NULL, out, scale);
         if (ok != MVG_SUCCESS) { fprintf(stderr, "mv_thumbnailer: %s\n", mvg_last_error(ctx)); rc = 1; break; }
         for (int k = 0; k < cnt && !rc; k++) {
             char path[PATH_MAX];
@@ -226,7 +233,8 @@ int main(int argc, char **argv)
     }
     printf("mv_thumbnailer: %d picture(s) exported\n", exported);
     mvg_host_free(pb.mb_kind); mvg_host_free(pb.i16_mode); mvg_host_free(pb.chroma_mode); mvg_host_free(pb.qp_y);
-    mvg_host_free(pb.cbp); mvg_host_free(pb.luma_modes); mvg_host_free(pb.coeff); mvg_host_free(out);
+    mvg_host_free(pb.luma_modes); mvg_host_free(pb.nz_blocks); mvg_host_free(pb.word_off); mvg_host_free(pb.pic_off);
+    mvg_host_free(pb.words); mvg_host_free(out);
     mvg_destroy(ctx);
     mvf_close(st);
     free(sel); free(data);

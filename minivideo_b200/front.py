@@ -26,6 +26,14 @@ class FrontBatch(C.Structure):
                 ("luma_modes", C.c_void_p), ("coeff", C.c_void_p)]
 
 
+class FrontPackedBatch(C.Structure):
+    """mvf_packed_batch of include/mvfront.h."""
+    _fields_ = [("n_pics", C.c_int32), ("mb_kind", C.c_void_p), ("i16_mode", C.c_void_p),
+                ("chroma_mode", C.c_void_p), ("qp_y", C.c_void_p), ("luma_modes", C.c_void_p),
+                ("nz_blocks", C.c_void_p), ("word_off", C.c_void_p), ("pic_off", C.c_void_p),
+                ("words", C.c_void_p), ("words_capacity", C.c_size_t)]
+
+
 class FrontError(RuntimeError):
     def __init__(self, msg, code):
         super().__init__(msg)
@@ -48,6 +56,7 @@ def lib():
         _LIB.mvf_get_info.argtypes = [vp, C.POINTER(Info)]
         _LIB.mvf_select_idr.argtypes = [vp, C.c_int, C.c_int, vp]
         _LIB.mvf_parse_pictures.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(FrontBatch), C.c_int]
+        _LIB.mvf_parse_pictures_packed.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(FrontPackedBatch), C.c_int]
     return _LIB
 
 
@@ -109,3 +118,28 @@ class Stream:
                   a["qp_y"], a["cbp"], a["luma_modes"], a["coeff"],
                   cb_qp_offset=self.info.cb_qp_offset, cr_qp_offset=self.info.cr_qp_offset)
         return soa
+
+    def parse_packed(self, first: int = 0, count: int | None = None, indices=None, n_threads: int | None = None,
+                     words_capacity: int | None = None) -> dict:
+        """CAVLC-parse pictures straight into the packed transfer format (mvf_parse_pictures_packed).
+        Returns the arrays of mvg_packed_batch as a dict (plus n_pics, n_mbs)."""
+        if indices is not None:
+            indices = np.ascontiguousarray(indices, np.int32)
+            count = len(indices)
+        elif count is None:
+            count = self.n_idr - first
+        N = self.info.width_mbs * self.info.height_mbs
+        n = N * count
+        cap = words_capacity if words_capacity is not None else n * 408
+        a = dict(mb_kind=np.zeros(n, np.uint8), i16_mode=np.zeros(n, np.uint8), chroma_mode=np.zeros(n, np.uint8),
+                 qp_y=np.zeros(n, np.int8), luma_modes=np.zeros((n, 16), np.uint8), nz_blocks=np.zeros(n, np.uint32),
+                 word_off=np.zeros(n, np.uint32), pic_off=np.zeros(count + 1, np.uint64), words=np.zeros(max(cap, 1), np.uint16))
+        b = FrontPackedBatch(count, *(a[k].ctypes.data for k in ("mb_kind", "i16_mode", "chroma_mode", "qp_y", "luma_modes",
+                                                                  "nz_blocks", "word_off", "pic_off", "words")), cap)
+        rc = self._lib.mvf_parse_pictures_packed(self.handle, indices.ctypes.data if indices is not None else None, first,
+                                                 count, C.byref(b), n_threads or os.cpu_count() or 1)
+        if rc != 1:
+            raise FrontError(self._lib.mvf_last_error(self.handle).decode(), rc)
+        a["words"] = a["words"][: max(int(a["pic_off"][count]), 1)]
+        a["n_pics"], a["n_mbs"] = count, N
+        return a

@@ -95,3 +95,23 @@ def test_packed_decode_rejects_bad_batches():
     with pytest.raises(api.MvgError, match="impossible word count"):
         ctx.decode_host_packed(pk, None, out, 1)
     ctx.close()
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_front_end_emits_the_same_packed_batch_as_the_packer(threads):
+    """mvf_parse_pictures_packed(stream) == mvg_pack_batch(mvf_parse_pictures(stream)), array by array."""
+    from minivideo_b200 import api, front, synth
+    stream, soa = synth.generate(5, width_mbs=9, height_mbs=6, profile_idc=100, transform8x8=1, scaling_lists=1, seed=321)
+    st = front.Stream(stream)
+    got = st.parse_packed(n_threads=threads)
+    want = api.Packed(st.parse())
+    for k in ("mb_kind", "i16_mode", "chroma_mode", "qp_y", "luma_modes", "nz_blocks", "word_off", "pic_off"):
+        assert np.array_equal(got[k], getattr(want, k)), k
+    n = int(want.pic_off[-1])
+    assert np.array_equal(got["words"][:n], want.words[:n])
+    # sub-range with explicit indices, and the capacity check
+    sub = st.parse_packed(indices=[3, 0], n_threads=threads)
+    w2 = api.Packed(st.parse(indices=[3, 0]))
+    assert np.array_equal(sub["words"][: int(w2.pic_off[-1])], w2.words[: int(w2.pic_off[-1])])
+    with pytest.raises(front.FrontError, match="capacity"):
+        st.parse_packed(words_capacity=10)
