@@ -442,6 +442,11 @@ typedef struct {
     uint8_t *tot_luma, *tot_chroma[2];
     int8_t *mode_grid;
     char err[200];
+    /* packed output: levels of the macroblock being parsed, and the words of the picture so far */
+    int packed;
+    int16_t mb_levels[384];
+    uint32_t *pk_nzb, *pk_off;          /* [N] of the output slot */
+    uint16_t *pk_words; size_t pk_n, pk_cap;
 } worker_t;
 
 static inline int blk_x(int blk) { return (blk & 1) + 2 * ((blk >> 2) & 1); }
@@ -521,6 +526,8 @@ static int read_residual_block(br_t *b, int *coef, int max_num, int nC)
 
 static inline int16_t clamp16(int v) { return (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
 
+static int pack_mb(worker_t *w, size_t m);
+
 static int wfail(worker_t *w, int code, const char *fmt, ...)
 {
     va_list ap;
@@ -573,7 +580,7 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
     for (int my = 0; my < H; my++)
         for (int mx = 0; mx < W; mx++) {
             const size_t mbi = pic_slot * N + (size_t)my * W + mx;
-            int16_t *cf = out->coeff + mbi * 384;
+            int16_t *cf = w->packed ? w->mb_levels : out->coeff + mbi * 384;
             uint8_t *modes = out->luma_modes + mbi * 16;
             memset(cf, 0, 768);
             memset(modes, 0, 16);
@@ -662,7 +669,8 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
             out->i16_mode[mbi] = (uint8_t)i16_mode;
             out->chroma_mode[mbi] = (uint8_t)chroma_mode;
             out->qp_y[mbi] = (int8_t)qp;
-            out->cbp[mbi] = (uint8_t)(cbp_c << 4 | cbp_l);
+            if (out->cbp) out->cbp[mbi] = (uint8_t)(cbp_c << 4 | cbp_l);
+            if (w->packed && !pack_mb(w, (size_t)my * W + mx)) return wfail(w, MVG_FAILURE, "picture %d: out of memory while packing", idr_index);
             if (br_overrun(&b)) return wfail(w, MVG_FAILURE, "picture %d: slice data ends at macroblock %d of %zu", idr_index, my * W + mx, N);
             continue;
         bad_block:
@@ -680,44 +688,39 @@ typedef struct {
     uint16_t **pic_words; uint64_t *pic_count;
 } job_t;
 
-/* one parsed picture (dense, in the worker's scratch) -> packed arrays of output slot i; the words go to a
- * buffer of their own, stitched together once every picture's size is known */
-static int pack_picture(const mvf_batch *d, size_t N, const mvf_packed_batch *pk, size_t i, uint16_t **words_out, uint64_t *count_out)
+/* the 384 levels of one macroblock -> chunk bitmap, masks and non-zero levels appended to the worker's words */
+static int pack_mb(worker_t *w, size_t m)
 {
-    memcpy(pk->mb_kind + i * N, d->mb_kind, N);
-    memcpy(pk->i16_mode + i * N, d->i16_mode, N);
-    memcpy(pk->chroma_mode + i * N, d->chroma_mode, N);
-    memcpy(pk->qp_y + i * N, d->qp_y, N);
-    memcpy(pk->luma_modes + i * N * 16, d->luma_modes, N * 16);
-    size_t cap = N * 64, n = 0;
-    uint16_t *w = malloc(cap * sizeof *w);
-    if (!w) return 0;
-    for (size_t m = 0; m < N; m++) {
-        const int16_t *c = d->coeff + m * 384;
-        if (n + MVG_PACKED_WORDS_PER_MB > cap) {
-            cap = cap * 2 + MVG_PACKED_WORDS_PER_MB;
-            uint16_t *w2 = realloc(w, cap * sizeof *w);
-            if (!w2) { free(w); return 0; }
-            w = w2;
-        }
-        uint32_t nzb = 0;
-        uint16_t masks[24];
-        int n_coded = 0;
-        for (int b = 0; b < 24; b++) {
-            unsigned mask = 0;
-            for (int k = 0; k < 16; k++) mask |= (unsigned)(c[b * 16 + k] != 0) << k;
-            if (mask) { nzb |= 1u << b; masks[n_coded++] = (uint16_t)mask; }
-        }
-        pk->nz_blocks[i * N + m] = nzb;
-        pk->word_off[i * N + m] = (uint32_t)n;
-        memcpy(w + n, masks, (size_t)n_coded * sizeof *w);
-        n += (size_t)n_coded;
-        for (int b = 0; b < 24; b++)
-            if ((nzb >> b) & 1u)
-                for (int k = 0; k < 16; k++)
-                    if (c[b * 16 + k]) w[n++] = (uint16_t)c[b * 16 + k];
+    if (w->pk_n + MVG_PACKED_WORDS_PER_MB > w->pk_cap) {
+        size_t cap = w->pk_cap * 2 + 64 * MVG_PACKED_WORDS_PER_MB;
+        uint16_t *w2 = realloc(w->pk_words, cap * sizeof *w2);
+        if (!w2) return 0;
+        w->pk_words = w2; w->pk_cap = cap;
     }
-    *words_out = w; *count_out = n;
+    const int16_t *c = w->mb_levels;
+    uint16_t *dst = w->pk_words + w->pk_n, *lv;
+    uint32_t nzb = 0;
+    uint16_t masks[24];
+    int n_coded = 0;
+    for (int b = 0; b < 24; b++) {
+        uint64_t q[4];
+        memcpy(q, c + b * 16, 32);
+        if (!(q[0] | q[1] | q[2] | q[3])) continue;
+        unsigned mask = 0;
+        for (int k = 0; k < 16; k++) mask |= (unsigned)(c[b * 16 + k] != 0) << k;
+        nzb |= 1u << b;
+        masks[n_coded++] = (uint16_t)mask;
+    }
+    w->pk_nzb[m] = nzb;
+    w->pk_off[m] = (uint32_t)w->pk_n;
+    memcpy(dst, masks, (size_t)n_coded * sizeof *dst);
+    lv = dst + n_coded;
+    for (int b = 0, i = 0; b < 24; b++)
+        if ((nzb >> b) & 1u) {
+            unsigned mask = masks[i++];
+            while (mask) { int k = __builtin_ctz(mask); mask &= mask - 1; *lv++ = (uint16_t)c[b * 16 + k]; }
+        }
+    w->pk_n = (size_t)(lv - w->pk_words);
     return 1;
 }
 
@@ -731,12 +734,12 @@ static void *worker_main(void *arg)
     w.s = s;
     w.tot_luma = malloc(N * 16); w.tot_chroma[0] = malloc(N * 4); w.tot_chroma[1] = malloc(N * 4);
     w.mode_grid = malloc(N * 16);
-    mvf_batch scratch;                                      /* one dense picture, packed output only */
-    memset(&scratch, 0, sizeof scratch);
+    mvf_batch view;                                         /* packed output: the small arrays of the output batch */
+    memset(&view, 0, sizeof view);
     if (j->pk) {
-        scratch.mb_kind = malloc(N); scratch.i16_mode = malloc(N); scratch.chroma_mode = malloc(N);
-        scratch.qp_y = malloc(N); scratch.cbp = malloc(N); scratch.luma_modes = malloc(N * 16);
-        scratch.coeff = malloc(N * 768);
+        w.packed = 1;
+        view.mb_kind = j->pk->mb_kind; view.i16_mode = j->pk->i16_mode; view.chroma_mode = j->pk->chroma_mode;
+        view.qp_y = j->pk->qp_y; view.luma_modes = j->pk->luma_modes;
     }
     for (;;) {
         pthread_mutex_lock(&j->mu);
@@ -745,9 +748,15 @@ static void *worker_main(void *arg)
         if (i >= j->count) break;
         int idx = j->indices ? j->indices[i] : j->first + i;
         int rc = (idx < 0 || idx >= s->n_idr) ? wfail(&w, MVG_FAILURE, "IDR index %d out of range (0..%d)", idx, s->n_idr - 1)
-                                              : parse_picture(&w, idx, j->pk ? &scratch : j->out, j->pk ? 0 : (size_t)i);
-        if (rc == MVG_SUCCESS && j->pk && !pack_picture(&scratch, N, j->pk, (size_t)i, &j->pic_words[i], &j->pic_count[i]))
-            rc = wfail(&w, MVG_FAILURE, "picture %d: out of memory while packing", idx);
+                                              : 1;
+        if (rc == 1) {
+            if (j->pk) {
+                w.pk_nzb = j->pk->nz_blocks + (size_t)i * N; w.pk_off = j->pk->word_off + (size_t)i * N;
+                w.pk_words = NULL; w.pk_n = 0; w.pk_cap = 0;
+            }
+            rc = parse_picture(&w, idx, j->pk ? &view : j->out, (size_t)i);
+            if (j->pk) { j->pic_words[i] = w.pk_words; j->pic_count[i] = w.pk_n; }
+        }
         if (rc != MVG_SUCCESS) {
             pthread_mutex_lock(&j->mu);
             if (j->rc == MVG_SUCCESS) { j->rc = rc; memcpy(j->err, w.err, sizeof j->err); }
@@ -755,8 +764,6 @@ static void *worker_main(void *arg)
         }
     }
     free(w.rbsp); free(w.tot_luma); free(w.tot_chroma[0]); free(w.tot_chroma[1]); free(w.mode_grid);
-    free(scratch.mb_kind); free(scratch.i16_mode); free(scratch.chroma_mode); free(scratch.qp_y); free(scratch.cbp);
-    free(scratch.luma_modes); free(scratch.coeff);
     return NULL;
 }
 
