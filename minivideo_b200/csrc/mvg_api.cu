@@ -227,7 +227,7 @@ extern "C" void mvg_build_luts(MvgLuts *out)
         for (int lane = 0; lane < 32; lane++) {
             uint32_t word = 0;
             for (int s = 0; s < 2; s++) {
-                const int x = 2 * (lane & 3) + s, y = lane >> 2;
+                const int x = ((lane >> 3) & 1) * 4 + (lane & 1) * 2 + s, y = (lane >> 4) * 4 + ((lane >> 1) & 3);
                 int idx = MVG_N8_DC, variant = 0;
                 if (mode != 2) {
                     const Taps t = nxn_taps(8, mode, x, y);

@@ -49,7 +49,8 @@ struct MvgMbCtl { uint32_t w0, w1, w2, w3; };
  *   Row 2 (DC) is unused.
  * lut8[mode][lane]: the Intra8x8 predictors read a filtered neighbour line of 32-bit words
  *   {p', f2 = (p'[n]+p'[n+1]+1)>>1, f3 = (p'[n-1]+2p'[n]+p'[n+1]+2)>>2} (n = 0..7 p'[-1,7..0], 8 p'[-1,-1],
- *   9..24 p'[0..15,-1], MVG_N8_DC the DC value).  A lane predicts samples (2*(lane&3) + {0,1}, lane>>2):
+ *   9..24 p'[0..15,-1], MVG_N8_DC the DC value).  A lane predicts two horizontally adjacent samples, x =
+ *   4*((lane>>3)&1) + 2*(lane&1) + {0,1}, y = 4*(lane>>4) + ((lane>>1)&3) (residual word 4*lane of the block):
  *   byte 0 = byte offset of the word of sample 0, byte 1 = its bit shift (0, 8, 16), bytes 2, 3 the same
  *   for sample 1.  The 3- and 2-tap forms of the spec always involve adjacent line entries, and the two
  *   "end" taps (p+3q) are f3 at a line end. */

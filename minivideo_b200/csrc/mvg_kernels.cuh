@@ -564,9 +564,9 @@ struct K2Ctx {
     int r4odd, r4even;          /* residual byte offset relative to the half-0 block, by0 odd / even */
     unsigned h4;                /* tile offset of my block relative to the half-1 block (0 or 4 rows down, 8 left) */
     unsigned m4c, m4b, m4cc;    /* nibbles (bit 0) whose block has no up-right neighbour: always / if !availB / if !availC */
-    /* Intra8x8: lane n = entry n of the neighbour line; samples (2*(lane&3) + {0,1}, lane>>2) */
+    /* Intra8x8: lane n = entry n of the neighbour line; its two samples: see MvgLuts::lut8 */
     int n8tr, n8notr;           /* tile offset of my neighbour sample relative to the block origin */
-    int s8, r8;
+    int s8;
     unsigned fixA, fixB, fixD;  /* bit 2b: next := raw, bit 2b+1: prev := raw in block b when A / B / D is unavailable */
 };
 
@@ -726,7 +726,7 @@ __device__ __forceinline__ void k2_luma8_block(const K2Ctx &c, unsigned modes, u
     const unsigned w0 = *reinterpret_cast<const unsigned *>(n8b + (e & 0xffu)) >> __byte_perm(e, 0, 0x4441);
     const unsigned w1 = *reinterpret_cast<const unsigned *>(n8b + __byte_perm(e, 0, 0x4442)) >> (e >> 24);
     const unsigned pp = __byte_perm(w0, w1, 0x5410) & 0x00ff00ffu;
-    const unsigned r2 = *reinterpret_cast<const unsigned *>(c.resid + B8 * 128 + c.r8);
+    const unsigned r2 = *reinterpret_cast<const unsigned *>(c.resid + B8 * 128 + lane * 4);
     *reinterpret_cast<uint16_t *>(lt + org + c.s8) = (uint16_t)__byte_perm(mvg_add_clip8x2(pp, r2), 0, 0x4420);
     __syncwarp();
 }
@@ -852,9 +852,10 @@ k2_wavefront(K2Params p)
         else if (n == 8) c.n8tr = -MVG_LT_STRIDE - 1;
         else             c.n8tr = -MVG_LT_STRIDE + (n - 9);
         c.n8notr = n > 16 ? -MVG_LT_STRIDE + 7 : c.n8tr;                    /* p[8..15,-1] := p[7,-1] */
-        const int y8 = lane >> 2, x8 = 2 * (lane & 3);
+        /* Intra8x8 samples of a lane: 4x4 sub-block lane>>3, row (lane>>1)&3, pair lane&1, so that the residual of
+         * the pair is the word at 4 * lane of the 8x8 block */
+        const int x8 = ((lane >> 3) & 1) * 4 + (lane & 1) * 2, y8 = (lane >> 4) * 4 + ((lane >> 1) & 3);
         c.s8 = y8 * MVG_LT_STRIDE + x8;
-        c.r8 = (((y8 >> 2) * 2 + (x8 >> 2)) * 16 + (y8 & 3) * 4 + (x8 & 3)) * 2;
         /* replicate at the corner: block 0 sees A, B, D of the macroblock; block 1: left = block 0, up and
          * up-left from B; block 2: up = block 0, left and up-left from A */
         c.fixA = lane == 7 ? 0x10u : lane == 8 ? 0x22u : lane == 9 ? 0x20u : 0u;
