@@ -80,12 +80,19 @@ def build_gpu(force: bool = False) -> Path:
 
 
 def build_thumbnailer(force: bool = False) -> Path:
-    """mv_thumbnailer: the CLI over libmvfront.so + libmvgpu.so (mini_thumbnailer-compatible arguments)."""
+    """mv_thumbnailer: the CLI over libmvfront.so + libmvgpu.so (mini_thumbnailer-compatible arguments), and
+    libminivideo_b200.so: the reference's public entry points (minivideo.h) backed by the same core."""
     out = PKG / "mv_thumbnailer"
-    src = [CSRC / "mv_thumbnailer.c", INC / "mvfront.h", INC / "mvgpu.h", PKG / "libmvfront.so", PKG / "libmvgpu.so"]
-    if force or _stale(out, src):
-        _run(["gcc", "-O2", "-Wall", "-Wextra", f"-I{INC}", "-o", str(out), str(src[0]), f"-L{PKG}",
-              "-Wl,-rpath,$ORIGIN", "-lmvfront", "-lmvgpu", "-lstdc++", "-lm", "-lpthread", "-ldl", "-lrt"])
+    core = [CSRC / "mv_thumbcore.c", CSRC / "mv_thumbcore.h", INC / "mvfront.h", INC / "mvgpu.h",
+            PKG / "libmvfront.so", PKG / "libmvgpu.so"]
+    libs = [f"-L{PKG}", "-Wl,-rpath,$ORIGIN", "-lmvfront", "-lmvgpu", "-lstdc++", "-lm", "-lpthread", "-ldl", "-lrt"]
+    if force or _stale(out, core + [CSRC / "mv_thumbnailer.c"]):
+        _run(["gcc", "-O2", "-Wall", "-Wextra", f"-I{INC}", f"-I{CSRC}", "-o", str(out), str(CSRC / "mv_thumbnailer.c"),
+              str(core[0]), *libs])
+    shim = PKG / "libminivideo_b200.so"
+    if force or _stale(shim, core + [CSRC / "minivideo_shim.c"]):
+        _run(["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", f"-I{INC}", f"-I{CSRC}", "-o", str(shim),
+              str(CSRC / "minivideo_shim.c"), str(core[0]), *libs])
     return out
 
 
@@ -107,8 +114,19 @@ def build_reference(force: bool = False) -> Path | None:
     return out
 
 
+def build_shim_cli(force: bool = False) -> Path | None:
+    """The reference's own mini_thumbnailer main.cpp linked against libminivideo_b200.so (only where the
+    reference tree is mounted; the binary lives in oracle/_ref and travels to the GPU box)."""
+    out = ROOT / "oracle" / "_ref" / "mini_thumbnailer_b200"
+    if not (REFERENCE / "mini_thumbnailer" / "src" / "main.cpp").exists():
+        return out if out.exists() else None
+    if force or _stale(out, [PKG / "libminivideo_b200.so", ROOT / "oracle" / "Makefile"]):
+        _run(["make", "-C", str(ROOT / "oracle"), "shimcli", f"REF={REFERENCE}"])
+    return out
+
+
 def build_all(force: bool = False) -> dict:
-    return {
+    out = {
         "synth": build_synth(force),
         "front": build_front(force),
         "oracle": build_oracle(force),
@@ -116,6 +134,8 @@ def build_all(force: bool = False) -> dict:
         "gpu": build_gpu(force),
         "thumbnailer": build_thumbnailer(force),
     }
+    out["shim_cli"] = build_shim_cli(force)
+    return out
 
 
 if __name__ == "__main__":

@@ -28,10 +28,51 @@ def test_cli_builds_and_rejects_bad_arguments(cli):
     assert r.returncode == 1 and "cannot open" in r.stderr
 
 
-def _run_both(stream: bytes, args: list[str], ref_may_crash: bool = False):
+SHIM_CLI = ROOT / "oracle" / "_ref" / "mini_thumbnailer_b200"     # the reference's main.cpp linked against our library
+
+
+def test_drop_in_library_exports_the_reference_entry_points(cli):
+    """libminivideo_b200.so: every function of minivideo/src/minivideo.h:89-149, callable without a GPU
+    up to the point where decoding starts."""
+    import ctypes as C
+    lib = C.CDLL(str(ROOT / "minivideo_b200" / "libminivideo_b200.so"))
+    for name in ("minivideo_print_infos", "minivideo_get_infos", "minivideo_endianness", "minivideo_open",
+                 "minivideo_parse", "minivideo_decode", "minivideo_extract", "minivideo_close"):
+        assert hasattr(lib, name), name
+    assert lib.minivideo_endianness() == 1234
+    media = C.c_void_p()
+    assert lib.minivideo_open(b"/nonexistent.264", C.byref(media)) == 0 and not media
+    from minivideo_b200 import synth
+    stream, _ = synth.generate(1, "cif", seed=3)
+    with tempfile.TemporaryDirectory() as d:
+        for name, parse_ok in (("a.264", 1), ("a.mp4", 0)):
+            (Path(d) / name).write_bytes(stream)
+            assert lib.minivideo_open(str(Path(d) / name).encode(), C.byref(media)) == 1
+            assert lib.minivideo_parse(media, False, True, False) == parse_ok
+            if parse_ok:
+                assert lib.minivideo_decode(media, b"", 3, 75, 1, 0) == 0        # PICTURE_PNG: not supported
+            assert lib.minivideo_close(C.byref(media)) == 1 and not media
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt,n,mode", [("yuv420", 1, "unfiltered"), ("bmp", 3, "unfiltered"), ("tga", 4, "ordered")])
+def test_reference_cli_linked_against_the_drop_in_library(cli, fmt, n, mode):
+    """The reference's own mini_thumbnailer main.cpp, unmodified, linked against libminivideo_b200.so, writes
+    the files the reference build of the same program writes."""
+    from minivideo_b200 import synth
+    if not (SHIM_CLI.exists() and ref.MINI_THUMBNAILER.exists()):
+        pytest.skip("reference CLI builds are not present")
+    stream, _ = synth.generate(9, "cif", seed=905)
+    want, got = _run_both(stream, ["-f", fmt, "-n", str(n), "-e", mode], exes=((ref.MINI_THUMBNAILER, []), (SHIM_CLI, [])))
+    assert sorted(want) == sorted(got) and len(want) == n
+    for name in want:
+        assert want[name] == got[name], name
+
+
+def _run_both(stream: bytes, args: list[str], ref_may_crash: bool = False, exes=None):
     """Run both CLIs in separate scratch directories on the same stream; return {file name: bytes} each."""
     out = []
-    for exe, extra in ((ref.MINI_THUMBNAILER, []), (MV, ["-o", "."])):
+    for exe, extra in (exes or ((ref.MINI_THUMBNAILER, []), (MV, ["-o", "."]))):
         with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
             (Path(d) / "in.264").write_bytes(stream)
             r = subprocess.run([str(exe), "-i", str(Path(d) / "in.264")] + args + extra, capture_output=True, text=True, cwd=d)
