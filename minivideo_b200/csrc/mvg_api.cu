@@ -517,6 +517,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         p.resid = ctx->d_resid; p.ctl = ctx->d_ctl; p.tiles = ctx->d_tiles; p.halo = ctx->d_halo;
         if (++ctx->epoch == 0) ctx->epoch = 1;      /* 0 is the value of never-written words */
         p.epoch = ctx->epoch; p.group = MVG_K2_GROUP; p.stagger = ctx->k2_stagger; p.stats = ctx->d_stats;
+        p.sel[0] = 1u; p.sel[1] = 1u << 8; p.sel[2] = 1u << 16; p.sel[3] = 1u << 24;
         p.work = work; p.luts = ctx->d_luts; p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics;
         const long long items = (long long)n_pics * H;
         const int grid = (int)std::min<long long>((items + K2_WARPS - 1) / K2_WARPS, (long long)ctx->sm_count * ctx->k2_ctas_per_sm);

@@ -490,6 +490,8 @@ struct K2Params {
     int w_mbs, h_mbs, first_slot, n_pics, group;
     int stagger;                /* a row starts once the row above has published this many macroblocks */
     unsigned long long *stats;  /* DEV (-DMVG_K2_PROFILE): cycle accounting, 16 counters */
+    unsigned        sel[4];     /* 1 << 8k: dot-product selectors of byte k; kernel parameters so that they are
+                                   constant-bank operands instead of per-use uniform moves */
 };
 
 #ifdef MVG_K2_PROFILE
@@ -564,6 +566,7 @@ struct K2Ctx {
     int r4odd, r4even;          /* residual byte offset relative to the half-0 block, by0 odd / even */
     unsigned h4;                /* tile offset of my block relative to the half-1 block (0 or 4 rows down, 8 left) */
     unsigned m4c, m4b, m4cc;    /* nibbles (bit 0) whose block has no up-right neighbour: always / if !availB / if !availC */
+    const unsigned *sel;        /* K2Params::sel */
     /* Intra8x8: lane n = entry n of the neighbour line; its two samples: see MvgLuts::lut8 */
     int n8tr, n8notr;           /* tile offset of my neighbour sample relative to the block origin */
     int s8;
@@ -653,8 +656,8 @@ __device__ __forceinline__ void k2_luma4_step(const K2Ctx &c, unsigned seq, bool
             unsigned e;
             asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(m | c.lut4));
             const uint8_t *nb = c.lt + (org1 - MVG_LUT4_BIAS);
-            pred = ((int)nb[__dp4a(e, 0x00000001u, c.h4)] + (int)nb[__dp4a(e, 0x00000100u, c.h4)] +
-                    (int)nb[__dp4a(e, 0x00010000u, c.h4)] + (int)nb[__dp4a(e, 0x01000000u, c.h4)] + 2) >> 2;
+            pred = ((int)nb[__dp4a(e, c.sel[0], c.h4)] + (int)nb[__dp4a(e, c.sel[1], c.h4)] +
+                    (int)nb[__dp4a(e, c.sel[2], c.h4)] + (int)nb[__dp4a(e, c.sel[3], c.h4)] + 2) >> 2;
         }
         const int r = *reinterpret_cast<const int16_t *>(c.resid + blk0 * 32 + ((by0 & 1) ? c.r4odd : c.r4even));
         c.lt[org1 + c.s4] = (uint8_t)mvg_add_clip8(pred, r);
@@ -835,6 +838,7 @@ k2_wavefront(K2Params p)
     K2Ctx c;
     c.lt = s.lt; c.ct = &s.ct[0][0]; c.n8 = s.n8; c.lut8 = reinterpret_cast<const uint8_t *>(&luts->lut8[0][lane]);
     c.lane = lane;
+    c.sel = p.sel;
     c.resid = reinterpret_cast<const uint8_t *>(s.resid[0]);
     {
         const int half = lane >> 4, pix = lane & 15, px = pix & 3, py = pix >> 2;
