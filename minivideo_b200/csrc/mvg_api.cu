@@ -532,8 +532,10 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         const long long threads = rgb_scale == 1 ? (long long)n * 8 * n_pics       /* 8 lanes per macroblock */
                                                  : (long long)(width / rgb_scale) * (height / rgb_scale) * n_pics;
         const int grid = (int)std::min<long long>((threads + 255) / 256, (long long)ctx->sm_count * 32);
+        const bool pow2 = rgb_scale == 2 || rgb_scale == 4 || rgb_scale == 8 || rgb_scale == 16;
         if (rgb_scale == 1) k3_rgb_full<<<grid, 256, 0, st>>>(p);
-        else k3_rgb_scaled<<<grid, 256, 0, st>>>(p);
+        else if (pow2) k3_rgb_scaled<<<(int)std::min<long long>(((long long)n * n_pics + 31) / 32, (long long)ctx->sm_count * 16), 256, 0, st>>>(p);
+        else k3_rgb_scaled_generic<<<grid, 256, 0, st>>>(p);
         launches++;
     }
     if (timed) {

@@ -1152,10 +1152,11 @@ k3_rgb_full(K3Params p)
     }
 }
 
-/* scale s > 1: one thread per output pixel, rounded s x s box average of the
- * full-resolution RGB picture. */
+/* scale s > 1, any s that divides the picture: one thread per output pixel, rounded s x s box average of the
+ * full-resolution RGB picture.  Slow (byte loads); k3_rgb_scaled covers the
+ * power-of-two scales up to 16. */
 __global__ void __launch_bounds__(256)
-k3_rgb_scaled(K3Params p)
+k3_rgb_scaled_generic(K3Params p)
 {
     const int s = p.scale, ow = p.width / s, oh = p.height / s;
     const long long per_pic = (long long)ow * oh, total = per_pic * p.n_pics;
@@ -1183,6 +1184,113 @@ k3_rgb_scaled(K3Params p)
         o[0] = (uint8_t)((aR + area / 2) / area);
         o[1] = (uint8_t)((aG + area / 2) / area);
         o[2] = (uint8_t)((aB + area / 2) / area);
+    }
+}
+
+/* scale s in {2, 4, 8, 16}: rounded s x s box average of the scale-1 RGB picture.
+ * Same staging as k3_rgb_full (32 tiles per CTA in shared memory); a thread then converts one 4x4 cell of a
+ * macroblock -- four 2x2 quads, each with its own chroma sample -- with the int16-pair arithmetic of
+ * k3_rgb_full and keeps per-quad colour sums.  s = 2: a quad is an output pixel; s = 4: the cell is; s = 8, 16:
+ * the cells of an output pixel sit in adjacent lanes (cells are numbered in Z order) and are added with shuffles. */
+__global__ void __launch_bounds__(256)
+k3_rgb_scaled(K3Params p)
+{
+    __shared__ __align__(16) uint8_t s_tiles[K3_MBS * K3_TILE];
+    const int w_mbs = p.width >> 4, h_mbs = p.height >> 4, n_mb = w_mbs * h_mbs;
+    const long long total_mbs = (long long)n_mb * p.n_pics;
+    const long long n_groups = (total_mbs + K3_MBS - 1) / K3_MBS;
+    const int sc = p.scale, ow = p.width / sc, oh = p.height / sc;
+    const int sh = sc == 2 ? 2 : sc == 4 ? 4 : sc == 8 ? 6 : 8;        /* log2(s * s) */
+    const size_t out_pic = (size_t)ow * oh * 3;
+    const uint8_t *tiles = p.tiles + (size_t)p.first_slot * n_mb * 384;
+    uint8_t *rgb = p.rgb + (size_t)p.first_slot * out_pic;
+    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const long long first = g * K3_MBS;
+        const int n_here = (int)min((long long)K3_MBS, total_mbs - first);
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(tiles + (size_t)first * 384);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int ch = threadIdx.x + 256 * k;
+                if (ch < n_here * 24) {
+                    const int t = ch / 24;
+                    *reinterpret_cast<uint4 *>(s_tiles + t * K3_TILE + (ch - t * 24) * 16) = __ldg(src + ch);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int cell = threadIdx.x + 256 * half;              /* 16 cells per macroblock, Z order */
+            const int mbl = cell >> 4, cz = cell & 15;
+            const int cx = (cz & 1) | ((cz >> 1) & 2), cy = ((cz >> 1) & 1) | ((cz >> 2) & 2);
+            const bool live = mbl < n_here;
+            unsigned sumR = 0, sumG = 0, sumB = 0;                  /* s >= 4: int16 pairs {even columns, odd columns} */
+            unsigned q2[2][2][3];                                   /* s == 2: per quad */
+            if (live) {
+                const uint8_t *tile = s_tiles + mbl * K3_TILE;
+                const unsigned cbp = *reinterpret_cast<const uint16_t *>(tile + 256 + (cy * 2) * 8 + cx * 2) |
+                                     (unsigned)*reinterpret_cast<const uint16_t *>(tile + 256 + (cy * 2 + 1) * 8 + cx * 2) << 16;
+                const unsigned crp = *reinterpret_cast<const uint16_t *>(tile + 320 + (cy * 2) * 8 + cx * 2) |
+                                     (unsigned)*reinterpret_cast<const uint16_t *>(tile + 320 + (cy * 2 + 1) * 8 + cx * 2) << 16;
+#pragma unroll
+                for (int qy = 0; qy < 2; qy++) {
+                    /* chroma samples (2cx, 2cy+qy) and (2cx+1, 2cy+qy) as an int16 pair: pixels x and x+2 of a row */
+                    const unsigned cb2 = qy ? mvg_pair_hi(cbp) : mvg_pair_lo(cbp);
+                    const unsigned cr2 = qy ? mvg_pair_hi(crp) : mvg_pair_lo(crp);
+                    const unsigned rC = __vsub2(((cr2 * 204u) >> 7) & 0x01ff01ffu, 0x00de00deu);
+                    const unsigned bC = __vsub2(((cb2 * 129u) >> 6) & 0x03ff03ffu, 0x01140114u);
+                    const unsigned gC = __vsub2(__vsub2(0x00870087u, ((cb2 * 25u) >> 6) & 0x00ff00ffu), ((cr2 * 13u) >> 4) & 0x00ff00ffu);
+                    unsigned aR = 0, aG = 0, aB = 0;                /* halves: quad qx = 0 (pixels 0,1) | quad qx = 1 (pixels 2,3) */
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const unsigned w = *reinterpret_cast<const unsigned *>(tile + (cy * 4 + qy * 2 + r) * 16 + cx * 4);
+                        const unsigned te = ((mvg_pair_even(w) * 149u) >> 7) & 0x01ff01ffu;       /* pixels 0, 2 */
+                        const unsigned to = ((mvg_pair_odd(w) * 149u) >> 7) & 0x01ff01ffu;        /* pixels 1, 3 */
+                        aR += mvg_add_clip8x2(te, rC) + mvg_add_clip8x2(to, rC);
+                        aG += mvg_add_clip8x2(te, gC) + mvg_add_clip8x2(to, gC);
+                        aB += mvg_add_clip8x2(te, bC) + mvg_add_clip8x2(to, bC);
+                    }
+                    q2[qy][0][0] = aR & 0xffffu; q2[qy][1][0] = aR >> 16;
+                    q2[qy][0][1] = aG & 0xffffu; q2[qy][1][1] = aG >> 16;
+                    q2[qy][0][2] = aB & 0xffffu; q2[qy][1][2] = aB >> 16;
+                    sumR += aR; sumG += aG; sumB += aB;
+                }
+            }
+            /* position of the macroblock in the picture */
+            const long long mb = first + mbl;
+            const int pic = (int)(mb / n_mb), rem = (int)(mb - (long long)pic * n_mb), my = rem / w_mbs, mx = rem - my * w_mbs;
+            uint8_t *out = rgb + (size_t)pic * out_pic;
+            if (sc == 2) {
+                if (live) {
+#pragma unroll
+                    for (int qy = 0; qy < 2; qy++)
+#pragma unroll
+                        for (int qx = 0; qx < 2; qx++) {
+                            uint8_t *o = out + ((size_t)(my * 8 + cy * 2 + qy) * ow + mx * 8 + cx * 2 + qx) * 3;
+                            o[0] = (uint8_t)((q2[qy][qx][0] + 2) >> 2);
+                            o[1] = (uint8_t)((q2[qy][qx][1] + 2) >> 2);
+                            o[2] = (uint8_t)((q2[qy][qx][2] + 2) >> 2);
+                        }
+                }
+            } else {
+                unsigned R = (sumR & 0xffffu) + (sumR >> 16), G = (sumG & 0xffffu) + (sumG >> 16), B = (sumB & 0xffffu) + (sumB >> 16);
+                const int span = sc == 4 ? 1 : sc == 8 ? 4 : 16;    /* cells per output pixel: adjacent lanes */
+                for (int o = 1; o < span; o <<= 1) {
+                    R += __shfl_xor_sync(MVG_FULL, R, o); G += __shfl_xor_sync(MVG_FULL, G, o); B += __shfl_xor_sync(MVG_FULL, B, o);
+                }
+                if (live && (cz & (span - 1)) == 0) {
+                    const int per = 16 / sc;                        /* output pixels per macroblock side */
+                    const int ox = sc == 4 ? cx : sc == 8 ? cx >> 1 : 0, oy = sc == 4 ? cy : sc == 8 ? cy >> 1 : 0;
+                    uint8_t *o = out + ((size_t)(my * per + oy) * ow + mx * per + ox) * 3;
+                    const unsigned rnd = 1u << (sh - 1);
+                    o[0] = (uint8_t)((R + rnd) >> sh);
+                    o[1] = (uint8_t)((G + rnd) >> sh);
+                    o[2] = (uint8_t)((B + rnd) >> sh);
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 

@@ -83,6 +83,17 @@ def test_gpu_rgb_downscale_matches_oracle_box_filter(scale):
     assert np.array_equal(got["rgb"], cpu.yuv_to_rgb(want_yuv, soa.width, soa.height, scale))
 
 
+@pytest.mark.parametrize("scale", [3, 6, 12])
+def test_gpu_rgb_downscale_by_other_factors_uses_the_generic_kernel(scale):
+    """Scales that are not a power of two (or exceed 16) go through k3_rgb_scaled_generic."""
+    from minivideo_b200 import api, synth
+    from oracle import cpu
+    _, soa = synth.generate(2, want_stream=False, width_mbs=6, height_mbs=3, profile_idc=100, transform8x8=1, seed=72)
+    want_yuv, _ = cpu.reconstruct(soa)
+    got = api.reconstruct(soa, rgb_scale=scale)
+    assert np.array_equal(got["rgb"], cpu.yuv_to_rgb(want_yuv, soa.width, soa.height, scale))
+
+
 def test_full_size_batch_properties_1080p():
     """BASELINE-size property checks (the oracle would take minutes on this many pictures):
     a batch built from 4 distinct pictures cloned into 96 slots reconstructs every clone to the
