@@ -75,30 +75,38 @@ static void build_luts(void)
 
 typedef struct { const uint8_t *p; size_t pos, nbits; } br_t;
 
-static inline uint32_t br_peek(const br_t *b, int n)      /* n <= 25 */
+/* 57 bits starting at the read position, left-aligned in 64: one unaligned load and a byte swap */
+static inline uint64_t br_window(const br_t *b)
 {
-    const uint8_t *q = b->p + (b->pos >> 3);
-    uint32_t w = (uint32_t)q[0] << 24 | (uint32_t)q[1] << 16 | (uint32_t)q[2] << 8 | q[3];
-    return (w << (b->pos & 7)) >> (32 - n);
+    uint64_t w;
+    memcpy(&w, b->p + (b->pos >> 3), 8);
+    return __builtin_bswap64(w) << (b->pos & 7);
+}
+static inline uint32_t br_peek(const br_t *b, int n)      /* 1 <= n <= 32 */
+{
+    return (uint32_t)(br_window(b) >> (64 - n));
 }
 static inline void br_skip(br_t *b, int n) { b->pos += (size_t)n; }
 static inline uint32_t br_get(br_t *b, int n)
 {
     if (n == 0) return 0;
-    uint32_t v;
-    if (n <= 25) { v = br_peek(b, n); b->pos += (size_t)n; return v; }
-    v = br_peek(b, 16); b->pos += 16;
-    v = (v << (n - 16)) | br_peek(b, n - 16); b->pos += (size_t)(n - 16);
+    const uint32_t v = br_peek(b, n);
+    b->pos += (size_t)n;
     return v;
 }
 static inline int br_bit(br_t *b) { return (int)br_get(b, 1); }
+/* number of leading zero bits at the read position, capped at 32 */
+static inline int br_zeros(const br_t *b)
+{
+    const uint32_t w = (uint32_t)(br_window(b) >> 32);
+    return w ? __builtin_clz(w) : 32;
+}
 static uint32_t br_ue(br_t *b)
 {
-    int z = 0;
-    while (z < 32 && b->pos < b->nbits + 64 && br_peek(b, 1) == 0) { z++; b->pos++; }
-    b->pos++;
+    const int z = br_zeros(b);
+    if (z >= 32) { b->pos += 33; return 0xffffffffu; }
+    b->pos += (size_t)z + 1;
     if (z == 0) return 0;
-    if (z >= 32) return 0xffffffffu;
     return (1u << z) - 1 + br_get(b, z);
 }
 static int br_se(br_t *b)
@@ -484,10 +492,9 @@ static int read_residual_block(br_t *b, int *coef, int max_num, int nC)
     int suffix_len = (tc > 10 && t1 < 3) ? 1 : 0;
     for (int i = 0; i < tc; i++) {
         if (i < t1) { level[i] = br_bit(b) ? -1 : 1; continue; }
-        int prefix = 0;
-        while (prefix < 32 && br_peek(b, 1) == 0) { prefix++; br_skip(b, 1); }
-        br_skip(b, 1);
+        const int prefix = br_zeros(b);
         if (prefix >= 32) return -1;
+        br_skip(b, prefix + 1);
         int code = (prefix < 15 ? prefix : 15) << suffix_len;           /* 9.2.2.1 */
         int ssize = suffix_len;
         if (prefix == 14 && suffix_len == 0) ssize = 4;
