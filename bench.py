@@ -260,6 +260,46 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_dense_s = time.perf_counter() - t0
 
+    # ---- from the bitstream: Annex-B bytes -> host front end (CAVLC on all host cores, packed output into pinned
+    # memory) -> mvg_decode_host_packed -> RGB24 in pinned host memory.  Same input and output as the reference
+    # arm (which times minivideo_decode() on the same kind of stream); bound by the host's entropy decoding.
+    stream_e2e = None
+    if rank == 0 and args.stream_frames > 0:
+        import ctypes as C
+        from minivideo_b200 import front
+        S = min(args.stream_frames, F)
+        stream, _ = synth.generate(S, "1080p", want_soa=False, seed=0xC0FFEE + 2)
+        st = front.Stream(stream)
+        ls4, ls8 = st.level_scale()
+        ctx.set_sps(st.info.width_mbs, st.info.height_mbs, ls4, ls8, st.info.cb_qp_offset, st.info.cr_qp_offset)
+        cap = S * N * 160                                       # words; ~5x what this stream needs
+        pk = {"mb_kind": api.PinnedArray((S * N,), np.uint8), "i16_mode": api.PinnedArray((S * N,), np.uint8),
+              "chroma_mode": api.PinnedArray((S * N,), np.uint8), "qp_y": api.PinnedArray((S * N,), np.int8),
+              "luma_modes": api.PinnedArray((S * N, 16), np.uint8), "nz_blocks": api.PinnedArray((S * N,), np.uint32),
+              "word_off": api.PinnedArray((S * N,), np.uint32), "pic_off": api.PinnedArray((S + 1,), np.uint64),
+              "words": api.PinnedArray((cap,), np.uint16)}
+        order = ("mb_kind", "i16_mode", "chroma_mode", "qp_y", "luma_modes", "nz_blocks", "word_off", "pic_off", "words")
+        fb = front.FrontPackedBatch(S, *(pk[k].ptr for k in order), cap)
+        gb = api.PackedBatch(S, *(pk[k].ptr for k in order))
+        out_s = api.PinnedArray((S, rgb_px), np.uint8)
+        threads = os.cpu_count() or 1
+        flib = front.lib()
+
+        def one_pass():
+            rc = flib.mvf_parse_pictures_packed(st.handle, None, 0, S, C.byref(fb), threads)
+            if rc != 1:
+                raise RuntimeError(flib.mvf_last_error(st.handle).decode())
+            ctx._ck(ctx.lib.mvg_decode_host_packed(ctx.handle, C.byref(gb), None, out_s.ptr, scale))
+        one_pass()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            one_pass()
+        dt = time.perf_counter() - t0
+        stream_e2e = {"value": S * args.steps / dt, "unit": UNIT, "pictures_per_step": S, "host_threads": threads,
+                      "stream_bytes_per_picture": len(stream) // S,
+                      "path": "Annex-B bytes -> mvf_parse_pictures_packed (CAVLC on the host cores) -> mvg_decode_host_packed -> RGB24; "
+                              "parse and GPU are not overlapped; one GPU, rank 0 only"}
+
     # ---- reduce over ranks (max time), rank 0 reports
     times = torch.tensor([dev_ms, wall_ms, e2e_s * 1e3, e2e_dense_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -297,6 +337,7 @@ def run_ours(args):
                     "path": "mvg_decode_host_packed: pinned host packed SoA (sparse levels) -> H2D -> k0 expand, k1, k2, k3 -> D2H RGB24",
                     "dense": {"value": world * E * args.steps / (e2e_dense_ms * 1e-3), "h2d_bytes_per_step": h2d_dense,
                               "path": "mvg_decode_host: dense int16[384] levels per macroblock"}},
+            "stream_e2e": stream_e2e,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": {"k1": "k1_dequant_idct", "k2": "k2_wavefront", "k3": "k3_rgb"}[dom],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -330,6 +371,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=32, help="distinct pictures generated on the host per GPU")
     ap.add_argument("--rgb-scale", type=int, default=1, help="RGB thumbnail downscale factor (1 = the reference's mb_to_rgb)")
     ap.add_argument("--e2e-frames", type=int, default=384, help="pictures per end-to-end step per GPU")
+    ap.add_argument("--stream-frames", type=int, default=64, help="pictures of the bitstream-to-RGB measurement (0 = skip)")
     ap.add_argument("--ref-pics", type=int, default=6, help="pictures each host core decodes in the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
