@@ -173,6 +173,12 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    try:        # run this rank (and allocate its pinned buffers) on the host cores next to its GPU
+        import pynvml as nv
+        nv.nvmlInit()
+        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

@@ -30,7 +30,6 @@ static char g_create_error[512] = "";
 struct mvg_ctx {
     int device = -1, sm_count = 0;
     int k1_ctas_per_sm = 1, k2_ctas_per_sm = 1;
-    int k2_stagger = 0;              /* macroblocks a row keeps behind the row above when it starts */
     int max_w = 0, max_h = 0, max_pics = 0;
     int w_mbs = 0, h_mbs = 0;
     bool have_sps = false;
@@ -280,8 +279,6 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     TRY("occupancy k1", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_ctas_per_sm, k1_dequant_idct, K1_WARPS * 32, 0));
     TRY("k2 shared memory", cudaFuncSetAttribute(k2_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM_BYTES));
     TRY("occupancy k2", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2_ctas_per_sm, k2_wavefront, K2_WARPS * 32, K2_SMEM_BYTES));
-    if (const char *e = getenv("MVG_K2_STAGGER")) ctx->k2_stagger = atoi(e);
-    if (const char *e = getenv("MVG_K2_CTAS")) { const int v = atoi(e); if (v >= 1 && v < ctx->k2_ctas_per_sm) ctx->k2_ctas_per_sm = v; }   /* dev */
     if (ctx->k1_ctas_per_sm < 1 || ctx->k2_ctas_per_sm < 1) return bail("kernel does not fit on an SM", cudaErrorLaunchOutOfResources);
     TRY("stream", cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     TRY("stream", cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
@@ -516,7 +513,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         K2Params p;
         p.resid = ctx->d_resid; p.ctl = ctx->d_ctl; p.tiles = ctx->d_tiles; p.halo = ctx->d_halo;
         if (++ctx->epoch == 0) ctx->epoch = 1;      /* 0 is the value of never-written words */
-        p.epoch = ctx->epoch; p.group = MVG_K2_GROUP; p.stagger = ctx->k2_stagger; p.stats = ctx->d_stats;
+        p.epoch = ctx->epoch; p.group = MVG_K2_GROUP; p.stats = ctx->d_stats;
         p.sel[0] = 1u; p.sel[1] = 1u << 8; p.sel[2] = 1u << 16; p.sel[3] = 1u << 24;
         p.work = work; p.luts = ctx->d_luts; p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics;
         const long long items = (long long)n_pics * H;

@@ -488,7 +488,6 @@ struct K2Params {
     const MvgLuts  *luts;
     unsigned        epoch;      /* flag value that marks halo words of THIS launch */
     int w_mbs, h_mbs, first_slot, n_pics, group;
-    int stagger;                /* a row starts once the row above has published this many macroblocks */
     unsigned long long *stats;  /* DEV (-DMVG_K2_PROFILE): cycle accounting, 16 counters */
     unsigned        sel[4];     /* 1 << 8k: dot-product selectors of byte k; kernel parameters so that they are
                                    constant-bank operands instead of per-use uniform moves */
@@ -924,19 +923,6 @@ k2_wavefront(K2Params p)
         const int hwords = W * 8;                               /* halo words of a macroblock row */
         uint2 qa = make_uint2(0, epoch), qb = make_uint2(0, epoch);
         if (availB) {
-            if (p.stagger > 1) {
-                /* keep rows of one picture apart: a row that runs two macroblocks behind the row above waits
-                 * on every macroblock and inherits all of its stalls */
-                const uint2 *far = ha_run + (size_t)(min(p.stagger, W) - 1) * 8;
-                uint2 t = make_uint2(0, epoch);
-                if (lane < 8) t = mvg_ld_relaxed_u64(far);
-                unsigned ns = 256;
-                while (!__all_sync(MVG_FULL, t.y == epoch)) {
-                    __nanosleep(ns);
-                    if (ns < 4096) ns *= 2;
-                    if (lane < 8) t = mvg_ld_relaxed_u64(far);
-                }
-            }
             if (lane < hwords) qb = mvg_ld_relaxed_u64(ha_run);     /* becomes qa at macroblock 0 */
         }
         unsigned okA = 0;
