@@ -725,6 +725,7 @@ extern "C" int mvg_pack_batch(const int16_t *coeff, int n_pics, int n_mbs, uint3
                               uint64_t *pic_off, uint16_t *words, size_t words_capacity, int n_threads)
 {
     if (!coeff || !nz_blocks || !word_off || !pic_off || !words || n_pics < 1 || n_mbs < 1) return MVG_FAILURE;
+    try {               /* allocation or thread creation may throw: nothing may unwind through the C ABI */
     /* pass 1 (threaded over pictures): chunk bitmaps and per-macroblock sizes -> offsets inside the picture */
     std::vector<uint64_t> pic_words((size_t)n_pics);
     auto pass1 = [&](int p) {
@@ -774,6 +775,9 @@ extern "C" int mvg_pack_batch(const int16_t *coeff, int n_pics, int n_mbs, uint3
     for (int p = 0; p < n_pics; p++) pic_off[p + 1] = pic_off[p] + pic_words[(size_t)p];
     if (pic_off[n_pics] > words_capacity) return MVG_FAILURE;
     run(pass2);
+    } catch (...) {
+        return MVG_FAILURE;
+    }
     return MVG_SUCCESS;
 }
 
@@ -794,12 +798,12 @@ extern "C" int mvg_decode_host_packed(mvg_ctx *ctx, const mvg_packed_batch *b, u
         CK(ctx, cudaMalloc((void **)&ctx->d_nzb, cap * sizeof(uint32_t)));
         CK(ctx, cudaMalloc((void **)&ctx->d_woff, cap * sizeof(uint32_t)));
         CK(ctx, cudaMalloc((void **)&ctx->d_words, cap * MVG_PACKED_WORDS_PER_MB * sizeof(uint16_t)));
-        CK(ctx, cudaMalloc((void **)&ctx->d_picbase, (size_t)ctx->max_pics * sizeof(uint64_t)));
+        CK(ctx, cudaMalloc((void **)&ctx->d_picbase, ((size_t)ctx->max_pics * 2 + 2) * sizeof(uint64_t)));
     }
     if (b->n_pics > ctx->h_picbase_cap) {
         if (ctx->h_picbase) cudaFreeHost(ctx->h_picbase);
         ctx->h_picbase = nullptr; ctx->h_picbase_cap = 0;
-        CK(ctx, cudaHostAlloc((void **)&ctx->h_picbase, (size_t)b->n_pics * sizeof(uint64_t), cudaHostAllocDefault));
+        CK(ctx, cudaHostAlloc((void **)&ctx->h_picbase, ((size_t)b->n_pics * 2 + 2) * sizeof(uint64_t), cudaHostAllocDefault));
         ctx->h_picbase_cap = b->n_pics;
     }
     for (int p = 0; p < b->n_pics; p++)
@@ -818,15 +822,17 @@ extern "C" int mvg_decode_host_packed(mvg_ctx *ctx, const mvg_packed_batch *b, u
         const uint64_t w0 = b->pic_off[done], w1 = b->pic_off[done + cnt], base = (uint64_t)o * MVG_PACKED_WORDS_PER_MB;
         if (w1 > w0)
             CK(ctx, cudaMemcpyAsync(ctx->d_words + base, b->words + w0, (size_t)(w1 - w0) * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-        /* one staging entry per picture of the batch: nothing is reused before the final synchronisation */
-        for (int i = 0; i < cnt; i++) ctx->h_picbase[done + i] = base + (b->pic_off[done + i] - w0);
-        CK(ctx, cudaMemcpyAsync(ctx->d_picbase + slot0, ctx->h_picbase + done, (size_t)cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        /* cnt + 1 offsets per chunk (the last one is the end of its words), at twice the picture index so that
+         * neighbouring chunks / slot regions do not overlap; host entries are not reused before the final sync */
+        uint64_t *hb = ctx->h_picbase + 2 * (size_t)done;
+        for (int i = 0; i <= cnt; i++) hb[i] = base + (b->pic_off[done + i] - w0);
+        CK(ctx, cudaMemcpyAsync(ctx->d_picbase + 2 * (size_t)slot0, hb, (size_t)(cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         return MVG_SUCCESS;
     };
     auto expand = [&](int slot0, int cnt) -> int {
         K0Params p;
         const size_t o = (size_t)slot0 * n;
-        p.nz_blocks = ctx->d_nzb + o; p.word_off = ctx->d_woff + o; p.pic_base = ctx->d_picbase + slot0;
+        p.nz_blocks = ctx->d_nzb + o; p.word_off = ctx->d_woff + o; p.pic_base = ctx->d_picbase + 2 * (size_t)slot0;
         p.words = ctx->d_words; p.coeff = ctx->d_coeff + o * 384; p.n_mbs = (long long)cnt * (long long)n; p.mbs_per_pic = (int)n;
         const long long warps = p.n_mbs;
         const int grid = (int)std::min<long long>((warps + 7) / 8, (long long)ctx->sm_count * 16);

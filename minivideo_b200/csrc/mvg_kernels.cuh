@@ -53,7 +53,7 @@ __device__ __forceinline__ int mvg_chroma_qp(int qp_y, int offset)
 
 struct K0Params {
     const uint32_t *nz_blocks, *word_off;   /* [n_mbs]                                    */
-    const uint64_t *pic_base;               /* [n_pics] first word of each picture in `words` */
+    const uint64_t *pic_base;               /* [n_pics + 1] first word of each picture in `words`, then the end */
     const uint16_t *words;
     int16_t        *coeff;                  /* [n_mbs][384]                               */
     long long       n_mbs;
@@ -70,9 +70,12 @@ k0_expand_levels(K0Params p)
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long mb = warp0; mb < p.n_mbs; mb += n_warps) {
         const unsigned nzb = __ldg(p.nz_blocks + mb) & 0x00FFFFFFu;
-        const uint16_t *w = p.words + __ldg(p.pic_base + mb / p.mbs_per_pic) + __ldg(p.word_off + mb);
+        const long long pic = mb / p.mbs_per_pic;
+        const uint16_t *w = p.words + __ldg(p.pic_base + pic) + __ldg(p.word_off + mb);
+        const uint16_t *end = p.words + __ldg(p.pic_base + pic + 1);        /* a malformed batch must not read past its picture */
         const bool coded = (nzb >> lane) & 1u;
-        const unsigned mask = coded ? (unsigned)__ldg(w + __popc(nzb & ((1u << lane) - 1u))) : 0u;
+        const uint16_t *mp = w + __popc(nzb & ((1u << lane) - 1u));
+        const unsigned mask = (coded && mp < end) ? (unsigned)__ldg(mp) : 0u;
         int pre = __popc(mask);
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -85,7 +88,8 @@ k0_expand_levels(K0Params p)
         while (m) {
             const int k = __ffs(m) - 1;
             m &= m - 1;
-            const unsigned v = (unsigned)__ldg(lv++);
+            const unsigned v = lv < end ? (unsigned)__ldg(lv) : 0u;
+            lv++;
 #pragma unroll
             for (int q = 0; q < 8; q++)
                 if ((k >> 1) == q) out[q] |= v << (16 * (k & 1));
@@ -283,7 +287,8 @@ k1_dequant_idct(K1Params p)
 
         /* per-lane view of "my" macroblock j = lane >> 3 */
         const int kind_j = (int)__shfl_sync(MVG_FULL, meta, (lane & ~7) + 4);
-        const int qp_j = (signed char)__shfl_sync(MVG_FULL, meta, (lane & ~7) + 5);
+        /* QPY outside 0..51 cannot come out of a conforming parse; clamp so that a bad batch cannot index past the tables */
+        const int qp_j = min(max((int)(signed char)__shfl_sync(MVG_FULL, meta, (lane & ~7) + 5), 0), 51);
         if (mt == 0) s.meta[mj] = (unsigned)kind_j | ((unsigned)(qp_j & 255) << 8);
 
         mvg_mbar_wait(&s.mbar[buf], (parity >> buf) & 1u);

@@ -115,3 +115,26 @@ def test_front_end_emits_the_same_packed_batch_as_the_packer(threads):
     assert np.array_equal(sub["words"][: int(w2.pic_off[-1])], w2.words[: int(w2.pic_off[-1])])
     with pytest.raises(front.FrontError, match="capacity"):
         st.parse_packed(words_capacity=10)
+
+
+@pytest.mark.gpu
+def test_packed_decode_survives_malformed_offsets_and_masks():
+    """Offsets and masks that point past a picture's words must not fault the device: the expand kernel
+    bounds every read by the picture's word range (results are then unspecified, not checked)."""
+    from minivideo_b200 import api
+    soa = _soa(3)
+    ctx = api.Context(0, soa.width_mbs, soa.height_mbs, 3)
+    ctx.set_sps_from(soa)
+    pk = api.Packed(soa, pinned=True)
+    out = np.zeros((3, soa.height * soa.width * 3), np.uint8)
+    pk.word_off[5] = 0xFFFFFF00                       # far outside
+    pk.word_off[soa.n_mbs + 1] = int(pk.pic_off[2] - pk.pic_off[1])      # exactly at the end of picture 1
+    pk.nz_blocks[7] = 0x00FFFFFF                      # claims 24 coded chunks
+    pk.words[: 64] = 0xFFFF                           # masks claiming 16 levels each
+    ctx.decode_host_packed(pk, None, out, 1)
+    good = api.Packed(soa, pinned=True)               # the context is still usable afterwards
+    ctx.decode_host_packed(good, None, out, 1)
+    from oracle import cpu
+    want = cpu.yuv_to_rgb(cpu.reconstruct(soa)[0], soa.width, soa.height, 1)
+    assert np.array_equal(out.reshape(want.shape), want)
+    ctx.close()
