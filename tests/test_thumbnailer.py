@@ -136,3 +136,20 @@ def test_cli_scaled_thumbnail_is_the_box_average(cli):
         full, small = bmp(Path(d) / "s1.bmp"), bmp(Path(d) / "s4.bmp")
         h, w = full.shape[:2]
         assert np.array_equal(small, (full.reshape(h // 4, 4, w // 4, 4, 3).sum(axis=(1, 3)) + 8) // 16)
+
+
+@pytest.mark.gpu
+def test_cli_2160p_distributed_extraction(cli):
+    """BASELINE.json configs[4]: a 3840x2160 High-profile stream in 'distributed' extraction mode, through the
+    CLI, against the files of the reference CLI (which may abort after writing them, see above)."""
+    from minivideo_b200 import synth
+    if not ref.MINI_THUMBNAILER.exists():
+        pytest.skip("reference CLI not built")
+    stream, _ = synth.generate(10, "2160p", seed=907)
+    want, got = _run_both(stream, ["-f", "yuv420", "-n", "3", "-e", "distributed"], ref_may_crash=True)
+    want = {k: v for k, v in want.items() if not k.startswith("core")}
+    assert set(want) <= set(got) and len(want) >= 2
+    full = {k: v for k, v in want.items() if len(v) == 3840 * 2160 * 3 // 2}      # a file cut short by the abort does not count
+    assert len(full) >= 2
+    for name in full:
+        assert full[name] == got[name], name
