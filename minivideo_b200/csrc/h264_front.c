@@ -20,6 +20,8 @@
 /* CAVLC decode look-up tables, built once from the (length, code) tables     */
 
 static uint16_t lut_ct[3][1 << 16];      /* len<<7 | TotalCoeff<<2 | TrailingOnes, indexed by next 16 bits */
+static uint16_t lut_ct10[3][1 << 10];    /* the codes of up to 10 bits (almost all that occur) in 2 KB: stays in L1;
+                                            0 = longer code, use lut_ct                                     */
 static uint16_t lut_ctc[1 << 8];         /* chroma DC coeff_token, next 8 bits                             */
 static uint8_t  lut_tz4[15][1 << 9];     /* len<<4 | total_zeros, next 9 bits                              */
 static uint8_t  lut_tz2[3][1 << 3];
@@ -56,7 +58,11 @@ static void build_luts(void)
     for (int t = 0; t < 3; t++)
         for (int t1 = 0; t1 < 4; t1++)
             for (int tc = t1; tc <= 16; tc++)
+            {
                 fill16(lut_ct[t], 16, ct_len[t][t1][tc], ct_code[t][t1][tc], (uint16_t)(ct_len[t][t1][tc] << 7 | tc << 2 | t1));
+                if (ct_len[t][t1][tc] <= 10)
+                    fill16(lut_ct10[t], 10, ct_len[t][t1][tc], ct_code[t][t1][tc], (uint16_t)(ct_len[t][t1][tc] << 7 | tc << 2 | t1));
+            }
     for (int t1 = 0; t1 < 4; t1++)
         for (int tc = t1; tc <= 4; tc++)
             fill16(lut_ctc, 8, ctc_len[t1][tc], ctc_code[t1][tc], (uint16_t)(ctc_len[t1][tc] << 7 | tc << 2 | t1));
@@ -468,11 +474,13 @@ static int nC_of(const uint8_t *tot, int stride, int X, int Y)
     return a ? nA : (b ? nB : 0);
 }
 
-/* 9.2: one residual block; coef[] in scan order, max_num 16 / 15 / 4.  Returns TotalCoeff or -1. */
-static int read_residual_block(br_t *b, int *coef, int max_num, int nC)
+static inline int16_t clamp16(int v) { return (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
+
+/* 9.2: one residual block of max_num 16 / 15 / 4 levels.  The non-zero levels go straight to their place,
+ * dst[scan index * stride] (the destination must hold zeros), clamped to int16.  Returns TotalCoeff or -1. */
+static int read_residual_block(br_t *b, int16_t *dst, int stride, int max_num, int nC)
 {
     int tc, t1;
-    memset(coef, 0, sizeof(int) * (size_t)max_num);
     if (nC == -1) {
         uint16_t e = lut_ctc[br_peek(b, 8)];
         if (!e) return -1;
@@ -481,7 +489,10 @@ static int read_residual_block(br_t *b, int *coef, int max_num, int nC)
         uint32_t v = br_get(b, 6);
         if (v == 3) { tc = 0; t1 = 0; } else { tc = (int)(v >> 2) + 1; t1 = (int)(v & 3); if (t1 > tc) return -1; }
     } else {
-        uint16_t e = lut_ct[nC < 2 ? 0 : (nC < 4 ? 1 : 2)][br_peek(b, 16)];
+        const int t = nC < 2 ? 0 : (nC < 4 ? 1 : 2);
+        const uint32_t bits = br_peek(b, 16);
+        uint16_t e = lut_ct10[t][bits >> 6];
+        if (!e) e = lut_ct[t][bits];
         if (!e) return -1;
         br_skip(b, e >> 7); tc = (e >> 2) & 31; t1 = e & 3;
     }
@@ -490,8 +501,11 @@ static int read_residual_block(br_t *b, int *coef, int max_num, int nC)
 
     int level[16];
     int suffix_len = (tc > 10 && t1 < 3) ? 1 : 0;
-    for (int i = 0; i < tc; i++) {
-        if (i < t1) { level[i] = br_bit(b) ? -1 : 1; continue; }
+    {   /* trailing ones: t1 sign bits at once */
+        const uint32_t signs = t1 ? br_get(b, t1) : 0;
+        for (int i = 0; i < t1; i++) level[i] = ((signs >> (t1 - 1 - i)) & 1) ? -1 : 1;
+    }
+    for (int i = t1; i < tc; i++) {
         const int prefix = br_zeros(b);
         if (prefix >= 32) return -1;
         br_skip(b, prefix + 1);
@@ -516,7 +530,7 @@ static int read_residual_block(br_t *b, int *coef, int max_num, int nC)
     int pos = zeros_left + tc - 1;                                      /* scan index of the first (highest) level */
     if (pos >= max_num) return -1;
     for (int i = 0; i < tc; i++) {
-        coef[pos] = level[i];
+        dst[pos * stride] = clamp16(level[i]);
         int run = 0;
         if (i < tc - 1 && zeros_left > 0) {
             uint8_t e = lut_run[(zeros_left > 7 ? 7 : zeros_left) - 1][br_peek(b, 11)];
@@ -530,8 +544,6 @@ static int read_residual_block(br_t *b, int *coef, int max_num, int nC)
     }
     return tc;
 }
-
-static inline int16_t clamp16(int v) { return (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
 
 static int pack_mb(worker_t *w, size_t m);
 
@@ -582,7 +594,6 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
     memset(w->tot_luma, 0, N * 16);
     memset(w->tot_chroma[0], 0, N * 4);
     memset(w->tot_chroma[1], 0, N * 4);
-    int coef[64], sub[16];
 
     for (int my = 0; my < H; my++)
         for (int mx = 0; mx < W; mx++) {
@@ -632,38 +643,36 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
                 if (delta) qp = (qp + delta + 52) % 52;     /* h264_macroblock.c:263-266 */
                 /* residual_luma, 7.3.5.3.1 */
                 if (kind == MVG_MB_I16x16) {
-                    if (read_residual_block(&b, coef, 16, nC_of(w->tot_luma, W4, mx * 4, my * 4)) < 0) goto bad_block;
+                    int16_t dc[16] = {0};
+                    if (read_residual_block(&b, dc, 1, 16, nC_of(w->tot_luma, W4, mx * 4, my * 4)) < 0) goto bad_block;
                     for (int k = 0; k < 16; k++) {
                         int r = zz4[k] >> 2, c = zz4[k] & 3;
-                        cf[((r & 1) * 2 + (r >> 1) * 8 + (c & 1) + (c >> 1) * 4) * 16] = clamp16(coef[k]);
+                        cf[((r & 1) * 2 + (r >> 1) * 8 + (c & 1) + (c >> 1) * 4) * 16] = dc[k];
                     }
                 }
                 for (int b8 = 0; b8 < 4; b8++)
                     for (int i4 = 0; i4 < 4; i4++) {
                         int blk = b8 * 4 + i4, X4 = mx * 4 + blk_x(blk), Y4 = my * 4 + blk_y(blk), tc = 0;
                         if ((cbp_l >> b8) & 1) {
-                            int maxn = kind == MVG_MB_I16x16 ? 15 : 16;
-                            tc = read_residual_block(&b, sub, maxn, nC_of(w->tot_luma, W4, X4, Y4));
+                            const int nC = nC_of(w->tot_luma, W4, X4, Y4);
+                            if (kind == MVG_MB_I4x4) tc = read_residual_block(&b, cf + blk * 16, 1, 16, nC);
+                            else if (kind == MVG_MB_I8x8) tc = read_residual_block(&b, cf + b8 * 64 + i4, 4, 16, nC);   /* h264_macroblock.c:1182 */
+                            else tc = read_residual_block(&b, cf + blk * 16 + 1, 1, 15, nC);
                             if (tc < 0) goto bad_block;
-                            if (kind == MVG_MB_I4x4) for (int k = 0; k < 16; k++) cf[blk * 16 + k] = clamp16(sub[k]);
-                            else if (kind == MVG_MB_I8x8) for (int k = 0; k < 16; k++) cf[b8 * 64 + 4 * k + i4] = clamp16(sub[k]);   /* h264_macroblock.c:1182 */
-                            else for (int k = 0; k < 15; k++) cf[blk * 16 + 1 + k] = clamp16(sub[k]);
                         }
                         w->tot_luma[Y4 * W4 + X4] = (uint8_t)tc;
                     }
                 /* residual chroma: DC of both planes, then AC of both planes (h264_macroblock.c:1222-1292) */
                 for (int c = 0; c < 2; c++)
                     if (cbp_c & 3) {
-                        if (read_residual_block(&b, sub, 4, -1) < 0) goto bad_block;
-                        for (int k = 0; k < 4; k++) cf[256 + c * 64 + k * 16] = clamp16(sub[k]);
+                        if (read_residual_block(&b, cf + 256 + c * 64, 16, 4, -1) < 0) goto bad_block;
                     }
                 for (int c = 0; c < 2; c++)
                     for (int blk = 0; blk < 4; blk++) {
                         int X2 = mx * 2 + (blk & 1), Y2 = my * 2 + (blk >> 1), tc = 0;
                         if (cbp_c & 2) {
-                            tc = read_residual_block(&b, sub, 15, nC_of(w->tot_chroma[c], W2, X2, Y2));
+                            tc = read_residual_block(&b, cf + 256 + c * 64 + blk * 16 + 1, 1, 15, nC_of(w->tot_chroma[c], W2, X2, Y2));
                             if (tc < 0) goto bad_block;
-                            for (int k = 0; k < 15; k++) cf[256 + c * 64 + blk * 16 + 1 + k] = clamp16(sub[k]);
                         }
                         w->tot_chroma[c][Y2 * W2 + X2] = (uint8_t)tc;
                     }
