@@ -74,6 +74,7 @@ def build_gpu(force: bool = False) -> Path:
     if force or _stale(out, deps):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         extra = ["-DMVG_K2_PROFILE"] if os.environ.get("MVG_K2_PROFILE") else []     # dev: in-kernel cycle accounting
+        extra += ["-D" + d for d in os.environ.get("MVG_EXTRA_DEFINES", "").split()]     # dev: experiments
         _run([nvcc, *NVCC_FLAGS, *extra, f"-I{INC}", f"-I{CSRC}", "-o", str(out), *map(str, cu)],
              log=PKG / "libmvgpu.build.log")
     return out
