@@ -79,14 +79,23 @@ static void build_luts(void)
 /* ------------------------------------------------------------------------ */
 /* bit reader over an unescaped RBSP (8 zero bytes of padding behind it)      */
 
-typedef struct { const uint8_t *p; size_t pos, nbits; } br_t;
+typedef struct { const uint8_t *p; size_t pos, nbits; uint64_t win; size_t wbit; } br_t;
+#define BR_INIT(ptr, nbits) { (ptr), 0, (nbits), 0, (size_t)-4096 }
 
-/* 57 bits starting at the read position, left-aligned in 64: one unaligned load and a byte swap */
-static inline uint64_t br_window(const br_t *b)
+/* at least 32 valid bits starting at the read position, left-aligned in 64.  The 8 bytes last loaded are kept:
+ * a reload (one unaligned load and a byte swap) is needed only every four bytes or so */
+static inline uint64_t br_window(const br_t *bc)
 {
-    uint64_t w;
-    memcpy(&w, b->p + (b->pos >> 3), 8);
-    return __builtin_bswap64(w) << (b->pos & 7);
+    br_t *b = (br_t *)bc;
+    size_t off = b->pos - b->wbit;
+    if (off > 32) {
+        uint64_t w;
+        memcpy(&w, b->p + (b->pos >> 3), 8);
+        b->win = __builtin_bswap64(w);
+        b->wbit = b->pos & ~(size_t)7;
+        off = b->pos & 7;
+    }
+    return b->win << off;
 }
 static inline uint32_t br_peek(const br_t *b, int n)      /* 1 <= n <= 32 */
 {
@@ -209,7 +218,7 @@ static int parse_scaling_list(br_t *b, uint8_t *list, int n)
 
 static int parse_sps(mvf_stream *s, const uint8_t *rbsp, size_t n)
 {
-    br_t b = { rbsp, 0, n * 8 };
+    br_t b = BR_INIT(rbsp, n * 8);
     sps_t v;
     memset(&v, 0, sizeof v);
     v.profile_idc = (int)br_get(&b, 8);
@@ -267,7 +276,7 @@ static int parse_sps(mvf_stream *s, const uint8_t *rbsp, size_t n)
 
 static int parse_pps(mvf_stream *s, const uint8_t *rbsp, size_t n)
 {
-    br_t b = { rbsp, 0, rbsp_payload_bits(rbsp, n) };
+    br_t b = BR_INIT(rbsp, rbsp_payload_bits(rbsp, n));
     pps_t v;
     memset(&v, 0, sizeof v);
     br_ue(&b); br_ue(&b);                                   /* pps id, sps id */
@@ -563,7 +572,7 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
     const nal_t *nl = &s->nals[s->idr[idr_index]];
     if (nl->size + 16 > w->rbsp_cap) { w->rbsp_cap = nl->size * 2 + 64; w->rbsp = realloc(w->rbsp, w->rbsp_cap); }
     size_t n = unescape(s->data + nl->off + 1, nl->size - 1, w->rbsp);
-    br_t b = { w->rbsp, 0, rbsp_payload_bits(w->rbsp, n) };
+    br_t b = BR_INIT(w->rbsp, rbsp_payload_bits(w->rbsp, n));
     int nal_ref_idc = (s->data[nl->off] >> 5) & 3;
 
     /* ---- slice header, 7.3.3 (h264_slice.c:156-334) ---- */
