@@ -515,16 +515,24 @@ static int read_residual_block(br_t *b, int16_t *dst, int stride, int max_num, i
         for (int i = 0; i < t1; i++) level[i] = ((signs >> (t1 - 1 - i)) & 1) ? -1 : 1;
     }
     for (int i = t1; i < tc; i++) {
-        const int prefix = br_zeros(b);
-        if (prefix >= 32) return -1;
-        br_skip(b, prefix + 1);
-        int code = (prefix < 15 ? prefix : 15) << suffix_len;           /* 9.2.2.1 */
-        int ssize = suffix_len;
-        if (prefix == 14 && suffix_len == 0) ssize = 4;
-        else if (prefix >= 15) ssize = prefix - 3;
-        if (ssize > 0) code += (int)br_get(b, ssize);
-        if (prefix >= 15 && suffix_len == 0) code += 15;
-        if (prefix >= 16) code += (1 << (prefix - 3)) - 4096;
+        const uint32_t w32 = (uint32_t)(br_window(b) >> 32);
+        const int prefix = w32 ? __builtin_clz(w32) : 32;
+        int code;
+        if (prefix < 14) {              /* the common case: prefix, stop bit and suffix (<= 20 bits) from one window */
+            code = prefix << suffix_len;
+            if (suffix_len) code += (int)((w32 << (prefix + 1)) >> (32 - suffix_len));
+            br_skip(b, prefix + 1 + suffix_len);
+        } else {
+            if (prefix >= 32) return -1;
+            br_skip(b, prefix + 1);
+            code = (prefix < 15 ? prefix : 15) << suffix_len;           /* 9.2.2.1 */
+            int ssize = suffix_len;
+            if (prefix == 14 && suffix_len == 0) ssize = 4;
+            else if (prefix >= 15) ssize = prefix - 3;
+            if (ssize > 0) code += (int)br_get(b, ssize);
+            if (prefix >= 15 && suffix_len == 0) code += 15;
+            if (prefix >= 16) code += (1 << (prefix - 3)) - 4096;
+        }
         if (i == t1 && t1 < 3) code += 2;
         level[i] = (code & 1) ? (-code - 1) >> 1 : (code + 2) >> 1;
         if (suffix_len == 0) suffix_len = 1;
