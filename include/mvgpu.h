@@ -236,6 +236,9 @@ int mvg_set_pipeline(mvg_ctx *ctx, int chunk_pics);
 void *mvg_host_alloc(size_t bytes);
 void  mvg_host_free(void *p);
 
+/* Number of CUDA devices visible to the process (0 when there is none or the driver is missing). */
+int mvg_device_count(void);
+
 /* Geometry helpers. */
 int mvg_width(const mvg_ctx *ctx);    /* luma width in samples  = 16*width_mbs  */
 int mvg_height(const mvg_ctx *ctx);   /* luma height in samples = 16*height_mbs */

@@ -20,7 +20,7 @@ EXPORTS = (
     "mvg_upload", "mvg_clone_slot", "mvg_run", "mvg_sync", "mvg_get_timing", "mvg_mark", "mvg_mark_elapsed",
     "mvg_download_yuv420", "mvg_download_rgb", "mvg_download_residual", "mvg_decode_host",
     "mvg_pack_batch", "mvg_decode_host_packed",
-    "mvg_set_pipeline", "mvg_host_alloc", "mvg_host_free", "mvg_width", "mvg_height", "mvg_max_pics", "mvg_sm_count",
+    "mvg_device_count", "mvg_set_pipeline", "mvg_host_alloc", "mvg_host_free", "mvg_width", "mvg_height", "mvg_max_pics", "mvg_sm_count",
 )
 
 

@@ -7,7 +7,8 @@
  *
  * The work is mvt_extract() (mv_thumbcore.c).  Extensions over the reference: -o is honoured (the reference
  * ignores it, h264.c:65), -s writes a box-downscaled RGB thumbnail, -d/-t/-b pick the GPU, parser threads and
- * batch size.  No CPU fallback: without a CUDA device the program fails.
+ * batch size; -d all (or -d -1) spreads the pictures over every GPU of the box.  No CPU fallback: without a CUDA
+ * device the program fails.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -45,7 +46,7 @@ int main(int argc, char **argv)
             else { fprintf(stderr, "mv_thumbnailer: unknown extraction mode '%s'\n", v); return 2; }
         }
         else if (!strcmp(a, "-s")) scale = atoi(v);
-        else if (!strcmp(a, "-d")) device = atoi(v);
+        else if (!strcmp(a, "-d")) device = !strcmp(v, "all") ? -1 : atoi(v);
         else if (!strcmp(a, "-t")) threads = atoi(v);
         else if (!strcmp(a, "-b")) batch = atoi(v);
         else if (!strcmp(a, "-q")) { /* JPEG quality: accepted, unused */ }

@@ -391,6 +391,12 @@ extern "C" int mvg_dev_k2_stats(mvg_ctx *ctx, unsigned long long out[16])
     return MVG_SUCCESS;
 }
 
+extern "C" int mvg_device_count(void)
+{
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 extern "C" int mvg_width(const mvg_ctx *ctx) { return ctx ? 16 * ctx->w_mbs : 0; }
 extern "C" int mvg_height(const mvg_ctx *ctx) { return ctx ? 16 * ctx->h_mbs : 0; }
 extern "C" int mvg_max_pics(const mvg_ctx *ctx) { return ctx ? ctx->max_pics : 0; }

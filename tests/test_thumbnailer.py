@@ -153,3 +153,20 @@ def test_cli_2160p_distributed_extraction(cli):
     assert len(full) >= 2
     for name in full:
         assert full[name] == got[name], name
+
+
+@pytest.mark.gpu
+def test_cli_all_gpus_writes_the_same_files_as_one_gpu(cli):
+    """-d all: one feeder thread and context per GPU, batches dealt round-robin; the files
+    do not depend on how many GPUs took part.  On a one-GPU box this still exercises the feeder path."""
+    from minivideo_b200 import synth
+    stream, _ = synth.generate(13, width_mbs=20, height_mbs=12, profile_idc=100, transform8x8=1, scaling_lists=1, seed=909)
+    outs = []
+    for dev in ("0", "all"):
+        with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+            (Path(d) / "in.264").write_bytes(stream)
+            r = subprocess.run([str(MV), "-i", str(Path(d) / "in.264"), "-f", "bmp", "-n", "13", "-b", "2", "-d", dev, "-o", d],
+                               capture_output=True, text=True)
+            assert r.returncode == 0 and "13 picture(s) exported" in r.stdout, (r.stdout, r.stderr)
+            outs.append({p.name: p.read_bytes() for p in Path(d).iterdir() if p.name != "in.264"})
+    assert len(outs[0]) == 13 and outs[0] == outs[1]
