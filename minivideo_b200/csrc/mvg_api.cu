@@ -276,7 +276,8 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     cudaDeviceProp prop;
     TRY("cudaGetDeviceProperties", cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
-    TRY("occupancy k1", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_ctas_per_sm, k1_dequant_idct, K1_WARPS * 32, 0));
+    TRY("k1 shared memory", cudaFuncSetAttribute(k1_dequant_idct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(K1WarpSmem) * K1_WARPS)));
+    TRY("occupancy k1", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_ctas_per_sm, k1_dequant_idct, K1_WARPS * 32, sizeof(K1WarpSmem) * K1_WARPS));
     TRY("k2 shared memory", cudaFuncSetAttribute(k2_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM_BYTES));
     TRY("occupancy k2", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2_ctas_per_sm, k2_wavefront, K2_WARPS * 32, K2_SMEM_BYTES));
     if (ctx->k1_ctas_per_sm < 1 || ctx->k2_ctas_per_sm < 1) return bail("kernel does not fit on an SM", cudaErrorLaunchOutOfResources);
@@ -511,7 +512,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         const long long groups = (p.n_mbs + K1_GROUP - 1) / K1_GROUP;
         const long long want = (groups + K1_WARPS - 1) / K1_WARPS;
         const int grid = (int)std::min<long long>(want, (long long)ctx->sm_count * ctx->k1_ctas_per_sm);
-        k1_dequant_idct<<<grid, K1_WARPS * 32, 0, st>>>(p);
+        k1_dequant_idct<<<grid, K1_WARPS * 32, sizeof(K1WarpSmem) * K1_WARPS, st>>>(p);
         launches++;
     }
     if (timed) CK(ctx, cudaEventRecord(ctx->ev[1], st));

@@ -157,7 +157,7 @@ __device__ __forceinline__ unsigned mvg_pack_shr6(int hi, int lo)
     return __vsub2(t, 0x02000200u);
 }
 
-#define K1_WARPS 4          /* warps per CTA                      */
+#define K1_WARPS 12         /* warps per CTA; two CTAs per SM     */
 #define K1_GROUP 4          /* macroblocks per warp iteration     */
 #define K1_TILE  (K1_GROUP * 384)
 
@@ -220,14 +220,15 @@ __device__ __forceinline__ int mvg_blk_of(int bx, int by) { return (bx & 1) | ((
  *   - non-zero 8x8 blocks (Intra8x8 luma, quant8x8/idct8x8 :1256-1383) are compacted the same
  *     way and transformed 4 per pass, 8 lanes per block, transposed through shared memory.
  * Residual layout out: per macroblock 24 blocks x 16 int16, block-major (see MvgMbCtl). */
-__global__ void __launch_bounds__(K1_WARPS * 32, 5)
+__global__ void __launch_bounds__(K1_WARPS * 32, 2)
 k1_dequant_idct(K1Params p)
 {
     __shared__ int32_t s_ls4[3 * 6 * 16];
     __shared__ int32_t s_ls4q[3 * 52 * 16];                     /* per qP; << (qP/6-4) folded in when qP >= 24 */
     __shared__ int32_t s_ls8[6 * 64];
     __shared__ uint8_t s_zz8inv[64];
-    __shared__ K1WarpSmem s_warp[K1_WARPS];
+    extern __shared__ __align__(128) uint8_t k1_smem[];         /* K1WarpSmem x K1_WARPS (dynamic: above the 48 KB static limit) */
+    K1WarpSmem *s_warp = reinterpret_cast<K1WarpSmem *>(k1_smem);
 
     for (int i = threadIdx.x; i < 3 * 6 * 16; i += blockDim.x) s_ls4[i] = (&p.tab->ls4[0][0][0])[i];
     for (int i = threadIdx.x; i < 3 * 52 * 16; i += blockDim.x) s_ls4q[i] = (&p.tab->ls4q[0][0][0])[i];
