@@ -953,11 +953,9 @@ k2_wavefront(K2Params p)
                 const bool availA = mx > 0, availC = availB && mx < W - 1, availD = availA && availB;
 
                 if (availB) {
-                    if (j == 0) {               /* group of four macroblocks above: requested a group ago; request the next */
+                    if (j == 0) {               /* group of four macroblocks above: requested a group ago */
                         qa = qb;
                         okA = __ballot_sync(MVG_FULL, qa.y == epoch);
-                        qb = make_uint2(0, epoch);
-                        if (mx * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(ha_run + 32);
                     }
                     /* words needed now: the 8 of the macroblock above and, for the up-right neighbour, the first
                      * two of the next one, which sit in qb when this is the last macroblock of the group */
@@ -988,6 +986,13 @@ k2_wavefront(K2Params p)
                 K2_PROF(const long long t1 = clock64();)
                 mvg_cp_async_wait<2>();         /* all but the two youngest groups: macroblock mx has landed */
                 __syncwarp();
+                if (availB && j == 0) {
+                    /* request the next group of the row above only now, behind everything that reads qb: those reads
+                     * are predicated per macroblock, and a predicated-off read still waits for a load in flight.  The
+                     * group is first needed three macroblocks from here. */
+                    qb = make_uint2(0, epoch);
+                    if (mx * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(ha_run + 32);
+                }
                 K2_PROF(const long long t2 = clock64();)
                 c.resid = reinterpret_cast<const uint8_t *>(s.resid[mx & (K2_RING - 1)]);
                 const uint4 ctlw = *reinterpret_cast<const uint4 *>(&s.ctl[mx & (2 * K2_CTL_CHUNK - 1)]);
