@@ -504,6 +504,9 @@ struct K2Params {
 #else
 #define K2_PROF(...)
 #endif
+#ifndef K2_POLL_NS
+#define K2_POLL_NS   100        /* first sleep of a row that has caught up with the row above; doubles up to 8x */
+#endif
 #define K2_WARPS     16         /* warps per CTA; two CTAs per SM                              */
 #define K2_CTL_CHUNK 32         /* control records per chunk (one 16-byte copy per lane)       */
 #define K2_RING      4          /* residual ring slots (power of two; three are live at a time)   */
@@ -965,11 +968,11 @@ k2_wavefront(K2Params p)
                     if ((have & need) != need) {
                         K2_PROF(pc[5]++;)
                         /* this row has caught up with the row above: poll, sleeping a fraction of a macroblock time */
-                        unsigned ns = 100;
+                        unsigned ns = K2_POLL_NS;
                         do {
                             K2_PROF(pc[6]++;)
                             __nanosleep(ns);
-                            if (ns < 800) ns *= 2;
+                            if (ns < 8 * K2_POLL_NS) ns *= 2;
                             if ((mx & ~3) * 8 + lane < hwords) qa = mvg_ld_relaxed_u64(ha_run);
                             if ((mx & ~3) * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(ha_run + 32);
                             okA = __ballot_sync(MVG_FULL, qa.y == epoch);
