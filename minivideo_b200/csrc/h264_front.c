@@ -169,7 +169,12 @@ static int sfail(mvf_stream *s, int code, const char *fmt, ...)
     return code;
 }
 
-/* NAL payload (after the header byte) -> RBSP; returns the RBSP length (7.4.1.1) */
+/* Zero bytes kept behind every unescaped RBSP.  The bit reader never checks bounds inside a macroblock (a corrupt
+ * slice is caught by br_overrun() after the macroblock it happens in); one macroblock reads at most 27 residual
+ * blocks of at most 16 x 28 + 60 bits plus a few hundred bits of header: well under 2 KB. */
+#define RBSP_SLACK 4096
+
+/* NAL payload (after the header byte) -> RBSP (`dst` holds n + RBSP_SLACK bytes); returns the RBSP length (7.4.1.1) */
 static size_t unescape(const uint8_t *src, size_t n, uint8_t *dst)
 {
     size_t o = 0;
@@ -179,7 +184,7 @@ static size_t unescape(const uint8_t *src, size_t n, uint8_t *dst)
         dst[o++] = src[i];
         zeros = src[i] == 0 ? zeros + 1 : 0;
     }
-    memset(dst + o, 0, 8);
+    memset(dst + o, 0, RBSP_SLACK);
     return o;
 }
 
@@ -340,7 +345,11 @@ int mvf_open_annexb(const uint8_t *data, size_t len, mvf_stream **out)
         if (nl->type != 7 && nl->type != 8) continue;
         if (s->n_idr == 0) s->n_param_nals++;
         if ((nl->type == 7 && s->sps.valid) || (nl->type == 8 && s->pps.valid)) continue;   /* first ones win */
-        tmp = realloc(tmp, nl->size + 16);
+        {
+            uint8_t *nt = realloc(tmp, nl->size + RBSP_SLACK);
+            if (!nt) { rc = sfail(s, MVG_FAILURE, "out of memory"); break; }
+            tmp = nt;
+        }
         size_t n = unescape(data + nl->off + 1, nl->size - 1, tmp);
         rc = nl->type == 7 ? parse_sps(s, tmp, n) : parse_pps(s, tmp, n);
     }
@@ -578,7 +587,12 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
     const mvf_stream *s = w->s;
     const sps_t *sps = &s->sps; const pps_t *pps = &s->pps;
     const nal_t *nl = &s->nals[s->idr[idr_index]];
-    if (nl->size + 16 > w->rbsp_cap) { w->rbsp_cap = nl->size * 2 + 64; w->rbsp = realloc(w->rbsp, w->rbsp_cap); }
+    if (nl->size + RBSP_SLACK > w->rbsp_cap) {
+        w->rbsp_cap = nl->size * 2 + RBSP_SLACK;
+        uint8_t *nb = realloc(w->rbsp, w->rbsp_cap);
+        if (!nb) return wfail(w, MVG_FAILURE, "picture %d: out of memory", idr_index);
+        w->rbsp = nb;
+    }
     size_t n = unescape(s->data + nl->off + 1, nl->size - 1, w->rbsp);
     br_t b = BR_INIT(w->rbsp, rbsp_payload_bits(w->rbsp, n));
     int nal_ref_idc = (s->data[nl->off] >> 5) & 3;
