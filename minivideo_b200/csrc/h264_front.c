@@ -432,10 +432,12 @@ int mvf_select_idr(const mvf_stream *s, int n_wanted, int mode, int32_t *indices
         for (int i = 0; i < n_wanted; i++) indices[i] = i;
         return n_wanted;
     }
-    if (n_idr == 0) return 0;
+    if (n_idr < 1) return 0;
     /* sample size = distance between NAL header bytes (esparser.c:91,:130) */
     long long payload = 0;
     long long *size = malloc(sizeof(long long) * (size_t)n_idr);
+    int *cand = malloc(sizeof(int) * (size_t)n_idr), n_cand = 0;
+    if (!size || !cand) { free(size); free(cand); return 0; }
     for (int i = 0; i < n_idr; i++) {
         int k = s->idr[i];
         size_t next = k + 1 < s->n_nals ? s->nals[k + 1].off : s->len;
@@ -444,7 +446,6 @@ int mvf_select_idr(const mvf_stream *s, int n_wanted, int mode, int32_t *indices
     }
     int threshold = (int)(((double)payload / (double)n_idr) / 1.66);          /* filter.c:109 */
     int borders = n_idr > 48 ? (int)ceil(n_idr * 0.03) : 0;                   /* filter.c:114-118 */
-    int *cand = malloc(sizeof(int) * (size_t)n_idr), n_cand = 0;
     for (int i = borders; i < n_idr - borders; i++)
         if (size[i] > threshold) cand[n_cand++] = i;                          /* filter.c:120-131 */
     if (n_wanted > n_cand) n_wanted = n_cand;
