@@ -84,16 +84,16 @@ def build_thumbnailer(force: bool = False) -> Path:
     """mv_thumbnailer: the CLI over libmvfront.so + libmvgpu.so (mini_thumbnailer-compatible arguments), and
     libminivideo_b200.so: the reference's public entry points (minivideo.h) backed by the same core."""
     out = PKG / "mv_thumbnailer"
-    core = [CSRC / "mv_thumbcore.c", CSRC / "mv_thumbcore.h", INC / "mvfront.h", INC / "mvgpu.h",
-            PKG / "libmvfront.so", PKG / "libmvgpu.so"]
+    core = [CSRC / "mv_thumbcore.c", CSRC / "mv_png.c", CSRC / "mv_thumbcore.h", CSRC / "mv_png.h", INC / "mvfront.h",
+            INC / "mvgpu.h", PKG / "libmvfront.so", PKG / "libmvgpu.so"]
     libs = [f"-L{PKG}", "-Wl,-rpath,$ORIGIN", "-lmvfront", "-lmvgpu", "-lstdc++", "-lm", "-lpthread", "-ldl", "-lrt"]
     if force or _stale(out, core + [CSRC / "mv_thumbnailer.c"]):
         _run(["gcc", "-O2", "-Wall", "-Wextra", f"-I{INC}", f"-I{CSRC}", "-o", str(out), str(CSRC / "mv_thumbnailer.c"),
-              str(core[0]), *libs])
+              str(core[0]), str(core[1]), *libs])
     shim = PKG / "libminivideo_b200.so"
     if force or _stale(shim, core + [CSRC / "minivideo_shim.c"]):
         _run(["gcc", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", f"-I{INC}", f"-I{CSRC}", "-o", str(shim),
-              str(CSRC / "minivideo_shim.c"), str(core[0]), *libs])
+              str(CSRC / "minivideo_shim.c"), str(core[0]), str(core[1]), *libs])
     return out
 
 
@@ -110,7 +110,7 @@ def build_reference(force: bool = False) -> Path | None:
     out = ROOT / "oracle" / "_ref" / "ref_decode"
     if not (REFERENCE / "minivideo" / "src").is_dir():
         return out if out.exists() else None
-    if force or _stale(out, [ROOT / "oracle" / "ref_driver.c", ROOT / "oracle" / "Makefile"]):
+    if force or _stale(out, [ROOT / "oracle" / "ref_driver.c", ROOT / "oracle" / "ref_png.c", ROOT / "oracle" / "Makefile"]):
         _run(["make", "-C", str(ROOT / "oracle"), "ref", f"REF={REFERENCE}", "-j8"])
     return out
 

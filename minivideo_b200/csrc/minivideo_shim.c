@@ -13,8 +13,8 @@
  *
  * MediaFile_t is opaque to the caller (main.cpp only passes the pointer on), so this library defines its own.
  * Scope: what this repository accelerates -- H.264 elementary streams (.264/.h264/.avc, the reference's
- * es_fileParse path), intra pictures, CAVLC, output yuv420 / bmp / tga.  Containers (AVI/MP4/MKV), jpg/png/webp
- * and minivideo_extract() answer FAILURE with a message.  Like the reference (h264.c:65) pictures are written
+ * es_fileParse path), intra pictures, CAVLC, output png (also for 'jpg', as in the reference's default build) / bmp / tga /
+ * yuv420 / yuv444.  Containers (AVI/MP4/MKV), webp and minivideo_extract() answer FAILURE with a message.  Like the reference (h264.c:65) pictures are written
  * to the current directory unless an output directory is given.  No CPU fallback.
  */
 #include <stdbool.h>
@@ -111,14 +111,17 @@ int minivideo_decode(MediaFile_t *m, const char *output_directory, const int pic
     case PICTURE_YUV420: fmt = MVT_YUV420; break;
     case PICTURE_BMP:    fmt = MVT_BMP; break;
     case PICTURE_TGA:    fmt = MVT_TGA; break;
+    case PICTURE_YUV444: fmt = MVT_YUV444; break;
+    case PICTURE_JPG:                                   /* default build: "No jpg export library available, trying png" (export.c:652-657) */
+    case PICTURE_PNG:    fmt = MVT_PNG; break;
     default:
-        fprintf(stderr, "minivideo_decode: picture format %d is not supported by the GPU path (yuv420, bmp, tga)\n", picture_format);
+        fprintf(stderr, "minivideo_decode: picture format %d is not supported by the GPU path (jpg/png, bmp, tga, yuv420, yuv444)\n", picture_format);
         return FAILURE;
     }
     if (picture_extractionmode < 0 || picture_extractionmode > 2) return FAILURE;
     int n = picture_number < 1 ? 1 : picture_number > 999 ? 999 : picture_number;     /* minivideo.c clamps to 0..999 */
     int exported = 0;
-    return mvt_extract(m->data, m->len, m->base, output_directory, fmt, n, picture_extractionmode, 1, 0, 0, 64, &exported);
+    return mvt_extract(m->data, m->len, m->base, output_directory, fmt, n, picture_extractionmode, 1, 0, 0, 0, &exported);
 }
 
 int minivideo_extract(MediaFile_t *m, const char *output_directory, const bool extract_audio, const bool extract_video,

@@ -7,8 +7,9 @@
  * kernels 0-4) -> picture
  * files named like export_idr() names them (export.c:627-642,:704-705): <input base name>[_<k>].<ext>
  * with k counting exported pictures when more than one was requested.  File contents are byte-identical
- * to the reference's: planar I420 (export.c:100-151), 24-bit bottom-up BMP and run-length TGA as
- * stb_image_write lays them out (export.c:535-539,:566-570).
+ * to the reference's: planar I420 (export.c:100-151), its "super sampled" planar 4:4:4 (export.c:197-330),
+ * 24-bit bottom-up BMP, run-length TGA and PNG as stb_image_write v1.01 produces them (export.c:535-539,
+ * :566-570,:597-601; PNG in mv_png.c).  Parsing, GPU work and file encoding of successive batches overlap.
  * No CPU fallback: without a CUDA device mvt_extract() fails.
  */
 #include <limits.h>
@@ -21,35 +22,51 @@
 #include "mvfront.h"
 #include "mvgpu.h"
 #include "mv_thumbcore.h"
+#include "mv_png.h"
+
+#include <time.h>
+/* MVT_TIMING=1 in the environment: stage times of every feeder on stderr */
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
 
 
-static void put16(FILE *f, unsigned v) { fputc(v & 255, f); fputc((v >> 8) & 255, f); }
-static void put32(FILE *f, unsigned v) { put16(f, v & 0xffff); put16(f, v >> 16); }
+/* ---- picture files, built in memory and written with one fwrite() ------------------------------------ */
+
+static int write_raw(const char *path, const uint8_t *data, size_t n)
+{
+    FILE *f = fopen(path, "wb");
+    if (!f) return 0;
+    size_t w = fwrite(data, 1, n, f);
+    return fclose(f) == 0 && w == n;
+}
+
+static uint8_t *le16(uint8_t *o, unsigned v) { o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); return o + 2; }
+static uint8_t *le32(uint8_t *o, unsigned v) { o = le16(o, v & 0xffff); return le16(o, v >> 16); }
 
 /* 24-bit uncompressed BMP: 14-byte file header, 40-byte BITMAPINFOHEADER, rows bottom-up, BGR,
  * padded to 4 bytes -- the layout stbi_write_bmp() produces for 3 components */
 static int write_bmp(const char *path, const uint8_t *rgb, int w, int h)
 {
-    FILE *f = fopen(path, "wb");
-    if (!f) return 0;
-    int pad = (4 - (w * 3) % 4) % 4;
-    fputc('B', f); fputc('M', f);
-    put32(f, (unsigned)(54 + (w * 3 + pad) * h)); put16(f, 0); put16(f, 0); put32(f, 54);
-    put32(f, 40); put32(f, (unsigned)w); put32(f, (unsigned)h); put16(f, 1); put16(f, 24);
-    for (int i = 0; i < 6; i++) put32(f, 0);
-    uint8_t *line = malloc((size_t)w * 3 + 4);
+    const int pad = (4 - (w * 3) % 4) % 4;
+    const size_t line = (size_t)w * 3 + (size_t)pad, total = 54 + line * (size_t)h;
+    uint8_t *buf = malloc(total), *o = buf;
+    if (!buf) return 0;
+    *o++ = 'B'; *o++ = 'M';
+    o = le32(o, (unsigned)total); o = le16(o, 0); o = le16(o, 0); o = le32(o, 54);
+    o = le32(o, 40); o = le32(o, (unsigned)w); o = le32(o, (unsigned)h); o = le16(o, 1); o = le16(o, 24);
+    for (int i = 0; i < 6; i++) o = le32(o, 0);
     for (int y = h - 1; y >= 0; y--) {
         const uint8_t *src = rgb + (size_t)y * w * 3;
-        for (int x = 0; x < w; x++) { line[3 * x] = src[3 * x + 2]; line[3 * x + 1] = src[3 * x + 1]; line[3 * x + 2] = src[3 * x]; }
-        memset(line + w * 3, 0, (size_t)pad);
-        fwrite(line, 1, (size_t)(w * 3 + pad), f);
+        for (int x = 0; x < w; x++) { o[3 * x] = src[3 * x + 2]; o[3 * x + 1] = src[3 * x + 1]; o[3 * x + 2] = src[3 * x]; }
+        memset(o + w * 3, 0, (size_t)pad);
+        o += line;
     }
-    free(line);
-    return fclose(f) == 0;
+    int ok = write_raw(path, buf, total);
+    free(buf);
+    return ok;
 }
 
 static int same_px(const uint8_t *a, const uint8_t *b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; }
-static void put_bgr(FILE *f, const uint8_t *p) { fputc(p[2], f); fputc(p[1], f); fputc(p[0], f); }
+static uint8_t *put_bgr(uint8_t *o, const uint8_t *p) { o[0] = p[2]; o[1] = p[1]; o[2] = p[0]; return o + 3; }
 
 /* run-length true-colour TGA (image type 10), origin bottom-left, BGR.  Packets are formed the way
  * stbi_write_tga() forms them so the files compare equal: a raw packet keeps growing while pixel k
@@ -57,12 +74,13 @@ static void put_bgr(FILE *f, const uint8_t *p) { fputc(p[2], f); fputc(p[1], f);
  * pixels equal its first one; both stop at 128 pixels. */
 static int write_tga(const char *path, const uint8_t *rgb, int w, int h)
 {
-    FILE *f = fopen(path, "wb");
-    if (!f) return 0;
-    fputc(0, f); fputc(0, f); fputc(10, f);
-    put16(f, 0); put16(f, 0); fputc(0, f);
-    put16(f, 0); put16(f, 0); put16(f, (unsigned)w); put16(f, (unsigned)h);
-    fputc(24, f); fputc(0, f);
+    /* worst case: every packet is a raw one of a single pixel (1 + 3 bytes) */
+    uint8_t *buf = malloc(18 + (size_t)w * h * 4), *o = buf;
+    if (!buf) return 0;
+    *o++ = 0; *o++ = 0; *o++ = 10;
+    o = le16(o, 0); o = le16(o, 0); *o++ = 0;
+    o = le16(o, 0); o = le16(o, 0); o = le16(o, (unsigned)w); o = le16(o, (unsigned)h);
+    *o++ = 24; *o++ = 0;
     for (int y = h - 1; y >= 0; y--) {
         const uint8_t *row = rgb + (size_t)y * w * 3;
         int len;
@@ -82,23 +100,55 @@ static int write_tga(const char *path, const uint8_t *rgb, int w, int h)
                     }
                 }
             }
-            if (is_run) { fputc(len + 127, f); put_bgr(f, first); }
-            else { fputc(len - 1, f); for (int k = 0; k < len; k++) put_bgr(f, first + 3 * k); }
+            if (is_run) { *o++ = (uint8_t)(len + 127); o = put_bgr(o, first); }
+            else { *o++ = (uint8_t)(len - 1); for (int k = 0; k < len; k++) o = put_bgr(o, first + 3 * k); }
         }
     }
-    return fclose(f) == 0;
+    int ok = write_raw(path, buf, (size_t)(o - buf));
+    free(buf);
+    return ok;
 }
 
-static int write_raw(const char *path, const uint8_t *data, size_t n)
+static int write_png(const char *path, const uint8_t *rgb, int w, int h)
 {
-    FILE *f = fopen(path, "wb");
-    if (!f) return 0;
-    size_t w = fwrite(data, 1, n, f);
-    return fclose(f) == 0 && w == n;
+    size_t n = 0;
+    uint8_t *png = mvt_png_encode(rgb, w, h, &n);
+    if (!png) return 0;
+    int ok = write_raw(path, png, n);
+    free(png);
+    return ok;
 }
 
-/* one feeder per GPU: its own context, pinned buffers and parser threads; it takes every
- * n_gpus-th batch of the selected pictures, no data crosses GPUs */
+/* planar 4:4:4 as export_idr_yuv444() writes it (export.c:197-330): the luma plane, then Cb and Cr "super
+ * sampled" -- each chroma sample goes to the left, right and lower-left positions of its 2x2 cell and the
+ * lower-right one keeps the 0 of the calloc()ed plane (export.c:268-269 never writes [i + img_width + 1]) */
+static int write_yuv444(const char *path, const uint8_t *i420, int w, int h)
+{
+    const size_t plane = (size_t)w * h;
+    uint8_t *buf = calloc(3, plane);
+    if (!buf) return 0;
+    memcpy(buf, i420, plane);
+    for (int c = 0; c < 2; c++) {
+        const uint8_t *src = i420 + plane + (size_t)c * (plane / 4);
+        uint8_t *dst = buf + plane * (size_t)(1 + c);
+        for (int y = 0; y < h / 2; y++) {
+            uint8_t *r0 = dst + (size_t)(2 * y) * w, *r1 = r0 + w;
+            for (int x = 0; x < w / 2; x++) { uint8_t v = src[(size_t)y * (w / 2) + x]; r0[2 * x] = v; r0[2 * x + 1] = v; r1[2 * x] = v; }
+        }
+    }
+    int ok = write_raw(path, buf, 3 * plane);
+    free(buf);
+    return ok;
+}
+
+static const char *const file_ext[] = {"yuv", "bmp", "tga", "png", "yuv"};
+static int fmt_is_yuv(int fmt) { return fmt == MVT_YUV420 || fmt == MVT_YUV444; }
+
+/* ---- one feeder per GPU -------------------------------------------------------------------------------
+ *  its own context, pinned buffers and helper threads; it takes every n_gpus-th batch of
+ * the selected pictures, no data crosses GPUs.  Inside a feeder three stages run concurrently over two buffer
+ * sets: CAVLC parsing of batch k+1 (parser thread, `threads` workers inside), GPU reconstruction of batch k
+ * (this thread), file encoding + writing of batch k-1 (writer thread, `threads` workers). */
 typedef struct {
     mvf_stream *st; const mvf_info *info; const int32_t *sel; int n_sel;
     const char *base, *outdir; int fmt, scale, device, threads, batch, numbered;
@@ -106,13 +156,108 @@ typedef struct {
     int exported, rc;
 } feeder_t;
 
+enum { SLOT_FREE, SLOT_PARSED, SLOT_DECODED };
+
+typedef struct {
+    mvf_packed_batch pb; uint8_t *out;
+    int state, first, cnt;              /* pictures sel[first .. first+cnt) */
+} slot_t;
+
+typedef struct {
+    feeder_t *f;
+    slot_t slot[2];
+    pthread_mutex_t mu; pthread_cond_t cv;
+    int failed;                         /* any stage: stop everything */
+    size_t pic_bytes; int ow, oh;
+    /* writer workers */
+    const slot_t *wslot; int wnext, wexported;
+} pipe_t;
+
+static void pipe_fail(pipe_t *p) { pthread_mutex_lock(&p->mu); p->failed = 1; pthread_cond_broadcast(&p->cv); pthread_mutex_unlock(&p->mu); }
+
+/* wait until slot s reaches `state`; 0 when the pipeline failed meanwhile */
+static int pipe_wait(pipe_t *p, slot_t *s, int state)
+{
+    pthread_mutex_lock(&p->mu);
+    while (s->state != state && !p->failed) pthread_cond_wait(&p->cv, &p->mu);
+    int ok = !p->failed;
+    pthread_mutex_unlock(&p->mu);
+    return ok;
+}
+
+static void pipe_set(pipe_t *p, slot_t *s, int state)
+{
+    pthread_mutex_lock(&p->mu); s->state = state; pthread_cond_broadcast(&p->cv); pthread_mutex_unlock(&p->mu);
+}
+
+static void *parser_main(void *arg)
+{
+    pipe_t *p = arg; feeder_t *f = p->f;
+    int k = 0;
+    for (int bi = f->first_batch; bi * f->batch < f->n_sel; bi += f->batch_stride, k++) {
+        slot_t *s = &p->slot[k & 1];
+        if (!pipe_wait(p, s, SLOT_FREE)) return NULL;
+        s->first = bi * f->batch;
+        s->cnt = f->n_sel - s->first < f->batch ? f->n_sel - s->first : f->batch;
+        if (mvf_parse_pictures_packed(f->st, f->sel + s->first, 0, s->cnt, &s->pb, f->threads) != MVG_SUCCESS) {
+            fprintf(stderr, "mvt_extract: %s\n", mvf_last_error(f->st));
+            pipe_fail(p);
+            return NULL;
+        }
+        pipe_set(p, s, SLOT_PARSED);
+    }
+    return NULL;
+}
+
+static void *write_worker(void *arg)
+{
+    pipe_t *p = arg; feeder_t *f = p->f; const slot_t *s = p->wslot;
+    for (;;) {
+        int k = __atomic_fetch_add(&p->wnext, 1, __ATOMIC_RELAXED);
+        if (k >= s->cnt || __atomic_load_n(&p->failed, __ATOMIC_RELAXED)) return NULL;
+        char path[PATH_MAX];
+        /* export_idr() numbers pictures in export order (export.c:630): the position in the selection */
+        if (f->numbered) snprintf(path, sizeof path, "%s/%s_%d.%s", f->outdir, f->base, s->first + k, file_ext[f->fmt]);
+        else snprintf(path, sizeof path, "%s/%s.%s", f->outdir, f->base, file_ext[f->fmt]);
+        const uint8_t *px = s->out + (size_t)k * p->pic_bytes;
+        int ok = f->fmt == MVT_YUV420 ? write_raw(path, px, p->pic_bytes)
+               : f->fmt == MVT_YUV444 ? write_yuv444(path, px, p->ow, p->oh)
+               : f->fmt == MVT_BMP    ? write_bmp(path, px, p->ow, p->oh)
+               : f->fmt == MVT_TGA    ? write_tga(path, px, p->ow, p->oh)
+                                      : write_png(path, px, p->ow, p->oh);
+        if (!ok) { fprintf(stderr, "mvt_extract: cannot write '%s'\n", path); pipe_fail(p); return NULL; }
+        __atomic_fetch_add(&p->wexported, 1, __ATOMIC_RELAXED);
+    }
+}
+
+static void *writer_main(void *arg)
+{
+    pipe_t *p = arg; feeder_t *f = p->f;
+    int k = 0;
+    for (int bi = f->first_batch; bi * f->batch < f->n_sel; bi += f->batch_stride, k++) {
+        slot_t *s = &p->slot[k & 1];
+        if (!pipe_wait(p, s, SLOT_DECODED)) return NULL;
+        p->wslot = s; p->wnext = 0;
+        int nw = f->threads < s->cnt ? f->threads : s->cnt;
+        if (nw > 256) nw = 256;
+        pthread_t th[256]; int started = 0;
+        for (int t = 1; t < nw; t++) { if (pthread_create(&th[started], NULL, write_worker, p) == 0) started++; }
+        write_worker(p);
+        for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+        if (p->failed) return NULL;
+        pipe_set(p, s, SLOT_FREE);
+    }
+    return NULL;
+}
+
 static void *feeder_main(void *arg)
 {
     feeder_t *f = arg;
     const mvf_info *info = f->info;
     const int W = 16 * info->width_mbs, H = 16 * info->height_mbs, batch = f->batch, fmt = f->fmt, scale = f->scale;
-    static const char *ext[] = {"yuv", "bmp", "tga"};
     f->rc = 1;
+    const int timing = getenv("MVT_TIMING") != NULL;
+    const double t0 = now_s();
     mvg_ctx *ctx = NULL;
     if (mvg_create(&ctx, f->device, info->width_mbs, info->height_mbs, batch) != MVG_SUCCESS) {
         fprintf(stderr, "mvt_extract: %s\n", mvg_last_error(NULL));
@@ -124,52 +269,73 @@ static void *feeder_main(void *arg)
         mvg_destroy(ctx);
         return NULL;
     }
+    const double t1 = now_s();
+    int n_my_batches = 0;
+    for (int bi = f->first_batch; bi * batch < f->n_sel; bi += f->batch_stride) n_my_batches++;
+    const int n_slots = n_my_batches > 1 ? 2 : 1;
     const size_t N = (size_t)info->width_mbs * info->height_mbs, nb = N * (size_t)batch;
-    /* parsed pictures travel in the packed transfer format (mvgpu.h): a fifth of the dense levels on the bus */
-    mvf_packed_batch pb;
-    pb.n_pics = 0;
-    pb.mb_kind = mvg_host_alloc(nb); pb.i16_mode = mvg_host_alloc(nb); pb.chroma_mode = mvg_host_alloc(nb);
-    pb.qp_y = mvg_host_alloc(nb); pb.luma_modes = mvg_host_alloc(nb * 16);
-    pb.nz_blocks = mvg_host_alloc(nb * sizeof(uint32_t)); pb.word_off = mvg_host_alloc(nb * sizeof(uint32_t));
-    pb.pic_off = mvg_host_alloc(((size_t)batch + 1) * sizeof(uint64_t));
-    pb.words_capacity = nb * MVG_PACKED_WORDS_PER_MB;
-    pb.words = mvg_host_alloc(pb.words_capacity * sizeof(uint16_t));
-    const int ow = W / scale, oh = H / scale;
-    const size_t yuv_sz = (size_t)W * H * 3 / 2, rgb_sz = (size_t)ow * oh * 3;
-    uint8_t *out = mvg_host_alloc((fmt == MVT_YUV420 ? yuv_sz : rgb_sz) * (size_t)batch);
+    pipe_t p;
+    memset(&p, 0, sizeof p);
+    p.f = f;
+    p.ow = fmt_is_yuv(fmt) ? W : W / scale; p.oh = fmt_is_yuv(fmt) ? H : H / scale;
+    p.pic_bytes = fmt_is_yuv(fmt) ? (size_t)W * H * 3 / 2 : (size_t)p.ow * p.oh * 3;
+    pthread_mutex_init(&p.mu, NULL); pthread_cond_init(&p.cv, NULL);
     int rc = 0;
-    if (!pb.mb_kind || !pb.i16_mode || !pb.chroma_mode || !pb.qp_y || !pb.luma_modes || !pb.nz_blocks || !pb.word_off ||
-        !pb.pic_off || !pb.words || !out) {
-        fprintf(stderr, "mvt_extract: pinned host allocation failed\n");
-        rc = 1;
-    }
-    for (int bi = f->first_batch; !rc && bi * batch < f->n_sel; bi += f->batch_stride) {
-        const int done = bi * batch;
-        int cnt = f->n_sel - done < batch ? f->n_sel - done : batch;
-        if (mvf_parse_pictures_packed(f->st, f->sel + done, 0, cnt, &pb, f->threads) != MVG_SUCCESS) {
-            fprintf(stderr, "mvt_extract: %s\n", mvf_last_error(f->st));
-            rc = 1; break;
-        }
-        mvg_packed_batch gb = { cnt, pb.mb_kind, pb.i16_mode, pb.chroma_mode, pb.qp_y, pb.luma_modes,
-                                pb.nz_blocks, pb.word_off, pb.pic_off, pb.words };
-        int ok = fmt == MVT_YUV420 ? mvg_decode_host_packed(ctx, &gb, out, NULL, 0) : mvg_decode_host_packed(ctx, &gb, NULL, out, scale);
-        if (ok != MVG_SUCCESS) { fprintf(stderr, "mvt_extract: %s\n", mvg_last_error(ctx)); rc = 1; break; }
-        for (int k = 0; k < cnt && !rc; k++) {
-            char path[PATH_MAX];
-            /* export_idr() numbers pictures in export order (export.c:630): the position in the selection */
-            if (f->numbered) snprintf(path, sizeof path, "%s/%s_%d.%s", f->outdir, f->base, done + k, ext[fmt]);
-            else snprintf(path, sizeof path, "%s/%s.%s", f->outdir, f->base, ext[fmt]);
-            int w = fmt == MVT_YUV420 ? write_raw(path, out + (size_t)k * yuv_sz, yuv_sz)
-                  : fmt == MVT_BMP    ? write_bmp(path, out + (size_t)k * rgb_sz, ow, oh)
-                                      : write_tga(path, out + (size_t)k * rgb_sz, ow, oh);
-            if (!w) { fprintf(stderr, "mvt_extract: cannot write '%s'\n", path); rc = 1; }
-            else f->exported++;
+    for (int k = 0; k < n_slots; k++) {
+        /* parsed pictures travel in the packed transfer format (mvgpu.h): a fifth of the dense levels on the bus */
+        mvf_packed_batch *pb = &p.slot[k].pb;
+        pb->n_pics = 0;
+        pb->mb_kind = mvg_host_alloc(nb); pb->i16_mode = mvg_host_alloc(nb); pb->chroma_mode = mvg_host_alloc(nb);
+        pb->qp_y = mvg_host_alloc(nb); pb->luma_modes = mvg_host_alloc(nb * 16);
+        pb->nz_blocks = mvg_host_alloc(nb * sizeof(uint32_t)); pb->word_off = mvg_host_alloc(nb * sizeof(uint32_t));
+        pb->pic_off = mvg_host_alloc(((size_t)batch + 1) * sizeof(uint64_t));
+        pb->words_capacity = nb * MVG_PACKED_WORDS_PER_MB;
+        pb->words = mvg_host_alloc(pb->words_capacity * sizeof(uint16_t));
+        p.slot[k].out = mvg_host_alloc(p.pic_bytes * (size_t)batch);
+        if (!pb->mb_kind || !pb->i16_mode || !pb->chroma_mode || !pb->qp_y || !pb->luma_modes || !pb->nz_blocks ||
+            !pb->word_off || !pb->pic_off || !pb->words || !p.slot[k].out) {
+            fprintf(stderr, "mvt_extract: pinned host allocation failed\n");
+            rc = 1;
         }
     }
-    mvg_host_free(pb.mb_kind); mvg_host_free(pb.i16_mode); mvg_host_free(pb.chroma_mode); mvg_host_free(pb.qp_y);
-    mvg_host_free(pb.luma_modes); mvg_host_free(pb.nz_blocks); mvg_host_free(pb.word_off); mvg_host_free(pb.pic_off);
-    mvg_host_free(pb.words); mvg_host_free(out);
+    const double t2 = now_s();
+    double t_gpu = 0;
+    pthread_t parser, writer;
+    int have_parser = 0, have_writer = 0;
+    if (!rc) {
+        have_parser = pthread_create(&parser, NULL, parser_main, &p) == 0;
+        have_writer = have_parser && pthread_create(&writer, NULL, writer_main, &p) == 0;
+        if (!have_parser || !have_writer) { fprintf(stderr, "mvt_extract: cannot start helper threads\n"); pipe_fail(&p); rc = 1; }
+    }
+    int k = 0;
+    for (int bi = f->first_batch; !rc && bi * batch < f->n_sel; bi += f->batch_stride, k++) {
+        slot_t *s = &p.slot[k & 1];
+        if (!pipe_wait(&p, s, SLOT_PARSED)) { rc = 1; break; }
+        const mvf_packed_batch *pb = &s->pb;
+        mvg_packed_batch gb = { s->cnt, pb->mb_kind, pb->i16_mode, pb->chroma_mode, pb->qp_y, pb->luma_modes,
+                                pb->nz_blocks, pb->word_off, pb->pic_off, pb->words };
+        const double tg = now_s();
+        int ok = fmt_is_yuv(fmt) ? mvg_decode_host_packed(ctx, &gb, s->out, NULL, 0) : mvg_decode_host_packed(ctx, &gb, NULL, s->out, scale);
+        t_gpu += now_s() - tg;
+        if (ok != MVG_SUCCESS) { fprintf(stderr, "mvt_extract: %s\n", mvg_last_error(ctx)); pipe_fail(&p); rc = 1; break; }
+        pipe_set(&p, s, SLOT_DECODED);
+    }
+    if (have_parser) pthread_join(parser, NULL);
+    if (have_writer) pthread_join(writer, NULL);
+    if (p.failed) rc = 1;
+    f->exported = p.wexported;
+    const double t3 = now_s();
+    for (int q = 0; q < n_slots; q++) {
+        mvf_packed_batch *pb = &p.slot[q].pb;
+        mvg_host_free(pb->mb_kind); mvg_host_free(pb->i16_mode); mvg_host_free(pb->chroma_mode); mvg_host_free(pb->qp_y);
+        mvg_host_free(pb->luma_modes); mvg_host_free(pb->nz_blocks); mvg_host_free(pb->word_off); mvg_host_free(pb->pic_off);
+        mvg_host_free(pb->words); mvg_host_free(p.slot[q].out);
+    }
+    pthread_mutex_destroy(&p.mu); pthread_cond_destroy(&p.cv);
     mvg_destroy(ctx);
+    if (timing)
+        fprintf(stderr, "mvt_extract[gpu %d]: context %.3f s, pinned buffers %.3f s, pipeline %.3f s (GPU calls %.3f s) for %d pictures, teardown %.3f s\n",
+                f->device, t1 - t0, t2 - t1, t3 - t2, t_gpu, f->exported, now_s() - t3);
     f->rc = rc;
     return NULL;
 }
@@ -178,7 +344,7 @@ int mvt_extract(const uint8_t *data, size_t len, const char *base, const char *o
                 int scale, int device, int threads, int batch, int *n_exported)
 {
     if (n_exported) *n_exported = 0;
-    if (!data || !base || n_want < 1 || scale < 1 || batch < 1 || fmt < MVT_YUV420 || fmt > MVT_TGA) return MVG_FAILURE;
+    if (!data || !base || n_want < 1 || scale < 1 || batch < 0 || fmt < MVT_YUV420 || fmt > MVT_YUV444) return MVG_FAILURE;
     if (!outdir || !*outdir) outdir = ".";
     if (threads < 1) { long c = sysconf(_SC_NPROCESSORS_ONLN); threads = c > 0 ? (int)c : 1; }
     mvf_stream *st = NULL;
@@ -200,10 +366,18 @@ int mvt_extract(const uint8_t *data, size_t len, const char *base, const char *o
         free(tmp);
     }
     const int W = 16 * info.width_mbs, H = 16 * info.height_mbs;
-    if (fmt != MVT_YUV420 && (W % scale || H % scale)) {
+    if (!fmt_is_yuv(fmt) && (W % scale || H % scale)) {
         fprintf(stderr, "mvt_extract: scale %d does not divide %dx%d\n", scale, W, H);
         free(sel); mvf_close(st);
         return MVG_FAILURE;
+    }
+    if (batch == 0) {
+        /* pictures per GPU call: about 256 MB of output per buffer set (pinned memory costs ~1 s per GB to set
+         * up), but never fewer than the PNG encoder threads that share a batch */
+        const size_t pic = fmt_is_yuv(fmt) ? (size_t)W * H * 3 / 2 : (size_t)(W / scale) * (H / scale) * 3;
+        batch = (int)(((size_t)256 << 20) / pic);
+        if (fmt == MVT_PNG && batch < threads) batch = threads;
+        batch = batch < 4 ? 4 : batch > 64 ? 64 : batch;
     }
     if (batch > n_sel) batch = n_sel;
 

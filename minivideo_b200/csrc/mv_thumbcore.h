@@ -7,14 +7,14 @@
 #include <stddef.h>
 #include <stdint.h>
 
-enum { MVT_YUV420, MVT_BMP, MVT_TGA };
+enum { MVT_YUV420, MVT_BMP, MVT_TGA, MVT_PNG, MVT_YUV444 };
 
 /* Decode up to `n_want` IDR pictures of the Annex-B stream `data` (selection `mode`: 0 unfiltered, 1 ordered,
  * 2 distributed, demuxer/filter.c:52-215) on CUDA device `device` and write them as
- * <outdir>/<base>[_<k>].{yuv,bmp,tga}, named and laid out like export_idr() does (export.c:627-642, :100-151,
- * :535-570).  scale > 1 writes box-downscaled RGB thumbnails (no reference counterpart).  threads < 1: one CAVLC
+ * <outdir>/<base>[_<k>].{yuv,bmp,tga,png}, named and laid out like export_idr() does (export.c:627-642, :100-151,
+ * :197-330, :535-601).  scale > 1 writes box-downscaled RGB thumbnails (no reference counterpart).  threads < 1: one CAVLC
  * parser thread per core.  device < 0: every visible GPU, one feeder thread each, batches of `batch` pictures dealt
- * round-robin (disjoint pictures per GPU, nothing crosses GPUs).  Returns MVG_SUCCESS (1) / MVG_FAILURE (0); messages go to stderr. */
+ * round-robin (disjoint pictures per GPU, nothing crosses GPUs); batch 0 picks a size from the picture size.  Returns MVG_SUCCESS (1) / MVG_FAILURE (0); messages go to stderr. */
 int mvt_extract(const uint8_t *data, size_t len, const char *base, const char *outdir, int fmt, int n_want, int mode,
                 int scale, int device, int threads, int batch, int *n_exported);
 

@@ -2,10 +2,11 @@
  * mv_thumbnailer.c -- command-line front of the GPU path, argument-compatible with the reference's
  * mini_thumbnailer (mini_thumbnailer/src/main.cpp:77-240):
  *
- *   mv_thumbnailer -i <file.264> [-o <dir>] [-f yuv420|bmp|tga] [-n N] [-e unfiltered|ordered|distributed]
+ *   mv_thumbnailer -i <file.264> [-o <dir>] [-f jpg|png|bmp|tga|yuv420|yuv444] [-n N] [-e unfiltered|ordered|distributed]
  *                  [-s scale] [-d device] [-t threads] [-b batch]
  *
- * The work is mvt_extract() (mv_thumbcore.c).  Extensions over the reference: -o is honoured (the reference
+ * The work is mvt_extract() (mv_thumbcore.c).  As in the reference's default build (no libjpeg, export.c:652-657)
+ * 'jpg' -- also the default format, main.cpp:56 -- is written as PNG.  Extensions over the reference: -o is honoured (the reference
  * ignores it, h264.c:65), -s writes a box-downscaled RGB thumbnail, -d/-t/-b pick the GPU, parser threads and
  * batch size; -d all (or -d -1) spreads the pictures over every GPU of the box.  No CPU fallback: without a CUDA
  * device the program fails.
@@ -18,14 +19,14 @@
 
 static void usage(void)
 {
-    fprintf(stderr, "usage: mv_thumbnailer -i <file.264> [-o <dir>] [-f yuv420|bmp|tga] [-n picture_number]\n"
+    fprintf(stderr, "usage: mv_thumbnailer -i <file.264> [-o <dir>] [-f jpg|png|bmp|tga|yuv420|yuv444] [-n picture_number]\n"
                     "                      [-e unfiltered|ordered|distributed] [-s scale] [-d device] [-t threads] [-b batch]\n");
 }
 
 int main(int argc, char **argv)
 {
     const char *in = NULL, *outdir = ".";
-    int fmt = MVT_YUV420, n_want = 1, mode = 0, scale = 1, device = 0, threads = 0, batch = 64;
+    int fmt = MVT_PNG, n_want = 1, mode = 0, scale = 1, device = 0, threads = 0, batch = 0;
     for (int i = 1; i < argc; i++) {
         const char *a = argv[i], *v = i + 1 < argc ? argv[i + 1] : NULL;
         if (!strcmp(a, "-h") || !strcmp(a, "--help")) { usage(); return 0; }
@@ -36,7 +37,10 @@ int main(int argc, char **argv)
             if (!strcmp(v, "yuv420")) fmt = MVT_YUV420;
             else if (!strcmp(v, "bmp")) fmt = MVT_BMP;
             else if (!strcmp(v, "tga")) fmt = MVT_TGA;
-            else { fprintf(stderr, "mv_thumbnailer: picture format '%s' is not supported (yuv420, bmp, tga)\n", v); return 2; }
+            else if (!strcmp(v, "png")) fmt = MVT_PNG;
+            else if (!strcmp(v, "jpg")) fmt = MVT_PNG;          /* "No jpg export library available, trying png" */
+            else if (!strcmp(v, "yuv444")) fmt = MVT_YUV444;
+            else { fprintf(stderr, "mv_thumbnailer: picture format '%s' is not supported (jpg, png, bmp, tga, yuv420, yuv444)\n", v); return 2; }
         }
         else if (!strcmp(a, "-n")) n_want = atoi(v);
         else if (!strcmp(a, "-e")) {
@@ -53,7 +57,7 @@ int main(int argc, char **argv)
         else { fprintf(stderr, "mv_thumbnailer: unknown argument '%s'\n", a); usage(); return 2; }
         i++;
     }
-    if (!in || n_want < 1 || scale < 1 || batch < 1) { usage(); return 2; }
+    if (!in || n_want < 1 || scale < 1 || batch < 0) { usage(); return 2; }
 
     FILE *f = fopen(in, "rb");
     if (!f) { fprintf(stderr, "mv_thumbnailer: cannot open '%s'\n", in); return 1; }

@@ -50,12 +50,13 @@ def test_drop_in_library_exports_the_reference_entry_points(cli):
             assert lib.minivideo_open(str(Path(d) / name).encode(), C.byref(media)) == 1
             assert lib.minivideo_parse(media, False, True, False) == parse_ok
             if parse_ok:
-                assert lib.minivideo_decode(media, b"", 3, 75, 1, 0) == 0        # PICTURE_PNG: not supported
+                assert lib.minivideo_decode(media, b"", 4, 75, 1, 0) == 0        # PICTURE_WEBP: not supported
             assert lib.minivideo_close(C.byref(media)) == 1 and not media
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fmt,n,mode", [("yuv420", 1, "unfiltered"), ("bmp", 3, "unfiltered"), ("tga", 4, "ordered")])
+@pytest.mark.parametrize("fmt,n,mode", [("yuv420", 1, "unfiltered"), ("bmp", 3, "unfiltered"), ("tga", 4, "ordered"),
+                                        ("png", 2, "unfiltered"), ("jpg", 2, "unfiltered"), ("yuv444", 2, "ordered")])
 def test_reference_cli_linked_against_the_drop_in_library(cli, fmt, n, mode):
     """The reference's own mini_thumbnailer main.cpp, unmodified, linked against libminivideo_b200.so, writes
     the files the reference build of the same program writes."""
@@ -83,7 +84,7 @@ def _run_both(stream: bytes, args: list[str], ref_may_crash: bool = False, exes=
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fmt", ["yuv420", "bmp", "tga"])
+@pytest.mark.parametrize("fmt", ["yuv420", "bmp", "tga", "png", "yuv444"])
 @pytest.mark.parametrize("mode,n", [("unfiltered", 1), ("unfiltered", 5), ("ordered", 4), ("distributed", 4)])
 def test_cli_files_equal_the_reference_cli(cli, fmt, mode, n):
     from minivideo_b200 import synth
@@ -102,6 +103,20 @@ def test_cli_files_equal_the_reference_cli(cli, fmt, mode, n):
         assert sorted(want) == sorted(got)
     for name in want:
         assert want[name] == got[name], name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [[], ["-f", "jpg"]], ids=["default", "jpg"])
+def test_cli_default_format_and_jpg_are_written_as_png_like_the_reference_build(cli, args):
+    """mini_thumbnailer defaults to 'jpg' (main.cpp:56); the reference build without libjpeg writes PNG files for
+    it (export.c:652-657) through its vendored stb writer."""
+    from minivideo_b200 import synth
+    if not ref.MINI_THUMBNAILER.exists():
+        pytest.skip("reference CLI not built")
+    stream, _ = synth.generate(3, width_mbs=20, height_mbs=12, profile_idc=100, transform8x8=1, scaling_lists=1, seed=911)
+    want, got = _run_both(stream, args + ["-n", "3"])
+    assert sorted(want) == sorted(got) == ["in_0.png", "in_1.png", "in_2.png"]
+    assert want == got
 
 
 @pytest.mark.gpu
