@@ -8,16 +8,22 @@
 #include <stdint.h>
 
 /* ---- kernel 2 shared-memory tile geometry (per warp) ----------------------
- * luma tile  : rows y = -1..15, row stride 48 B, sample x at byte (x + 16):
- *              x = -1 -> 15, x = 0..15 -> 16..31 (16-byte aligned rows for the write-out),
- *              x = 16..23 (macroblock C, top row only) -> 32..39
- * chroma tile: rows y = -1..7, row stride 48 B (as luma: conflict-free row reads), sample x at byte (x + 16) */
-#define MVG_LT_STRIDE 48
+ * luma tile  : rows y = -1..15, sample x at byte (x + 16): x = -1 -> 15, x = 0..15 -> 16..31,
+ *              x = 16..23 (macroblock C, top row only) -> 32..39.  Row stride 40 B = 10 words: 10 y mod 32 is
+ *              a different even bank for each of 16 rows, so a column (x = -1 hand-over, Horizontal
+ *              predictors) and the 8-byte row pieces of the write-out are free of bank conflicts; rows are
+ *              8-byte aligned.
+ * chroma tile: rows y = -1..7, sample x at byte (x + 8), row stride 24 B = 6 words, Cr plane 320 B = 80 words
+ *              after Cb: the 2 x 8 rows x 2 words of both planes cover all 32 banks exactly once. */
+#ifndef MVG_LT_STRIDE
+#define MVG_LT_STRIDE 40
+#endif
 #define MVG_LT_XOFF   16
 #define MVG_LT_ROWS   17
-#define MVG_CT_STRIDE 32
-#define MVG_CT_XOFF   16
+#define MVG_CT_STRIDE 24
+#define MVG_CT_XOFF   8
 #define MVG_CT_ROWS   9
+#define MVG_CT_PLANE  320
 
 /* ---- per-macroblock control record kernel 1 writes for kernel 2 (16 B) ----
  * w0: byte0 mb_kind, byte1 Intra16x16PredMode, byte2 intra_chroma_pred_mode,

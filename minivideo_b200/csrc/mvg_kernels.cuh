@@ -517,7 +517,7 @@ struct K2WarpSmem {
     __align__(16) int16_t  resid[K2_RING][384];         /* residual ring, filled by per-lane async copies two macroblocks ahead */
     __align__(16) MvgMbCtl ctl[2 * K2_CTL_CHUNK];       /* control records, two chunks: record of macroblock mx at [mx & 63]      */
     __align__(16) uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
-    __align__(16) uint8_t  ct[2][MVG_CT_ROWS * MVG_CT_STRIDE];
+    __align__(16) uint8_t  ct[2][MVG_CT_PLANE];
     __align__(16) uint32_t n8[36];                      /* Intra8x8 neighbour line: p' | f2 << 8 | f3 << 16; [32] = DC */
 };
 
@@ -563,7 +563,7 @@ __device__ __forceinline__ unsigned mvg_pairs_to_bytes(unsigned a, unsigned b) {
  * warp-uniform (they come from a lane-0 broadcast, so they live in uniform registers and shared-memory
  * accesses take the form [lane register + uniform base + immediate]) */
 struct K2Ctx {
-    uint8_t *lt, *ct;           /* luma tile, chroma tiles (plane stride MVG_CT_ROWS * MVG_CT_STRIDE) */
+    uint8_t *lt, *ct;           /* luma tile, chroma tiles (plane stride MVG_CT_PLANE) */
     uint32_t *n8;
     const uint8_t *resid;       /* residual buffer of the current macroblock */
     const uint8_t *lut8;        /* MvgLuts::lut8[0][lane] in shared memory */
@@ -758,7 +758,7 @@ __device__ __forceinline__ void k2_chroma(const K2Ctx &c, int mode, bool left, b
 {
     const int lane = c.lane, pl = lane >> 4;
     const int x0 = (lane & 4), yo = (lane & 8) >> 1, y = yo + (lane & 3);
-    uint8_t *ct = c.ct + pl * (MVG_CT_ROWS * MVG_CT_STRIDE);
+    uint8_t *ct = c.ct + pl * MVG_CT_PLANE;
     unsigned p0, p1;
     if (mode == 0) {            /* DC, per 4x4 block */
         int st = 0, sl = 0;
@@ -880,17 +880,19 @@ k2_wavefront(K2Params p)
                             : lane < 8 ? s.ct[(lane >> 1) & 1] + K2_CO((lane & 1) * 4, -1)
                                        : s.lt + K2_TO(16 + (lane & 1) * 4, -1);
     const uint8_t *const halo_bot = lane < 4 ? halo_top + 16 * MVG_LT_STRIDE : halo_top + 8 * MVG_CT_STRIDE;
-    /* column x = 15 -> x = -1 hand-over: lanes 0..16 luma rows -1..15, lanes 17..31 and, in a second move,
-     * lanes 0..2 the 2 x 9 chroma rows */
-    const int cj = lane >= 17 ? lane - 17 : min(lane + 15, 17);            /* chroma hand-over item 0..17 */
-    uint8_t *const lc_src = lane < 17 ? s.lt + K2_TO(15, lane - 1)
-                                      : s.ct[cj / 9] + K2_CO(7, cj % 9 - 1);
-    const int lc_back = lane < 17 ? 16 : 8;
-    uint8_t *const lc_src2 = s.ct[cj / 9] + K2_CO(7, cj % 9 - 1);              /* used by lanes 0..2 */
-    /* tile write-out: lanes 0..15 one luma row (16 B), lanes 16..23 Cb rows, 24..31 Cr rows (8 B) */
+    /* tile write-out: lanes 0..15 one luma row (16 B as two 8-byte pieces), lanes 16..23 Cb rows, 24..31 Cr rows (8 B) */
     const uint8_t *const wo_src = lane < 16 ? s.lt + K2_TO(0, lane)
                                             : s.ct[(lane >> 3) & 1] + K2_CO(0, lane & 7);
     const int wo_off = lane < 16 ? lane * 16 : 256 + (lane - 16) * 8;
+    /* column x = 15 (luma) / x = 7 (chroma) -> x = -1 hand-over to the next macroblock: the last byte of what a
+     * lane has just loaded for the write-out, stored one column left of its row ... */
+    uint8_t *const lc_dst = lane < 16 ? s.lt + K2_TO(-1, lane) : s.ct[(lane >> 3) & 1] + K2_CO(-1, lane & 7);
+    const unsigned lc_sel = lane < 16 ? 7u : 3u;            /* byte 3 of the second / first 8-byte piece */
+    /* ... and row -1: lanes 3, 5, 7 hold the last word of the luma / Cb / Cr line above (see halo_top); the
+     * other lanes copy an unused byte onto itself so that the move needs no predicate */
+    const uint8_t *const cn_src = (lane == 3 || lane == 5 || lane == 7) ? halo_top + 3 : s.lt;
+    uint8_t *const cn_dst = lane == 3 ? s.lt + K2_TO(-1, -1) : lane == 5 ? s.ct[0] + K2_CO(-1, -1)
+                          : lane == 7 ? s.ct[1] + K2_CO(-1, -1) : s.lt;
     /* staging: lane l copies bytes [16 l, 16 l + 16) of a residual and, lanes 0..15, [512 + 16 l, ..) */
     uint8_t *const st_dst = reinterpret_cast<uint8_t *>(s.resid[0]) + lane * 16;
 
@@ -1010,19 +1012,20 @@ k2_wavefront(K2Params p)
 
                 /* write the macroblock out as one 384-byte tile (coalesced; scattering 16-byte row pieces over a
                  * planar picture costs more than the whole prediction: measured 4.5 ms vs 1.8 ms per 1000 pictures) */
-                {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(wo_src);
-                    if (lane < 16) *reinterpret_cast<uint4 *>(wo_run) = v;
-                    else *reinterpret_cast<uint2 *>(wo_run) = make_uint2(v.x, v.y);
-                    wo_run += 384;
-                }
+                const uint2 wa = *reinterpret_cast<const uint2 *>(wo_src);
+                uint2 wb = make_uint2(0u, 0u);
+                if (lane < 16) {
+                    wb = *reinterpret_cast<const uint2 *>(wo_src + 8);
+                    *reinterpret_cast<uint4 *>(wo_run) = make_uint4(wa.x, wa.y, wb.x, wb.y);
+                } else *reinterpret_cast<uint2 *>(wo_run) = wa;
+                wo_run += 384;
                 /* publish the bottom sample line for the row below */
                 if (publish && lane < 8)
                     mvg_st_relaxed_u64(hm_run, *reinterpret_cast<const unsigned *>(halo_bot), epoch);
                 hm_run += 8;
                 /* next macroblock: x = 15 becomes x = -1 (luma rows -1..15, chroma x = 7, rows -1..7) */
-                lc_src[-lc_back] = lc_src[0];
-                if (lane < 3) lc_src2[-8] = lc_src2[0];
+                *lc_dst = (uint8_t)__byte_perm(wa.y, wb.y, lc_sel);
+                *cn_dst = *cn_src;
                 __syncwarp();
                 K2_PROF(const long long t4 = clock64(); pc[1] += t1 - t0; pc[2] += t2 - t1; pc[3] += t3 - t2; pc[4] += t4 - t3;)
             }

@@ -72,7 +72,10 @@ def test_pred_tap_tables_reproduce_the_oracle_predictors():
     lib.mvg_build_luts(C.byref(luts))
     lut4 = np.frombuffer(luts.lut4, np.uint32).reshape(16, 32)
     lut8 = np.frombuffer(luts.lut8, np.uint32).reshape(9, 32)
-    STRIDE, BIAS = 48, 49                                   # MVG_LT_STRIDE, MVG_LUT4_BIAS
+    import re
+    hdr = (ROOT / "minivideo_b200" / "csrc" / "mvg_internal.h").read_text()
+    STRIDE = int(re.search(r"#define MVG_LT_STRIDE\s+(\d+)", hdr).group(1))
+    BIAS = STRIDE + 1                                       # MVG_LUT4_BIAS
     taps4 = lambda row: np.stack([(lut4[row, :16] >> (8 * k)) & 255 for k in range(4)], -1).astype(np.int64) - BIAS
     assert np.array_equal(lut4[:, :16], lut4[:, 16:])       # both lane halves read the same taps
     # rows 11 / 15: modes 3 / 7 with the taps on p[4..7,-1] moved to p[3,-1]
