@@ -13,6 +13,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "h264_cavlc_tables.h"
 
@@ -626,13 +629,14 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
     memset(w->tot_luma, 0, N * 16);
     memset(w->tot_chroma[0], 0, N * 4);
     memset(w->tot_chroma[1], 0, N * 4);
+    if (w->packed) memset(w->mb_levels, 0, sizeof w->mb_levels);      /* a failed picture may have left levels behind */
 
     for (int my = 0; my < H; my++)
         for (int mx = 0; mx < W; mx++) {
             const size_t mbi = pic_slot * N + (size_t)my * W + mx;
             int16_t *cf = w->packed ? w->mb_levels : out->coeff + mbi * 384;
             uint8_t *modes = out->luma_modes + mbi * 16;
-            memset(cf, 0, 768);
+            if (!w->packed) memset(cf, 0, 768);         /* packed mode: pack_mb() hands the buffer back zeroed */
             memset(modes, 0, 16);
             uint32_t mb_type = br_ue(&b);
             if (mb_type == 25) return wfail(w, MVG_UNSUPPORTED, "picture %d: I_PCM macroblock (h264_macroblock.c:151-154)", idr_index);
@@ -745,30 +749,42 @@ static int pack_mb(worker_t *w, size_t m)
         if (!w2) return 0;
         w->pk_words = w2; w->pk_cap = cap;
     }
-    const int16_t *c = w->mb_levels;
-    uint16_t *dst = w->pk_words + w->pk_n, *lv;
+    int16_t *c = w->mb_levels;
+    uint16_t *dst = w->pk_words + w->pk_n;
     uint32_t nzb = 0;
-    uint16_t masks[24];
-    int n_coded = 0;
+    uint16_t masks[24], lv[384];
+    int n_coded = 0, n_lv = 0;
+    /* one pass: per block the mask of non-zero levels, the levels themselves in scan order, and the block is
+     * zeroed again for the next macroblock (so that the parser needs no 768-byte memset per macroblock) */
     for (int b = 0; b < 24; b++) {
+        int16_t *cb = c + b * 16;
+#if defined(__SSE2__)
+        const __m128i z = _mm_setzero_si128();
+        const __m128i v0 = _mm_loadu_si128((const __m128i *)cb), v1 = _mm_loadu_si128((const __m128i *)(cb + 8));
+        unsigned mask = ~(unsigned)_mm_movemask_epi8(_mm_packs_epi16(_mm_cmpeq_epi16(v0, z), _mm_cmpeq_epi16(v1, z))) & 0xffffu;
+        if (!mask) continue;
+        _mm_storeu_si128((__m128i *)cb, z); _mm_storeu_si128((__m128i *)(cb + 8), z);
+        const uint16_t keep = (uint16_t)mask;
+        int16_t tmp[16];
+        _mm_storeu_si128((__m128i *)tmp, v0); _mm_storeu_si128((__m128i *)(tmp + 8), v1);
+        while (mask) { int k = __builtin_ctz(mask); mask &= mask - 1; lv[n_lv++] = (uint16_t)tmp[k]; }
+#else
         uint64_t q[4];
-        memcpy(q, c + b * 16, 32);
+        memcpy(q, cb, 32);
         if (!(q[0] | q[1] | q[2] | q[3])) continue;
         unsigned mask = 0;
-        for (int k = 0; k < 16; k++) mask |= (unsigned)(c[b * 16 + k] != 0) << k;
+        for (int k = 0; k < 16; k++) if (cb[k]) { mask |= 1u << k; lv[n_lv++] = (uint16_t)cb[k]; }
+        memset(cb, 0, 32);
+        const uint16_t keep = (uint16_t)mask;
+#endif
         nzb |= 1u << b;
-        masks[n_coded++] = (uint16_t)mask;
+        masks[n_coded++] = keep;
     }
     w->pk_nzb[m] = nzb;
     w->pk_off[m] = (uint32_t)w->pk_n;
     memcpy(dst, masks, (size_t)n_coded * sizeof *dst);
-    lv = dst + n_coded;
-    for (int b = 0, i = 0; b < 24; b++)
-        if ((nzb >> b) & 1u) {
-            unsigned mask = masks[i++];
-            while (mask) { int k = __builtin_ctz(mask); mask &= mask - 1; *lv++ = (uint16_t)c[b * 16 + k]; }
-        }
-    w->pk_n = (size_t)(lv - w->pk_words);
+    memcpy(dst + n_coded, lv, (size_t)n_lv * sizeof *dst);
+    w->pk_n += (size_t)(n_coded + n_lv);
     return 1;
 }
 
