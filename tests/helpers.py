@@ -3,6 +3,8 @@ from __future__ import annotations
 
 import hashlib
 import json
+import struct
+import zlib
 from pathlib import Path
 
 import numpy as np
@@ -62,3 +64,43 @@ def oracle_reconstruct_with_tables(soa, ls4, ls8, want_residual=False):
         L.oracle_reconstruct_picture(C.byref(sps), *[p_(a) for a in arrs], p_(y), p_(cb), p_(cr),
                                      p_(r) if r is not None else None)
     return yuv, res
+
+
+def png_decode(png: bytes) -> np.ndarray:
+    """Minimal PNG reader (8-bit truecolour, no interlace) -- independent of both writers."""
+    assert png[:8] == bytes([137, 80, 78, 71, 13, 10, 26, 10])
+    pos, idat, w, h = 8, b"", 0, 0
+    while pos < len(png):
+        n, tag = struct.unpack(">I4s", png[pos:pos + 8])
+        body = png[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", png[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body)
+        if tag == b"IHDR":
+            w, h, depth, ctype, comp, filt, lace = struct.unpack(">IIBBBBB", body)
+            assert (depth, ctype, comp, filt, lace) == (8, 2, 0, 0, 0)
+        elif tag == b"IDAT":
+            idat += body
+        pos += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 3 * w + 1)
+    out = np.zeros((h, 3 * w), np.int32)
+    for y in range(h):
+        f, line = int(raw[y, 0]), raw[y, 1:].astype(np.int32)
+        up = out[y - 1] if y else np.zeros(3 * w, np.int32)
+        if f == 0:
+            out[y] = line
+        elif f == 2:
+            out[y] = (line + up) & 255
+        else:
+            for i in range(3 * w):
+                a = out[y, i - 3] if i >= 3 else 0
+                c = up[i - 3] if i >= 3 else 0
+                b = up[i]
+                if f == 1:
+                    pred = a
+                elif f == 3:
+                    pred = (a + b) >> 1
+                else:
+                    p = a + b - c
+                    pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
+                    pred = a if pa <= pb and pa <= pc else (b if pb <= pc else c)
+                out[y, i] = (line[i] + pred) & 255
+    return out.reshape(h, w, 3).astype(np.uint8)

@@ -2,14 +2,14 @@
 minivideo/src/stb_image_write.h, the call export_idr_png() makes, export.c:539): byte for byte, plus an
 independent check that the file is a valid PNG holding the same pixels (zlib inflate + unfilter in numpy)."""
 import ctypes as C
-import struct
 import subprocess
 import tempfile
-import zlib
 from pathlib import Path
 
 import numpy as np
 import pytest
+
+from helpers import png_decode as decode
 
 ROOT = Path(__file__).resolve().parent.parent
 REF_PNG = ROOT / "oracle" / "_ref" / "ref_png"
@@ -43,46 +43,6 @@ def reference(img: np.ndarray) -> bytes:
         np.ascontiguousarray(img, np.uint8).tofile(Path(d) / "in.rgb")
         subprocess.run([str(REF_PNG), str(w), str(h), str(Path(d) / "in.rgb"), str(Path(d) / "out.png")], check=True)
         return (Path(d) / "out.png").read_bytes()
-
-
-def decode(png: bytes) -> np.ndarray:
-    """Minimal PNG reader (8-bit truecolour, no interlace) -- independent of both writers."""
-    assert png[:8] == bytes([137, 80, 78, 71, 13, 10, 26, 10])
-    pos, idat, w, h = 8, b"", 0, 0
-    while pos < len(png):
-        n, tag = struct.unpack(">I4s", png[pos:pos + 8])
-        body = png[pos + 8:pos + 8 + n]
-        assert struct.unpack(">I", png[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body)
-        if tag == b"IHDR":
-            w, h, depth, ctype, comp, filt, lace = struct.unpack(">IIBBBBB", body)
-            assert (depth, ctype, comp, filt, lace) == (8, 2, 0, 0, 0)
-        elif tag == b"IDAT":
-            idat += body
-        pos += 12 + n
-    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 3 * w + 1)
-    out = np.zeros((h, 3 * w), np.int32)
-    for y in range(h):
-        f, line = int(raw[y, 0]), raw[y, 1:].astype(np.int32)
-        up = out[y - 1] if y else np.zeros(3 * w, np.int32)
-        if f == 0:
-            out[y] = line
-        elif f == 2:
-            out[y] = (line + up) & 255
-        else:
-            for i in range(3 * w):
-                a = out[y, i - 3] if i >= 3 else 0
-                c = up[i - 3] if i >= 3 else 0
-                b = up[i]
-                if f == 1:
-                    pred = a
-                elif f == 3:
-                    pred = (a + b) >> 1
-                else:
-                    p = a + b - c
-                    pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
-                    pred = a if pa <= pb and pa <= pc else (b if pb <= pc else c)
-                out[y, i] = (line[i] + pred) & 255
-    return out.reshape(h, w, 3).astype(np.uint8)
 
 
 def pictures():

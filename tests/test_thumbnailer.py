@@ -154,6 +154,25 @@ def test_cli_scaled_thumbnail_is_the_box_average(cli):
 
 
 @pytest.mark.gpu
+def test_cli_scaled_png_and_unwritable_directory(cli):
+    """-s with PNG output holds the same pixels as -s with BMP output; an unwritable output directory is an error
+    exit, not a silent success."""
+    from minivideo_b200 import synth
+    stream, _ = synth.generate(2, "cif", seed=913)
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "in.264").write_bytes(stream)
+        for fmt in ("png", "bmp"):
+            r = subprocess.run([str(MV), "-i", str(Path(d) / "in.264"), "-f", fmt, "-n", "2", "-s", "2", "-o", d], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+        from helpers import png_decode
+        png = png_decode((Path(d) / "in_1.png").read_bytes())
+        bmp = np.fromfile(Path(d) / "in_1.bmp", np.uint8)[54:].reshape(144, 176, 3)[::-1, :, ::-1]
+        assert png.shape == (144, 176, 3) and np.array_equal(png, bmp)
+        r = subprocess.run([str(MV), "-i", str(Path(d) / "in.264"), "-f", "bmp", "-o", str(Path(d) / "missing" / "dir")], capture_output=True, text=True)
+        assert r.returncode != 0 and "cannot write" in r.stderr
+
+
+@pytest.mark.gpu
 def test_cli_2160p_distributed_extraction(cli):
     """BASELINE.json configs[4]: a 3840x2160 High-profile stream in 'distributed' extraction mode, through the
     CLI, against the files of the reference CLI (which may abort after writing them, see above)."""
