@@ -202,11 +202,19 @@ extern "C" void mvg_build_luts(MvgLuts *out)
     memset(out, 0, sizeof *out);
     for (int row = 0; row < 16; row++) {
         const int mode = row == 11 ? 3 : row == 15 ? 7 : row;
-        if (mode > 8 || mode == 2) continue;
+        /* DC (h264_intra_prediction.c:554-600) as tap rows: row 9 = the four samples above, (sum + 2) >> 2;
+         * row 10 = the four samples to the left; row 2 (both sides available) = even x the four above, odd x the
+         * four to the left: kernel 2 adds the half-sum of the lane next door and shifts by 3 */
+        const bool dc = row == 2 || row == 9 || row == 10;
+        if ((mode > 8 && !dc)) continue;
         const bool tr = row < 9;
         for (int y = 0; y < 4; y++)
             for (int x = 0; x < 4; x++) {
-                const Taps t = nxn_taps(4, mode, x, y);
+                Taps t = nxn_taps(4, mode, x, y);
+                if (dc) {
+                    const bool above = row == 9 || (row == 2 && !(x & 1));
+                    for (int k = 0; k < 4; k++) t.r[k] = above ? T(k) : L(k);
+                }
                 uint32_t word = 0;
                 for (int k = 0; k < 4; k++) {
                     int off;

@@ -52,7 +52,9 @@ struct MvgMbCtl { uint32_t w0, w1, w2, w3; };
  *   to (origin of the lane's block) - MVG_LUT4_BIAS; the two halves hold the same values (a lane reads
  *   word `lane`: no bank conflicts).  Rows 0..8 are the nine modes with p[4..7,-1] available, rows 11 and
  *   15 are modes 3 and 7 when they are not (taps stop at p[3,-1], h264_intra_prediction.c:431-439).
- *   Row 2 (DC) is unused.
+ *   DC: row 9 = the four samples above, row 10 = the four to the left (one side available: (sum + 2) >> 2 like
+ *   any other row); row 2 (both sides) = lanes with even x the four above, odd x the four to the left, the
+ *   kernel adds the half-sum of lane ^ 1 and shifts by 3.
  * lut8[mode][lane]: the Intra8x8 predictors read a filtered neighbour line of 32-bit words
  *   {p', f2 = (p'[n]+p'[n+1]+1)>>1, f3 = (p'[n-1]+2p'[n]+p'[n+1]+2)>>2} (n = 0..7 p'[-1,7..0], 8 p'[-1,-1],
  *   9..24 p'[0..15,-1], MVG_N8_DC the DC value).  A lane predicts two horizontally adjacent samples, x =

@@ -641,53 +641,81 @@ __device__ __forceinline__ void k2_luma16(const K2Ctx &c, int mode, bool left, b
  * an address: offset = dp4a(entry, 1 << 8k, lane's block offset).  Modes 3 and 7 without an up-right
  * neighbour use rows 11 and 15, whose taps stop at p[3,-1] (h264_intra_prediction.c:431-439). */
 template <int T>
-__device__ __forceinline__ void k2_luma4_step(const K2Ctx &c, unsigned seq, bool availA, bool availB)
+__device__ __forceinline__ void k2_luma4_step(const K2Ctx &c, unsigned seq, unsigned dcsteps)
 {
     constexpr int bx0 = T & 1, by0 = T >> 1;
     constexpr bool v0 = T <= 7, v1 = T >= 2;
     constexpr int org1 = K2_TO(bx0 * 4 + 8, by0 * 4 - 4);       /* origin of the half-1 block */
     constexpr int blk0 = (bx0 & 1) | ((by0 & 1) << 1) | ((bx0 >> 1) << 2) | ((by0 >> 1) << 3);
     constexpr int sh = 4 * (T & 7);
-    const bool half = c.lane >= 16;
-    if ((v0 && v1) || (half ? v1 : v0)) {
-        const unsigned m = (sh >= 7 ? (seq >> (sh >= 7 ? sh - 7 : 0)) : (seq << (sh >= 7 ? 0 : 7 - sh))) & 0x780u;
-        int pred;
-        if (m == 0x100u) {          /* DC (h264_intra_prediction.c:554-600) */
-            const bool left = half ? true : (bx0 > 0 || availA);
-            const bool up = (half ? by0 - 1 > 0 : by0 > 0) || availB;
-            const uint8_t *o = c.lt + org1 + c.h4;
-            int sum = 0;
-            if (up) sum = mvg_sum4(*reinterpret_cast<const unsigned *>(o - MVG_LT_STRIDE));
-            if (left) sum += (int)o[-1] + (int)o[MVG_LT_STRIDE - 1] + (int)o[2 * MVG_LT_STRIDE - 1] + (int)o[3 * MVG_LT_STRIDE - 1];
-            pred = (left && up) ? (sum + 4) >> 3 : (left || up) ? (sum + 2) >> 2 : 128;
-        } else {
-            unsigned e;
-            asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(m | c.lut4));
-            const uint8_t *nb = c.lt + (org1 - MVG_LUT4_BIAS);
-            pred = ((int)nb[__dp4a(e, c.sel[0], c.h4)] + (int)nb[__dp4a(e, c.sel[1], c.h4)] +
-                    (int)nb[__dp4a(e, c.sel[2], c.h4)] + (int)nb[__dp4a(e, c.sel[3], c.h4)] + 2) >> 2;
-        }
-        const int r = *reinterpret_cast<const int16_t *>(c.resid + blk0 * 32 + ((by0 & 1) ? c.r4odd : c.r4even));
-        c.lt[org1 + c.s4] = (uint8_t)mvg_add_clip8(pred, r);
+    /* Every lane runs the whole step; in steps 0, 1, 8, 9 one half has no block and computes on whatever lies at
+     * its (in-bounds) addresses -- only the store is conditional.  That keeps the shuffle in converged code. */
+    const unsigned m = (sh >= 7 ? (seq >> (sh >= 7 ? sh - 7 : 0)) : (seq << (sh >= 7 ? 0 : 7 - sh))) & 0x780u;
+    unsigned e;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(m | c.lut4));
+    const uint8_t *nb = c.lt + (org1 - MVG_LUT4_BIAS);
+    int sum = (int)nb[__dp4a(e, c.sel[0], c.h4)] + (int)nb[__dp4a(e, c.sel[1], c.h4)] +
+              (int)nb[__dp4a(e, c.sel[2], c.h4)] + (int)nb[__dp4a(e, c.sel[3], c.h4)] + 2;
+    int shift = 2;
+    if (dcsteps & (1u << T)) {              /* warp-uniform: some block of this step is DC with both sides available */
+        const int other = __shfl_xor_sync(MVG_FULL, sum, 1);
+        if (m == 0x100u) { sum += other; shift = 3; }
     }
+    const int r = *reinterpret_cast<const int16_t *>(c.resid + blk0 * 32 + ((by0 & 1) ? c.r4odd : c.r4even));
+    const int v = mvg_add_clip8(sum >> shift, r);
+    if ((v0 && v1) || (c.lane >= 16 ? v1 : v0)) c.lt[org1 + c.s4] = (uint8_t)v;
     __syncwarp();
+}
+
+/* nibbles equal to 2 (DC), as bit 0 of the nibble */
+__device__ __forceinline__ unsigned k2_dc_nibbles(unsigned seq)
+{
+    return (seq >> 1) & ~seq & ~(seq >> 2) & ~(seq >> 3) & 0x11111111u;
 }
 
 __device__ __forceinline__ void k2_luma4(const K2Ctx &c, unsigned w1, unsigned w2, bool availA, bool availB, bool availC)
 {
-    unsigned seq = c.lane >= 16 ? w2 : w1;
+    const bool half = c.lane >= 16;
+    unsigned seq = half ? w2 : w1;
     const unsigned notr = c.m4c | (availB ? 0u : c.m4b) | (availC ? 0u : c.m4cc);
     seq |= (seq & (seq >> 1) & notr) << 3;          /* modes 3, 7 -> 11, 15 where p[4..7,-1] are not available */
-    k2_luma4_step<0>(c, seq, availA, availB);
-    k2_luma4_step<1>(c, seq, availA, availB);
-    k2_luma4_step<2>(c, seq, availA, availB);
-    k2_luma4_step<3>(c, seq, availA, availB);
-    k2_luma4_step<4>(c, seq, availA, availB);
-    k2_luma4_step<5>(c, seq, availA, availB);
-    k2_luma4_step<6>(c, seq, availA, availB);
-    k2_luma4_step<7>(c, seq, availA, availB);
-    k2_luma4_step<8>(c, seq, availA, availB);
-    k2_luma4_step<9>(c, seq, availA, availB);
+    if (!availA || !availB) {
+        /* DC at the picture edge (h264_intra_prediction.c:554-600): blocks of the top row without a macroblock above
+         * use the left samples only (row 10), blocks of the left column without a macroblock to the left the ones
+         * above (row 9).  Block 0 with neither: the caller has set both neighbour lines to 128, it stays row 2. */
+        const unsigned d = k2_dc_nibbles(seq);
+        unsigned top = 0, left = 0;
+        if (!availB) top = half ? 0x00001100u : (availA ? 0x00000011u : 0x00000010u);
+        if (!availA && !half) left = availB ? 0x01010101u : 0x01010100u;
+        seq |= (d & top) << 3;                      /* 2 -> 10 */
+        seq ^= (d & left) * 0xBu;                   /* 2 -> 9  */
+        if (!availA && !availB) {                   /* first macroblock of a picture: p[-1,0..3] = p[0..3,-1] = 128 */
+            if (c.lane < 4) c.lt[K2_TO(-1, 0) + c.lane * MVG_LT_STRIDE] = 128;
+            if (c.lane == 4) *reinterpret_cast<unsigned *>(c.lt + K2_TO(0, -1)) = 0x80808080u;
+            __syncwarp();
+        }
+    }
+    /* steps in which a block is DC with both sides: nibble t of either half -> bit t; half 0 covers steps 0..7 with
+     * nibbles 0..7, half 1 steps 2..9 with nibbles 2..7, 0, 1 (see MvgMbCtl) */
+    unsigned dcsteps;
+    {
+        const unsigned d = k2_dc_nibbles(seq);
+        unsigned bits = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) bits |= ((d >> (4 * t)) & 1u) << t;
+        if (half) bits = (bits & 0xfcu) | ((bits & 3u) << 8);
+        dcsteps = __reduce_or_sync(MVG_FULL, bits);
+    }
+    k2_luma4_step<0>(c, seq, dcsteps);
+    k2_luma4_step<1>(c, seq, dcsteps);
+    k2_luma4_step<2>(c, seq, dcsteps);
+    k2_luma4_step<3>(c, seq, dcsteps);
+    k2_luma4_step<4>(c, seq, dcsteps);
+    k2_luma4_step<5>(c, seq, dcsteps);
+    k2_luma4_step<6>(c, seq, dcsteps);
+    k2_luma4_step<7>(c, seq, dcsteps);
+    k2_luma4_step<8>(c, seq, dcsteps);
+    k2_luma4_step<9>(c, seq, dcsteps);
 }
 
 /* ---- Intra8x8 luma: 4 blocks in order ------------------------------------------ */
