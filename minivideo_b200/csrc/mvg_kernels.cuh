@@ -507,7 +507,9 @@ struct K2Params {
 #ifndef K2_POLL_NS
 #define K2_POLL_NS   100        /* first sleep of a row that has caught up with the row above; doubles up to 8x */
 #endif
+#ifndef K2_WARPS
 #define K2_WARPS     16         /* warps per CTA; two CTAs per SM                              */
+#endif
 #define K2_CTL_CHUNK 32         /* control records per chunk (one 16-byte copy per lane)       */
 #define K2_RING      4          /* residual ring slots (power of two; three are live at a time)   */
 #define K2_TO(x, y)  (((y) + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + (x))    /* luma tile offset of sample (x, y)   */
