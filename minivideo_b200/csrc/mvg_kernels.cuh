@@ -702,9 +702,9 @@ __device__ __forceinline__ void k2_luma4(const K2Ctx &c, unsigned w1, unsigned w
     unsigned dcsteps;
     {
         const unsigned d = k2_dc_nibbles(seq);
-        unsigned bits = 0;
-#pragma unroll
-        for (int t = 0; t < 8; t++) bits |= ((d >> (4 * t)) & 1u) << t;
+        /* bit 4t -> bit t: pair the nibbles of a byte, then gather the four 2-bit fields with a multiplication
+         * (fields land at bits 24, 26, 28, 30 of the product; all partial products are disjoint, so no carries) */
+        unsigned bits = (((d | (d >> 3)) & 0x03030303u) * 0x01041040u) >> 24;
         if (half) bits = (bits & 0xfcu) | ((bits & 3u) << 8);
         dcsteps = __reduce_or_sync(MVG_FULL, bits);
     }
