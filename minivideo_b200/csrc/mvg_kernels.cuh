@@ -515,9 +515,12 @@ struct K2Params {
 #define K2_TO(x, y)  (((y) + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + (x))    /* luma tile offset of sample (x, y)   */
 #define K2_CO(x, y)  (((y) + 1) * MVG_CT_STRIDE + MVG_CT_XOFF + (x))    /* chroma tile offset of sample (x, y) */
 
+/* Member order matters to the Intra4x4 steps: lanes without a block in a step still run it and read up to 64 bytes
+ * below resid[] and 140 bytes below lt[] (and past the end of lt[] into ct[]); those reads must stay inside this
+ * warp's record, hence ctl[] first. */
 struct K2WarpSmem {
-    __align__(16) int16_t  resid[K2_RING][384];         /* residual ring, filled by per-lane async copies two macroblocks ahead */
     __align__(16) MvgMbCtl ctl[2 * K2_CTL_CHUNK];       /* control records, two chunks: record of macroblock mx at [mx & 63]      */
+    __align__(16) int16_t  resid[K2_RING][384];         /* residual ring, filled by per-lane async copies two macroblocks ahead */
     __align__(16) uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
     __align__(16) uint8_t  ct[2][MVG_CT_PLANE];
     __align__(16) uint32_t n8[36];                      /* Intra8x8 neighbour line: p' | f2 << 8 | f3 << 16; [32] = DC */
