@@ -523,7 +523,7 @@ struct K2WarpSmem {
     __align__(16) int16_t  resid[K2_RING][384];         /* residual ring, filled by per-lane async copies two macroblocks ahead */
     __align__(16) uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
     __align__(16) uint8_t  ct[2][MVG_CT_PLANE];
-    __align__(16) uint32_t n8[36];                      /* Intra8x8 neighbour line: p' | f2 << 8 | f3 << 16; [32] = DC */
+    __align__(16) uint8_t  n8[MVG_N8_BYTES];            /* Intra8x8 neighbour line: byte planes p', f2, f3; [MVG_N8_DC] = DC */
 };
 
 /* dynamic shared memory: warp records and the tap tables (2 KB aligned, see the kernel) */
@@ -569,7 +569,7 @@ __device__ __forceinline__ unsigned mvg_pairs_to_bytes(unsigned a, unsigned b) {
  * accesses take the form [lane register + uniform base + immediate]) */
 struct K2Ctx {
     uint8_t *lt, *ct;           /* luma tile, chroma tiles (plane stride MVG_CT_PLANE) */
-    uint32_t *n8;
+    uint8_t *n8;
     const uint8_t *resid;       /* residual buffer of the current macroblock */
     const uint8_t *lut8;        /* MvgLuts::lut8[0][lane] in shared memory */
     int lane;
@@ -754,7 +754,7 @@ __device__ __forceinline__ void k2_luma8_block(const K2Ctx &c, unsigned modes, u
     int fn = __shfl_down_sync(MVG_FULL, filt, 1);
     if (lane == 24) fn = filt;
     const int f2 = (filt + fn + 1) >> 1, f3 = (fp + 2 * filt + fn + 2) >> 2;
-    c.n8[lane] = (unsigned)filt | ((unsigned)f2 << 8) | ((unsigned)f3 << 16);
+    c.n8[lane] = (uint8_t)filt; c.n8[32 + lane] = (uint8_t)f2; c.n8[64 + lane] = (uint8_t)f3;
     if (mode == 2) {                                        /* warp-uniform */
         int v = 0;
         if (lane < 8 && left) v = filt;
@@ -762,14 +762,11 @@ __device__ __forceinline__ void k2_luma8_block(const K2Ctx &c, unsigned modes, u
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MVG_FULL, v, o);
         v = (left && up) ? (v + 8) >> 4 : (left || up) ? (v + 4) >> 3 : 128;
-        if (lane == 0) c.n8[MVG_N8_DC] = (unsigned)v;
+        if (lane == 0) c.n8[MVG_N8_DC] = (uint8_t)v;
     }
     __syncwarp();
     const unsigned e = *reinterpret_cast<const unsigned *>(c.lut8 + mode * 128);
-    const uint8_t *n8b = reinterpret_cast<const uint8_t *>(c.n8);
-    const unsigned w0 = *reinterpret_cast<const unsigned *>(n8b + (e & 0xffu)) >> __byte_perm(e, 0, 0x4441);
-    const unsigned w1 = *reinterpret_cast<const unsigned *>(n8b + __byte_perm(e, 0, 0x4442)) >> (e >> 24);
-    const unsigned pp = __byte_perm(w0, w1, 0x5410) & 0x00ff00ffu;
+    const unsigned pp = (unsigned)c.n8[e & 0xffffu] | ((unsigned)c.n8[e >> 16] << 16);
     const unsigned r2 = *reinterpret_cast<const unsigned *>(c.resid + B8 * 128 + lane * 4);
     *reinterpret_cast<uint16_t *>(lt + org + c.s8) = (uint16_t)__byte_perm(mvg_add_clip8x2(pp, r2), 0, 0x4420);
     __syncwarp();
