@@ -36,8 +36,7 @@
  *                                                                   = blkIdx 4,5,6,7,12,13,14,15
  *     so that both lane halves find the mode of step t at nibble (t & 7).
  *     Intra8x8 modes sit in nibbles 0..3 of w1
- * w3: bit b set <=> 4x4 block b has a non-zero residual sample
- *     (b = 0..15 luma blocks in decoding order, 16..19 Cb, 20..23 Cr)          */
+ * w3: reserved (0)                                                             */
 struct MvgMbCtl { uint32_t w0, w1, w2, w3; };
 
 /* ---- prediction tables -----------------------------------------------------

@@ -330,11 +330,10 @@ k1_dequant_idct(K1Params p)
 
         /* ---------------- classify the 4x4 blocks, compact the general ones ---------------- */
         int n4 = 0, n8 = 0;
-        unsigned nzbal[3];
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             const int u = lane + 32 * r, j = u / 24, b = u - 24 * j;
-            bool general = false, nonzero = false, nz8q = false;
+            bool general = false, nz8q = false;
             const unsigned mw = j < nmb ? s.meta[j] : 0u;
             const int kind = mw & 255, qp = (signed char)(mw >> 8);
             const bool is8 = kind == MVG_MB_I8x8 && b < 16;
@@ -344,7 +343,7 @@ k1_dequant_idct(K1Params p)
                 const unsigned rest = (w0.x & 0xffff0000u) | w0.y | w0.z | w0.w | w1.x | w1.y | w1.z | w1.w;
                 const int dcraw = (short)(w0.x & 0xffff);
                 if (is8) nz8q = (rest | (unsigned)dcraw) != 0;
-                else if (rest) general = nonzero = true;
+                else if (rest) general = true;
                 else {
                     const bool has_dc = b >= 16 || kind == MVG_MB_I16x16;
                     int rv = 0;
@@ -355,8 +354,7 @@ k1_dequant_idct(K1Params p)
                         rv = (d + 32) >> 6;
                     }
                     rv = min(max(rv, -512), 511);
-                    nonzero = rv != 0;
-                    if (nonzero || dcraw) {
+                    if (rv != 0 || dcraw) {
                         const unsigned pk = (unsigned)(rv & 0xffff) * 0x10001u;
                         blk[0] = make_uint4(pk, pk, pk, pk); blk[1] = make_uint4(pk, pk, pk, pk);
                     }
@@ -372,7 +370,6 @@ k1_dequant_idct(K1Params p)
             const unsigned lb = __ballot_sync(MVG_FULL, lead8);
             if (lead8) s.list8[n8 + __popc(lb & ((1u << lane) - 1))] = (uint8_t)(j * 4 + (b >> 2));
             n8 += __popc(lb);
-            nzbal[r] = __ballot_sync(MVG_FULL, nonzero || any8);
         }
         __syncwarp();
 
@@ -460,11 +457,6 @@ k1_dequant_idct(K1Params p)
         /* ---------------- residual out (one bulk store) + control records ---------------- */
         if (lane == 0) mvg_bulk_store(p.resid + mb0 * 384, tile, (unsigned)nmb * 768u);
         {
-            /* 96-bit non-zero map -> 24 bits per macroblock */
-            const unsigned long long lo = (unsigned long long)nzbal[0] | ((unsigned long long)nzbal[1] << 32);
-            const unsigned hi = nzbal[2];
-            const unsigned nz = mj == 0 ? nzbal[0] : mj == 1 ? (unsigned)(lo >> 24)
-                              : mj == 2 ? ((unsigned)(lo >> 48) | (hi << 16)) : (hi >> 8);
             /* 4 mode bytes -> 4 nibbles; lane 8j collects its macroblock's record */
             unsigned nib = (meta & 0xF) | ((meta >> 4) & 0xF0) | ((meta >> 8) & 0xF00) | ((meta >> 12) & 0xF000);
             const unsigned n1 = __shfl_down_sync(MVG_FULL, nib, 1), n2 = __shfl_down_sync(MVG_FULL, nib, 2);
@@ -474,7 +466,7 @@ k1_dequant_idct(K1Params p)
             if (mt == 0 && mj < nmb)
                 *reinterpret_cast<uint4 *>(p.ctl + mb0 + mj) =
                     make_uint4((k4 & 255) | ((k6 & 255) << 8) | ((k7 & 255) << 16), nib | (n2 << 16),
-                               __funnelshift_l(n1 | (n3 << 16), n1 | (n3 << 16), 8), nz & 0x00FFFFFFu);
+                               __funnelshift_l(n1 | (n3 << 16), n1 | (n3 << 16), 8), 0u);
         }
         __syncwarp();
     }
