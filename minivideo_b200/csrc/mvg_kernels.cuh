@@ -227,6 +227,7 @@ k1_dequant_idct(K1Params p)
     __shared__ int32_t s_ls4q[3 * 52 * 16];                     /* per qP; << (qP/6-4) folded in when qP >= 24 */
     __shared__ int32_t s_ls8[6 * 64];
     __shared__ uint8_t s_zz8inv[64];
+    __shared__ uint16_t s_qpc[2][52];                           /* QPC | QPC / 6 << 8 for Cb, Cr by QPY (derivChromaQP) */
     extern __shared__ __align__(128) uint8_t k1_smem[];         /* K1WarpSmem x K1_WARPS (dynamic: above the 48 KB static limit) */
     K1WarpSmem *s_warp = reinterpret_cast<K1WarpSmem *>(k1_smem);
 
@@ -234,7 +235,10 @@ k1_dequant_idct(K1Params p)
     for (int i = threadIdx.x; i < 3 * 52 * 16; i += blockDim.x) s_ls4q[i] = (&p.tab->ls4q[0][0][0])[i];
     for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) s_ls8[i] = (&p.tab->ls8[0][0])[i];
     if (threadIdx.x < 64) s_zz8inv[threadIdx.x] = p.tab->zz8inv[threadIdx.x];
-    const int cb_off = p.tab->cb_qp_offset, cr_off = p.tab->cr_qp_offset;
+    if (threadIdx.x < 104) {
+        const int pl = threadIdx.x >= 52, qpc = mvg_chroma_qp(threadIdx.x - 52 * pl, pl ? p.tab->cr_qp_offset : p.tab->cb_qp_offset);
+        s_qpc[pl][threadIdx.x - 52 * pl] = (uint16_t)(qpc | ((qpc / 6) << 8));
+    }
 
     const int lane = threadIdx.x & 31;
     K1WarpSmem &s = s_warp[threadIdx.x >> 5];
@@ -250,13 +254,19 @@ k1_dequant_idct(K1Params p)
     /* side information of a group, one 32-bit word per lane: lane = 8*j + t for macroblock j;
      * t = 0..3 luma modes 4t..4t+3, t = 4 mb_kind, 5 QPY, 6 Intra16x16PredMode, 7 intra_chroma_pred_mode */
     const int mj = lane >> 3, mt = lane & 7;
+    /* per-lane source: a word of luma_modes (16 bytes per macroblock) or a byte of one of the four byte arrays */
+    const uint8_t *const meta_src = mt < 4 ? p.luma_modes + 4 * mt : mt == 4 ? p.mb_kind
+                                  : mt == 5 ? reinterpret_cast<const uint8_t *>(p.qp_y) : mt == 6 ? p.i16_mode : p.chroma_mode;
+    const int meta_stride = mt < 4 ? 16 : 1;
     auto load_meta = [&](long long grp) -> unsigned {
         const long long mb = grp * K1_GROUP + mj;
-        if (mb >= p.n_mbs) return 0u;
-        if (mt < 4) return __ldg(reinterpret_cast<const unsigned *>(p.luma_modes + mb * 16) + mt);
-        const uint8_t *src = mt == 4 ? p.mb_kind : mt == 5 ? reinterpret_cast<const uint8_t *>(p.qp_y)
-                           : mt == 6 ? p.i16_mode : p.chroma_mode;
-        return (unsigned)__ldg(src + mb);
+        unsigned v = 0u;
+        if (mb < p.n_mbs) {
+            const uint8_t *src = meta_src + mb * meta_stride;
+            if (mt < 4) v = __ldg(reinterpret_cast<const unsigned *>(src));
+            else v = (unsigned)__ldg(src);
+        }
+        return v;
     };
     auto issue_load = [&](int buf, long long grp) {
         const long long mb0 = grp * K1_GROUP;
@@ -307,8 +317,8 @@ k1_dequant_idct(K1Params p)
                 const int pl = mt - 4;
                 const int16_t *cc = cf + 256 + pl * 64;
                 const int c00 = cc[0], c01 = cc[16], c10 = cc[32], c11 = cc[48];
-                const int qpc = mvg_chroma_qp(qp_j, pl ? cr_off : cb_off);
-                const int qd = qpc / 6, ls00 = s_ls4[((pl + 1) * 6 + (qpc - 6 * qd)) * 16];
+                const int qe = s_qpc[pl][qp_j], qpc = qe & 255, qd = qe >> 8;
+                const int ls00 = s_ls4[((pl + 1) * 6 + (qpc - 6 * qd)) * 16];
                 const int f[4] = {c00 + c01 + c10 + c11, c00 - c01 + c10 - c11, c00 + c01 - c10 - c11, c00 - c01 - c10 + c11};
 #pragma unroll
                 for (int k = 0; k < 4; k++) s.dc[mj][16 + pl * 4 + k] = (int)((unsigned)(f[k] * ls00) << qd) >> 5;
@@ -380,7 +390,7 @@ k1_dequant_idct(K1Params p)
                 const unsigned mw = s.meta[j];
                 const int kind = mw & 255, qp = (signed char)(mw >> 8);
                 const int comp = b < 16 ? 0 : (b < 20 ? 1 : 2);
-                const int qpb = comp ? mvg_chroma_qp(qp, comp == 1 ? cb_off : cr_off) : qp;
+                const int qpb = comp ? (s_qpc[comp - 1][qp] & 255) : qp;
                 uint4 *blk = reinterpret_cast<uint4 *>(tile + j * 384 + b * 16);
                 const uint4 a = blk[0], bb = blk[1];
                 int c[16];                      /* zig-zag k -> (row,col): utils.h:64 / spec Table 8-13 */
