@@ -226,7 +226,7 @@ k1_dequant_idct(K1Params p)
     __shared__ int32_t s_ls4[3 * 6 * 16];
     __shared__ int32_t s_ls4q[3 * 52 * 16];                     /* per qP; << (qP/6-4) folded in when qP >= 24 */
     __shared__ int32_t s_ls8[6 * 64];
-    __shared__ uint8_t s_zz8inv[64];
+    __shared__ __align__(8) uint8_t s_zz8inv[64];
     __shared__ uint16_t s_qpc[2][52];                           /* QPC | QPC / 6 << 8 for Cb, Cr by QPY (derivChromaQP) */
     extern __shared__ __align__(128) uint8_t k1_smem[];         /* K1WarpSmem x K1_WARPS (dynamic: above the 48 KB static limit) */
     K1WarpSmem *s_warp = reinterpret_cast<K1WarpSmem *>(k1_smem);
@@ -441,9 +441,11 @@ k1_dequant_idct(K1Params p)
                 const int qd8 = qp / 6;
                 const int32_t *l8 = s_ls8 + (qp - 6 * qd8) * 64 + row * 8;
                 const int16_t *in = tile + j * 384 + b8 * 64;
+                const uint2 zz = *reinterpret_cast<const uint2 *>(s_zz8inv + row * 8);   /* scan positions of my row */
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
-                    const int t = (int)in[s_zz8inv[row * 8 + q]] * l8[q];       /* quant8x8, h264_transform.c:1256-1284 */
+                    const unsigned k = ((q < 4 ? zz.x : zz.y) >> (8 * (q & 3))) & 255u;
+                    const int t = (int)in[k] * l8[q];                           /* quant8x8, h264_transform.c:1256-1284 */
                     v[q] = (qp > 35) ? (int)((unsigned)t << (qd8 - 6)) : ((t + (1 << (5 - qd8))) >> (6 - qd8));
                 }
                 if (row == 0) v[0] += 32;                                       /* rounding of the final >> 6 (:1382) */
