@@ -227,6 +227,7 @@ k1_dequant_idct(K1Params p)
     __shared__ int32_t s_ls4q[3 * 52 * 16];                     /* per qP; << (qP/6-4) folded in when qP >= 24 */
     __shared__ int32_t s_ls8[6 * 64];
     __shared__ __align__(8) uint8_t s_zz8inv[64];
+    __shared__ uint8_t s_dcsh[52];                              /* 4 - qP / 6 below qP 24, else 0 */
     __shared__ uint16_t s_qpc[2][52];                           /* QPC | QPC / 6 << 8 for Cb, Cr by QPY (derivChromaQP) */
     extern __shared__ __align__(128) uint8_t k1_smem[];         /* K1WarpSmem x K1_WARPS (dynamic: above the 48 KB static limit) */
     K1WarpSmem *s_warp = reinterpret_cast<K1WarpSmem *>(k1_smem);
@@ -235,6 +236,7 @@ k1_dequant_idct(K1Params p)
     for (int i = threadIdx.x; i < 3 * 52 * 16; i += blockDim.x) s_ls4q[i] = (&p.tab->ls4q[0][0][0])[i];
     for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) s_ls8[i] = (&p.tab->ls8[0][0])[i];
     if (threadIdx.x < 64) s_zz8inv[threadIdx.x] = p.tab->zz8inv[threadIdx.x];
+    if (threadIdx.x >= 128 && threadIdx.x < 180) s_dcsh[threadIdx.x - 128] = (uint8_t)(threadIdx.x - 128 > 23 ? 0 : 4 - (threadIdx.x - 128) / 6);
     if (threadIdx.x < 104) {
         const int pl = threadIdx.x >= 52, qpc = mvg_chroma_qp(threadIdx.x - 52 * pl, pl ? p.tab->cr_qp_offset : p.tab->cb_qp_offset);
         s_qpc[pl][threadIdx.x - 52 * pl] = (uint16_t)(qpc | ((qpc / 6) << 8));
@@ -343,31 +345,30 @@ k1_dequant_idct(K1Params p)
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             const int u = lane + 32 * r, j = u / 24, b = u - 24 * j;
-            bool general = false, nz8q = false;
-            const unsigned mw = j < nmb ? s.meta[j] : 0u;
+            /* straight-line code: every lane loads its block (in bounds also beyond the last macroblock of a short
+             * group) and derives all three answers; only the DC-only rewrite is conditional */
+            const bool live = j < nmb;
+            const unsigned mw = s.meta[j];
             const int kind = mw & 255, qp = (signed char)(mw >> 8);
             const bool is8 = kind == MVG_MB_I8x8 && b < 16;
-            if (j < nmb) {
-                uint4 *blk = reinterpret_cast<uint4 *>(tile + j * 384 + b * 16);
-                const uint4 w0 = blk[0], w1 = blk[1];
-                const unsigned rest = (w0.x & 0xffff0000u) | w0.y | w0.z | w0.w | w1.x | w1.y | w1.z | w1.w;
-                const int dcraw = (short)(w0.x & 0xffff);
-                if (is8) nz8q = (rest | (unsigned)dcraw) != 0;
-                else if (rest) general = true;
-                else {
-                    const bool has_dc = b >= 16 || kind == MVG_MB_I16x16;
-                    int rv = 0;
-                    if (has_dc) rv = (s.dc[j][b] + 32) >> 6;          /* d00 = c00 (h264_transform.c:1126-1129) */
-                    else if (dcraw) {
-                        const int qd = qp / 6, lq = s_ls4q[qp * 16];
-                        const int d = qp > 23 ? dcraw * lq : (dcraw * lq + (1 << (3 - qd))) >> (4 - qd);
-                        rv = (d + 32) >> 6;
-                    }
-                    rv = min(max(rv, -512), 511);
-                    if (rv != 0 || dcraw) {
-                        const unsigned pk = (unsigned)(rv & 0xffff) * 0x10001u;
-                        blk[0] = make_uint4(pk, pk, pk, pk); blk[1] = make_uint4(pk, pk, pk, pk);
-                    }
+            uint4 *blk = reinterpret_cast<uint4 *>(tile + j * 384 + b * 16);
+            const uint4 w0 = blk[0], w1 = blk[1];
+            const unsigned rest = (w0.x & 0xffff0000u) | w0.y | w0.z | w0.w | w1.x | w1.y | w1.z | w1.w;
+            const int dcraw = (short)(w0.x & 0xffff);
+            const bool nz8q = live && is8 && (rest | (w0.x & 0xffffu)) != 0;
+            const bool general = live && !is8 && rest != 0;
+            {
+                /* DC only: every residual sample is (d00 + 32) >> 6.  d00 = c00 (already dequantised by the DC
+                 * transforms, h264_transform.c:1126-1129) for chroma and Intra16x16, else quant4x4 of the level:
+                 * (c * LS + rnd) >> sh with sh = 0 from qP 24 on (the left shift is folded into s_ls4q) */
+                const bool has_dc = b >= 16 || kind == MVG_MB_I16x16;
+                const int sh = s_dcsh[qp];
+                const int plain = (dcraw * s_ls4q[qp * 16] + ((1 << sh) >> 1)) >> sh;
+                const int d = has_dc ? s.dc[j][b] : plain;
+                const int rv = min(max((d + 32) >> 6, -512), 511);
+                if (live && !is8 && rest == 0 && (rv != 0 || dcraw != 0)) {
+                    const unsigned pk = (unsigned)(rv & 0xffff) * 0x10001u;
+                    blk[0] = make_uint4(pk, pk, pk, pk); blk[1] = make_uint4(pk, pk, pk, pk);
                 }
             }
             const unsigned gb = __ballot_sync(MVG_FULL, general);
