@@ -446,8 +446,15 @@ k1_dequant_idct(K1Params p)
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
                     const unsigned k = ((q < 4 ? zz.x : zz.y) >> (8 * (q & 3))) & 255u;
-                    const int t = (int)in[k] * l8[q];                           /* quant8x8, h264_transform.c:1256-1284 */
-                    v[q] = (qp > 35) ? (int)((unsigned)t << (qd8 - 6)) : ((t + (1 << (5 - qd8))) >> (6 - qd8));
+                    v[q] = (int)in[k] * l8[q];                                  /* quant8x8, h264_transform.c:1256-1284 */
+                }
+                if (qp > 35) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) v[q] = (int)((unsigned)v[q] << (qd8 - 6));
+                } else {
+                    const int rnd = 1 << (5 - qd8), sh = 6 - qd8;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) v[q] = (v[q] + rnd) >> sh;
                 }
                 if (row == 0) v[0] += 32;                                       /* rounding of the final >> 6 (:1382) */
                 mvg_idct8_1d(v);                                                /* row pass */
