@@ -523,7 +523,7 @@ struct K2Params {
 #define K2_WARPS     16         /* warps per CTA; two CTAs per SM                              */
 #endif
 #define K2_CTL_CHUNK 32         /* control records per chunk (one 16-byte copy per lane)       */
-#define K2_RING      4          /* residual ring slots (power of two; three are live at a time)   */
+#define K2_RING      4          /* residual ring slots: the pair in use and the pair in flight     */
 #define K2_TO(x, y)  (((y) + 1) * MVG_LT_STRIDE + MVG_LT_XOFF + (x))    /* luma tile offset of sample (x, y)   */
 #define K2_CO(x, y)  (((y) + 1) * MVG_CT_STRIDE + MVG_CT_XOFF + (x))    /* chroma tile offset of sample (x, y) */
 
@@ -532,7 +532,7 @@ struct K2Params {
  * warp's record, hence ctl[] first. */
 struct K2WarpSmem {
     __align__(16) MvgMbCtl ctl[2 * K2_CTL_CHUNK];       /* control records, two chunks: record of macroblock mx at [mx & 63]      */
-    __align__(16) int16_t  resid[K2_RING][384];         /* residual ring, filled by per-lane async copies two macroblocks ahead */
+    __align__(16) int16_t  resid[K2_RING][384];         /* residual ring, filled by per-lane async copies a pair of macroblocks ahead */
     __align__(16) uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
     __align__(16) uint8_t  ct[2][MVG_CT_PLANE];
     __align__(16) uint8_t  n8[MVG_N8_BYTES];            /* Intra8x8 neighbour line: byte planes p', f2, f3; [MVG_N8_DC] = DC */
@@ -855,8 +855,8 @@ __device__ __forceinline__ void k2_chroma(const K2Ctx &c, int mode, bool left, b
  * r (no deadlock: it runs on a resident warp).
  *
  * Inputs arrive by per-lane asynchronous copies (LDGSTS, completion by per-thread groups, no barrier
- * objects): the 768-byte residual of macroblock x+2 is requested while x is predicted, control records
- * come 32 macroblocks at a time.  Output is one 384-byte tile per macroblock.
+ * objects): the residuals of macroblocks x+2 and x+3 (1536 bytes: three full-warp 16-byte copies, no lane
+ * condition) are requested while x is predicted, control records come 32 macroblocks at a time.  Output is one 384-byte tile per macroblock.
  *
  * What bounds the kernel (ncu, profiles/): instruction issue and the shared-memory data pipe, not HBM;
  * hence tables with ready-to-use offsets, [lane constant + uniform base + immediate] addressing,
@@ -955,15 +955,12 @@ k2_wavefront(K2Params p)
 
         const uint8_t *st_src = reinterpret_cast<const uint8_t *>(p.resid + mb0 * 384) + lane * 16;
         const MvgMbCtl *ctl = p.ctl + mb0;
-        /* group 0: control records 0..31 and residual 0; group 1: residual 1 */
+        /* residuals travel in pairs of macroblocks: 1536 bytes are three full-warp 16-byte copies, no lane condition.
+         * group 0: control records 0..31 and residuals 0, 1 */
         if (lane < W) mvg_cp_async16(&s.ctl[lane], ctl + lane);
         mvg_cp_async16(st_dst, st_src);
-        if (lane < 16) mvg_cp_async16(st_dst + 512, st_src + 512);
-        mvg_cp_async_commit();
-        if (W > 1) {
-            mvg_cp_async16(st_dst + 768, st_src + 768);
-            if (lane < 16) mvg_cp_async16(st_dst + 768 + 512, st_src + 768 + 512);
-        }
+        if (W > 1) { mvg_cp_async16(st_dst + 512, st_src + 512); mvg_cp_async16(st_dst + 1024, st_src + 1024); }
+        else if (lane < 16) mvg_cp_async16(st_dst + 512, st_src + 512);
         mvg_cp_async_commit();
 
         /* running pointers: source of the residual requested next (macroblock mx + 2), this lane's piece of the
@@ -989,14 +986,20 @@ k2_wavefront(K2Params p)
             for (int mx = c0; mx < cend; mx++) {
                 K2_PROF(const long long t0 = clock64();)
                 const int j = mx & 3;
-                /* request macroblock mx + 2: its ring slot was last read before the __syncwarp() that closed mx - 2 */
-                if (mx + 2 < W) {
+                /* every second macroblock: request the pair mx + 2, mx + 3; their ring slots were last read before the
+                 * __syncwarp() that closed mx - 1 */
+                if ((mx & 1) == 0) {
+                    const int left = W - (mx + 2);
                     uint8_t *d = st_dst + ((mx + 2) & (K2_RING - 1)) * 768;
-                    mvg_cp_async16(d, st_run);
-                    if (lane < 16) mvg_cp_async16(d + 512, st_run + 512);
+                    if (left >= 2) {
+                        mvg_cp_async16(d, st_run); mvg_cp_async16(d + 512, st_run + 512); mvg_cp_async16(d + 1024, st_run + 1024);
+                    } else if (left == 1) {
+                        mvg_cp_async16(d, st_run);
+                        if (lane < 16) mvg_cp_async16(d + 512, st_run + 512);
+                    }
+                    st_run += 2 * 768;
+                    mvg_cp_async_commit();
                 }
-                st_run += 768;
-                mvg_cp_async_commit();
                 const bool availA = mx > 0, availC = availB && mx < W - 1, availD = availA && availB;
 
                 if (availB) {
@@ -1031,7 +1034,7 @@ k2_wavefront(K2Params p)
                     if (j == 3) ha_run += 32;
                 }
                 K2_PROF(const long long t1 = clock64();)
-                mvg_cp_async_wait<2>();         /* all but the two youngest groups: macroblock mx has landed */
+                mvg_cp_async_wait<1>();         /* all but the youngest group: the pair of macroblock mx has landed */
                 __syncwarp();
                 if (availB && j == 0) {
                     /* request the next group of the row above only now, behind everything that reads qb: those reads
