@@ -369,6 +369,9 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src},
             "kernels": kernels,
+            # the three stages together: algorithmic bytes of all kernels over the sum of their launch times
+            "roofline_all_stages": {"achieved": sum(ab.values()) * F / (sum(mean_ms.values()) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": sum(ab.values()) * F / (sum(mean_ms.values()) * 1e-3) / 1e9 / peak},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
