@@ -498,81 +498,103 @@ static int nC_of(const uint8_t *tot, int stride, int X, int Y)
 
 static inline int16_t clamp16(int v) { return (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
 
+static inline uint64_t rrb_load(const uint8_t *base, size_t pos)
+{
+    uint64_t w;
+    memcpy(&w, base + (pos >> 3), 8);
+    return __builtin_bswap64(w) << (pos & 7);
+}
+
 /* 9.2: one residual block of max_num 16 / 15 / 4 levels.  The non-zero levels go straight to their place,
  * dst[scan index * stride] (the destination must hold zeros), clamped to int16.  Returns TotalCoeff or -1. */
 static int read_residual_block(br_t *b, int16_t *dst, int stride, int max_num, int nC)
 {
+    /* The read position lives in a local for the whole block and every look at the stream is an unconditional
+     * 8-byte load + byte swap + shift (the RBSP has RBSP_SLACK zero bytes behind it): no state in memory between
+     * the symbols and no refill branch.  The data-dependent decisions of the level loop are arithmetic. */
+    const uint8_t *const base = b->p;
+    size_t pos = b->pos;
+#define RRB_WIN()      (rrb_load(base, pos))
+#define RRB_PEEK(n)    ((uint32_t)(RRB_WIN() >> (64 - (n))))
+#define RRB_FAIL()     do { b->pos = pos; return -1; } while (0)
     int tc, t1;
     if (nC == -1) {
-        uint16_t e = lut_ctc[br_peek(b, 8)];
-        if (!e) return -1;
-        br_skip(b, e >> 7); tc = (e >> 2) & 31; t1 = e & 3;
+        uint16_t e = lut_ctc[RRB_PEEK(8)];
+        if (!e) RRB_FAIL();
+        pos += e >> 7; tc = (e >> 2) & 31; t1 = e & 3;
     } else if (nC >= 8) {
-        uint32_t v = br_get(b, 6);
-        if (v == 3) { tc = 0; t1 = 0; } else { tc = (int)(v >> 2) + 1; t1 = (int)(v & 3); if (t1 > tc) return -1; }
+        uint32_t v = RRB_PEEK(6);
+        pos += 6;
+        if (v == 3) { tc = 0; t1 = 0; } else { tc = (int)(v >> 2) + 1; t1 = (int)(v & 3); if (t1 > tc) RRB_FAIL(); }
     } else {
         const int t = nC < 2 ? 0 : (nC < 4 ? 1 : 2);
-        const uint32_t bits = br_peek(b, 16);
+        const uint32_t bits = RRB_PEEK(16);
         uint16_t e = lut_ct10[t][bits >> 6];
         if (!e) e = lut_ct[t][bits];
-        if (!e) return -1;
-        br_skip(b, e >> 7); tc = (e >> 2) & 31; t1 = e & 3;
+        if (!e) RRB_FAIL();
+        pos += e >> 7; tc = (e >> 2) & 31; t1 = e & 3;
     }
-    if (tc == 0) return 0;
-    if (tc > max_num) return -1;
+    if (tc == 0) { b->pos = pos; return 0; }
+    if (tc > max_num) RRB_FAIL();
 
     int level[16];
     int suffix_len = (tc > 10 && t1 < 3) ? 1 : 0;
-    {   /* trailing ones: t1 sign bits at once */
-        const uint32_t signs = t1 ? br_get(b, t1) : 0;
-        for (int i = 0; i < t1; i++) level[i] = ((signs >> (t1 - 1 - i)) & 1) ? -1 : 1;
+    if (t1) {   /* trailing ones: t1 sign bits at once */
+        const uint32_t signs = RRB_PEEK(3) >> (3 - t1);
+        pos += (size_t)t1;
+        for (int i = 0; i < t1; i++) level[i] = 1 - 2 * (int)((signs >> (t1 - 1 - i)) & 1);
     }
+    int first_adj = t1 < 3 ? 2 : 0;                 /* the first level after fewer than three trailing ones (9.2.2.1) */
     for (int i = t1; i < tc; i++) {
-        const uint32_t w32 = (uint32_t)(br_window(b) >> 32);
-        const int prefix = w32 ? __builtin_clz(w32) : 32;
+        const uint32_t w32 = (uint32_t)(RRB_WIN() >> 32);
+        if (!w32) RRB_FAIL();                       /* 32 or more zero bits */
+        const int prefix = __builtin_clz(w32);
         int code;
         if (prefix < 14) {              /* the common case: prefix, stop bit and suffix (<= 20 bits) from one window */
-            code = prefix << suffix_len;
-            if (suffix_len) code += (int)((w32 << (prefix + 1)) >> (32 - suffix_len));
-            br_skip(b, prefix + 1 + suffix_len);
+            code = (prefix << suffix_len) + (int)((uint64_t)(uint32_t)(w32 << (prefix + 1)) >> (32 - suffix_len));
+            pos += (size_t)(prefix + 1 + suffix_len);
         } else {
-            if (prefix >= 32) return -1;
-            br_skip(b, prefix + 1);
+            pos += (size_t)prefix + 1;
             code = (prefix < 15 ? prefix : 15) << suffix_len;           /* 9.2.2.1 */
             int ssize = suffix_len;
             if (prefix == 14 && suffix_len == 0) ssize = 4;
             else if (prefix >= 15) ssize = prefix - 3;
-            if (ssize > 0) code += (int)br_get(b, ssize);
+            if (ssize > 0) { code += (int)RRB_PEEK(ssize); pos += (size_t)ssize; }
             if (prefix >= 15 && suffix_len == 0) code += 15;
             if (prefix >= 16) code += (1 << (prefix - 3)) - 4096;
         }
-        if (i == t1 && t1 < 3) code += 2;
-        level[i] = (code & 1) ? (-code - 1) >> 1 : (code + 2) >> 1;
-        if (suffix_len == 0) suffix_len = 1;
-        if (abs(level[i]) > (3 << (suffix_len - 1)) && suffix_len < 6) suffix_len++;
+        code += first_adj; first_adj = 0;
+        const int sign = -(code & 1), mag = (code + 2) >> 1;            /* odd: -(code + 1) / 2, even: (code + 2) / 2 */
+        level[i] = (mag ^ sign) - sign;
+        suffix_len += suffix_len == 0;
+        suffix_len += (mag > (3 << (suffix_len - 1))) & (suffix_len < 6);
     }
     int zeros_left = 0;
     if (tc < max_num) {
-        uint8_t e = max_num == 4 ? lut_tz2[tc - 1][br_peek(b, 3)] : lut_tz4[tc - 1][br_peek(b, 9)];
-        if (!e) return -1;
-        br_skip(b, e >> 4); zeros_left = e & 15;
+        uint8_t e = max_num == 4 ? lut_tz2[tc - 1][RRB_PEEK(3)] : lut_tz4[tc - 1][RRB_PEEK(9)];
+        if (!e) RRB_FAIL();
+        pos += e >> 4; zeros_left = e & 15;
     }
-    int pos = zeros_left + tc - 1;                                      /* scan index of the first (highest) level */
-    if (pos >= max_num) return -1;
+    int at = zeros_left + tc - 1;                                       /* scan index of the first (highest) level */
+    if (at >= max_num) RRB_FAIL();
     for (int i = 0; i < tc; i++) {
-        dst[pos * stride] = clamp16(level[i]);
+        dst[at * stride] = clamp16(level[i]);
         int run = 0;
         if (i < tc - 1 && zeros_left > 0) {
-            uint8_t e = lut_run[(zeros_left > 7 ? 7 : zeros_left) - 1][br_peek(b, 11)];
-            if (!e) return -1;
-            br_skip(b, e >> 4); run = e & 15;
-            if (run > zeros_left) return -1;
+            uint8_t e = lut_run[(zeros_left > 7 ? 7 : zeros_left) - 1][RRB_PEEK(11)];
+            if (!e) RRB_FAIL();
+            pos += e >> 4; run = e & 15;
+            if (run > zeros_left) RRB_FAIL();
             zeros_left -= run;
         }
-        pos -= 1 + run;
-        if (i < tc - 1 && pos < 0) return -1;
+        at -= 1 + run;
+        if (i < tc - 1 && at < 0) RRB_FAIL();
     }
+    b->pos = pos;
     return tc;
+#undef RRB_WIN
+#undef RRB_PEEK
+#undef RRB_FAIL
 }
 
 static int pack_mb(worker_t *w, size_t m);
