@@ -820,12 +820,15 @@ __device__ __forceinline__ void k2_chroma(const K2Ctx &c, int mode, bool left, b
         const unsigned t = *reinterpret_cast<const unsigned *>(ct + K2_CO(0, -1) + x0);
         p0 = mvg_pair_lo(t); p1 = mvg_pair_hi(t);
     } else {                    /* Plane */
-        int H = 0, V = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            H += (i + 1) * ((int)ct[K2_CO(4 + i, -1)] - (int)ct[K2_CO(2 - i, -1)]);
-            V += (i + 1) * ((int)ct[K2_CO(-1, 4 + i)] - (int)ct[K2_CO(-1, 2 - i)]);
-        }
+        /* the eight products of a plane, one per lane (lanes 0..3 of a plane: H, 4..7: V, the rest contribute 0),
+         * summed with two butterfly shuffles and handed to all 16 lanes of the plane with two more */
+        const int i = lane & 3, g = (lane >> 2) & 3;
+        const int step = g == 0 ? 1 : MVG_CT_STRIDE;                                    /* along the top row / down the left column */
+        const int mid = g == 0 ? K2_CO(3, -1) : K2_CO(-1, 3);                           /* p[3,-1] resp. p[-1,3] */
+        const int term = (g < 2 ? i + 1 : 0) * ((int)ct[mid + (i + 1) * step] - (int)ct[mid - (i + 1) * step]);
+        int sum = term + __shfl_xor_sync(MVG_FULL, term, 1);
+        sum += __shfl_xor_sync(MVG_FULL, sum, 2);
+        const int H = __shfl_sync(MVG_FULL, sum, lane & 16), V = __shfl_sync(MVG_FULL, sum, (lane & 16) + 4);
         const int a = 16 * ((int)ct[K2_CO(-1, 7)] + (int)ct[K2_CO(7, -1)]);
         const int b = (34 * H + 32) >> 6, cc = (34 * V + 32) >> 6;
         /* |a + b (x - 3) + c (y - 3) + 16| < 2^15: int16 pairs as in the luma plane predictor */
