@@ -88,3 +88,26 @@ def test_png_rejects_bad_arguments(lib):
     buf = np.zeros(48, np.uint8)
     assert not lib.mvt_png_encode(buf.ctypes.data, 0, 4, C.byref(n))
     assert not lib.mvt_png_encode(buf.ctypes.data, 4, -1, C.byref(n))
+
+
+@pytest.mark.skipif(not REF_PNG.exists(), reason="oracle/_ref/ref_png not built")
+def test_png_random_small_images_equal_the_reference_writer(lib):
+    """Sizes 1..40 and contents from flat to noise, with repeats at random distances: the corner cases of the
+    filter choice (ties, first row) and of the match finder (matches at the very end, overlapping matches,
+    the lazy step) show up in small pictures far more often than in large ones."""
+    rng = np.random.default_rng(77)
+    for k in range(60):
+        w, h = int(rng.integers(1, 41)), int(rng.integers(1, 41))
+        kind = k % 4
+        if kind == 0:
+            img = rng.integers(0, 256, (h, w, 3))
+        elif kind == 1:
+            img = rng.integers(0, 3, (h, w, 3)) * 100
+        elif kind == 2:
+            base = rng.integers(0, 256, (int(rng.integers(1, 5)), int(rng.integers(1, 7)), 3))
+            img = np.tile(base, (h // base.shape[0] + 1, w // base.shape[1] + 1, 1))[:h, :w]
+        else:
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = np.stack([xx * 7 + yy, xx + yy * 5, (xx * yy) % 17], -1) + rng.integers(0, 2, (h, w, 3))
+        img = np.asarray(img & 255, np.uint8)
+        assert encode(lib, img) == reference(img), (k, w, h, kind)
