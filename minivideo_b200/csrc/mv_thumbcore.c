@@ -141,6 +141,21 @@ static int write_yuv444(const char *path, const uint8_t *i420, int w, int h)
     return ok;
 }
 
+/* one picture file from host pixels (RGB24 top-down; MVT_YUV420 / MVT_YUV444: planar I420): the writers above behind
+ * one entry point, so that tests can pin them against the reference's writers without a GPU */
+int mvt_write_image(const char *path, int fmt, const uint8_t *pixels, int w, int h)
+{
+    if (!path || !pixels || w < 1 || h < 1) return 0;
+    switch (fmt) {
+    case MVT_YUV420: return write_raw(path, pixels, (size_t)w * h * 3 / 2);
+    case MVT_YUV444: return write_yuv444(path, pixels, w, h);
+    case MVT_BMP:    return write_bmp(path, pixels, w, h);
+    case MVT_TGA:    return write_tga(path, pixels, w, h);
+    case MVT_PNG:    return write_png(path, pixels, w, h);
+    default:         return 0;
+    }
+}
+
 static const char *const file_ext[] = {"yuv", "bmp", "tga", "png", "yuv"};
 static int fmt_is_yuv(int fmt) { return fmt == MVT_YUV420 || fmt == MVT_YUV444; }
 

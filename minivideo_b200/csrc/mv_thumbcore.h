@@ -18,4 +18,8 @@ enum { MVT_YUV420, MVT_BMP, MVT_TGA, MVT_PNG, MVT_YUV444 };
 int mvt_extract(const uint8_t *data, size_t len, const char *base, const char *outdir, int fmt, int n_want, int mode,
                 int scale, int device, int threads, int batch, int *n_exported);
 
+/* Write one picture file in format `fmt` from host pixels (RGB24 rows top-down, or planar I420 for the two YUV formats).
+ * Returns 1 / 0. */
+int mvt_write_image(const char *path, int fmt, const uint8_t *pixels, int w, int h);
+
 #endif
