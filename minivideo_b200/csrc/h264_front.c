@@ -180,12 +180,22 @@ static int sfail(mvf_stream *s, int code, const char *fmt, ...)
 /* NAL payload (after the header byte) -> RBSP (`dst` holds n + RBSP_SLACK bytes); returns the RBSP length (7.4.1.1) */
 static size_t unescape(const uint8_t *src, size_t n, uint8_t *dst)
 {
-    size_t o = 0;
+    /* emulation_prevention_three_byte (7.4.1): the 03 of every 00 00 03 goes.  An escape can only follow a zero byte,
+     * so the stretches between zero bytes (hundreds of bytes in entropy-coded data) are copied wholesale. */
+    size_t o = 0, i = 0;
     int zeros = 0;
-    for (size_t i = 0; i < n; i++) {
-        if (zeros >= 2 && src[i] == 3) { zeros = 0; continue; }
+    while (i < n) {
+        if (zeros == 0) {
+            const uint8_t *z = memchr(src + i, 0, n - i);
+            const size_t run = z ? (size_t)(z - (src + i)) : n - i;
+            memcpy(dst + o, src + i, run);
+            o += run; i += run;
+            if (i >= n) break;
+        }
+        if (zeros >= 2 && src[i] == 3) { zeros = 0; i++; continue; }
         dst[o++] = src[i];
         zeros = src[i] == 0 ? zeros + 1 : 0;
+        i++;
     }
     memset(dst + o, 0, RBSP_SLACK);
     return o;
