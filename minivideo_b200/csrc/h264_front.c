@@ -335,14 +335,20 @@ int mvf_open_annexb(const uint8_t *data, size_t len, mvf_stream **out)
     /* start codes 00 00 01 (a 4-byte start code is the same with one more leading zero) */
     int cap = 1024;
     s->nals = malloc(sizeof(nal_t) * (size_t)cap);
-    for (size_t i = 0; i + 3 < len; i++) {
-        if (data[i] == 0 && data[i + 1] == 0 && data[i + 2] == 1) {
-            if (s->n_nals == cap) { cap *= 2; s->nals = realloc(s->nals, sizeof(nal_t) * (size_t)cap); }
-            s->nals[s->n_nals].off = i + 3;
-            s->nals[s->n_nals].type = data[i + 3] & 31;
-            s->n_nals++;
-            i += 2;
+    if (!s->nals) { free(s); return sfail(NULL, MVG_FAILURE, "out of memory"); }
+    /* look for the 01 (one byte in 256 of entropy-coded data) and check the two bytes before it */
+    for (const uint8_t *q = data + 2, *const end = data + len - 1; q < end; q++) {
+        q = memchr(q, 1, (size_t)(end - q));
+        if (!q) break;
+        if (q[-1] != 0 || q[-2] != 0) continue;
+        if (s->n_nals == cap) {
+            nal_t *nn = realloc(s->nals, sizeof(nal_t) * (size_t)cap * 2);
+            if (!nn) { free(s->nals); free(s); return sfail(NULL, MVG_FAILURE, "out of memory"); }
+            s->nals = nn; cap *= 2;
         }
+        s->nals[s->n_nals].off = (size_t)(q - data) + 1;
+        s->nals[s->n_nals].type = q[1] & 31;
+        s->n_nals++;
     }
     for (int k = 0; k < s->n_nals; k++) {
         size_t end = k + 1 < s->n_nals ? s->nals[k + 1].off - 3 : len;
@@ -350,6 +356,7 @@ int mvf_open_annexb(const uint8_t *data, size_t len, mvf_stream **out)
         s->nals[k].size = end - s->nals[k].off;
     }
     s->idr = malloc(sizeof(int) * (size_t)(s->n_nals + 1));
+    if (!s->idr) { free(s->nals); free(s); return sfail(NULL, MVG_FAILURE, "out of memory"); }
     int rc = MVG_SUCCESS;
     uint8_t *tmp = NULL;
     for (int k = 0; k < s->n_nals && rc == MVG_SUCCESS; k++) {
