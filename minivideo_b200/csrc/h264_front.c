@@ -614,7 +614,7 @@ static int read_residual_block(br_t *b, int16_t *dst, int stride, int max_num, i
 #undef RRB_FAIL
 }
 
-static int pack_mb(worker_t *w, size_t m);
+static int pack_mb(worker_t *w, size_t m, uint32_t touched);
 
 static int wfail(worker_t *w, int code, const char *fmt, ...)
 {
@@ -713,13 +713,16 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
                 int cbp = cbp_from_codenum[cn];
                 cbp_l = cbp & 15; cbp_c = cbp >> 4;
             }
+            uint32_t touched = 0;                           /* blocks of cf[] that received levels (for pack_mb) */
             if (cbp_l || cbp_c || kind == MVG_MB_I16x16) {
                 int delta = br_se(&b);
                 if (delta) qp = (qp + delta + 52) % 52;     /* h264_macroblock.c:263-266 */
                 /* residual_luma, 7.3.5.3.1 */
                 if (kind == MVG_MB_I16x16) {
                     int16_t dc[16] = {0};
-                    if (read_residual_block(&b, dc, 1, 16, nC_of(w->tot_luma, W4, mx * 4, my * 4)) < 0) goto bad_block;
+                    const int tcdc = read_residual_block(&b, dc, 1, 16, nC_of(w->tot_luma, W4, mx * 4, my * 4));
+                    if (tcdc < 0) goto bad_block;
+                    if (tcdc > 0) touched |= 0xffffu;        /* the DC levels go to slot 0 of all sixteen blocks */
                     for (int k = 0; k < 16; k++) {
                         int r = zz4[k] >> 2, c = zz4[k] & 3;
                         cf[((r & 1) * 2 + (r >> 1) * 8 + (c & 1) + (c >> 1) * 4) * 16] = dc[k];
@@ -734,13 +737,16 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
                             else if (kind == MVG_MB_I8x8) tc = read_residual_block(&b, cf + b8 * 64 + i4, 4, 16, nC);   /* h264_macroblock.c:1182 */
                             else tc = read_residual_block(&b, cf + blk * 16 + 1, 1, 15, nC);
                             if (tc < 0) goto bad_block;
+                            if (tc > 0) touched |= kind == MVG_MB_I8x8 ? 0xfu << (4 * b8) : 1u << blk;   /* 8x8: interleaved over its four blocks */
                         }
                         w->tot_luma[Y4 * W4 + X4] = (uint8_t)tc;
                     }
                 /* residual chroma: DC of both planes, then AC of both planes (h264_macroblock.c:1222-1292) */
                 for (int c = 0; c < 2; c++)
                     if (cbp_c & 3) {
-                        if (read_residual_block(&b, cf + 256 + c * 64, 16, 4, -1) < 0) goto bad_block;
+                        const int tcc = read_residual_block(&b, cf + 256 + c * 64, 16, 4, -1);
+                        if (tcc < 0) goto bad_block;
+                        if (tcc > 0) touched |= 0xfu << (16 + 4 * c);
                     }
                 for (int c = 0; c < 2; c++)
                     for (int blk = 0; blk < 4; blk++) {
@@ -748,6 +754,7 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
                         if (cbp_c & 2) {
                             tc = read_residual_block(&b, cf + 256 + c * 64 + blk * 16 + 1, 1, 15, nC_of(w->tot_chroma[c], W2, X2, Y2));
                             if (tc < 0) goto bad_block;
+                            if (tc > 0) touched |= 1u << (16 + 4 * c + blk);
                         }
                         w->tot_chroma[c][Y2 * W2 + X2] = (uint8_t)tc;
                     }
@@ -761,7 +768,7 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
             out->chroma_mode[mbi] = (uint8_t)chroma_mode;
             out->qp_y[mbi] = (int8_t)qp;
             if (out->cbp) out->cbp[mbi] = (uint8_t)(cbp_c << 4 | cbp_l);
-            if (w->packed && !pack_mb(w, (size_t)my * W + mx)) return wfail(w, MVG_FAILURE, "picture %d: out of memory while packing", idr_index);
+            if (w->packed && !pack_mb(w, (size_t)my * W + mx, touched)) return wfail(w, MVG_FAILURE, "picture %d: out of memory while packing", idr_index);
             if (br_overrun(&b)) return wfail(w, MVG_FAILURE, "picture %d: slice data ends at macroblock %d of %zu", idr_index, my * W + mx, N);
             continue;
         bad_block:
@@ -780,7 +787,7 @@ typedef struct {
 } job_t;
 
 /* the 384 levels of one macroblock -> chunk bitmap, masks and non-zero levels appended to the worker's words */
-static int pack_mb(worker_t *w, size_t m)
+static int pack_mb(worker_t *w, size_t m, uint32_t touched)
 {
     if (w->pk_n + MVG_PACKED_WORDS_PER_MB > w->pk_cap) {
         size_t cap = w->pk_cap * 2 + 64 * MVG_PACKED_WORDS_PER_MB;
@@ -795,7 +802,9 @@ static int pack_mb(worker_t *w, size_t m)
     int n_coded = 0, n_lv = 0;
     /* one pass: per block the mask of non-zero levels, the levels themselves in scan order, and the block is
      * zeroed again for the next macroblock (so that the parser needs no 768-byte memset per macroblock) */
-    for (int b = 0; b < 24; b++) {
+    /* `touched`: the blocks the parser wrote levels into (a superset of the non-zero ones); the others hold zeros */
+    for (uint32_t todo = touched; todo; todo &= todo - 1) {
+        const int b = __builtin_ctz(todo);
         int16_t *cb = c + b * 16;
 #if defined(__SSE2__)
         const __m128i z = _mm_setzero_si128();
