@@ -268,24 +268,35 @@ static int parse_sps(mvf_stream *s, const uint8_t *rbsp, size_t n)
             }
         }
     }
-    v.log2_max_frame_num = (int)br_ue(&b) + 4;
-    v.poc_type = (int)br_ue(&b);
-    if (v.poc_type == 0) v.log2_max_poc_lsb = (int)br_ue(&b) + 4;
+    {   /* log2_max_frame_num_minus4 and log2_max_pic_order_cnt_lsb_minus4 are 0..12 (7.4.2.1.1); they become bit counts */
+        const uint32_t fn = br_ue(&b), pt = br_ue(&b);
+        if (fn > 12 || pt > 2) return sfail(s, MVG_FAILURE, "bad SPS (log2_max_frame_num_minus4 %u, pic_order_cnt_type %u)", fn, pt);
+        v.log2_max_frame_num = (int)fn + 4;
+        v.poc_type = (int)pt;
+    }
+    if (v.poc_type == 0) {
+        const uint32_t pl = br_ue(&b);
+        if (pl > 12) return sfail(s, MVG_FAILURE, "bad SPS (log2_max_pic_order_cnt_lsb_minus4 %u)", pl);
+        v.log2_max_poc_lsb = (int)pl + 4;
+    }
     else if (v.poc_type == 1) {
         v.delta_pic_order_always_zero = br_bit(&b);
         br_se(&b); br_se(&b);
         uint32_t cyc = br_ue(&b);
         if (cyc > 255) return sfail(s, MVG_FAILURE, "bad SPS");
         for (uint32_t i = 0; i < cyc; i++) br_se(&b);
-    } else if (v.poc_type != 2) return sfail(s, MVG_FAILURE, "pic_order_cnt_type %d", v.poc_type);
+    }
     br_ue(&b);                                              /* max_num_ref_frames */
     br_bit(&b);                                             /* gaps_in_frame_num_value_allowed_flag */
-    v.width_mbs = (int)br_ue(&b) + 1;
-    v.height_mbs = (int)br_ue(&b) + 1;
+    {
+        const uint32_t wm = br_ue(&b), hm = br_ue(&b);      /* pic_width_in_mbs_minus1, pic_height_in_map_units_minus1 */
+        if (wm > 1023 || hm > 1023) return sfail(s, MVG_FAILURE, "bad SPS (%u x %u macroblocks)", wm + 1, hm + 1);
+        v.width_mbs = (int)wm + 1; v.height_mbs = (int)hm + 1;
+    }
     v.frame_mbs_only = br_bit(&b);
     if (!v.frame_mbs_only) return sfail(s, MVG_UNSUPPORTED, "interlaced (frame_mbs_only_flag = 0)");
     br_bit(&b);                                             /* direct_8x8_inference_flag */
-    if (br_bit(&b)) for (int i = 0; i < 4; i++) v.crop[i] = (int)br_ue(&b);
+    if (br_bit(&b)) for (int i = 0; i < 4; i++) { const uint32_t cr = br_ue(&b); v.crop[i] = cr > 16384 ? 16384 : (int)cr; }
     if (br_overrun(&b) || v.width_mbs > 1024 || v.height_mbs > 1024) return sfail(s, MVG_FAILURE, "truncated or bad SPS");
     v.valid = 1;
     s->sps = v;
@@ -303,9 +314,13 @@ static int parse_pps(mvf_stream *s, const uint8_t *rbsp, size_t n)
     if (br_ue(&b) != 0) return sfail(s, MVG_UNSUPPORTED, "FMO (num_slice_groups_minus1 > 0)");
     br_ue(&b); br_ue(&b);                                   /* num_ref_idx defaults */
     br_bit(&b); br_get(&b, 2);                              /* weighted prediction */
-    v.init_qp = 26 + br_se(&b);
-    br_se(&b);                                              /* pic_init_qs */
-    v.cb_off = br_se(&b);
+    {   /* pic_init_qp_minus26 is -26..25, the chroma offsets -12..12 (7.4.2.2) */
+        const int iq = br_se(&b);
+        br_se(&b);                                          /* pic_init_qs */
+        const int co = br_se(&b);
+        if (iq < -26 || iq > 25 || co < -12 || co > 12) return sfail(s, MVG_FAILURE, "bad PPS (pic_init_qp_minus26 %d, chroma_qp_index_offset %d)", iq, co);
+        v.init_qp = 26 + iq; v.cb_off = co;
+    }
     v.deblocking_control = br_bit(&b);
     v.constrained_intra = br_bit(&b);
     v.redundant_pic_cnt = br_bit(&b);
@@ -314,6 +329,7 @@ static int parse_pps(mvf_stream *s, const uint8_t *rbsp, size_t n)
         v.transform8x8 = br_bit(&b);
         if (br_bit(&b)) return sfail(s, MVG_UNSUPPORTED, "PPS scaling lists (h264_parameterset.c:904-921)");
         v.cr_off = br_se(&b);
+        if (v.cr_off < -12 || v.cr_off > 12) return sfail(s, MVG_FAILURE, "bad PPS (second_chroma_qp_index_offset %d)", v.cr_off);
     }
     if (v.entropy_cabac) return sfail(s, MVG_UNSUPPORTED, "CABAC (entropy_coding_mode_flag = 1)");
     if (b.pos > b.nbits + 1) return sfail(s, MVG_FAILURE, "truncated PPS");
@@ -656,7 +672,9 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
     }
     if (pps->redundant_pic_cnt) br_ue(&b);
     if (nal_ref_idc) { br_bit(&b); br_bit(&b); }            /* dec_ref_pic_marking of an IDR picture */
-    int qp = pps->init_qp + br_se(&b);                      /* SliceQPY */
+    const int sqd = br_se(&b);                              /* slice_qp_delta */
+    if (sqd < -51 || sqd > 51) return wfail(w, MVG_FAILURE, "picture %d: slice_qp_delta %d out of range", idr_index, sqd);
+    int qp = pps->init_qp + sqd;                            /* SliceQPY */
     if (pps->deblocking_control) {
         if (br_ue(&b) != 1) { br_se(&b); br_se(&b); }
     }
@@ -716,6 +734,7 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
             uint32_t touched = 0;                           /* blocks of cf[] that received levels (for pack_mb) */
             if (cbp_l || cbp_c || kind == MVG_MB_I16x16) {
                 int delta = br_se(&b);
+                if (delta < -26 || delta > 25) return wfail(w, MVG_FAILURE, "picture %d mb %d: mb_qp_delta %d out of range", idr_index, my * W + mx, delta);
                 if (delta) qp = (qp + delta + 52) % 52;     /* h264_macroblock.c:263-266 */
                 /* residual_luma, 7.3.5.3.1 */
                 if (kind == MVG_MB_I16x16) {
