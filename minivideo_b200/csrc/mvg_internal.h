@@ -69,7 +69,7 @@ struct MvgMbCtl { uint32_t w0, w1, w2, w3; };
 
 struct MvgLuts {
     uint32_t lut4[16][32];
-    uint32_t lut8[9][32];
+    uint32_t lut8[16][32];      /* rows 9..15 are zero: a mode nibble outside 0..8 (malformed input) reads entry 0, never out of bounds */
 };
 
 #ifdef __cplusplus

@@ -66,12 +66,13 @@ def test_pred_tap_tables_reproduce_the_oracle_predictors():
     from oracle import cpu
 
     class Luts(C.Structure):
-        _fields_ = [("lut4", C.c_uint32 * (16 * 32)), ("lut8", C.c_uint32 * (9 * 32))]
+        _fields_ = [("lut4", C.c_uint32 * (16 * 32)), ("lut8", C.c_uint32 * (16 * 32))]
     lib = api.load_library()
     luts = Luts()
     lib.mvg_build_luts(C.byref(luts))
     lut4 = np.frombuffer(luts.lut4, np.uint32).reshape(16, 32)
-    lut8 = np.frombuffer(luts.lut8, np.uint32).reshape(9, 32)
+    lut8 = np.frombuffer(luts.lut8, np.uint32).reshape(16, 32)
+    assert not lut8[9:].any()                               # rows of mode values no conforming stream has
     import re
     hdr = (ROOT / "minivideo_b200" / "csrc" / "mvg_internal.h").read_text()
     STRIDE = int(re.search(r"#define MVG_LT_STRIDE\s+(\d+)", hdr).group(1))

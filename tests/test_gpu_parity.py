@@ -164,3 +164,33 @@ def test_error_paths():
     ctx.close()
     with pytest.raises(api.MvgError, match="out of range"):
         api.Context(99, 4, 4, 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [9, 10, 11, 12, 13, 14])
+def test_garbage_side_information_terminates_and_leaves_the_context_usable(seed):
+    """Random bytes in every SoA field (macroblock kinds, modes and QPs far outside their ranges, arbitrary levels): the
+    result is undefined, but the kernels must finish (every macroblock still publishes its line, so no row waits for
+    ever), must not fault, and the context must reconstruct a proper batch correctly afterwards."""
+    from minivideo_b200 import api, synth
+    from oracle import cpu
+    _, good = synth.generate(3, want_stream=False, width_mbs=9, height_mbs=7, profile_idc=100, transform8x8=1, seed=71)
+    rng = np.random.default_rng(seed)
+    bad = synth.generate(3, want_stream=False, width_mbs=9, height_mbs=7, profile_idc=100, transform8x8=1, seed=72)[1]
+    for name in ("mb_kind", "i16_mode", "chroma_mode", "cbp", "luma_modes"):
+        a = getattr(bad, name)
+        a[...] = rng.integers(0, 256, a.shape, dtype=np.uint8)
+    bad.qp_y[...] = rng.integers(-128, 128, bad.qp_y.shape).astype(np.int8)
+    bad.coeff[...] = rng.integers(-32768, 32768, bad.coeff.shape).astype(np.int16)
+    ctx = api.Context(0, 9, 7, 3)
+    ctx.set_sps_from(good)
+    ctx.upload(bad, 0)
+    ctx.run(0, 3, 1)
+    ctx.sync()                                          # a fault or a hang would surface here
+    ctx.upload(good, 0)
+    ctx.run(0, 3, 1)
+    ctx.sync()
+    want, _ = cpu.reconstruct(good, want_residual=True)
+    for i in range(3):
+        assert np.array_equal(ctx.download_yuv420(i), want[i])
+    ctx.close()
