@@ -370,6 +370,7 @@ int mvt_extract(const uint8_t *data, size_t len, const char *base, const char *o
     mvf_info info;
     mvf_get_info(st, &info);
     int32_t *sel = malloc(sizeof(int32_t) * (size_t)(n_want > info.n_idr ? n_want : info.n_idr + 1));
+    if (!sel) { fprintf(stderr, "mvt_extract: out of memory\n"); mvf_close(st); return MVG_FAILURE; }
     int n_sel = mvf_select_idr(st, n_want, mode, sel);
     if (n_sel < 1) { fprintf(stderr, "mvt_extract: no picture to decode after filtering\n"); free(sel); mvf_close(st); return MVG_FAILURE; }
     /* the reference appends _<k> when more than one picture was requested after filtering (export.c:630) */
@@ -377,7 +378,7 @@ int mvt_extract(const uint8_t *data, size_t len, const char *base, const char *o
     if (mode == 0) numbered = (n_want < info.n_idr ? n_want : info.n_idr) > 1;
     else {      /* picture_number after filtering = min(requested, candidates) = what 'ordered' would return */
         int32_t *tmp = malloc(sizeof(int32_t) * (size_t)(n_want > info.n_idr ? n_want : info.n_idr + 1));
-        numbered = mvf_select_idr(st, n_want, 1, tmp) > 1;
+        numbered = tmp ? mvf_select_idr(st, n_want, 1, tmp) > 1 : n_sel > 1;
         free(tmp);
     }
     const int W = 16 * info.width_mbs, H = 16 * info.height_mbs;
