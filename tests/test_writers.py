@@ -66,3 +66,22 @@ def test_writer_rejects_bad_arguments(lib):
     assert lib.mvt_write_image(b"/nonexistent-dir/x.bmp", 1, buf.ctypes.data, 4, 4) == 0
     assert lib.mvt_write_image(b"/tmp/x.bmp", 1, buf.ctypes.data, 0, 4) == 0
     assert lib.mvt_write_image(b"/tmp/x.bmp", 9, buf.ctypes.data, 4, 4) == 0
+
+
+def test_extract_rejects_bad_arguments_without_touching_a_gpu(lib):
+    """mvt_extract(): argument checks come before any CUDA call."""
+    from minivideo_b200 import synth
+    stream, _ = synth.generate(2, "cif", seed=5)
+    buf = np.frombuffer(stream, np.uint8)
+    lib.mvt_extract.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_int, C.POINTER(C.c_int)]
+    n = C.c_int(7)
+    ok = dict(fmt=0, n_want=1, mode=0, scale=1, device=0, threads=1, batch=0)
+    for bad in (dict(fmt=9), dict(fmt=-1), dict(n_want=0), dict(scale=0), dict(batch=-1)):
+        a = dict(ok, **bad)
+        assert lib.mvt_extract(buf.ctypes.data, len(buf), b"x", b"/tmp", a["fmt"], a["n_want"], a["mode"], a["scale"],
+                               a["device"], a["threads"], a["batch"], C.byref(n)) == 0, bad
+        assert n.value == 0
+    assert lib.mvt_extract(None, 0, b"x", b"/tmp", 0, 1, 0, 1, 0, 1, 0, C.byref(n)) == 0
+    garbage = np.arange(4096, dtype=np.uint8)
+    assert lib.mvt_extract(garbage.ctypes.data, len(garbage), b"x", b"/tmp", 0, 1, 0, 1, 0, 1, 0, C.byref(n)) == 0   # no SPS/PPS
