@@ -38,6 +38,15 @@ struct MvgTables {
 
 __device__ __forceinline__ int mvg_clip8(int v) { return min(max(v, 0), 255); }
 
+/* lane index read once through an opaque instruction: from `threadIdx.x & 31` the compiler re-reads the thread id
+ * (S2R, tens of cycles) inside the loops whenever it is short of registers */
+__device__ __forceinline__ int mvg_lane()
+{
+    int l;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+    return l;
+}
+
 /* Table 8-15: QPC as a function of qPI >= 30 (h264_transform.c:71) */
 __constant__ unsigned char mvg_qpc_tab[22] = {29,30,31,32,32,33,34,34,35,35,36,36,37,37,37,38,38,38,39,39,39,39};
 
@@ -242,7 +251,7 @@ k1_dequant_idct(K1Params p)
         s_qpc[pl][threadIdx.x - 52 * pl] = (uint16_t)(qpc | ((qpc / 6) << 8));
     }
 
-    const int lane = threadIdx.x & 31;
+    const int lane = mvg_lane();
     K1WarpSmem &s = s_warp[threadIdx.x >> 5];
     if (lane == 0) { mvg_mbar_init(&s.mbar[0], 1); mvg_mbar_init(&s.mbar[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -868,7 +877,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 2)
 k2_wavefront(K2Params p)
 {
     extern __shared__ __align__(128) uint8_t k2_smem[];
-    const int lane = threadIdx.x & 31;
+    const int lane = mvg_lane();
     const unsigned wid = __shfl_sync(MVG_FULL, threadIdx.x >> 5, 0);       /* warp-uniform by construction */
     /* layout: the tap tables sit on the first 2 KB boundary (so that (mode << 7) can be OR-ed into a lane's
      * table address); warp records fill the space before it, the others follow the tables */
