@@ -1,6 +1,6 @@
 """Wall-clock of the mv_thumbnailer CLI (bitstream file -> picture files on /dev/shm) against the reference CLI
 on the same 1080p stream.  Development aid; numbers go to profiles/ by hand.
-    python scripts/cli_timing.py [n_pictures] [n_reference_pictures]"""
+    python tests/tools/cli_timing.py [n_pictures] [n_reference_pictures]"""
 import os
 import subprocess
 import sys
@@ -8,7 +8,7 @@ import tempfile
 import time
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from minivideo_b200 import synth  # noqa: E402
 

@@ -1,6 +1,6 @@
 """BASELINE.json configs[4]: a 3840x2160 High-profile intra stream, 'distributed' thumbnail extraction, all GPUs of the
 box (`mv_thumbnailer -d all`) beside the reference CLI on the same stream.  Development aid; prints wall-clock times.
-    python scripts/config4_demo.py [n_pictures_in_stream] [n_extracted]"""
+    python tests/tools/config4_demo.py [n_pictures_in_stream] [n_extracted]"""
 import os
 import subprocess
 import sys
@@ -8,7 +8,7 @@ import tempfile
 import time
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from minivideo_b200 import synth  # noqa: E402
 
