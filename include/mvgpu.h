@@ -99,6 +99,7 @@ typedef struct mvg_timing {
     float k3_rgb_ms;            /* kernel 3: 4:2:0 -> RGB24 (+ box downscale)    */
     float total_ms;             /* first launch -> last kernel end               */
     int32_t launches;           /* kernels launched by this run                  */
+    float fused_ms;             /* fused pipeline: kf_recon (then k1 = k2 = 0)    */
 } mvg_timing;
 
 /* -- life cycle ----------------------------------------------------------- */
@@ -148,7 +149,19 @@ int mvg_clone_slot(mvg_ctx *ctx, int src_slot, int dst_slot);
  * if rgb_scale >= 1, kernel 3 (RGB24 at 1/rgb_scale size; rgb_scale = 0 skips
  * it).  Asynchronous on the context stream; mvg_sync() waits. */
 int mvg_run(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale);
+/* The same for callers that want the exported RGB picture and nothing else (what export_idr() does for the
+ * bmp/tga/png formats, export.c:535-601): ONE kernel, levels in -> full-size RGB24 out, no intermediate picture
+ * in HBM.  mvg_download_yuv420() is not available for these slots afterwards. */
+int mvg_run_rgb(mvg_ctx *ctx, int first_slot, int n_pics);
 int mvg_sync(mvg_ctx *ctx);
+
+/* Which kernels reconstruct: the fused kernel (default; dequantisation, transforms, prediction and -- for
+ * mvg_run_rgb() and the RGB-only end-to-end calls -- the RGB conversion in one launch) or round 1's separate
+ * kernels 1, 2, 3 (kept for comparison; same results).  The environment variable MVG_PIPELINE=split selects
+ * the latter at mvg_create(). */
+#define MVG_PIPELINE_FUSED 0
+#define MVG_PIPELINE_SPLIT 1
+int mvg_set_pipeline_mode(mvg_ctx *ctx, int mode);
 int mvg_get_timing(mvg_ctx *ctx, mvg_timing *out);
 
 /* Bracket a region of several mvg_run() calls with two CUDA events on the context

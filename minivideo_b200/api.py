@@ -17,7 +17,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libmvgpu.so"
 # every symbol include/mvgpu.h declares
 EXPORTS = (
     "mvg_create", "mvg_destroy", "mvg_last_error", "mvg_set_sps", "mvg_build_level_scale",
-    "mvg_upload", "mvg_clone_slot", "mvg_run", "mvg_sync", "mvg_get_timing", "mvg_mark", "mvg_mark_elapsed",
+    "mvg_upload", "mvg_clone_slot", "mvg_run", "mvg_run_rgb", "mvg_set_pipeline_mode", "mvg_sync", "mvg_get_timing", "mvg_mark", "mvg_mark_elapsed",
     "mvg_download_yuv420", "mvg_download_rgb", "mvg_download_residual", "mvg_decode_host",
     "mvg_pack_batch", "mvg_decode_host_packed",
     "mvg_device_count", "mvg_set_pipeline", "mvg_host_alloc", "mvg_host_free", "mvg_width", "mvg_height", "mvg_max_pics", "mvg_sm_count",
@@ -46,7 +46,10 @@ class Batch(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("k1_dequant_idct_ms", C.c_float), ("k2_wavefront_ms", C.c_float),
-                ("k3_rgb_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_int32)]
+                ("k3_rgb_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_int32), ("fused_ms", C.c_float)]
+
+
+PIPELINE_FUSED, PIPELINE_SPLIT = 0, 1
 
 
 _LIB = None
@@ -71,6 +74,8 @@ def load_library() -> C.CDLL:
     lib.mvg_upload.argtypes = [vp, C.POINTER(Batch), i32]
     lib.mvg_clone_slot.argtypes = [vp, i32, i32]
     lib.mvg_run.argtypes = [vp, i32, i32, i32]
+    lib.mvg_run_rgb.argtypes = [vp, i32, i32]
+    lib.mvg_set_pipeline_mode.argtypes = [vp, i32]
     lib.mvg_sync.argtypes = [vp]
     lib.mvg_get_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.mvg_mark.argtypes = [vp, i32]
@@ -207,6 +212,13 @@ class Context:
     def run(self, first_slot, n_pics, rgb_scale=1):
         self._ck(self.lib.mvg_run(self.handle, first_slot, n_pics, rgb_scale))
 
+    def run_rgb(self, first_slot, n_pics):
+        """One fused kernel: levels -> full-size RGB24 (no tiles; download_yuv420 is not available afterwards)."""
+        self._ck(self.lib.mvg_run_rgb(self.handle, first_slot, n_pics))
+
+    def set_pipeline_mode(self, mode: int):
+        self._ck(self.lib.mvg_set_pipeline_mode(self.handle, mode))
+
     def sync(self):
         self._ck(self.lib.mvg_sync(self.handle))
 
@@ -327,18 +339,27 @@ def unpack_levels(pk: "Packed") -> np.ndarray:
     return out
 
 
-def reconstruct(soa, device=0, rgb_scale=1, want_residual=False):
+def reconstruct(soa, device=0, rgb_scale=1, want_residual=False, mode=PIPELINE_FUSED):
     """Convenience for tests: run a whole Soa through the resident path.
-    Returns dict(yuv [P, 1.5WH], rgb [P, H/s, W/s, 3] | None, residual | None)."""
+    Returns dict(yuv [P, 1.5WH], rgb [P, H/s, W/s, 3] | None, rgb_k3 (the same through the tiles + kernel 3),
+    residual | None).  With the fused pipeline and rgb_scale 1, `rgb` comes from mvg_run_rgb() (one kernel, levels ->
+    RGB24) and `rgb_k3` from mvg_run() (fused kernel -> tiles -> kernel 3); otherwise both are the same array."""
     ctx = Context(device, soa.width_mbs, soa.height_mbs, soa.n_pics)
     try:
+        ctx.set_pipeline_mode(mode)
         ctx.set_sps_from(soa)
         ctx.upload(soa, 0)
         ctx.run(0, soa.n_pics, rgb_scale)
         ctx.sync()
+        timing = ctx.timing()
         yuv = np.stack([ctx.download_yuv420(i) for i in range(soa.n_pics)])
         rgb = np.stack([ctx.download_rgb(i, rgb_scale) for i in range(soa.n_pics)]) if rgb_scale >= 1 else None
         res = np.concatenate([ctx.download_residual(i) for i in range(soa.n_pics)]) if want_residual else None
-        return dict(yuv=yuv, rgb=rgb, residual=res, timing=ctx.timing())
+        rgb_k3 = rgb
+        if rgb_scale == 1 and mode == PIPELINE_FUSED:
+            ctx.run_rgb(0, soa.n_pics)
+            ctx.sync()
+            rgb = np.stack([ctx.download_rgb(i, 1) for i in range(soa.n_pics)])
+        return dict(yuv=yuv, rgb=rgb, rgb_k3=rgb_k3, residual=res, timing=timing)
     finally:
         ctx.close()

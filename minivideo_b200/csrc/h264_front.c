@@ -139,7 +139,7 @@ static inline int br_overrun(const br_t *b) { return b->pos > b->nbits; }
 typedef struct { size_t off, size; int type; } nal_t;     /* off: NAL header byte */
 
 typedef struct {
-    int valid, profile_idc, level_idc, chroma_format_idc;
+    int valid, id, err_code, profile_idc, level_idc, chroma_format_idc;
     int log2_max_frame_num, poc_type, log2_max_poc_lsb, delta_pic_order_always_zero;
     int width_mbs, height_mbs, frame_mbs_only;
     int crop[4];
@@ -147,17 +147,28 @@ typedef struct {
 } sps_t;
 
 typedef struct {
-    int valid, entropy_cabac, bottom_field_poc_present, init_qp, cb_off, cr_off;
-    int deblocking_control, constrained_intra, redundant_pic_cnt, transform8x8;
+    int valid, id, sps_id, err_code, entropy_cabac, bottom_field_poc_present, init_qp, cb_off, cr_off;
+    int deblocking_control, constrained_intra, redundant_pic_cnt, transform8x8, has_extension;
 } pps_t;
+
+/* A "parameter generation": the SPS + PPS pair in force for a run of IDR pictures.  The reference decodes every
+ * SPS / PPS NAL where it meets it (h264.c:128-150) and each slice looks its PPS up by pic_parameter_set_id and
+ * the SPS through it (h264_slice.c:168-169), so later pictures use later tables, offsets, QPs and even geometry.
+ * mvf_open_annexb() replays that in stream order and gives every IDR picture the index of its generation. */
+typedef struct { sps_t sps; pps_t pps; } paramgen_t;
+
+#define MVF_MAX_SPS 32
+#define MVF_MAX_PPS 256
 
 struct mvf_stream {
     const uint8_t *data; size_t len;
     nal_t *nals; int n_nals;
     int *idr; int n_idr;                                    /* indices into nals[] */
-    int n_param_nals;
-    sps_t sps; pps_t pps;
+    int *idr_gen;                                           /* per IDR picture: its generation, or -1 (no usable SPS/PPS) */
+    paramgen_t *gens; int n_gens, cap_gens;
+    int max_mbs;                                            /* largest picture of any generation, in macroblocks */
     char err[256];
+    pthread_mutex_t err_mu;                                 /* several parsers may report into err */
 };
 
 static char g_open_error[256];
@@ -234,15 +245,23 @@ static int parse_scaling_list(br_t *b, uint8_t *list, int n)
     return use_default;
 }
 
-static int parse_sps(mvf_stream *s, const uint8_t *rbsp, size_t n)
+/* seq_parameter_set_rbsp (7.3.2.1.1; decodeSPS, h264_parameterset.c:123-397).  *out is written only on success;
+ * *id receives seq_parameter_set_id (or -1) whenever it could be read, so that a failed SPS can retire the one
+ * it would have replaced. */
+static int parse_sps(mvf_stream *s, const uint8_t *rbsp, size_t n, sps_t *out, int *id)
 {
     br_t b = BR_INIT(rbsp, n * 8);
     sps_t v;
     memset(&v, 0, sizeof v);
+    *id = -1;
     v.profile_idc = (int)br_get(&b, 8);
     br_get(&b, 8);                                          /* constraint_set flags + reserved */
     v.level_idc = (int)br_get(&b, 8);
-    br_ue(&b);                                              /* seq_parameter_set_id */
+    {
+        const uint32_t sid = br_ue(&b);                     /* seq_parameter_set_id, 0..31 (7.4.2.1.1) */
+        if (sid >= MVF_MAX_SPS) return sfail(s, MVG_FAILURE, "bad SPS (seq_parameter_set_id %u)", sid);
+        v.id = *id = (int)sid;
+    }
     v.chroma_format_idc = 1;
     for (int i = 0; i < 6; i++) memset(v.list4[i], 16, 16);
     for (int i = 0; i < 2; i++) memset(v.list8[i], 16, 64);
@@ -299,16 +318,23 @@ static int parse_sps(mvf_stream *s, const uint8_t *rbsp, size_t n)
     if (br_bit(&b)) for (int i = 0; i < 4; i++) { const uint32_t cr = br_ue(&b); v.crop[i] = cr > 16384 ? 16384 : (int)cr; }
     if (br_overrun(&b) || v.width_mbs > 1024 || v.height_mbs > 1024) return sfail(s, MVG_FAILURE, "truncated or bad SPS");
     v.valid = 1;
-    s->sps = v;
+    *out = v;
     return MVG_SUCCESS;
 }
 
-static int parse_pps(mvf_stream *s, const uint8_t *rbsp, size_t n)
+/* pic_parameter_set_rbsp (7.3.2.2; decodePPS, h264_parameterset.c:812-926) */
+static int parse_pps(mvf_stream *s, const uint8_t *rbsp, size_t n, pps_t *out, int *id)
 {
     br_t b = BR_INIT(rbsp, rbsp_payload_bits(rbsp, n));
     pps_t v;
     memset(&v, 0, sizeof v);
-    br_ue(&b); br_ue(&b);                                   /* pps id, sps id */
+    *id = -1;
+    {
+        const uint32_t pid = br_ue(&b), sid = br_ue(&b);    /* 0..255, 0..31 (7.4.2.2) */
+        if (pid >= MVF_MAX_PPS || sid >= MVF_MAX_SPS)
+            return sfail(s, MVG_FAILURE, "bad PPS (pic_parameter_set_id %u, seq_parameter_set_id %u)", pid, sid);
+        v.id = *id = (int)pid; v.sps_id = (int)sid;
+    }
     v.entropy_cabac = br_bit(&b);
     v.bottom_field_poc_present = br_bit(&b);
     if (br_ue(&b) != 0) return sfail(s, MVG_UNSUPPORTED, "FMO (num_slice_groups_minus1 > 0)");
@@ -326,6 +352,7 @@ static int parse_pps(mvf_stream *s, const uint8_t *rbsp, size_t n)
     v.redundant_pic_cnt = br_bit(&b);
     v.cr_off = v.cb_off;
     if (b.pos < b.nbits) {                                  /* more_rbsp_data() */
+        v.has_extension = 1;
         v.transform8x8 = br_bit(&b);
         if (br_bit(&b)) return sfail(s, MVG_UNSUPPORTED, "PPS scaling lists (h264_parameterset.c:904-921)");
         v.cr_off = br_se(&b);
@@ -334,8 +361,57 @@ static int parse_pps(mvf_stream *s, const uint8_t *rbsp, size_t n)
     if (v.entropy_cabac) return sfail(s, MVG_UNSUPPORTED, "CABAC (entropy_coding_mode_flag = 1)");
     if (b.pos > b.nbits + 1) return sfail(s, MVG_FAILURE, "truncated PPS");
     v.valid = 1;
-    s->pps = v;
+    *out = v;
     return MVG_SUCCESS;
+}
+
+/* The generation of an IDR slice: read pic_parameter_set_id from the first bytes of its header (7.3.3), follow it
+ * to the PPS and SPS stored under those ids at this point of the stream, and find or append the pair.
+ * Returns the generation index, or -1 with a message in s->err when the picture names a parameter set the stream
+ * has not delivered (or delivered broken). */
+static int generation_of(mvf_stream *s, const nal_t *nl, const sps_t *sps_tab, const pps_t *pps_tab)
+{
+    uint8_t head[48 + 8];
+    size_t n = nl->size > 1 ? nl->size - 1 : 0, o = 0;
+    int zeros = 0;
+    for (size_t i = 0; i < n && o < 48; i++) {              /* unescape the first bytes (7.4.1) */
+        const uint8_t c = s->data[nl->off + 1 + i];
+        if (zeros >= 2 && c == 3) { zeros = 0; continue; }
+        head[o++] = c;
+        zeros = c == 0 ? zeros + 1 : 0;
+    }
+    memset(head + o, 0, 8);
+    br_t b = BR_INIT(head, o * 8);
+    br_ue(&b); br_ue(&b);                                   /* first_mb_in_slice, slice_type */
+    const uint32_t pid = br_ue(&b);
+    if (br_overrun(&b) || pid >= MVF_MAX_PPS) { sfail(s, MVG_FAILURE, "slice header: pic_parameter_set_id out of range"); return -1; }
+    const pps_t *pps = &pps_tab[pid];
+    if (!pps->valid) {
+        if (pps->err_code == 0) sfail(s, MVG_FAILURE, "slice refers to PPS %u, which the stream has not delivered", pid);
+        return -1;                                          /* a PPS that failed to parse left its message in s->err */
+    }
+    const sps_t *sps = &sps_tab[pps->sps_id];
+    if (!sps->valid) {
+        if (sps->err_code == 0) sfail(s, MVG_FAILURE, "PPS %u refers to SPS %d, which the stream has not delivered", pid, pps->sps_id);
+        return -1;
+    }
+    paramgen_t g;
+    memset(&g, 0, sizeof g);
+    g.sps = *sps; g.pps = *pps;
+    /* the PPS extension (transform_8x8_mode_flag, second_chroma_qp_index_offset) only exists for the reference when
+     * the SPS says High or above (h264_parameterset.c:898-926) */
+    if (g.sps.profile_idc < 100) { g.pps.transform8x8 = 0; g.pps.cr_off = g.pps.cb_off; }
+    for (int k = s->n_gens - 1; k >= 0; k--)
+        if (memcmp(&s->gens[k], &g, sizeof g) == 0) return k;
+    if (s->n_gens == s->cap_gens) {
+        const int cap = s->cap_gens ? 2 * s->cap_gens : 4;
+        paramgen_t *ng = realloc(s->gens, sizeof(paramgen_t) * (size_t)cap);
+        if (!ng) { sfail(s, MVG_FAILURE, "out of memory"); return -1; }
+        s->gens = ng; s->cap_gens = cap;
+    }
+    s->gens[s->n_gens] = g;
+    if (g.sps.width_mbs * g.sps.height_mbs > s->max_mbs) s->max_mbs = g.sps.width_mbs * g.sps.height_mbs;
+    return s->n_gens++;
 }
 
 int mvf_open_annexb(const uint8_t *data, size_t len, mvf_stream **out)
@@ -347,11 +423,12 @@ int mvf_open_annexb(const uint8_t *data, size_t len, mvf_stream **out)
     mvf_stream *s = calloc(1, sizeof *s);
     if (!s) return sfail(NULL, MVG_FAILURE, "out of memory");
     s->data = data; s->len = len;
+    pthread_mutex_init(&s->err_mu, NULL);
 
     /* start codes 00 00 01 (a 4-byte start code is the same with one more leading zero) */
     int cap = 1024;
     s->nals = malloc(sizeof(nal_t) * (size_t)cap);
-    if (!s->nals) { free(s); return sfail(NULL, MVG_FAILURE, "out of memory"); }
+    if (!s->nals) { mvf_close(s); return sfail(NULL, MVG_FAILURE, "out of memory"); }
     /* look for the 01 (one byte in 256 of entropy-coded data) and check the two bytes before it */
     for (const uint8_t *q = data + 2, *const end = data + len - 1; q < end; q++) {
         q = memchr(q, 1, (size_t)(end - q));
@@ -359,7 +436,7 @@ int mvf_open_annexb(const uint8_t *data, size_t len, mvf_stream **out)
         if (q[-1] != 0 || q[-2] != 0) continue;
         if (s->n_nals == cap) {
             nal_t *nn = realloc(s->nals, sizeof(nal_t) * (size_t)cap * 2);
-            if (!nn) { free(s->nals); free(s); return sfail(NULL, MVG_FAILURE, "out of memory"); }
+            if (!nn) { mvf_close(s); return sfail(NULL, MVG_FAILURE, "out of memory"); }
             s->nals = nn; cap *= 2;
         }
         s->nals[s->n_nals].off = (size_t)(q - data) + 1;
@@ -372,31 +449,59 @@ int mvf_open_annexb(const uint8_t *data, size_t len, mvf_stream **out)
         s->nals[k].size = end - s->nals[k].off;
     }
     s->idr = malloc(sizeof(int) * (size_t)(s->n_nals + 1));
-    if (!s->idr) { free(s->nals); free(s); return sfail(NULL, MVG_FAILURE, "out of memory"); }
-    int rc = MVG_SUCCESS;
+    s->idr_gen = malloc(sizeof(int) * (size_t)(s->n_nals + 1));
+    sps_t *sps_tab = calloc(MVF_MAX_SPS, sizeof *sps_tab);
+    pps_t *pps_tab = calloc(MVF_MAX_PPS, sizeof *pps_tab);
+    if (!s->idr || !s->idr_gen || !sps_tab || !pps_tab) {
+        free(sps_tab); free(pps_tab); mvf_close(s);
+        return sfail(NULL, MVG_FAILURE, "out of memory");
+    }
+    /* Parameter sets in stream order, as the reference's NAL loop meets them (h264.c:128-150): a new SPS / PPS
+     * replaces the one stored under its id (h264_parameterset.c:162-164, :835-837 -- the reference files a PPS under
+     * its seq_parameter_set_id and looks it up by pic_parameter_set_id, which is the same slot whenever the two
+     * ids are equal, the only case it decodes; this front end files it under pic_parameter_set_id as 7.4.1.2.1 says).
+     * One that cannot be used retires the slot: pictures that name it fail one by one, with its message. */
+    int rc_first = MVG_SUCCESS, usable = 0;
+    char err_first[256] = "";
     uint8_t *tmp = NULL;
-    for (int k = 0; k < s->n_nals && rc == MVG_SUCCESS; k++) {
+    for (int k = 0; k < s->n_nals; k++) {
         const nal_t *nl = &s->nals[k];
-        if (nl->type == 5) { s->idr[s->n_idr++] = k; continue; }
+        if (nl->type == 5) {
+            s->idr_gen[s->n_idr] = generation_of(s, nl, sps_tab, pps_tab);
+            if (s->idr_gen[s->n_idr] >= 0) usable++;
+            else if (rc_first == MVG_SUCCESS) { rc_first = MVG_FAILURE; memcpy(err_first, s->err, sizeof err_first); }
+            s->idr[s->n_idr++] = k;
+            continue;
+        }
         if (nl->type != 7 && nl->type != 8) continue;
-        if (s->n_idr == 0) s->n_param_nals++;
-        if ((nl->type == 7 && s->sps.valid) || (nl->type == 8 && s->pps.valid)) continue;   /* first ones win */
         {
             uint8_t *nt = realloc(tmp, nl->size + RBSP_SLACK);
-            if (!nt) { rc = sfail(s, MVG_FAILURE, "out of memory"); break; }
+            if (!nt) { free(tmp); free(sps_tab); free(pps_tab); mvf_close(s); return sfail(NULL, MVG_FAILURE, "out of memory"); }
             tmp = nt;
         }
-        size_t n = unescape(data + nl->off + 1, nl->size - 1, tmp);
-        rc = nl->type == 7 ? parse_sps(s, tmp, n) : parse_pps(s, tmp, n);
+        size_t n = unescape(data + nl->off + 1, nl->size ? nl->size - 1 : 0, tmp);
+        int id = -1, rc;
+        if (nl->type == 7) {
+            sps_t v;
+            rc = parse_sps(s, tmp, n, &v, &id);
+            if (rc == MVG_SUCCESS) sps_tab[id] = v;
+            else if (id >= 0) { memset(&sps_tab[id], 0, sizeof sps_tab[id]); sps_tab[id].err_code = rc; }
+        } else {
+            pps_t v;
+            rc = parse_pps(s, tmp, n, &v, &id);
+            if (rc == MVG_SUCCESS) pps_tab[id] = v;
+            else if (id >= 0) { memset(&pps_tab[id], 0, sizeof pps_tab[id]); pps_tab[id].err_code = rc; }
+        }
+        if (rc != MVG_SUCCESS && rc_first == MVG_SUCCESS) { rc_first = rc; memcpy(err_first, s->err, sizeof err_first); }
     }
-    free(tmp);
-    if (rc == MVG_SUCCESS && (!s->sps.valid || !s->pps.valid)) rc = sfail(s, MVG_FAILURE, "no SPS/PPS in the stream");
-    if (rc == MVG_SUCCESS && s->pps.transform8x8 && s->sps.profile_idc < 100) s->pps.transform8x8 = 0;
-    if (rc != MVG_SUCCESS) {
-        memcpy(g_open_error, s->err, sizeof g_open_error);
+    free(tmp); free(sps_tab); free(pps_tab);
+    if (!usable) {          /* nothing to decode: answer with the first thing that went wrong */
+        if (rc_first == MVG_SUCCESS) { rc_first = MVG_FAILURE; snprintf(err_first, sizeof err_first, "no SPS/PPS in the stream"); }
+        memcpy(g_open_error, err_first, sizeof g_open_error);
         mvf_close(s);
-        return rc;
+        return rc_first;
     }
+    s->err[0] = 0;
     *out = s;
     return MVG_SUCCESS;
 }
@@ -404,7 +509,8 @@ int mvf_open_annexb(const uint8_t *data, size_t len, mvf_stream **out)
 int mvf_close(mvf_stream *s)
 {
     if (!s) return MVG_FAILURE;
-    free(s->nals); free(s->idr); free(s);
+    pthread_mutex_destroy(&s->err_mu);
+    free(s->nals); free(s->idr); free(s->idr_gen); free(s->gens); free(s);
     return MVG_SUCCESS;
 }
 

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <thread>
@@ -18,6 +19,7 @@
 
 #include "mvg_internal.h"
 #include "mvg_kernels.cuh"
+#include "mvg_fused.cuh"
 
 /* ------------------------------------------------------------------------- */
 
@@ -29,7 +31,8 @@ static char g_create_error[512] = "";
 
 struct mvg_ctx {
     int device = -1, sm_count = 0;
-    int k1_ctas_per_sm = 1, k2_ctas_per_sm = 1;
+    int k1_ctas_per_sm = 1, k2_ctas_per_sm = 1, kf_ctas_per_sm = 1;
+    int mode = MVG_PIPELINE_FUSED;   /* mvg_set_pipeline_mode() */
     int max_w = 0, max_h = 0, max_pics = 0;
     int w_mbs = 0, h_mbs = 0;
     bool have_sps = false;
@@ -39,7 +42,8 @@ struct mvg_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_mark[2] = {nullptr, nullptr};
     cudaEvent_t ev_h2d[MVG_PIPE_DEPTH] = {}, ev_comp[MVG_PIPE_DEPTH] = {}, ev_d2h[MVG_PIPE_DEPTH] = {};
-    bool ran_k3 = false;
+    bool ran_k3 = false, ran_fused = false;
+    bool tiles_valid = false;        /* the last run wrote macroblock tiles (planar YUV can be gathered) */
     int launches = 0, last_scale = 0;
 
     /* inputs (SoA), slot-major */
@@ -288,7 +292,12 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     TRY("occupancy k1", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_ctas_per_sm, k1_dequant_idct, K1_WARPS * 32, sizeof(K1WarpSmem) * K1_WARPS));
     TRY("k2 shared memory", cudaFuncSetAttribute(k2_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM_BYTES));
     TRY("occupancy k2", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2_ctas_per_sm, k2_wavefront, K2_WARPS * 32, K2_SMEM_BYTES));
-    if (ctx->k1_ctas_per_sm < 1 || ctx->k2_ctas_per_sm < 1) return bail("kernel does not fit on an SM", cudaErrorLaunchOutOfResources);
+    TRY("kf shared memory", cudaFuncSetAttribute(kf_recon<KF_OUT_TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES));
+    TRY("kf shared memory", cudaFuncSetAttribute(kf_recon<KF_OUT_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES));
+    TRY("occupancy kf", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->kf_ctas_per_sm, kf_recon<KF_OUT_RGB>, KF_WARPS * 32, KF_SMEM_BYTES));
+    if (ctx->k1_ctas_per_sm < 1 || ctx->k2_ctas_per_sm < 1 || ctx->kf_ctas_per_sm < 1)
+        return bail("kernel does not fit on an SM", cudaErrorLaunchOutOfResources);
+    if (const char *m = getenv("MVG_PIPELINE")) ctx->mode = strcmp(m, "split") == 0 ? MVG_PIPELINE_SPLIT : MVG_PIPELINE_FUSED;
     TRY("stream", cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     TRY("stream", cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     TRY("stream", cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
@@ -307,10 +316,8 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     TRY("alloc cbp", dalloc(&ctx->d_cbp, n));
     TRY("alloc luma_modes", dalloc(&ctx->d_modes, n * 16));
     TRY("alloc coeff", dalloc(&ctx->d_coeff, n * 384));
-    TRY("alloc residual", dalloc(&ctx->d_resid, n * 384));
-    TRY("alloc ctl", dalloc(&ctx->d_ctl, n));
+    /* d_resid, d_ctl (split pipeline / residual tap) and d_yuv (planar output) are allocated on first use */
     TRY("alloc tiles", dalloc(&ctx->d_tiles, n * 384));
-    TRY("alloc yuv", dalloc(&ctx->d_yuv, n * 384));
     TRY("alloc rgb", dalloc(&ctx->d_rgb, n * 768));
     TRY("alloc halo", dalloc(&ctx->d_halo, n * 8));
     TRY("clear halo", cudaMemset(ctx->d_halo, 0, n * 8 * sizeof(uint2)));
@@ -483,9 +490,24 @@ extern "C" int mvg_clone_slot(mvg_ctx *ctx, int src_slot, int dst_slot)
 /* ------------------------------------------------------------------------- */
 /* launches                                                                    */
 
+/* buffers only some paths need */
+static int ensure_yuv(mvg_ctx *ctx)
+{
+    if (!ctx->d_yuv) CK(ctx, cudaMalloc((void **)&ctx->d_yuv, ctx->n_mb_max() * (size_t)ctx->max_pics * 384));
+    return MVG_SUCCESS;
+}
+static int ensure_split(mvg_ctx *ctx)
+{
+    const size_t n = ctx->n_mb_max() * (size_t)ctx->max_pics;
+    if (!ctx->d_resid) CK(ctx, cudaMalloc((void **)&ctx->d_resid, n * 768));
+    if (!ctx->d_ctl) CK(ctx, cudaMalloc((void **)&ctx->d_ctl, n * sizeof(MvgMbCtl)));
+    return MVG_SUCCESS;
+}
+
 /* planar I420 of slots [first_slot, first_slot + n_pics) from the macroblock tiles (kernel 4) */
 static int launch_planar(mvg_ctx *ctx, int first_slot, int n_pics, cudaStream_t st)
 {
+    if (ensure_yuv(ctx) != MVG_SUCCESS) return MVG_FAILURE;
     K3Params p;
     p.tiles = ctx->d_tiles; p.yuv = ctx->d_yuv; p.rgb = nullptr; p.width = 16 * ctx->w_mbs; p.height = 16 * ctx->h_mbs;
     p.scale = 1; p.first_slot = first_slot; p.n_pics = n_pics;
@@ -496,7 +518,48 @@ static int launch_planar(mvg_ctx *ctx, int first_slot, int n_pics, cudaStream_t 
     return MVG_SUCCESS;
 }
 
-static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale, cudaStream_t st, bool timed)
+/* kernel 1 alone over slots [first_slot, first_slot + n_pics): residual + control records (split pipeline, residual tap) */
+static int launch_k1(mvg_ctx *ctx, int first_slot, int n_pics, cudaStream_t st)
+{
+    if (ensure_split(ctx) != MVG_SUCCESS) return MVG_FAILURE;
+    const size_t n = ctx->n_mb();
+    K1Params p;
+    const size_t o = (size_t)first_slot * n;
+    p.mb_kind = ctx->d_kind + o; p.i16_mode = ctx->d_i16 + o; p.chroma_mode = ctx->d_cm + o;
+    p.luma_modes = ctx->d_modes + o * 16; p.qp_y = ctx->d_qp + o; p.coeff = ctx->d_coeff + o * 384;
+    p.resid = ctx->d_resid + o * 384; p.ctl = ctx->d_ctl + o; p.tab = ctx->d_tab;
+    p.n_mbs = (long long)n * n_pics;
+    const long long groups = (p.n_mbs + K1_GROUP - 1) / K1_GROUP;
+    const long long want = (groups + K1_WARPS - 1) / K1_WARPS;
+    const int grid = (int)std::min<long long>(want, (long long)ctx->sm_count * ctx->k1_ctas_per_sm);
+    k1_dequant_idct<<<grid, K1_WARPS * 32, sizeof(K1WarpSmem) * K1_WARPS, st>>>(p);
+    CK(ctx, cudaGetLastError());
+    return MVG_SUCCESS;
+}
+
+static int launch_k3(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale, cudaStream_t st)
+{
+    const size_t n = ctx->n_mb();
+    const int width = 16 * ctx->w_mbs, height = 16 * ctx->h_mbs;
+    K3Params p;
+    p.tiles = ctx->d_tiles; p.yuv = nullptr; p.rgb = ctx->d_rgb; p.width = width; p.height = height; p.scale = rgb_scale;
+    p.first_slot = first_slot; p.n_pics = n_pics;
+    const long long threads = rgb_scale == 1 ? (long long)n * 8 * n_pics       /* 8 lanes per macroblock */
+                                             : (long long)(width / rgb_scale) * (height / rgb_scale) * n_pics;
+    const int grid = (int)std::min<long long>((threads + 255) / 256, (long long)ctx->sm_count * 32);
+    const bool pow2 = rgb_scale == 2 || rgb_scale == 4 || rgb_scale == 8 || rgb_scale == 16;
+    if (rgb_scale == 1) k3_rgb_full<<<grid, 256, 0, st>>>(p);
+    else if (pow2) k3_rgb_scaled<<<(int)std::min<long long>(((long long)n * n_pics + 31) / 32, (long long)ctx->sm_count * 16), 256, 0, st>>>(p);
+    else k3_rgb_scaled_generic<<<grid, 256, 0, st>>>(p);
+    CK(ctx, cudaGetLastError());
+    return MVG_SUCCESS;
+}
+
+/* The reconstruction stages for slots [first_slot, first_slot + n_pics).
+ *   fused pipeline (default): kf_recon<RGB> alone when only full-size RGB24 is wanted (`want_tiles` false and
+ *     rgb_scale 1); otherwise kf_recon<TILES> and, for rgb_scale >= 1, kernel 3 on the tiles;
+ *   split pipeline (mvg_set_pipeline_mode): kernel 1, kernel 2, kernel 3 as in round 1. */
+static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale, bool want_tiles, cudaStream_t st, bool timed)
 {
     const int W = ctx->w_mbs, H = ctx->h_mbs;
     const size_t n = ctx->n_mb();
@@ -507,56 +570,54 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
     int *work = ctx->d_work + ctx->work_next;
     ctx->work_next = (ctx->work_next + 1) % MVG_WORK_RING;
     CK(ctx, cudaMemsetAsync(work, 0, sizeof(int), st));
+    if (++ctx->epoch == 0) ctx->epoch = 1;      /* 0 is the value of never-written words */
 
+    const bool fused = ctx->mode == MVG_PIPELINE_FUSED;
+    const bool rgb_direct = fused && rgb_scale == 1 && !want_tiles;
     int launches = 0;
     if (timed) CK(ctx, cudaEventRecord(ctx->ev[0], st));
-    {
-        K1Params p;
-        const size_t o = (size_t)first_slot * n;
-        p.mb_kind = ctx->d_kind + o; p.i16_mode = ctx->d_i16 + o; p.chroma_mode = ctx->d_cm + o;
-        p.luma_modes = ctx->d_modes + o * 16; p.qp_y = ctx->d_qp + o; p.coeff = ctx->d_coeff + o * 384;
-        p.resid = ctx->d_resid + o * 384; p.ctl = ctx->d_ctl + o; p.tab = ctx->d_tab;
-        p.n_mbs = (long long)n * n_pics;
-        const long long groups = (p.n_mbs + K1_GROUP - 1) / K1_GROUP;
-        const long long want = (groups + K1_WARPS - 1) / K1_WARPS;
-        const int grid = (int)std::min<long long>(want, (long long)ctx->sm_count * ctx->k1_ctas_per_sm);
-        k1_dequant_idct<<<grid, K1_WARPS * 32, sizeof(K1WarpSmem) * K1_WARPS, st>>>(p);
+    if (!fused) {
+        if (launch_k1(ctx, first_slot, n_pics, st) != MVG_SUCCESS) return MVG_FAILURE;
         launches++;
     }
     if (timed) CK(ctx, cudaEventRecord(ctx->ev[1], st));
-    {
+    const long long items = (long long)n_pics * H;
+    if (fused) {
+        KFParams p;
+        p.mb_kind = ctx->d_kind; p.i16_mode = ctx->d_i16; p.chroma_mode = ctx->d_cm; p.luma_modes = ctx->d_modes;
+        p.qp_y = ctx->d_qp; p.coeff = ctx->d_coeff; p.tiles = ctx->d_tiles; p.rgb = ctx->d_rgb; p.halo = ctx->d_halo;
+        p.work = work; p.tab = ctx->d_tab; p.luts = ctx->d_luts; p.epoch = ctx->epoch;
+        p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics; p.group = MVG_K2_GROUP;
+        p.sel[0] = 1u; p.sel[1] = 1u << 8; p.sel[2] = 1u << 16; p.sel[3] = 1u << 24;
+        const int grid = (int)std::min<long long>((items + KF_WARPS - 1) / KF_WARPS, (long long)ctx->sm_count * ctx->kf_ctas_per_sm);
+        if (rgb_direct) kf_recon<KF_OUT_RGB><<<grid, KF_WARPS * 32, KF_SMEM_BYTES, st>>>(p);
+        else kf_recon<KF_OUT_TILES><<<grid, KF_WARPS * 32, KF_SMEM_BYTES, st>>>(p);
+        launches++;
+    } else {
         K2Params p;
         p.resid = ctx->d_resid; p.ctl = ctx->d_ctl; p.tiles = ctx->d_tiles; p.halo = ctx->d_halo;
-        if (++ctx->epoch == 0) ctx->epoch = 1;      /* 0 is the value of never-written words */
         p.epoch = ctx->epoch; p.group = MVG_K2_GROUP; p.stats = ctx->d_stats;
         p.sel[0] = 1u; p.sel[1] = 1u << 8; p.sel[2] = 1u << 16; p.sel[3] = 1u << 24;
         p.work = work; p.luts = ctx->d_luts; p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics;
-        const long long items = (long long)n_pics * H;
         const int grid = (int)std::min<long long>((items + K2_WARPS - 1) / K2_WARPS, (long long)ctx->sm_count * ctx->k2_ctas_per_sm);
         k2_wavefront<<<grid, K2_WARPS * 32, K2_SMEM_BYTES, st>>>(p);
         launches++;
     }
+    CK(ctx, cudaGetLastError());
     if (timed) CK(ctx, cudaEventRecord(ctx->ev[2], st));
-    if (rgb_scale >= 1) {
-        K3Params p;
-        p.tiles = ctx->d_tiles; p.yuv = ctx->d_yuv; p.rgb = ctx->d_rgb; p.width = width; p.height = height; p.scale = rgb_scale;
-        p.first_slot = first_slot; p.n_pics = n_pics;
-        const long long threads = rgb_scale == 1 ? (long long)n * 8 * n_pics       /* 8 lanes per macroblock */
-                                                 : (long long)(width / rgb_scale) * (height / rgb_scale) * n_pics;
-        const int grid = (int)std::min<long long>((threads + 255) / 256, (long long)ctx->sm_count * 32);
-        const bool pow2 = rgb_scale == 2 || rgb_scale == 4 || rgb_scale == 8 || rgb_scale == 16;
-        if (rgb_scale == 1) k3_rgb_full<<<grid, 256, 0, st>>>(p);
-        else if (pow2) k3_rgb_scaled<<<(int)std::min<long long>(((long long)n * n_pics + 31) / 32, (long long)ctx->sm_count * 16), 256, 0, st>>>(p);
-        else k3_rgb_scaled_generic<<<grid, 256, 0, st>>>(p);
+    const bool run_k3 = rgb_scale >= 1 && !rgb_direct;
+    if (run_k3) {
+        if (launch_k3(ctx, first_slot, n_pics, rgb_scale, st) != MVG_SUCCESS) return MVG_FAILURE;
         launches++;
     }
     if (timed) {
         CK(ctx, cudaEventRecord(ctx->ev[3], st));
-        ctx->ran_k3 = rgb_scale >= 1;
+        ctx->ran_k3 = run_k3;
+        ctx->ran_fused = fused;
         ctx->launches = launches;
     }
     ctx->last_scale = rgb_scale;
-    CK(ctx, cudaGetLastError());
+    ctx->tiles_valid = !rgb_direct;
     return MVG_SUCCESS;
 }
 
@@ -564,7 +625,21 @@ extern "C" int mvg_run(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale)
 {
     if (check_ready(ctx, first_slot, n_pics, "mvg_run") != MVG_SUCCESS) return MVG_FAILURE;
     CK(ctx, cudaSetDevice(ctx->device));
-    return launch_stages(ctx, first_slot, n_pics, rgb_scale, ctx->stream, true);
+    return launch_stages(ctx, first_slot, n_pics, rgb_scale, true, ctx->stream, true);
+}
+
+extern "C" int mvg_run_rgb(mvg_ctx *ctx, int first_slot, int n_pics)
+{
+    if (check_ready(ctx, first_slot, n_pics, "mvg_run_rgb") != MVG_SUCCESS) return MVG_FAILURE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return launch_stages(ctx, first_slot, n_pics, 1, false, ctx->stream, true);
+}
+
+extern "C" int mvg_set_pipeline_mode(mvg_ctx *ctx, int mode)
+{
+    if (!ctx || (mode != MVG_PIPELINE_FUSED && mode != MVG_PIPELINE_SPLIT)) return MVG_FAILURE;
+    ctx->mode = mode;
+    return MVG_SUCCESS;
 }
 
 extern "C" int mvg_sync(mvg_ctx *ctx)
@@ -582,8 +657,12 @@ extern "C" int mvg_get_timing(mvg_ctx *ctx, mvg_timing *out)
     if (!ctx || !out) return MVG_FAILURE;
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaEventSynchronize(ctx->ev[3]));
-    CK(ctx, cudaEventElapsedTime(&out->k1_dequant_idct_ms, ctx->ev[0], ctx->ev[1]));
-    CK(ctx, cudaEventElapsedTime(&out->k2_wavefront_ms, ctx->ev[1], ctx->ev[2]));
+    out->k1_dequant_idct_ms = out->k2_wavefront_ms = out->fused_ms = 0.f;
+    if (ctx->ran_fused) CK(ctx, cudaEventElapsedTime(&out->fused_ms, ctx->ev[1], ctx->ev[2]));
+    else {
+        CK(ctx, cudaEventElapsedTime(&out->k1_dequant_idct_ms, ctx->ev[0], ctx->ev[1]));
+        CK(ctx, cudaEventElapsedTime(&out->k2_wavefront_ms, ctx->ev[1], ctx->ev[2]));
+    }
     out->k3_rgb_ms = 0.f;
     if (ctx->ran_k3) CK(ctx, cudaEventElapsedTime(&out->k3_rgb_ms, ctx->ev[2], ctx->ev[3]));
     CK(ctx, cudaEventElapsedTime(&out->total_ms, ctx->ev[0], ctx->ev[3]));
@@ -619,10 +698,11 @@ static size_t rgb_bytes(const mvg_ctx *ctx, int scale)
 extern "C" int mvg_download_yuv420(mvg_ctx *ctx, int slot, uint8_t *y, uint8_t *cb, uint8_t *cr)
 {
     if (check_ready(ctx, slot, 1, "mvg_download_yuv420") != MVG_SUCCESS) return MVG_FAILURE;
+    if (!ctx->tiles_valid) return fail(ctx, "mvg_download_yuv420: the last run produced RGB24 only (mvg_run_rgb); use mvg_run()");
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t n = ctx->n_mb();
-    const uint8_t *src = ctx->d_yuv + (size_t)slot * n * 384;
     if (launch_planar(ctx, slot, 1, ctx->stream) != MVG_SUCCESS) return MVG_FAILURE;
+    const uint8_t *src = ctx->d_yuv + (size_t)slot * n * 384;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     if (y) CK(ctx, cudaMemcpy(y, src, n * 256, cudaMemcpyDeviceToHost));
     if (cb) CK(ctx, cudaMemcpy(cb, src + n * 256, n * 64, cudaMemcpyDeviceToHost));
@@ -647,6 +727,8 @@ extern "C" int mvg_download_residual(mvg_ctx *ctx, int slot, int16_t *residual)
     if (!residual) return fail(ctx, "mvg_download_residual: NULL");
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t n = ctx->n_mb();
+    /* the fused kernel never writes the residual to HBM: run kernel 1 (the same transform code) on this slot */
+    if (launch_k1(ctx, slot, 1, ctx->stream) != MVG_SUCCESS) return MVG_FAILURE;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     int16_t *tmp = new (std::nothrow) int16_t[n * 384];
     if (!tmp) return fail(ctx, "mvg_download_residual: out of host memory");
@@ -683,6 +765,7 @@ static int decode_pipeline(mvg_ctx *ctx, int n_pics, uint8_t *yuv_out, uint8_t *
     const int scale = rgb_out ? rgb_scale : 0;
     const size_t n = ctx->n_mb();
     const size_t yuv_sz = n * 384, rgb_sz = scale ? rgb_bytes(ctx, scale) : 0;
+    if (yuv_out && ensure_yuv(ctx) != MVG_SUCCESS) return MVG_FAILURE;
     /* slot regions: MVG_PIPE_DEPTH of them; a region holds at most a third of the context
      * and at most an eighth of the batch, so that H2D, kernels and D2H of neighbouring
      * chunks overlap even when the whole batch would fit in one region. */
@@ -703,7 +786,7 @@ static int decode_pipeline(mvg_ctx *ctx, int n_pics, uint8_t *yuv_out, uint8_t *
         CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[r], 0));
         if (idx >= depth) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[r], 0));
         if (expand(slot0, cnt) != MVG_SUCCESS) return MVG_FAILURE;
-        if (launch_stages(ctx, slot0, cnt, scale, ctx->stream, false) != MVG_SUCCESS) return MVG_FAILURE;
+        if (launch_stages(ctx, slot0, cnt, scale, yuv_out != nullptr, ctx->stream, false) != MVG_SUCCESS) return MVG_FAILURE;
         if (yuv_out && launch_planar(ctx, slot0, cnt, ctx->stream) != MVG_SUCCESS) return MVG_FAILURE;
         CK(ctx, cudaEventRecord(ctx->ev_comp[r], ctx->stream));
         CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[r], 0));

@@ -1,0 +1,344 @@
+/*
+ * mvg_fused.cuh -- the fused reconstruction kernel: levels in, reconstructed picture out, one launch.
+ *
+ *   kf_recon<KF_OUT_TILES>  dequantisation + inverse transforms + intra prediction + residual add
+ *                           -> macroblock tiles (what kernel 3 / kernel 4 read)
+ *   kf_recon<KF_OUT_RGB>    the same + 4:2:0 -> RGB24 of mb_to_rgb() (export_utils.c:266-303)
+ *                           -> the RGB picture; nothing else is written
+ *
+ * This is kernel 1 folded into the row loop of kernel 2 (and kernel 3 folded into its write-out), the way the
+ * reference itself interleaves them per block (h264_intra_prediction.c:173,954,1929,2319 call
+ * transform4x4_luma / transform8x8_luma / transform16x16_luma / transform4x4_chroma of h264_transform.c:121-402
+ * right after predicting).  The residual never exists in HBM: per picture the kernel reads the 789 B of
+ * structure-of-arrays per macroblock and writes 384 B (tiles) or 768 B (RGB24), against 31.8 MB for the three
+ * separate kernels.  All device code it is made of lives in mvg_kernels.cuh and is shared with kernels 1-3
+ * (mvg_xf_group, k2_luma4/8/16, k2_chroma), so the split pipeline and the fused one cannot drift apart.
+ */
+#pragma once
+
+#include "mvg_kernels.cuh"
+
+#ifndef KF_GROUP
+#define KF_GROUP 2          /* macroblocks transformed together (and written out together in RGB mode) */
+#endif
+#ifndef KF_WARPS
+#define KF_WARPS 24         /* warps per CTA; one CTA per SM */
+#endif
+#define KF_OUT_TILES 0
+#define KF_OUT_RGB   1
+/* RGB staging rows: KF_GROUP x 48 bytes + padding that makes the 8-byte stores of the conversion (lane = 2 y + h,
+ * 24 bytes apart) free of bank conflicts: 28 y + 6 h resp. 52 y + 6 h words cover 16 distinct bank pairs */
+#define KF_RGB_STRIDE (KF_GROUP == 2 ? 112 : KF_GROUP * 48 + 16)
+
+struct KFParams {
+    const uint8_t *mb_kind, *i16_mode, *chroma_mode, *luma_modes;   /* [slot][n_mb](x16), slot 0 */
+    const int8_t  *qp_y;
+    const int16_t *coeff;       /* [slot][n_mb][384] levels                                           */
+    uint8_t       *tiles;       /* [slot][n_mb][384] (KF_OUT_TILES)                                   */
+    uint8_t       *rgb;         /* [slot][3 * W * H] (KF_OUT_RGB)                                     */
+    uint2         *halo;        /* [slot][n_mb][8] bottom sample line of every macroblock + epoch     */
+    int           *work;        /* work counter of this launch (starts at 0)                          */
+    const MvgTables *tab;
+    const MvgLuts   *luts;
+    unsigned        epoch;
+    int w_mbs, h_mbs, first_slot, n_pics, group;
+    unsigned        sel[4];
+};
+
+/* Member order matters (see K2WarpSmem): lanes without a block in an Intra4x4 step read up to 64 bytes below
+ * the residual and 140 bytes below lt[] (and past the end of lt[] into ct[]); all of that stays inside this record. */
+struct KFWarpSmem {
+    union {
+        MvgXfScratch<KF_GROUP> x;                       /* transform stage                                      */
+        uint8_t rgb[16 * KF_RGB_STRIDE];                /* RGB24 rows of the group (prediction stage, KF_OUT_RGB) */
+    } u;
+    __align__(128) int16_t tile[2][KF_GROUP * 384];     /* levels in -> residual in place; double buffered      */
+    __align__(8) uint64_t mbar[2];
+    __align__(16) uint8_t lt[MVG_LT_ROWS * MVG_LT_STRIDE];
+    __align__(16) uint8_t ct[2][MVG_CT_PLANE];
+    __align__(16) uint8_t n8[MVG_N8_BYTES];
+};
+
+#define KF_LUT_BYTES  ((sizeof(MvgLuts) + 127) / 128 * 128)
+#define KF_TAB_BYTES  ((sizeof(MvgXfTables) + 127) / 128 * 128)
+#define KF_SMEM_BYTES (sizeof(KFWarpSmem) * KF_WARPS + 2048 + KF_LUT_BYTES + KF_TAB_BYTES)
+
+/* Persistent warps, one CTA per SM.  A work item is one macroblock row of one picture (claimed from an atomic
+ * counter, rows of a picture in order, pictures interleaved: see k2_wavefront for the dependency protocol, which
+ * is unchanged: flag-in-data bottom lines, no fences).  A warp walks its row in groups of KF_GROUP macroblocks:
+ *   1. the group's levels arrive by one bulk asynchronous copy (TMA 1-D + mbarrier), requested a group ahead;
+ *   2. mvg_xf_group() turns them into the residual in place (kernel 1's code);
+ *   3. each macroblock is predicted and reconstructed in the warp's tile (kernel 2's code), its bottom line
+ *      published, and then either stored as a 384-byte tile or converted to RGB24 into a staging area;
+ *   4. RGB mode: the group's 16 rows x (KF_GROUP x 48) bytes leave as 16-byte stores, whole 32-byte sectors. */
+template <int OUT>
+__global__ void __launch_bounds__(KF_WARPS * 32, 1)
+kf_recon(KFParams p)
+{
+    extern __shared__ __align__(128) uint8_t kf_smem[];
+    const int lane = mvg_lane();
+    const unsigned wid = __shfl_sync(MVG_FULL, threadIdx.x >> 5, 0);       /* warp-uniform by construction */
+    /* layout: the tap tables sit on the first 2 KB boundary (so that (mode << 7) can be OR-ed into a lane's
+     * table address), the dequantisation tables behind them; warp records fill the space before, the rest follow */
+    const unsigned base = mvg_smem_u32(kf_smem);
+    const unsigned lut_addr = (base + 2047u) & ~2047u;
+    const unsigned n_before = (lut_addr - base) / (unsigned)sizeof(KFWarpSmem);
+    MvgLuts *luts = reinterpret_cast<MvgLuts *>(kf_smem + (lut_addr - base));
+    MvgXfTables &T = *reinterpret_cast<MvgXfTables *>(kf_smem + (lut_addr - base) + KF_LUT_BYTES);
+    KFWarpSmem &s = *reinterpret_cast<KFWarpSmem *>(
+        wid < n_before ? kf_smem + wid * sizeof(KFWarpSmem)
+                       : kf_smem + (lut_addr - base) + KF_LUT_BYTES + KF_TAB_BYTES + (wid - n_before) * sizeof(KFWarpSmem));
+    for (int i = threadIdx.x; i < (int)(sizeof(MvgLuts) / 16); i += blockDim.x)
+        reinterpret_cast<uint4 *>(luts)[i] = __ldg(reinterpret_cast<const uint4 *>(p.luts) + i);
+    mvg_xf_load_tables(T, p.tab);
+    if (lane == 0) { mvg_mbar_init(&s.mbar[0], 1); mvg_mbar_init(&s.mbar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const int W = p.w_mbs, H = p.h_mbs, n_mb = W * H;
+    const int total = p.n_pics * H;
+    const unsigned epoch = p.epoch;
+    const int n_groups = (W + KF_GROUP - 1) / KF_GROUP;
+
+    /* per-lane constants (as in k2_wavefront) ------------------------------------------ */
+    K2Ctx c;
+    c.lt = s.lt; c.ct = &s.ct[0][0]; c.n8 = s.n8; c.lut8 = reinterpret_cast<const uint8_t *>(&luts->lut8[0][lane]);
+    c.lane = lane;
+    c.sel = p.sel;
+    c.resid = reinterpret_cast<const uint8_t *>(s.tile[0]);
+    {
+        const int half = lane >> 4, pix = lane & 15, px = pix & 3, py = pix >> 2;
+        c.lut4 = lut_addr + (unsigned)lane * 4u;
+        c.h4 = half ? 0u : (unsigned)(4 * MVG_LT_STRIDE - 8);
+        c.s4 = py * MVG_LT_STRIDE + px + (int)c.h4;
+        c.r4odd = pix * 2 + (half ? 64 : 0);
+        c.r4even = pix * 2 + (half ? -64 : 0);
+        c.m4c = half ? 0x10100010u : 0x10001000u;
+        c.m4b = half ? 0x00000100u : 0x00000011u;
+        c.m4cc = half ? 0x00001000u : 0u;
+        const int n = lane < 25 ? lane : 24;
+        if (n < 8)       c.n8tr = (7 - n) * MVG_LT_STRIDE - 1;
+        else if (n == 8) c.n8tr = -MVG_LT_STRIDE - 1;
+        else             c.n8tr = -MVG_LT_STRIDE + (n - 9);
+        c.n8notr = n > 16 ? -MVG_LT_STRIDE + 7 : c.n8tr;
+        const int x8 = ((lane >> 3) & 1) * 4 + (lane & 1) * 2, y8 = (lane >> 4) * 4 + ((lane >> 1) & 3);
+        c.s8 = y8 * MVG_LT_STRIDE + x8;
+        c.fixA = lane == 7 ? 0x10u : lane == 8 ? 0x22u : lane == 9 ? 0x20u : 0u;
+        c.fixB = lane == 7 ? 0x04u : lane == 8 ? 0x05u : lane == 9 ? 0x08u : 0u;
+        c.fixD = lane == 7 ? 0x01u : lane == 9 ? 0x02u : 0u;
+    }
+    /* sample row -1 of the tiles comes from the halo words of the row above: lanes 0..3 luma x = 4*lane,
+     * 4,5 Cb, 6,7 Cr of the macroblock above, lanes 8,9 luma x = 16..23 of the macroblock above-right */
+    uint8_t *const halo_top = lane < 4 ? s.lt + K2_TO(lane * 4, -1)
+                            : lane < 8 ? s.ct[(lane >> 1) & 1] + K2_CO((lane & 1) * 4, -1)
+                                       : s.lt + K2_TO(16 + (lane & 1) * 4, -1);
+    const uint8_t *const halo_bot = lane < 4 ? halo_top + 16 * MVG_LT_STRIDE : halo_top + 8 * MVG_CT_STRIDE;
+    /* row -1, x = 15 (luma) / 7 (chroma) -> x = -1 of the next macroblock: lanes 3, 5, 7 hold the last word of the
+     * luma / Cb / Cr line above; the other lanes copy an unused byte onto itself so that the move needs no predicate */
+    const uint8_t *const cn_src = (lane == 3 || lane == 5 || lane == 7) ? halo_top + 3 : s.lt;
+    uint8_t *const cn_dst = lane == 3 ? s.lt + K2_TO(-1, -1) : lane == 5 ? s.ct[0] + K2_CO(-1, -1)
+                          : lane == 7 ? s.ct[1] + K2_CO(-1, -1) : s.lt;
+    /* what a lane reads of the finished macroblock, and where the last byte of it goes as the left neighbour column
+     * of the next macroblock (x = 15 -> x = -1 luma, x = 7 -> x = -1 chroma):
+     *   tiles: lanes 0..15 one luma row (two 8-byte pieces), 16..23 Cb rows, 24..31 Cr rows (8 bytes)
+     *   RGB:   lane = 2 y + h: luma samples 8h..8h+7 of row y, Cb and Cr samples 4h..4h+3 of row y >> 1; the h = 1
+     *          lanes hold x = 15 of their luma row and x = 7 of their chroma row (even y stores Cb's, odd y Cr's);
+     *          the h = 0 lanes store to two spare bytes of the Intra8x8 line buffer                               */
+    const uint8_t *wo_src, *wo_csrc = nullptr;
+    uint8_t *lc_dst, *lc_cdst = nullptr, *rgb_dst = nullptr;
+    int wo_off = 0;
+    if (OUT == KF_OUT_TILES) {
+        wo_src = lane < 16 ? s.lt + K2_TO(0, lane) : s.ct[(lane >> 3) & 1] + K2_CO(0, lane & 7);
+        wo_off = lane < 16 ? lane * 16 : 256 + (lane - 16) * 8;
+        lc_dst = lane < 16 ? s.lt + K2_TO(-1, lane) : s.ct[(lane >> 3) & 1] + K2_CO(-1, lane & 7);
+    } else {
+        const int y = lane >> 1, h = lane & 1;
+        wo_src = s.lt + K2_TO(8 * h, y);
+        wo_csrc = s.ct[0] + K2_CO(4 * h, y >> 1);
+        lc_dst = h ? s.lt + K2_TO(-1, y) : s.n8 + MVG_N8_BYTES - 1;
+        lc_cdst = h ? s.ct[y & 1] + K2_CO(-1, y >> 1) : s.n8 + MVG_N8_BYTES - 2;
+        rgb_dst = s.u.rgb + y * KF_RGB_STRIDE + 24 * h;
+    }
+    const unsigned lc_sel = lane < 16 ? 7u : 3u;            /* tiles: byte 3 of the second / first 8-byte piece */
+    const int pitch = 48 * W;                               /* bytes per RGB24 picture row */
+
+    MvgSideInfo side;
+    side.init(lane, p.mb_kind, p.i16_mode, p.chroma_mode, p.luma_modes, p.qp_y);
+    unsigned parity = 0;            /* bit b: phase parity of mbar[b] */
+    unsigned it = 0;                /* groups processed by this warp: buffer = it & 1 */
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(p.work, 1);
+        item = __shfl_sync(MVG_FULL, item, 0);
+        if (item >= total) break;
+        const int g0 = item / (p.group * H);
+        const int gsize = min(p.group, p.n_pics - g0 * p.group);
+        const int within = item - g0 * p.group * H;
+        const int row = within / gsize;
+        const int slot = p.first_slot + g0 * p.group + (within - row * gsize);
+        const size_t mb0 = (size_t)slot * n_mb + (size_t)row * W;           /* first macroblock of the row */
+        const int16_t *lv_run = p.coeff + mb0 * 384;                        /* levels of the group requested next */
+
+        /* group 0: levels and side information.  The buffer was last touched by this warp's generic-proxy
+         * accesses (residual of an earlier group): order them before the asynchronous write. */
+        if (lane == 0) {
+            const unsigned bytes = (unsigned)min(KF_GROUP, W) * 768u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mvg_mbar_expect_tx(&s.mbar[it & 1], bytes);
+            mvg_bulk_load(s.tile[it & 1], lv_run, bytes, &s.mbar[it & 1]);
+        }
+        lv_run += KF_GROUP * 384;
+        unsigned nmeta = side.load(lane, (long long)mb0, min(KF_GROUP, W));
+
+        uint8_t *wo_run = OUT == KF_OUT_TILES ? p.tiles + mb0 * 384 + wo_off
+                                              : p.rgb + (size_t)slot * ((size_t)n_mb * 768) + (size_t)row * 16 * pitch;
+        uint2 *hm_run = p.halo + mb0 * 8 + lane;
+        const uint2 *ha_run = p.halo + (mb0 - W) * 8 + lane;           /* group of macroblock mx (at hj == 0) */
+        const bool availB = row > 0, publish = row < H - 1;
+        const int hwords = W * 8;                               /* halo words of a macroblock row */
+        uint2 qa = make_uint2(0, epoch), qb = make_uint2(0, epoch);
+        if (availB) {
+            if (lane < hwords) qb = mvg_ld_relaxed_u64(ha_run);     /* becomes qa at macroblock 0 */
+        }
+        unsigned okA = 0;
+
+        for (int g = 0; g < n_groups; g++, it++) {
+            const int buf = it & 1;
+            const unsigned meta = nmeta;
+            const int nmb = min(KF_GROUP, W - g * KF_GROUP);
+            if (g + 1 < n_groups) {     /* next group: its buffer held the residual of group g - 1, fully consumed */
+                const int nn = min(KF_GROUP, W - (g + 1) * KF_GROUP);
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mvg_mbar_expect_tx(&s.mbar[buf ^ 1], (unsigned)nn * 768u);
+                    mvg_bulk_load(s.tile[buf ^ 1], lv_run, (unsigned)nn * 768u, &s.mbar[buf ^ 1]);
+                }
+                lv_run += KF_GROUP * 384;
+                nmeta = side.load(lane, (long long)mb0 + (g + 1) * KF_GROUP, nn);
+            }
+            int16_t *tile = s.tile[buf];
+            mvg_mbar_wait(&s.mbar[buf], (parity >> buf) & 1u);
+            parity ^= 1u << buf;
+
+            /* ---- levels -> residual, in place (kernel 1's stage) ---- */
+            mvg_xf_group<KF_GROUP>(tile, s.u.x, T, meta, nmb, lane);
+            const uint4 rec = mvg_ctl_from_meta(meta);      /* valid in lane 8 j */
+
+            for (int j = 0; j < nmb; j++) {
+                const int mx = g * KF_GROUP + j, hj = mx & 3;
+                const bool availA = mx > 0, availC = availB && mx < W - 1, availD = availA && availB;
+
+                if (availB) {
+                    if (hj == 0) {              /* group of four macroblocks above: requested a group ago */
+                        qa = qb;
+                        okA = __ballot_sync(MVG_FULL, qa.y == epoch);
+                    }
+                    /* words needed now: the 8 of the macroblock above and, for the up-right neighbour, the first
+                     * two of the next one, which sit in qb when this is the last macroblock of the group */
+                    const unsigned need = availC ? 0x3FFu : 0xFFu;
+                    unsigned have = __funnelshift_r(okA, hj == 3 ? __ballot_sync(MVG_FULL, qb.y == epoch) : 0u, 8 * hj);
+                    if ((have & need) != need) {
+                        /* this row has caught up with the row above: poll, sleeping a fraction of a macroblock time */
+                        unsigned ns = K2_POLL_NS;
+                        do {
+                            __nanosleep(ns);
+                            if (ns < 8 * K2_POLL_NS) ns *= 2;
+                            if ((mx & ~3) * 8 + lane < hwords) qa = mvg_ld_relaxed_u64(ha_run);
+                            if ((mx & ~3) * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(ha_run + 32);
+                            okA = __ballot_sync(MVG_FULL, qa.y == epoch);
+                            have = __funnelshift_r(okA, __ballot_sync(MVG_FULL, qb.y == epoch), 8 * hj);
+                        } while ((have & need) != need);
+                    }
+                    /* sample row -1 of the tiles: lanes 0..7 the macroblock above, lanes 8,9 x = 16..23 */
+                    const unsigned src = (hj == 3 && lane < 2) ? qb.x : qa.x;
+                    const unsigned v = __shfl_sync(MVG_FULL, src, (8 * hj + lane) & 31);
+                    if (lane < 10) *reinterpret_cast<unsigned *>(halo_top) = v;
+                    if (hj == 3) ha_run += 32;
+                }
+                __syncwarp();
+                if (availB && hj == 0) {
+                    /* request the next group of the row above behind everything that reads qb (see k2_wavefront) */
+                    qb = make_uint2(0, epoch);
+                    if (mx * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(ha_run + 32);
+                }
+                c.resid = reinterpret_cast<const uint8_t *>(tile + j * 384);
+                const unsigned cx = __shfl_sync(MVG_FULL, rec.x, 8 * j), cy = __shfl_sync(MVG_FULL, rec.y, 8 * j);
+                const unsigned cz = __shfl_sync(MVG_FULL, rec.z, 8 * j);
+
+                const int kind = cx & 255, i16 = (cx >> 8) & 255, cmode = (cx >> 16) & 255;
+                if (kind == MVG_MB_I16x16)    k2_luma16(c, i16, availA, availB);
+                else if (kind == MVG_MB_I4x4) k2_luma4(c, cy, cz, availA, availB, availC);
+                else                          k2_luma8(c, cy, availA, availB, availC, availD);
+                k2_chroma(c, cmode, availA, availB);
+                __syncwarp();
+
+                /* publish the bottom sample line for the row below */
+                if (publish && lane < 8)
+                    mvg_st_relaxed_u64(hm_run, *reinterpret_cast<const unsigned *>(halo_bot), epoch);
+                hm_run += 8;
+                if (OUT == KF_OUT_TILES) {
+                    /* the macroblock as one 384-byte tile (coalesced) */
+                    const uint2 wa = *reinterpret_cast<const uint2 *>(wo_src);
+                    uint2 wb = make_uint2(0u, 0u);
+                    if (lane < 16) {
+                        wb = *reinterpret_cast<const uint2 *>(wo_src + 8);
+                        *reinterpret_cast<uint4 *>(wo_run) = make_uint4(wa.x, wa.y, wb.x, wb.y);
+                    } else *reinterpret_cast<uint2 *>(wo_run) = wa;
+                    wo_run += 384;
+                    *lc_dst = (uint8_t)__byte_perm(wa.y, wb.y, lc_sel);
+                } else {
+                    /* RGB24 of my 8 pixels (export_utils.c:300-302 on int16 pairs, see k3_rgb_full) into the staging rows */
+                    const uint2 yw = *reinterpret_cast<const uint2 *>(wo_src);
+                    const unsigned cbw = *reinterpret_cast<const unsigned *>(wo_csrc);
+                    const unsigned crw = *reinterpret_cast<const unsigned *>(wo_csrc + MVG_CT_PLANE);
+                    *lc_dst = (uint8_t)(yw.y >> 24);
+                    *lc_cdst = (uint8_t)(((lane & 2) ? crw : cbw) >> 24);
+                    unsigned out[6];
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const unsigned cb2 = k ? mvg_pair_hi(cbw) : mvg_pair_lo(cbw);
+                        const unsigned cr2 = k ? mvg_pair_hi(crw) : mvg_pair_lo(crw);
+                        const unsigned rC = __vsub2(((cr2 * 204u) >> 7) & 0x01ff01ffu, 0x00de00deu);                   /* - 222 */
+                        const unsigned bC = __vsub2(((cb2 * 129u) >> 6) & 0x03ff03ffu, 0x01140114u);                   /* - 276 */
+                        const unsigned gC = __vsub2(__vsub2(0x00870087u, ((cb2 * 25u) >> 6) & 0x00ff00ffu),            /* 135 - .. - .. */
+                                                    ((cr2 * 13u) >> 4) & 0x00ff00ffu);
+                        const unsigned w = k ? yw.y : yw.x;
+                        const unsigned te = ((mvg_pair_even(w) * 149u) >> 7) & 0x01ff01ffu;       /* pixels 4k, 4k+2 */
+                        const unsigned to = ((mvg_pair_odd(w) * 149u) >> 7) & 0x01ff01ffu;        /* pixels 4k+1, 4k+3 */
+                        const unsigned Re = mvg_add_clip8x2(te, rC), Ro = mvg_add_clip8x2(to, rC);
+                        const unsigned Ge = mvg_add_clip8x2(te, gC), Go = mvg_add_clip8x2(to, gC);
+                        const unsigned Be = mvg_add_clip8x2(te, bC), Bo = mvg_add_clip8x2(to, bC);
+                        const unsigned X = __byte_perm(Re, Ge, 0x6240);       /* R0 G0 R2 G2 */
+                        const unsigned Y = __byte_perm(Be, Ro, 0x6240);       /* B0 R1 B2 R3 */
+                        const unsigned Z = __byte_perm(Go, Bo, 0x6240);       /* G1 B1 G3 B3 */
+                        out[3 * k]     = __byte_perm(X, Y, 0x5410);           /* R0 G0 B0 R1 */
+                        out[3 * k + 1] = __byte_perm(Z, X, 0x7610);           /* G1 B1 R2 G2 */
+                        out[3 * k + 2] = __byte_perm(Y, Z, 0x7632);           /* B2 R3 G3 B3 */
+                    }
+                    uint2 *d = reinterpret_cast<uint2 *>(rgb_dst + 48 * j);
+                    d[0] = make_uint2(out[0], out[1]); d[1] = make_uint2(out[2], out[3]); d[2] = make_uint2(out[4], out[5]);
+                }
+                /* next macroblock: row -1, x = 15 / 7 becomes x = -1 */
+                *cn_dst = *cn_src;
+                __syncwarp();
+            }
+            if (OUT == KF_OUT_RGB) {
+                /* the group's 16 rows x (48 nmb) bytes: 16-byte chunks in row-major order over the lanes, so that a
+                 * full group leaves as whole 32-byte sectors (96 bytes per row at a multiple of 96) */
+                const int row_chunks = 3 * KF_GROUP;
+#pragma unroll
+                for (int k = 0; k < (16 * 3 * KF_GROUP + 31) / 32; k++) {
+                    const int ch = lane + 32 * k, r = ch / row_chunks, col = ch - r * row_chunks;
+                    if (ch < 16 * row_chunks && col < 3 * nmb) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(s.u.rgb + r * KF_RGB_STRIDE + col * 16);
+                        *reinterpret_cast<uint4 *>(wo_run + (size_t)r * pitch + col * 16) = v;
+                    }
+                }
+                wo_run += 48 * KF_GROUP;
+                __syncwarp();
+            }
+        }
+    }
+}

@@ -202,24 +202,79 @@ __device__ __forceinline__ void mvg_bulk_store(void *dst, const void *src_smem, 
 }
 __device__ __forceinline__ void mvg_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+/* per-warp scratch of the transform stage for a group of G macroblocks */
+template <int G>
+struct MvgXfScratch {
+    int32_t  dc[G][24];                         /* dequantised DC of Intra16x16 luma / chroma blocks   */
+    int32_t  f1[G][16];                         /* first stage of the luma DC Hadamard                 */
+    int32_t  tr[4][8][9];                       /* 8x8 transpose, padded                               */
+    uint32_t meta[G];                           /* mb_kind | QPY << 8                                  */
+    uint8_t  list4[G * 24 + 8];                 /* 4x4 blocks that need the full transform             */
+    uint8_t  list8[G * 4 + 4];                  /* 8x8 blocks with non-zero levels                     */
+};
+
+/* dequantisation tables in shared memory (filled by mvg_xf_load_tables) */
+struct MvgXfTables {
+    int32_t  ls4[3 * 6 * 16];
+    int32_t  ls4q[3 * 52 * 16];                 /* per qP; << (qP/6-4) folded in when qP >= 24 */
+    int32_t  ls8[6 * 64];
+    __align__(8) uint8_t zz8inv[64];
+    uint8_t  dcsh[52];                          /* 4 - qP / 6 below qP 24, else 0 */
+    uint16_t qpc[2][52];                        /* QPC | QPC / 6 << 8 for Cb, Cr by QPY (derivChromaQP) */
+};
+
 struct K1WarpSmem {
     __align__(128) int16_t tile[2][K1_TILE];    /* levels in, residual out (in place), double buffered */
-    int32_t  dc[K1_GROUP][24];                  /* dequantised DC of Intra16x16 luma / chroma blocks   */
-    int32_t  f1[K1_GROUP][16];                  /* first stage of the luma DC Hadamard                 */
-    int32_t  tr[4][8][9];                       /* 8x8 transpose, padded                               */
-    uint32_t meta[K1_GROUP];                    /* mb_kind | QPY << 8                                  */
-    uint8_t  list4[K1_GROUP * 24 + 8];          /* 4x4 blocks that need the full transform             */
-    uint8_t  list8[K1_GROUP * 4 + 4];           /* 8x8 blocks with non-zero levels                     */
+    MvgXfScratch<K1_GROUP> x;
     __align__(8) uint64_t mbar[2];
 };
 
 /* position (bx,by) -> luma4x4BlkIdx (h264_spatial.c:210-225 inverted) */
 __device__ __forceinline__ int mvg_blk_of(int bx, int by) { return (bx & 1) | ((by & 1) << 1) | ((bx >> 1) << 2) | ((by >> 1) << 3); }
 
-/* One warp transforms K1_GROUP macroblocks per iteration, in place in shared memory:
- *   - the 3 KB of levels arrive with ONE bulk asynchronous copy (cp.async.bulk + mbarrier), the
- *     next group's copy is in flight while this one is processed, and the residual leaves with
- *     one bulk store -- no per-thread global loads/stores for the payload;
+/* cooperative fill of the dequantisation tables (all threads of the CTA; the caller synchronises) */
+__device__ __forceinline__ void mvg_xf_load_tables(MvgXfTables &t, const MvgTables *tab)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < 3 * 6 * 16; i += nt) t.ls4[i] = (&tab->ls4[0][0][0])[i];
+    for (int i = tid; i < 3 * 52 * 16; i += nt) t.ls4q[i] = (&tab->ls4q[0][0][0])[i];
+    for (int i = tid; i < 6 * 64; i += nt) t.ls8[i] = (&tab->ls8[0][0])[i];
+    for (int i = tid; i < 64; i += nt) t.zz8inv[i] = tab->zz8inv[i];
+    for (int i = tid; i < 52; i += nt) t.dcsh[i] = (uint8_t)(i > 23 ? 0 : 4 - i / 6);
+    for (int i = tid; i < 104; i += nt) {
+        const int pl = i >= 52, qpc = mvg_chroma_qp(i - 52 * pl, pl ? tab->cr_qp_offset : tab->cb_qp_offset);
+        t.qpc[pl][i - 52 * pl] = (uint16_t)(qpc | ((qpc / 6) << 8));
+    }
+}
+
+/* Side information of a group of G <= 4 macroblocks, one 32-bit word per lane: lane = 8*j + t for macroblock j;
+ * t = 0..3 luma modes 4t..4t+3, t = 4 mb_kind, 5 QPY, 6 Intra16x16PredMode, 7 intra_chroma_pred_mode.
+ * `first` = index of the group's first macroblock, `n` = macroblocks in the group. */
+struct MvgSideInfo {
+    const uint8_t *src;         /* this lane's array, at macroblock 0 */
+    int stride;                 /* bytes per macroblock in that array */
+    __device__ __forceinline__ void init(int lane, const uint8_t *mb_kind, const uint8_t *i16_mode, const uint8_t *chroma_mode,
+                                         const uint8_t *luma_modes, const int8_t *qp_y)
+    {
+        const int mt = lane & 7;
+        src = mt < 4 ? luma_modes + 4 * mt : mt == 4 ? mb_kind : mt == 5 ? reinterpret_cast<const uint8_t *>(qp_y)
+                     : mt == 6 ? i16_mode : chroma_mode;
+        stride = mt < 4 ? 16 : 1;
+    }
+    __device__ __forceinline__ unsigned load(int lane, long long first, int n) const
+    {
+        unsigned v = 0u;
+        if ((lane >> 3) < n) {
+            const uint8_t *q = src + (first + (lane >> 3)) * stride;
+            if ((lane & 7) < 4) v = __ldg(reinterpret_cast<const unsigned *>(q));
+            else v = (unsigned)__ldg(q);
+        }
+        return v;
+    }
+};
+
+/* The transform stage for a group of G macroblocks whose levels sit in `tile` (G x 384 int16, zig-zag order as in
+ * mvgpu.h); the residual replaces them in place, block-major (24 blocks x 16 int16 per macroblock, see MvgMbCtl):
  *   - Intra16x16 luma DC (4x4 Hadamard, h264_transform.c:756-812) and chroma DC (2x2, :827-936)
  *     are done first, separably, a few lanes per macroblock;
  *   - every 4x4 block is classified: all-zero (nothing to do), DC-only (every residual sample is
@@ -228,28 +283,212 @@ __device__ __forceinline__ int mvg_blk_of(int bx, int by) { return (bx & 1) | ((
  *     (h264_transform.c:1100-1191) 32 at a time, one block per lane, entirely in registers;
  *   - non-zero 8x8 blocks (Intra8x8 luma, quant8x8/idct8x8 :1256-1383) are compacted the same
  *     way and transformed 4 per pass, 8 lanes per block, transposed through shared memory.
- * Residual layout out: per macroblock 24 blocks x 16 int16, block-major (see MvgMbCtl). */
+ * `meta` = the group's side information (MvgSideInfo), nmb = macroblocks present (1..G).  Warp-collective. */
+template <int G>
+__device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, const MvgXfTables &T, unsigned meta, int nmb, int lane)
+{
+    const int mj = lane >> 3, mt = lane & 7;
+    /* per-lane view of "my" macroblock j = lane >> 3 */
+    const int kind_j = (int)__shfl_sync(MVG_FULL, meta, (lane & ~7) + 4);
+    /* QPY outside 0..51 cannot come out of a conforming parse; clamp so that a bad batch cannot index past the tables */
+    const int qp_j = min(max((int)(signed char)__shfl_sync(MVG_FULL, meta, (lane & ~7) + 5), 0), 51);
+    if (mt == 0 && mj < G) s.meta[mj] = (unsigned)kind_j | ((unsigned)(qp_j & 255) << 8);
+
+    /* ---------------- DC transforms ---------------- */
+    if (mj < nmb) {
+        const int16_t *cf = tile + mj * 384;
+        if (kind_j == MVG_MB_I16x16 && mt < 4) {         /* row mt of c: t = c * H */
+            const int a = cf[mvg_blk_of(0, mt) * 16], b = cf[mvg_blk_of(1, mt) * 16];
+            const int c = cf[mvg_blk_of(2, mt) * 16], d = cf[mvg_blk_of(3, mt) * 16];
+            int32_t *f1 = s.f1[mj] + mt * 4;
+            f1[0] = a + b + c + d; f1[1] = a + b - c - d; f1[2] = a - b - c + d; f1[3] = a - b + c - d;
+        } else if (mt == 4 || mt == 5) {                 /* chroma plane mt-4: f = A c A, then scale */
+            const int pl = mt - 4;
+            const int16_t *cc = cf + 256 + pl * 64;
+            const int c00 = cc[0], c01 = cc[16], c10 = cc[32], c11 = cc[48];
+            const int qe = T.qpc[pl][qp_j], qpc = qe & 255, qd = qe >> 8;
+            const int ls00 = T.ls4[((pl + 1) * 6 + (qpc - 6 * qd)) * 16];
+            const int f[4] = {c00 + c01 + c10 + c11, c00 - c01 + c10 - c11, c00 + c01 - c10 - c11, c00 - c01 - c10 + c11};
+#pragma unroll
+            for (int k = 0; k < 4; k++) s.dc[mj][16 + pl * 4 + k] = (int)((unsigned)(f[k] * ls00) << qd) >> 5;
+        }
+    }
+    __syncwarp();
+    if (mj < nmb && kind_j == MVG_MB_I16x16 && mt < 4) { /* column mt: f = H * t, then scale */
+        const int32_t *f1 = s.f1[mj];
+        const int a = f1[mt], b = f1[4 + mt], c = f1[8 + mt], d = f1[12 + mt];
+        const int f[4] = {a + b + c + d, a + b - c - d, a - b - c + d, a - b + c - d};
+        const int qd = qp_j / 6, ls00 = T.ls4[(qp_j - 6 * qd) * 16];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int t = f[i] * ls00;
+            s.dc[mj][mvg_blk_of(mt, i)] = (qp_j >= 36) ? (int)((unsigned)t << (qd - 6)) : ((t + (1 << (5 - qd))) >> (6 - qd));
+        }
+    }
+    __syncwarp();
+
+    /* ---------------- classify the 4x4 blocks, compact the general ones ---------------- */
+    int n4 = 0, n8 = 0;
+#pragma unroll
+    for (int r = 0; r < (G * 24 + 31) / 32; r++) {
+        const int u = lane + 32 * r, j0 = u / 24, b = u - 24 * j0;
+        /* straight-line code: every lane loads a block (its own, or block b of macroblock 0 beyond the last
+         * macroblock of a short group) and derives all three answers; only the DC-only rewrite is conditional */
+        const bool live = j0 < nmb;
+        const int j = live ? j0 : 0;
+        const unsigned mw = s.meta[j];
+        const int kind = mw & 255, qp = (signed char)(mw >> 8);
+        const bool is8 = kind == MVG_MB_I8x8 && b < 16;
+        uint4 *blk = reinterpret_cast<uint4 *>(tile + j * 384 + b * 16);
+        const uint4 w0 = blk[0], w1 = blk[1];
+        const unsigned rest = (w0.x & 0xffff0000u) | w0.y | w0.z | w0.w | w1.x | w1.y | w1.z | w1.w;
+        const int dcraw = (short)(w0.x & 0xffff);
+        const bool nz8q = live && is8 && (rest | (w0.x & 0xffffu)) != 0;
+        const bool general = live && !is8 && rest != 0;
+        {
+            /* DC only: every residual sample is (d00 + 32) >> 6.  d00 = c00 (already dequantised by the DC
+             * transforms, h264_transform.c:1126-1129) for chroma and Intra16x16, else quant4x4 of the level:
+             * (c * LS + rnd) >> sh with sh = 0 from qP 24 on (the left shift is folded into ls4q) */
+            const bool has_dc = b >= 16 || kind == MVG_MB_I16x16;
+            const int sh = T.dcsh[qp];
+            const int plain = (dcraw * T.ls4q[qp * 16] + ((1 << sh) >> 1)) >> sh;
+            const int d = has_dc ? s.dc[j][b] : plain;
+            const int rv = min(max((d + 32) >> 6, -512), 511);
+            if (live && !is8 && rest == 0 && (rv != 0 || dcraw != 0)) {
+                const unsigned pk = (unsigned)(rv & 0xffff) * 0x10001u;
+                blk[0] = make_uint4(pk, pk, pk, pk); blk[1] = make_uint4(pk, pk, pk, pk);
+            }
+        }
+        const unsigned gb = __ballot_sync(MVG_FULL, general);
+        if (general) s.list4[n4 + __popc(gb & ((1u << lane) - 1))] = (uint8_t)u;
+        n4 += __popc(gb);
+        /* Intra8x8: slots 4*b8..4*b8+3 are the four quarters of 8x8 block b8 (aligned lane quads) */
+        const unsigned qb = __ballot_sync(MVG_FULL, nz8q);
+        const bool any8 = live && is8 && ((qb >> (lane & ~3)) & 0xFu) != 0;
+        const bool lead8 = any8 && (lane & 3) == 0;
+        const unsigned lb = __ballot_sync(MVG_FULL, lead8);
+        if (lead8) s.list8[n8 + __popc(lb & ((1u << lane) - 1))] = (uint8_t)(j * 4 + (b >> 2));
+        n8 += __popc(lb);
+    }
+    __syncwarp();
+
+    /* ---------------- general 4x4 blocks, 32 per pass ---------------- */
+    for (int base = 0; base < n4; base += 32) {
+        if (base + lane < n4) {
+            const int u = s.list4[base + lane], j = u / 24, b = u - 24 * j;
+            const unsigned mw = s.meta[j];
+            const int kind = mw & 255, qp = (signed char)(mw >> 8);
+            const int comp = b < 16 ? 0 : (b < 20 ? 1 : 2);
+            const int qpb = comp ? (T.qpc[comp - 1][qp] & 255) : qp;
+            uint4 *blk = reinterpret_cast<uint4 *>(tile + j * 384 + b * 16);
+            const uint4 a = blk[0], bb = blk[1];
+            int c[16];                      /* zig-zag k -> (row,col): utils.h:64 / spec Table 8-13 */
+            c[0] = (short)(a.x & 0xffff); c[1] = (int)a.x >> 16; c[4] = (short)(a.y & 0xffff); c[8] = (int)a.y >> 16;
+            c[5] = (short)(a.z & 0xffff); c[2] = (int)a.z >> 16; c[3] = (short)(a.w & 0xffff); c[6] = (int)a.w >> 16;
+            c[9] = (short)(bb.x & 0xffff); c[12] = (int)bb.x >> 16; c[13] = (short)(bb.y & 0xffff); c[10] = (int)bb.y >> 16;
+            c[7] = (short)(bb.z & 0xffff); c[11] = (int)bb.z >> 16; c[14] = (short)(bb.w & 0xffff); c[15] = (int)bb.w >> 16;
+            const bool keep_dc = comp != 0 || kind == MVG_MB_I16x16;
+            const int dc_in = keep_dc ? s.dc[j][b] : 0;
+            /* quant4x4, h264_transform.c:1100-1134 */
+            const int4 *lq = reinterpret_cast<const int4 *>(T.ls4q + (comp * 52 + qpb) * 16);
+            const int4 l0 = lq[0], l1 = lq[1], l2 = lq[2], l3 = lq[3];
+            const int ls[16] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w, l2.x, l2.y, l2.z, l2.w, l3.x, l3.y, l3.z, l3.w};
+            if (qpb > 23) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) c[k] = c[k] * ls[k];
+            } else {
+                const int qd = qpb / 6, rnd = 1 << (3 - qd), sh = 4 - qd;
+#pragma unroll
+                for (int k = 0; k < 16; k++) c[k] = (c[k] * ls[k] + rnd) >> sh;
+            }
+            if (keep_dc) c[0] = dc_in;
+            c[0] += 32;                     /* rounding of the final >> 6 (h264_transform.c:1190) */
+#pragma unroll
+            for (int i = 0; i < 4; i++)     /* idct4x4: rows, then columns */
+                mvg_bfly4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3], c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                mvg_bfly4(c[q], c[4 + q], c[8 + q], c[12 + q], c[q], c[4 + q], c[8 + q], c[12 + q]);
+            uint4 o0, o1;
+            o0.x = mvg_pack_shr6(c[1], c[0]);   o0.y = mvg_pack_shr6(c[3], c[2]);
+            o0.z = mvg_pack_shr6(c[5], c[4]);   o0.w = mvg_pack_shr6(c[7], c[6]);
+            o1.x = mvg_pack_shr6(c[9], c[8]);   o1.y = mvg_pack_shr6(c[11], c[10]);
+            o1.z = mvg_pack_shr6(c[13], c[12]); o1.w = mvg_pack_shr6(c[15], c[14]);
+            blk[0] = o0; blk[1] = o1;
+        }
+    }
+
+    /* ---------------- non-zero 8x8 blocks, 4 per pass ---------------- */
+    for (int base = 0; base < n8; base += 4) {
+        const int slot = base + (lane >> 3), row = lane & 7;
+        const bool act = slot < n8;
+        int v[8];
+        int16_t *o8 = tile;
+        if (act) {
+            const int id = s.list8[slot], j = id >> 2, b8 = id & 3;
+            const int qp = (signed char)(s.meta[j] >> 8);
+            const int qd8 = qp / 6;
+            const int32_t *l8 = T.ls8 + (qp - 6 * qd8) * 64 + row * 8;
+            const int16_t *in = tile + j * 384 + b8 * 64;
+            const uint2 zz = *reinterpret_cast<const uint2 *>(T.zz8inv + row * 8);   /* scan positions of my row */
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const unsigned k = ((q < 4 ? zz.x : zz.y) >> (8 * (q & 3))) & 255u;
+                v[q] = (int)in[k] * l8[q];                                  /* quant8x8, h264_transform.c:1256-1284 */
+            }
+            if (qp > 35) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = (int)((unsigned)v[q] << (qd8 - 6));
+            } else {
+                const int rnd = 1 << (5 - qd8), sh = 6 - qd8;
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = (v[q] + rnd) >> sh;
+            }
+            if (row == 0) v[0] += 32;                                       /* rounding of the final >> 6 (:1382) */
+            mvg_idct8_1d(v);                                                /* row pass */
+#pragma unroll
+            for (int q = 0; q < 8; q++) s.tr[lane >> 3][row][q] = v[q];
+            o8 = tile + j * 384 + (b8 * 4 + (row >> 2)) * 16 + (row & 3);
+        }
+        __syncwarp();
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = s.tr[lane >> 3][i][row];     /* this lane now owns column `row` */
+            mvg_idct8_1d(v);                                                /* column pass */
+#pragma unroll
+            for (int i = 0; i < 8; i++) o8[(i >> 2) * 32 + (i & 3) * 4] = (int16_t)min(max(v[i] >> 6, -512), 511);
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+}
+
+/* the 16-byte control record of a macroblock (MvgMbCtl) from the side-information words of its lanes 8j..8j+7;
+ * valid in lane 8j */
+__device__ __forceinline__ uint4 mvg_ctl_from_meta(unsigned meta)
+{
+    /* 4 mode bytes -> 4 nibbles; lane 8j collects its macroblock's record */
+    const unsigned nib = (meta & 0xF) | ((meta >> 4) & 0xF0) | ((meta >> 8) & 0xF00) | ((meta >> 12) & 0xF000);
+    const unsigned n1 = __shfl_down_sync(MVG_FULL, nib, 1), n2 = __shfl_down_sync(MVG_FULL, nib, 2);
+    const unsigned n3 = __shfl_down_sync(MVG_FULL, nib, 3);
+    const unsigned k4 = __shfl_down_sync(MVG_FULL, meta, 4), k6 = __shfl_down_sync(MVG_FULL, meta, 6);
+    const unsigned k7 = __shfl_down_sync(MVG_FULL, meta, 7);
+    return make_uint4((k4 & 255) | ((k6 & 255) << 8) | ((k7 & 255) << 16), nib | (n2 << 16),
+                      __funnelshift_l(n1 | (n3 << 16), n1 | (n3 << 16), 8), 0u);
+}
+
+/* Kernel 1 (kept as the verification tap behind mvg_download_residual() and as the first stage of the split
+ * pipeline): one warp transforms K1_GROUP macroblocks per iteration, in place in shared memory.  The 3 KB of
+ * levels arrive with ONE bulk asynchronous copy (cp.async.bulk + mbarrier), the next group's copy is in flight
+ * while this one is processed, and the residual leaves with one bulk store -- no per-thread global loads/stores
+ * for the payload.  Residual layout out: per macroblock 24 blocks x 16 int16, block-major (see MvgMbCtl). */
 __global__ void __launch_bounds__(K1_WARPS * 32, 2)
 k1_dequant_idct(K1Params p)
 {
-    __shared__ int32_t s_ls4[3 * 6 * 16];
-    __shared__ int32_t s_ls4q[3 * 52 * 16];                     /* per qP; << (qP/6-4) folded in when qP >= 24 */
-    __shared__ int32_t s_ls8[6 * 64];
-    __shared__ __align__(8) uint8_t s_zz8inv[64];
-    __shared__ uint8_t s_dcsh[52];                              /* 4 - qP / 6 below qP 24, else 0 */
-    __shared__ uint16_t s_qpc[2][52];                           /* QPC | QPC / 6 << 8 for Cb, Cr by QPY (derivChromaQP) */
+    __shared__ MvgXfTables s_tab;
     extern __shared__ __align__(128) uint8_t k1_smem[];         /* K1WarpSmem x K1_WARPS (dynamic: above the 48 KB static limit) */
     K1WarpSmem *s_warp = reinterpret_cast<K1WarpSmem *>(k1_smem);
-
-    for (int i = threadIdx.x; i < 3 * 6 * 16; i += blockDim.x) s_ls4[i] = (&p.tab->ls4[0][0][0])[i];
-    for (int i = threadIdx.x; i < 3 * 52 * 16; i += blockDim.x) s_ls4q[i] = (&p.tab->ls4q[0][0][0])[i];
-    for (int i = threadIdx.x; i < 6 * 64; i += blockDim.x) s_ls8[i] = (&p.tab->ls8[0][0])[i];
-    if (threadIdx.x < 64) s_zz8inv[threadIdx.x] = p.tab->zz8inv[threadIdx.x];
-    if (threadIdx.x >= 128 && threadIdx.x < 180) s_dcsh[threadIdx.x - 128] = (uint8_t)(threadIdx.x - 128 > 23 ? 0 : 4 - (threadIdx.x - 128) / 6);
-    if (threadIdx.x < 104) {
-        const int pl = threadIdx.x >= 52, qpc = mvg_chroma_qp(threadIdx.x - 52 * pl, pl ? p.tab->cr_qp_offset : p.tab->cb_qp_offset);
-        s_qpc[pl][threadIdx.x - 52 * pl] = (uint16_t)(qpc | ((qpc / 6) << 8));
-    }
+    mvg_xf_load_tables(s_tab, p.tab);
 
     const int lane = mvg_lane();
     K1WarpSmem &s = s_warp[threadIdx.x >> 5];
@@ -262,23 +501,8 @@ k1_dequant_idct(K1Params p)
     const long long stride = (long long)gridDim.x * K1_WARPS;
     long long g = (long long)blockIdx.x * K1_WARPS + (threadIdx.x >> 5);
 
-    /* side information of a group, one 32-bit word per lane: lane = 8*j + t for macroblock j;
-     * t = 0..3 luma modes 4t..4t+3, t = 4 mb_kind, 5 QPY, 6 Intra16x16PredMode, 7 intra_chroma_pred_mode */
-    const int mj = lane >> 3, mt = lane & 7;
-    /* per-lane source: a word of luma_modes (16 bytes per macroblock) or a byte of one of the four byte arrays */
-    const uint8_t *const meta_src = mt < 4 ? p.luma_modes + 4 * mt : mt == 4 ? p.mb_kind
-                                  : mt == 5 ? reinterpret_cast<const uint8_t *>(p.qp_y) : mt == 6 ? p.i16_mode : p.chroma_mode;
-    const int meta_stride = mt < 4 ? 16 : 1;
-    auto load_meta = [&](long long grp) -> unsigned {
-        const long long mb = grp * K1_GROUP + mj;
-        unsigned v = 0u;
-        if (mb < p.n_mbs) {
-            const uint8_t *src = meta_src + mb * meta_stride;
-            if (mt < 4) v = __ldg(reinterpret_cast<const unsigned *>(src));
-            else v = (unsigned)__ldg(src);
-        }
-        return v;
-    };
+    MvgSideInfo side;
+    side.init(lane, p.mb_kind, p.i16_mode, p.chroma_mode, p.luma_modes, p.qp_y);
     auto issue_load = [&](int buf, long long grp) {
         const long long mb0 = grp * K1_GROUP;
         const unsigned bytes = (unsigned)min((long long)K1_GROUP, p.n_mbs - mb0) * 768u;
@@ -289,7 +513,7 @@ k1_dequant_idct(K1Params p)
     unsigned nmeta = 0;
     if (g < n_groups) {
         if (lane == 0) issue_load(0, g);
-        nmeta = load_meta(g);
+        nmeta = side.load(lane, g * K1_GROUP, (int)min((long long)K1_GROUP, p.n_mbs - g * K1_GROUP));
     }
     unsigned parity = 0;            /* bit b: phase parity of mbar[b] */
 
@@ -300,202 +524,23 @@ k1_dequant_idct(K1Params p)
             const long long gn = g + stride;
             if (gn < n_groups) {
                 if (lane == 0) { mvg_bulk_wait_read(); issue_load(buf ^ 1, gn); }
-                nmeta = load_meta(gn);
+                nmeta = side.load(lane, gn * K1_GROUP, (int)min((long long)K1_GROUP, p.n_mbs - gn * K1_GROUP));
             }
         }
         const long long mb0 = g * K1_GROUP;
         const int nmb = (int)min((long long)K1_GROUP, p.n_mbs - mb0);
         int16_t *tile = s.tile[buf];
 
-        /* per-lane view of "my" macroblock j = lane >> 3 */
-        const int kind_j = (int)__shfl_sync(MVG_FULL, meta, (lane & ~7) + 4);
-        /* QPY outside 0..51 cannot come out of a conforming parse; clamp so that a bad batch cannot index past the tables */
-        const int qp_j = min(max((int)(signed char)__shfl_sync(MVG_FULL, meta, (lane & ~7) + 5), 0), 51);
-        if (mt == 0) s.meta[mj] = (unsigned)kind_j | ((unsigned)(qp_j & 255) << 8);
-
         mvg_mbar_wait(&s.mbar[buf], (parity >> buf) & 1u);
         parity ^= 1u << buf;
 
-        /* ---------------- DC transforms ---------------- */
-        if (mj < nmb) {
-            const int16_t *cf = tile + mj * 384;
-            if (kind_j == MVG_MB_I16x16 && mt < 4) {         /* row mt of c: t = c * H */
-                const int a = cf[mvg_blk_of(0, mt) * 16], b = cf[mvg_blk_of(1, mt) * 16];
-                const int c = cf[mvg_blk_of(2, mt) * 16], d = cf[mvg_blk_of(3, mt) * 16];
-                int32_t *f1 = s.f1[mj] + mt * 4;
-                f1[0] = a + b + c + d; f1[1] = a + b - c - d; f1[2] = a - b - c + d; f1[3] = a - b + c - d;
-            } else if (mt == 4 || mt == 5) {                 /* chroma plane mt-4: f = A c A, then scale */
-                const int pl = mt - 4;
-                const int16_t *cc = cf + 256 + pl * 64;
-                const int c00 = cc[0], c01 = cc[16], c10 = cc[32], c11 = cc[48];
-                const int qe = s_qpc[pl][qp_j], qpc = qe & 255, qd = qe >> 8;
-                const int ls00 = s_ls4[((pl + 1) * 6 + (qpc - 6 * qd)) * 16];
-                const int f[4] = {c00 + c01 + c10 + c11, c00 - c01 + c10 - c11, c00 + c01 - c10 - c11, c00 - c01 - c10 + c11};
-#pragma unroll
-                for (int k = 0; k < 4; k++) s.dc[mj][16 + pl * 4 + k] = (int)((unsigned)(f[k] * ls00) << qd) >> 5;
-            }
-        }
-        __syncwarp();
-        if (mj < nmb && kind_j == MVG_MB_I16x16 && mt < 4) { /* column mt: f = H * t, then scale */
-            const int32_t *f1 = s.f1[mj];
-            const int a = f1[mt], b = f1[4 + mt], c = f1[8 + mt], d = f1[12 + mt];
-            const int f[4] = {a + b + c + d, a + b - c - d, a - b - c + d, a - b + c - d};
-            const int qd = qp_j / 6, ls00 = s_ls4[(qp_j - 6 * qd) * 16];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int t = f[i] * ls00;
-                s.dc[mj][mvg_blk_of(mt, i)] = (qp_j >= 36) ? (int)((unsigned)t << (qd - 6)) : ((t + (1 << (5 - qd))) >> (6 - qd));
-            }
-        }
-        __syncwarp();
-
-        /* ---------------- classify the 4x4 blocks, compact the general ones ---------------- */
-        int n4 = 0, n8 = 0;
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            const int u = lane + 32 * r, j = u / 24, b = u - 24 * j;
-            /* straight-line code: every lane loads its block (in bounds also beyond the last macroblock of a short
-             * group) and derives all three answers; only the DC-only rewrite is conditional */
-            const bool live = j < nmb;
-            const unsigned mw = s.meta[j];
-            const int kind = mw & 255, qp = (signed char)(mw >> 8);
-            const bool is8 = kind == MVG_MB_I8x8 && b < 16;
-            uint4 *blk = reinterpret_cast<uint4 *>(tile + j * 384 + b * 16);
-            const uint4 w0 = blk[0], w1 = blk[1];
-            const unsigned rest = (w0.x & 0xffff0000u) | w0.y | w0.z | w0.w | w1.x | w1.y | w1.z | w1.w;
-            const int dcraw = (short)(w0.x & 0xffff);
-            const bool nz8q = live && is8 && (rest | (w0.x & 0xffffu)) != 0;
-            const bool general = live && !is8 && rest != 0;
-            {
-                /* DC only: every residual sample is (d00 + 32) >> 6.  d00 = c00 (already dequantised by the DC
-                 * transforms, h264_transform.c:1126-1129) for chroma and Intra16x16, else quant4x4 of the level:
-                 * (c * LS + rnd) >> sh with sh = 0 from qP 24 on (the left shift is folded into s_ls4q) */
-                const bool has_dc = b >= 16 || kind == MVG_MB_I16x16;
-                const int sh = s_dcsh[qp];
-                const int plain = (dcraw * s_ls4q[qp * 16] + ((1 << sh) >> 1)) >> sh;
-                const int d = has_dc ? s.dc[j][b] : plain;
-                const int rv = min(max((d + 32) >> 6, -512), 511);
-                if (live && !is8 && rest == 0 && (rv != 0 || dcraw != 0)) {
-                    const unsigned pk = (unsigned)(rv & 0xffff) * 0x10001u;
-                    blk[0] = make_uint4(pk, pk, pk, pk); blk[1] = make_uint4(pk, pk, pk, pk);
-                }
-            }
-            const unsigned gb = __ballot_sync(MVG_FULL, general);
-            if (general) s.list4[n4 + __popc(gb & ((1u << lane) - 1))] = (uint8_t)u;
-            n4 += __popc(gb);
-            /* Intra8x8: slots 4*b8..4*b8+3 are the four quarters of 8x8 block b8 (aligned lane quads) */
-            const unsigned qb = __ballot_sync(MVG_FULL, nz8q);
-            const bool any8 = is8 && ((qb >> (lane & ~3)) & 0xFu) != 0;
-            const bool lead8 = any8 && (lane & 3) == 0;
-            const unsigned lb = __ballot_sync(MVG_FULL, lead8);
-            if (lead8) s.list8[n8 + __popc(lb & ((1u << lane) - 1))] = (uint8_t)(j * 4 + (b >> 2));
-            n8 += __popc(lb);
-        }
-        __syncwarp();
-
-        /* ---------------- general 4x4 blocks, 32 per pass ---------------- */
-        for (int base = 0; base < n4; base += 32) {
-            if (base + lane < n4) {
-                const int u = s.list4[base + lane], j = u / 24, b = u - 24 * j;
-                const unsigned mw = s.meta[j];
-                const int kind = mw & 255, qp = (signed char)(mw >> 8);
-                const int comp = b < 16 ? 0 : (b < 20 ? 1 : 2);
-                const int qpb = comp ? (s_qpc[comp - 1][qp] & 255) : qp;
-                uint4 *blk = reinterpret_cast<uint4 *>(tile + j * 384 + b * 16);
-                const uint4 a = blk[0], bb = blk[1];
-                int c[16];                      /* zig-zag k -> (row,col): utils.h:64 / spec Table 8-13 */
-                c[0] = (short)(a.x & 0xffff); c[1] = (int)a.x >> 16; c[4] = (short)(a.y & 0xffff); c[8] = (int)a.y >> 16;
-                c[5] = (short)(a.z & 0xffff); c[2] = (int)a.z >> 16; c[3] = (short)(a.w & 0xffff); c[6] = (int)a.w >> 16;
-                c[9] = (short)(bb.x & 0xffff); c[12] = (int)bb.x >> 16; c[13] = (short)(bb.y & 0xffff); c[10] = (int)bb.y >> 16;
-                c[7] = (short)(bb.z & 0xffff); c[11] = (int)bb.z >> 16; c[14] = (short)(bb.w & 0xffff); c[15] = (int)bb.w >> 16;
-                const bool keep_dc = comp != 0 || kind == MVG_MB_I16x16;
-                const int dc_in = keep_dc ? s.dc[j][b] : 0;
-                /* quant4x4, h264_transform.c:1100-1134 */
-                const int4 *lq = reinterpret_cast<const int4 *>(s_ls4q + (comp * 52 + qpb) * 16);
-                const int4 l0 = lq[0], l1 = lq[1], l2 = lq[2], l3 = lq[3];
-                const int ls[16] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w, l2.x, l2.y, l2.z, l2.w, l3.x, l3.y, l3.z, l3.w};
-                if (qpb > 23) {
-#pragma unroll
-                    for (int k = 0; k < 16; k++) c[k] = c[k] * ls[k];
-                } else {
-                    const int qd = qpb / 6, rnd = 1 << (3 - qd), sh = 4 - qd;
-#pragma unroll
-                    for (int k = 0; k < 16; k++) c[k] = (c[k] * ls[k] + rnd) >> sh;
-                }
-                if (keep_dc) c[0] = dc_in;
-                c[0] += 32;                     /* rounding of the final >> 6 (h264_transform.c:1190) */
-#pragma unroll
-                for (int i = 0; i < 4; i++)     /* idct4x4: rows, then columns */
-                    mvg_bfly4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3], c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    mvg_bfly4(c[q], c[4 + q], c[8 + q], c[12 + q], c[q], c[4 + q], c[8 + q], c[12 + q]);
-                uint4 o0, o1;
-                o0.x = mvg_pack_shr6(c[1], c[0]);   o0.y = mvg_pack_shr6(c[3], c[2]);
-                o0.z = mvg_pack_shr6(c[5], c[4]);   o0.w = mvg_pack_shr6(c[7], c[6]);
-                o1.x = mvg_pack_shr6(c[9], c[8]);   o1.y = mvg_pack_shr6(c[11], c[10]);
-                o1.z = mvg_pack_shr6(c[13], c[12]); o1.w = mvg_pack_shr6(c[15], c[14]);
-                blk[0] = o0; blk[1] = o1;
-            }
-        }
-
-        /* ---------------- non-zero 8x8 blocks, 4 per pass ---------------- */
-        for (int base = 0; base < n8; base += 4) {
-            const int slot = base + (lane >> 3), row = lane & 7;
-            const bool act = slot < n8;
-            int v[8];
-            int16_t *o8 = tile;
-            if (act) {
-                const int id = s.list8[slot], j = id >> 2, b8 = id & 3;
-                const int qp = (signed char)(s.meta[j] >> 8);
-                const int qd8 = qp / 6;
-                const int32_t *l8 = s_ls8 + (qp - 6 * qd8) * 64 + row * 8;
-                const int16_t *in = tile + j * 384 + b8 * 64;
-                const uint2 zz = *reinterpret_cast<const uint2 *>(s_zz8inv + row * 8);   /* scan positions of my row */
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const unsigned k = ((q < 4 ? zz.x : zz.y) >> (8 * (q & 3))) & 255u;
-                    v[q] = (int)in[k] * l8[q];                                  /* quant8x8, h264_transform.c:1256-1284 */
-                }
-                if (qp > 35) {
-#pragma unroll
-                    for (int q = 0; q < 8; q++) v[q] = (int)((unsigned)v[q] << (qd8 - 6));
-                } else {
-                    const int rnd = 1 << (5 - qd8), sh = 6 - qd8;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) v[q] = (v[q] + rnd) >> sh;
-                }
-                if (row == 0) v[0] += 32;                                       /* rounding of the final >> 6 (:1382) */
-                mvg_idct8_1d(v);                                                /* row pass */
-#pragma unroll
-                for (int q = 0; q < 8; q++) s.tr[lane >> 3][row][q] = v[q];
-                o8 = tile + j * 384 + (b8 * 4 + (row >> 2)) * 16 + (row & 3);
-            }
-            __syncwarp();
-            if (act) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = s.tr[lane >> 3][i][row];     /* this lane now owns column `row` */
-                mvg_idct8_1d(v);                                                /* column pass */
-#pragma unroll
-                for (int i = 0; i < 8; i++) o8[(i >> 2) * 32 + (i & 3) * 4] = (int16_t)min(max(v[i] >> 6, -512), 511);
-            }
-            __syncwarp();
-        }
-        __syncwarp();
+        mvg_xf_group<K1_GROUP>(tile, s.x, s_tab, meta, nmb, lane);
 
         /* ---------------- residual out (one bulk store) + control records ---------------- */
         if (lane == 0) mvg_bulk_store(p.resid + mb0 * 384, tile, (unsigned)nmb * 768u);
         {
-            /* 4 mode bytes -> 4 nibbles; lane 8j collects its macroblock's record */
-            unsigned nib = (meta & 0xF) | ((meta >> 4) & 0xF0) | ((meta >> 8) & 0xF00) | ((meta >> 12) & 0xF000);
-            const unsigned n1 = __shfl_down_sync(MVG_FULL, nib, 1), n2 = __shfl_down_sync(MVG_FULL, nib, 2);
-            const unsigned n3 = __shfl_down_sync(MVG_FULL, nib, 3);
-            const unsigned k4 = __shfl_down_sync(MVG_FULL, meta, 4), k6 = __shfl_down_sync(MVG_FULL, meta, 6);
-            const unsigned k7 = __shfl_down_sync(MVG_FULL, meta, 7);
-            if (mt == 0 && mj < nmb)
-                *reinterpret_cast<uint4 *>(p.ctl + mb0 + mj) =
-                    make_uint4((k4 & 255) | ((k6 & 255) << 8) | ((k7 & 255) << 16), nib | (n2 << 16),
-                               __funnelshift_l(n1 | (n3 << 16), n1 | (n3 << 16), 8), 0u);
+            const uint4 rec = mvg_ctl_from_meta(meta);
+            if ((lane & 7) == 0 && (lane >> 3) < nmb) *reinterpret_cast<uint4 *>(p.ctl + mb0 + (lane >> 3)) = rec;
         }
         __syncwarp();
     }

@@ -30,6 +30,10 @@ def test_gpu_matches_reference_golden_vectors(name):
     for i in range(soa.n_pics):
         assert np.array_equal(ctx.download_yuv420(i), z["yuv"][i]), f"{name} pic {i} YUV"
         assert np.array_equal(ctx.download_rgb(i), z["rgb"][i]), f"{name} pic {i} RGB"
+    ctx.run_rgb(0, soa.n_pics)                  # one fused kernel, levels -> RGB24
+    ctx.sync()
+    for i in range(soa.n_pics):
+        assert np.array_equal(ctx.download_rgb(i), z["rgb"][i]), f"{name} pic {i} RGB (fused, direct)"
     ctx.close()
 
 
@@ -58,19 +62,25 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("mode", ["fused", "split"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_gpu_matches_oracle(name):
-    """Same seeded SoA through the oracle and the CUDA path: residual (kernel 1), YUV (kernel 2)
-    and RGB (kernel 3) must be identical, including int32 wrap-around on hostile levels."""
+def test_gpu_matches_oracle(name, mode):
+    """Same seeded SoA through the oracle and the CUDA path: residual (the transform stage), YUV and RGB
+    must be identical, including int32 wrap-around on hostile levels.  `fused`: kf_recon (tiles, then
+    kernel 3) and kf_recon straight to RGB24; `split`: round 1's kernels 1, 2, 3."""
     from minivideo_b200 import api, synth
     from oracle import cpu
     n, kw = CASES[name]
     _, soa = synth.generate(n, want_stream=False, **kw)
     want_yuv, want_res = cpu.reconstruct(soa, want_residual=True)
-    got = api.reconstruct(soa, rgb_scale=1, want_residual=True)
+    got = api.reconstruct(soa, rgb_scale=1, want_residual=True,
+                          mode=api.PIPELINE_FUSED if mode == "fused" else api.PIPELINE_SPLIT)
     assert np.array_equal(got["residual"], want_res)
     assert np.array_equal(got["yuv"], want_yuv)
-    assert np.array_equal(got["rgb"], cpu.yuv_to_rgb(want_yuv, soa.width, soa.height, 1))
+    want_rgb = cpu.yuv_to_rgb(want_yuv, soa.width, soa.height, 1)
+    assert np.array_equal(got["rgb_k3"], want_rgb)
+    assert np.array_equal(got["rgb"], want_rgb)
+    assert got["timing"].launches == (2 if mode == "fused" else 3)
 
 
 @pytest.mark.parametrize("scale", [2, 4, 8, 16])
@@ -125,7 +135,16 @@ def test_full_size_batch_properties_1080p():
         box = (full.reshape(h // 4, 4, w // 4, 4, 3).sum(axis=(1, 3)) + 8) // 16
         assert np.array_equal(ctx.download_rgb(s, 4), box.astype(np.uint8))
     t = ctx.timing()
-    assert t.launches == 3 and t.k2_wavefront_ms > 0
+    assert t.launches == 2 and t.fused_ms > 0 and t.k3_rgb_ms > 0       # kf_recon<tiles>, k3_rgb_scaled
+    # the one-kernel path (levels -> RGB24) over the same batch: every clone equals its source, and a
+    # repeat is bit-identical
+    ctx.run_rgb(0, F)
+    ctx.sync()
+    assert ctx.timing().launches == 1
+    for s in (0, 1, G, 37, 50, F - 2, F - 1):
+        assert np.array_equal(ctx.download_rgb(s), base_rgb[s % G]), s
+    with pytest.raises(api.MvgError, match="RGB24 only"):
+        ctx.download_yuv420(0)
     ctx.close()
 
 
