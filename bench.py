@@ -2,20 +2,31 @@
 """Benchmark of the H.264 intra reconstruction hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--frames F] [--distinct G] [--rgb-scale S] [--e2e-frames E]
+                    [--frames F] [--distinct G] [--rgb-scale S] [--e2e-frames E] [--pipeline fused|split]
 
-One "step" = one pass of the hot path (kernel 1 dequant/IDCT, kernel 2 wavefront
-prediction, kernel 3 RGB) over one batch of F synthetic 1920x1088 High-profile
-IDR pictures (BASELINE.json configs[2]) that are already resident in HBM.
-Rank 0 prints ONE JSON line.  Multi-GPU: one process per GPU (torchrun), disjoint
-pictures per GPU, no collective on the data path ("scaling": "weak").
+One "step" = one pass of the hot path over one batch of F synthetic 1920x1088 High-profile IDR pictures
+(BASELINE.json configs[2]) that are already resident in HBM: ONE launch of the fused kernel kf_recon
+(dequantisation + inverse transforms + intra prediction + residual add + RGB24), or with
+--pipeline split round 1's kernels 1, 2, 3.  Rank 0 prints ONE JSON line.  Multi-GPU: one process per GPU
+(torchrun), disjoint pictures per GPU, no collective on the data path ("scaling": "weak").
 
---impl reference times the reference's own CPU implementation (oracle/_ref, the
-unmodified reference compiled by oracle/Makefile) on all host cores.
+What the line carries besides `value` (device-timed, resident inputs):
+  e2e          the same through the C ABI with HOST buffers (mvg_decode_host_packed: pinned packed SoA in, RGB24 out);
+               scope: after the CAVLC parse (the boundary of SURVEY.md section 8b)
+  stream_e2e   Annex-B bytes in host memory -> host front end (CAVLC on the host cores) -> C ABI -> RGB24 in host
+               memory, on EVERY rank, summed: the like-for-like figure beside the reference arm, which also parses
+  configs3     BASELINE.json configs[3]: 8000 pictures sharded over the GPUs, RGB thumbnails at 1/4 size
+  split_pipeline  round 1's three kernels on the same batch (kept for one round for comparison)
+  parity_checked  pictures of every timed path were downloaded after the timed region and compared (SHA-256) with
+               the CPU oracle; any mismatch makes the run exit non-zero without a line
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, the unmodified reference compiled by
+oracle/Makefile): one process pinned to each host core, every process decodes --ref-pics pictures.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -34,6 +45,10 @@ sys.path.insert(0, str(ROOT))
 METRIC = "1080p_idr_frames_per_s_recon_rgb"
 UNIT = "frames/s"
 WORKLOAD = "configs[2]: 1920x1080 High-profile CAVLC, 8x8 transform + custom scaling lists, 1000 IDR frames on 1 B200"
+# identical in both arms (the driver compares the dicts)
+CONFIG = {"workload": WORKLOAD, "coded_size": "1920x1088", "profile": "High (100), CAVLC, transform_8x8_mode, 8 SPS scaling lists",
+          "macroblock_mix": "1/3 Intra4x4, 1/3 Intra8x8, 1/3 Intra16x16", "output": "RGB24 1920x1088 (mb_to_rgb)",
+          "stream": "synthetic, committed generator (minivideo_b200/csrc/h264_synth.c), seed 0xC0FFEE+2"}
 
 
 # ----------------------------------------------------------------------------
@@ -54,6 +69,10 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def sha(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
 class ClockSampler(threading.Thread):
@@ -96,59 +115,98 @@ class ClockSampler(threading.Thread):
 
 
 def algorithmic_bytes(n_mb: int, width: int, height: int, scale: int):
-    """SURVEY.md section 8(d), per picture; kernel 2 reads the 16-byte control record
-    kernel 1 writes instead of the 32 B/MB the survey budgeted (stated in DESIGN.md)."""
+    """Per picture.  SURVEY.md section 8(d) with the side information this repository actually carries
+    (21 B of SoA per macroblock in, a 16-byte control record between kernels 1 and 2; the survey budgeted 32 B)."""
     meta_in = 21                      # mb_kind, i16_mode, chroma_mode, qp_y, cbp, 16 luma modes
-    k1 = n_mb * (768 + meta_in) + n_mb * (768 + 16)
-    k2 = n_mb * (768 + 16) + width * height * 3 // 2
-    k3 = width * height * 3 // 2 + 3 * (width // scale) * (height // scale) if scale >= 1 else 0
-    kf = n_mb * (768 + meta_in) + 3 * width * height      # fused: SoA in, RGB24 out
-    return {"k1": k1, "k2": k2, "k3": k3, "kf": kf}
+    rgb = 3 * (width // scale) * (height // scale) if scale >= 1 else 0
+    yuv = width * height * 3 // 2
+    return {
+        "k1": n_mb * (768 + meta_in) + n_mb * (768 + 16),
+        "k2": n_mb * (768 + 16) + yuv,
+        "k3": yuv + rgb,
+        "kf_rgb": n_mb * (768 + meta_in) + rgb,       # fused, SoA in -> RGB24 out: what kf_recon<RGB> must move
+        "kf_tiles": n_mb * (768 + meta_in) + yuv,     # fused, SoA in -> reconstructed picture out
+        # SURVEY.md 8(d): "if K1 is fused into K2 the algorithmic figure is N_mb*800 + 1.5WH + B_K3"
+        "survey_fused_pipeline": n_mb * 800 + yuv + yuv + rgb,
+    }
 
 
 # ----------------------------------------------------------------------------
 # reference arm: the unmodified reference decoder on the host cores
 
-def reference_sample(n_procs: int, pics_per_proc: int, rgb: bool = True):
-    """Every core decodes the same `pics_per_proc` 1080p pictures with the reference
-    (CAVLC parse + reconstruction + mb_to_rgb, no file output).  Returns
-    (frames_per_s, wall_s)."""
-    from minivideo_b200 import synth
+def _pinned_run(cmd, cwd, core):
+    def pin():
+        try:
+            os.sched_setaffinity(0, {core})
+        except OSError:
+            pass
+    return subprocess.run(cmd, capture_output=True, text=True, cwd=cwd, preexec_fn=pin)
+
+
+def reference_sample(stream_path: str, cwd: str, cores: list, pics_per_proc: int, rgb: bool = True):
+    """One process of the reference per host core, each pinned to its core and decoding the
+    same `pics_per_proc` 1080p pictures (CAVLC parse + reconstruction + mb_to_rgb, no file output).  Returns
+    (frames_per_s over the slowest process's in-process minivideo_decode() time, wall_s)."""
+    import re
     from oracle import ref
-    if not ref.available():
-        raise RuntimeError("oracle/_ref/ref_decode is missing (run `make -C oracle ref` where the reference is mounted)")
-    stream, _ = synth.generate(pics_per_proc, "1080p", want_soa=False)
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
-    with tempfile.TemporaryDirectory(dir=base, prefix="mvbench_") as d:
-        path = os.path.join(d, "sample.264")
-        Path(path).write_bytes(stream)
-        ref.time_decode(path, 1, rgb=rgb, cwd=d)            # warm the page cache / binary
-        t0 = time.perf_counter()
-        with ThreadPoolExecutor(max_workers=n_procs) as ex:
-            secs = list(ex.map(lambda _: ref.time_decode(path, pics_per_proc, rgb=rgb, cwd=d), range(n_procs)))
-        wall = time.perf_counter() - t0
-    return n_procs * pics_per_proc / max(secs), wall
+    cmd = [str(ref.REF_DECODE), stream_path, str(pics_per_proc), "--time"] + ([] if rgb else ["--norgb"])
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=len(cores)) as ex:
+        res = list(ex.map(lambda c: _pinned_run(cmd, cwd, c), cores))
+    wall = time.perf_counter() - t0
+    secs = []
+    for r in res:
+        m = re.search(r"REFTIME pictures=(\d+) seconds=([0-9.]+)", r.stdout)
+        if r.returncode != 0 or not m or int(m.group(1)) != pics_per_proc:
+            raise RuntimeError(f"ref_decode --time failed: {r.stdout[-500:]} {r.stderr[-500:]}")
+        secs.append(float(m.group(2)))
+    return len(cores) * pics_per_proc / max(secs), wall
+
+
+class ReferenceRunner:
+    """The stream the reference decodes (written once to /dev/shm) and the cores it may use."""
+
+    def __init__(self, pics: int):
+        from minivideo_b200 import synth
+        from oracle import ref
+        if not ref.available():
+            raise RuntimeError("oracle/_ref/ref_decode is missing (run `make -C oracle ref` where the reference is mounted)")
+        self.pics = pics
+        self.cores = sorted(os.sched_getaffinity(0)) or [0]
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        self.tmp = tempfile.TemporaryDirectory(dir=base, prefix="mvbench_")
+        stream, _ = synth.generate(pics, "1080p", want_soa=False, seed=0xC0FFEE + 2)
+        self.path = os.path.join(self.tmp.name, "sample.264")
+        Path(self.path).write_bytes(stream)
+        _pinned_run([str(ref.REF_DECODE), self.path, "1", "--time"], self.tmp.name, self.cores[0])      # page cache, binary
+
+    def sample(self):
+        return reference_sample(self.path, self.tmp.name, self.cores, self.pics)
+
+    @property
+    def description(self):
+        return (f"{self.pics} pictures per process x {len(self.cores)} processes, one pinned to each host core, same 1080p "
+                "stream, the unmodified reference's parse + reconstruction + mb_to_rgb (in-process minivideo_decode() time, "
+                "slowest process)")
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    per = args.ref_pics
+    runner = ReferenceRunner(args.ref_pics)
     vals, walls = [], []
     for i in range(args.warmup + args.steps):
-        fps, wall = reference_sample(cores, per)
+        fps, wall = runner.sample()
         if i >= args.warmup:
             vals.append(fps); walls.append(wall)
     value = float(np.mean(vals))
-    sample = f"{per} pictures per process x {cores} processes (one per host core), same 1080p stream, in-process minivideo_decode() time"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(walls)) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "config": CONFIG,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": len(runner.cores), "kind": "reference", "sample": runner.description},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -159,6 +217,10 @@ def run_reference(args):
 # ----------------------------------------------------------------------------
 # our arm
 
+class ParityError(RuntimeError):
+    pass
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     if args.gpus > 1 and world == 1:
@@ -167,9 +229,11 @@ def run_ours(args):
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                                    "--master-port", str(port), str(Path(__file__).resolve())] + sys.argv[1:])
+    import ctypes as C
     import torch
     import torch.distributed as dist
-    from minivideo_b200 import api, synth
+    from minivideo_b200 import api, front, synth
+    from oracle import cpu          # the checker (outside every timed region)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
@@ -193,6 +257,8 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(keep, 1)
             os.close(keep)
+    # the host cores are shared by the ranks: each takes its share for the bitstream path
+    host_threads = max(1, (len(os.sched_getaffinity(0)) or 1) // world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -200,46 +266,85 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    checks = []             # (what, ok)
+
+    def check(what, got, want):
+        ok = sha(np.asarray(got).reshape(-1)) == sha(np.asarray(want).reshape(-1))
+        checks.append((what, ok))
+        if not ok:
+            raise ParityError(f"rank {rank}: {what} differs from the oracle")
+
     # ---- synthetic input: G distinct pictures per rank, replicated on the device to F
     F, G, scale = args.frames, min(args.distinct, args.frames), args.rgb_scale
+    P3 = 8000 // max(world, 2) if args.configs3 else 0          # configs[3]: 8000 pictures over 2/4/8 GPUs
     _, soa = synth.generate(G, "1080p", want_stream=False, seed=0xC0FFEE + 2 + 1000 * rank)
     W, H, N = soa.width, soa.height, soa.n_mbs
-    ctx = api.Context(local, soa.width_mbs, soa.height_mbs, F)
+    slots = max(F, P3)
+    ctx = api.Context(local, soa.width_mbs, soa.height_mbs, slots)
     ctx.set_sps_from(soa)
     ctx.upload(soa, 0)
-    for s in range(G, F):
+    for s in range(G, slots):
         ctx.clone_slot(s % G, s)
     ctx.sync()
+    # what the oracle says about two of the distinct pictures (computed before anything is timed)
+    probe = [0, G - 1] if G > 1 else [0]
+    want_yuv = {i: cpu.reconstruct(soa.pictures(i, 1))[0][0] for i in probe}
+
+    def oracle_rgb(i, s):
+        return cpu.yuv_to_rgb(want_yuv[i][None], W, H, s)[0]
+    want_rgb_s = {i: oracle_rgb(i, scale) for i in probe}
 
     # ---- timed region: K steps over the resident batch
+    split = args.pipeline == "split"
+
+    def timed_resident(n_pics, rgb_scale, use_split):
+        ctx.set_pipeline_mode(api.PIPELINE_SPLIT if use_split else api.PIPELINE_FUSED)
+        step = (lambda: ctx.run(0, n_pics, rgb_scale)) if (use_split or rgb_scale != 1) else (lambda: ctx.run_rgb(0, n_pics))
+        for _ in range(args.warmup):
+            step()
+        ctx.sync()
+        barrier()
+        k_ms = {"k1": [], "k2": [], "k3": [], "kf": []}
+        launches = 0
+        t0 = time.perf_counter()
+        ctx.mark(0)
+        for _ in range(args.steps):
+            step()
+            t = ctx.timing()                      # waits for the step; per-kernel CUDA-event times
+            k_ms["k1"].append(t.k1_dequant_idct_ms); k_ms["k2"].append(t.k2_wavefront_ms); k_ms["k3"].append(t.k3_rgb_ms)
+            k_ms["kf"].append(t.fused_ms)
+            launches += t.launches
+        ctx.mark(1)
+        dev_ms = ctx.mark_elapsed_ms()
+        barrier()
+        t1 = time.perf_counter()
+        return dev_ms, {k: float(np.mean(v)) for k, v in k_ms.items() if np.mean(v) > 0}, launches, t0, t1
+
     sampler = ClockSampler(local)
     sampler.start()
     t_wait = time.perf_counter()
     while not sampler.samples and sampler.err is None and time.perf_counter() - t_wait < 10.0:
         time.sleep(0.01)                      # NVML initialisation can take longer than the warm-up
-    split = args.pipeline == "split"
-    ctx.set_pipeline_mode(api.PIPELINE_SPLIT if split else api.PIPELINE_FUSED)
-    step = (lambda: ctx.run(0, F, scale)) if (split or scale != 1) else (lambda: ctx.run_rgb(0, F))
-    for _ in range(args.warmup):
-        step()
-    ctx.sync()
-    barrier()
-    k_ms = {"k1": [], "k2": [], "k3": [], "kf": []}
-    launches = 0
-    t_wall0 = time.perf_counter()
-    ctx.mark(0)
-    for _ in range(args.steps):
-        step()
-        t = ctx.timing()                      # waits for the step; per-kernel CUDA-event times
-        k_ms["k1"].append(t.k1_dequant_idct_ms); k_ms["k2"].append(t.k2_wavefront_ms); k_ms["k3"].append(t.k3_rgb_ms)
-        k_ms["kf"].append(t.fused_ms)
-        launches += t.launches
-    ctx.mark(1)
-    dev_ms = ctx.mark_elapsed_ms()
-    barrier()
-    t_wall1 = time.perf_counter()
+    dev_ms, mean_ms, launches, t_wall0, t_wall1 = timed_resident(F, scale, split)
     wall_ms = (t_wall1 - t_wall0) * 1e3
     clocks = sampler.result(t_wall0, t_wall1)
+    # what was timed produced the right pictures: a source slot, a clone in the middle, one of the last slots
+    for s in sorted({probe[-1], (F // 2) // G * G + probe[0] if F >= 2 * G else probe[0], (F - 1) // G * G + probe[0] if F > G else probe[0]}):
+        if s < F:
+            check(f"resident RGB, slot {s}", ctx.download_rgb(s, scale), want_rgb_s[s % G])
+
+    # the other pipeline on the same batch, for comparison (round 1's three kernels / the fused kernel)
+    other_dev_ms, other_ms, other_launches, _, _ = timed_resident(F, scale, not split)
+    check("resident RGB (other pipeline)", ctx.download_rgb(probe[0], scale), want_rgb_s[probe[0]])
+    ctx.set_pipeline_mode(api.PIPELINE_SPLIT if split else api.PIPELINE_FUSED)
+
+    # ---- configs[3]: 8000 pictures sharded over the GPUs, RGB thumbnails at 1/4 size (resident + end to end)
+    configs3 = None
+    if P3:
+        c3_dev_ms, c3_ms, c3_launches, _, _ = timed_resident(P3, 4, split)
+        check("configs[3] RGB at 1/4 size", ctx.download_rgb((P3 - 1) // G * G + probe[0] if P3 > G else probe[0], 4), oracle_rgb(probe[0], 4))
+        launches += c3_launches
+        configs3 = {"dev_ms": c3_dev_ms, "kernels_ms": c3_ms}
 
     # ---- end to end: pinned host buffers -> H2D -> kernels -> D2H RGB in pinned host memory, through the
     # C ABI.  Headline: the packed transfer format (mvg_decode_host_packed, what the front end emits);
@@ -250,14 +355,22 @@ def run_ours(args):
     d2h = rgb_out.nbytes
     packed = api.Packed(soa, n_pics=E, pinned=True)
     h2d = packed.nbytes
-    for _ in range(max(1, args.warmup // 2)):
-        ctx.decode_host_packed(packed, None, rgb_out.array, scale)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.decode_host_packed(packed, None, rgb_out.array, scale)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+
+    def timed_host(fn):
+        for _ in range(max(1, args.warmup // 2)):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    rgb_out.array[...] = 0
+    e2e_s = timed_host(lambda: ctx.decode_host_packed(packed, None, rgb_out.array, scale))
+    for k in sorted({probe[-1], (E - 1) // G * G + probe[0] if E > G else probe[0]}):
+        if k < E:
+            check(f"end-to-end RGB, picture {k}", rgb_out.array[k], want_rgb_s[k % G])
 
     reps = -(-E // G)
     pin = {
@@ -274,77 +387,119 @@ def run_ours(args):
     for name, pa in pin.items():
         setattr(batch, name, pa.ptr)
     h2d_dense = sum(pa.nbytes for pa in pin.values())
-    ctx.decode_host(None, None, rgb_out.array, scale, batch=batch)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.decode_host(None, None, rgb_out.array, scale, batch=batch)
-    torch.cuda.synchronize()
-    e2e_dense_s = time.perf_counter() - t0
+    rgb_out.array[...] = 0
+    e2e_dense_s = timed_host(lambda: ctx.decode_host(None, None, rgb_out.array, scale, batch=batch))
+    check("end-to-end RGB (dense levels)", rgb_out.array[probe[-1]], want_rgb_s[probe[-1]])
+    del pin, batch
 
-    # ---- from the bitstream: Annex-B bytes -> host front end (CAVLC on all host cores, packed output into pinned
-    # memory) -> mvg_decode_host_packed -> RGB24 in pinned host memory.  Same input and output as the reference
-    # arm (which times minivideo_decode() on the same kind of stream); bound by the host's entropy decoding.
+    c3_e2e_s = None
+    if P3:
+        E3 = min(E, P3)
+        out4 = api.PinnedArray((E3, (W // 4) * (H // 4) * 3), np.uint8)
+        packed3 = packed if E3 == E else api.Packed(soa, n_pics=E3, pinned=True)
+        c3_e2e_s = timed_host(lambda: ctx.decode_host_packed(packed3, None, out4.array, 4))
+        check("configs[3] end-to-end RGB at 1/4 size", out4.array[probe[0]], oracle_rgb(probe[0], 4))
+        configs3.update(e2e_s=c3_e2e_s, e2e_pictures=E3, d2h=out4.nbytes)
+        del out4, packed3
+    del packed
+
+    # ---- from the bitstream, on every rank: Annex-B bytes -> host front end (CAVLC on this rank's share of the host
+    # cores, a persistent parser, packed output into pinned memory) -> mvg_decode_host_packed -> RGB24 in pinned host
+    # memory.  Same input and output as the reference arm.  A step = S pictures in sub-batches of B: the parse of
+    # sub-batch k+1 overlaps the GPU work of sub-batch k (what mvt_extract() does with its two buffer sets).
     stream_e2e = None
-    if rank == 0 and args.stream_frames > 0:
-        import ctypes as C
-        from minivideo_b200 import front
-        S = min(args.stream_frames, F)
-        stream, _ = synth.generate(S, "1080p", want_soa=False, seed=0xC0FFEE + 2)
+    stream_s, S = 0.0, 0
+    if args.stream_frames > 0:
+        S, B = args.stream_frames, min(args.stream_batch, args.stream_frames)
+        D = min(S, 64)                                          # distinct pictures in the stream, visited cyclically
+        stream, _ = synth.generate(D, "1080p", want_soa=False, seed=0xC0FFEE + 2 + 1000 * rank)
         st = front.Stream(stream)
+        info = st.info
         ls4, ls8 = st.level_scale()
-        ctx.set_sps(st.info.width_mbs, st.info.height_mbs, ls4, ls8, st.info.cb_qp_offset, st.info.cr_qp_offset)
-        cap = S * N * 160                                       # words; ~5x what this stream needs
-        order = ("mb_kind", "i16_mode", "chroma_mode", "qp_y", "luma_modes", "nz_blocks", "word_off", "pic_off", "words")
-
-        def buffers():
-            pk = {"mb_kind": api.PinnedArray((S * N,), np.uint8), "i16_mode": api.PinnedArray((S * N,), np.uint8),
-                  "chroma_mode": api.PinnedArray((S * N,), np.uint8), "qp_y": api.PinnedArray((S * N,), np.int8),
-                  "luma_modes": api.PinnedArray((S * N, 16), np.uint8), "nz_blocks": api.PinnedArray((S * N,), np.uint32),
-                  "word_off": api.PinnedArray((S * N,), np.uint32), "pic_off": api.PinnedArray((S + 1,), np.uint64),
-                  "words": api.PinnedArray((cap,), np.uint16)}
-            return pk, front.FrontPackedBatch(S, *(pk[k].ptr for k in order), cap), api.PackedBatch(S, *(pk[k].ptr for k in order))
-        sets = [buffers(), buffers()]                           # parse of step k+1 runs while step k is on the GPU
-        out_s = api.PinnedArray((S, rgb_px), np.uint8)
-        threads = os.cpu_count() or 1
+        ctx.set_sps(info.width_mbs, info.height_mbs, ls4, ls8, info.cb_qp_offset, info.cr_qp_offset)
         flib = front.lib()
+        parser = C.c_void_p()
+        if flib.mvf_parser_create(st.handle, host_threads, C.byref(parser)) != 1:
+            raise RuntimeError("mvf_parser_create failed")
+        order = ("mb_kind", "i16_mode", "chroma_mode", "qp_y", "luma_modes", "nz_blocks", "word_off", "pic_off", "words")
+        idx_all = np.ascontiguousarray(np.arange(S, dtype=np.int32) % D)
+
+        def buffers(cap):
+            pk = {"mb_kind": api.PinnedArray((B * N,), np.uint8), "i16_mode": api.PinnedArray((B * N,), np.uint8),
+                  "chroma_mode": api.PinnedArray((B * N,), np.uint8), "qp_y": api.PinnedArray((B * N,), np.int8),
+                  "luma_modes": api.PinnedArray((B * N, 16), np.uint8), "nz_blocks": api.PinnedArray((B * N,), np.uint32),
+                  "word_off": api.PinnedArray((B * N,), np.uint32), "pic_off": api.PinnedArray((B + 1,), np.uint64),
+                  "words": api.PinnedArray((cap,), np.uint16)}
+            return pk, front.FrontPackedBatch(B, *(pk[k].ptr for k in order), cap), api.PackedBatch(B, *(pk[k].ptr for k in order))
+        # right-sized pinned buffers: a first parse into a token buffer fails on capacity and reports what a sub-batch needs
+        probe_set = buffers(1)
+        flib.mvf_parser_parse_packed(parser, idx_all.ctypes.data, 0, B, C.byref(probe_set[1]))
+        cap = int(probe_set[1].words_needed * 1.25) + 4096
+        del probe_set
+        sets = [buffers(cap), buffers(cap)]
+        outs = [api.PinnedArray((B, rgb_px), np.uint8), api.PinnedArray((B, rgb_px), np.uint8)]
+        n_sub = -(-S // B)
 
         def parse(k):
-            rc = flib.mvf_parse_pictures_packed(st.handle, None, 0, S, C.byref(sets[k & 1][1]), threads)
+            cnt = min(B, S - k * B)
+            rc = flib.mvf_parser_parse_packed(parser, idx_all[k * B:].ctypes.data, 0, cnt, C.byref(sets[k & 1][1]))
             if rc != 1:
-                raise RuntimeError(flib.mvf_last_error(st.handle).decode())
+                raise RuntimeError(flib.mvf_parser_last_error(parser).decode())
+            return cnt
 
-        def decode(k):
-            ctx._ck(ctx.lib.mvg_decode_host_packed(ctx.handle, C.byref(sets[k & 1][2]), None, out_s.ptr, scale))
-        parse(0); decode(0)                                     # warm-up
-        with ThreadPoolExecutor(max_workers=1) as ex:           # ctypes calls release the GIL
-            t0 = time.perf_counter()
-            parse(0)
-            for k in range(args.steps):
-                nxt = ex.submit(parse, k + 1) if k + 1 < args.steps else None
-                decode(k)
+        def decode(k, cnt):
+            sets[k & 1][2].n_pics = cnt
+            ctx._ck(ctx.lib.mvg_decode_host_packed(ctx.handle, C.byref(sets[k & 1][2]), None, outs[k & 1].ptr, scale))
+
+        def stream_step(ex):
+            cnt = parse(0)
+            for k in range(n_sub):
+                nxt = ex.submit(parse, k + 1) if k + 1 < n_sub else None
+                decode(k, cnt)
                 if nxt:
-                    nxt.result()
-            dt = time.perf_counter() - t0
-        stream_e2e = {"value": S * args.steps / dt, "unit": UNIT, "pictures_per_step": S, "host_threads": threads,
-                      "stream_bytes_per_picture": len(stream) // S,
-                      "path": "Annex-B bytes -> mvf_parse_pictures_packed (CAVLC on the host cores) -> mvg_decode_host_packed -> RGB24; "
-                              "the parse of step k+1 overlaps the GPU work of step k; one GPU, rank 0 only"}
+                    cnt = nxt.result()
+        with ThreadPoolExecutor(max_workers=1) as ex:           # ctypes calls release the GIL
+            stream_step(ex)                                     # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                stream_step(ex)
+            torch.cuda.synchronize()
+            stream_s = time.perf_counter() - t0
+        # the last sub-batch is still in its output buffer: one of its pictures against the oracle, from the stream
+        k_last = n_sub - 1
+        dense = st.parse(indices=[int(idx_all[k_last * B])], n_threads=1)
+        o_sps = cpu.OracleSps()
+        o_sps.width_mbs, o_sps.height_mbs = info.width_mbs, info.height_mbs
+        C.memmove(o_sps.ls4, np.ascontiguousarray(ls4, np.int32).ctypes.data, 288 * 4)
+        C.memmove(o_sps.ls8, np.ascontiguousarray(ls8, np.int32).ctypes.data, 384 * 4)
+        o_sps.cb_qp_offset, o_sps.cr_qp_offset = info.cb_qp_offset, info.cr_qp_offset
+        yuv1 = np.zeros(W * H * 3 // 2, np.uint8)
+        arrs = [np.ascontiguousarray(x) for x in (dense.mb_kind, dense.i16_mode, dense.chroma_mode, dense.qp_y, dense.luma_modes, dense.coeff)]
+        pv = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        cpu.lib().oracle_reconstruct_picture(C.byref(o_sps), *[pv(a) for a in arrs], pv(yuv1[:W * H]), pv(yuv1[W * H:W * H * 5 // 4]),
+                                             pv(yuv1[W * H * 5 // 4:]), None)
+        check("bitstream-to-RGB, last sub-batch", outs[k_last & 1].array[0], cpu.yuv_to_rgb(yuv1[None], W, H, scale)[0])
+        flib.mvf_parser_destroy(parser)
+        stream_e2e = {"pictures_per_step_per_gpu": S, "sub_batch": B, "host_threads_per_gpu": host_threads,
+                      "stream_bytes_per_picture": len(stream) // D, "distinct_pictures": D,
+                      "pinned_words_per_sub_batch": cap}
+        del sets, outs
 
     # ---- reduce over ranks (max time), rank 0 reports
-    times = torch.tensor([dev_ms, wall_ms, e2e_s * 1e3, e2e_dense_s * 1e3], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_ms, wall_ms, e2e_s * 1e3, e2e_dense_s * 1e3, stream_s * 1e3, other_dev_ms,
+                          configs3["dev_ms"] if configs3 else 0.0, (c3_e2e_s or 0.0) * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, e2e_ms, e2e_dense_ms = (float(x) for x in times.tolist())
+    dev_ms, wall_ms, e2e_ms, e2e_dense_ms, stream_ms, other_dev_ms, c3_dev_ms, c3_e2e_ms = (float(x) for x in times.tolist())
 
     if rank == 0:
         peak, peak_src = measured_peak()
         ab = algorithmic_bytes(N, W, H, scale)
-        mean_ms = {k: float(np.mean(v)) for k, v in k_ms.items()}
-        ab = {k: v for k, v in ab.items() if mean_ms[k] > 0}
-        mean_ms = {k: v for k, v in mean_ms.items() if v > 0}
+        name_of = {"k1": "k1_dequant_idct", "k2": "k2_wavefront", "k3": "k3_rgb", "kf": "kf_recon"}
+        ab_of = dict(ab, kf=ab["kf_rgb"] if scale == 1 else ab["kf_tiles"])
         dom = max(mean_ms, key=mean_ms.get)
-        achieved = ab[dom] * F / (mean_ms[dom] * 1e-3) / 1e9
+        achieved = ab_of[dom] * F / (mean_ms[dom] * 1e-3) / 1e9
         traffic = None
         tfile = ROOT / "profiles" / "ncu_traffic.json"
         if tfile.exists():
@@ -352,41 +507,74 @@ def run_ours(args):
                 traffic = json.loads(tfile.read_text())["per_picture_dram_bytes"][dom] * F
             except Exception:
                 traffic = None
-        kernels = {k: {"ms_per_launch": mean_ms[k], "algorithmic_bytes": ab[k] * F,
-                       "achieved_gbs": ab[k] * F / (mean_ms[k] * 1e-3) / 1e9 if mean_ms[k] > 0 else None,
-                       "frac": ab[k] * F / (mean_ms[k] * 1e-3) / 1e9 / peak if mean_ms[k] > 0 else None}
-                   for k in mean_ms}
+
+        def kernel_block(ms):
+            return {name_of[k]: {"ms_per_launch": v, "algorithmic_bytes": ab_of[k] * F, "achieved_gbs": ab_of[k] * F / (v * 1e-3) / 1e9,
+                                 "frac": ab_of[k] * F / (v * 1e-3) / 1e9 / peak} for k, v in ms.items()}
+        step_ms = dev_ms / args.steps
         line = {
             "metric": METRIC, "value": world * F * args.steps / (dev_ms * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pictures_per_step_per_gpu": F, "distinct_pictures": G,
-                       "coded_size": f"{W}x{H}", "rgb_scale": scale, "pipeline": "3 kernels (k1 dequant/idct, k2 wavefront -> macroblock tiles, k3 rgb)",
-                       "l2": f"inputs {F * N * 789 / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
-                       "timing": "CUDA events on the launch stream, max over ranks", "wall_ms_per_step": wall_ms / args.steps},
+            "config": CONFIG,
+            "run": {"pictures_per_step_per_gpu": F, "distinct_pictures": G, "rgb_scale": scale,
+                    "pipeline": "split: k1_dequant_idct, k2_wavefront -> tiles, k3_rgb" if split else
+                                "fused: one launch of kf_recon per step (levels in HBM -> RGB24 in HBM)",
+                    "l2": f"inputs {F * N * 789 / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
+                    "timing": "CUDA events on the launch stream, max over ranks", "wall_ms_per_step": wall_ms / args.steps},
             "clocks": clocks,
             "e2e": {"value": world * E * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "pictures_per_step_per_gpu": E,
-                    "path": "mvg_decode_host_packed: pinned host packed SoA (sparse levels) -> H2D -> k0 expand, k1, k2, k3 -> D2H RGB24",
+                    "scope": "post-parse: starts from the parsed structure-of-arrays (the C-ABI boundary, SURVEY.md 8b); the "
+                             "reference arm also parses -- stream_e2e is the like-for-like figure",
+                    "path": "mvg_decode_host_packed: pinned host packed SoA (sparse levels) -> H2D -> k0 expand, kf_recon -> D2H RGB24",
                     "dense": {"value": world * E * args.steps / (e2e_dense_ms * 1e-3), "h2d_bytes_per_step": h2d_dense,
                               "path": "mvg_decode_host: dense int16[384] levels per macroblock"}},
-            "stream_e2e": stream_e2e,
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": {"k1": "k1_dequant_idct", "k2": "k2_wavefront", "k3": "k3_rgb", "kf": "kf_recon"}[dom],
+            "roofline": {"bound": "hbm", "kernel": name_of[dom],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src},
-            "kernels": kernels,
-            # the three stages together: algorithmic bytes of all kernels over the sum of their launch times
-            "roofline_all_stages": {"achieved": sum(ab.values()) * F / (sum(mean_ms.values()) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                    "frac": sum(ab.values()) * F / (sum(mean_ms.values()) * 1e-3) / 1e9 / peak},
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_picture": ab_of[dom],
+                         "note": "kf_recon is bound by instruction issue, not HBM (profiles/): the fraction is what the task asks to report"},
+            # the same step against SURVEY.md 8(d)'s figure for a k1-into-k2 fused PIPELINE (which still counts a tiles
+            # round trip and kernel 3's traffic: 19 061 760 B per picture at scale 1)
+            "roofline_survey_fused": {"algorithmic_bytes_per_picture": ab["survey_fused_pipeline"],
+                                      "achieved": ab["survey_fused_pipeline"] * F / (step_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                      "frac": ab["survey_fused_pipeline"] * F / (step_ms * 1e-3) / 1e9 / peak},
+            "kernels": kernel_block(mean_ms),
+            ("fused_pipeline" if split else "split_pipeline"): {
+                "value": world * F * args.steps / (other_dev_ms * 1e-3), "ms_per_step": other_dev_ms / args.steps,
+                "kernels": kernel_block(other_ms), "launches": other_launches,
+                "roofline_all_stages": {"frac": sum(ab_of[k] for k in other_ms) * F / (sum(other_ms.values()) * 1e-3) / 1e9 / peak}},
+            "parity_checked": bool(checks) and all(ok for _, ok in checks),
+            "parity_checks": [w for w, _ in checks],
         }
+        if stream_e2e:
+            stream_e2e.update(value=world * S * args.steps / (stream_ms * 1e-3), unit=UNIT,
+                              path="Annex-B bytes -> mvf_parser_parse_packed (CAVLC on the host cores, persistent workers) -> "
+                                   "mvg_decode_host_packed -> RGB24; sub-batch k+1 is parsed while sub-batch k is on the GPU; "
+                                   "every rank runs its own feeder on its share of the host cores, the value is the sum")
+            line["stream_e2e"] = stream_e2e
+        if configs3:
+            ab3 = algorithmic_bytes(N, W, H, 4)
+            line["configs3"] = {
+                "workload": "configs[3]: 1920x1080 High-profile batch of 8000 IDR frames sharded across 2/4/8 B200 with fused RGB thumbnail downscale",
+                "pictures_per_gpu": P3, "pictures_total": P3 * world, "rgb_scale": 4,
+                "value": world * P3 * args.steps / (c3_dev_ms * 1e-3), "unit": UNIT, "ms_per_step": c3_dev_ms / args.steps,
+                "kernels_ms": configs3["kernels_ms"],
+                "pipeline": "kf_recon -> macroblock tiles, k3_rgb_scaled (1/4 size box average)",
+                "algorithmic_bytes_per_picture": ab3["kf_tiles"] + ab3["k3"],
+                "e2e": {"value": world * configs3["e2e_pictures"] * args.steps / (c3_e2e_ms * 1e-3), "unit": UNIT,
+                        "pictures_per_step_per_gpu": configs3["e2e_pictures"], "d2h_bytes_per_step": configs3["d2h"], "h2d_bytes_per_step": h2d,
+                        "scope": "post-parse (mvg_decode_host_packed), RGB24 at 480x272 back to pinned host memory"},
+                "note": "at 1 GPU the batch is 4000 pictures (half of configs[3], which names 2/4/8 GPUs)" if world == 1 else None}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cores = os.cpu_count() or 1
-                fps, _ = reference_sample(cores, args.ref_pics)
-                line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference",
-                                        "sample": f"{args.ref_pics} pictures per process x {cores} processes of the same 1080p "
-                                                  "stream through the unmodified reference (parse + recon + mb_to_rgb)"}
+                runner = ReferenceRunner(args.ref_pics)
+                fps, _ = runner.sample()
+                line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": len(runner.cores), "kind": "reference", "sample": runner.description}
+                if stream_e2e:
+                    line["stream_e2e"]["vs_cpu_baseline"] = stream_e2e["value"] / fps
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
         print(json.dumps(line), flush=True)
@@ -407,16 +595,22 @@ def main():
     ap.add_argument("--distinct", type=int, default=32, help="distinct pictures generated on the host per GPU")
     ap.add_argument("--rgb-scale", type=int, default=1, help="RGB thumbnail downscale factor (1 = the reference's mb_to_rgb)")
     ap.add_argument("--e2e-frames", type=int, default=384, help="pictures per end-to-end step per GPU")
-    ap.add_argument("--stream-frames", type=int, default=64, help="pictures of the bitstream-to-RGB measurement (0 = skip)")
-    ap.add_argument("--ref-pics", type=int, default=6, help="pictures each host core decodes in the CPU baseline")
+    ap.add_argument("--stream-frames", type=int, default=512, help="pictures per step of the bitstream-to-RGB measurement (0 = skip)")
+    ap.add_argument("--stream-batch", type=int, default=64, help="pictures per sub-batch of the bitstream-to-RGB measurement")
+    ap.add_argument("--ref-pics", type=int, default=30, help="pictures each host core decodes in the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs3", dest="configs3", action="store_false", help="skip the configs[3] block (8000 pictures, 1/4-size RGB)")
     ap.add_argument("--pipeline", default="fused", choices=["fused", "split"], help="fused kernel (default) or round 1's three kernels")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
-    return run_ours(args)
+    try:
+        return run_ours(args)
+    except ParityError as e:
+        print(f"bench.py: PARITY FAILURE: {e}", file=sys.stderr, flush=True)
+        return 3
 
 
 if __name__ == "__main__":

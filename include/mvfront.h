@@ -45,6 +45,8 @@ typedef struct mvf_info {
     int32_t crop_left, crop_right, crop_top, crop_bottom;   /* parsed, never applied (export.c:80-81) */
     int32_t level_scale4x4[3 * 6 * 16]; /* ready for mvg_set_sps()                              */
     int32_t level_scale8x8[6 * 64];
+    int32_t n_generations;              /* parameter generations in the stream (see below)      */
+    int32_t generation;                 /* the one this structure describes                     */
 } mvf_info;
 
 /* Writable twin of mvg_batch: the caller allocates the arrays (pinned memory from
@@ -55,14 +57,24 @@ typedef struct mvf_batch {
     int8_t  *qp_y;
     uint8_t *cbp, *luma_modes;
     int16_t *coeff;
+    int32_t *status;    /* NULL, or [n_pics]: see "errors" below */
 } mvf_batch;
 
-/* Scan an Annex-B byte stream held in memory (it must stay valid until mvf_close), parse the
- * first SPS and PPS, index the IDR slices. */
+/* Scan an Annex-B byte stream held in memory (it must stay valid until mvf_close), index the IDR slices and
+ * replay the parameter sets in stream order the way the reference's NAL loop does (h264.c:128-150): every SPS /
+ * PPS replaces the one stored under its id, every IDR slice resolves its PPS by pic_parameter_set_id and its SPS
+ * through it (h264_slice.c:168-169).  Each distinct (SPS, PPS) pair in force for some IDR picture is a
+ * "parameter generation"; most streams have exactly one.  A generation fixes picture geometry, the LevelScale
+ * tables, the chroma QP offsets, pic_init_qp and transform_8x8_mode -- what mvg_set_sps() installs -- so a
+ * caller reconstructs each generation's pictures with that generation's mvf_info.  FAILURE / UNSUPPORTED only
+ * when no IDR picture at all has usable parameter sets. */
 int mvf_open_annexb(const uint8_t *data, size_t len, mvf_stream **out);
 int mvf_close(mvf_stream *s);
 const char *mvf_last_error(const mvf_stream *s);      /* s may be NULL after a failed open */
-int mvf_get_info(const mvf_stream *s, mvf_info *out);
+int mvf_get_info(const mvf_stream *s, mvf_info *out);                       /* generation 0 */
+int mvf_generation_count(const mvf_stream *s);
+int mvf_get_generation_info(const mvf_stream *s, int generation, mvf_info *out);
+int mvf_picture_generation(const mvf_stream *s, int idr_index);             /* -1: the picture has no usable SPS/PPS */
 
 /* Frame selection, the work-list builder for the GPUs: mirrors idr_filtering()
  * (demuxer/filter.c:52-215).  mode 0 = unfiltered (first n), 1 = ordered, 2 = distributed.
@@ -70,7 +82,12 @@ int mvf_get_info(const mvf_stream *s, mvf_info *out);
 int mvf_select_idr(const mvf_stream *s, int n_wanted, int mode, int32_t *indices);
 
 /* CAVLC-parse `count` IDR pictures given by `indices` (NULL = first, first+1, ...) into `out`
- * using up to `n_threads` host threads (one slice per thread). */
+ * using up to `n_threads` host threads (one slice per thread).  All pictures of a call must have the geometry
+ * of the first one (one parameter generation per call, or generations of equal picture size).
+ * Errors: with out->status == NULL the call is all-or-nothing -- the first picture that fails fails the call
+ * with its code.  With out->status pointing to `count` ints every picture reports its own code there
+ * (MVG_SUCCESS / MVG_FAILURE / MVG_UNSUPPORTED), a failed picture leaves an all-zero slot, and the call itself
+ * succeeds: the reference, too, counts a bad picture and goes on (h264.c:103-109, :181). */
 int mvf_parse_pictures(mvf_stream *s, const int32_t *indices, int first, int count,
                        mvf_batch *out, int n_threads);
 
@@ -86,12 +103,25 @@ typedef struct mvf_packed_batch {
     uint64_t *pic_off;
     uint16_t *words;
     size_t    words_capacity;
+    int32_t  *status;           /* NULL, or [n_pics]: per-picture codes (see mvf_parse_pictures) */
+    size_t    words_needed;     /* out: words the pictures of the call need (also when the capacity was too small) */
 } mvf_packed_batch;
 
 /* mvf_parse_pictures() emitting the packed transfer format directly: the levels of a picture never exist
  * densely outside a per-thread scratch picture.  FAILURE (with a message) when `words` is too small. */
 int mvf_parse_pictures_packed(mvf_stream *s, const int32_t *indices, int first, int count,
                               mvf_packed_batch *out, int n_threads);
+
+/* A parser keeps its worker threads and their scratch memory between calls (the two functions above create and
+ * destroy one per call).  One call at a time per parser; several parsers may share a stream.  While the workers
+ * parse, the calling thread gathers finished pictures' words in order, so the packed output is complete when the
+ * last picture is. */
+typedef struct mvf_parser mvf_parser;
+int mvf_parser_create(mvf_stream *s, int n_threads, mvf_parser **out);
+int mvf_parser_destroy(mvf_parser *p);
+int mvf_parser_parse(mvf_parser *p, const int32_t *indices, int first, int count, mvf_batch *out);
+int mvf_parser_parse_packed(mvf_parser *p, const int32_t *indices, int first, int count, mvf_packed_batch *out);
+const char *mvf_parser_last_error(const mvf_parser *p);     /* of this parser's last call (never NULL) */
 
 #ifdef __cplusplus
 }

@@ -193,6 +193,20 @@ int mvg_download_residual(mvg_ctx *ctx, int slot, int16_t *residual);
 int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *host_batch,
                     uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale);
 
+/* -- asynchronous form -----------------------------------------------------------
+ * mvg_submit() enqueues everything mvg_decode_host() does -- H2D copies, kernels, D2H copies, over the same three
+ * streams -- and returns without waiting for the device; mvg_wait() blocks until the outputs of that submission are
+ * complete in host memory.  A caller overlaps its own work (parsing the next batch, encoding the previous one) with
+ * the GPU without threads of its own, and may have several submissions in flight (at most 8): their chunks follow
+ * each other through the context's slot regions in submission order.  The batch ARRAYS and the output buffers must
+ * stay valid and untouched until mvg_wait() returns; the batch structure itself may go away after the call.
+ * mvg_decode_host*() are mvg_submit*() + mvg_wait().  mvg_set_sps() drains the context before it changes tables. */
+typedef int32_t mvg_ticket;
+int mvg_submit(mvg_ctx *ctx, const mvg_batch *host_batch, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale,
+               mvg_ticket *ticket);
+int mvg_wait(mvg_ctx *ctx, mvg_ticket ticket);
+int mvg_poll(mvg_ctx *ctx, mvg_ticket ticket, int *done);     /* *done = 1 when mvg_wait() would not block */
+
 /* -- packed transfer format ---------------------------------------------------
  * A parsed intra picture is mostly zero levels (a CAVLC block carries a handful of
  * them), and the end-to-end path is bound by PCIe, so the levels can cross the bus
@@ -236,9 +250,11 @@ int mvg_pack_batch(const int16_t *coeff, int n_pics, int n_mbs,
                    uint32_t *nz_blocks, uint32_t *word_off, uint64_t *pic_off,
                    uint16_t *words, size_t words_capacity, int n_threads);
 
-/* mvg_decode_host() for a packed batch: same pipeline, same outputs. */
+/* mvg_decode_host() / mvg_submit() for a packed batch: same pipeline, same outputs. */
 int mvg_decode_host_packed(mvg_ctx *ctx, const mvg_packed_batch *host_batch,
                            uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale);
+int mvg_submit_packed(mvg_ctx *ctx, const mvg_packed_batch *host_batch,
+                      uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale, mvg_ticket *ticket);
 
 /* Pictures per pipeline chunk of mvg_decode_host() (0 = automatic: an eighth of the batch, at
  * most a third of the context).  Larger chunks fill the GPU better, smaller ones overlap the

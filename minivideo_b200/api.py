@@ -19,7 +19,7 @@ EXPORTS = (
     "mvg_create", "mvg_destroy", "mvg_last_error", "mvg_set_sps", "mvg_build_level_scale",
     "mvg_upload", "mvg_clone_slot", "mvg_run", "mvg_run_rgb", "mvg_set_pipeline_mode", "mvg_sync", "mvg_get_timing", "mvg_mark", "mvg_mark_elapsed",
     "mvg_download_yuv420", "mvg_download_rgb", "mvg_download_residual", "mvg_decode_host",
-    "mvg_pack_batch", "mvg_decode_host_packed",
+    "mvg_pack_batch", "mvg_decode_host_packed", "mvg_submit", "mvg_submit_packed", "mvg_wait", "mvg_poll",
     "mvg_device_count", "mvg_set_pipeline", "mvg_host_alloc", "mvg_host_free", "mvg_width", "mvg_height", "mvg_max_pics", "mvg_sm_count",
 )
 
@@ -86,6 +86,10 @@ def load_library() -> C.CDLL:
     lib.mvg_decode_host.argtypes = [vp, C.POINTER(Batch), vp, vp, i32]
     lib.mvg_pack_batch.argtypes = [vp, i32, i32, vp, vp, vp, vp, C.c_size_t, i32]
     lib.mvg_decode_host_packed.argtypes = [vp, C.POINTER(PackedBatch), vp, vp, i32]
+    lib.mvg_submit.argtypes = [vp, C.POINTER(Batch), vp, vp, i32, C.POINTER(C.c_int32)]
+    lib.mvg_submit_packed.argtypes = [vp, C.POINTER(PackedBatch), vp, vp, i32, C.POINTER(C.c_int32)]
+    lib.mvg_wait.argtypes = [vp, i32]
+    lib.mvg_poll.argtypes = [vp, i32, C.POINTER(C.c_int)]
     lib.mvg_set_pipeline.argtypes = [vp, i32]
     lib.mvg_host_alloc.argtypes = [C.c_size_t]
     lib.mvg_host_alloc.restype = vp
@@ -253,6 +257,24 @@ class Context:
         self._ck(self.lib.mvg_download_residual(self.handle, slot, out.ctypes.data))
         return out
 
+    def submit(self, soa, yuv_out, rgb_out, rgb_scale=1, keep: list | None = None) -> int:
+        """mvg_submit(): returns the ticket.  `keep` receives the arrays that must stay alive until wait()."""
+        keep = keep if keep is not None else []
+        b = _batch_of(soa, keep)
+        self._keep_alive = getattr(self, "_keep_alive", [])
+        self._keep_alive.append(keep)
+        t = C.c_int32(-1)
+        self._ck(self.lib.mvg_submit(self.handle, C.byref(b), _ptr(yuv_out), _ptr(rgb_out), rgb_scale, C.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket: int):
+        self._ck(self.lib.mvg_wait(self.handle, ticket))
+
+    def poll(self, ticket: int) -> bool:
+        done = C.c_int(0)
+        self._ck(self.lib.mvg_poll(self.handle, ticket, C.byref(done)))
+        return bool(done.value)
+
     def set_pipeline(self, chunk_pics: int):
         self._ck(self.lib.mvg_set_pipeline(self.handle, chunk_pics))
 
@@ -269,6 +291,17 @@ class Context:
         self._ck(self.lib.mvg_decode_host_packed(self.handle, C.byref(packed.struct),
                                                  yuv_out.ctypes.data if yuv_out is not None else None,
                                                  rgb_out.ctypes.data if rgb_out is not None else None, rgb_scale))
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def submit_packed(ctx: "Context", packed: "Packed", yuv_out, rgb_out, rgb_scale=1) -> int:
+    """mvg_submit_packed(): returns the ticket; ctx.wait(ticket) completes it."""
+    t = C.c_int32(-1)
+    ctx._ck(ctx.lib.mvg_submit_packed(ctx.handle, C.byref(packed.struct), _ptr(yuv_out), _ptr(rgb_out), rgb_scale, C.byref(t)))
+    return int(t.value)
 
 
 class Packed:

@@ -385,15 +385,18 @@ static int generation_of(mvf_stream *s, const nal_t *nl, const sps_t *sps_tab, c
     br_ue(&b); br_ue(&b);                                   /* first_mb_in_slice, slice_type */
     const uint32_t pid = br_ue(&b);
     if (br_overrun(&b) || pid >= MVF_MAX_PPS) { sfail(s, MVG_FAILURE, "slice header: pic_parameter_set_id out of range"); return -1; }
+    /* a generation index of -1 / -2 = the picture cannot be decoded (MVG_FAILURE / MVG_UNSUPPORTED) */
     const pps_t *pps = &pps_tab[pid];
     if (!pps->valid) {
         if (pps->err_code == 0) sfail(s, MVG_FAILURE, "slice refers to PPS %u, which the stream has not delivered", pid);
-        return -1;                                          /* a PPS that failed to parse left its message in s->err */
+        else sfail(s, pps->err_code, "slice refers to PPS %u, which is %s", pid, pps->err_code == MVG_UNSUPPORTED ? "unsupported" : "damaged");
+        return pps->err_code == MVG_UNSUPPORTED ? -2 : -1;
     }
     const sps_t *sps = &sps_tab[pps->sps_id];
     if (!sps->valid) {
         if (sps->err_code == 0) sfail(s, MVG_FAILURE, "PPS %u refers to SPS %d, which the stream has not delivered", pid, pps->sps_id);
-        return -1;
+        else sfail(s, sps->err_code, "PPS %u refers to SPS %d, which is %s", pid, pps->sps_id, sps->err_code == MVG_UNSUPPORTED ? "unsupported" : "damaged");
+        return sps->err_code == MVG_UNSUPPORTED ? -2 : -1;
     }
     paramgen_t g;
     memset(&g, 0, sizeof g);
@@ -549,19 +552,32 @@ static void build_level_scale(const uint8_t l4[3][16], const uint8_t l8[64], int
             }
 }
 
-int mvf_get_info(const mvf_stream *s, mvf_info *o)
+int mvf_get_generation_info(const mvf_stream *s, int gen, mvf_info *o)
 {
-    if (!s || !o) return MVG_FAILURE;
+    if (!s || !o || gen < 0 || gen >= s->n_gens) return MVG_FAILURE;
+    const sps_t *sps = &s->gens[gen].sps; const pps_t *pps = &s->gens[gen].pps;
     memset(o, 0, sizeof *o);
-    o->width_mbs = s->sps.width_mbs; o->height_mbs = s->sps.height_mbs;
-    o->profile_idc = s->sps.profile_idc; o->level_idc = s->sps.level_idc;
-    o->n_idr = s->n_idr; o->transform_8x8_mode = s->pps.transform8x8;
-    o->cb_qp_offset = s->pps.cb_off; o->cr_qp_offset = s->pps.cr_off; o->pic_init_qp = s->pps.init_qp;
-    o->crop_left = s->sps.crop[0]; o->crop_right = s->sps.crop[1]; o->crop_top = s->sps.crop[2]; o->crop_bottom = s->sps.crop[3];
+    o->width_mbs = sps->width_mbs; o->height_mbs = sps->height_mbs;
+    o->profile_idc = sps->profile_idc; o->level_idc = sps->level_idc;
+    o->n_idr = s->n_idr; o->transform_8x8_mode = pps->transform8x8;
+    o->cb_qp_offset = pps->cb_off; o->cr_qp_offset = pps->cr_off; o->pic_init_qp = pps->init_qp;
+    o->crop_left = sps->crop[0]; o->crop_right = sps->crop[1]; o->crop_top = sps->crop[2]; o->crop_bottom = sps->crop[3];
+    o->n_generations = s->n_gens; o->generation = gen;
     uint8_t l4[3][16];
-    for (int c = 0; c < 3; c++) memcpy(l4[c], s->sps.list4[c], 16);           /* intra Y, Cb, Cr */
-    build_level_scale(l4, s->sps.list8[0], o->level_scale4x4, o->level_scale8x8);
+    for (int c = 0; c < 3; c++) memcpy(l4[c], sps->list4[c], 16);           /* intra Y, Cb, Cr */
+    build_level_scale(l4, sps->list8[0], o->level_scale4x4, o->level_scale8x8);
     return MVG_SUCCESS;
+}
+
+/* the parameters of the first decodable IDR picture (all there is for a stream that never changes them) */
+int mvf_get_info(const mvf_stream *s, mvf_info *o) { return mvf_get_generation_info(s, 0, o); }
+
+int mvf_generation_count(const mvf_stream *s) { return s ? s->n_gens : 0; }
+
+int mvf_picture_generation(const mvf_stream *s, int idr_index)
+{
+    if (!s || idr_index < 0 || idr_index >= s->n_idr) return -1;
+    return s->idr_gen[idr_index] < 0 ? -1 : s->idr_gen[idr_index];
 }
 
 /* demuxer/filter.c:52-215, on IDR indices instead of bitstream-map samples */
@@ -747,10 +763,16 @@ static int wfail(worker_t *w, int code, const char *fmt, ...)
     return code;
 }
 
-static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_t pic_slot)
+static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_t pic_slot, int want_w, int want_h)
 {
     const mvf_stream *s = w->s;
-    const sps_t *sps = &s->sps; const pps_t *pps = &s->pps;
+    const int gen = s->idr_gen[idr_index];
+    if (gen < 0)
+        return wfail(w, gen == -2 ? MVG_UNSUPPORTED : MVG_FAILURE, "picture %d: no usable SPS/PPS (missing, damaged or unsupported parameter set)", idr_index);
+    const sps_t *sps = &s->gens[gen].sps; const pps_t *pps = &s->gens[gen].pps;
+    if (sps->width_mbs != want_w || sps->height_mbs != want_h)
+        return wfail(w, MVG_FAILURE, "picture %d is %dx%d macroblocks, the batch %dx%d: parse each parameter generation in a call of its own",
+                     idr_index, sps->width_mbs, sps->height_mbs, want_w, want_h);
     const nal_t *nl = &s->nals[s->idr[idr_index]];
     if (nl->size + RBSP_SLACK > w->rbsp_cap) {
         w->rbsp_cap = nl->size * 2 + RBSP_SLACK;
@@ -902,15 +924,6 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
     return MVG_SUCCESS;
 }
 
-typedef struct {
-    mvf_stream *s; const int32_t *indices; int first, count; const mvf_batch *out;
-    int next; int rc; char err[200];
-    pthread_mutex_t mu;
-    /* packed output (mvf_parse_pictures_packed): per picture, the words it needs */
-    const mvf_packed_batch *pk;
-    uint16_t **pic_words; uint64_t *pic_count;
-} job_t;
-
 /* the 384 levels of one macroblock -> chunk bitmap, masks and non-zero levels appended to the worker's words */
 static int pack_mb(worker_t *w, size_t m, uint32_t touched)
 {
@@ -961,109 +974,301 @@ static int pack_mb(worker_t *w, size_t m, uint32_t touched)
     return 1;
 }
 
-static void *worker_main(void *arg)
+/* ------------------------------------------------------------------------ */
+/* the parser: persistent worker threads, one IDR slice per thread at a time  */
+
+typedef struct { uint16_t *w; size_t n, cap; } picbuf_t;
+
+struct mvf_parser {
+    mvf_stream *s;
+    int n_workers;                      /* threads started (0: everything runs in the caller) */
+    int scratch_count;                  /* entries of workers[] */
+    pthread_t *th;
+    worker_t *workers;                  /* n_workers, or 1 for the inline case */
+    pthread_mutex_t mu;
+    pthread_cond_t cv_work, cv_done;
+    unsigned job_seq; int quit, active;
+    /* the job in flight */
+    const int32_t *indices; int first, count, W, H, strict;
+    const mvf_batch *out; const mvf_packed_batch *pk; int32_t *status;
+    int next;                           /* next picture to claim (atomic) */
+    uint8_t *done; int done_cap;        /* per picture: finished (release/acquire) */
+    picbuf_t *pic; int pic_cap;         /* packed output: the words of each picture, kept between calls */
+    int rc; char err[200];              /* first failure */
+};
+
+static int worker_scratch(worker_t *w, const mvf_stream *s)
 {
-    job_t *j = arg;
-    const mvf_stream *s = j->s;
-    size_t N = (size_t)s->sps.width_mbs * s->sps.height_mbs;
-    worker_t w;
-    memset(&w, 0, sizeof w);
-    w.s = s;
-    w.tot_luma = malloc(N * 16); w.tot_chroma[0] = malloc(N * 4); w.tot_chroma[1] = malloc(N * 4);
-    w.mode_grid = malloc(N * 16);
+    const size_t N = (size_t)s->max_mbs;
+    memset(w, 0, sizeof *w);
+    w->s = s;
+    w->tot_luma = malloc(N * 16); w->tot_chroma[0] = malloc(N * 4); w->tot_chroma[1] = malloc(N * 4);
+    w->mode_grid = malloc(N * 16);
+    return w->tot_luma && w->tot_chroma[0] && w->tot_chroma[1] && w->mode_grid;
+}
+static void worker_release(worker_t *w)
+{
+    free(w->rbsp); free(w->tot_luma); free(w->tot_chroma[0]); free(w->tot_chroma[1]); free(w->mode_grid);
+    memset(w, 0, sizeof *w);
+}
+
+/* a picture that could not be parsed leaves a slot the kernels can still run over: no levels, all-zero side information */
+static void blank_picture(const mvf_parser *p, int i)
+{
+    const size_t N = (size_t)p->W * p->H, o = (size_t)i * N;
+    if (p->pk) {
+        memset(p->pk->mb_kind + o, 0, N); memset(p->pk->i16_mode + o, 0, N); memset(p->pk->chroma_mode + o, 0, N);
+        memset(p->pk->qp_y + o, 0, N); memset(p->pk->luma_modes + o * 16, 0, N * 16);
+        memset(p->pk->nz_blocks + o, 0, N * 4); memset(p->pk->word_off + o, 0, N * 4);
+    } else {
+        memset(p->out->mb_kind + o, 0, N); memset(p->out->i16_mode + o, 0, N); memset(p->out->chroma_mode + o, 0, N);
+        memset(p->out->qp_y + o, 0, N); memset(p->out->cbp + o, 0, N); memset(p->out->luma_modes + o * 16, 0, N * 16);
+        memset(p->out->coeff + o * 384, 0, N * 768);
+    }
+}
+
+/* claim pictures of the current job until none is left */
+static void work_on_job(mvf_parser *p, worker_t *w)
+{
+    const mvf_stream *s = p->s;
+    const size_t N = (size_t)p->W * p->H;
     mvf_batch view;                                         /* packed output: the small arrays of the output batch */
     memset(&view, 0, sizeof view);
-    if (j->pk) {
-        w.packed = 1;
-        view.mb_kind = j->pk->mb_kind; view.i16_mode = j->pk->i16_mode; view.chroma_mode = j->pk->chroma_mode;
-        view.qp_y = j->pk->qp_y; view.luma_modes = j->pk->luma_modes;
+    w->packed = p->pk != NULL;
+    if (p->pk) {
+        view.mb_kind = p->pk->mb_kind; view.i16_mode = p->pk->i16_mode; view.chroma_mode = p->pk->chroma_mode;
+        view.qp_y = p->pk->qp_y; view.luma_modes = p->pk->luma_modes;
     }
     for (;;) {
-        pthread_mutex_lock(&j->mu);
-        int i = j->rc == MVG_SUCCESS ? j->next++ : j->count;
-        pthread_mutex_unlock(&j->mu);
-        if (i >= j->count) break;
-        int idx = j->indices ? j->indices[i] : j->first + i;
-        int rc = (idx < 0 || idx >= s->n_idr) ? wfail(&w, MVG_FAILURE, "IDR index %d out of range (0..%d)", idx, s->n_idr - 1)
-                                              : 1;
-        if (rc == 1) {
-            if (j->pk) {
-                w.pk_nzb = j->pk->nz_blocks + (size_t)i * N; w.pk_off = j->pk->word_off + (size_t)i * N;
-                w.pk_words = NULL; w.pk_n = 0; w.pk_cap = 0;
+        const int i = __atomic_fetch_add(&p->next, 1, __ATOMIC_RELAXED);
+        if (i >= p->count) break;
+        const int idx = p->indices ? p->indices[i] : p->first + i;
+        int rc = (idx < 0 || idx >= s->n_idr) ? wfail(w, MVG_FAILURE, "IDR index %d out of range (0..%d)", idx, s->n_idr - 1)
+                                              : MVG_SUCCESS;
+        if (rc == MVG_SUCCESS) {
+            if (p->pk) {
+                w->pk_nzb = p->pk->nz_blocks + (size_t)i * N; w->pk_off = p->pk->word_off + (size_t)i * N;
+                w->pk_words = p->pic[i].w; w->pk_n = 0; w->pk_cap = p->pic[i].cap;
             }
-            rc = parse_picture(&w, idx, j->pk ? &view : j->out, (size_t)i);
-            if (j->pk) { j->pic_words[i] = w.pk_words; j->pic_count[i] = w.pk_n; }
-        }
+            rc = parse_picture(w, idx, p->pk ? &view : p->out, (size_t)i, p->W, p->H);
+            if (p->pk) { p->pic[i].w = w->pk_words; p->pic[i].cap = w->pk_cap; p->pic[i].n = rc == MVG_SUCCESS ? w->pk_n : 0; }
+        } else if (p->pk) p->pic[i].n = 0;
+        if (p->status) p->status[i] = rc;
         if (rc != MVG_SUCCESS) {
-            pthread_mutex_lock(&j->mu);
-            if (j->rc == MVG_SUCCESS) { j->rc = rc; memcpy(j->err, w.err, sizeof j->err); }
-            pthread_mutex_unlock(&j->mu);
+            if (!p->strict) blank_picture(p, i);
+            pthread_mutex_lock(&p->mu);
+            if (p->rc == MVG_SUCCESS) { p->rc = rc; memcpy(p->err, w->err, sizeof p->err); }
+            pthread_mutex_unlock(&p->mu);
+            if (p->strict) __atomic_store_n(&p->next, p->count, __ATOMIC_RELAXED);      /* all or nothing: stop handing out work */
+        }
+        __atomic_store_n(&p->done[i], 1, __ATOMIC_RELEASE);
+        if (p->n_workers) { pthread_mutex_lock(&p->mu); pthread_cond_broadcast(&p->cv_done); pthread_mutex_unlock(&p->mu); }
+    }
+}
+
+typedef struct { mvf_parser *p; int k; } worker_arg_t;
+
+static void *worker_main(void *arg)
+{
+    worker_arg_t *a = arg;
+    mvf_parser *p = a->p;
+    worker_t *w = &p->workers[a->k];
+    free(a);
+    unsigned seen = 0;
+    for (;;) {
+        pthread_mutex_lock(&p->mu);
+        while (!p->quit && p->job_seq == seen) pthread_cond_wait(&p->cv_work, &p->mu);
+        if (p->quit) { pthread_mutex_unlock(&p->mu); return NULL; }
+        seen = p->job_seq;
+        pthread_mutex_unlock(&p->mu);
+        work_on_job(p, w);
+        pthread_mutex_lock(&p->mu);
+        if (--p->active == 0) pthread_cond_broadcast(&p->cv_done);
+        pthread_mutex_unlock(&p->mu);
+    }
+}
+
+int mvf_parser_create(mvf_stream *s, int n_threads, mvf_parser **out)
+{
+    if (!out) return MVG_FAILURE;
+    *out = NULL;
+    if (!s) return MVG_FAILURE;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    mvf_parser *p = calloc(1, sizeof *p);
+    if (!p) return sfail(s, MVG_FAILURE, "mvf_parser_create: out of memory");
+    p->s = s;
+    pthread_mutex_init(&p->mu, NULL); pthread_cond_init(&p->cv_work, NULL); pthread_cond_init(&p->cv_done, NULL);
+    const int n_scratch = n_threads;
+    p->workers = calloc((size_t)n_scratch, sizeof *p->workers);
+    p->th = calloc((size_t)n_threads, sizeof *p->th);
+    int ok = p->workers && p->th;
+    if (p->workers) p->scratch_count = n_scratch;
+    for (int k = 0; ok && k < n_scratch; k++) ok = worker_scratch(&p->workers[k], s);
+    if (!ok) { mvf_parser_destroy(p); return sfail(s, MVG_FAILURE, "mvf_parser_create: out of memory (%d workers, %d macroblocks per picture)", n_threads, s->max_mbs); }
+    if (n_threads > 1)
+        for (int k = 0; k < n_threads; k++) {
+            worker_arg_t *a = malloc(sizeof *a);
+            if (!a) break;
+            a->p = p; a->k = k;
+            if (pthread_create(&p->th[p->n_workers], NULL, worker_main, a) != 0) { free(a); break; }
+            p->n_workers++;
+        }
+    /* no thread could be started (or one was asked for): the caller's thread parses, with workers[0]'s scratch */
+    *out = p;
+    return MVG_SUCCESS;
+}
+
+int mvf_parser_destroy(mvf_parser *p)
+{
+    if (!p) return MVG_FAILURE;
+    pthread_mutex_lock(&p->mu); p->quit = 1; pthread_cond_broadcast(&p->cv_work); pthread_mutex_unlock(&p->mu);
+    for (int k = 0; k < p->n_workers; k++) pthread_join(p->th[k], NULL);
+    free(p->th);
+    if (p->workers) { for (int k = 0; k < p->scratch_count; k++) worker_release(&p->workers[k]); free(p->workers); }
+    for (int i = 0; i < p->pic_cap; i++) free(p->pic[i].w);
+    free(p->pic); free(p->done);
+    pthread_mutex_destroy(&p->mu); pthread_cond_destroy(&p->cv_work); pthread_cond_destroy(&p->cv_done);
+    free(p);
+    return MVG_SUCCESS;
+}
+
+const char *mvf_parser_last_error(const mvf_parser *p) { return p ? p->err : ""; }
+
+/* run one job: `out` xor `pk` is set */
+static int parser_run(mvf_parser *p, const int32_t *indices, int first, int count, const mvf_batch *out, mvf_packed_batch *pk,
+                      int32_t *status)
+{
+    mvf_stream *s = p->s;
+    p->rc = MVG_SUCCESS; p->err[0] = 0;
+    if (count == 0) return MVG_SUCCESS;
+    /* geometry of the call: that of the first requested picture that has any */
+    p->W = p->H = 0;
+    for (int i = 0; i < count && !p->W; i++) {
+        const int idx = indices ? indices[i] : first + i;
+        if (idx >= 0 && idx < s->n_idr && s->idr_gen[idx] >= 0) { p->W = s->gens[s->idr_gen[idx]].sps.width_mbs; p->H = s->gens[s->idr_gen[idx]].sps.height_mbs; }
+    }
+    if (!p->W) { p->W = s->gens[0].sps.width_mbs; p->H = s->gens[0].sps.height_mbs; }
+    if (count > p->done_cap) {
+        uint8_t *d = realloc(p->done, (size_t)count);
+        if (!d) { snprintf(p->err, sizeof p->err, "out of memory"); return MVG_FAILURE; }
+        p->done = d; p->done_cap = count;
+    }
+    memset(p->done, 0, (size_t)count);
+    if (pk && count > p->pic_cap) {
+        picbuf_t *np = realloc(p->pic, sizeof(picbuf_t) * (size_t)count);
+        if (!np) { snprintf(p->err, sizeof p->err, "out of memory"); return MVG_FAILURE; }
+        memset(np + p->pic_cap, 0, sizeof(picbuf_t) * (size_t)(count - p->pic_cap));
+        p->pic = np; p->pic_cap = count;
+    }
+    p->indices = indices; p->first = first; p->count = count; p->out = out; p->pk = pk; p->status = status;
+    p->strict = status == NULL;
+    __atomic_store_n(&p->next, 0, __ATOMIC_RELAXED);
+
+    const int threaded = p->n_workers > 0 && count > 1;
+    if (threaded) {
+        pthread_mutex_lock(&p->mu);
+        p->active = p->n_workers; p->job_seq++;
+        pthread_cond_broadcast(&p->cv_work);
+        pthread_mutex_unlock(&p->mu);
+    } else {
+        const int keep = p->n_workers;
+        p->n_workers = 0;                   /* no signalling inside work_on_job */
+        work_on_job(p, &p->workers[0]);
+        p->n_workers = keep;
+    }
+    int rc = MVG_SUCCESS;
+    if (pk) {
+        /* the words of the pictures, in picture order, while the workers are still parsing the later ones */
+        pk->pic_off[0] = 0;
+        for (int i = 0; i < count; i++) {
+            int abandoned = 0;      /* all-or-nothing mode: after a failure the pictures not yet claimed never get done */
+            if (threaded && !__atomic_load_n(&p->done[i], __ATOMIC_ACQUIRE)) {
+                pthread_mutex_lock(&p->mu);
+                while (!__atomic_load_n(&p->done[i], __ATOMIC_ACQUIRE) && !(p->strict && p->rc != MVG_SUCCESS))
+                    pthread_cond_wait(&p->cv_done, &p->mu);
+                abandoned = !__atomic_load_n(&p->done[i], __ATOMIC_ACQUIRE);
+                pthread_mutex_unlock(&p->mu);
+            } else if (!threaded && !p->done[i]) abandoned = 1;
+            if (abandoned) {
+                for (int k = i; k < count; k++) pk->pic_off[k + 1] = pk->pic_off[i];
+                break;
+            }
+            const uint64_t at = pk->pic_off[i], n = p->pic[i].n;
+            pk->pic_off[i + 1] = at + n;
+            if (n && at + n <= pk->words_capacity) memcpy(pk->words + at, p->pic[i].w, (size_t)n * sizeof(uint16_t));
+        }
+        pk->words_needed = (size_t)pk->pic_off[count];
+        if (pk->pic_off[count] > pk->words_capacity) {
+            rc = MVG_FAILURE;
+            snprintf(p->err, sizeof p->err, "mvf_parse_pictures_packed: %llu words needed, capacity %zu",
+                     (unsigned long long)pk->pic_off[count], pk->words_capacity);
         }
     }
-    free(w.rbsp); free(w.tot_luma); free(w.tot_chroma[0]); free(w.tot_chroma[1]); free(w.mode_grid);
-    return NULL;
-}
-
-static int run_job(mvf_stream *s, job_t *j, int n_threads)
-{
-    if (n_threads < 1) n_threads = 1;
-    if (n_threads > j->count) n_threads = j->count;
-    if (n_threads > 256) n_threads = 256;
-    j->rc = MVG_SUCCESS;
-    pthread_mutex_init(&j->mu, NULL);
-    if (n_threads == 1) worker_main(j);
-    else {
-        pthread_t th[256];
-        int started = 0;
-        for (int t = 0; t < n_threads; t++)
-            if (pthread_create(&th[started], NULL, worker_main, j) == 0) started++;
-        if (started == 0) worker_main(j);
-        for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+    if (threaded) {
+        pthread_mutex_lock(&p->mu);
+        while (p->active) pthread_cond_wait(&p->cv_done, &p->mu);
+        pthread_mutex_unlock(&p->mu);
     }
-    pthread_mutex_destroy(&j->mu);
-    if (j->rc != MVG_SUCCESS) memcpy(s->err, j->err, sizeof j->err);
-    return j->rc;
+    if (rc == MVG_SUCCESS && p->strict) rc = p->rc;         /* tolerant mode: per-picture codes are in status[] */
+    return rc;
 }
 
+static void publish_error(mvf_parser *p)
+{
+    pthread_mutex_lock(&p->s->err_mu);
+    memcpy(p->s->err, p->err, sizeof p->err);
+    pthread_mutex_unlock(&p->s->err_mu);
+}
+
+int mvf_parser_parse(mvf_parser *p, const int32_t *indices, int first, int count, mvf_batch *out)
+{
+    if (!p || !out || count < 0) return MVG_FAILURE;
+    if (!out->mb_kind || !out->i16_mode || !out->chroma_mode || !out->qp_y || !out->cbp || !out->luma_modes || !out->coeff) {
+        snprintf(p->err, sizeof p->err, "mvf_parse_pictures: a batch pointer is NULL");
+        publish_error(p);
+        return MVG_FAILURE;
+    }
+    out->n_pics = count;
+    const int rc = parser_run(p, indices, first, count, out, NULL, out->status);
+    if (p->err[0]) publish_error(p);
+    return rc;
+}
+
+int mvf_parser_parse_packed(mvf_parser *p, const int32_t *indices, int first, int count, mvf_packed_batch *out)
+{
+    if (!p || !out || count < 0) return MVG_FAILURE;
+    if (!out->mb_kind || !out->i16_mode || !out->chroma_mode || !out->qp_y || !out->luma_modes || !out->nz_blocks ||
+        !out->word_off || !out->pic_off || !out->words) {
+        snprintf(p->err, sizeof p->err, "mvf_parse_pictures_packed: a batch pointer is NULL");
+        publish_error(p);
+        return MVG_FAILURE;
+    }
+    out->n_pics = count;
+    out->pic_off[0] = 0;
+    out->words_needed = 0;
+    const int rc = parser_run(p, indices, first, count, NULL, out, out->status);
+    if (p->err[0]) publish_error(p);
+    return rc;
+}
+
+/* one-shot forms: a parser for the duration of the call */
 int mvf_parse_pictures(mvf_stream *s, const int32_t *indices, int first, int count, mvf_batch *out, int n_threads)
 {
     if (!s || !out || count < 0) return MVG_FAILURE;
-    if (!out->mb_kind || !out->i16_mode || !out->chroma_mode || !out->qp_y || !out->cbp || !out->luma_modes || !out->coeff)
-        return sfail(s, MVG_FAILURE, "mvf_parse_pictures: a batch pointer is NULL");
-    out->n_pics = count;
-    if (count == 0) return MVG_SUCCESS;
-    job_t j;
-    memset(&j, 0, sizeof j);
-    j.s = s; j.indices = indices; j.first = first; j.count = count; j.out = out;
-    return run_job(s, &j, n_threads);
+    mvf_parser *p = NULL;
+    if (mvf_parser_create(s, n_threads < count ? n_threads : count, &p) != MVG_SUCCESS) return MVG_FAILURE;
+    const int rc = mvf_parser_parse(p, indices, first, count, out);
+    mvf_parser_destroy(p);
+    return rc;
 }
 
 int mvf_parse_pictures_packed(mvf_stream *s, const int32_t *indices, int first, int count, mvf_packed_batch *out, int n_threads)
 {
     if (!s || !out || count < 0) return MVG_FAILURE;
-    if (!out->mb_kind || !out->i16_mode || !out->chroma_mode || !out->qp_y || !out->luma_modes || !out->nz_blocks ||
-        !out->word_off || !out->pic_off || !out->words)
-        return sfail(s, MVG_FAILURE, "mvf_parse_pictures_packed: a batch pointer is NULL");
-    out->n_pics = count;
-    out->pic_off[0] = 0;
-    if (count == 0) return MVG_SUCCESS;
-    job_t j;
-    memset(&j, 0, sizeof j);
-    j.s = s; j.indices = indices; j.first = first; j.count = count; j.pk = out;
-    j.pic_words = calloc((size_t)count, sizeof *j.pic_words);
-    j.pic_count = calloc((size_t)count, sizeof *j.pic_count);
-    if (!j.pic_words || !j.pic_count) { free(j.pic_words); free(j.pic_count); return sfail(s, MVG_FAILURE, "mvf_parse_pictures_packed: out of memory"); }
-    int rc = run_job(s, &j, n_threads);
-    if (rc == MVG_SUCCESS) {
-        for (int i = 0; i < count; i++) out->pic_off[i + 1] = out->pic_off[i] + j.pic_count[i];
-        if (out->pic_off[count] > out->words_capacity)
-            rc = sfail(s, MVG_FAILURE, "mvf_parse_pictures_packed: %llu words needed, capacity %zu",
-                       (unsigned long long)out->pic_off[count], out->words_capacity);
-        else
-            for (int i = 0; i < count; i++)
-                memcpy(out->words + out->pic_off[i], j.pic_words[i], (size_t)j.pic_count[i] * sizeof(uint16_t));
-    }
-    for (int i = 0; i < count; i++) free(j.pic_words[i]);
-    free(j.pic_words); free(j.pic_count);
+    mvf_parser *p = NULL;
+    if (mvf_parser_create(s, n_threads < count ? n_threads : count, &p) != MVG_SUCCESS) return MVG_FAILURE;
+    const int rc = mvf_parser_parse_packed(p, indices, first, count, out);
+    mvf_parser_destroy(p);
     return rc;
 }

@@ -60,13 +60,27 @@ int main(int argc, char **argv)
     }
     if (!in || n_want < 1 || scale < 1 || batch < 0) { usage(); return 2; }
 
+    /* the whole stream in memory; read in growing chunks so that pipes and FIFOs (no size, no seeking) work too */
     FILE *f = fopen(in, "rb");
     if (!f) { fprintf(stderr, "mv_thumbnailer: cannot open '%s'\n", in); return 1; }
-    fseek(f, 0, SEEK_END);
-    long flen = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    uint8_t *data = malloc((size_t)flen + 8);
-    if (!data || fread(data, 1, (size_t)flen, f) != (size_t)flen) { fprintf(stderr, "mv_thumbnailer: read error\n"); return 1; }
+    size_t cap = 1u << 20, flen = 0;
+    if (fseek(f, 0, SEEK_END) == 0) {
+        const long sz = ftell(f);
+        if (sz > 0) cap = (size_t)sz + 1;               /* + 1: the read that finds end-of-file */
+        if (fseek(f, 0, SEEK_SET) != 0) { fprintf(stderr, "mv_thumbnailer: cannot rewind '%s'\n", in); fclose(f); return 1; }
+    } else clearerr(f);
+    uint8_t *data = malloc(cap + 8);
+    while (data) {
+        const size_t got = fread(data + flen, 1, cap - flen, f);
+        flen += got;
+        if (got == 0) break;
+        if (flen == cap) {
+            uint8_t *nd = realloc(data, cap * 2 + 8);
+            if (!nd) { free(data); data = NULL; break; }
+            data = nd; cap *= 2;
+        }
+    }
+    if (!data || ferror(f)) { fprintf(stderr, "mv_thumbnailer: cannot read '%s'\n", in); free(data); fclose(f); return 1; }
     fclose(f);
 
     /* input base name without directory and extension (import.c: file_name) */
@@ -92,7 +106,7 @@ int main(int argc, char **argv)
     }
 
     int exported = 0;
-    const int ok = mvt_extract(data, (size_t)flen, base, outdir, fmt, n_want, mode, scale, device, threads, batch, &exported);
+    const int ok = mvt_extract(data, flen, base, outdir, fmt, n_want, mode, scale, device, threads, batch, &exported);
     printf("mv_thumbnailer: %d picture(s) exported\n", exported);
     free(data);
     return ok == 1 ? 0 : 1;

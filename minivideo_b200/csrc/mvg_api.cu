@@ -25,7 +25,16 @@
 
 static char g_create_error[512] = "";
 
-#define MVG_PIPE_DEPTH 3       /* slot regions used by mvg_decode_host */
+#define MVG_PIPE_DEPTH 3       /* slot regions used by the end-to-end calls */
+#define MVG_MAX_TICKETS 8      /* submissions in flight (mvg_submit*) */
+
+/* one submission of the end-to-end path: completion event + the host staging of its picture offsets */
+struct MvgTicket {
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    uint64_t *h_picbase = nullptr;      /* pinned; read by asynchronous copies until `done` */
+    int cap = 0;
+};
 #define MVG_WORK_RING  64      /* work counters, one per kernel-2 launch in flight */
 #define MVG_K2_GROUP   1024    /* pictures interleaved row by row in kernel 2's claim order */
 
@@ -53,8 +62,10 @@ struct mvg_ctx {
     /* packed transfer format (allocated by the first mvg_decode_host_packed) */
     uint32_t *d_nzb = nullptr, *d_woff = nullptr;
     uint16_t *d_words = nullptr;
-    uint64_t *d_picbase = nullptr, *h_picbase = nullptr;
-    int h_picbase_cap = 0;
+    uint64_t *d_picbase = nullptr;
+    MvgTicket tickets[MVG_MAX_TICKETS];
+    long long pipe_idx = 0;          /* chunks enqueued so far: region = pipe_idx % depth, across submissions */
+    bool region_used[MVG_PIPE_DEPTH] = {};
     /* intermediates / outputs */
     int16_t *d_resid = nullptr;
     MvgMbCtl *d_ctl = nullptr;
@@ -344,7 +355,7 @@ extern "C" int mvg_destroy(mvg_ctx *ctx)
     cudaFree(ctx->d_tiles); cudaFree(ctx->d_yuv); cudaFree(ctx->d_rgb); cudaFree(ctx->d_halo); cudaFree(ctx->d_work); cudaFree(ctx->d_stats);
     cudaFree(ctx->d_tab); cudaFree(ctx->d_luts);
     cudaFree(ctx->d_nzb); cudaFree(ctx->d_woff); cudaFree(ctx->d_words); cudaFree(ctx->d_picbase);
-    if (ctx->h_picbase) cudaFreeHost(ctx->h_picbase);
+    for (auto &t : ctx->tickets) { if (t.h_picbase) cudaFreeHost(t.h_picbase); if (t.done) cudaEventDestroy(t.done); }
     for (auto ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : ctx->ev_mark) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < MVG_PIPE_DEPTH; i++) {
@@ -383,7 +394,10 @@ extern "C" int mvg_set_sps(mvg_ctx *ctx, int width_mbs, int height_mbs,
     zigzag(8, zz8);
     for (int k = 0; k < 64; k++) t.zz8inv[zz8[k]] = (uint8_t)k;
     t.cb_qp_offset = cb_qp_offset; t.cr_qp_offset = cr_qp_offset;
+    /* the tables are read by kernels that may still be queued (asynchronous submissions): drain first */
+    CK(ctx, cudaStreamSynchronize(ctx->s_h2d));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
     CK(ctx, cudaMemcpy(ctx->d_tab, &t, sizeof t, cudaMemcpyHostToDevice));
     ctx->w_mbs = width_mbs; ctx->h_mbs = height_mbs; ctx->have_sps = true;
     return MVG_SUCCESS;
@@ -756,35 +770,51 @@ extern "C" int mvg_download_residual(mvg_ctx *ctx, int slot, int16_t *residual)
 /* ------------------------------------------------------------------------- */
 /* end-to-end: host SoA in, host pictures out, pipelined over slot regions     */
 
+static int take_ticket(mvg_ctx *ctx, mvg_ticket *out)
+{
+    for (int i = 0; i < MVG_MAX_TICKETS; i++)
+        if (!ctx->tickets[i].busy) {
+            if (!ctx->tickets[i].done) CK(ctx, cudaEventCreateWithFlags(&ctx->tickets[i].done, cudaEventDisableTiming));
+            *out = i;
+            return MVG_SUCCESS;
+        }
+    return fail(ctx, "too many submissions in flight (%d): mvg_wait() for one first", MVG_MAX_TICKETS);
+}
+
 /* chunk loop shared by the dense and the packed entry points: `upload(done, slot0, cnt)` enqueues the H2D
  * copies of pictures [done, done+cnt) into slots [slot0, ..) on ctx->s_h2d, `expand(slot0, cnt)` enqueues
- * whatever must run on ctx->stream before kernel 1 */
+ * whatever must run on ctx->stream before the reconstruction.  Nothing here waits for the device: the chunks of
+ * one submission and of the next one follow each other through the same MVG_PIPE_DEPTH slot regions, ordered by
+ * events (a region's inputs are overwritten after the compute that read them, its outputs after the D2H copy
+ * that read them).  Completion = the event recorded behind the last D2H copy. */
 template <typename Upload, typename Expand>
-static int decode_pipeline(mvg_ctx *ctx, int n_pics, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale, Upload upload, Expand expand)
+static int decode_pipeline(mvg_ctx *ctx, int n_pics, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale, cudaEvent_t done_ev,
+                           Upload upload, Expand expand)
 {
     const int scale = rgb_out ? rgb_scale : 0;
     const size_t n = ctx->n_mb();
     const size_t yuv_sz = n * 384, rgb_sz = scale ? rgb_bytes(ctx, scale) : 0;
     if (yuv_out && ensure_yuv(ctx) != MVG_SUCCESS) return MVG_FAILURE;
-    /* slot regions: MVG_PIPE_DEPTH of them; a region holds at most a third of the context
-     * and at most an eighth of the batch, so that H2D, kernels and D2H of neighbouring
-     * chunks overlap even when the whole batch would fit in one region. */
+    /* slot regions: MVG_PIPE_DEPTH of them, a third of the context each (fixed, so that submissions with different
+     * chunk sizes agree on what a region is); a chunk is at most a region and at most an eighth of the batch, so
+     * that H2D, kernels and D2H of neighbouring chunks overlap even when the whole batch would fit in one region. */
     int depth = MVG_PIPE_DEPTH;
-    int chunk = std::max(1, ctx->max_pics / depth);
-    if (ctx->max_pics < depth) { depth = 1; chunk = ctx->max_pics; }
-    chunk = std::min(chunk, std::max(1, (n_pics + 7) / 8));
-    if (ctx->pipe_chunk > 0) chunk = std::min(ctx->pipe_chunk, std::max(1, ctx->max_pics / depth));
-    int idx = 0;
-    for (int done = 0; done < n_pics; done += chunk, idx++) {
+    if (ctx->max_pics < depth) depth = 1;
+    const int region = std::max(1, ctx->max_pics / depth);
+    int chunk = std::min(region, std::max(1, (n_pics + 7) / 8));
+    if (ctx->pipe_chunk > 0) chunk = std::min(ctx->pipe_chunk, region);
+    for (int done = 0; done < n_pics; done += chunk, ctx->pipe_idx++) {
         const int cnt = std::min(chunk, n_pics - done);
-        const int r = idx % depth, slot0 = r * chunk;
-        /* inputs of region r were last read by the compute of chunk idx-depth */
-        if (idx >= depth) CK(ctx, cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[r], 0));
+        const int r = (int)(ctx->pipe_idx % depth), slot0 = r * region;
+        const bool used = ctx->region_used[r];
+        ctx->region_used[r] = true;
+        /* inputs of region r were last read by the compute of the chunk that used it before */
+        if (used) CK(ctx, cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[r], 0));
         if (upload(done, slot0, cnt) != MVG_SUCCESS) return MVG_FAILURE;
         CK(ctx, cudaEventRecord(ctx->ev_h2d[r], ctx->s_h2d));
-        /* outputs of region r were last read by the D2H of chunk idx-depth */
+        /* outputs of region r were last read by the D2H of the chunk that used it before */
         CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[r], 0));
-        if (idx >= depth) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[r], 0));
+        if (used) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[r], 0));
         if (expand(slot0, cnt) != MVG_SUCCESS) return MVG_FAILURE;
         if (launch_stages(ctx, slot0, cnt, scale, yuv_out != nullptr, ctx->stream, false) != MVG_SUCCESS) return MVG_FAILURE;
         if (yuv_out && launch_planar(ctx, slot0, cnt, ctx->stream) != MVG_SUCCESS) return MVG_FAILURE;
@@ -798,22 +828,54 @@ static int decode_pipeline(mvg_ctx *ctx, int n_pics, uint8_t *yuv_out, uint8_t *
                                     (size_t)cnt * rgb_sz, cudaMemcpyDeviceToHost, ctx->s_d2h));
         CK(ctx, cudaEventRecord(ctx->ev_d2h[r], ctx->s_d2h));
     }
-    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaEventRecord(done_ev, ctx->s_d2h));
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_wait(mvg_ctx *ctx, mvg_ticket ticket)
+{
+    if (!ctx) return MVG_FAILURE;
+    if (ticket < 0 || ticket >= MVG_MAX_TICKETS || !ctx->tickets[ticket].busy) return fail(ctx, "mvg_wait: ticket %d is not in flight", (int)ticket);
+    CK(ctx, cudaSetDevice(ctx->device));
+    ctx->tickets[ticket].busy = false;
+    CK(ctx, cudaEventSynchronize(ctx->tickets[ticket].done));
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_poll(mvg_ctx *ctx, mvg_ticket ticket, int *done)
+{
+    if (!ctx || !done) return MVG_FAILURE;
+    if (ticket < 0 || ticket >= MVG_MAX_TICKETS || !ctx->tickets[ticket].busy) return fail(ctx, "mvg_poll: ticket %d is not in flight", (int)ticket);
+    const cudaError_t e = cudaEventQuery(ctx->tickets[ticket].done);
+    if (e != cudaSuccess && e != cudaErrorNotReady) return fail(ctx, "mvg_poll: %s", cudaGetErrorString(e));
+    *done = e == cudaSuccess;
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_submit(mvg_ctx *ctx, const mvg_batch *b, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale, mvg_ticket *ticket)
+{
+    if (!ctx) return MVG_FAILURE;
+    if (!ticket) return fail(ctx, "mvg_submit: ticket is NULL");
+    if (check_batch(ctx, b, "mvg_submit") != MVG_SUCCESS) return MVG_FAILURE;
+    if (!ctx->have_sps) return fail(ctx, "mvg_submit: mvg_set_sps() has not been called");
+    if (b->n_pics < 1) return fail(ctx, "mvg_submit: empty batch");
+    if (rgb_out && rgb_scale < 1) return fail(ctx, "mvg_submit: rgb_out given but rgb_scale < 1");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (take_ticket(ctx, ticket) != MVG_SUCCESS) return MVG_FAILURE;
+    MvgTicket &t = ctx->tickets[*ticket];
+    const mvg_batch batch = *b;     /* the arrays must stay valid until mvg_wait(); the structure need not */
+    if (decode_pipeline(ctx, batch.n_pics, yuv_out, rgb_out, rgb_scale, t.done,
+                        [&](int done, int slot0, int cnt) { return upload_async(ctx, &batch, done, slot0, cnt, ctx->s_h2d); },
+                        [&](int, int) { return (int)MVG_SUCCESS; }) != MVG_SUCCESS) return MVG_FAILURE;
+    t.busy = true;
     return MVG_SUCCESS;
 }
 
 extern "C" int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *b, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale)
 {
-    if (!ctx) return MVG_FAILURE;
-    if (check_batch(ctx, b, "mvg_decode_host") != MVG_SUCCESS) return MVG_FAILURE;
-    if (!ctx->have_sps) return fail(ctx, "mvg_decode_host: mvg_set_sps() has not been called");
-    if (b->n_pics < 1) return fail(ctx, "mvg_decode_host: empty batch");
-    if (rgb_out && rgb_scale < 1) return fail(ctx, "mvg_decode_host: rgb_out given but rgb_scale < 1");
-    CK(ctx, cudaSetDevice(ctx->device));
-    return decode_pipeline(ctx, b->n_pics, yuv_out, rgb_out, rgb_scale,
-                           [&](int done, int slot0, int cnt) { return upload_async(ctx, b, done, slot0, cnt, ctx->s_h2d); },
-                           [&](int, int) { return (int)MVG_SUCCESS; });
+    mvg_ticket t;
+    if (mvg_submit(ctx, b, yuv_out, rgb_out, rgb_scale, &t) != MVG_SUCCESS) return MVG_FAILURE;
+    return mvg_wait(ctx, t);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -879,9 +941,10 @@ extern "C" int mvg_pack_batch(const int16_t *coeff, int n_pics, int n_mbs, uint3
     return MVG_SUCCESS;
 }
 
-extern "C" int mvg_decode_host_packed(mvg_ctx *ctx, const mvg_packed_batch *b, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale)
+extern "C" int mvg_submit_packed(mvg_ctx *ctx, const mvg_packed_batch *b, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale, mvg_ticket *ticket)
 {
     if (!ctx) return MVG_FAILURE;
+    if (!ticket) return fail(ctx, "mvg_submit_packed: ticket is NULL");
     if (!b) return fail(ctx, "mvg_decode_host_packed: batch is NULL");
     if (!b->mb_kind || !b->i16_mode || !b->chroma_mode || !b->qp_y || !b->luma_modes || !b->nz_blocks || !b->word_off ||
         !b->pic_off || !b->words)
@@ -898,11 +961,13 @@ extern "C" int mvg_decode_host_packed(mvg_ctx *ctx, const mvg_packed_batch *b, u
         CK(ctx, cudaMalloc((void **)&ctx->d_words, cap * MVG_PACKED_WORDS_PER_MB * sizeof(uint16_t)));
         CK(ctx, cudaMalloc((void **)&ctx->d_picbase, ((size_t)ctx->max_pics * 2 + 2) * sizeof(uint64_t)));
     }
-    if (b->n_pics > ctx->h_picbase_cap) {
-        if (ctx->h_picbase) cudaFreeHost(ctx->h_picbase);
-        ctx->h_picbase = nullptr; ctx->h_picbase_cap = 0;
-        CK(ctx, cudaHostAlloc((void **)&ctx->h_picbase, ((size_t)b->n_pics * 2 + 2) * sizeof(uint64_t), cudaHostAllocDefault));
-        ctx->h_picbase_cap = b->n_pics;
+    if (take_ticket(ctx, ticket) != MVG_SUCCESS) return MVG_FAILURE;
+    MvgTicket &tk = ctx->tickets[*ticket];
+    if (b->n_pics > tk.cap) {
+        if (tk.h_picbase) cudaFreeHost(tk.h_picbase);
+        tk.h_picbase = nullptr; tk.cap = 0;
+        CK(ctx, cudaHostAlloc((void **)&tk.h_picbase, ((size_t)b->n_pics * 2 + 2) * sizeof(uint64_t), cudaHostAllocDefault));
+        tk.cap = b->n_pics;
     }
     for (int p = 0; p < b->n_pics; p++)
         if (b->pic_off[p + 1] < b->pic_off[p] || b->pic_off[p + 1] - b->pic_off[p] > (uint64_t)n * MVG_PACKED_WORDS_PER_MB)
@@ -922,7 +987,7 @@ extern "C" int mvg_decode_host_packed(mvg_ctx *ctx, const mvg_packed_batch *b, u
             CK(ctx, cudaMemcpyAsync(ctx->d_words + base, b->words + w0, (size_t)(w1 - w0) * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
         /* cnt + 1 offsets per chunk (the last one is the end of its words), at twice the picture index so that
          * neighbouring chunks / slot regions do not overlap; host entries are not reused before the final sync */
-        uint64_t *hb = ctx->h_picbase + 2 * (size_t)done;
+        uint64_t *hb = tk.h_picbase + 2 * (size_t)done;
         for (int i = 0; i <= cnt; i++) hb[i] = base + (b->pic_off[done + i] - w0);
         CK(ctx, cudaMemcpyAsync(ctx->d_picbase + 2 * (size_t)slot0, hb, (size_t)(cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         return MVG_SUCCESS;
@@ -938,6 +1003,15 @@ extern "C" int mvg_decode_host_packed(mvg_ctx *ctx, const mvg_packed_batch *b, u
         CK(ctx, cudaGetLastError());
         return MVG_SUCCESS;
     };
-    return decode_pipeline(ctx, b->n_pics, yuv_out, rgb_out, rgb_scale, upload, expand);
+    if (decode_pipeline(ctx, b->n_pics, yuv_out, rgb_out, rgb_scale, tk.done, upload, expand) != MVG_SUCCESS) return MVG_FAILURE;
+    tk.busy = true;
+    return MVG_SUCCESS;
+}
+
+extern "C" int mvg_decode_host_packed(mvg_ctx *ctx, const mvg_packed_batch *b, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale)
+{
+    mvg_ticket t;
+    if (mvg_submit_packed(ctx, b, yuv_out, rgb_out, rgb_scale, &t) != MVG_SUCCESS) return MVG_FAILURE;
+    return mvg_wait(ctx, t);
 }
 

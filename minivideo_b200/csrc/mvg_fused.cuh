@@ -19,16 +19,27 @@
 #include "mvg_kernels.cuh"
 
 #ifndef KF_GROUP
-#define KF_GROUP 2          /* macroblocks transformed together (and written out together in RGB mode) */
+#define KF_GROUP 4          /* macroblocks transformed together: the compaction of non-zero blocks over a group is what
+                               makes the transform stage cheap (2 macroblocks: 6.1 ms, 4: 5.4 ms per 1000 pictures) */
 #endif
 #ifndef KF_WARPS
 #define KF_WARPS 24         /* warps per CTA; one CTA per SM */
 #endif
+#ifndef KF_COMPACT8
+#define KF_COMPACT8 true    /* Intra8x8 blocks through one run-time-indexed copy of the code */
+#endif
+#ifndef KF_POLL_NS
+#define KF_POLL_NS 1000     /* sleep between two looks at the row above while waiting for the distance */
+#endif
+#ifndef KF_STAGGER
+#define KF_STAGGER 12       /* distance (macroblocks) a row keeps from the row above: waited for at the row start and
+                               again whenever the row catches up; the halo prefetch reaches 10 macroblocks ahead */
+#endif
 #define KF_OUT_TILES 0
 #define KF_OUT_RGB   1
-/* RGB staging rows: KF_GROUP x 48 bytes + padding that makes the 8-byte stores of the conversion (lane = 2 y + h,
- * 24 bytes apart) free of bank conflicts: 28 y + 6 h resp. 52 y + 6 h words cover 16 distinct bank pairs */
-#define KF_RGB_STRIDE (KF_GROUP == 2 ? 112 : KF_GROUP * 48 + 16)
+/* RGB staging rows of a PAIR of macroblocks: 2 x 48 bytes + padding that makes the 8-byte stores of the conversion
+ * (lane = 2 y + h, 24 bytes apart) free of bank conflicts: 28 y + 6 h words cover 16 distinct bank pairs */
+#define KF_RGB_STRIDE 112
 
 struct KFParams {
     const uint8_t *mb_kind, *i16_mode, *chroma_mode, *luma_modes;   /* [slot][n_mb](x16), slot 0 */
@@ -50,10 +61,11 @@ struct KFParams {
 struct KFWarpSmem {
     union {
         MvgXfScratch<KF_GROUP> x;                       /* transform stage                                      */
-        uint8_t rgb[16 * KF_RGB_STRIDE];                /* RGB24 rows of the group (prediction stage, KF_OUT_RGB) */
+        uint8_t rgb[16 * KF_RGB_STRIDE];                /* RGB24 rows of a macroblock pair (prediction stage, KF_OUT_RGB) */
     } u;
-    __align__(128) int16_t tile[2][KF_GROUP * 384];     /* levels in -> residual in place; double buffered      */
-    __align__(8) uint64_t mbar[2];
+    __align__(128) int16_t tile[KF_GROUP * 384];        /* levels in -> residual in place; slot j is refilled with macroblock j
+                                                           of the next group as soon as macroblock j has been predicted */
+    __align__(8) uint64_t mbar;
     __align__(16) uint8_t lt[MVG_LT_ROWS * MVG_LT_STRIDE];
     __align__(16) uint8_t ct[2][MVG_CT_PLANE];
     __align__(16) uint8_t n8[MVG_N8_BYTES];
@@ -66,11 +78,12 @@ struct KFWarpSmem {
 /* Persistent warps, one CTA per SM.  A work item is one macroblock row of one picture (claimed from an atomic
  * counter, rows of a picture in order, pictures interleaved: see k2_wavefront for the dependency protocol, which
  * is unchanged: flag-in-data bottom lines, no fences).  A warp walks its row in groups of KF_GROUP macroblocks:
- *   1. the group's levels arrive by one bulk asynchronous copy (TMA 1-D + mbarrier), requested a group ahead;
+ *   1. the group's levels arrive by bulk asynchronous copies (TMA 1-D + mbarrier), 768 bytes per macroblock, each
+ *      requested as soon as its slot is free: right after the macroblock that held it a group earlier is predicted;
  *   2. mvg_xf_group() turns them into the residual in place (kernel 1's code);
  *   3. each macroblock is predicted and reconstructed in the warp's tile (kernel 2's code), its bottom line
  *      published, and then either stored as a 384-byte tile or converted to RGB24 into a staging area;
- *   4. RGB mode: the group's 16 rows x (KF_GROUP x 48) bytes leave as 16-byte stores, whole 32-byte sectors. */
+ *   4. RGB mode: after every second macroblock the pair's 16 rows x 96 bytes leave as 16-byte stores, whole sectors. */
 template <int OUT>
 __global__ void __launch_bounds__(KF_WARPS * 32, 1)
 kf_recon(KFParams p)
@@ -91,7 +104,7 @@ kf_recon(KFParams p)
     for (int i = threadIdx.x; i < (int)(sizeof(MvgLuts) / 16); i += blockDim.x)
         reinterpret_cast<uint4 *>(luts)[i] = __ldg(reinterpret_cast<const uint4 *>(p.luts) + i);
     mvg_xf_load_tables(T, p.tab);
-    if (lane == 0) { mvg_mbar_init(&s.mbar[0], 1); mvg_mbar_init(&s.mbar[1], 1); }
+    if (lane == 0) mvg_mbar_init(&s.mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -106,7 +119,7 @@ kf_recon(KFParams p)
     c.lt = s.lt; c.ct = &s.ct[0][0]; c.n8 = s.n8; c.lut8 = reinterpret_cast<const uint8_t *>(&luts->lut8[0][lane]);
     c.lane = lane;
     c.sel = p.sel;
-    c.resid = reinterpret_cast<const uint8_t *>(s.tile[0]);
+    c.resid = reinterpret_cast<const uint8_t *>(s.tile);
     {
         const int half = lane >> 4, pix = lane & 15, px = pix & 3, py = pix >> 2;
         c.lut4 = lut_addr + (unsigned)lane * 4u;
@@ -165,8 +178,7 @@ kf_recon(KFParams p)
 
     MvgSideInfo side;
     side.init(lane, p.mb_kind, p.i16_mode, p.chroma_mode, p.luma_modes, p.qp_y);
-    unsigned parity = 0;            /* bit b: phase parity of mbar[b] */
-    unsigned it = 0;                /* groups processed by this warp: buffer = it & 1 */
+    unsigned parity = 0;            /* phase parity of the mbarrier: one phase per group */
 
     for (;;) {
         int item = 0;
@@ -179,17 +191,16 @@ kf_recon(KFParams p)
         const int row = within / gsize;
         const int slot = p.first_slot + g0 * p.group + (within - row * gsize);
         const size_t mb0 = (size_t)slot * n_mb + (size_t)row * W;           /* first macroblock of the row */
-        const int16_t *lv_run = p.coeff + mb0 * 384;                        /* levels of the group requested next */
+        const int16_t *lv_row = p.coeff + mb0 * 384;                        /* levels of this row */
 
         /* group 0: levels and side information.  The buffer was last touched by this warp's generic-proxy
          * accesses (residual of an earlier group): order them before the asynchronous write. */
         if (lane == 0) {
             const unsigned bytes = (unsigned)min(KF_GROUP, W) * 768u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mvg_mbar_expect_tx(&s.mbar[it & 1], bytes);
-            mvg_bulk_load(s.tile[it & 1], lv_run, bytes, &s.mbar[it & 1]);
+            mvg_mbar_expect_tx(&s.mbar, bytes);
+            mvg_bulk_load(s.tile, lv_row, bytes, &s.mbar);
         }
-        lv_run += KF_GROUP * 384;
         unsigned nmeta = side.load(lane, (long long)mb0, min(KF_GROUP, W));
 
         uint8_t *wo_run = OUT == KF_OUT_TILES ? p.tiles + mb0 * 384 + wo_off
@@ -200,27 +211,28 @@ kf_recon(KFParams p)
         const int hwords = W * 8;                               /* halo words of a macroblock row */
         uint2 qa = make_uint2(0, epoch), qb = make_uint2(0, epoch);
         if (availB) {
+            if (KF_STAGGER > 0) {
+                /* Slack between the rows of a picture: wait here, once, until the row above is KF_STAGGER macroblocks
+                 * ahead.  Rows that follow each other at the minimum distance (two macroblocks) run in lock step and
+                 * every burst of the row above -- it transforms KF_GROUP macroblocks, then predicts them -- stalls all
+                 * rows below in turn; with slack the per-macroblock check further down almost never fails. */
+                const uint2 *probe = p.halo + (mb0 - W + min(KF_STAGGER, W - 1)) * 8 + 7;
+                while (mvg_ld_relaxed_u64(probe).y != epoch) __nanosleep(2000);
+            }
             if (lane < hwords) qb = mvg_ld_relaxed_u64(ha_run);     /* becomes qa at macroblock 0 */
         }
         unsigned okA = 0;
 
-        for (int g = 0; g < n_groups; g++, it++) {
-            const int buf = it & 1;
+        for (int g = 0; g < n_groups; g++) {
             const unsigned meta = nmeta;
             const int nmb = min(KF_GROUP, W - g * KF_GROUP);
-            if (g + 1 < n_groups) {     /* next group: its buffer held the residual of group g - 1, fully consumed */
-                const int nn = min(KF_GROUP, W - (g + 1) * KF_GROUP);
-                if (lane == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mvg_mbar_expect_tx(&s.mbar[buf ^ 1], (unsigned)nn * 768u);
-                    mvg_bulk_load(s.tile[buf ^ 1], lv_run, (unsigned)nn * 768u, &s.mbar[buf ^ 1]);
-                }
-                lv_run += KF_GROUP * 384;
-                nmeta = side.load(lane, (long long)mb0 + (g + 1) * KF_GROUP, nn);
-            }
-            int16_t *tile = s.tile[buf];
-            mvg_mbar_wait(&s.mbar[buf], (parity >> buf) & 1u);
-            parity ^= 1u << buf;
+            const int n_next = min(KF_GROUP, W - (g + 1) * KF_GROUP);       /* macroblocks of the next group (<= 0: none) */
+            if (n_next > 0) nmeta = side.load(lane, (long long)mb0 + (g + 1) * KF_GROUP, n_next);
+            int16_t *tile = s.tile;
+            mvg_mbar_wait(&s.mbar, parity);
+            parity ^= 1u;
+            /* the next phase collects the next group's copies, which are issued one by one below */
+            if (n_next > 0 && lane == 0) mvg_mbar_expect_tx(&s.mbar, (unsigned)n_next * 768u);
 
             /* ---- levels -> residual, in place (kernel 1's stage) ---- */
             mvg_xf_group<KF_GROUP>(tile, s.u.x, T, meta, nmb, lane);
@@ -240,11 +252,13 @@ kf_recon(KFParams p)
                     const unsigned need = availC ? 0x3FFu : 0xFFu;
                     unsigned have = __funnelshift_r(okA, hj == 3 ? __ballot_sync(MVG_FULL, qb.y == epoch) : 0u, 8 * hj);
                     if ((have & need) != need) {
-                        /* this row has caught up with the row above: poll, sleeping a fraction of a macroblock time */
-                        unsigned ns = K2_POLL_NS;
-                        do {
-                            __nanosleep(ns);
-                            if (ns < 8 * K2_POLL_NS) ns *= 2;
+                        /* This row has caught up with the row above.  Do not follow it at the minimum distance: rows in
+                         * lock step find the words they prefetch a group ahead stale every time and pay a round trip to
+                         * L2 per macroblock.  Fall back until the row above is KF_STAGGER macroblocks ahead again, then
+                         * reload; after that the prefetches hit for the next KF_STAGGER - 8 macroblocks at least. */
+                        const uint2 *probe = p.halo + (mb0 - W + min(mx + max(KF_STAGGER, 2), W - 1)) * 8 + 7;
+                        while (mvg_ld_relaxed_u64(probe).y != epoch) __nanosleep(KF_POLL_NS);
+                        do {    /* every word validates itself: the probe word says nothing about its neighbours */
                             if ((mx & ~3) * 8 + lane < hwords) qa = mvg_ld_relaxed_u64(ha_run);
                             if ((mx & ~3) * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(ha_run + 32);
                             okA = __ballot_sync(MVG_FULL, qa.y == epoch);
@@ -270,7 +284,7 @@ kf_recon(KFParams p)
                 const int kind = cx & 255, i16 = (cx >> 8) & 255, cmode = (cx >> 16) & 255;
                 if (kind == MVG_MB_I16x16)    k2_luma16(c, i16, availA, availB);
                 else if (kind == MVG_MB_I4x4) k2_luma4(c, cy, cz, availA, availB, availC);
-                else                          k2_luma8(c, cy, availA, availB, availC, availD);
+                else                          k2_luma8<KF_COMPACT8>(c, cy, availA, availB, availC, availD);
                 k2_chroma(c, cmode, availA, availB);
                 __syncwarp();
 
@@ -317,27 +331,32 @@ kf_recon(KFParams p)
                         out[3 * k + 1] = __byte_perm(Z, X, 0x7610);           /* G1 B1 R2 G2 */
                         out[3 * k + 2] = __byte_perm(Y, Z, 0x7632);           /* B2 R3 G3 B3 */
                     }
-                    uint2 *d = reinterpret_cast<uint2 *>(rgb_dst + 48 * j);
+                    uint2 *d = reinterpret_cast<uint2 *>(rgb_dst + 48 * (j & 1));
                     d[0] = make_uint2(out[0], out[1]); d[1] = make_uint2(out[2], out[3]); d[2] = make_uint2(out[4], out[5]);
                 }
                 /* next macroblock: row -1, x = 15 / 7 becomes x = -1 */
                 *cn_dst = *cn_src;
                 __syncwarp();
-            }
-            if (OUT == KF_OUT_RGB) {
-                /* the group's 16 rows x (48 nmb) bytes: 16-byte chunks in row-major order over the lanes, so that a
-                 * full group leaves as whole 32-byte sectors (96 bytes per row at a multiple of 96) */
-                const int row_chunks = 3 * KF_GROUP;
-#pragma unroll
-                for (int k = 0; k < (16 * 3 * KF_GROUP + 31) / 32; k++) {
-                    const int ch = lane + 32 * k, r = ch / row_chunks, col = ch - r * row_chunks;
-                    if (ch < 16 * row_chunks && col < 3 * nmb) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(s.u.rgb + r * KF_RGB_STRIDE + col * 16);
-                        *reinterpret_cast<uint4 *>(wo_run + (size_t)r * pitch + col * 16) = v;
-                    }
+                /* this macroblock's residual is spent: its slot takes macroblock j of the next group */
+                if (j < n_next && lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mvg_bulk_load(tile + j * 384, lv_row + (size_t)(mx + KF_GROUP) * 384, 768u, &s.mbar);
                 }
-                wo_run += 48 * KF_GROUP;
-                __syncwarp();
+                if (OUT == KF_OUT_RGB && ((j & 1) || j == nmb - 1)) {
+                    /* the pair's 16 rows x 96 bytes (48 for a lone last macroblock): 16-byte chunks in row-major order over
+                     * the lanes, so that a pair leaves as whole 32-byte sectors (96 bytes per row at a multiple of 96) */
+                    const int n_here = (j & 1) + 1;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const int ch = lane + 32 * k, r = ch / 6, col = ch - r * 6;
+                        if (col < 3 * n_here) {
+                            const uint4 v = *reinterpret_cast<const uint4 *>(s.u.rgb + r * KF_RGB_STRIDE + col * 16);
+                            *reinterpret_cast<uint4 *>(wo_run + (size_t)r * pitch + col * 16) = v;
+                        }
+                    }
+                    wo_run += 96;
+                    __syncwarp();
+                }
             }
         }
     }

@@ -329,7 +329,7 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
 
     /* ---------------- classify the 4x4 blocks, compact the general ones ---------------- */
     int n4 = 0, n8 = 0;
-#pragma unroll
+#pragma unroll 1        /* code size: the fused kernel has to fit the instruction cache */
     for (int r = 0; r < (G * 24 + 31) / 32; r++) {
         const int u = lane + 32 * r, j0 = u / 24, b = u - 24 * j0;
         /* straight-line code: every lane loads a block (its own, or block b of macroblock 0 beyond the last
@@ -393,11 +393,9 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
             const int4 *lq = reinterpret_cast<const int4 *>(T.ls4q + (comp * 52 + qpb) * 16);
             const int4 l0 = lq[0], l1 = lq[1], l2 = lq[2], l3 = lq[3];
             const int ls[16] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w, l2.x, l2.y, l2.z, l2.w, l3.x, l3.y, l3.z, l3.w};
-            if (qpb > 23) {
-#pragma unroll
-                for (int k = 0; k < 16; k++) c[k] = c[k] * ls[k];
-            } else {
-                const int qd = qpb / 6, rnd = 1 << (3 - qd), sh = 4 - qd;
+            {   /* one code path for both halves of h264_transform.c:1112-1123: from qP 24 on the left shift is part of
+                 * ls4q and what remains is (c * LS + 0) >> 0 */
+                const int sh = T.dcsh[qpb], rnd = (1 << sh) >> 1;
 #pragma unroll
                 for (int k = 0; k < 16; k++) c[k] = (c[k] * ls[k] + rnd) >> sh;
             }
@@ -436,13 +434,11 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
                 const unsigned k = ((q < 4 ? zz.x : zz.y) >> (8 * (q & 3))) & 255u;
                 v[q] = (int)in[k] * l8[q];                                  /* quant8x8, h264_transform.c:1256-1284 */
             }
-            if (qp > 35) {
+            {   /* both halves of h264_transform.c:1268-1279 as (v * 2^up + rnd) >> down: up = qP/6 - 6 and rnd = down = 0
+                 * from qP 36 on, else up = 0 (the product wraps exactly like the reference's left shift) */
+                const int up = max(qd8 - 6, 0), down = max(6 - qd8, 0), rnd = (1 << down) >> 1, mul = 1 << up;
 #pragma unroll
-                for (int q = 0; q < 8; q++) v[q] = (int)((unsigned)v[q] << (qd8 - 6));
-            } else {
-                const int rnd = 1 << (5 - qd8), sh = 6 - qd8;
-#pragma unroll
-                for (int q = 0; q < 8; q++) v[q] = (v[q] + rnd) >> sh;
+                for (int q = 0; q < 8; q++) v[q] = (v[q] * mul + rnd) >> down;
             }
             if (row == 0) v[0] += 32;                                       /* rounding of the final >> 6 (:1382) */
             mvg_idct8_1d(v);                                                /* row pass */
@@ -838,9 +834,56 @@ __device__ __forceinline__ void k2_luma8_block(const K2Ctx &c, unsigned modes, u
     __syncwarp();
 }
 
+/* the same with the block index at run time: one copy of the code instead of four (the fused kernel has to fit
+ * the instruction cache), a handful of address instructions more per block */
+__device__ __forceinline__ void k2_luma8_block_rt(const K2Ctx &c, int b8, unsigned modes, unsigned fix, bool availA, bool availB, bool availC)
+{
+    uint8_t *lt = c.lt;
+    const int lane = c.lane;
+    const int org = K2_TO(0, 0) + (b8 & 1) * 8 + (b8 >> 1) * 8 * MVG_LT_STRIDE;
+    const unsigned mode = (modes >> (4 * b8)) & 15u;
+    const bool left = (b8 & 1) ? true : availA, up = (b8 & 2) ? true : availB;
+    const bool tr = b8 == 0 ? availB : (b8 == 1 ? availC : (b8 == 2));
+
+    const int raw = lt[org + (tr ? c.n8tr : c.n8notr)];
+    int prev = __shfl_up_sync(MVG_FULL, raw, 1), next = __shfl_down_sync(MVG_FULL, raw, 1);
+    {
+        const unsigned f2 = b8 == 3 ? 0u : fix >> (2 * b8);
+        if (f2 & 1u) next = raw;
+        if (f2 & 2u) prev = raw;
+    }
+    const int filt = (prev + 2 * raw + next + 2) >> 2;
+    const int fp = __shfl_up_sync(MVG_FULL, filt, 1);
+    int fn = __shfl_down_sync(MVG_FULL, filt, 1);
+    if (lane == 24) fn = filt;
+    const int f2 = (filt + fn + 1) >> 1, f3 = (fp + 2 * filt + fn + 2) >> 2;
+    c.n8[lane] = (uint8_t)filt; c.n8[32 + lane] = (uint8_t)f2; c.n8[64 + lane] = (uint8_t)f3;
+    if (mode == 2) {                                        /* warp-uniform */
+        int v = 0;
+        if (lane < 8 && left) v = filt;
+        if (lane >= 9 && lane < 17 && up) v = filt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MVG_FULL, v, o);
+        v = (left && up) ? (v + 8) >> 4 : (left || up) ? (v + 4) >> 3 : 128;
+        if (lane == 0) c.n8[MVG_N8_DC] = (uint8_t)v;
+    }
+    __syncwarp();
+    const unsigned e = *reinterpret_cast<const unsigned *>(c.lut8 + mode * 128);
+    const unsigned pp = (unsigned)c.n8[e & 0xffffu] | ((unsigned)c.n8[e >> 16] << 16);
+    const unsigned r2 = *reinterpret_cast<const unsigned *>(c.resid + b8 * 128 + lane * 4);
+    *reinterpret_cast<uint16_t *>(lt + org + c.s8) = (uint16_t)__byte_perm(mvg_add_clip8x2(pp, r2), 0, 0x4420);
+    __syncwarp();
+}
+
+template <bool COMPACT = false>
 __device__ __forceinline__ void k2_luma8(const K2Ctx &c, unsigned modes, bool availA, bool availB, bool availC, bool availD)
 {
     const unsigned fix = (availA ? 0u : c.fixA) | (availB ? 0u : c.fixB) | (availD ? 0u : c.fixD);
+    if (COMPACT) {
+#pragma unroll 1
+        for (int b8 = 0; b8 < 4; b8++) k2_luma8_block_rt(c, b8, modes, fix, availA, availB, availC);
+        return;
+    }
     k2_luma8_block<0>(c, modes, fix, availA, availB, availC);
     k2_luma8_block<1>(c, modes, fix, availA, availB, availC);
     k2_luma8_block<2>(c, modes, fix, availA, availB, availC);

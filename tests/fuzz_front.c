@@ -38,14 +38,23 @@ int main(int argc, char **argv)
             if (in.n_idr > 0 && in.width_mbs > 0 && in.width_mbs <= 64 && in.height_mbs <= 64) {
                 const size_t N = (size_t)in.width_mbs * in.height_mbs, P = (size_t)in.n_idr;
                 mvf_batch b;
+                memset(&b, 0, sizeof b);
+                int32_t *status = malloc(P * sizeof *status);
                 b.mb_kind = malloc(N * P); b.i16_mode = malloc(N * P); b.chroma_mode = malloc(N * P); b.qp_y = malloc(N * P);
                 b.cbp = malloc(N * P); b.luma_modes = malloc(N * P * 16); b.coeff = malloc(N * P * 768);
                 if (mvf_parse_pictures(s, NULL, 0, (int)P, &b, 1 + r % 3) == 1) parsed++;
+                b.status = status;                      /* tolerant mode: per-picture codes, the call itself succeeds */
+                mvf_parse_pictures(s, NULL, 0, (int)P, &b, 1 + r % 3);
                 mvf_packed_batch pk;
+                memset(&pk, 0, sizeof pk);
                 pk.mb_kind = b.mb_kind; pk.i16_mode = b.i16_mode; pk.chroma_mode = b.chroma_mode; pk.qp_y = b.qp_y; pk.luma_modes = b.luma_modes;
                 pk.nz_blocks = malloc(N * P * 4); pk.word_off = malloc(N * P * 4); pk.pic_off = malloc((P + 1) * 8);
                 pk.words_capacity = N * P * 408; pk.words = malloc(pk.words_capacity * 2);
                 mvf_parse_pictures_packed(s, NULL, 0, (int)P, &pk, 2);
+                pk.status = status;
+                mvf_parse_pictures_packed(s, NULL, 0, (int)P, &pk, 2);
+                for (int g = 0; g < mvf_generation_count(s); g++) { mvf_info gi; mvf_get_generation_info(s, g, &gi); }
+                free(status);
                 int32_t *sel = malloc(sizeof(int32_t) * (P + 8));
                 mvf_select_idr(s, 3, r % 3, sel);
                 free(sel); free(pk.nz_blocks); free(pk.word_off); free(pk.pic_off); free(pk.words);

@@ -69,6 +69,16 @@ def main():
             soa_qp_y=rs.qp_y, soa_cbp=rs.cbp, soa_luma_modes=rs.luma_modes, soa_coeff=rs.coeff,
             yuv=r["yuv"], rgb=r["rgb"])
         print(f"{name:26s} {n} pics {soa.width}x{soa.height}  {(HERE / (name + '.npz')).stat().st_size / 1024:.0f} KiB")
+    # a stream whose SPS / PPS change between pictures (tests/helpers.py builds it from three generated segments):
+    # the reference re-decodes every parameter set where it meets it (h264.c:128-150)
+    sys.path.insert(0, str(HERE.parent))
+    from helpers import paramset_change_stream
+    stream, segs = paramset_change_stream()
+    n = sum(s.n_pics for s in segs)
+    r = ref.decode(stream, n, segs[0].width, segs[0].height, want_rgb=True)
+    np.savez_compressed(HERE / "multi_paramsets.npz", stream=np.frombuffer(stream, np.uint8), n_pics=n,
+                        width_mbs=segs[0].width_mbs, height_mbs=segs[0].height_mbs, yuv=r["yuv"], rgb=r["rgb"])
+    print(f"{'multi_paramsets':26s} {n} pics, 3 parameter generations")
     digests = {}
     for name, (n, kw) in LARGE.items():
         stream, soa = synth.generate(n, **kw)

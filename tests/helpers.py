@@ -13,7 +13,8 @@ GOLDEN = Path(__file__).resolve().parent / "golden"
 
 
 def golden_names():
-    return sorted(p.stem for p in GOLDEN.glob("*.npz"))
+    """Single-generation fixtures (one SPS/PPS pair); multi_*.npz hold streams whose parameter sets change."""
+    return sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith("multi_"))
 
 
 def load_golden(name):
@@ -104,3 +105,32 @@ def png_decode(png: bytes) -> np.ndarray:
                     pred = a if pa <= pb and pa <= pc else (b if pb <= pc else c)
                 out[y, i] = (line[i] + pred) & 255
     return out.reshape(h, w, 3).astype(np.uint8)
+
+
+def split_nals(stream: bytes) -> list[bytes]:
+    """NAL units of a generated stream (4-byte start codes, 64 bytes of zero padding at the end), start codes included."""
+    body = stream.rstrip(b"\x00")
+    # a NAL may end in zero bytes that rstrip took: the generator never ends one that way (rbsp_trailing_bits)
+    parts = body.split(b"\x00\x00\x00\x01")[1:]
+    return [b"\x00\x00\x00\x01" + p for p in parts]
+
+
+PAD = b"\x00" * 64
+
+
+def paramset_change_stream(geometry_change: bool = False):
+    """A stream whose parameter sets change between IDR pictures, the way BASELINE.md's chunk files do when their
+    headers differ: segment A (SPS + PPS + 2 pictures), segment B (a new SPS with other scaling lists and a new PPS with
+    other chroma QP offsets and pic_init_qp, 2 pictures), segment C (only a new PPS, 2 pictures).  With
+    geometry_change the second SPS also changes the picture size.  Returns (stream, [per-segment Soa])."""
+    from minivideo_b200 import synth
+    geo_a = dict(width_mbs=6, height_mbs=4)
+    geo_b = dict(width_mbs=8, height_mbs=5) if geometry_change else geo_a
+    common = dict(profile_idc=100, transform8x8=1, scaling_lists=1, qp_min=12, qp_max=44)
+    a, soa_a = synth.generate(2, seed=301, init_qp=26, cb_qp_offset=0, cr_qp_offset=0, **geo_a, **common)
+    b, soa_b = synth.generate(2, seed=302, init_qp=33, cb_qp_offset=5, cr_qp_offset=-4, **geo_b, **common)
+    c, soa_c = synth.generate(2, seed=302, init_qp=21, cb_qp_offset=-3, cr_qp_offset=2, **geo_b, **common)
+    nb, nc = split_nals(b), split_nals(c)
+    assert nb[0][4] == 0x67 and nc[0] == nb[0], "segments B and C must carry the same SPS"
+    stream = b"".join(split_nals(a)) + b"".join(nb) + b"".join(nc[1:]) + PAD
+    return stream, [soa_a, soa_b, soa_c]

@@ -23,7 +23,10 @@ def test_reference_arm_prints_the_agreed_json_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 3
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"] and "sample" in d["config"]
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert d["config"] == bench.CONFIG, "both arms print the same config dict (the driver compares them)"
+    assert "one pinned to each host core" in d["cpu_baseline"]["sample"]
 
 
 def test_our_arm_refuses_to_run_without_a_gpu():

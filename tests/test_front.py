@@ -119,3 +119,89 @@ def test_unfiltered_selection_is_the_first_n():
     st = front.Stream(stream)
     assert st.select_idr(3, 0).tolist() == [0, 1, 2]
     assert st.select_idr(9, 0).tolist() == [0, 1, 2, 3, 4]
+
+
+# ---- parameter sets that change inside the stream ("first ones win" was wrong) ------------------------
+
+def _multi():
+    import numpy as np
+    from helpers import GOLDEN
+    return np.load(GOLDEN / "multi_paramsets.npz")
+
+
+def test_parameter_sets_are_tracked_per_picture():
+    """The reference decodes every SPS / PPS where it meets it (h264.c:128-150); later pictures use later tables,
+    offsets and pic_init_qp.  The front end reports one parameter generation per distinct (SPS, PPS) pair in force
+    and parses each picture with its own."""
+    from helpers import paramset_change_stream
+    from minivideo_b200 import front
+    stream, segs = paramset_change_stream()
+    assert stream == _multi()["stream"].tobytes(), "the committed fixture was made from this stream"
+    st = front.Stream(stream)
+    assert st.n_generations == 3 and list(st.picture_generations()) == [0, 0, 1, 1, 2, 2]
+    want = [(26, 0, 0), (33, 5, -4), (21, -3, 2)]
+    for g, seg in enumerate(segs):
+        info = st.generation_info(g)
+        assert (info.pic_init_qp, info.cb_qp_offset, info.cr_qp_offset) == want[g]
+        assert (info.n_generations, info.generation) == (3, g)
+        assert same(st.parse(first=2 * g, count=2), seg), f"segment {g}: QPs come from this segment's pic_init_qp"
+    # generations 1 and 2 share the SPS (same scaling lists), generation 0 has other lists
+    l0, l1, l2 = (st.level_scale(st.generation_info(g))[0] for g in range(3))
+    assert np.array_equal(l1, l2) and not np.array_equal(l0, l1)
+    # one call may span generations of equal picture size: every picture still gets its own parameters
+    whole = st.parse()
+    for f in FIELDS:
+        assert np.array_equal(getattr(whole, f), np.concatenate([getattr(s, f) for s in segs])), f
+
+
+def test_changing_parameter_sets_reconstruct_like_the_reference():
+    """Golden: the reference's own output for the stream above (tests/golden/make_golden.py).  Front end +
+    per-generation tables + oracle must reproduce it byte for byte."""
+    from helpers import oracle_reconstruct_with_tables
+    from minivideo_b200 import front
+    from oracle import cpu
+    z = _multi()
+    st = front.Stream(z["stream"].tobytes())
+    gens = st.picture_generations()
+    for g in range(st.n_generations):
+        idx = [i for i in range(st.n_idr) if gens[i] == g]
+        info = st.generation_info(g)
+        soa = st.parse(indices=idx)
+        yuv, _ = oracle_reconstruct_with_tables(soa, *st.level_scale(info))
+        for k, i in enumerate(idx):
+            assert np.array_equal(yuv[k], z["yuv"][i]), f"picture {i} (generation {g})"
+        assert np.array_equal(cpu.yuv_to_rgb(yuv, soa.width, soa.height, 1), z["rgb"][idx])
+    # with the first generation's tables for everything (what round 1 did) pictures 2..5 come out different
+    soa = st.parse()
+    yuv, _ = oracle_reconstruct_with_tables(soa, *st.level_scale(st.generation_info(0)))
+    assert np.array_equal(yuv[:2], z["yuv"][:2]) and not np.array_equal(yuv[2:], z["yuv"][2:])
+
+
+def test_parameter_set_ids_and_missing_sets():
+    """Tables are indexed by id (7.4.1.2.1): a PPS under another id does not disturb pictures that name PPS 0, a
+    picture naming a PPS the stream never delivered fails alone, and so does one behind a damaged PPS."""
+    from helpers import PAD, split_nals
+    from minivideo_b200 import front, synth
+    stream, soa = synth.generate(3, width_mbs=4, height_mbs=3, profile_idc=66, seed=17)
+    nals = split_nals(stream)
+    sps, pps, pics = nals[0], nals[1], nals[2:]
+    assert pps[4] == 0x68 and pps[5] & 0x80, "pic_parameter_set_id 0 is coded as the single bit 1"
+    # PPS id 1 ('010'), sps id 0 ('1'): the first payload byte 1 1 e b ... becomes 010 1 e b ..: rebuild the bit string
+    bits = "".join(f"{b:08b}" for b in pps[5:])
+    end = bits.rindex("1")                              # rbsp_stop_one_bit
+    body = "010" + bits[1:end] + "1"
+    body += "0" * (-len(body) % 8)
+    pps1 = pps[:5] + bytes(int(body[i:i + 8], 2) for i in range(0, len(body), 8))
+    st = front.Stream(sps + pps + pps1 + b"".join(pics) + PAD)
+    assert st.n_generations == 1 and same(st.parse(), soa)
+    # no PPS 0 at all: nothing is decodable
+    with pytest.raises(front.FrontError, match="PPS 0"):
+        front.Stream(sps + pps1 + b"".join(pics) + PAD)
+    # PPS 0 arrives after the first picture: picture 0 fails alone (tolerant mode), the others decode
+    st = front.Stream(sps + pics[0] + pps + pics[1] + pics[2] + PAD)
+    assert list(st.picture_generations()) == [-1, 0, 0]
+    with pytest.raises(front.FrontError, match="picture 0"):
+        st.parse()
+    got = st.parse(tolerant=True)
+    assert list(got.status) == [0, 1, 1]
+    assert same(got.pictures(1, 2), soa.pictures(1, 2)) and not got.coeff[: soa.n_mbs].any()

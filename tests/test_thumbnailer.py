@@ -204,3 +204,49 @@ def test_cli_all_gpus_writes_the_same_files_as_one_gpu(cli):
             assert r.returncode == 0 and "13 picture(s) exported" in r.stdout, (r.stdout, r.stderr)
             outs.append({p.name: p.read_bytes() for p in Path(d).iterdir() if p.name != "in.264"})
     assert len(outs[0]) == 13 and outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geometry_change", [False, True], ids=["same_size", "new_size"])
+@pytest.mark.parametrize("fmt", ["yuv420", "bmp"])
+def test_cli_follows_parameter_set_changes_like_the_reference_cli(cli, geometry_change, fmt):
+    """A stream whose SPS / PPS change between pictures (other scaling lists, chroma QP offsets, pic_init_qp, and
+    with `new_size` other picture dimensions): the reference re-decodes every parameter set where it meets it
+    (h264.c:128-150); mvt_extract() switches tables -- and output size -- per parameter generation."""
+    from helpers import paramset_change_stream
+    if not ref.MINI_THUMBNAILER.exists():
+        pytest.skip("reference CLI not built")
+    stream, segs = paramset_change_stream(geometry_change)
+    want, _ = _run_both(stream, ["-f", fmt, "-n", "6"])
+    assert len(want) == 6
+    for extra in ([], ["-b", "1"], ["-b", "4", "-t", "2"]):      # batches that end at, inside and across the segments
+        _, got = _run_both(stream, ["-f", fmt, "-n", "6"] + extra)
+        assert want == got, extra
+
+
+@pytest.mark.gpu
+def test_cli_skips_a_picture_it_cannot_decode_like_the_reference_cli(cli):
+    """The reference counts a picture that fails and goes on (h264.c:103-109); the pictures after it move up one
+    number (export.c:630 numbers by pictures decoded).  Picture 1 of 5 is turned into a P slice (slice_type 5), which
+    both decoders refuse."""
+    from helpers import PAD, split_nals
+    from minivideo_b200 import synth
+    if not ref.MINI_THUMBNAILER.exists():
+        pytest.skip("reference CLI not built")
+    stream, _ = synth.generate(5, width_mbs=6, height_mbs=4, profile_idc=100, transform8x8=1, seed=31)
+    nals = split_nals(stream)
+    bad = nals[3][:5] + bytes([0b10100000 | (nals[3][5] & 0x0f)]) + nals[3][6:]     # first_mb 0 ('1'), slice_type ue '010..'
+    broken = b"".join(nals[:3] + [bad] + nals[4:]) + PAD
+    good, _ = _run_both(stream, ["-f", "yuv420", "-n", "5"])
+    out = []
+    for exe, extra in ((ref.MINI_THUMBNAILER, []), (MV, ["-o", "."])):
+        with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+            (Path(d) / "in.264").write_bytes(broken)
+            r = subprocess.run([str(exe), "-i", str(Path(d) / "in.264"), "-f", "yuv420", "-n", "5"] + extra,
+                               capture_output=True, text=True, cwd=d)
+            out.append(({p.name: p.read_bytes() for p in Path(d).iterdir() if p.name != "in.264"}, r))
+    (want, _), (got, r) = out
+    assert sorted(want) == sorted(got) == ["in_0.yuv", "in_1.yuv", "in_2.yuv", "in_3.yuv"]
+    assert want == got
+    assert got["in_0.yuv"] == good["in_0.yuv"] and got["in_1.yuv"] == good["in_2.yuv"] and got["in_3.yuv"] == good["in_4.yuv"]
+    assert r.returncode == 1 and "4 of 5 pictures exported" in r.stderr and "picture 1 skipped" in r.stderr
