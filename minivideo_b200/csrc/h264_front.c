@@ -28,7 +28,10 @@ static uint16_t lut_ct10[3][1 << 10];    /* the codes of up to 10 bits (almost a
 static uint16_t lut_ctc[1 << 8];         /* chroma DC coeff_token, next 8 bits                             */
 static uint8_t  lut_tz4[15][1 << 9];     /* len<<4 | total_zeros, next 9 bits                              */
 static uint8_t  lut_tz2[3][1 << 3];
-static uint8_t  lut_run[7][1 << 11];     /* len<<4 | run_before, next 11 bits                              */
+static uint8_t  lut_run3[7][8];          /* run_before for zerosLeft 0..6 (Table 9-10): codes of at most 3 bits,
+                                            len<<4 | run, next 3 bits; row 0 = nothing left to place (no bits, run 0);
+                                            entries no code leads to say run 15, which no zerosLeft allows;
+                                            zerosLeft > 6 is decoded arithmetically                             */
 static uint8_t  cbp_from_codenum[48];
 static uint8_t  zz4[16], zz8[64];
 static pthread_once_t lut_once = PTHREAD_ONCE_INIT;
@@ -47,6 +50,7 @@ static void fill8s(uint8_t *lut, int bits, const char *str, int sym)
     unsigned lo = code << (bits - len), n = 1u << (bits - len);
     for (unsigned i = 0; i < n; i++) lut[lo + i] = (uint8_t)(len << 4 | sym);
 }
+static void pack_choose(void);
 static void zigzag_build(int n, uint8_t *zz)
 {
     int r = 0, c = 0, up = 1;
@@ -73,10 +77,13 @@ static void build_luts(void)
         for (int tz = 0; tz <= 16 - tc; tz++) fill8s(lut_tz4[tc - 1], 9, tz4x4[tc - 1][tz], tz);
     for (int tc = 1; tc <= 3; tc++)
         for (int tz = 0; tz <= 4 - tc; tz++) fill8s(lut_tz2[tc - 1], 3, tz2x2[tc - 1][tz], tz);
-    for (int zl = 1; zl <= 7; zl++)
-        for (int run = 0; run <= (zl < 7 ? zl : 14); run++) fill8s(lut_run[zl - 1], 11, runb[zl - 1][run], run);
+    for (int zl = 1; zl <= 6; zl++) {
+        memset(lut_run3[zl], 0x1f, 8);
+        for (int run = 0; run <= zl; run++) fill8s(lut_run3[zl], 3, runb[zl - 1][run], run);
+    }
     for (int k = 0; k < 48; k++) cbp_from_codenum[k] = cbp_intra_by_codenum[k];
     zigzag_build(4, zz4); zigzag_build(8, zz8);
+    pack_choose();
 }
 
 /* ------------------------------------------------------------------------ */
@@ -640,46 +647,36 @@ typedef struct {
     uint16_t *pk_words; size_t pk_n, pk_cap;
 } worker_t;
 
-static inline int blk_x(int blk) { return (blk & 1) + 2 * ((blk >> 2) & 1); }
-static inline int blk_y(int blk) { return ((blk >> 1) & 1) + 2 * (blk >> 3); }
-
-static int nC_of(const uint8_t *tot, int stride, int X, int Y)
-{
-    int a = X > 0, b = Y > 0;
-    int nA = a ? tot[Y * stride + X - 1] : 0, nB = b ? tot[(Y - 1) * stride + X] : 0;
-    if (a && b) return (nA + nB + 1) >> 1;
-    return a ? nA : (b ? nB : 0);
-}
-
 static inline int16_t clamp16(int v) { return (int16_t)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); }
 
-static inline uint64_t rrb_load(const uint8_t *base, size_t pos)
-{
-    uint64_t w;
-    memcpy(&w, base + (pos >> 3), 8);
-    return __builtin_bswap64(w) << (pos & 7);
-}
-
 /* 9.2: one residual block of max_num 16 / 15 / 4 levels.  The non-zero levels go straight to their place,
- * dst[scan index * stride] (the destination must hold zeros), clamped to int16.  Returns TotalCoeff or -1. */
+ * dst[scan index * stride] (the destination must hold zeros), clamped to int16.  Returns TotalCoeff or -1.
+ *
+ * The bits live in a register window: `win` holds the stream left-aligned at the read position, `have` says how many
+ * of its bits are real.  A refill is one unaligned 8-byte load + byte swap + shift (the RBSP has RBSP_SLACK zero bytes
+ * behind it, so it never needs a bounds check) and happens at fixed points of the code -- block entry, every second
+ * level, every fourth run -- so that its branches are periodic; the data-dependent "window nearly empty" test beside
+ * them is almost never true.  Between refills a symbol costs shift + table look-up + shift instead of address +
+ * load + swap + shift + look-up: the chain from one symbol's length to the next symbol's bits is what bounds CAVLC. */
 static int read_residual_block(br_t *b, int16_t *dst, int stride, int max_num, int nC)
 {
-    /* The read position lives in a local for the whole block and every look at the stream is an unconditional
-     * 8-byte load + byte swap + shift (the RBSP has RBSP_SLACK zero bytes behind it): no state in memory between
-     * the symbols and no refill branch.  The data-dependent decisions of the level loop are arithmetic. */
     const uint8_t *const base = b->p;
     size_t pos = b->pos;
-#define RRB_WIN()      (rrb_load(base, pos))
-#define RRB_PEEK(n)    ((uint32_t)(RRB_WIN() >> (64 - (n))))
+    uint64_t win;
+    int have;
+#define RRB_REFILL()   do { uint64_t t_; memcpy(&t_, base + (pos >> 3), 8); win = __builtin_bswap64(t_) << (pos & 7); have = 64 - (int)(pos & 7); } while (0)
+#define RRB_SKIP(n)    do { const int n_ = (int)(n); win <<= n_; pos += (size_t)n_; have -= n_; } while (0)
+#define RRB_PEEK(n)    ((uint32_t)(win >> (64 - (n))))
 #define RRB_FAIL()     do { b->pos = pos; return -1; } while (0)
+    RRB_REFILL();                                   /* >= 57 bits */
     int tc, t1;
     if (nC == -1) {
         uint16_t e = lut_ctc[RRB_PEEK(8)];
         if (!e) RRB_FAIL();
-        pos += e >> 7; tc = (e >> 2) & 31; t1 = e & 3;
+        RRB_SKIP(e >> 7); tc = (e >> 2) & 31; t1 = e & 3;
     } else if (nC >= 8) {
         uint32_t v = RRB_PEEK(6);
-        pos += 6;
+        RRB_SKIP(6);
         if (v == 3) { tc = 0; t1 = 0; } else { tc = (int)(v >> 2) + 1; t1 = (int)(v & 3); if (t1 > tc) RRB_FAIL(); }
     } else {
         const int t = nC < 2 ? 0 : (nC < 4 ? 1 : 2);
@@ -687,36 +684,40 @@ static int read_residual_block(br_t *b, int16_t *dst, int stride, int max_num, i
         uint16_t e = lut_ct10[t][bits >> 6];
         if (!e) e = lut_ct[t][bits];
         if (!e) RRB_FAIL();
-        pos += e >> 7; tc = (e >> 2) & 31; t1 = e & 3;
+        RRB_SKIP(e >> 7); tc = (e >> 2) & 31; t1 = e & 3;
     }
     if (tc == 0) { b->pos = pos; return 0; }
     if (tc > max_num) RRB_FAIL();
 
     int level[16];
     int suffix_len = (tc > 10 && t1 < 3) ? 1 : 0;
-    if (t1) {   /* trailing ones: t1 sign bits at once */
-        const uint32_t signs = RRB_PEEK(3) >> (3 - t1);
-        pos += (size_t)t1;
-        for (int i = 0; i < t1; i++) level[i] = 1 - 2 * (int)((signs >> (t1 - 1 - i)) & 1);
+    {   /* trailing ones: up to three sign bits, taken without a branch (the ones beyond t1 are overwritten by the
+         * level loop; coeff_token took at most 16 bits, so at least 41 are left in the window) */
+        const uint32_t signs = RRB_PEEK(3);
+        level[0] = 1 - (int)((signs >> 1) & 2); level[1] = 1 - (int)(signs & 2); level[2] = 1 - (int)((signs << 1) & 2);
+        RRB_SKIP(t1);
     }
     int first_adj = t1 < 3 ? 2 : 0;                 /* the first level after fewer than three trailing ones (9.2.2.1) */
-    for (int i = t1; i < tc; i++) {
-        const uint32_t w32 = (uint32_t)(RRB_WIN() >> 32);
+    for (int i = t1, k = 0; i < tc; i++, k++) {
+        if (!(k & 1) || have < 32) RRB_REFILL();    /* a level is 28 bits at most unless it is an escape */
+        const uint32_t w32 = (uint32_t)(win >> 32);
         if (!w32) RRB_FAIL();                       /* 32 or more zero bits */
         const int prefix = __builtin_clz(w32);
         int code;
-        if (prefix < 14) {              /* the common case: prefix, stop bit and suffix (<= 20 bits) from one window */
+        if (prefix < 14) {              /* the common case: prefix, stop bit and suffix (<= 20 bits) from the window */
             code = (prefix << suffix_len) + (int)((uint64_t)(uint32_t)(w32 << (prefix + 1)) >> (32 - suffix_len));
-            pos += (size_t)(prefix + 1 + suffix_len);
+            RRB_SKIP(prefix + 1 + suffix_len);
         } else {
-            pos += (size_t)prefix + 1;
+            RRB_SKIP(prefix + 1);
+            RRB_REFILL();
             code = (prefix < 15 ? prefix : 15) << suffix_len;           /* 9.2.2.1 */
             int ssize = suffix_len;
             if (prefix == 14 && suffix_len == 0) ssize = 4;
             else if (prefix >= 15) ssize = prefix - 3;
-            if (ssize > 0) { code += (int)RRB_PEEK(ssize); pos += (size_t)ssize; }
+            if (ssize > 0) { code += (int)RRB_PEEK(ssize); RRB_SKIP(ssize); }
             if (prefix >= 15 && suffix_len == 0) code += 15;
             if (prefix >= 16) code += (1 << (prefix - 3)) - 4096;
+            RRB_REFILL();
         }
         code += first_adj; first_adj = 0;
         const int sign = -(code & 1), mag = (code + 2) >> 1;            /* odd: -(code + 1) / 2, even: (code + 2) / 2 */
@@ -725,29 +726,45 @@ static int read_residual_block(br_t *b, int16_t *dst, int stride, int max_num, i
         suffix_len += (mag > (3 << (suffix_len - 1))) & (suffix_len < 6);
     }
     int zeros_left = 0;
+    RRB_REFILL();
     if (tc < max_num) {
         uint8_t e = max_num == 4 ? lut_tz2[tc - 1][RRB_PEEK(3)] : lut_tz4[tc - 1][RRB_PEEK(9)];
         if (!e) RRB_FAIL();
-        pos += e >> 4; zeros_left = e & 15;
+        RRB_SKIP(e >> 4); zeros_left = e & 15;
     }
     int at = zeros_left + tc - 1;                                       /* scan index of the first (highest) level */
     if (at >= max_num) RRB_FAIL();
-    for (int i = 0; i < tc; i++) {
+    /* run_before for every level but the last, while there are zeros left to place (the branch on zerosLeft is worth
+     * keeping: predicted, it takes the table look-ups off the dependency chain; a branch-free loop was 20 % slower) */
+    for (int i = 0; i < tc - 1; i++) {
         dst[at * stride] = clamp16(level[i]);
         int run = 0;
-        if (i < tc - 1 && zeros_left > 0) {
-            uint8_t e = lut_run[(zeros_left > 7 ? 7 : zeros_left) - 1][RRB_PEEK(11)];
-            if (!e) RRB_FAIL();
-            pos += e >> 4; run = e & 15;
-            if (run > zeros_left) RRB_FAIL();
+        if (zeros_left > 0) {
+            if ((i & 3) == 3 || have < 11) RRB_REFILL();                /* total_zeros took <= 9 bits, a run takes <= 11 */
+            if (zeros_left < 7) {
+                const uint8_t e = lut_run3[zeros_left][RRB_PEEK(3)];
+                RRB_SKIP(e >> 4); run = e & 15;
+            } else {                                /* Table 9-10, zerosLeft > 6: 3 bits for runs 0..6, then unary */
+                const uint32_t t3 = RRB_PEEK(3);
+                if (t3) { run = 7 - (int)t3; RRB_SKIP(3); }
+                else {
+                    const uint32_t w32 = (uint32_t)(win >> 32);
+                    const int z = w32 ? __builtin_clz(w32) : 32;
+                    if (z > 10) RRB_FAIL();
+                    run = z + 4; RRB_SKIP(z + 1);
+                }
+            }
+            if (run > zeros_left) RRB_FAIL();       /* also catches the invalid codes of lut_run3 (run 15) */
             zeros_left -= run;
         }
         at -= 1 + run;
-        if (i < tc - 1 && at < 0) RRB_FAIL();
+        if (at < 0) RRB_FAIL();
     }
+    dst[at * stride] = clamp16(level[tc - 1]);
     b->pos = pos;
     return tc;
-#undef RRB_WIN
+#undef RRB_REFILL
+#undef RRB_SKIP
 #undef RRB_PEEK
 #undef RRB_FAIL
 }
@@ -808,49 +825,74 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
     }
     if (qp < 0 || qp > 51) return wfail(w, MVG_FAILURE, "picture %d: SliceQPY %d out of range", idr_index, qp);
 
-    /* ---- slice data, 7.3.4 / 7.3.5 ---- */
-    const int W = sps->width_mbs, H = sps->height_mbs, W4 = W * 4, W2 = W * 2;
+    /* ---- slice data, 7.3.4 / 7.3.5 ----
+     * Neighbour context (TotalCoeff for nC, 9.2.1; prediction modes for 8.3.1.1 / 8.3.2.1) is kept as one line of the
+     * macroblock row above plus the column to the left, and per macroblock in small local grids with a border:
+     * grid[y + 1][x + 1] is block (x, y), row 0 the blocks above, column 0 the blocks to the left.  An unavailable
+     * TotalCoeff neighbour holds NA (more than any two real counts add up to), an unavailable mode -1. */
+    enum { NA = 64 };
+    static const uint8_t BX[16] = {0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3}, BY[16] = {0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3};
+    const int W = sps->width_mbs, H = sps->height_mbs;
     const size_t N = (size_t)W * H;
-    memset(w->tot_luma, 0, N * 16);
-    memset(w->tot_chroma[0], 0, N * 4);
-    memset(w->tot_chroma[1], 0, N * 4);
+    uint8_t *const top_l = w->tot_luma, *const top_c[2] = {w->tot_chroma[0], w->tot_chroma[1]};
+    int8_t *const top_m = w->mode_grid;
     if (w->packed) memset(w->mb_levels, 0, sizeof w->mb_levels);      /* a failed picture may have left levels behind */
+#define NC_OF(a, b) ((a) + (b) < NA ? ((a) + (b) + 1) >> 1 : ((a) + (b) < 2 * NA ? (a) + (b) - NA : 0))
 
-    for (int my = 0; my < H; my++)
+    for (int my = 0; my < H; my++) {
+        uint8_t left_l[4] = {NA, NA, NA, NA}, left_c[2][2] = {{NA, NA}, {NA, NA}};
+        int8_t left_m[4] = {-1, -1, -1, -1};
         for (int mx = 0; mx < W; mx++) {
             const size_t mbi = pic_slot * N + (size_t)my * W + mx;
             int16_t *cf = w->packed ? w->mb_levels : out->coeff + mbi * 384;
             uint8_t *modes = out->luma_modes + mbi * 16;
             if (!w->packed) memset(cf, 0, 768);         /* packed mode: pack_mb() hands the buffer back zeroed */
             memset(modes, 0, 16);
+            uint8_t gl[5][8], gc[2][3][4];
+            int8_t gm[5][8];
+            for (int i = 0; i < 4; i++) {
+                gl[0][i + 1] = my ? top_l[mx * 4 + i] : NA; gl[i + 1][0] = left_l[i];
+                gm[0][i + 1] = my ? top_m[mx * 4 + i] : -1; gm[i + 1][0] = left_m[i];
+            }
+            for (int c = 0; c < 2; c++)
+                for (int i = 0; i < 2; i++) { gc[c][0][i + 1] = my ? top_c[c][mx * 2 + i] : NA; gc[c][i + 1][0] = left_c[c][i]; }
+
             uint32_t mb_type = br_ue(&b);
             if (mb_type == 25) return wfail(w, MVG_UNSUPPORTED, "picture %d: I_PCM macroblock (h264_macroblock.c:151-154)", idr_index);
             if (mb_type > 25) return wfail(w, MVG_FAILURE, "picture %d mb %d: bad mb_type %u", idr_index, my * W + mx, mb_type);
             int kind, i16_mode = 0, cbp_l, cbp_c;
             if (mb_type == 0) {
                 kind = (pps->transform8x8 && br_bit(&b)) ? MVG_MB_I8x8 : MVG_MB_I4x4;
-                int nb = kind == MVG_MB_I4x4 ? 16 : 4;
-                for (int i = 0; i < nb; i++) {
-                    int X4 = mx * 4 + (kind == MVG_MB_I4x4 ? blk_x(i) : (i & 1) * 2);
-                    int Y4 = my * 4 + (kind == MVG_MB_I4x4 ? blk_y(i) : (i >> 1) * 2);
-                    int pred = 2;                           /* 8.3.1.1 / 8.3.2.1 */
-                    if (X4 > 0 && Y4 > 0) {
-                        int a = w->mode_grid[Y4 * W4 + X4 - 1], bb = w->mode_grid[(Y4 - 1) * W4 + X4];
-                        pred = a < bb ? a : bb;
+                if (kind == MVG_MB_I4x4) {
+                    for (int i = 0; i < 16; i++) {
+                        const int x = BX[i], y = BY[i], a = gm[y + 1][x], bb = gm[y][x + 1];
+                        const int pred = (a | bb) < 0 ? 2 : (a < bb ? a : bb);      /* 8.3.1.1 */
+                        const uint32_t f = br_peek(&b, 4);                           /* prev_intra4x4_pred_mode_flag, rem_intra4x4_pred_mode */
+                        const int rem = (int)(f & 7);
+                        const int mode = (f & 8) ? pred : (rem < pred ? rem : rem + 1);
+                        br_skip(&b, (f & 8) ? 1 : 4);
+                        modes[i] = (uint8_t)mode;
+                        gm[y + 1][x + 1] = (int8_t)mode;
                     }
-                    int mode = pred;
-                    if (!br_bit(&b)) { int rem = (int)br_get(&b, 3); mode = rem < pred ? rem : rem + 1; }
-                    modes[i] = (uint8_t)mode;
-                    int span = kind == MVG_MB_I4x4 ? 1 : 2;
-                    for (int dy = 0; dy < span; dy++)
-                        for (int dx = 0; dx < span; dx++) w->mode_grid[(Y4 + dy) * W4 + X4 + dx] = (int8_t)mode;
+                } else {
+                    for (int i = 0; i < 4; i++) {
+                        const int x = (i & 1) * 2, y = (i >> 1) * 2, a = gm[y + 1][x], bb = gm[y][x + 1];
+                        const int pred = (a | bb) < 0 ? 2 : (a < bb ? a : bb);      /* 8.3.2.1 */
+                        const uint32_t f = br_peek(&b, 4);
+                        const int rem = (int)(f & 7);
+                        const int mode = (f & 8) ? pred : (rem < pred ? rem : rem + 1);
+                        br_skip(&b, (f & 8) ? 1 : 4);
+                        modes[i] = (uint8_t)mode;
+                        gm[y + 1][x + 1] = gm[y + 1][x + 2] = gm[y + 2][x + 1] = gm[y + 2][x + 2] = (int8_t)mode;
+                    }
                 }
             } else {
                 kind = MVG_MB_I16x16;
                 int t = (int)mb_type - 1;
                 i16_mode = t & 3; cbp_c = (t >> 2) % 3; cbp_l = t >= 12 ? 15 : 0;
-                for (int blk = 0; blk < 16; blk++) w->mode_grid[(my * 4 + blk_y(blk)) * W4 + mx * 4 + blk_x(blk)] = 2;
+                for (int y = 1; y < 5; y++) gm[y][1] = gm[y][2] = gm[y][3] = gm[y][4] = 2;
             }
+            for (int i = 0; i < 4; i++) { top_m[mx * 4 + i] = gm[4][i + 1]; left_m[i] = gm[i + 1][4]; }
             uint32_t chroma_mode = br_ue(&b);
             if (chroma_mode > 3) return wfail(w, MVG_FAILURE, "picture %d mb %d: intra_chroma_pred_mode %u", idr_index, my * W + mx, chroma_mode);
             if (kind != MVG_MB_I16x16) {
@@ -860,6 +902,8 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
                 cbp_l = cbp & 15; cbp_c = cbp >> 4;
             }
             uint32_t touched = 0;                           /* blocks of cf[] that received levels (for pack_mb) */
+            for (int y = 1; y < 5; y++) gl[y][1] = gl[y][2] = gl[y][3] = gl[y][4] = 0;
+            for (int c = 0; c < 2; c++) gc[c][1][1] = gc[c][1][2] = gc[c][2][1] = gc[c][2][2] = 0;
             if (cbp_l || cbp_c || kind == MVG_MB_I16x16) {
                 int delta = br_se(&b);
                 if (delta < -26 || delta > 25) return wfail(w, MVG_FAILURE, "picture %d mb %d: mb_qp_delta %d out of range", idr_index, my * W + mx, delta);
@@ -867,49 +911,50 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
                 /* residual_luma, 7.3.5.3.1 */
                 if (kind == MVG_MB_I16x16) {
                     int16_t dc[16] = {0};
-                    const int tcdc = read_residual_block(&b, dc, 1, 16, nC_of(w->tot_luma, W4, mx * 4, my * 4));
+                    const int tcdc = read_residual_block(&b, dc, 1, 16, NC_OF(gl[1][0], gl[0][1]));
                     if (tcdc < 0) goto bad_block;
-                    if (tcdc > 0) touched |= 0xffffu;        /* the DC levels go to slot 0 of all sixteen blocks */
-                    for (int k = 0; k < 16; k++) {
-                        int r = zz4[k] >> 2, c = zz4[k] & 3;
-                        cf[((r & 1) * 2 + (r >> 1) * 8 + (c & 1) + (c >> 1) * 4) * 16] = dc[k];
+                    if (tcdc > 0) {                          /* the DC levels go to slot 0 of all sixteen blocks */
+                        touched |= 0xffffu;
+                        for (int k = 0; k < 16; k++) {
+                            int r = zz4[k] >> 2, c = zz4[k] & 3;
+                            cf[((r & 1) * 2 + (r >> 1) * 8 + (c & 1) + (c >> 1) * 4) * 16] = dc[k];
+                        }
                     }
                 }
-                for (int b8 = 0; b8 < 4; b8++)
+                for (int b8 = 0; b8 < 4; b8++) {
+                    if (!((cbp_l >> b8) & 1)) continue;
                     for (int i4 = 0; i4 < 4; i4++) {
-                        int blk = b8 * 4 + i4, X4 = mx * 4 + blk_x(blk), Y4 = my * 4 + blk_y(blk), tc = 0;
-                        if ((cbp_l >> b8) & 1) {
-                            const int nC = nC_of(w->tot_luma, W4, X4, Y4);
-                            if (kind == MVG_MB_I4x4) tc = read_residual_block(&b, cf + blk * 16, 1, 16, nC);
-                            else if (kind == MVG_MB_I8x8) tc = read_residual_block(&b, cf + b8 * 64 + i4, 4, 16, nC);   /* h264_macroblock.c:1182 */
-                            else tc = read_residual_block(&b, cf + blk * 16 + 1, 1, 15, nC);
-                            if (tc < 0) goto bad_block;
-                            if (tc > 0) touched |= kind == MVG_MB_I8x8 ? 0xfu << (4 * b8) : 1u << blk;   /* 8x8: interleaved over its four blocks */
-                        }
-                        w->tot_luma[Y4 * W4 + X4] = (uint8_t)tc;
+                        const int blk = b8 * 4 + i4, x = BX[blk], y = BY[blk];
+                        const int nC = NC_OF(gl[y + 1][x], gl[y][x + 1]);
+                        int tc;
+                        if (kind == MVG_MB_I4x4) tc = read_residual_block(&b, cf + blk * 16, 1, 16, nC);
+                        else if (kind == MVG_MB_I8x8) tc = read_residual_block(&b, cf + b8 * 64 + i4, 4, 16, nC);   /* h264_macroblock.c:1182 */
+                        else tc = read_residual_block(&b, cf + blk * 16 + 1, 1, 15, nC);
+                        if (tc < 0) goto bad_block;
+                        if (tc > 0) touched |= kind == MVG_MB_I8x8 ? 0xfu << (4 * b8) : 1u << blk;   /* 8x8: interleaved over its four blocks */
+                        gl[y + 1][x + 1] = (uint8_t)tc;
                     }
+                }
                 /* residual chroma: DC of both planes, then AC of both planes (h264_macroblock.c:1222-1292) */
-                for (int c = 0; c < 2; c++)
-                    if (cbp_c & 3) {
+                if (cbp_c & 3)
+                    for (int c = 0; c < 2; c++) {
                         const int tcc = read_residual_block(&b, cf + 256 + c * 64, 16, 4, -1);
                         if (tcc < 0) goto bad_block;
                         if (tcc > 0) touched |= 0xfu << (16 + 4 * c);
                     }
-                for (int c = 0; c < 2; c++)
-                    for (int blk = 0; blk < 4; blk++) {
-                        int X2 = mx * 2 + (blk & 1), Y2 = my * 2 + (blk >> 1), tc = 0;
-                        if (cbp_c & 2) {
-                            tc = read_residual_block(&b, cf + 256 + c * 64 + blk * 16 + 1, 1, 15, nC_of(w->tot_chroma[c], W2, X2, Y2));
+                if (cbp_c & 2)
+                    for (int c = 0; c < 2; c++)
+                        for (int blk = 0; blk < 4; blk++) {
+                            const int x = blk & 1, y = blk >> 1;
+                            const int tc = read_residual_block(&b, cf + 256 + c * 64 + blk * 16 + 1, 1, 15, NC_OF(gc[c][y + 1][x], gc[c][y][x + 1]));
                             if (tc < 0) goto bad_block;
                             if (tc > 0) touched |= 1u << (16 + 4 * c + blk);
+                            gc[c][y + 1][x + 1] = (uint8_t)tc;
                         }
-                        w->tot_chroma[c][Y2 * W2 + X2] = (uint8_t)tc;
-                    }
-            } else {
-                for (int blk = 0; blk < 16; blk++) w->tot_luma[(my * 4 + blk_y(blk)) * W4 + mx * 4 + blk_x(blk)] = 0;
-                for (int c = 0; c < 2; c++)
-                    for (int blk = 0; blk < 4; blk++) w->tot_chroma[c][(my * 2 + (blk >> 1)) * W2 + mx * 2 + (blk & 1)] = 0;
             }
+            for (int i = 0; i < 4; i++) { top_l[mx * 4 + i] = gl[4][i + 1]; left_l[i] = gl[i + 1][4]; }
+            for (int c = 0; c < 2; c++)
+                for (int i = 0; i < 2; i++) { top_c[c][mx * 2 + i] = gc[c][2][i + 1]; left_c[c][i] = gc[c][i + 1][2]; }
             out->mb_kind[mbi] = (uint8_t)kind;
             out->i16_mode[mbi] = (uint8_t)i16_mode;
             out->chroma_mode[mbi] = (uint8_t)chroma_mode;
@@ -921,11 +966,15 @@ static int parse_picture(worker_t *w, int idr_index, const mvf_batch *out, size_
         bad_block:
             return wfail(w, MVG_FAILURE, "picture %d mb %d: invalid CAVLC code", idr_index, my * W + mx);
         }
+    }
+#undef NC_OF
     return MVG_SUCCESS;
 }
 
-/* the 384 levels of one macroblock -> chunk bitmap, masks and non-zero levels appended to the worker's words */
-static int pack_mb(worker_t *w, size_t m, uint32_t touched)
+/* the 384 levels of one macroblock -> chunk bitmap, masks and non-zero levels appended to the worker's words.
+ * `touched`: the blocks the parser wrote levels into (a superset of the non-zero ones); the others hold zeros.  Every
+ * non-zero block is zeroed again for the next macroblock (so that the parser needs no 768-byte memset per macroblock). */
+static int pack_reserve(worker_t *w)
 {
     if (w->pk_n + MVG_PACKED_WORDS_PER_MB > w->pk_cap) {
         size_t cap = w->pk_cap * 2 + 64 * MVG_PACKED_WORDS_PER_MB;
@@ -933,14 +982,17 @@ static int pack_mb(worker_t *w, size_t m, uint32_t touched)
         if (!w2) return 0;
         w->pk_words = w2; w->pk_cap = cap;
     }
+    return 1;
+}
+
+static int pack_mb_generic(worker_t *w, size_t m, uint32_t touched)
+{
+    if (!pack_reserve(w)) return 0;
     int16_t *c = w->mb_levels;
     uint16_t *dst = w->pk_words + w->pk_n;
     uint32_t nzb = 0;
     uint16_t masks[24], lv[384];
     int n_coded = 0, n_lv = 0;
-    /* one pass: per block the mask of non-zero levels, the levels themselves in scan order, and the block is
-     * zeroed again for the next macroblock (so that the parser needs no 768-byte memset per macroblock) */
-    /* `touched`: the blocks the parser wrote levels into (a superset of the non-zero ones); the others hold zeros */
     for (uint32_t todo = touched; todo; todo &= todo - 1) {
         const int b = __builtin_ctz(todo);
         int16_t *cb = c + b * 16;
@@ -974,6 +1026,56 @@ static int pack_mb(worker_t *w, size_t m, uint32_t touched)
     return 1;
 }
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+/* the same with AVX-512 (VBMI2): the non-zero levels of a block leave with one compress-store.  Chosen at run time. */
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi2,popcnt")))
+static int pack_mb_avx512(worker_t *w, size_t m, uint32_t touched)
+{
+    if (!pack_reserve(w)) return 0;
+    int16_t *c = w->mb_levels;
+    uint16_t *dst = w->pk_words + w->pk_n;
+    uint32_t nzb = 0;
+    uint16_t masks[24];
+    int n_coded = 0;
+    /* the masks come first in the output and their number decides where the levels start: masks in a first pass */
+    for (uint32_t todo = touched; todo; todo &= todo - 1) {
+        const int b = __builtin_ctz(todo);
+        const __m256i v = _mm256_loadu_si256((const __m256i *)(c + b * 16));
+        const __mmask16 k = _mm256_test_epi16_mask(v, v);
+        if (k) { nzb |= 1u << b; masks[n_coded++] = (uint16_t)k; }
+    }
+    uint16_t *lv = dst + n_coded;
+    const __m256i z = _mm256_setzero_si256();
+    int i = 0;
+    for (uint32_t todo = nzb; todo; todo &= todo - 1, i++) {
+        int16_t *cb = c + __builtin_ctz(todo) * 16;
+        const __m256i v = _mm256_loadu_si256((const __m256i *)cb);
+        _mm256_mask_compressstoreu_epi16(lv, (__mmask16)masks[i], v);
+        _mm256_storeu_si256((__m256i *)cb, z);
+        lv += __builtin_popcount(masks[i]);
+        dst[i] = masks[i];
+    }
+    w->pk_nzb[m] = nzb;
+    w->pk_off[m] = (uint32_t)w->pk_n;
+    w->pk_n += (size_t)(lv - dst);
+    return 1;
+}
+#endif
+
+static int (*pack_mb_impl)(worker_t *, size_t, uint32_t) = pack_mb_generic;
+static int pack_mb(worker_t *w, size_t m, uint32_t touched) { return pack_mb_impl(w, m, touched); }
+
+static void pack_choose(void)       /* called once from build_luts() */
+{
+#if defined(__x86_64__) && defined(__GNUC__)
+    __builtin_cpu_init();
+    if (__builtin_cpu_supports("avx512vbmi2") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") &&
+        !getenv("MVF_NO_AVX512"))
+        pack_mb_impl = pack_mb_avx512;
+#endif
+}
+
 /* ------------------------------------------------------------------------ */
 /* the parser: persistent worker threads, one IDR slice per thread at a time  */
 
@@ -1002,8 +1104,10 @@ static int worker_scratch(worker_t *w, const mvf_stream *s)
     const size_t N = (size_t)s->max_mbs;
     memset(w, 0, sizeof *w);
     w->s = s;
-    w->tot_luma = malloc(N * 16); w->tot_chroma[0] = malloc(N * 4); w->tot_chroma[1] = malloc(N * 4);
-    w->mode_grid = malloc(N * 16);
+    /* one line of neighbour context per macroblock row (TotalCoeff of luma / Cb / Cr blocks, prediction modes): N bounds
+     * the picture width of every generation */
+    w->tot_luma = malloc(N * 4 + 16); w->tot_chroma[0] = malloc(N * 2 + 16); w->tot_chroma[1] = malloc(N * 2 + 16);
+    w->mode_grid = malloc(N * 4 + 16);
     return w->tot_luma && w->tot_chroma[0] && w->tot_chroma[1] && w->mode_grid;
 }
 static void worker_release(worker_t *w)

@@ -425,7 +425,7 @@ static void *feeder_main(void *arg)
     p.f = f; p.final = -1;
     pthread_mutex_init(&p.mu, NULL); pthread_cond_init(&p.cv, NULL);
     int rc = 0;
-    const int n_slots = f->job->n_cand > batch ? 2 : 1;
+    const int n_slots = (f->job->n_cand > batch || f->n_gens > 1) ? 2 : 1;     /* batches end at parameter generations too */
     for (int k = 0; k < n_slots; k++) {
         /* parsed pictures travel in the packed transfer format (mvgpu.h): a fifth of the dense levels on the bus */
         mvf_packed_batch *pb = &p.slot[k].pb;

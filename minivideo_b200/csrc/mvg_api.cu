@@ -603,6 +603,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         p.work = work; p.tab = ctx->d_tab; p.luts = ctx->d_luts; p.epoch = ctx->epoch;
         p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics; p.group = MVG_K2_GROUP;
         p.sel[0] = 1u; p.sel[1] = 1u << 8; p.sel[2] = 1u << 16; p.sel[3] = 1u << 24;
+        p.stats = ctx->d_stats;
         const int grid = (int)std::min<long long>((items + KF_WARPS - 1) / KF_WARPS, (long long)ctx->sm_count * ctx->kf_ctas_per_sm);
         if (rgb_direct) kf_recon<KF_OUT_RGB><<<grid, KF_WARPS * 32, KF_SMEM_BYTES, st>>>(p);
         else kf_recon<KF_OUT_TILES><<<grid, KF_WARPS * 32, KF_SMEM_BYTES, st>>>(p);

@@ -26,7 +26,7 @@
 #define KF_WARPS 24         /* warps per CTA; one CTA per SM */
 #endif
 #ifndef KF_COMPACT8
-#define KF_COMPACT8 true    /* Intra8x8 blocks through one run-time-indexed copy of the code */
+#define KF_COMPACT8 false   /* true: Intra8x8 blocks through one run-time-indexed copy of the code (smaller, 4 % slower) */
 #endif
 #ifndef KF_POLL_NS
 #define KF_POLL_NS 1000     /* sleep between two looks at the row above while waiting for the distance */
@@ -54,7 +54,14 @@ struct KFParams {
     unsigned        epoch;
     int w_mbs, h_mbs, first_slot, n_pics, group;
     unsigned        sel[4];
+    unsigned long long *stats;  /* DEV (-DKF_STATS): wait accounting, 16 counters */
 };
+
+#ifdef KF_STATS
+#define KF_STAT(...) __VA_ARGS__
+#else
+#define KF_STAT(...)
+#endif
 
 /* Member order matters (see K2WarpSmem): lanes without a block in an Intra4x4 step read up to 64 bytes below
  * the residual and 140 bytes below lt[] (and past the end of lt[] into ct[]); all of that stays inside this record. */
@@ -84,8 +91,13 @@ struct KFWarpSmem {
  *   3. each macroblock is predicted and reconstructed in the warp's tile (kernel 2's code), its bottom line
  *      published, and then either stored as a 384-byte tile or converted to RGB24 into a staging area;
  *   4. RGB mode: after every second macroblock the pair's 16 rows x 96 bytes leave as 16-byte stores, whole sectors. */
+#ifdef KF_MAXREG
+#define KF_BOUNDS __maxnreg__(KF_MAXREG)        /* explicit register budget (the block size is given at launch) */
+#else
+#define KF_BOUNDS __launch_bounds__(KF_WARPS * 32, 1)
+#endif
 template <int OUT>
-__global__ void __launch_bounds__(KF_WARPS * 32, 1)
+__global__ void KF_BOUNDS
 kf_recon(KFParams p)
 {
     extern __shared__ __align__(128) uint8_t kf_smem[];
@@ -155,9 +167,10 @@ kf_recon(KFParams p)
     /* what a lane reads of the finished macroblock, and where the last byte of it goes as the left neighbour column
      * of the next macroblock (x = 15 -> x = -1 luma, x = 7 -> x = -1 chroma):
      *   tiles: lanes 0..15 one luma row (two 8-byte pieces), 16..23 Cb rows, 24..31 Cr rows (8 bytes)
-     *   RGB:   lane = 2 y + h: luma samples 8h..8h+7 of row y, Cb and Cr samples 4h..4h+3 of row y >> 1; the h = 1
-     *          lanes hold x = 15 of their luma row and x = 7 of their chroma row (even y stores Cb's, odd y Cr's);
-     *          the h = 0 lanes store to two spare bytes of the Intra8x8 line buffer                               */
+     *   RGB:   lane = 4 q + h: luma samples 4h..4h+3 of rows 2q and 2q+1, Cb and Cr samples 2h, 2h+1 of row q -- the
+     *          four pixels of a row and the row below share their two chroma samples, so the chroma terms of the
+     *          conversion are computed once per lane; the h = 3 lanes hold x = 15 of both luma rows and x = 7 of
+     *          the chroma row                                                                                      */
     const uint8_t *wo_src, *wo_csrc = nullptr;
     uint8_t *lc_dst, *lc_cdst = nullptr, *rgb_dst = nullptr;
     int wo_off = 0;
@@ -166,12 +179,12 @@ kf_recon(KFParams p)
         wo_off = lane < 16 ? lane * 16 : 256 + (lane - 16) * 8;
         lc_dst = lane < 16 ? s.lt + K2_TO(-1, lane) : s.ct[(lane >> 3) & 1] + K2_CO(-1, lane & 7);
     } else {
-        const int y = lane >> 1, h = lane & 1;
-        wo_src = s.lt + K2_TO(8 * h, y);
-        wo_csrc = s.ct[0] + K2_CO(4 * h, y >> 1);
-        lc_dst = h ? s.lt + K2_TO(-1, y) : s.n8 + MVG_N8_BYTES - 1;
-        lc_cdst = h ? s.ct[y & 1] + K2_CO(-1, y >> 1) : s.n8 + MVG_N8_BYTES - 2;
-        rgb_dst = s.u.rgb + y * KF_RGB_STRIDE + 24 * h;
+        const int q = lane >> 2, h = lane & 3;
+        wo_src = s.lt + K2_TO(4 * h, 2 * q);
+        wo_csrc = s.ct[0] + K2_CO(2 * h, q);
+        lc_dst = s.lt + K2_TO(-1, 2 * q);
+        lc_cdst = s.ct[0] + K2_CO(-1, q);
+        rgb_dst = s.u.rgb + 2 * q * KF_RGB_STRIDE + 12 * h;
     }
     const unsigned lc_sel = lane < 16 ? 7u : 3u;            /* tiles: byte 3 of the second / first 8-byte piece */
     const int pitch = 48 * W;                               /* bytes per RGB24 picture row */
@@ -179,6 +192,7 @@ kf_recon(KFParams p)
     MvgSideInfo side;
     side.init(lane, p.mb_kind, p.i16_mode, p.chroma_mode, p.luma_modes, p.qp_y);
     unsigned parity = 0;            /* phase parity of the mbarrier: one phase per group */
+    KF_STAT(unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};)
 
     for (;;) {
         int item = 0;
@@ -217,12 +231,15 @@ kf_recon(KFParams p)
                  * every burst of the row above -- it transforms KF_GROUP macroblocks, then predicts them -- stalls all
                  * rows below in turn; with slack the per-macroblock check further down almost never fails. */
                 const uint2 *probe = p.halo + (mb0 - W + min(KF_STAGGER, W - 1)) * 8 + 7;
-                while (mvg_ld_relaxed_u64(probe).y != epoch) __nanosleep(2000);
+                KF_STAT(const long long ts = clock64();)
+                while (mvg_ld_relaxed_u64(probe).y != epoch) { __nanosleep(2000); KF_STAT(st[0]++;) }
+                KF_STAT(st[1] += clock64() - ts;)
             }
             if (lane < hwords) qb = mvg_ld_relaxed_u64(ha_run);     /* becomes qa at macroblock 0 */
         }
         unsigned okA = 0;
 
+        KF_STAT(st[5]++; const long long trow = clock64();)
         for (int g = 0; g < n_groups; g++) {
             const unsigned meta = nmeta;
             const int nmb = min(KF_GROUP, W - g * KF_GROUP);
@@ -257,7 +274,9 @@ kf_recon(KFParams p)
                          * L2 per macroblock.  Fall back until the row above is KF_STAGGER macroblocks ahead again, then
                          * reload; after that the prefetches hit for the next KF_STAGGER - 8 macroblocks at least. */
                         const uint2 *probe = p.halo + (mb0 - W + min(mx + max(KF_STAGGER, 2), W - 1)) * 8 + 7;
-                        while (mvg_ld_relaxed_u64(probe).y != epoch) __nanosleep(KF_POLL_NS);
+                        KF_STAT(const long long ts = clock64(); st[2]++;)
+                        while (mvg_ld_relaxed_u64(probe).y != epoch) { __nanosleep(KF_POLL_NS); KF_STAT(st[3]++;) }
+                        KF_STAT(st[4] += clock64() - ts;)
                         do {    /* every word validates itself: the probe word says nothing about its neighbours */
                             if ((mx & ~3) * 8 + lane < hwords) qa = mvg_ld_relaxed_u64(ha_run);
                             if ((mx & ~3) * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(ha_run + 32);
@@ -303,36 +322,36 @@ kf_recon(KFParams p)
                     wo_run += 384;
                     *lc_dst = (uint8_t)__byte_perm(wa.y, wb.y, lc_sel);
                 } else {
-                    /* RGB24 of my 8 pixels (export_utils.c:300-302 on int16 pairs, see k3_rgb_full) into the staging rows */
-                    const uint2 yw = *reinterpret_cast<const uint2 *>(wo_src);
-                    const unsigned cbw = *reinterpret_cast<const unsigned *>(wo_csrc);
-                    const unsigned crw = *reinterpret_cast<const unsigned *>(wo_csrc + MVG_CT_PLANE);
-                    *lc_dst = (uint8_t)(yw.y >> 24);
-                    *lc_cdst = (uint8_t)(((lane & 2) ? crw : cbw) >> 24);
-                    unsigned out[6];
+                    /* RGB24 of my 2 x 4 pixels (export_utils.c:300-302 on int16 pairs, see k3_rgb_full) into the staging rows */
+                    const unsigned y0 = *reinterpret_cast<const unsigned *>(wo_src);
+                    const unsigned y1 = *reinterpret_cast<const unsigned *>(wo_src + MVG_LT_STRIDE);
+                    const unsigned cb2 = mvg_pair_lo(*reinterpret_cast<const uint16_t *>(wo_csrc));
+                    const unsigned cr2 = mvg_pair_lo(*reinterpret_cast<const uint16_t *>(wo_csrc + MVG_CT_PLANE));
+                    if ((lane & 3) == 3) {      /* x = 15 of both luma rows, x = 7 of the chroma row: the next macroblock's left column */
+                        lc_dst[0] = (uint8_t)(y0 >> 24); lc_dst[MVG_LT_STRIDE] = (uint8_t)(y1 >> 24);
+                        lc_cdst[0] = (uint8_t)(cb2 >> 16); lc_cdst[MVG_CT_PLANE] = (uint8_t)(cr2 >> 16);
+                    }
+                    /* the terms that do not depend on Y: pixels x and x + 2 of a row use chroma samples c and c + 1 */
+                    const unsigned rC = __vsub2(((cr2 * 204u) >> 7) & 0x01ff01ffu, 0x00de00deu);                   /* - 222 */
+                    const unsigned bC = __vsub2(((cb2 * 129u) >> 6) & 0x03ff03ffu, 0x01140114u);                   /* - 276 */
+                    const unsigned gC = __vsub2(__vsub2(0x00870087u, ((cb2 * 25u) >> 6) & 0x00ff00ffu),            /* 135 - .. - .. */
+                                                ((cr2 * 13u) >> 4) & 0x00ff00ffu);
 #pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        const unsigned cb2 = k ? mvg_pair_hi(cbw) : mvg_pair_lo(cbw);
-                        const unsigned cr2 = k ? mvg_pair_hi(crw) : mvg_pair_lo(crw);
-                        const unsigned rC = __vsub2(((cr2 * 204u) >> 7) & 0x01ff01ffu, 0x00de00deu);                   /* - 222 */
-                        const unsigned bC = __vsub2(((cb2 * 129u) >> 6) & 0x03ff03ffu, 0x01140114u);                   /* - 276 */
-                        const unsigned gC = __vsub2(__vsub2(0x00870087u, ((cb2 * 25u) >> 6) & 0x00ff00ffu),            /* 135 - .. - .. */
-                                                    ((cr2 * 13u) >> 4) & 0x00ff00ffu);
-                        const unsigned w = k ? yw.y : yw.x;
-                        const unsigned te = ((mvg_pair_even(w) * 149u) >> 7) & 0x01ff01ffu;       /* pixels 4k, 4k+2 */
-                        const unsigned to = ((mvg_pair_odd(w) * 149u) >> 7) & 0x01ff01ffu;        /* pixels 4k+1, 4k+3 */
+                    for (int r = 0; r < 2; r++) {
+                        const unsigned w = r ? y1 : y0;
+                        const unsigned te = ((mvg_pair_even(w) * 149u) >> 7) & 0x01ff01ffu;       /* pixels 0, 2 */
+                        const unsigned to = ((mvg_pair_odd(w) * 149u) >> 7) & 0x01ff01ffu;        /* pixels 1, 3 */
                         const unsigned Re = mvg_add_clip8x2(te, rC), Ro = mvg_add_clip8x2(to, rC);
                         const unsigned Ge = mvg_add_clip8x2(te, gC), Go = mvg_add_clip8x2(to, gC);
                         const unsigned Be = mvg_add_clip8x2(te, bC), Bo = mvg_add_clip8x2(to, bC);
                         const unsigned X = __byte_perm(Re, Ge, 0x6240);       /* R0 G0 R2 G2 */
                         const unsigned Y = __byte_perm(Be, Ro, 0x6240);       /* B0 R1 B2 R3 */
                         const unsigned Z = __byte_perm(Go, Bo, 0x6240);       /* G1 B1 G3 B3 */
-                        out[3 * k]     = __byte_perm(X, Y, 0x5410);           /* R0 G0 B0 R1 */
-                        out[3 * k + 1] = __byte_perm(Z, X, 0x7610);           /* G1 B1 R2 G2 */
-                        out[3 * k + 2] = __byte_perm(Y, Z, 0x7632);           /* B2 R3 G3 B3 */
+                        unsigned *d = reinterpret_cast<unsigned *>(rgb_dst + r * KF_RGB_STRIDE + 48 * (j & 1));
+                        d[0] = __byte_perm(X, Y, 0x5410);                     /* R0 G0 B0 R1 */
+                        d[1] = __byte_perm(Z, X, 0x7610);                     /* G1 B1 R2 G2 */
+                        d[2] = __byte_perm(Y, Z, 0x7632);                     /* B2 R3 G3 B3 */
                     }
-                    uint2 *d = reinterpret_cast<uint2 *>(rgb_dst + 48 * (j & 1));
-                    d[0] = make_uint2(out[0], out[1]); d[1] = make_uint2(out[2], out[3]); d[2] = make_uint2(out[4], out[5]);
                 }
                 /* next macroblock: row -1, x = 15 / 7 becomes x = -1 */
                 *cn_dst = *cn_src;
@@ -351,7 +370,11 @@ kf_recon(KFParams p)
                         const int ch = lane + 32 * k, r = ch / 6, col = ch - r * 6;
                         if (col < 3 * n_here) {
                             const uint4 v = *reinterpret_cast<const uint4 *>(s.u.rgb + r * KF_RGB_STRIDE + col * 16);
+#ifdef KF_RGB_LINEAR    /* DEV, timing only (wrong picture): the pair's 1536 bytes in one piece instead of 16 row segments */
+                            *reinterpret_cast<uint4 *>(p.rgb + (size_t)slot * ((size_t)n_mb * 768) + ((size_t)row * W + mx - (j & 1)) * 768 + ch * 16) = v;
+#else
                             *reinterpret_cast<uint4 *>(wo_run + (size_t)r * pitch + col * 16) = v;
+#endif
                         }
                     }
                     wo_run += 96;
@@ -359,5 +382,7 @@ kf_recon(KFParams p)
                 }
             }
         }
+        KF_STAT(st[6] += clock64() - trow;)
     }
+    KF_STAT(if (lane == 0 && p.stats) for (int i = 0; i < 8; i++) atomicAdd(p.stats + i, st[i]);)
 }

@@ -1,7 +1,8 @@
 """Dev helper: executed warp instructions of one profiled kernel, per enclosing source function (and per 8-line window
 of the kernel body), normalised per macroblock.  Joins the SASS page of an .ncu-rep (executed counts, address order)
 with `nvdisasm -g` of the SAME libmvgpu.so build (source lines, address order).
-    python scripts/ncu_regions.py <rep> <kernel-substring> <n_macroblocks> [launch-index]"""
+    python scripts/ncu_regions.py <rep> <kernel-substring> <n_macroblocks> [launch-index]
+MVG_SO / MVG_SRC: the libmvgpu.so and the csrc directory of the profiled build (scripts/ncu_kf.sh keeps both)."""
 import collections, csv, io, os, re, subprocess, sys, tempfile
 
 rep, name, n_mb = sys.argv[1], sys.argv[2], float(sys.argv[3])
@@ -46,13 +47,14 @@ if not blocks:
     sys.exit(f"no launch with {len(static)} instructions in the report (is the .so the profiled build?)")
 kname, hdr, rows = blocks[min(which, len(blocks) - 1)]
 iI, iS = hdr.index("Instructions Executed"), hdr.index("# Samples")
+iW, iX = hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Excessive")
 print(kname, "launch", which, ":", len(rows), "SASS instructions")
 
 # ---- source functions
 funcs = {}
 for f in ("mvg_kernels.cuh", "mvg_fused.cuh"):
     cur_f, table = "?", []
-    for i, l in enumerate(open(os.path.join(ROOT, "minivideo_b200/csrc", f)), 1):
+    for i, l in enumerate(open(os.path.join(os.environ.get("MVG_SRC", os.path.join(ROOT, "minivideo_b200/csrc")), f)), 1):
         m = re.match(r"^(?:template.*\n)?(?:__device__|__global__|static|template)[^;]*?\b([A-Za-z_0-9]+)\s*\(", l)
         if m and not l.startswith(" "):
             cur_f = m.group(1)
@@ -62,19 +64,25 @@ for f in ("mvg_kernels.cuh", "mvg_fused.cuh"):
         table.append(cur_f)
     funcs[f] = table
 
-by_f, by_w, samples = collections.Counter(), collections.Counter(), collections.Counter()
+by_f, by_w, samples, wave, wavex = (collections.Counter() for _ in range(5))
 tot = tot_s = 0
 for loc, r in zip(static, rows):
     n, s = int(float(r[iI] or 0)), int(float(r[iS] or 0))
     tot += n; tot_s += s
+    fnw = funcs[loc[0]][loc[1] - 1] if loc else "?"
+    wave[fnw] += int(float(r[iW] or 0)); wavex[fnw] += int(float(r[iX] or 0))
     fn = funcs[loc[0]][loc[1] - 1] if loc else "?"
     by_f[fn] += n; samples[fn] += s
-    if loc and loc[0] == "mvg_fused.cuh":
-        by_w[loc[1] // 8 * 8] += n
+    if loc:
+        by_w[(loc[0], loc[1] // 8 * 8)] += n
 print(f"total {tot / n_mb:7.1f} warp instructions per macroblock, {tot_s} samples")
 for fn, n in by_f.most_common():
-    print(f"  {fn:28s} {n / n_mb:7.1f}  {100 * n / tot:5.1f}% inst  {100 * samples[fn] / max(tot_s, 1):5.1f}% samples")
-print("kernel body by 8-line window (mvg_fused.cuh):")
+    print(f"  {fn:28s} {n / n_mb:7.1f}  {100 * n / tot:5.1f}% inst  {100 * samples[fn] / max(tot_s, 1):5.1f}% samples   "
+          f"shared wavefronts {wave[fn] / n_mb:6.1f} (excess {wavex[fn] / n_mb:5.1f})")
+print(f"  shared-memory wavefronts per macroblock: {sum(wave.values()) / n_mb:.1f}, of which bank conflicts {sum(wavex.values()) / n_mb:.1f}")
+if True:
+    pass
+print("by 8-line window:")
 for w in sorted(by_w):
     if by_w[w] / n_mb >= 1.0:
-        print(f"  line {w:4d}  {by_w[w] / n_mb:7.1f}")
+        print(f"  {w[0]:18s} line {w[1]:4d}  {by_w[w] / n_mb:7.1f}")
