@@ -579,10 +579,21 @@ int mvt_extract(const uint8_t *data, size_t len, const char *base, const char *o
         if (n_gpus > n_batches) n_gpus = n_batches;
         if (n_gpus > 64) n_gpus = 64;
         if (n_gpus < 1) n_gpus = 1;
-        if (!getenv("CUDA_VISIBLE_DEVICES")) {          /* the runtime only wakes the GPUs it can see */
-            char list[256]; int o = 0;
-            for (int g = 0; g < n_gpus && o < 240; g++) o += snprintf(list + o, sizeof list - (size_t)o, g ? ",%d" : "%d", g);
-            setenv("CUDA_VISIBLE_DEVICES", list, 0);
+        /* the runtime only wakes the GPUs it can see: narrow the list (the first n_gpus of the one in force, else
+         * 0 .. n_gpus-1) before the first CUDA call of the process */
+        {
+            char list[512]; int o = 0;
+            const char *vis = getenv("CUDA_VISIBLE_DEVICES");
+            if (vis) {
+                int seen = 0;
+                for (const char *c = vis; *c && o < 500; c++) {
+                    if (*c == ',' && ++seen == n_gpus) break;
+                    list[o++] = *c;
+                }
+                list[o] = 0;
+            } else
+                for (int g = 0; g < n_gpus && o < 500; g++) o += snprintf(list + o, sizeof list - (size_t)o, g ? ",%d" : "%d", g);
+            setenv("CUDA_VISIBLE_DEVICES", list, 1);
         }
     }
     job_t job;

@@ -79,6 +79,12 @@ struct mvg_ctx {
     int pipe_chunk = 0;              /* pictures per mvg_decode_host() chunk, 0 = automatic    */
     MvgTables *d_tab = nullptr;
     MvgLuts *d_luts = nullptr;
+    /* every device allocation (base pointer as returned by cudaMalloc, payload size, name); with MVG_DEBUG_GUARD=1 in the
+     * environment each one sits between two guard bands filled with a pattern that mvg_debug_check() verifies, and its
+     * payload starts out poisoned instead of zero -- the stand-in for compute-sanitizer's memcheck / initcheck */
+    struct Alloc { void *base; size_t bytes; const char *name; };
+    std::vector<Alloc> allocs;
+    bool guard = false;
 
     size_t n_mb_max() const { return (size_t)max_w * max_h; }
     size_t n_mb() const { return (size_t)w_mbs * h_mbs; }
@@ -270,8 +276,27 @@ extern "C" void mvg_build_luts(MvgLuts *out)
 
 extern "C" const char *mvg_last_error(const mvg_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
 
+#define MVG_GUARD_BYTES ((size_t)64 << 10)
+#define MVG_GUARD_BYTE  0xA5
+#define MVG_POISON_BYTE 0x5A
+
+static cudaError_t galloc(mvg_ctx *ctx, void **p, size_t bytes, const char *name)
+{
+    const size_t g = ctx->guard ? MVG_GUARD_BYTES : 0;
+    void *base = nullptr;
+    cudaError_t e = cudaMalloc(&base, bytes + 2 * g);
+    if (e != cudaSuccess) return e;
+    try { ctx->allocs.push_back({base, bytes, name}); } catch (...) { cudaFree(base); return cudaErrorMemoryAllocation; }
+    if (ctx->guard) {
+        e = cudaMemset(base, MVG_GUARD_BYTE, bytes + 2 * g);
+        if (e == cudaSuccess) e = cudaMemset((uint8_t *)base + g, MVG_POISON_BYTE, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    *p = (uint8_t *)base + g;
+    return cudaSuccess;
+}
 template <typename T>
-static cudaError_t dalloc(T **p, size_t count) { return cudaMalloc((void **)p, count * sizeof(T)); }
+static cudaError_t dalloc(mvg_ctx *ctx, T **p, size_t count, const char *name) { return galloc(ctx, (void **)p, count * sizeof(T), name); }
 
 extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mbs, int max_pics)
 {
@@ -288,6 +313,7 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     mvg_ctx *ctx = new (std::nothrow) mvg_ctx;
     if (!ctx) return fail(nullptr, "mvg_create: out of host memory");
     ctx->device = device; ctx->max_w = max_w_mbs; ctx->max_h = max_h_mbs; ctx->max_pics = max_pics;
+    if (const char *gd = getenv("MVG_DEBUG_GUARD")) ctx->guard = gd[0] == '1';
 
     auto bail = [&](const char *what, cudaError_t err) {
         fail(nullptr, "mvg_create: %s: %s", what, cudaGetErrorString(err));
@@ -320,23 +346,23 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
         TRY("event", cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
     }
     const size_t n = ctx->n_mb_max() * (size_t)max_pics;
-    TRY("alloc mb_kind", dalloc(&ctx->d_kind, n));
-    TRY("alloc i16_mode", dalloc(&ctx->d_i16, n));
-    TRY("alloc chroma_mode", dalloc(&ctx->d_cm, n));
-    TRY("alloc qp", dalloc(&ctx->d_qp, n));
-    TRY("alloc cbp", dalloc(&ctx->d_cbp, n));
-    TRY("alloc luma_modes", dalloc(&ctx->d_modes, n * 16));
-    TRY("alloc coeff", dalloc(&ctx->d_coeff, n * 384));
+    TRY("alloc mb_kind", dalloc(ctx, &ctx->d_kind, n, "mb_kind"));
+    TRY("alloc i16_mode", dalloc(ctx, &ctx->d_i16, n, "i16_mode"));
+    TRY("alloc chroma_mode", dalloc(ctx, &ctx->d_cm, n, "chroma_mode"));
+    TRY("alloc qp", dalloc(ctx, &ctx->d_qp, n, "qp"));
+    TRY("alloc cbp", dalloc(ctx, &ctx->d_cbp, n, "cbp"));
+    TRY("alloc luma_modes", dalloc(ctx, &ctx->d_modes, n * 16, "luma_modes"));
+    TRY("alloc coeff", dalloc(ctx, &ctx->d_coeff, n * 384, "coeff"));
     /* d_resid, d_ctl (split pipeline / residual tap) and d_yuv (planar output) are allocated on first use */
-    TRY("alloc tiles", dalloc(&ctx->d_tiles, n * 384));
-    TRY("alloc rgb", dalloc(&ctx->d_rgb, n * 768));
-    TRY("alloc halo", dalloc(&ctx->d_halo, n * 8));
-    TRY("clear halo", cudaMemset(ctx->d_halo, 0, n * 8 * sizeof(uint2)));
-    TRY("alloc work", dalloc(&ctx->d_work, MVG_WORK_RING));
-    TRY("alloc stats", dalloc(&ctx->d_stats, 16));
+    TRY("alloc tiles", dalloc(ctx, &ctx->d_tiles, n * 384, "tiles"));
+    TRY("alloc rgb", dalloc(ctx, &ctx->d_rgb, n * 768, "rgb"));
+    TRY("alloc halo", dalloc(ctx, &ctx->d_halo, n * 8, "halo"));
+    if (!ctx->guard) TRY("clear halo", cudaMemset(ctx->d_halo, 0, n * 8 * sizeof(uint2)));      /* guard mode: poison is as good a "never written" value */
+    TRY("alloc work", dalloc(ctx, &ctx->d_work, MVG_WORK_RING, "work"));
+    TRY("alloc stats", dalloc(ctx, &ctx->d_stats, 16, "stats"));
     TRY("clear stats", cudaMemset(ctx->d_stats, 0, 16 * sizeof(unsigned long long)));
-    TRY("alloc tables", dalloc(&ctx->d_tab, 1));
-    TRY("alloc luts", dalloc(&ctx->d_luts, 1));
+    TRY("alloc tables", dalloc(ctx, &ctx->d_tab, 1, "tables"));
+    TRY("alloc luts", dalloc(ctx, &ctx->d_luts, 1, "luts"));
     MvgLuts luts;
     mvg_build_luts(&luts);
     TRY("upload luts", cudaMemcpy(ctx->d_luts, &luts, sizeof luts, cudaMemcpyHostToDevice));
@@ -350,11 +376,7 @@ extern "C" int mvg_destroy(mvg_ctx *ctx)
     if (!ctx) return MVG_FAILURE;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ctx->d_kind); cudaFree(ctx->d_i16); cudaFree(ctx->d_cm); cudaFree(ctx->d_qp); cudaFree(ctx->d_cbp);
-    cudaFree(ctx->d_modes); cudaFree(ctx->d_coeff); cudaFree(ctx->d_resid); cudaFree(ctx->d_ctl);
-    cudaFree(ctx->d_tiles); cudaFree(ctx->d_yuv); cudaFree(ctx->d_rgb); cudaFree(ctx->d_halo); cudaFree(ctx->d_work); cudaFree(ctx->d_stats);
-    cudaFree(ctx->d_tab); cudaFree(ctx->d_luts);
-    cudaFree(ctx->d_nzb); cudaFree(ctx->d_woff); cudaFree(ctx->d_words); cudaFree(ctx->d_picbase);
+    for (auto &a : ctx->allocs) cudaFree(a.base);
     for (auto &t : ctx->tickets) { if (t.h_picbase) cudaFreeHost(t.h_picbase); if (t.done) cudaEventDestroy(t.done); }
     for (auto ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto ev : ctx->ev_mark) if (ev) cudaEventDestroy(ev);
@@ -419,6 +441,47 @@ extern "C" int mvg_dev_k2_stats(mvg_ctx *ctx, unsigned long long out[16])
     CK(ctx, cudaMemcpy(out, ctx->d_stats, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     CK(ctx, cudaMemset(ctx->d_stats, 0, 16 * sizeof(unsigned long long)));
     return MVG_SUCCESS;
+}
+
+/* DEV: with MVG_DEBUG_GUARD=1, count the guard-band bytes around every device allocation that no longer hold the
+ * pattern (0 = nothing wrote outside its buffer); `report` receives the names of the damaged allocations */
+extern "C" long long mvg_debug_check(mvg_ctx *ctx, char *report, size_t report_cap)
+{
+    if (!ctx) return -1;
+    if (report && report_cap) report[0] = 0;
+    if (!ctx->guard) return 0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return -1;
+    std::vector<uint8_t> h(MVG_GUARD_BYTES);
+    long long bad = 0;
+    for (auto &a : ctx->allocs)
+        for (int side = 0; side < 2; side++) {
+            const uint8_t *src = (const uint8_t *)a.base + (side ? MVG_GUARD_BYTES + a.bytes : 0);
+            if (cudaMemcpy(h.data(), src, MVG_GUARD_BYTES, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+            long long here = 0;
+            for (uint8_t b : h) here += b != MVG_GUARD_BYTE;
+            if (here && report && report_cap) {
+                const size_t o = strlen(report);
+                snprintf(report + o, report_cap - o, "%s%s(%s): %lld bytes", o ? ", " : "", a.name, side ? "after" : "before", here);
+            }
+            bad += here;
+        }
+    return bad;
+}
+
+/* DEV: the violation counters of a -DMVG_CHECKED build ([0] shared-memory address outside the warp record, [1] list
+ * index, [2] canary word overwritten, [3] table index); all zero -- and 0 returned -- in a product build */
+extern "C" int mvg_debug_check_kernels(mvg_ctx *ctx, unsigned long long out[8])
+{
+    if (!ctx || !out) return MVG_FAILURE;
+    memset(out, 0, 8 * sizeof(unsigned long long));
+#ifdef MVG_CHECKED
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaDeviceSynchronize());
+    CK(ctx, cudaMemcpyFromSymbol(out, mvg_check_fail, 8 * sizeof(unsigned long long)));
+    return MVG_SUCCESS;
+#else
+    return MVG_UNSUPPORTED;
+#endif
 }
 
 extern "C" int mvg_device_count(void)
@@ -507,14 +570,14 @@ extern "C" int mvg_clone_slot(mvg_ctx *ctx, int src_slot, int dst_slot)
 /* buffers only some paths need */
 static int ensure_yuv(mvg_ctx *ctx)
 {
-    if (!ctx->d_yuv) CK(ctx, cudaMalloc((void **)&ctx->d_yuv, ctx->n_mb_max() * (size_t)ctx->max_pics * 384));
+    if (!ctx->d_yuv) CK(ctx, dalloc(ctx, &ctx->d_yuv, ctx->n_mb_max() * (size_t)ctx->max_pics * 384, "yuv"));
     return MVG_SUCCESS;
 }
 static int ensure_split(mvg_ctx *ctx)
 {
     const size_t n = ctx->n_mb_max() * (size_t)ctx->max_pics;
-    if (!ctx->d_resid) CK(ctx, cudaMalloc((void **)&ctx->d_resid, n * 768));
-    if (!ctx->d_ctl) CK(ctx, cudaMalloc((void **)&ctx->d_ctl, n * sizeof(MvgMbCtl)));
+    if (!ctx->d_resid) CK(ctx, dalloc(ctx, &ctx->d_resid, n * 384, "residual"));
+    if (!ctx->d_ctl) CK(ctx, dalloc(ctx, &ctx->d_ctl, n, "ctl"));
     return MVG_SUCCESS;
 }
 
@@ -604,7 +667,9 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics; p.group = MVG_K2_GROUP;
         p.sel[0] = 1u; p.sel[1] = 1u << 8; p.sel[2] = 1u << 16; p.sel[3] = 1u << 24;
         p.stats = ctx->d_stats;
-        const int grid = (int)std::min<long long>((items + KF_WARPS - 1) / KF_WARPS, (long long)ctx->sm_count * ctx->kf_ctas_per_sm);
+        /* one CTA per SM; a small batch is spread over as many SMs as it has rows (warps without a row exit at once):
+         * a row's warp then has a scheduler to itself instead of sharing it with five others */
+        const int grid = (int)std::min<long long>(items, (long long)ctx->sm_count * ctx->kf_ctas_per_sm);
         if (rgb_direct) kf_recon<KF_OUT_RGB><<<grid, KF_WARPS * 32, KF_SMEM_BYTES, st>>>(p);
         else kf_recon<KF_OUT_TILES><<<grid, KF_WARPS * 32, KF_SMEM_BYTES, st>>>(p);
         launches++;
@@ -775,7 +840,8 @@ static int take_ticket(mvg_ctx *ctx, mvg_ticket *out)
 {
     for (int i = 0; i < MVG_MAX_TICKETS; i++)
         if (!ctx->tickets[i].busy) {
-            if (!ctx->tickets[i].done) CK(ctx, cudaEventCreateWithFlags(&ctx->tickets[i].done, cudaEventDisableTiming));
+            /* blocking sync: a caller waiting in mvg_wait() sleeps instead of spinning on a host core the parser could use */
+            if (!ctx->tickets[i].done) CK(ctx, cudaEventCreateWithFlags(&ctx->tickets[i].done, cudaEventDisableTiming | cudaEventBlockingSync));
             *out = i;
             return MVG_SUCCESS;
         }
@@ -957,10 +1023,10 @@ extern "C" int mvg_submit_packed(mvg_ctx *ctx, const mvg_packed_batch *b, uint8_
     const size_t n = ctx->n_mb();
     if (!ctx->d_words) {
         const size_t cap = ctx->n_mb_max() * (size_t)ctx->max_pics;
-        CK(ctx, cudaMalloc((void **)&ctx->d_nzb, cap * sizeof(uint32_t)));
-        CK(ctx, cudaMalloc((void **)&ctx->d_woff, cap * sizeof(uint32_t)));
-        CK(ctx, cudaMalloc((void **)&ctx->d_words, cap * MVG_PACKED_WORDS_PER_MB * sizeof(uint16_t)));
-        CK(ctx, cudaMalloc((void **)&ctx->d_picbase, ((size_t)ctx->max_pics * 2 + 2) * sizeof(uint64_t)));
+        CK(ctx, dalloc(ctx, &ctx->d_nzb, cap, "nz_blocks"));
+        CK(ctx, dalloc(ctx, &ctx->d_woff, cap, "word_off"));
+        CK(ctx, dalloc(ctx, &ctx->d_words, cap * MVG_PACKED_WORDS_PER_MB, "words"));
+        CK(ctx, dalloc(ctx, &ctx->d_picbase, (size_t)ctx->max_pics * 2 + 2, "pic_base"));
     }
     if (take_ticket(ctx, ticket) != MVG_SUCCESS) return MVG_FAILURE;
     MvgTicket &tk = ctx->tickets[*ticket];

@@ -70,12 +70,16 @@ struct KFWarpSmem {
         MvgXfScratch<KF_GROUP> x;                       /* transform stage                                      */
         uint8_t rgb[16 * KF_RGB_STRIDE];                /* RGB24 rows of a macroblock pair (prediction stage, KF_OUT_RGB) */
     } u;
+    MVG_CANARY(c0)
     __align__(128) int16_t tile[KF_GROUP * 384];        /* levels in -> residual in place; slot j is refilled with macroblock j
                                                            of the next group as soon as macroblock j has been predicted */
     __align__(8) uint64_t mbar;
+    MVG_CANARY(c1)
     __align__(16) uint8_t lt[MVG_LT_ROWS * MVG_LT_STRIDE];
     __align__(16) uint8_t ct[2][MVG_CT_PLANE];
+    MVG_CANARY(c2)
     __align__(16) uint8_t n8[MVG_N8_BYTES];
+    MVG_CANARY(c3)
 };
 
 #define KF_LUT_BYTES  ((sizeof(MvgLuts) + 127) / 128 * 128)
@@ -128,6 +132,11 @@ kf_recon(KFParams p)
 
     /* per-lane constants (as in k2_wavefront) ------------------------------------------ */
     K2Ctx c;
+#ifdef MVG_CHECKED
+    c.rec_lo = reinterpret_cast<const uint8_t *>(&s); c.rec_hi = c.rec_lo + sizeof(KFWarpSmem);
+    if (lane < 4) s.c0[lane] = s.c1[lane] = s.c2[lane] = s.c3[lane] = MVG_CANARY_WORD;
+    __syncwarp();
+#endif
     c.lt = s.lt; c.ct = &s.ct[0][0]; c.n8 = s.n8; c.lut8 = reinterpret_cast<const uint8_t *>(&luts->lut8[0][lane]);
     c.lane = lane;
     c.sel = p.sel;
@@ -385,4 +394,8 @@ kf_recon(KFParams p)
         KF_STAT(st[6] += clock64() - trow;)
     }
     KF_STAT(if (lane == 0 && p.stats) for (int i = 0; i < 8; i++) atomicAdd(p.stats + i, st[i]);)
+#ifdef MVG_CHECKED
+    __syncwarp();
+    if (lane < 4) MVG_ASSERT(s.c0[lane] == MVG_CANARY_WORD && s.c1[lane] == MVG_CANARY_WORD && s.c2[lane] == MVG_CANARY_WORD && s.c3[lane] == MVG_CANARY_WORD, 2);
+#endif
 }

@@ -25,6 +25,21 @@
 
 #define MVG_FULL 0xffffffffu
 
+/* ---- checked build (-DMVG_CHECKED, tests/tools/checked_build.py): the stand-in for compute-sanitizer, which is closed
+ * on this pool.  Every computed shared-memory address of the prediction stage and every list index of the transform
+ * stage is compared with the bounds of the warp's own record, the records carry canary words between their members,
+ * and violations are counted in a device variable that mvg_debug_check_kernels() reads.  Nothing of this exists in
+ * the product build. */
+#ifdef MVG_CHECKED
+__device__ unsigned long long mvg_check_fail[8];    /* [0] address outside the warp record, [1] list index, [2] canary, [3] table index */
+#define MVG_ASSERT(cond, slot) do { if (!(cond)) atomicAdd(&mvg_check_fail[slot], 1ull); } while (0)
+#define MVG_CANARY(name) uint32_t name[4];
+#define MVG_CANARY_WORD 0xC0DEC0DEu
+#else
+#define MVG_ASSERT(cond, slot) do { } while (0)
+#define MVG_CANARY(name)
+#endif
+
 /* ------------------------------------------------------------------------- */
 /* constant tables                                                             */
 
@@ -376,6 +391,7 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
     for (int base = 0; base < n4; base += 32) {
         if (base + lane < n4) {
             const int u = s.list4[base + lane], j = u / 24, b = u - 24 * j;
+            MVG_ASSERT(base + lane < G * 24 + 8 && j < nmb, 1);
             const unsigned mw = s.meta[j];
             const int kind = mw & 255, qp = (signed char)(mw >> 8);
             const int comp = b < 16 ? 0 : (b < 20 ? 1 : 2);
@@ -424,6 +440,7 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
         int16_t *o8 = tile;
         if (act) {
             const int id = s.list8[slot], j = id >> 2, b8 = id & 3;
+            MVG_ASSERT(slot < G * 4 + 4 && j < nmb, 1);
             const int qp = (signed char)(s.meta[j] >> 8);
             const int qd8 = qp / 6;
             const int32_t *l8 = T.ls8 + (qp - 6 * qd8) * 64 + row * 8;
@@ -582,10 +599,14 @@ struct K2Params {
  * warp's record, hence ctl[] first. */
 struct K2WarpSmem {
     __align__(16) MvgMbCtl ctl[2 * K2_CTL_CHUNK];       /* control records, two chunks: record of macroblock mx at [mx & 63]      */
+    MVG_CANARY(c0)
     __align__(16) int16_t  resid[K2_RING][384];         /* residual ring, filled by per-lane async copies a pair of macroblocks ahead */
+    MVG_CANARY(c1)
     __align__(16) uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
     __align__(16) uint8_t  ct[2][MVG_CT_PLANE];
+    MVG_CANARY(c2)
     __align__(16) uint8_t  n8[MVG_N8_BYTES];            /* Intra8x8 neighbour line: byte planes p', f2, f3; [MVG_N8_DC] = DC */
+    MVG_CANARY(c3)
 };
 
 /* dynamic shared memory: warp records and the tap tables (2 KB aligned, see the kernel) */
@@ -630,6 +651,9 @@ __device__ __forceinline__ unsigned mvg_pairs_to_bytes(unsigned a, unsigned b) {
  * warp-uniform (they come from a lane-0 broadcast, so they live in uniform registers and shared-memory
  * accesses take the form [lane register + uniform base + immediate]) */
 struct K2Ctx {
+#ifdef MVG_CHECKED
+    const uint8_t *rec_lo, *rec_hi;     /* this warp's shared-memory record */
+#endif
     uint8_t *lt, *ct;           /* luma tile, chroma tiles (plane stride MVG_CT_PLANE) */
     uint8_t *n8;
     const uint8_t *resid;       /* residual buffer of the current macroblock */
@@ -721,6 +745,17 @@ __device__ __forceinline__ void k2_luma4_step(const K2Ctx &c, unsigned seq, unsi
     unsigned e;
     asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(m | c.lut4));
     const uint8_t *nb = c.lt + (org1 - MVG_LUT4_BIAS);
+#ifdef MVG_CHECKED
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint8_t *a = nb + __dp4a(e, c.sel[k], c.h4);
+        MVG_ASSERT(a >= c.rec_lo && a < c.rec_hi, 0);
+    }
+    {
+        const uint8_t *a = c.resid + blk0 * 32 + ((by0 & 1) ? c.r4odd : c.r4even);
+        MVG_ASSERT(a >= c.rec_lo && a + 2 <= c.rec_hi, 0);
+    }
+#endif
     int sum = (int)nb[__dp4a(e, c.sel[0], c.h4)] + (int)nb[__dp4a(e, c.sel[1], c.h4)] +
               (int)nb[__dp4a(e, c.sel[2], c.h4)] + (int)nb[__dp4a(e, c.sel[3], c.h4)] + 2;
     int shift = 2;
@@ -828,6 +863,7 @@ __device__ __forceinline__ void k2_luma8_block(const K2Ctx &c, unsigned modes, u
     }
     __syncwarp();
     const unsigned e = *reinterpret_cast<const unsigned *>(c.lut8 + mode * 128);
+    MVG_ASSERT(mode < 16 && (e & 0xffffu) < MVG_N8_BYTES && (e >> 16) < MVG_N8_BYTES, 3);
     const unsigned pp = (unsigned)c.n8[e & 0xffffu] | ((unsigned)c.n8[e >> 16] << 16);
     const unsigned r2 = *reinterpret_cast<const unsigned *>(c.resid + B8 * 128 + lane * 4);
     *reinterpret_cast<uint16_t *>(lt + org + c.s8) = (uint16_t)__byte_perm(mvg_add_clip8x2(pp, r2), 0, 0x4420);
@@ -986,6 +1022,11 @@ k2_wavefront(K2Params p)
 
     /* per-lane constants --------------------------------------------------------------- */
     K2Ctx c;
+#ifdef MVG_CHECKED
+    c.rec_lo = reinterpret_cast<const uint8_t *>(&s); c.rec_hi = c.rec_lo + sizeof(K2WarpSmem);
+    if (lane < 4) s.c0[lane] = s.c1[lane] = s.c2[lane] = s.c3[lane] = MVG_CANARY_WORD;
+    __syncwarp();
+#endif
     c.lt = s.lt; c.ct = &s.ct[0][0]; c.n8 = s.n8; c.lut8 = reinterpret_cast<const uint8_t *>(&luts->lut8[0][lane]);
     c.lane = lane;
     c.sel = p.sel;
@@ -1178,6 +1219,10 @@ k2_wavefront(K2Params p)
         mvg_cp_async_wait<0>();
     }
     K2_PROF(if (lane == 0 && p.stats) { for (int i = 0; i < 8; i++) atomicAdd(p.stats + i, (unsigned long long)pc[i]); atomicAdd(p.stats + 8, (unsigned long long)(clock64() - pt0)); })
+#ifdef MVG_CHECKED
+    __syncwarp();
+    if (lane < 4) MVG_ASSERT(s.c0[lane] == MVG_CANARY_WORD && s.c1[lane] == MVG_CANARY_WORD && s.c2[lane] == MVG_CANARY_WORD && s.c3[lane] == MVG_CANARY_WORD, 2);
+#endif
 }
 
 /* ========================================================================= */

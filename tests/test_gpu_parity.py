@@ -213,3 +213,49 @@ def test_garbage_side_information_terminates_and_leaves_the_context_usable(seed)
     for i in range(3):
         assert np.array_equal(ctx.download_yuv420(i), want[i])
     ctx.close()
+
+
+def test_async_submissions_two_batches_in_flight():
+    """mvg_submit*/mvg_wait (the asynchronous boundary): several submissions in flight through one context -- different
+    batches, packed and dense, RGB and YUV, a context smaller than a batch -- complete with the right bytes whatever the
+    order they are waited for in; mvg_poll answers without blocking; a ticket cannot be waited for twice."""
+    from minivideo_b200 import api, synth
+    from oracle import cpu
+    kw = dict(width_mbs=20, height_mbs=12, profile_idc=100, transform8x8=1, scaling_lists=1)
+    _, a = synth.generate(7, want_stream=False, seed=91, **kw)
+    _, b = synth.generate(5, want_stream=False, seed=91, **kw)          # same tables (lists come from the seed)
+    b = b.pictures(2, 3)
+    want = {"a": cpu.reconstruct(a)[0], "b": cpu.reconstruct(b)[0]}
+    want_rgb = {k: cpu.yuv_to_rgb(v, a.width, a.height, 1) for k, v in want.items()}
+    for slots in (4, 16):
+        ctx = _ctx_for(a, slots)
+        pa, pb = api.Packed(a, pinned=True), api.Packed(b, pinned=True)
+        rgb_a = api.PinnedArray((a.n_pics, a.height, a.width, 3), np.uint8)
+        yuv_b = api.PinnedArray((b.n_pics, a.width * a.height * 3 // 2), np.uint8)
+        rgb_b = api.PinnedArray((b.n_pics, a.height, a.width, 3), np.uint8)
+        rgb_a2 = api.PinnedArray((a.n_pics, a.height, a.width, 3), np.uint8)
+        t1 = api.submit_packed(ctx, pa, None, rgb_a.array, 1)
+        t2 = api.submit_packed(ctx, pb, yuv_b.array, rgb_b.array, 1)
+        keep = []
+        t3 = ctx.submit(a, None, rgb_a2.array, 1, keep)                 # dense levels, third submission in flight
+        assert len({t1, t2, t3}) == 3
+        ctx.wait(t2)                                                    # out of order
+        assert np.array_equal(yuv_b.array, want["b"]) and np.array_equal(rgb_b.array, want_rgb["b"])
+        ctx.wait(t3)
+        assert ctx.poll(t1) is True                                     # submitted before t3: done by now
+        ctx.wait(t1)
+        assert np.array_equal(rgb_a.array, want_rgb["a"]) and np.array_equal(rgb_a2.array, want_rgb["a"])
+        with pytest.raises(api.MvgError, match="not in flight"):
+            ctx.wait(t1)
+        # the blocking calls are submit + wait: same results right after
+        rgb_a.array[...] = 0
+        ctx.decode_host_packed(pa, None, rgb_a.array.reshape(a.n_pics, -1), 1)
+        assert np.array_equal(rgb_a.array, want_rgb["a"])
+        # more than eight submissions in flight are refused with a message, and the context stays usable
+        tickets = [api.submit_packed(ctx, pb, None, rgb_b.array, 1) for _ in range(8)]
+        with pytest.raises(api.MvgError, match="too many submissions"):
+            api.submit_packed(ctx, pb, None, rgb_b.array, 1)
+        for t in tickets:
+            ctx.wait(t)
+        assert np.array_equal(rgb_b.array, want_rgb["b"])
+        ctx.close()
