@@ -658,7 +658,7 @@ static inline int16_t clamp16(int v) { return (int16_t)(v < -32768 ? -32768 : (v
  * level, every fourth run -- so that its branches are periodic; the data-dependent "window nearly empty" test beside
  * them is almost never true.  Between refills a symbol costs shift + table look-up + shift instead of address +
  * load + swap + shift + look-up: the chain from one symbol's length to the next symbol's bits is what bounds CAVLC. */
-static int read_residual_block(br_t *b, int16_t *dst, int stride, int max_num, int nC)
+static int read_residual_block(br_t *b, int16_t *dst, const int stride, const int max_num, int nC)
 {
     const uint8_t *const base = b->p;
     size_t pos = b->pos;

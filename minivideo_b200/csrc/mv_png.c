@@ -19,6 +19,7 @@
  * the bucket of position i+1 (less than 32767 back) matches longer from i+1, position i becomes a literal.
  */
 #include <stdint.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -70,10 +71,16 @@ static uint32_t reverse_bits(uint32_t v, int n)
 static uint16_t lit_code[288]; static uint8_t lit_len[288];
 static uint16_t len_sym[PNG_MAX_MATCH + 1]; static uint8_t len_xbits[PNG_MAX_MATCH + 1]; static uint16_t len_xval[PNG_MAX_MATCH + 1];
 static uint8_t dist_code_rev[30]; static uint16_t dist_base[31]; static uint8_t dist_xbits[30];
-static int tables_ready;
+static pthread_once_t tables_once = PTHREAD_ONCE_INIT;     /* several writer threads encode at once */
+static uint32_t crc_table[256];
 
 static void build_tables(void)
 {
+    for (uint32_t k = 0; k < 256; k++) {
+        uint32_t c = k;
+        for (int b = 0; b < 8; b++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+        crc_table[k] = c;
+    }
     for (int s = 0; s < 288; s++) {
         int code, n;
         if (s < 144) { code = 0x30 + s; n = 8; }
@@ -102,7 +109,6 @@ static void build_tables(void)
         d += 1 << xb;
     }
     dist_base[30] = 32769;
-    __atomic_store_n(&tables_ready, 1, __ATOMIC_RELEASE);
 }
 
 static inline void put_symbol(bitsink *s, int sym) { sink_bits(s, lit_code[sym], lit_len[sym]); }
@@ -205,18 +211,8 @@ static uint32_t adler32(const uint8_t *d, size_t n)
     return (b << 16) | a;
 }
 
-static uint32_t crc_table[256]; static int crc_ready;
-
-static uint32_t crc32_png(const uint8_t *d, size_t n)
+static uint32_t crc32_png(const uint8_t *d, size_t n)       /* tables: build_tables(), once */
 {
-    if (!__atomic_load_n(&crc_ready, __ATOMIC_ACQUIRE)) {
-        for (uint32_t k = 0; k < 256; k++) {
-            uint32_t c = k;
-            for (int b = 0; b < 8; b++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
-            crc_table[k] = c;
-        }
-        __atomic_store_n(&crc_ready, 1, __ATOMIC_RELEASE);
-    }
     uint32_t c = ~0u;
     for (size_t i = 0; i < n; i++) c = (c >> 8) ^ crc_table[(c ^ d[i]) & 255];
     return ~c;
@@ -263,7 +259,7 @@ uint8_t *mvt_png_encode(const uint8_t *rgb, int w, int h, size_t *out_len)
 {
     if (out_len) *out_len = 0;
     if (!rgb || !out_len || w < 1 || h < 1 || (long long)w * 3 + 1 > 0x7fffffff / h) return NULL;
-    if (!__atomic_load_n(&tables_ready, __ATOMIC_ACQUIRE)) build_tables();
+    pthread_once(&tables_once, build_tables);
     const int row_bytes = 3 * w;
     const int n = (row_bytes + 1) * h;
     uint8_t *filt = malloc((size_t)n), *scratch = malloc((size_t)row_bytes * 6);

@@ -329,9 +329,14 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     TRY("occupancy k1", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_ctas_per_sm, k1_dequant_idct, K1_WARPS * 32, sizeof(K1WarpSmem) * K1_WARPS));
     TRY("k2 shared memory", cudaFuncSetAttribute(k2_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM_BYTES));
     TRY("occupancy k2", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2_ctas_per_sm, k2_wavefront, K2_WARPS * 32, K2_SMEM_BYTES));
-    TRY("kf shared memory", cudaFuncSetAttribute(kf_recon<KF_OUT_TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES));
-    TRY("kf shared memory", cudaFuncSetAttribute(kf_recon<KF_OUT_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES));
-    TRY("occupancy kf", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->kf_ctas_per_sm, kf_recon<KF_OUT_RGB>, KF_WARPS * 32, KF_SMEM_BYTES));
+    TRY("kf shared memory", cudaFuncSetAttribute(kf_recon<KF_OUT_TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES(KF_OUT_TILES)));
+    TRY("kf shared memory", cudaFuncSetAttribute(kf_recon<KF_OUT_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES(KF_OUT_RGB)));
+    {
+        int a = 0, b = 0;
+        TRY("occupancy kf", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, kf_recon<KF_OUT_RGB>, KF_WARPS_OF(KF_OUT_RGB) * 32, KF_SMEM_BYTES(KF_OUT_RGB)));
+        TRY("occupancy kf", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kf_recon<KF_OUT_TILES>, KF_WARPS_OF(KF_OUT_TILES) * 32, KF_SMEM_BYTES(KF_OUT_TILES)));
+        ctx->kf_ctas_per_sm = std::min(a, b);
+    }
     if (ctx->k1_ctas_per_sm < 1 || ctx->k2_ctas_per_sm < 1 || ctx->kf_ctas_per_sm < 1)
         return bail("kernel does not fit on an SM", cudaErrorLaunchOutOfResources);
     if (const char *m = getenv("MVG_PIPELINE")) ctx->mode = strcmp(m, "split") == 0 ? MVG_PIPELINE_SPLIT : MVG_PIPELINE_FUSED;
@@ -670,8 +675,8 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         /* one CTA per SM; a small batch is spread over as many SMs as it has rows (warps without a row exit at once):
          * a row's warp then has a scheduler to itself instead of sharing it with five others */
         const int grid = (int)std::min<long long>(items, (long long)ctx->sm_count * ctx->kf_ctas_per_sm);
-        if (rgb_direct) kf_recon<KF_OUT_RGB><<<grid, KF_WARPS * 32, KF_SMEM_BYTES, st>>>(p);
-        else kf_recon<KF_OUT_TILES><<<grid, KF_WARPS * 32, KF_SMEM_BYTES, st>>>(p);
+        if (rgb_direct) kf_recon<KF_OUT_RGB><<<grid, KF_WARPS_OF(KF_OUT_RGB) * 32, KF_SMEM_BYTES(KF_OUT_RGB), st>>>(p);
+        else kf_recon<KF_OUT_TILES><<<grid, KF_WARPS_OF(KF_OUT_TILES) * 32, KF_SMEM_BYTES(KF_OUT_TILES), st>>>(p);
         launches++;
     } else {
         K2Params p;

@@ -23,8 +23,12 @@
                                makes the transform stage cheap (2 macroblocks: 6.1 ms, 4: 5.4 ms per 1000 pictures) */
 #endif
 #ifndef KF_WARPS
-#define KF_WARPS 24         /* warps per CTA; one CTA per SM */
+#define KF_WARPS 24         /* warps per CTA (one CTA per SM), RGB mode: its staging traffic saturates the LSU pipe first, more warps make it slower */
 #endif
+#ifndef KF_WARPS_TILES
+#define KF_WARPS_TILES 28   /* tiles mode: 5.19 ms per 1000 pictures at 28 warps against 5.31 at 24 */
+#endif
+#define KF_WARPS_OF(out) ((out) == 1 ? KF_WARPS : KF_WARPS_TILES)
 #ifndef KF_COMPACT8
 #define KF_COMPACT8 false   /* true: Intra8x8 blocks through one run-time-indexed copy of the code (smaller, 4 % slower) */
 #endif
@@ -84,7 +88,7 @@ struct KFWarpSmem {
 
 #define KF_LUT_BYTES  ((sizeof(MvgLuts) + 127) / 128 * 128)
 #define KF_TAB_BYTES  ((sizeof(MvgXfTables) + 127) / 128 * 128)
-#define KF_SMEM_BYTES (sizeof(KFWarpSmem) * KF_WARPS + 2048 + KF_LUT_BYTES + KF_TAB_BYTES)
+#define KF_SMEM_BYTES(out) (sizeof(KFWarpSmem) * KF_WARPS_OF(out) + 2048 + KF_LUT_BYTES + KF_TAB_BYTES)
 
 /* Persistent warps, one CTA per SM.  A work item is one macroblock row of one picture (claimed from an atomic
  * counter, rows of a picture in order, pictures interleaved: see k2_wavefront for the dependency protocol, which
@@ -98,7 +102,7 @@ struct KFWarpSmem {
 #ifdef KF_MAXREG
 #define KF_BOUNDS __maxnreg__(KF_MAXREG)        /* explicit register budget (the block size is given at launch) */
 #else
-#define KF_BOUNDS __launch_bounds__(KF_WARPS * 32, 1)
+#define KF_BOUNDS __launch_bounds__(KF_WARPS_OF(OUT) * 32, 1)
 #endif
 template <int OUT>
 __global__ void KF_BOUNDS
