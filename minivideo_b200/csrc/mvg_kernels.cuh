@@ -62,6 +62,12 @@ __device__ __forceinline__ int mvg_lane()
     return l;
 }
 
+/* A per-lane INTEGER constant computed once in a kernel's prologue, made opaque so that the compiler keeps it in a
+ * register instead of re-deriving it from the lane index inside the row loop.  Only for integers (offsets): a pointer
+ * that goes through an asm loses its address space, and every access through it becomes a generic load or store. */
+__device__ __forceinline__ int mvg_keep(int v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ unsigned mvg_keep(unsigned v) { asm volatile("" : "+r"(v)); return v; }
+
 /* Table 8-15: QPC as a function of qPI >= 30 (h264_transform.c:71) */
 __constant__ unsigned char mvg_qpc_tab[22] = {29,30,31,32,32,33,34,34,35,35,36,36,37,37,37,38,38,38,39,39,39,39};
 
