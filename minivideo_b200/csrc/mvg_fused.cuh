@@ -41,11 +41,30 @@
 #define KF_STAGGER 12       /* distance (macroblocks) a row keeps from the row above: waited for at the row start and
                                again whenever the row catches up; the halo prefetch reaches 10 macroblocks ahead */
 #endif
+#ifndef KF_MBS
+#define KF_MBS 392          /* int16 per macroblock slot of the level buffer: 768 bytes of levels + 16 of padding, so that the DC
+                               levels of the group's macroblocks fall into different banks (see mvg_xf_group) */
+#endif
 #define KF_OUT_TILES 0
 #define KF_OUT_RGB   1
-/* RGB staging rows of a PAIR of macroblocks: 2 x 48 bytes + padding that makes the 8-byte stores of the conversion
- * (lane = 2 y + h, 24 bytes apart) free of bank conflicts: 28 y + 6 h words cover 16 distinct bank pairs */
+/* RGB staging of a PAIR of macroblocks: 16 rows of 2 x 48 bytes + 16 of padding (7 pieces of 16 bytes: 7 is odd, so
+ * eight consecutive rows start in eight different 16-byte bank groups).  KF_RGB_PERM: picture row R sits in staging row
+ * (R >> 1) + 8 (R & 1), even rows first.  The conversion's lane 4 q + h stores words 3 h + w of picture rows 2 q and
+ * 2 q + 1 = staging rows q and q + 8: banks 28 q + 3 h + w, all different over a warp; the write-out reads staging row
+ * l & 15, pieces 2 k + (l >> 4): conflict-free as well.  (Picture order: both are two-way conflicts.) */
 #define KF_RGB_STRIDE 112
+#ifndef KF_OPAQUE_BASE
+#define KF_OPAQUE_BASE 1
+#endif
+#ifndef KF_HALO_FAST
+#define KF_HALO_FAST 1      /* one comparison per macroblock while the whole group of halo words above is valid */
+#endif
+#ifndef KF_LCOL_COPY
+#define KF_LCOL_COPY 1      /* RGB mode: left-column hand-over as a one-sample-per-lane copy */
+#endif
+#ifndef KF_RGB_PERM
+#define KF_RGB_PERM 0
+#endif
 
 struct KFParams {
     const uint8_t *mb_kind, *i16_mode, *chroma_mode, *luma_modes;   /* [slot][n_mb](x16), slot 0 */
@@ -77,7 +96,7 @@ struct KFWarpSmem {
         uint8_t rgb[16 * KF_RGB_STRIDE];                /* RGB24 rows of a macroblock pair (prediction stage, KF_OUT_RGB) */
     } u;
     MVG_CANARY(c0)
-    __align__(128) int16_t tile[KF_GROUP * 384];        /* levels in -> residual in place; slot j is refilled with macroblock j
+    __align__(128) int16_t tile[KF_GROUP * KF_MBS];        /* levels in -> residual in place; slot j is refilled with macroblock j
                                                            of the next group as soon as macroblock j has been predicted */
     __align__(8) uint64_t mbar;
     MVG_CANARY(c1)
@@ -116,6 +135,20 @@ kf_recon(KFParams p)
     /* layout: the tap tables sit on the first 2 KB boundary (so that (mode << 7) can be OR-ed into a lane's
      * table address), the dequantisation tables behind them; warp records fill the space before, the rest follow */
     const unsigned base = mvg_smem_u32(kf_smem);
+#if KF_OPAQUE_BASE
+    /* The addresses everything hangs on -- the tables and this warp's record -- as opaque warp-uniform 32-bit shared
+     * addresses.  Left to itself the compiler carries them as (shared window base) + (offset) in two uniform registers,
+     * spends two instructions per lane-dependent address on adding them up and, worse, re-derives the window base inside
+     * the row loop from a special register (S2R SR_CgaCtaId: tens of cycles each time). */
+    const unsigned lut_addr = __shfl_sync(MVG_FULL, mvg_keep((base + 2047u) & ~2047u), 0);
+    const unsigned n_before = (lut_addr - base) / (unsigned)sizeof(KFWarpSmem);
+    MvgLuts *luts = reinterpret_cast<MvgLuts *>(__cvta_shared_to_generic(lut_addr));
+    MvgXfTables &T = *reinterpret_cast<MvgXfTables *>(__cvta_shared_to_generic(lut_addr + (unsigned)KF_LUT_BYTES));
+    unsigned rec_addr = base + (wid < n_before ? wid * (unsigned)sizeof(KFWarpSmem)
+                                               : (lut_addr - base) + (unsigned)(KF_LUT_BYTES + KF_TAB_BYTES) + (wid - n_before) * (unsigned)sizeof(KFWarpSmem));
+    rec_addr = __shfl_sync(MVG_FULL, mvg_keep(rec_addr), 0);
+    KFWarpSmem &s = *reinterpret_cast<KFWarpSmem *>(__cvta_shared_to_generic(rec_addr));
+#else
     const unsigned lut_addr = (base + 2047u) & ~2047u;
     const unsigned n_before = (lut_addr - base) / (unsigned)sizeof(KFWarpSmem);
     MvgLuts *luts = reinterpret_cast<MvgLuts *>(kf_smem + (lut_addr - base));
@@ -123,6 +156,7 @@ kf_recon(KFParams p)
     KFWarpSmem &s = *reinterpret_cast<KFWarpSmem *>(
         wid < n_before ? kf_smem + wid * sizeof(KFWarpSmem)
                        : kf_smem + (lut_addr - base) + KF_LUT_BYTES + KF_TAB_BYTES + (wid - n_before) * sizeof(KFWarpSmem));
+#endif
     for (int i = threadIdx.x; i < (int)(sizeof(MvgLuts) / 16); i += blockDim.x)
         reinterpret_cast<uint4 *>(luts)[i] = __ldg(reinterpret_cast<const uint4 *>(p.luts) + i);
     mvg_xf_load_tables(T, p.tab);
@@ -192,6 +226,7 @@ kf_recon(KFParams p)
      *          the chroma row                                                                                      */
     const uint8_t *wo_src, *wo_csrc = nullptr;
     uint8_t *lc_dst, *lc_cdst = nullptr, *rgb_dst = nullptr;
+    const uint8_t *lc_src = nullptr;
     int wo_off = 0;
     if (OUT == KF_OUT_TILES) {
         wo_src = lane < 16 ? s.lt + K2_TO(0, lane) : s.ct[(lane >> 3) & 1] + K2_CO(0, lane & 7);
@@ -203,7 +238,13 @@ kf_recon(KFParams p)
         wo_csrc = s.ct[0] + K2_CO(2 * h, q);
         lc_dst = s.lt + K2_TO(-1, 2 * q);
         lc_cdst = s.ct[0] + K2_CO(-1, q);
-        rgb_dst = s.u.rgb + 2 * q * KF_RGB_STRIDE + 12 * h;
+#if KF_LCOL_COPY
+        /* the left neighbour column of the next macroblock by a copy of its own, one sample per lane (rows 0..15 of
+         * luma, 0..7 of Cb, 0..7 of Cr): one load and one store instead of four predicated byte stores */
+        lc_dst = lane < 16 ? s.lt + K2_TO(-1, lane) : s.ct[(lane >> 3) & 1] + K2_CO(-1, lane & 7);
+        lc_src = lc_dst + (lane < 16 ? 16 : 8);
+#endif
+        rgb_dst = s.u.rgb + (KF_RGB_PERM ? q : 2 * q) * KF_RGB_STRIDE + 12 * h;
     }
     const unsigned lc_sel = lane < 16 ? 7u : 3u;            /* tiles: byte 3 of the second / first 8-byte piece */
     const int pitch = 48 * W;                               /* bytes per RGB24 picture row */
@@ -229,10 +270,11 @@ kf_recon(KFParams p)
         /* group 0: levels and side information.  The buffer was last touched by this warp's generic-proxy
          * accesses (residual of an earlier group): order them before the asynchronous write. */
         if (lane == 0) {
-            const unsigned bytes = (unsigned)min(KF_GROUP, W) * 768u;
+            const int n0 = min(KF_GROUP, W);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mvg_mbar_expect_tx(&s.mbar, bytes);
-            mvg_bulk_load(s.tile, lv_row, bytes, &s.mbar);
+            mvg_mbar_expect_tx(&s.mbar, (unsigned)n0 * 768u);
+            if (KF_MBS == 384) mvg_bulk_load(s.tile, lv_row, (unsigned)n0 * 768u, &s.mbar);
+            else for (int j = 0; j < n0; j++) mvg_bulk_load(s.tile + j * KF_MBS, lv_row + j * 384, 768u, &s.mbar);
         }
         unsigned nmeta = side.load(lane, (long long)mb0, min(KF_GROUP, W));
 
@@ -271,7 +313,7 @@ kf_recon(KFParams p)
             if (n_next > 0 && lane == 0) mvg_mbar_expect_tx(&s.mbar, (unsigned)n_next * 768u);
 
             /* ---- levels -> residual, in place (kernel 1's stage) ---- */
-            mvg_xf_group<KF_GROUP>(tile, s.u.x, T, meta, nmb, lane);
+            mvg_xf_group<KF_GROUP, KF_MBS>(tile, s.u.x, T, meta, nmb, lane);
             const uint4 rec = mvg_ctl_from_meta(meta);      /* valid in lane 8 j */
 
             for (int j = 0; j < nmb; j++) {
@@ -285,9 +327,14 @@ kf_recon(KFParams p)
                     }
                     /* words needed now: the 8 of the macroblock above and, for the up-right neighbour, the first
                      * two of the next one, which sit in qb when this is the last macroblock of the group */
-                    const unsigned need = availC ? 0x3FFu : 0xFFu;
-                    unsigned have = __funnelshift_r(okA, hj == 3 ? __ballot_sync(MVG_FULL, qb.y == epoch) : 0u, 8 * hj);
-                    if ((have & need) != need) {
+                    /* the common case first: all 32 words of the group are this launch's (lanes past the end of the row
+                     * hold the epoch from their initialisation), and so are the two of the next group where they matter */
+                    bool all_ok = KF_HALO_FAST && okA == MVG_FULL;
+                    if (hj == 3 && availC) all_ok = all_ok && (__ballot_sync(MVG_FULL, qb.y == epoch) & 3u) == 3u;
+                    if (!all_ok) {
+                      const unsigned need = availC ? 0x3FFu : 0xFFu;
+                      unsigned have = __funnelshift_r(okA, hj == 3 ? __ballot_sync(MVG_FULL, qb.y == epoch) : 0u, 8 * hj);
+                      if ((have & need) != need) {
                         /* This row has caught up with the row above.  Do not follow it at the minimum distance: rows in
                          * lock step find the words they prefetch a group ahead stale every time and pay a round trip to
                          * L2 per macroblock.  Fall back until the row above is KF_STAGGER macroblocks ahead again, then
@@ -302,6 +349,7 @@ kf_recon(KFParams p)
                             okA = __ballot_sync(MVG_FULL, qa.y == epoch);
                             have = __funnelshift_r(okA, __ballot_sync(MVG_FULL, qb.y == epoch), 8 * hj);
                         } while ((have & need) != need);
+                      }
                     }
                     /* sample row -1 of the tiles: lanes 0..7 the macroblock above, lanes 8,9 x = 16..23 */
                     const unsigned src = (hj == 3 && lane < 2) ? qb.x : qa.x;
@@ -315,7 +363,7 @@ kf_recon(KFParams p)
                     qb = make_uint2(0, epoch);
                     if (mx * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(ha_run + 32);
                 }
-                c.resid = reinterpret_cast<const uint8_t *>(tile + j * 384);
+                c.resid = reinterpret_cast<const uint8_t *>(tile + j * KF_MBS);
                 const unsigned cx = __shfl_sync(MVG_FULL, rec.x, 8 * j), cy = __shfl_sync(MVG_FULL, rec.y, 8 * j);
                 const unsigned cz = __shfl_sync(MVG_FULL, rec.z, 8 * j);
 
@@ -346,10 +394,14 @@ kf_recon(KFParams p)
                     const unsigned y1 = *reinterpret_cast<const unsigned *>(wo_src + MVG_LT_STRIDE);
                     const unsigned cb2 = mvg_pair_lo(*reinterpret_cast<const uint16_t *>(wo_csrc));
                     const unsigned cr2 = mvg_pair_lo(*reinterpret_cast<const uint16_t *>(wo_csrc + MVG_CT_PLANE));
+#if KF_LCOL_COPY
+                    *lc_dst = *lc_src;                                  /* x = 15 / 7 -> x = -1 of my row */
+#else
                     if ((lane & 3) == 3) {      /* x = 15 of both luma rows, x = 7 of the chroma row: the next macroblock's left column */
                         lc_dst[0] = (uint8_t)(y0 >> 24); lc_dst[MVG_LT_STRIDE] = (uint8_t)(y1 >> 24);
                         lc_cdst[0] = (uint8_t)(cb2 >> 16); lc_cdst[MVG_CT_PLANE] = (uint8_t)(cr2 >> 16);
                     }
+#endif
                     /* the terms that do not depend on Y: pixels x and x + 2 of a row use chroma samples c and c + 1 */
                     const unsigned rC = __vsub2(((cr2 * 204u) >> 7) & 0x01ff01ffu, 0x00de00deu);                   /* - 222 */
                     const unsigned bC = __vsub2(((cb2 * 129u) >> 6) & 0x03ff03ffu, 0x01140114u);                   /* - 276 */
@@ -366,7 +418,7 @@ kf_recon(KFParams p)
                         const unsigned X = __byte_perm(Re, Ge, 0x6240);       /* R0 G0 R2 G2 */
                         const unsigned Y = __byte_perm(Be, Ro, 0x6240);       /* B0 R1 B2 R3 */
                         const unsigned Z = __byte_perm(Go, Bo, 0x6240);       /* G1 B1 G3 B3 */
-                        unsigned *d = reinterpret_cast<unsigned *>(rgb_dst + r * KF_RGB_STRIDE + 48 * (j & 1));
+                        unsigned *d = reinterpret_cast<unsigned *>(rgb_dst + r * (KF_RGB_PERM ? 8 : 1) * KF_RGB_STRIDE + 48 * (j & 1));
                         d[0] = __byte_perm(X, Y, 0x5410);                     /* R0 G0 B0 R1 */
                         d[1] = __byte_perm(Z, X, 0x7610);                     /* G1 B1 R2 G2 */
                         d[2] = __byte_perm(Y, Z, 0x7632);                     /* B2 R3 G3 B3 */
@@ -378,12 +430,25 @@ kf_recon(KFParams p)
                 /* this macroblock's residual is spent: its slot takes macroblock j of the next group */
                 if (j < n_next && lane == 0) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mvg_bulk_load(tile + j * 384, lv_row + (size_t)(mx + KF_GROUP) * 384, 768u, &s.mbar);
+                    mvg_bulk_load(tile + j * KF_MBS, lv_row + (size_t)(mx + KF_GROUP) * 384, 768u, &s.mbar);
                 }
                 if (OUT == KF_OUT_RGB && ((j & 1) || j == nmb - 1)) {
                     /* the pair's 16 rows x 96 bytes (48 for a lone last macroblock): 16-byte chunks in row-major order over
                      * the lanes, so that a pair leaves as whole 32-byte sectors (96 bytes per row at a multiple of 96) */
                     const int n_here = (j & 1) + 1;
+#if KF_RGB_PERM
+                    {
+                        /* lane l: staging row l & 15 = picture row 2 (l & 7) + (l >> 3 & 1), 16-byte pieces 2 k + (l >> 4) of
+                         * its 6 (3 for a lone last macroblock): a row's two pieces of one instruction are one 32-byte sector */
+                        const int sr = lane & 15, cpar = lane >> 4, R = 2 * (sr & 7) + (sr >> 3);
+                        const uint8_t *rd = s.u.rgb + sr * KF_RGB_STRIDE + cpar * 16;
+                        uint8_t *gd = wo_run + (size_t)R * pitch + cpar * 16;
+#pragma unroll
+                        for (int k = 0; k < 3; k++)
+                            if (2 * k + cpar < 3 * n_here)
+                                *reinterpret_cast<uint4 *>(gd + 32 * k) = *reinterpret_cast<const uint4 *>(rd + 32 * k);
+                    }
+#else
 #pragma unroll
                     for (int k = 0; k < 3; k++) {
                         const int ch = lane + 32 * k, r = ch / 6, col = ch - r * 6;
@@ -396,6 +461,7 @@ kf_recon(KFParams p)
 #endif
                         }
                     }
+#endif
                     wo_run += 96;
                     __syncwarp();
                 }

@@ -187,6 +187,12 @@ __device__ __forceinline__ unsigned mvg_pack_shr6(int hi, int lo)
     return __vsub2(t, 0x02000200u);
 }
 
+#ifndef MVG_CLS_SWAP
+#define MVG_CLS_SWAP 1      /* classification pass of mvg_xf_group: bank-conflict-free half order (0: the plain order, for comparison) */
+#endif
+#ifndef MVG_GEN_SWAP
+#define MVG_GEN_SWAP 0
+#endif
 #define K1_WARPS 12         /* warps per CTA; two CTAs per SM     */
 #define K1_GROUP 4          /* macroblocks per warp iteration     */
 #define K1_TILE  (K1_GROUP * 384)
@@ -305,9 +311,12 @@ struct MvgSideInfo {
  *   - non-zero 8x8 blocks (Intra8x8 luma, quant8x8/idct8x8 :1256-1383) are compacted the same
  *     way and transformed 4 per pass, 8 lanes per block, transposed through shared memory.
  * `meta` = the group's side information (MvgSideInfo), nmb = macroblocks present (1..G).  Warp-collective. */
-template <int G>
+template <int G, int MBS = 384>
 __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, const MvgXfTables &T, unsigned meta, int nmb, int lane)
 {
+    /* MBS = int16 per macroblock slot of `tile`: 384 when the group is one contiguous piece (kernel 1: it leaves with one
+     * bulk store), 392 in the fused kernel -- 16 bytes of padding per macroblock put the DC levels of the four macroblocks
+     * (every 32 bytes: banks 0, 8, 16, 24 only) into different banks */
     const int mj = lane >> 3, mt = lane & 7;
     /* per-lane view of "my" macroblock j = lane >> 3 */
     const int kind_j = (int)__shfl_sync(MVG_FULL, meta, (lane & ~7) + 4);
@@ -317,7 +326,7 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
 
     /* ---------------- DC transforms ---------------- */
     if (mj < nmb) {
-        const int16_t *cf = tile + mj * 384;
+        const int16_t *cf = tile + mj * MBS;
         if (kind_j == MVG_MB_I16x16 && mt < 4) {         /* row mt of c: t = c * H */
             const int a = cf[mvg_blk_of(0, mt) * 16], b = cf[mvg_blk_of(1, mt) * 16];
             const int c = cf[mvg_blk_of(2, mt) * 16], d = cf[mvg_blk_of(3, mt) * 16];
@@ -360,11 +369,23 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
         const unsigned mw = s.meta[j];
         const int kind = mw & 255, qp = (signed char)(mw >> 8);
         const bool is8 = kind == MVG_MB_I8x8 && b < 16;
-        uint4 *blk = reinterpret_cast<uint4 *>(tile + j * 384 + b * 16);
+        uint4 *blk = reinterpret_cast<uint4 *>(tile + j * MBS + b * 16);
+#if MVG_CLS_SWAP
+        /* a lane's block is two 16-byte halves 32 bytes apart from its neighbour's: read in the same order by all lanes,
+         * the eight lanes of a quarter warp touch only four of the eight 16-byte bank groups (two wavefronts per quarter).
+         * Lanes 4..7 of every eight take the second half first: 2 l + (l >> 2 & 1) covers all eight groups. */
+        const int o = (lane >> 2) & 1;
+        const uint4 wa = blk[o], wb = blk[o ^ 1];
+        const unsigned x0 = o ? wb.x : wa.x, x4 = o ? wa.x : wb.x;        /* first word of the first / second half */
+        const unsigned rest = (x0 & 0xffff0000u) | x4 | wa.y | wa.z | wa.w | wb.y | wb.z | wb.w;
+#else
+        const int o = 0;
         const uint4 w0 = blk[0], w1 = blk[1];
+        const unsigned x0 = w0.x;
         const unsigned rest = (w0.x & 0xffff0000u) | w0.y | w0.z | w0.w | w1.x | w1.y | w1.z | w1.w;
-        const int dcraw = (short)(w0.x & 0xffff);
-        const bool nz8q = live && is8 && (rest | (w0.x & 0xffffu)) != 0;
+#endif
+        const int dcraw = (short)(x0 & 0xffff);
+        const bool nz8q = live && is8 && (rest | (x0 & 0xffffu)) != 0;
         const bool general = live && !is8 && rest != 0;
         {
             /* DC only: every residual sample is (d00 + 32) >> 6.  d00 = c00 (already dequantised by the DC
@@ -377,7 +398,7 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
             const int rv = min(max((d + 32) >> 6, -512), 511);
             if (live && !is8 && rest == 0 && (rv != 0 || dcraw != 0)) {
                 const unsigned pk = (unsigned)(rv & 0xffff) * 0x10001u;
-                blk[0] = make_uint4(pk, pk, pk, pk); blk[1] = make_uint4(pk, pk, pk, pk);
+                blk[o] = make_uint4(pk, pk, pk, pk); blk[o ^ 1] = make_uint4(pk, pk, pk, pk);
             }
         }
         const unsigned gb = __ballot_sync(MVG_FULL, general);
@@ -402,8 +423,14 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
             const int kind = mw & 255, qp = (signed char)(mw >> 8);
             const int comp = b < 16 ? 0 : (b < 20 ? 1 : 2);
             const int qpb = comp ? (T.qpc[comp - 1][qp] & 255) : qp;
-            uint4 *blk = reinterpret_cast<uint4 *>(tile + j * 384 + b * 16);
+            uint4 *blk = reinterpret_cast<uint4 *>(tile + j * MBS + b * 16);
+#if MVG_GEN_SWAP    /* same half order trick as in the classification pass; the halves are swapped back with selects */
+            const int o = (lane >> 2) & 1;
+            const uint4 h0 = blk[o], h1 = blk[o ^ 1];
+            const uint4 a = o ? h1 : h0, bb = o ? h0 : h1;
+#else
             const uint4 a = blk[0], bb = blk[1];
+#endif
             int c[16];                      /* zig-zag k -> (row,col): utils.h:64 / spec Table 8-13 */
             c[0] = (short)(a.x & 0xffff); c[1] = (int)a.x >> 16; c[4] = (short)(a.y & 0xffff); c[8] = (int)a.y >> 16;
             c[5] = (short)(a.z & 0xffff); c[2] = (int)a.z >> 16; c[3] = (short)(a.w & 0xffff); c[6] = (int)a.w >> 16;
@@ -434,7 +461,11 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
             o0.z = mvg_pack_shr6(c[5], c[4]);   o0.w = mvg_pack_shr6(c[7], c[6]);
             o1.x = mvg_pack_shr6(c[9], c[8]);   o1.y = mvg_pack_shr6(c[11], c[10]);
             o1.z = mvg_pack_shr6(c[13], c[12]); o1.w = mvg_pack_shr6(c[15], c[14]);
+#if MVG_GEN_SWAP
+            blk[o] = o ? o1 : o0; blk[o ^ 1] = o ? o0 : o1;
+#else
             blk[0] = o0; blk[1] = o1;
+#endif
         }
     }
 
@@ -450,7 +481,7 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
             const int qp = (signed char)(s.meta[j] >> 8);
             const int qd8 = qp / 6;
             const int32_t *l8 = T.ls8 + (qp - 6 * qd8) * 64 + row * 8;
-            const int16_t *in = tile + j * 384 + b8 * 64;
+            const int16_t *in = tile + j * MBS + b8 * 64;
             const uint2 zz = *reinterpret_cast<const uint2 *>(T.zz8inv + row * 8);   /* scan positions of my row */
 #pragma unroll
             for (int q = 0; q < 8; q++) {
@@ -467,7 +498,7 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
             mvg_idct8_1d(v);                                                /* row pass */
 #pragma unroll
             for (int q = 0; q < 8; q++) s.tr[lane >> 3][row][q] = v[q];
-            o8 = tile + j * 384 + (b8 * 4 + (row >> 2)) * 16 + (row & 3);
+            o8 = tile + j * MBS + (b8 * 4 + (row >> 2)) * 16 + (row & 3);
         }
         __syncwarp();
         if (act) {
