@@ -56,6 +56,28 @@
 #ifndef KF_OPAQUE_BASE
 #define KF_OPAQUE_BASE 1
 #endif
+/* KF_WO_GROUP: the RGB24 of a whole group of four macroblocks is staged and written out once per group.  Staging: 16
+ * rows of 4 x 48 bytes + 16 of padding = 13 pieces of 16 bytes (odd: eight consecutive rows start in eight different
+ * 16-byte bank groups), even picture rows in staging rows 0..7, odd ones in 8..15.  The conversion's lane 4 q + h stores
+ * words 3 h + w of picture rows 2 q, 2 q + 1 = staging rows q, q + 8: banks 52 q + 3 h + w, all 32 different.  The
+ * write-out moves 64-byte pieces: the eight lanes of a quarter warp -- the unit in which 16-byte accesses are processed,
+ * for the global stores too: a quarter that covers eight picture rows costs eight tag look-ups -- take 4 x 16 bytes of
+ * staging row s and of s + 4 (13 s and 13 (s + 4) pieces differ by 4 modulo 8: all eight bank groups), i.e. two picture
+ * rows, two 128-byte lines.  Every address is a lane constant plus an immediate. */
+#ifndef KF_WO_GROUP
+#define KF_WO_GROUP (KF_GROUP == 4)
+#endif
+#define KF_RGB_GSTRIDE 208
+#ifndef KF_WO_PAIR
+#define KF_WO_PAIR 1         /* RGB write-out lane mapping with two lane constants (0: row-major pieces, KF_RGB_PERM: permuted staging rows) */
+#endif
+#ifndef KF_WO_KEEP
+#define KF_WO_KEEP 0
+#endif
+#ifndef KF_HALO_GROUP
+#define KF_HALO_GROUP (KF_GROUP == 4)   /* the halo words of the row above are validated and parked in shared memory once
+                                           per group of four macroblocks (0: checked per macroblock, kept in registers) */
+#endif
 #ifndef KF_HALO_FAST
 #define KF_HALO_FAST 1      /* one comparison per macroblock while the whole group of halo words above is valid */
 #endif
@@ -90,26 +112,32 @@ struct KFParams {
 
 /* Member order matters (see K2WarpSmem): lanes without a block in an Intra4x4 step read up to 64 bytes below
  * the residual and 140 bytes below lt[] (and past the end of lt[] into ct[]); all of that stays inside this record. */
-struct KFWarpSmem {
+template <int OUT>
+struct KFWarpSmemT {
     union {
         MvgXfScratch<KF_GROUP> x;                       /* transform stage                                      */
-        uint8_t rgb[16 * KF_RGB_STRIDE];                /* RGB24 rows of a macroblock pair (prediction stage, KF_OUT_RGB) */
+        uint8_t rgb[OUT != 1 ? 16 : KF_WO_GROUP ? 16 * KF_RGB_GSTRIDE : 16 * KF_RGB_STRIDE];    /* RGB24 rows of a macroblock group / pair (prediction stage, KF_OUT_RGB) */
     } u;
     MVG_CANARY(c0)
     __align__(128) int16_t tile[KF_GROUP * KF_MBS];        /* levels in -> residual in place; slot j is refilled with macroblock j
                                                            of the next group as soon as macroblock j has been predicted */
     __align__(8) uint64_t mbar;
+    __align__(16) uint32_t hrow[36];                    /* KF_HALO_GROUP: the bottom sample line of the four macroblocks above this
+                                                           group and the first two words of the next one */
     MVG_CANARY(c1)
     __align__(16) uint8_t lt[MVG_LT_ROWS * MVG_LT_STRIDE];
     __align__(16) uint8_t ct[2][MVG_CT_PLANE];
     MVG_CANARY(c2)
     __align__(16) uint8_t n8[MVG_N8_BYTES];
     MVG_CANARY(c3)
+#ifdef KF_REC_PAD        /* DEV: a larger record without any use of it (shared memory carve-out experiments) */
+    uint8_t pad[KF_REC_PAD];
+#endif
 };
 
 #define KF_LUT_BYTES  ((sizeof(MvgLuts) + 127) / 128 * 128)
 #define KF_TAB_BYTES  ((sizeof(MvgXfTables) + 127) / 128 * 128)
-#define KF_SMEM_BYTES(out) (sizeof(KFWarpSmem) * KF_WARPS_OF(out) + 2048 + KF_LUT_BYTES + KF_TAB_BYTES)
+#define KF_SMEM_BYTES(out) (sizeof(KFWarpSmemT<out>) * KF_WARPS_OF(out) + 2048 + KF_LUT_BYTES + KF_TAB_BYTES)
 
 /* Persistent warps, one CTA per SM.  A work item is one macroblock row of one picture (claimed from an atomic
  * counter, rows of a picture in order, pictures interleaved: see k2_wavefront for the dependency protocol, which
@@ -130,6 +158,7 @@ __global__ void KF_BOUNDS
 kf_recon(KFParams p)
 {
     extern __shared__ __align__(128) uint8_t kf_smem[];
+    typedef KFWarpSmemT<OUT> KFWarpSmem;        /* the tiles mode has no RGB staging area */
     const int lane = mvg_lane();
     const unsigned wid = __shfl_sync(MVG_FULL, threadIdx.x >> 5, 0);       /* warp-uniform by construction */
     /* layout: the tap tables sit on the first 2 KB boundary (so that (mode << 7) can be OR-ed into a lane's
@@ -244,10 +273,19 @@ kf_recon(KFParams p)
         lc_dst = lane < 16 ? s.lt + K2_TO(-1, lane) : s.ct[(lane >> 3) & 1] + K2_CO(-1, lane & 7);
         lc_src = lc_dst + (lane < 16 ? 16 : 8);
 #endif
-        rgb_dst = s.u.rgb + (KF_RGB_PERM ? q : 2 * q) * KF_RGB_STRIDE + 12 * h;
+        rgb_dst = KF_WO_GROUP ? s.u.rgb + q * KF_RGB_GSTRIDE + 12 * h : s.u.rgb + (KF_RGB_PERM ? q : 2 * q) * KF_RGB_STRIDE + 12 * h;
     }
     const unsigned lc_sel = lane < 16 ? 7u : 3u;            /* tiles: byte 3 of the second / first 8-byte piece */
     const int pitch = 48 * W;                               /* bytes per RGB24 picture row */
+#if KF_WO_PAIR && !KF_WO_GROUP
+    /* RGB write-out of a macroblock pair: lane l takes staging row l >> 1 and the 16-byte pieces 2 k + (l & 1), k = 0..2,
+     * of its 6 (a row's two pieces of one instruction are one 32-byte sector): one lane constant for the staging address
+     * and one for the picture, the rest are immediates */
+    int wo_rd_off = (lane >> 1) * KF_RGB_STRIDE + (lane & 1) * 16, wo_g_off = (lane >> 1) * pitch + (lane & 1) * 16;
+#if KF_WO_KEEP
+    wo_rd_off = mvg_keep(wo_rd_off); wo_g_off = mvg_keep(wo_g_off);
+#endif
+#endif
 
     MvgSideInfo side;
     side.init(lane, p.mb_kind, p.i16_mode, p.chroma_mode, p.luma_modes, p.qp_y);
@@ -281,10 +319,16 @@ kf_recon(KFParams p)
         uint8_t *wo_run = OUT == KF_OUT_TILES ? p.tiles + mb0 * 384 + wo_off
                                               : p.rgb + (size_t)slot * ((size_t)n_mb * 768) + (size_t)row * 16 * pitch;
         uint2 *hm_run = p.halo + mb0 * 8 + lane;
-        const uint2 *ha_run = p.halo + (mb0 - W) * 8 + lane;           /* group of macroblock mx (at hj == 0) */
         const bool availB = row > 0, publish = row < H - 1;
         const int hwords = W * 8;                               /* halo words of a macroblock row */
+#if KF_HALO_GROUP
+        /* lanes 0..16: words 2 l and 2 l + 1 of the 32 + 2 a group needs; lanes that have nothing to load keep the epoch */
+        const uint4 *ha_run = reinterpret_cast<const uint4 *>(p.halo + (mb0 - W) * 8) + lane;
+        uint4 hq = make_uint4(0, epoch, 0, epoch);
+#else
+        const uint2 *ha_run = p.halo + (mb0 - W) * 8 + lane;           /* group of macroblock mx (at hj == 0) */
         uint2 qa = make_uint2(0, epoch), qb = make_uint2(0, epoch);
+#endif
         if (availB) {
             if (KF_STAGGER > 0) {
                 /* Slack between the rows of a picture: wait here, once, until the row above is KF_STAGGER macroblocks
@@ -296,9 +340,15 @@ kf_recon(KFParams p)
                 while (mvg_ld_relaxed_u64(probe).y != epoch) { __nanosleep(2000); KF_STAT(st[0]++;) }
                 KF_STAT(st[1] += clock64() - ts;)
             }
+#if KF_HALO_GROUP
+            if (lane < 17 && 2 * lane < hwords) hq = mvg_ld_relaxed_2u64(ha_run);
+#else
             if (lane < hwords) qb = mvg_ld_relaxed_u64(ha_run);     /* becomes qa at macroblock 0 */
+#endif
         }
+#if !KF_HALO_GROUP
         unsigned okA = 0;
+#endif
 
         KF_STAT(st[5]++; const long long trow = clock64();)
         for (int g = 0; g < n_groups; g++) {
@@ -316,10 +366,44 @@ kf_recon(KFParams p)
             mvg_xf_group<KF_GROUP, KF_MBS>(tile, s.u.x, T, meta, nmb, lane);
             const uint4 rec = mvg_ctl_from_meta(meta);      /* valid in lane 8 j */
 
+#if KF_HALO_GROUP
+            /* The bottom sample line of the row above for this whole group: 32 words of the four macroblocks above and the
+             * first two of the next one (up-right neighbour of the group's last macroblock), requested a group ago with one
+             * 16-byte load per lane.  Validated once, parked in shared memory, and the next group's request goes out.  A group
+             * therefore starts only when the row above is five macroblocks past the group's first one (the per-macroblock
+             * rule is two): with the distance KF_STAGGER that rows keep anyway this costs nothing. */
+            if (availB) {
+                for (;;) {
+                    if (__all_sync(MVG_FULL, hq.y == epoch && hq.w == epoch)) break;
+                    /* This row has caught up with the row above.  Do not follow it at the minimum distance: fall back until
+                     * the row above is KF_STAGGER macroblocks ahead again, then reload (every word validates itself: the
+                     * probe word says nothing about its neighbours). */
+                    const uint2 *probe = p.halo + (mb0 - W + min(g * KF_GROUP + max(KF_STAGGER, KF_GROUP + 1), W - 1)) * 8 + 7;
+                    KF_STAT(const long long ts = clock64(); st[2]++;)
+                    while (mvg_ld_relaxed_u64(probe).y != epoch) { __nanosleep(KF_POLL_NS); KF_STAT(st[3]++;) }
+                    KF_STAT(st[4] += clock64() - ts;)
+                    if (lane < 17 && g * 32 + 2 * lane < hwords) hq = mvg_ld_relaxed_2u64(ha_run);
+                }
+                if (lane < 17) *reinterpret_cast<uint2 *>(s.hrow + 2 * lane) = make_uint2(hq.x, hq.z);
+                ha_run += 16;
+                hq = make_uint4(0, epoch, 0, epoch);
+                if (n_next > 0 && lane < 17 && (g + 1) * 32 + 2 * lane < hwords) hq = mvg_ld_relaxed_2u64(ha_run);
+                __syncwarp();
+            }
+#endif
+
             for (int j = 0; j < nmb; j++) {
-                const int mx = g * KF_GROUP + j, hj = mx & 3;
+                const int mx = g * KF_GROUP + j;
+#if !KF_HALO_GROUP
+                const int hj = mx & 3;
+#endif
                 const bool availA = mx > 0, availC = availB && mx < W - 1, availD = availA && availB;
 
+#if KF_HALO_GROUP
+                /* sample row -1 of the tiles: lanes 0..7 the macroblock above, lanes 8,9 x = 16..23 (above-right) */
+                if (availB && lane < 10) *reinterpret_cast<unsigned *>(halo_top) = s.hrow[8 * j + lane];
+                __syncwarp();
+#else
                 if (availB) {
                     if (hj == 0) {              /* group of four macroblocks above: requested a group ago */
                         qa = qb;
@@ -363,6 +447,7 @@ kf_recon(KFParams p)
                     qb = make_uint2(0, epoch);
                     if (mx * 8 + 32 + lane < hwords) qb = mvg_ld_relaxed_u64(ha_run + 32);
                 }
+#endif
                 c.resid = reinterpret_cast<const uint8_t *>(tile + j * KF_MBS);
                 const unsigned cx = __shfl_sync(MVG_FULL, rec.x, 8 * j), cy = __shfl_sync(MVG_FULL, rec.y, 8 * j);
                 const unsigned cz = __shfl_sync(MVG_FULL, rec.z, 8 * j);
@@ -418,7 +503,8 @@ kf_recon(KFParams p)
                         const unsigned X = __byte_perm(Re, Ge, 0x6240);       /* R0 G0 R2 G2 */
                         const unsigned Y = __byte_perm(Be, Ro, 0x6240);       /* B0 R1 B2 R3 */
                         const unsigned Z = __byte_perm(Go, Bo, 0x6240);       /* G1 B1 G3 B3 */
-                        unsigned *d = reinterpret_cast<unsigned *>(rgb_dst + r * (KF_RGB_PERM ? 8 : 1) * KF_RGB_STRIDE + 48 * (j & 1));
+                        unsigned *d = KF_WO_GROUP ? reinterpret_cast<unsigned *>(rgb_dst + r * 8 * KF_RGB_GSTRIDE + 48 * j)
+                                                  : reinterpret_cast<unsigned *>(rgb_dst + r * (KF_RGB_PERM ? 8 : 1) * KF_RGB_STRIDE + 48 * (j & 1));
                         d[0] = __byte_perm(X, Y, 0x5410);                     /* R0 G0 B0 R1 */
                         d[1] = __byte_perm(Z, X, 0x7610);                     /* G1 B1 R2 G2 */
                         d[2] = __byte_perm(Y, Z, 0x7632);                     /* B2 R3 G3 B3 */
@@ -432,11 +518,37 @@ kf_recon(KFParams p)
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mvg_bulk_load(tile + j * KF_MBS, lv_row + (size_t)(mx + KF_GROUP) * 384, 768u, &s.mbar);
                 }
+#if KF_WO_GROUP
+                if (OUT == KF_OUT_RGB && j == nmb - 1) {
+                    /* the group's 16 rows x 192 bytes (48 per macroblock present) */
+                    const int wc = lane & 3, ws = (lane >> 3) + 4 * ((lane >> 2) & 1);     /* piece within 64 bytes, staging row (+ 8 hb) */
+                    const uint8_t *rd = s.u.rgb + ws * KF_RGB_GSTRIDE + wc * 16;
+                    uint8_t *gd = wo_run + (size_t)(2 * ws) * pitch + wc * 16;
+#pragma unroll
+                    for (int hb = 0; hb < 2; hb++)
+#pragma unroll
+                        for (int m = 0; m < 3; m++)
+                            if (4 * m + wc < 3 * nmb)
+                                *reinterpret_cast<uint4 *>(gd + (size_t)hb * pitch + 64 * m) =
+                                    *reinterpret_cast<const uint4 *>(rd + hb * 8 * KF_RGB_GSTRIDE + 64 * m);
+                    wo_run += 192;
+                    __syncwarp();
+                }
+#else
                 if (OUT == KF_OUT_RGB && ((j & 1) || j == nmb - 1)) {
                     /* the pair's 16 rows x 96 bytes (48 for a lone last macroblock): 16-byte chunks in row-major order over
                      * the lanes, so that a pair leaves as whole 32-byte sectors (96 bytes per row at a multiple of 96) */
                     const int n_here = (j & 1) + 1;
-#if KF_RGB_PERM
+#if KF_WO_PAIR
+                    {
+                        const uint8_t *rd = s.u.rgb + wo_rd_off;
+                        uint8_t *gd = wo_run + wo_g_off;
+#pragma unroll
+                        for (int k = 0; k < 3; k++)
+                            if (2 * k + (lane & 1) < 3 * n_here)
+                                *reinterpret_cast<uint4 *>(gd + 32 * k) = *reinterpret_cast<const uint4 *>(rd + 32 * k);
+                    }
+#elif KF_RGB_PERM
                     {
                         /* lane l: staging row l & 15 = picture row 2 (l & 7) + (l >> 3 & 1), 16-byte pieces 2 k + (l >> 4) of
                          * its 6 (3 for a lone last macroblock): a row's two pieces of one instruction are one 32-byte sector */
@@ -465,6 +577,7 @@ kf_recon(KFParams p)
                     wo_run += 96;
                     __syncwarp();
                 }
+#endif
             }
         }
         KF_STAT(st[6] += clock64() - trow;)

@@ -665,6 +665,13 @@ __device__ __forceinline__ uint2 mvg_ld_relaxed_u64(const uint2 *p)
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return make_uint2((unsigned)v, (unsigned)(v >> 32));
 }
+/* two neighbouring halo words with one request; each 64-bit half is a relaxed access of its own */
+__device__ __forceinline__ uint4 mvg_ld_relaxed_2u64(const uint4 *p)
+{
+    unsigned long long a, b;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    return make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
+}
 __device__ __forceinline__ void mvg_st_relaxed_u64(uint2 *p, unsigned lo, unsigned hi)
 {
     const unsigned long long v = (unsigned long long)lo | ((unsigned long long)hi << 32);
