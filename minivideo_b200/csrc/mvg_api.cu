@@ -7,6 +7,7 @@
 #include "mvgpu.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      /* header-only: the ranges cost two empty calls unless a profiler has injected itself */
 
 #include <algorithm>
 #include <cstdarg>
@@ -24,6 +25,13 @@
 /* ------------------------------------------------------------------------- */
 
 static char g_create_error[512] = "";
+
+/* NVTX range around an entry point of the C ABI (tracing).  A timeline (Nsight Systems) then shows
+ * the host calls above the copies and launches they enqueue. */
+struct MvgRange {
+    explicit MvgRange(const char *name) { nvtxRangePushA(name); }
+    ~MvgRange() { nvtxRangePop(); }
+};
 
 #define MVG_PIPE_DEPTH 3       /* slot regions used by the end-to-end calls */
 #define MVG_MAX_TICKETS 8      /* submissions in flight (mvg_submit*) */
@@ -401,6 +409,7 @@ extern "C" int mvg_set_sps(mvg_ctx *ctx, int width_mbs, int height_mbs,
                            const int32_t level_scale4x4[3 * 6 * 16], const int32_t level_scale8x8[6 * 64],
                            int cb_qp_offset, int cr_qp_offset)
 {
+    MvgRange nvtx_range("mvg_set_sps");
     if (!ctx) return MVG_FAILURE;
     if (!level_scale4x4 || !level_scale8x8) return fail(ctx, "mvg_set_sps: NULL table");
     if (width_mbs < 1 || height_mbs < 1 || width_mbs > ctx->max_w || height_mbs > ctx->max_h)
@@ -543,6 +552,7 @@ static int check_batch(mvg_ctx *ctx, const mvg_batch *b, const char *who)
 
 extern "C" int mvg_upload(mvg_ctx *ctx, const mvg_batch *b, int first_slot)
 {
+    MvgRange nvtx_range("mvg_upload");
     if (!ctx) return MVG_FAILURE;
     if (check_batch(ctx, b, "mvg_upload") != MVG_SUCCESS) return MVG_FAILURE;
     if (check_ready(ctx, first_slot, b->n_pics, "mvg_upload") != MVG_SUCCESS) return MVG_FAILURE;
@@ -554,6 +564,7 @@ extern "C" int mvg_upload(mvg_ctx *ctx, const mvg_batch *b, int first_slot)
 
 extern "C" int mvg_clone_slot(mvg_ctx *ctx, int src_slot, int dst_slot)
 {
+    MvgRange nvtx_range("mvg_clone_slot");
     if (check_ready(ctx, src_slot, 1, "mvg_clone_slot") != MVG_SUCCESS) return MVG_FAILURE;
     if (check_ready(ctx, dst_slot, 1, "mvg_clone_slot") != MVG_SUCCESS) return MVG_FAILURE;
     CK(ctx, cudaSetDevice(ctx->device));
@@ -708,6 +719,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
 
 extern "C" int mvg_run(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale)
 {
+    MvgRange nvtx_range("mvg_run");
     if (check_ready(ctx, first_slot, n_pics, "mvg_run") != MVG_SUCCESS) return MVG_FAILURE;
     CK(ctx, cudaSetDevice(ctx->device));
     return launch_stages(ctx, first_slot, n_pics, rgb_scale, true, ctx->stream, true);
@@ -715,6 +727,7 @@ extern "C" int mvg_run(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale)
 
 extern "C" int mvg_run_rgb(mvg_ctx *ctx, int first_slot, int n_pics)
 {
+    MvgRange nvtx_range("mvg_run_rgb");
     if (check_ready(ctx, first_slot, n_pics, "mvg_run_rgb") != MVG_SUCCESS) return MVG_FAILURE;
     CK(ctx, cudaSetDevice(ctx->device));
     return launch_stages(ctx, first_slot, n_pics, 1, false, ctx->stream, true);
@@ -782,6 +795,7 @@ static size_t rgb_bytes(const mvg_ctx *ctx, int scale)
 
 extern "C" int mvg_download_yuv420(mvg_ctx *ctx, int slot, uint8_t *y, uint8_t *cb, uint8_t *cr)
 {
+    MvgRange nvtx_range("mvg_download_yuv420");
     if (check_ready(ctx, slot, 1, "mvg_download_yuv420") != MVG_SUCCESS) return MVG_FAILURE;
     if (!ctx->tiles_valid) return fail(ctx, "mvg_download_yuv420: the last run produced RGB24 only (mvg_run_rgb); use mvg_run()");
     CK(ctx, cudaSetDevice(ctx->device));
@@ -797,6 +811,7 @@ extern "C" int mvg_download_yuv420(mvg_ctx *ctx, int slot, uint8_t *y, uint8_t *
 
 extern "C" int mvg_download_rgb(mvg_ctx *ctx, int slot, uint8_t *rgb)
 {
+    MvgRange nvtx_range("mvg_download_rgb");
     if (check_ready(ctx, slot, 1, "mvg_download_rgb") != MVG_SUCCESS) return MVG_FAILURE;
     if (!rgb || ctx->last_scale < 1) return fail(ctx, "mvg_download_rgb: no RGB output (last run had rgb_scale 0)");
     CK(ctx, cudaSetDevice(ctx->device));
@@ -808,6 +823,7 @@ extern "C" int mvg_download_rgb(mvg_ctx *ctx, int slot, uint8_t *rgb)
 
 extern "C" int mvg_download_residual(mvg_ctx *ctx, int slot, int16_t *residual)
 {
+    MvgRange nvtx_range("mvg_download_residual");
     if (check_ready(ctx, slot, 1, "mvg_download_residual") != MVG_SUCCESS) return MVG_FAILURE;
     if (!residual) return fail(ctx, "mvg_download_residual: NULL");
     CK(ctx, cudaSetDevice(ctx->device));
@@ -906,6 +922,7 @@ static int decode_pipeline(mvg_ctx *ctx, int n_pics, uint8_t *yuv_out, uint8_t *
 
 extern "C" int mvg_wait(mvg_ctx *ctx, mvg_ticket ticket)
 {
+    MvgRange nvtx_range("mvg_wait");
     if (!ctx) return MVG_FAILURE;
     if (ticket < 0 || ticket >= MVG_MAX_TICKETS || !ctx->tickets[ticket].busy) return fail(ctx, "mvg_wait: ticket %d is not in flight", (int)ticket);
     CK(ctx, cudaSetDevice(ctx->device));
@@ -926,6 +943,7 @@ extern "C" int mvg_poll(mvg_ctx *ctx, mvg_ticket ticket, int *done)
 
 extern "C" int mvg_submit(mvg_ctx *ctx, const mvg_batch *b, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale, mvg_ticket *ticket)
 {
+    MvgRange nvtx_range("mvg_submit");
     if (!ctx) return MVG_FAILURE;
     if (!ticket) return fail(ctx, "mvg_submit: ticket is NULL");
     if (check_batch(ctx, b, "mvg_submit") != MVG_SUCCESS) return MVG_FAILURE;
@@ -956,6 +974,7 @@ extern "C" int mvg_decode_host(mvg_ctx *ctx, const mvg_batch *b, uint8_t *yuv_ou
 extern "C" int mvg_pack_batch(const int16_t *coeff, int n_pics, int n_mbs, uint32_t *nz_blocks, uint32_t *word_off,
                               uint64_t *pic_off, uint16_t *words, size_t words_capacity, int n_threads)
 {
+    MvgRange nvtx_range("mvg_pack_batch");
     if (!coeff || !nz_blocks || !word_off || !pic_off || !words || n_pics < 1 || n_mbs < 1) return MVG_FAILURE;
     try {               /* allocation or thread creation may throw: nothing may unwind through the C ABI */
     /* pass 1 (threaded over pictures): chunk bitmaps and per-macroblock sizes -> offsets inside the picture */
@@ -1015,6 +1034,7 @@ extern "C" int mvg_pack_batch(const int16_t *coeff, int n_pics, int n_mbs, uint3
 
 extern "C" int mvg_submit_packed(mvg_ctx *ctx, const mvg_packed_batch *b, uint8_t *yuv_out, uint8_t *rgb_out, int rgb_scale, mvg_ticket *ticket)
 {
+    MvgRange nvtx_range("mvg_submit_packed");
     if (!ctx) return MVG_FAILURE;
     if (!ticket) return fail(ctx, "mvg_submit_packed: ticket is NULL");
     if (!b) return fail(ctx, "mvg_decode_host_packed: batch is NULL");

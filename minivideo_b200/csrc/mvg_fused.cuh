@@ -25,7 +25,7 @@
                                makes the transform stage cheap (2 macroblocks: 6.1 ms, 4: 5.4 ms per 1000 pictures) */
 #endif
 #ifndef KF_WARPS
-#define KF_WARPS 24         /* warps per CTA (one CTA per SM), RGB mode: its staging traffic saturates the LSU pipe first, more warps make it slower */
+#define KF_WARPS 25         /* warps per CTA (one CTA per SM), RGB mode: its staging traffic saturates the LSU pipe first, more warps make it slower */
 #endif
 #ifndef KF_WARPS_TILES
 #define KF_WARPS_TILES 28   /* tiles mode: 5.19 ms per 1000 pictures at 28 warps against 5.31 at 24 */
@@ -64,6 +64,9 @@
  * for the global stores too: a quarter that covers eight picture rows costs eight tag look-ups -- take 4 x 16 bytes of
  * staging row s and of s + 4 (13 s and 13 (s + 4) pieces differ by 4 modulo 8: all eight bank groups), i.e. two picture
  * rows, two 128-byte lines.  Every address is a lane constant plus an immediate. */
+#ifndef KF_LDGSTS
+#define KF_LDGSTS 0         /* 1: levels by per-lane 16-byte asynchronous copies instead of one bulk copy per macroblock + mbarrier (correct, 2 % slower) */
+#endif
 #ifndef KF_WO_GROUP
 #define KF_WO_GROUP (KF_GROUP == 4)
 #endif
@@ -289,7 +292,9 @@ kf_recon(KFParams p)
 
     MvgSideInfo side;
     side.init(lane, p.mb_kind, p.i16_mode, p.chroma_mode, p.luma_modes, p.qp_y);
+#if !KF_LDGSTS
     unsigned parity = 0;            /* phase parity of the mbarrier: one phase per group */
+#endif
     KF_STAT(unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};)
 
     for (;;) {
@@ -307,6 +312,22 @@ kf_recon(KFParams p)
 
         /* group 0: levels and side information.  The buffer was last touched by this warp's generic-proxy
          * accesses (residual of an earlier group): order them before the asynchronous write. */
+#if KF_LDGSTS
+        /* per-lane 16-byte asynchronous copies (LDGSTS), 48 per macroblock: a full-warp instruction and a half-warp one.
+         * Completion by the lanes' own copy groups + __syncwarp(): no barrier object, no proxy fence, no single-lane
+         * issue sequence -- and six 128-byte shared-memory wavefronts per macroblock, where the bulk copy's writes are
+         * counted as twenty-four of 32 bytes */
+        const uint8_t *lv_lane = reinterpret_cast<const uint8_t *>(lv_row) + lane * 16;
+        uint8_t *const tile_lane = reinterpret_cast<uint8_t *>(s.tile) + lane * 16;
+        {
+            const int n0 = min(KF_GROUP, W);
+            for (int j = 0; j < n0; j++) {
+                mvg_cp_async16(tile_lane + j * (KF_MBS * 2), lv_lane + j * 768);
+                if (lane < 16) mvg_cp_async16(tile_lane + j * (KF_MBS * 2) + 512, lv_lane + j * 768 + 512);
+            }
+            mvg_cp_async_commit();
+        }
+#else
         if (lane == 0) {
             const int n0 = min(KF_GROUP, W);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -314,6 +335,7 @@ kf_recon(KFParams p)
             if (KF_MBS == 384) mvg_bulk_load(s.tile, lv_row, (unsigned)n0 * 768u, &s.mbar);
             else for (int j = 0; j < n0; j++) mvg_bulk_load(s.tile + j * KF_MBS, lv_row + j * 384, 768u, &s.mbar);
         }
+#endif
         unsigned nmeta = side.load(lane, (long long)mb0, min(KF_GROUP, W));
 
         uint8_t *wo_run = OUT == KF_OUT_TILES ? p.tiles + mb0 * 384 + wo_off
@@ -357,10 +379,15 @@ kf_recon(KFParams p)
             const int n_next = min(KF_GROUP, W - (g + 1) * KF_GROUP);       /* macroblocks of the next group (<= 0: none) */
             if (n_next > 0) nmeta = side.load(lane, (long long)mb0 + (g + 1) * KF_GROUP, n_next);
             int16_t *tile = s.tile;
+#if KF_LDGSTS
+            mvg_cp_async_wait<0>();
+            __syncwarp();
+#else
             mvg_mbar_wait(&s.mbar, parity);
             parity ^= 1u;
             /* the next phase collects the next group's copies, which are issued one by one below */
             if (n_next > 0 && lane == 0) mvg_mbar_expect_tx(&s.mbar, (unsigned)n_next * 768u);
+#endif
 
             /* ---- levels -> residual, in place (kernel 1's stage) ---- */
             mvg_xf_group<KF_GROUP, KF_MBS>(tile, s.u.x, T, meta, nmb, lane);
@@ -514,10 +541,19 @@ kf_recon(KFParams p)
                 *cn_dst = *cn_src;
                 __syncwarp();
                 /* this macroblock's residual is spent: its slot takes macroblock j of the next group */
+#if KF_LDGSTS
+                if (j < n_next) {
+                    const uint8_t *src = lv_lane + (size_t)(mx + KF_GROUP) * 768;
+                    mvg_cp_async16(tile_lane + j * (KF_MBS * 2), src);
+                    if (lane < 16) mvg_cp_async16(tile_lane + j * (KF_MBS * 2) + 512, src + 512);
+                    mvg_cp_async_commit();
+                }
+#else
                 if (j < n_next && lane == 0) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mvg_bulk_load(tile + j * KF_MBS, lv_row + (size_t)(mx + KF_GROUP) * 384, 768u, &s.mbar);
                 }
+#endif
 #if KF_WO_GROUP
                 if (OUT == KF_OUT_RGB && j == nmb - 1) {
                     /* the group's 16 rows x 192 bytes (48 per macroblock present) */

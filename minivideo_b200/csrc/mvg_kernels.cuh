@@ -190,6 +190,12 @@ __device__ __forceinline__ unsigned mvg_pack_shr6(int hi, int lo)
 #ifndef MVG_CLS_SWAP
 #define MVG_CLS_SWAP 1      /* classification pass of mvg_xf_group: bank-conflict-free half order (0: the plain order, for comparison) */
 #endif
+#ifndef MVG_DC_WHT
+#define MVG_DC_WHT 0        /* DC transforms as cross-lane butterflies (correct, but 1 % slower than the default: a few lanes per macroblock, through a scratch array -- the shuffles cost more than the divergent code they replace) */
+#endif
+#ifndef MVG_CLS_UNROLL
+#define MVG_CLS_UNROLL 0
+#endif
 #ifndef MVG_GEN_SWAP
 #define MVG_GEN_SWAP 0
 #endif
@@ -235,7 +241,8 @@ struct MvgXfScratch {
     int32_t  dc[G][24];                         /* dequantised DC of Intra16x16 luma / chroma blocks   */
     int32_t  f1[G][16];                         /* first stage of the luma DC Hadamard                 */
     int32_t  tr[4][8][9];                       /* 8x8 transpose, padded                               */
-    uint32_t meta[G];                           /* mb_kind | QPY << 8                                  */
+    uint32_t meta[G];                           /* mb_kind | QPY << 8 | (shift | rounding << 8) of quant4x4 at QPY << 16 */
+    int32_t  ls0[G];                            /* LevelScale4x4 (luma, position 0) at QPY, shift folded in: DC-only luma blocks */
     uint8_t  list4[G * 24 + 8];                 /* 4x4 blocks that need the full transform             */
     uint8_t  list8[G * 4 + 4];                  /* 8x8 blocks with non-zero levels                     */
 };
@@ -322,9 +329,52 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
     const int kind_j = (int)__shfl_sync(MVG_FULL, meta, (lane & ~7) + 4);
     /* QPY outside 0..51 cannot come out of a conforming parse; clamp so that a bad batch cannot index past the tables */
     const int qp_j = min(max((int)(signed char)__shfl_sync(MVG_FULL, meta, (lane & ~7) + 5), 0), 51);
-    if (mt == 0 && mj < G) s.meta[mj] = (unsigned)kind_j | ((unsigned)(qp_j & 255) << 8);
+    if (mt == 0 && mj < G) {
+        /* what the classification pass needs of a macroblock besides its kind: one word and the DC scale, instead of
+         * three dependent table reads per block */
+        const unsigned sh = T.dcsh[qp_j];
+        s.meta[mj] = (unsigned)kind_j | ((unsigned)(qp_j & 255) << 8) | (sh << 16) | (((1u << sh) >> 1) << 24);
+        s.ls0[mj] = T.ls4q[qp_j * 16];
+    }
 
     /* ---------------- DC transforms ---------------- */
+#if MVG_DC_WHT
+    /* Both DC transforms are Walsh-Hadamard transforms (2x2: natural order; 4x4: the standard's row order 0, 2, 3, 1 of
+     * the natural one), so they run as butterflies ACROSS lanes, one coefficient per lane: a shuffle and an add/subtract
+     * per stage, no scratch array, no lane-divergent code. */
+    {   /* chroma DC (h264_transform.c:827-936): lane = 8 j + 4 plane + k, f = A c A, then scale */
+        const int pl = (lane >> 2) & 1;
+        int v = 0;
+        if (mj < nmb) v = tile[mj * MBS + 256 + (lane & 7) * 16];
+        int t = __shfl_xor_sync(MVG_FULL, v, 1); v = (lane & 1) ? t - v : v + t;
+        t = __shfl_xor_sync(MVG_FULL, v, 2);     v = (lane & 2) ? t - v : v + t;
+        const int qe = T.qpc[pl][qp_j], qpc = qe & 255, qd = qe >> 8;
+        const int ls00 = T.ls4[((pl + 1) * 6 + (qpc - 6 * qd)) * 16];
+        if (mj < nmb) s.dc[mj][16 + (lane & 7)] = (int)((unsigned)(v * ls00) << qd) >> 5;
+    }
+    {   /* Intra16x16 luma DC (h264_transform.c:756-812): two macroblocks per pass, lane = 16 m + 4 y + x holds c[y][x]; after
+         * the four stages it holds the output whose row / column index is the inverse of 0, 2, 3, 1 at y / x */
+        const int x = lane & 3, y = (lane >> 2) & 3;
+        const int src = mvg_blk_of(x, y) * 16, dst = mvg_blk_of((0x9C >> (2 * x)) & 3, (0x9C >> (2 * y)) & 3);
+#pragma unroll 1
+        for (int p = 0; p < (G + 1) / 2; p++) {
+            const int m2 = 2 * p + (lane >> 4);
+            const unsigned kq = __shfl_sync(MVG_FULL, meta, (8 * m2 + 4) & 31), qq = __shfl_sync(MVG_FULL, meta, (8 * m2 + 5) & 31);
+            const bool act = m2 < nmb && (int)kq == MVG_MB_I16x16;
+            if (!__any_sync(MVG_FULL, act)) continue;
+            const int qp = min(max((int)(signed char)qq, 0), 51);
+            int v = act ? (int)tile[m2 * MBS + src] : 0;
+#pragma unroll
+            for (int st = 1; st < 16; st <<= 1) {
+                const int t = __shfl_xor_sync(MVG_FULL, v, st);
+                v = (lane & st) ? t - v : v + t;
+            }
+            const int qd = qp / 6, tt = v * T.ls4[(qp - 6 * qd) * 16];
+            if (act) s.dc[m2][dst] = (qp >= 36) ? (int)((unsigned)tt << (qd - 6)) : ((tt + (1 << (5 - qd))) >> (6 - qd));
+        }
+    }
+    __syncwarp();
+#else
     if (mj < nmb) {
         const int16_t *cf = tile + mj * MBS;
         if (kind_j == MVG_MB_I16x16 && mt < 4) {         /* row mt of c: t = c * H */
@@ -356,18 +406,24 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
         }
     }
     __syncwarp();
+#endif
 
     /* ---------------- classify the 4x4 blocks, compact the general ones ---------------- */
     int n4 = 0, n8 = 0;
+#if MVG_CLS_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1        /* code size: the fused kernel has to fit the instruction cache */
+#endif
     for (int r = 0; r < (G * 24 + 31) / 32; r++) {
-        const int u = lane + 32 * r, j0 = u / 24, b = u - 24 * j0;
+        /* u / 24 for u = lane + 32 r < 96: r, and one more from lane 24 - 8 r on */
+        const int u = lane + 32 * r, j0 = G <= 4 ? r + (lane >= 24 - 8 * r) : u / 24, b = u - 24 * j0;
         /* straight-line code: every lane loads a block (its own, or block b of macroblock 0 beyond the last
          * macroblock of a short group) and derives all three answers; only the DC-only rewrite is conditional */
         const bool live = j0 < nmb;
         const int j = live ? j0 : 0;
         const unsigned mw = s.meta[j];
-        const int kind = mw & 255, qp = (signed char)(mw >> 8);
+        const int kind = mw & 255;
         const bool is8 = kind == MVG_MB_I8x8 && b < 16;
         uint4 *blk = reinterpret_cast<uint4 *>(tile + j * MBS + b * 16);
 #if MVG_CLS_SWAP
@@ -392,8 +448,8 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
              * transforms, h264_transform.c:1126-1129) for chroma and Intra16x16, else quant4x4 of the level:
              * (c * LS + rnd) >> sh with sh = 0 from qP 24 on (the left shift is folded into ls4q) */
             const bool has_dc = b >= 16 || kind == MVG_MB_I16x16;
-            const int sh = T.dcsh[qp];
-            const int plain = (dcraw * T.ls4q[qp * 16] + ((1 << sh) >> 1)) >> sh;
+            const int sh = (mw >> 16) & 255;
+            const int plain = (dcraw * s.ls0[j] + (int)(mw >> 24)) >> sh;
             const int d = has_dc ? s.dc[j][b] : plain;
             const int rv = min(max((d + 32) >> 6, -512), 511);
             if (live && !is8 && rest == 0 && (rv != 0 || dcraw != 0)) {
