@@ -215,9 +215,10 @@ kf_recon(KFParams p)
     c.resid = reinterpret_cast<const uint8_t *>(s.tile);
     {
         const int half = lane >> 4, pix = lane & 15, px = pix & 3, py = pix >> 2;
-        c.lut4 = lut_addr + (unsigned)lane * 4u;
+        c.lut4 = lut_addr + (MVG_L4_SHFL ? (unsigned)offsetof(MvgLuts, lut4s) : 0u) + (unsigned)lane * 4u;
         c.h4 = half ? 0u : (unsigned)(4 * MVG_LT_STRIDE - 8);
         c.s4 = py * MVG_LT_STRIDE + px + (int)c.h4;
+        c.nb4 = (int)c.h4 + (pix >= 9 && pix <= 12 ? (pix - 9) * MVG_LT_STRIDE - 1 : pix >= 1 && pix <= 8 ? -MVG_LT_STRIDE + pix - 1 : -MVG_LT_STRIDE - 1);
         c.r4odd = pix * 2 + (half ? 64 : 0);
         c.r4even = pix * 2 + (half ? -64 : 0);
         c.m4c = half ? 0x10100010u : 0x10001000u;
@@ -236,7 +237,7 @@ kf_recon(KFParams p)
         /* the Intra4x4 step constants stay in registers (mvg_keep): without this the compiler re-derives them from the
          * lane index in every one of the ten steps.  6.58 -> 6.41 ms per 1000 pictures; keeping the Intra8x8 and the RGB
          * output offsets as well costs more in register pressure than it saves (6.51 / 7.11 ms) */
-        c.lut4 = mvg_keep(c.lut4); c.h4 = mvg_keep(c.h4); c.s4 = mvg_keep(c.s4); c.r4odd = mvg_keep(c.r4odd); c.r4even = mvg_keep(c.r4even);
+        c.lut4 = mvg_keep(c.lut4); c.h4 = mvg_keep(c.h4); c.s4 = mvg_keep(c.s4); c.nb4 = mvg_keep(c.nb4); c.r4odd = mvg_keep(c.r4odd); c.r4even = mvg_keep(c.r4even);
     }
     /* sample row -1 of the tiles comes from the halo words of the row above: lanes 0..3 luma x = 4*lane,
      * 4,5 Cb, 6,7 Cr of the macroblock above, lanes 8,9 luma x = 16..23 of the macroblock above-right */

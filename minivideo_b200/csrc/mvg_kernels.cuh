@@ -190,6 +190,9 @@ __device__ __forceinline__ unsigned mvg_pack_shr6(int hi, int lo)
 #ifndef MVG_CLS_SWAP
 #define MVG_CLS_SWAP 1      /* classification pass of mvg_xf_group: bank-conflict-free half order (0: the plain order, for comparison) */
 #endif
+#ifndef MVG_L4_SHFL
+#define MVG_L4_SHFL 0       /* 1: Intra4x4 taps by shuffles from a per-half neighbour vector instead of four byte loads per sample (correct, 1 % slower: a shuffle costs the pipe as much as the load it replaces) */
+#endif
 #ifndef MVG_DC_WHT
 #define MVG_DC_WHT 0        /* DC transforms as cross-lane butterflies (correct, but 1 % slower than the default: a few lanes per macroblock, through a scratch array -- the shuffles cost more than the divergent code they replace) */
 #endif
@@ -760,7 +763,8 @@ struct K2Ctx {
     const uint8_t *lut8;        /* MvgLuts::lut8[0][lane] in shared memory */
     int lane;
     /* Intra4x4: lane = 16 * half + 4 * py + px */
-    unsigned lut4;              /* shared-memory address of lut4[0][lane] (table 2 KB aligned) */
+    unsigned lut4;              /* shared-memory address of lut4[0][lane] (lut4s with MVG_L4_SHFL; tables 2 KB aligned) */
+    int nb4;                    /* MVG_L4_SHFL: tile offset of neighbour lane & 15 of my half's block, relative to the half-1 block origin */
     int s4;                     /* tile offset of my sample relative to the origin of the half-1 block */
     int r4odd, r4even;          /* residual byte offset relative to the half-0 block, by0 odd / even */
     unsigned h4;                /* tile offset of my block relative to the half-1 block (0 or 4 rows down, 8 left) */
@@ -844,6 +848,15 @@ __device__ __forceinline__ void k2_luma4_step(const K2Ctx &c, unsigned seq, unsi
     const unsigned m = (sh >= 7 ? (seq >> (sh >= 7 ? sh - 7 : 0)) : (seq << (sh >= 7 ? 0 : 7 - sh))) & 0x780u;
     unsigned e;
     asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(m | c.lut4));
+#if MVG_L4_SHFL
+    /* The 13 neighbours of a block, one per lane of its half warp (one shared-memory wavefront), and the four taps of
+     * every sample by shuffles from the lanes the table names: 4 wavefronts per step instead of 7 (the shared-memory
+     * pipe is what this kernel runs out of first), at the same instruction count. */
+    MVG_ASSERT(c.lt + org1 + c.nb4 >= c.rec_lo && c.lt + org1 + c.nb4 < c.rec_hi, 0);
+    const int nraw = c.lt[org1 + c.nb4];
+    int sum = __shfl_sync(MVG_FULL, nraw, e) + __shfl_sync(MVG_FULL, nraw, e >> 8) +
+              __shfl_sync(MVG_FULL, nraw, e >> 16) + __shfl_sync(MVG_FULL, nraw, e >> 24) + 2;
+#else
     const uint8_t *nb = c.lt + (org1 - MVG_LUT4_BIAS);
 #ifdef MVG_CHECKED
 #pragma unroll
@@ -851,13 +864,16 @@ __device__ __forceinline__ void k2_luma4_step(const K2Ctx &c, unsigned seq, unsi
         const uint8_t *a = nb + __dp4a(e, c.sel[k], c.h4);
         MVG_ASSERT(a >= c.rec_lo && a < c.rec_hi, 0);
     }
+#endif
+    int sum = (int)nb[__dp4a(e, c.sel[0], c.h4)] + (int)nb[__dp4a(e, c.sel[1], c.h4)] +
+              (int)nb[__dp4a(e, c.sel[2], c.h4)] + (int)nb[__dp4a(e, c.sel[3], c.h4)] + 2;
+#endif
+#ifdef MVG_CHECKED
     {
         const uint8_t *a = c.resid + blk0 * 32 + ((by0 & 1) ? c.r4odd : c.r4even);
         MVG_ASSERT(a >= c.rec_lo && a + 2 <= c.rec_hi, 0);
     }
 #endif
-    int sum = (int)nb[__dp4a(e, c.sel[0], c.h4)] + (int)nb[__dp4a(e, c.sel[1], c.h4)] +
-              (int)nb[__dp4a(e, c.sel[2], c.h4)] + (int)nb[__dp4a(e, c.sel[3], c.h4)] + 2;
     int shift = 2;
     if (dcsteps & (1u << T)) {              /* warp-uniform: some block of this step is DC with both sides available */
         const int other = __shfl_xor_sync(MVG_FULL, sum, 1);
@@ -1133,9 +1149,10 @@ k2_wavefront(K2Params p)
     c.resid = reinterpret_cast<const uint8_t *>(s.resid[0]);
     {
         const int half = lane >> 4, pix = lane & 15, px = pix & 3, py = pix >> 2;
-        c.lut4 = lut_addr + (unsigned)lane * 4u;
+        c.lut4 = lut_addr + (MVG_L4_SHFL ? (unsigned)offsetof(MvgLuts, lut4s) : 0u) + (unsigned)lane * 4u;
         c.h4 = half ? 0u : (unsigned)(4 * MVG_LT_STRIDE - 8);
         c.s4 = py * MVG_LT_STRIDE + px + (int)c.h4;
+        c.nb4 = (int)c.h4 + (pix >= 9 && pix <= 12 ? (pix - 9) * MVG_LT_STRIDE - 1 : pix >= 1 && pix <= 8 ? -MVG_LT_STRIDE + pix - 1 : -MVG_LT_STRIDE - 1);
         c.r4odd = pix * 2 + (half ? 64 : 0);
         c.r4even = pix * 2 + (half ? -64 : 0);
         c.m4c = half ? 0x10100010u : 0x10001000u;
