@@ -25,10 +25,10 @@
                                makes the transform stage cheap (2 macroblocks: 6.1 ms, 4: 5.4 ms per 1000 pictures) */
 #endif
 #ifndef KF_WARPS
-#define KF_WARPS 25         /* warps per CTA (one CTA per SM), RGB mode: its staging traffic saturates the LSU pipe first, more warps make it slower */
+#define KF_WARPS 25         /* warps per CTA (one CTA per SM), RGB mode: 8 KB of shared memory per warp (the group's RGB24 staging is 3.3 KB of it) */
 #endif
 #ifndef KF_WARPS_TILES
-#define KF_WARPS_TILES 28   /* tiles mode: 5.19 ms per 1000 pictures at 28 warps against 5.31 at 24 */
+#define KF_WARPS_TILES 28   /* tiles mode: 4.75 ms per 1000 pictures at 28 warps (24: 4.84, 30: 4.82) */
 #endif
 #define KF_WARPS_OF(out) ((out) == 1 ? KF_WARPS : KF_WARPS_TILES)
 #ifndef KF_COMPACT8
@@ -47,11 +47,7 @@
 #endif
 #define KF_OUT_TILES 0
 #define KF_OUT_RGB   1
-/* RGB staging of a PAIR of macroblocks: 16 rows of 2 x 48 bytes + 16 of padding (7 pieces of 16 bytes: 7 is odd, so
- * eight consecutive rows start in eight different 16-byte bank groups).  KF_RGB_PERM: picture row R sits in staging row
- * (R >> 1) + 8 (R & 1), even rows first.  The conversion's lane 4 q + h stores words 3 h + w of picture rows 2 q and
- * 2 q + 1 = staging rows q and q + 8: banks 28 q + 3 h + w, all different over a warp; the write-out reads staging row
- * l & 15, pieces 2 k + (l >> 4): conflict-free as well.  (Picture order: both are two-way conflicts.) */
+/* RGB staging of a PAIR of macroblocks (only with KF_WO_GROUP = 0): 16 rows of 2 x 48 bytes + 16 of padding */
 #define KF_RGB_STRIDE 112
 #ifndef KF_OPAQUE_BASE
 #define KF_OPAQUE_BASE 1
@@ -71,12 +67,6 @@
 #define KF_WO_GROUP (KF_GROUP == 4)
 #endif
 #define KF_RGB_GSTRIDE 208
-#ifndef KF_WO_PAIR
-#define KF_WO_PAIR 1         /* RGB write-out lane mapping with two lane constants (0: row-major pieces, KF_RGB_PERM: permuted staging rows) */
-#endif
-#ifndef KF_WO_KEEP
-#define KF_WO_KEEP 0
-#endif
 #ifndef KF_HALO_GROUP
 #define KF_HALO_GROUP (KF_GROUP == 4)   /* the halo words of the row above are validated and parked in shared memory once
                                            per group of four macroblocks (0: checked per macroblock, kept in registers) */
@@ -86,9 +76,6 @@
 #endif
 #ifndef KF_LCOL_COPY
 #define KF_LCOL_COPY 1      /* RGB mode: left-column hand-over as a one-sample-per-lane copy */
-#endif
-#ifndef KF_RGB_PERM
-#define KF_RGB_PERM 0
 #endif
 
 struct KFParams {
@@ -148,9 +135,16 @@ struct KFWarpSmemT {
  *   1. the group's levels arrive by bulk asynchronous copies (TMA 1-D + mbarrier), 768 bytes per macroblock, each
  *      requested as soon as its slot is free: right after the macroblock that held it a group earlier is predicted;
  *   2. mvg_xf_group() turns them into the residual in place (kernel 1's code);
- *   3. each macroblock is predicted and reconstructed in the warp's tile (kernel 2's code), its bottom line
- *      published, and then either stored as a 384-byte tile or converted to RGB24 into a staging area;
- *   4. RGB mode: after every second macroblock the pair's 16 rows x 96 bytes leave as 16-byte stores, whole sectors. */
+ *   3. the bottom sample line of the four macroblocks above (+ the first two words of the next one), requested a group
+ *      ago with one 16-byte relaxed load per lane, is validated once and parked in shared memory;
+ *   4. each macroblock is predicted and reconstructed in the warp's tile (kernel 2's code), its bottom line
+ *      published, and then either stored as a 384-byte tile or converted to RGB24 into the group's staging area;
+ *   5. RGB mode: after the group's last macroblock its 16 rows x 192 bytes leave as 16-byte stores, 64 bytes of two
+ *      picture rows per quarter warp.
+ * What the kernel runs out of first is the shared-memory/LSU data pipe and instruction issue, both at about 80 % (ncu,
+ * profiles/): hence conflict-free layouts everywhere, and nothing in the row loop that the compiler could turn into a
+ * special-register read (KF_OPAQUE_BASE).  The body is 49 KB of code, just under what the instruction cache holds for
+ * 25 warps at different places of it: unrolling one 95-instruction loop three times costs 17 % (profiles/r02_notes.md). */
 #ifdef KF_MAXREG
 #define KF_BOUNDS __maxnreg__(KF_MAXREG)        /* explicit register budget (the block size is given at launch) */
 #else
@@ -277,19 +271,10 @@ kf_recon(KFParams p)
         lc_dst = lane < 16 ? s.lt + K2_TO(-1, lane) : s.ct[(lane >> 3) & 1] + K2_CO(-1, lane & 7);
         lc_src = lc_dst + (lane < 16 ? 16 : 8);
 #endif
-        rgb_dst = KF_WO_GROUP ? s.u.rgb + q * KF_RGB_GSTRIDE + 12 * h : s.u.rgb + (KF_RGB_PERM ? q : 2 * q) * KF_RGB_STRIDE + 12 * h;
+        rgb_dst = KF_WO_GROUP ? s.u.rgb + q * KF_RGB_GSTRIDE + 12 * h : s.u.rgb + 2 * q * KF_RGB_STRIDE + 12 * h;
     }
     const unsigned lc_sel = lane < 16 ? 7u : 3u;            /* tiles: byte 3 of the second / first 8-byte piece */
     const int pitch = 48 * W;                               /* bytes per RGB24 picture row */
-#if KF_WO_PAIR && !KF_WO_GROUP
-    /* RGB write-out of a macroblock pair: lane l takes staging row l >> 1 and the 16-byte pieces 2 k + (l & 1), k = 0..2,
-     * of its 6 (a row's two pieces of one instruction are one 32-byte sector): one lane constant for the staging address
-     * and one for the picture, the rest are immediates */
-    int wo_rd_off = (lane >> 1) * KF_RGB_STRIDE + (lane & 1) * 16, wo_g_off = (lane >> 1) * pitch + (lane & 1) * 16;
-#if KF_WO_KEEP
-    wo_rd_off = mvg_keep(wo_rd_off); wo_g_off = mvg_keep(wo_g_off);
-#endif
-#endif
 
     MvgSideInfo side;
     side.init(lane, p.mb_kind, p.i16_mode, p.chroma_mode, p.luma_modes, p.qp_y);
@@ -532,7 +517,7 @@ kf_recon(KFParams p)
                         const unsigned Y = __byte_perm(Be, Ro, 0x6240);       /* B0 R1 B2 R3 */
                         const unsigned Z = __byte_perm(Go, Bo, 0x6240);       /* G1 B1 G3 B3 */
                         unsigned *d = KF_WO_GROUP ? reinterpret_cast<unsigned *>(rgb_dst + r * 8 * KF_RGB_GSTRIDE + 48 * j)
-                                                  : reinterpret_cast<unsigned *>(rgb_dst + r * (KF_RGB_PERM ? 8 : 1) * KF_RGB_STRIDE + 48 * (j & 1));
+                                                  : reinterpret_cast<unsigned *>(rgb_dst + r * KF_RGB_STRIDE + 48 * (j & 1));
                         d[0] = __byte_perm(X, Y, 0x5410);                     /* R0 G0 B0 R1 */
                         d[1] = __byte_perm(Z, X, 0x7610);                     /* G1 B1 R2 G2 */
                         d[2] = __byte_perm(Y, Z, 0x7632);                     /* B2 R3 G3 B3 */
@@ -576,28 +561,6 @@ kf_recon(KFParams p)
                     /* the pair's 16 rows x 96 bytes (48 for a lone last macroblock): 16-byte chunks in row-major order over
                      * the lanes, so that a pair leaves as whole 32-byte sectors (96 bytes per row at a multiple of 96) */
                     const int n_here = (j & 1) + 1;
-#if KF_WO_PAIR
-                    {
-                        const uint8_t *rd = s.u.rgb + wo_rd_off;
-                        uint8_t *gd = wo_run + wo_g_off;
-#pragma unroll
-                        for (int k = 0; k < 3; k++)
-                            if (2 * k + (lane & 1) < 3 * n_here)
-                                *reinterpret_cast<uint4 *>(gd + 32 * k) = *reinterpret_cast<const uint4 *>(rd + 32 * k);
-                    }
-#elif KF_RGB_PERM
-                    {
-                        /* lane l: staging row l & 15 = picture row 2 (l & 7) + (l >> 3 & 1), 16-byte pieces 2 k + (l >> 4) of
-                         * its 6 (3 for a lone last macroblock): a row's two pieces of one instruction are one 32-byte sector */
-                        const int sr = lane & 15, cpar = lane >> 4, R = 2 * (sr & 7) + (sr >> 3);
-                        const uint8_t *rd = s.u.rgb + sr * KF_RGB_STRIDE + cpar * 16;
-                        uint8_t *gd = wo_run + (size_t)R * pitch + cpar * 16;
-#pragma unroll
-                        for (int k = 0; k < 3; k++)
-                            if (2 * k + cpar < 3 * n_here)
-                                *reinterpret_cast<uint4 *>(gd + 32 * k) = *reinterpret_cast<const uint4 *>(rd + 32 * k);
-                    }
-#else
 #pragma unroll
                     for (int k = 0; k < 3; k++) {
                         const int ch = lane + 32 * k, r = ch / 6, col = ch - r * 6;
@@ -610,7 +573,6 @@ kf_recon(KFParams p)
 #endif
                         }
                     }
-#endif
                     wo_run += 96;
                     __syncwarp();
                 }
