@@ -153,6 +153,11 @@ int mvg_run(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale);
  * bmp/tga/png formats, export.c:535-601): ONE kernel, levels in -> full-size RGB24 out, no intermediate picture
  * in HBM.  mvg_download_yuv420() is not available for these slots afterwards. */
 int mvg_run_rgb(mvg_ctx *ctx, int first_slot, int n_pics);
+/* RGB24 thumbnails and nothing else: the picture of mvg_run_rgb() averaged over rgb_scale x rgb_scale boxes (rounded;
+ * no reference counterpart).  rgb_scale 2, 4, 8, 16: ONE kernel, levels in -> thumbnail
+ * out (BASELINE.json configs[3]: "fused RGB thumbnail downscale"); rgb_scale 1 is mvg_run_rgb(); any other divisor of
+ * the picture size runs the reconstruction to tiles and kernel 3.  mvg_download_rgb() fetches the result. */
+int mvg_run_thumbs(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale);
 int mvg_sync(mvg_ctx *ctx);
 
 /* Which kernels reconstruct: the fused kernel (default; dequantisation, transforms, prediction and -- for

@@ -17,7 +17,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libmvgpu.so"
 # every symbol include/mvgpu.h declares
 EXPORTS = (
     "mvg_create", "mvg_destroy", "mvg_last_error", "mvg_set_sps", "mvg_build_level_scale",
-    "mvg_upload", "mvg_clone_slot", "mvg_run", "mvg_run_rgb", "mvg_set_pipeline_mode", "mvg_sync", "mvg_get_timing", "mvg_mark", "mvg_mark_elapsed",
+    "mvg_upload", "mvg_clone_slot", "mvg_run", "mvg_run_rgb", "mvg_run_thumbs", "mvg_set_pipeline_mode", "mvg_sync", "mvg_get_timing", "mvg_mark", "mvg_mark_elapsed",
     "mvg_download_yuv420", "mvg_download_rgb", "mvg_download_residual", "mvg_decode_host",
     "mvg_pack_batch", "mvg_decode_host_packed", "mvg_submit", "mvg_submit_packed", "mvg_wait", "mvg_poll",
     "mvg_device_count", "mvg_set_pipeline", "mvg_host_alloc", "mvg_host_free", "mvg_width", "mvg_height", "mvg_max_pics", "mvg_sm_count",
@@ -75,6 +75,7 @@ def load_library() -> C.CDLL:
     lib.mvg_clone_slot.argtypes = [vp, i32, i32]
     lib.mvg_run.argtypes = [vp, i32, i32, i32]
     lib.mvg_run_rgb.argtypes = [vp, i32, i32]
+    lib.mvg_run_thumbs.argtypes = [vp, i32, i32, i32]
     lib.mvg_set_pipeline_mode.argtypes = [vp, i32]
     lib.mvg_sync.argtypes = [vp]
     lib.mvg_get_timing.argtypes = [vp, C.POINTER(Timing)]
@@ -219,6 +220,10 @@ class Context:
     def run_rgb(self, first_slot, n_pics):
         """One fused kernel: levels -> full-size RGB24 (no tiles; download_yuv420 is not available afterwards)."""
         self._ck(self.lib.mvg_run_rgb(self.handle, first_slot, n_pics))
+
+    def run_thumbs(self, first_slot, n_pics, rgb_scale):
+        """One fused kernel for rgb_scale 2, 4, 8, 16: levels -> RGB24 at 1/rgb_scale size (no tiles)."""
+        self._ck(self.lib.mvg_run_thumbs(self.handle, first_slot, n_pics, rgb_scale))
 
     def set_pipeline_mode(self, mode: int):
         self._ck(self.lib.mvg_set_pipeline_mode(self.handle, mode))
@@ -376,7 +381,8 @@ def reconstruct(soa, device=0, rgb_scale=1, want_residual=False, mode=PIPELINE_F
     """Convenience for tests: run a whole Soa through the resident path.
     Returns dict(yuv [P, 1.5WH], rgb [P, H/s, W/s, 3] | None, rgb_k3 (the same through the tiles + kernel 3),
     residual | None).  With the fused pipeline and rgb_scale 1, `rgb` comes from mvg_run_rgb() (one kernel, levels ->
-    RGB24) and `rgb_k3` from mvg_run() (fused kernel -> tiles -> kernel 3); otherwise both are the same array."""
+    RGB24) and `rgb_k3` from mvg_run() (fused kernel -> tiles -> kernel 3); with rgb_scale 2, 4, 8, 16 `rgb` comes from
+    mvg_run_thumbs() (one kernel, levels -> thumbnail); otherwise both are the same array."""
     ctx = Context(device, soa.width_mbs, soa.height_mbs, soa.n_pics)
     try:
         ctx.set_pipeline_mode(mode)
@@ -393,6 +399,10 @@ def reconstruct(soa, device=0, rgb_scale=1, want_residual=False, mode=PIPELINE_F
             ctx.run_rgb(0, soa.n_pics)
             ctx.sync()
             rgb = np.stack([ctx.download_rgb(i, 1) for i in range(soa.n_pics)])
+        elif rgb_scale in (2, 4, 8, 16) and mode == PIPELINE_FUSED:
+            ctx.run_thumbs(0, soa.n_pics, rgb_scale)        # one kernel: levels -> thumbnail
+            ctx.sync()
+            rgb = np.stack([ctx.download_rgb(i, rgb_scale) for i in range(soa.n_pics)])
         return dict(yuv=yuv, rgb=rgb, rgb_k3=rgb_k3, residual=res, timing=timing)
     finally:
         ctx.close()

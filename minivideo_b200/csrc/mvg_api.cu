@@ -348,6 +348,10 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     TRY("occupancy k2", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2_ctas_per_sm, k2_wavefront, K2_WARPS * 32, K2_SMEM_BYTES));
     TRY("kf shared memory", cudaFuncSetAttribute(kf_recon<KF_OUT_TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES(KF_OUT_TILES)));
     TRY("kf shared memory", cudaFuncSetAttribute(kf_recon<KF_OUT_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES(KF_OUT_RGB)));
+    TRY("kf shared memory", cudaFuncSetAttribute(kf_recon<KF_OUT_RGBS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES(KF_OUT_RGBS)));
+    TRY("kf shared memory", cudaFuncSetAttribute(kf_recon<KF_OUT_RGBS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES(KF_OUT_RGBS)));
+    TRY("kf shared memory", cudaFuncSetAttribute(kf_recon<KF_OUT_RGBS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES(KF_OUT_RGBS)));
+    TRY("kf shared memory", cudaFuncSetAttribute(kf_recon<KF_OUT_RGBS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_SMEM_BYTES(KF_OUT_RGBS)));
     {
         int a = 0, b = 0;
         TRY("occupancy kf", cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, kf_recon<KF_OUT_RGB>, KF_WARPS_OF(KF_OUT_RGB) * 32, KF_SMEM_BYTES(KF_OUT_RGB)));
@@ -675,7 +679,9 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
     if (++ctx->epoch == 0) ctx->epoch = 1;      /* 0 is the value of never-written words */
 
     const bool fused = ctx->mode == MVG_PIPELINE_FUSED;
-    const bool rgb_direct = fused && rgb_scale == 1 && !want_tiles;
+    /* RGB-only requests go through one kernel: full size, or a box downscale by 2, 4, 8, 16 (other factors: tiles + kernel 3) */
+    const bool thumbs = rgb_scale == 2 || rgb_scale == 4 || rgb_scale == 8 || rgb_scale == 16;
+    const bool rgb_direct = fused && !want_tiles && (rgb_scale == 1 || thumbs);
     int launches = 0;
     if (timed) CK(ctx, cudaEventRecord(ctx->ev[0], st));
     if (!fused) {
@@ -695,7 +701,14 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         /* one CTA per SM; a small batch is spread over as many SMs as it has rows (warps without a row exit at once):
          * a row's warp then has a scheduler to itself instead of sharing it with five others */
         const int grid = (int)std::min<long long>(items, (long long)ctx->sm_count * ctx->kf_ctas_per_sm);
-        if (rgb_direct) kf_recon<KF_OUT_RGB><<<grid, KF_WARPS_OF(KF_OUT_RGB) * 32, KF_SMEM_BYTES(KF_OUT_RGB), st>>>(p);
+        if (rgb_direct && thumbs) {
+            const unsigned bt = KF_WARPS_OF(KF_OUT_RGBS) * 32;
+            const size_t sm = KF_SMEM_BYTES(KF_OUT_RGBS);
+            if (rgb_scale == 2)      kf_recon<KF_OUT_RGBS, 1><<<grid, bt, sm, st>>>(p);
+            else if (rgb_scale == 4) kf_recon<KF_OUT_RGBS, 2><<<grid, bt, sm, st>>>(p);
+            else if (rgb_scale == 8) kf_recon<KF_OUT_RGBS, 3><<<grid, bt, sm, st>>>(p);
+            else                     kf_recon<KF_OUT_RGBS, 4><<<grid, bt, sm, st>>>(p);
+        } else if (rgb_direct) kf_recon<KF_OUT_RGB><<<grid, KF_WARPS_OF(KF_OUT_RGB) * 32, KF_SMEM_BYTES(KF_OUT_RGB), st>>>(p);
         else kf_recon<KF_OUT_TILES><<<grid, KF_WARPS_OF(KF_OUT_TILES) * 32, KF_SMEM_BYTES(KF_OUT_TILES), st>>>(p);
         launches++;
     } else {
@@ -732,6 +745,15 @@ extern "C" int mvg_run(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale)
     if (check_ready(ctx, first_slot, n_pics, "mvg_run") != MVG_SUCCESS) return MVG_FAILURE;
     CK(ctx, cudaSetDevice(ctx->device));
     return launch_stages(ctx, first_slot, n_pics, rgb_scale, true, ctx->stream, true);
+}
+
+extern "C" int mvg_run_thumbs(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale)
+{
+    MvgRange nvtx_range("mvg_run_thumbs");
+    if (check_ready(ctx, first_slot, n_pics, "mvg_run_thumbs") != MVG_SUCCESS) return MVG_FAILURE;
+    if (rgb_scale < 1) return fail(ctx, "mvg_run_thumbs: rgb_scale %d", rgb_scale);
+    CK(ctx, cudaSetDevice(ctx->device));
+    return launch_stages(ctx, first_slot, n_pics, rgb_scale, false, ctx->stream, true);
 }
 
 extern "C" int mvg_run_rgb(mvg_ctx *ctx, int first_slot, int n_pics)

@@ -5,6 +5,7 @@
  *                           -> macroblock tiles (what kernel 3 / kernel 4 read)
  *   kf_recon<KF_OUT_RGB>    the same + 4:2:0 -> RGB24 of mb_to_rgb() (export_utils.c:266-303)
  *                           -> the RGB picture; nothing else is written
+ *   kf_recon<KF_OUT_RGBS>   the same + box downscale by 2, 4, 8 or 16 -> the RGB thumbnail; nothing else is written
  *
  * This is kernel 1 folded into the row loop of kernel 2 (and kernel 3 folded into its write-out), the way the
  * reference itself interleaves them per block (h264_intra_prediction.c:173,954,1929,2319 call
@@ -30,7 +31,10 @@
 #ifndef KF_WARPS_TILES
 #define KF_WARPS_TILES 28   /* tiles mode: 4.75 ms per 1000 pictures at 28 warps (24: 4.84, 30: 4.82) */
 #endif
-#define KF_WARPS_OF(out) ((out) == 1 ? KF_WARPS : KF_WARPS_TILES)
+#ifndef KF_WARPS_RGBS
+#define KF_WARPS_RGBS 28    /* thumbnail mode */
+#endif
+#define KF_WARPS_OF(out) ((out) == 1 ? KF_WARPS : (out) == 2 ? KF_WARPS_RGBS : KF_WARPS_TILES)
 #ifndef KF_COMPACT8
 #define KF_COMPACT8 false   /* true: Intra8x8 blocks through one run-time-indexed copy of the code (smaller, 4 % slower) */
 #endif
@@ -47,6 +51,8 @@
 #endif
 #define KF_OUT_TILES 0
 #define KF_OUT_RGB   1
+#define KF_OUT_RGBS  2      /* RGB24 thumbnails: the s x s box average of the RGB picture, s = 2, 4, 8, 16 */
+#define KF_RGBS_PITCH 96     /* staging row of a group in thumbnail mode: at most 4 macroblocks x 8 pixels x 3 bytes (s = 2) */
 /* RGB staging of a PAIR of macroblocks (only with KF_WO_GROUP = 0): 16 rows of 2 x 48 bytes + 16 of padding */
 #define KF_RGB_STRIDE 112
 #ifndef KF_OPAQUE_BASE
@@ -83,7 +89,7 @@ struct KFParams {
     const int8_t  *qp_y;
     const int16_t *coeff;       /* [slot][n_mb][384] levels                                           */
     uint8_t       *tiles;       /* [slot][n_mb][384] (KF_OUT_TILES)                                   */
-    uint8_t       *rgb;         /* [slot][3 * W * H] (KF_OUT_RGB)                                     */
+    uint8_t       *rgb;         /* [slot][3 * W * H] (KF_OUT_RGB), [slot][3 * (W / s) * (H / s)] (KF_OUT_RGBS) */
     uint2         *halo;        /* [slot][n_mb][8] bottom sample line of every macroblock + epoch     */
     int           *work;        /* work counter of this launch (starts at 0)                          */
     const MvgTables *tab;
@@ -106,7 +112,7 @@ template <int OUT>
 struct KFWarpSmemT {
     union {
         MvgXfScratch<KF_GROUP> x;                       /* transform stage                                      */
-        uint8_t rgb[OUT != 1 ? 16 : KF_WO_GROUP ? 16 * KF_RGB_GSTRIDE : 16 * KF_RGB_STRIDE];    /* RGB24 rows of a macroblock group / pair (prediction stage, KF_OUT_RGB) */
+        uint8_t rgb[OUT == 0 ? 16 : OUT == 2 ? 8 * KF_RGBS_PITCH : KF_WO_GROUP ? 16 * KF_RGB_GSTRIDE : 16 * KF_RGB_STRIDE];    /* RGB24 rows of a macroblock group / pair (prediction stage, KF_OUT_RGB) */
     } u;
     MVG_CANARY(c0)
     __align__(128) int16_t tile[KF_GROUP * KF_MBS];        /* levels in -> residual in place; slot j is refilled with macroblock j
@@ -150,7 +156,8 @@ struct KFWarpSmemT {
 #else
 #define KF_BOUNDS __launch_bounds__(KF_WARPS_OF(OUT) * 32, 1)
 #endif
-template <int OUT>
+template <int OUT, int SL = 2>      /* SL: log2 of the thumbnail scale (KF_OUT_RGBS only).  A template parameter, not a kernel
+                                       argument: with all four scales in one body the code outgrows the instruction cache */
 __global__ void KF_BOUNDS
 kf_recon(KFParams p)
 {
@@ -324,8 +331,12 @@ kf_recon(KFParams p)
 #endif
         unsigned nmeta = side.load(lane, (long long)mb0, min(KF_GROUP, W));
 
+        /* thumbnail mode: `per` output pixels per macroblock side, picture rows of W * per * 3 bytes */
+        constexpr int sl = SL, per = 16 >> sl;
+        const int opitch = W * per * 3;
         uint8_t *wo_run = OUT == KF_OUT_TILES ? p.tiles + mb0 * 384 + wo_off
-                                              : p.rgb + (size_t)slot * ((size_t)n_mb * 768) + (size_t)row * 16 * pitch;
+                        : OUT == KF_OUT_RGB   ? p.rgb + (size_t)slot * ((size_t)n_mb * 768) + (size_t)row * 16 * pitch
+                                              : p.rgb + ((size_t)slot * H + row) * ((size_t)per * opitch);
         uint2 *hm_run = p.halo + mb0 * 8 + lane;
         const bool availB = row > 0, publish = row < H - 1;
         const int hwords = W * 8;                               /* halo words of a macroblock row */
@@ -505,6 +516,47 @@ kf_recon(KFParams p)
                     const unsigned bC = __vsub2(((cb2 * 129u) >> 6) & 0x03ff03ffu, 0x01140114u);                   /* - 276 */
                     const unsigned gC = __vsub2(__vsub2(0x00870087u, ((cb2 * 25u) >> 6) & 0x00ff00ffu),            /* 135 - .. - .. */
                                                 ((cr2 * 13u) >> 4) & 0x00ff00ffu);
+                    if (OUT == KF_OUT_RGBS) {
+                        /* sums over my 2 x 4 pixels as int16 pairs {pixels 0, 1 | pixels 2, 3} (both rows): the two 2 x 2 cells
+                         * of s = 2; larger cells are sums over neighbouring lanes (q = lane >> 2 down, h = lane & 3 across) */
+                        unsigned aR = 0, aG = 0, aB = 0;
+#pragma unroll
+                        for (int r = 0; r < 2; r++) {
+                            const unsigned w = r ? y1 : y0;
+                            const unsigned te = ((mvg_pair_even(w) * 149u) >> 7) & 0x01ff01ffu;
+                            const unsigned to = ((mvg_pair_odd(w) * 149u) >> 7) & 0x01ff01ffu;
+                            aR += mvg_add_clip8x2(te, rC) + mvg_add_clip8x2(to, rC);
+                            aG += mvg_add_clip8x2(te, gC) + mvg_add_clip8x2(to, gC);
+                            aB += mvg_add_clip8x2(te, bC) + mvg_add_clip8x2(to, bC);
+                        }
+                        const int q = lane >> 2, h = lane & 3;
+                        if constexpr (sl == 1) {
+                            uint16_t *d = reinterpret_cast<uint16_t *>(s.u.rgb + q * KF_RGBS_PITCH + j * 24 + h * 6);
+                            const unsigned R0 = ((aR & 0xffffu) + 2) >> 2, R1 = ((aR >> 16) + 2) >> 2;
+                            const unsigned G0 = ((aG & 0xffffu) + 2) >> 2, G1 = ((aG >> 16) + 2) >> 2;
+                            const unsigned B0 = ((aB & 0xffffu) + 2) >> 2, B1 = ((aB >> 16) + 2) >> 2;
+                            d[0] = (uint16_t)(R0 | (G0 << 8)); d[1] = (uint16_t)(B0 | (R1 << 8)); d[2] = (uint16_t)(G1 | (B1 << 8));
+                        } else {
+                            unsigned R = (aR & 0xffffu) + (aR >> 16), G = (aG & 0xffffu) + (aG >> 16), B = (aB & 0xffffu) + (aB >> 16);
+                            R += __shfl_xor_sync(MVG_FULL, R, 4); G += __shfl_xor_sync(MVG_FULL, G, 4); B += __shfl_xor_sync(MVG_FULL, B, 4);
+                            if constexpr (sl >= 3) {
+                                R += __shfl_xor_sync(MVG_FULL, R, 8); G += __shfl_xor_sync(MVG_FULL, G, 8); B += __shfl_xor_sync(MVG_FULL, B, 8);
+                                R += __shfl_xor_sync(MVG_FULL, R, 1); G += __shfl_xor_sync(MVG_FULL, G, 1); B += __shfl_xor_sync(MVG_FULL, B, 1);
+                            }
+                            if constexpr (sl == 4) {
+                                R += __shfl_xor_sync(MVG_FULL, R, 16); G += __shfl_xor_sync(MVG_FULL, G, 16); B += __shfl_xor_sync(MVG_FULL, B, 16);
+                                R += __shfl_xor_sync(MVG_FULL, R, 2); G += __shfl_xor_sync(MVG_FULL, G, 2); B += __shfl_xor_sync(MVG_FULL, B, 2);
+                            }
+                            /* the first lane of a cell writes its pixel */
+                            const bool writer = sl == 2 ? !(q & 1) : sl == 3 ? !(q & 3) && !(h & 1) : lane == 0;
+                            if (writer) {
+                                constexpr unsigned rnd = 1u << (2 * sl - 1);
+                                constexpr int qs = sl > 1 ? sl - 1 : 0, hs = sl > 2 ? sl - 2 : 0;
+                                uint8_t *d = s.u.rgb + (q >> qs) * KF_RGBS_PITCH + (j * per + (h >> hs)) * 3;
+                                d[0] = (uint8_t)((R + rnd) >> (2 * sl)); d[1] = (uint8_t)((G + rnd) >> (2 * sl)); d[2] = (uint8_t)((B + rnd) >> (2 * sl));
+                            }
+                        }
+                    } else
 #pragma unroll
                     for (int r = 0; r < 2; r++) {
                         const unsigned w = r ? y1 : y0;
@@ -540,6 +592,21 @@ kf_recon(KFParams p)
                     mvg_bulk_load(tile + j * KF_MBS, lv_row + (size_t)(mx + KF_GROUP) * 384, 768u, &s.mbar);
                 }
 #endif
+                if (OUT == KF_OUT_RGBS && j == nmb - 1) {
+                    /* the group's `per` rows of nmb * per * 3 bytes: 32-bit pieces where rows are whole words (s = 2, 4), bytes
+                     * otherwise; piece idx of a full group's geometry, of which a short last group uses the first columns */
+                    constexpr int unit = sl <= 2 ? 4 : 1, ppr = KF_GROUP * per * 3 / unit, total = per * ppr;
+#pragma unroll 1
+                    for (int idx = lane; idx < total; idx += 32) {
+                        const int r = idx / ppr, c = idx - r * ppr;
+                        if (c * unit < nmb * per * 3) {
+                            if (unit == 4) *reinterpret_cast<unsigned *>(wo_run + (size_t)r * opitch + 4 * c) = *reinterpret_cast<const unsigned *>(s.u.rgb + r * KF_RGBS_PITCH + 4 * c);
+                            else wo_run[(size_t)r * opitch + c] = s.u.rgb[r * KF_RGBS_PITCH + c];
+                        }
+                    }
+                    wo_run += KF_GROUP * per * 3;
+                    __syncwarp();
+                }
 #if KF_WO_GROUP
                 if (OUT == KF_OUT_RGB && j == nmb - 1) {
                     /* the group's 16 rows x 192 bytes (48 per macroblock present) */

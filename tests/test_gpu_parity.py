@@ -83,14 +83,28 @@ def test_gpu_matches_oracle(name, mode):
     assert got["timing"].launches == (2 if mode == "fused" else 3)
 
 
+@pytest.mark.parametrize("geometry", [(12, 8), (13, 5), (1, 3)])
 @pytest.mark.parametrize("scale", [2, 4, 8, 16])
-def test_gpu_rgb_downscale_matches_oracle_box_filter(scale):
+def test_gpu_rgb_downscale_matches_oracle_box_filter(scale, geometry):
+    """Thumbnails through both routes -- mvg_run_thumbs() (the fused kernel's thumbnail mode: levels -> RGB24 at 1/scale)
+    and mvg_run() (tiles, then kernel 3) -- against the oracle's box filter; widths that are not a multiple of the
+    kernel's group of four macroblocks included.  And the end-to-end call, which takes the one-kernel route."""
     from minivideo_b200 import api, synth
     from oracle import cpu
-    _, soa = synth.generate(2, want_stream=False, width_mbs=12, height_mbs=8, profile_idc=100, transform8x8=1, seed=71)
+    w, h = geometry
+    _, soa = synth.generate(2, want_stream=False, width_mbs=w, height_mbs=h, profile_idc=100, transform8x8=1, seed=71 + w)
     want_yuv, _ = cpu.reconstruct(soa)
+    want = cpu.yuv_to_rgb(want_yuv, soa.width, soa.height, scale)
     got = api.reconstruct(soa, rgb_scale=scale)
-    assert np.array_equal(got["rgb"], cpu.yuv_to_rgb(want_yuv, soa.width, soa.height, scale))
+    assert np.array_equal(got["rgb"], want)
+    assert np.array_equal(got["rgb_k3"], want)
+    ctx = _ctx_for(soa, soa.n_pics)
+    try:
+        out = np.zeros_like(want)
+        ctx.decode_host(soa, None, out, rgb_scale=scale)
+        assert np.array_equal(out, want)
+    finally:
+        ctx.close()
 
 
 @pytest.mark.parametrize("scale", [3, 6, 12])

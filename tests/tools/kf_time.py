@@ -43,8 +43,10 @@ def timed(fn, name, digest):
 
 timed(lambda: ctx.run_rgb(0, F), "fused -> RGB24", lambda s: ctx.download_rgb(s, 1))
 timed(lambda: ctx.run(0, F, 0), "fused -> tiles", lambda s: ctx.download_yuv420(s))
+timed(lambda: ctx.run_thumbs(0, F, 4), "fused -> RGB24 at 1/4", lambda s: ctx.download_rgb(s, 4))
 if not quick:
     timed(lambda: ctx.run(0, F, 1), "fused -> tiles -> k3", lambda s: ctx.download_rgb(s, 1))
+    timed(lambda: ctx.run(0, F, 4), "fused -> tiles -> k3 at 1/4", lambda s: ctx.download_rgb(s, 4))
     ctx.set_pipeline_mode(api.PIPELINE_SPLIT)
     timed(lambda: ctx.run(0, F, 1), "split k1 k2 k3", lambda s: ctx.download_rgb(s, 1))
 ctx.close()
