@@ -282,7 +282,7 @@ extern "C" void mvg_build_luts(MvgLuts *out)
                         idx = a < b ? a : b; variant = 1;
                     } else { idx = line8(t.r[1]); variant = 2; }  /* centre (or the line end of an end tap) */
                 }
-                word |= (uint32_t)(mode == 2 ? MVG_N8_DC : 32 * variant + idx) << (16 * s);
+                word |= (uint32_t)(mode == 2 ? MVG_N8_DC : MVG_N8_IDX(idx, variant)) << (16 * s);
             }
             out->lut8[mode][lane] = word;
         }

@@ -122,7 +122,13 @@ struct KFWarpSmemT {
                                                            group and the first two words of the next one */
     MVG_CANARY(c1)
     __align__(16) uint8_t lt[MVG_LT_ROWS * MVG_LT_STRIDE];
-    __align__(16) uint8_t ct[2][MVG_CT_PLANE];
+    /* RGB modes: the chroma tiles start an ODD number of words behind the luma tile.  The hand-over of the right column
+     * (x = 15 / 7 -> x = -1) is one byte per lane, rows 0..15 of luma in lanes 0..15 and the 2 x 8 chroma rows in lanes
+     * 16..31: luma words are 10 l + const apart (16 odd banks), chroma words 6 r + const (16 even banks, Cr 80 words behind
+     * Cb) -- conflict-free only if the two sets have different parity.  The tiles mode reads chroma rows as 8-byte pieces
+     * and keeps the aligned layout. */
+    uint8_t ct_pad[4];
+    alignas(OUT == 0 ? 16 : 4) uint8_t ct[2][MVG_CT_PLANE];
     MVG_CANARY(c2)
     __align__(16) uint8_t n8[MVG_N8_BYTES];
     MVG_CANARY(c3)

@@ -54,18 +54,20 @@ struct MvgMbCtl { uint32_t w0, w1, w2, w3; };
  *   DC: row 9 = the four samples above, row 10 = the four to the left (one side available: (sum + 2) >> 2 like
  *   any other row); row 2 (both sides) = lanes with even x the four above, odd x the four to the left, the
  *   kernel adds the half-sum of lane ^ 1 and shifts by 3.
- * lut8[mode][lane]: the Intra8x8 predictors read a filtered neighbour line kept as three byte planes of 32 entries:
- *   plane 0 p', plane 1 f2 = (p'[n]+p'[n+1]+1)>>1, plane 2 f3 = (p'[n-1]+2p'[n]+p'[n+1]+2)>>2 (n = 0..7 p'[-1,7..0],
- *   8 p'[-1,-1], 9..24 p'[0..15,-1]); byte MVG_N8_DC holds the DC value.  A lane predicts two horizontally adjacent
+ * lut8[mode][lane]: the Intra8x8 predictors read a filtered neighbour line kept as 32 words of three bytes, one word per
+ *   line entry n (n = 0..7 p'[-1,7..0], 8 p'[-1,-1], 9..24 p'[0..15,-1]), written with ONE store per lane:
+ *   byte 0 p', byte 1 f2 = (p'[n]+p'[n+1]+1)>>1, byte 2 f3 = (p'[n-1]+2p'[n]+p'[n+1]+2)>>2; byte MVG_N8_DC, behind
+ *   the 32 words, holds the DC value.  A lane predicts two horizontally adjacent
  *   samples, x = 4*((lane>>3)&1) + 2*(lane&1) + {0,1}, y = 4*(lane>>4) + ((lane>>1)&3) (residual word 4*lane of the
- *   block): bits 0..15 = byte index (32 * plane + n) of sample 0, bits 16..31 = of sample 1.  The 3- and 2-tap forms
+ *   block): bits 0..15 = byte index (4 * n + variant) of sample 0, bits 16..31 = of sample 1.  The 3- and 2-tap forms
  *   of the spec always involve adjacent line entries, and the two "end" taps (p+3q) are f3 at a line end. */
 #define MVG_LUT4_BIAS    (MVG_LT_STRIDE + 1)   /* p[-1,-1] is the lowest address */
 #define MVG_N8_LEFT(y)  (7 - (y))
 #define MVG_N8_CORNER   8
 #define MVG_N8_TOP(x)   (9 + (x))
-#define MVG_N8_DC       96      /* byte index of the DC value behind the three planes */
-#define MVG_N8_BYTES    128
+#define MVG_N8_IDX(n, variant) (4 * (n) + (variant))
+#define MVG_N8_DC       128     /* byte index of the DC value behind the 32 line words */
+#define MVG_N8_BYTES    144
 
 struct MvgLuts {
     uint32_t lut4[16][32];

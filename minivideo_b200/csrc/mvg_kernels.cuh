@@ -701,7 +701,7 @@ struct K2WarpSmem {
     __align__(16) uint8_t  lt[MVG_LT_ROWS * MVG_LT_STRIDE];
     __align__(16) uint8_t  ct[2][MVG_CT_PLANE];
     MVG_CANARY(c2)
-    __align__(16) uint8_t  n8[MVG_N8_BYTES];            /* Intra8x8 neighbour line: byte planes p', f2, f3; [MVG_N8_DC] = DC */
+    __align__(16) uint8_t  n8[MVG_N8_BYTES];            /* Intra8x8 neighbour line: 32 words {p', f2, f3, -}; [MVG_N8_DC] = DC */
     MVG_CANARY(c3)
 };
 
@@ -967,7 +967,8 @@ __device__ __forceinline__ void k2_luma8_block(const K2Ctx &c, unsigned modes, u
     int fn = __shfl_down_sync(MVG_FULL, filt, 1);
     if (lane == 24) fn = filt;
     const int f2 = (filt + fn + 1) >> 1, f3 = (fp + 2 * filt + fn + 2) >> 2;
-    c.n8[lane] = (uint8_t)filt; c.n8[32 + lane] = (uint8_t)f2; c.n8[64 + lane] = (uint8_t)f3;
+    /* p', f2, f3 of my line entry as ONE word (all three are 0..255): one shared-memory wavefront instead of three */
+    reinterpret_cast<unsigned *>(c.n8)[lane] = (unsigned)filt | ((unsigned)f2 << 8) | ((unsigned)f3 << 16);
     if (mode == 2) {                                        /* warp-uniform */
         int v = 0;
         if (lane < 8 && left) v = filt;
@@ -1009,7 +1010,8 @@ __device__ __forceinline__ void k2_luma8_block_rt(const K2Ctx &c, int b8, unsign
     int fn = __shfl_down_sync(MVG_FULL, filt, 1);
     if (lane == 24) fn = filt;
     const int f2 = (filt + fn + 1) >> 1, f3 = (fp + 2 * filt + fn + 2) >> 2;
-    c.n8[lane] = (uint8_t)filt; c.n8[32 + lane] = (uint8_t)f2; c.n8[64 + lane] = (uint8_t)f3;
+    /* p', f2, f3 of my line entry as ONE word (all three are 0..255): one shared-memory wavefront instead of three */
+    reinterpret_cast<unsigned *>(c.n8)[lane] = (unsigned)filt | ((unsigned)f2 << 8) | ((unsigned)f3 << 16);
     if (mode == 2) {                                        /* warp-uniform */
         int v = 0;
         if (lane < 8 && left) v = filt;

@@ -148,6 +148,6 @@ def test_pred_tap_tables_reproduce_the_oracle_predictors():
                     for x in range(8):
                         lane = (y // 4) * 16 + (x // 4) * 8 + (y % 4) * 2 + (x % 4) // 2
                         e = (int(lut8[mode, lane]) >> (16 * (x % 2))) & 0xffff
-                        idx, var = e % 32, e // 32                          # byte plane var, entry idx
+                        idx, var = e // 4, e % 4                            # line entry idx, byte var of its word
                         pred[y, x] = variants[8 * var][idx]
                 assert np.array_equal(pred, Y[y0:y0 + 8, x0:x0 + 8]), (kind, mode)
