@@ -9,4 +9,5 @@ mkdir -p gpurun_out/$tag.src && cp minivideo_b200/csrc/mvg_kernels.cuh minivideo
 python tests/tools/kf_time.py ${KF_FRAMES:-1000} 2 quick > gpurun_out/$tag.time.txt 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:kf_recon --launch-skip 3 -c 1 -f -o gpurun_out/${tag}_rgb python tests/tools/kf_time.py ${KF_FRAMES:-1000} 1 quick > gpurun_out/$tag.ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:kf_recon --launch-skip 7 -c 1 -f -o gpurun_out/${tag}_tiles python tests/tools/kf_time.py ${KF_FRAMES:-1000} 1 quick >> gpurun_out/$tag.ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:kf_recon --launch-skip 11 -c 1 -f -o gpurun_out/${tag}_thumbs python tests/tools/kf_time.py ${KF_FRAMES:-1000} 1 quick >> gpurun_out/$tag.ncu.log 2>&1
 cat gpurun_out/$tag.time.txt
