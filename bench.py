@@ -503,7 +503,7 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         ab = algorithmic_bytes(N, W, H, scale)
         name_of = {"k1": "k1_dequant_idct", "k2": "k2_wavefront", "k3": "k3_rgb", "kf": "kf_recon"}
-        ab_of = dict(ab, kf=ab["kf_rgb"] if scale == 1 else ab["kf_tiles"])
+        ab_of = dict(ab, kf=ab["kf_rgb"] if scale == 1 else ab["kf_thumbs"] if scale in (2, 4, 8, 16) else ab["kf_tiles"])
         dom = max(mean_ms, key=mean_ms.get)
         achieved = ab_of[dom] * F / (mean_ms[dom] * 1e-3) / 1e9
         traffic = None
@@ -546,7 +546,8 @@ def run_ours(args):
                           "traffic": traffic, "peak_source": peak_src,
                           "algorithmic_bytes_per_picture": ab["survey_fused_pipeline"],
                           "basis": "SURVEY.md 8(d), k1 fused into k2: N_mb*800 + 1.5*W*H + (1.5 + 3)*W*H",
-                          "note": "kf_recon is bound by instruction issue (80 % issue-active, profiles/r02_kf_rgb_f1000_*), not by HBM"}
+                          "note": "kf_recon is bound by the shared-memory/LSU data pipe (81 % of its peak) and instruction issue (81 % issue-active), "
+                                  "not by HBM: profiles/r02_final_kf_rgb_summary.txt, profiles/r02_notes.md"}
                          if dom == "kf" and scale == 1 else
                          {"bound": "hbm", "kernel": name_of[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                           "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_picture": ab_of[dom]}),
