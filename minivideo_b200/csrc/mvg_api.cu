@@ -698,6 +698,11 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
         p.w_mbs = W; p.h_mbs = H; p.first_slot = first_slot; p.n_pics = n_pics; p.group = MVG_K2_GROUP;
         p.sel[0] = 1u; p.sel[1] = 1u << 8; p.sel[2] = 1u << 16; p.sel[3] = 1u << 24;
         p.stats = ctx->d_stats;
+        /* A launch with fewer rows than twice the GPU's warps is bound by the critical path through a picture (row r
+         * starts `stagger` macroblocks behind row r - 1), not by throughput: let its rows follow each other as closely as the
+         * group rule allows.  Large launches keep the distance that prevents rows from running in lock step. */
+        p.stagger = items < 2LL * ctx->sm_count * KF_WARPS ? KF_GROUP + 1 : KF_STAGGER;
+        if (const char *e = getenv("MVG_KF_STAGGER")) p.stagger = atoi(e);     /* DEV */
         /* one CTA per SM; a small batch is spread over as many SMs as it has rows (warps without a row exit at once):
          * a row's warp then has a scheduler to itself instead of sharing it with five others */
         const int grid = (int)std::min<long long>(items, (long long)ctx->sm_count * ctx->kf_ctas_per_sm);
@@ -921,6 +926,9 @@ static int decode_pipeline(mvg_ctx *ctx, int n_pics, uint8_t *yuv_out, uint8_t *
     if (ctx->max_pics < depth) depth = 1;
     const int region = std::max(1, ctx->max_pics / depth);
     int chunk = std::min(region, std::max(1, (n_pics + 7) / 8));
+    /* thumbnails: little to copy back, and a launch over few pictures is bound by the critical path through a picture
+     * (about 1 ms whatever their number): fewer, larger chunks */
+    if (scale > 1 && !yuv_out) chunk = std::min(region, std::max(chunk, std::min(n_pics, 128)));
     if (ctx->pipe_chunk > 0) chunk = std::min(ctx->pipe_chunk, region);
     for (int done = 0; done < n_pics; done += chunk, ctx->pipe_idx++) {
         const int cnt = std::min(chunk, n_pics - done);

@@ -42,7 +42,8 @@
 #define KF_POLL_NS 1000     /* sleep between two looks at the row above while waiting for the distance */
 #endif
 #ifndef KF_STAGGER
-#define KF_STAGGER 12       /* distance (macroblocks) a row keeps from the row above: waited for at the row start and
+#define KF_STAGGER 12       /* distance (macroblocks) a row keeps from the row above in a launch that has more rows than the
+                               GPU has warps (KFParams::stagger; smaller launches follow at the minimum): waited for at the row start and
                                again whenever the row catches up; the halo prefetch reaches 10 macroblocks ahead */
 #endif
 #ifndef KF_MBS
@@ -96,6 +97,7 @@ struct KFParams {
     const MvgLuts   *luts;
     unsigned        epoch;
     int w_mbs, h_mbs, first_slot, n_pics, group;
+    int stagger;                /* distance in macroblocks a row keeps from the row above (KF_STAGGER; less for small launches) */
     unsigned        sel[4];
     unsigned long long *stats;  /* DEV (-DKF_STATS): wait accounting, 16 counters */
 };
@@ -355,12 +357,12 @@ kf_recon(KFParams p)
         uint2 qa = make_uint2(0, epoch), qb = make_uint2(0, epoch);
 #endif
         if (availB) {
-            if (KF_STAGGER > 0) {
+            if (p.stagger > 0) {
                 /* Slack between the rows of a picture: wait here, once, until the row above is KF_STAGGER macroblocks
                  * ahead.  Rows that follow each other at the minimum distance (two macroblocks) run in lock step and
                  * every burst of the row above -- it transforms KF_GROUP macroblocks, then predicts them -- stalls all
                  * rows below in turn; with slack the per-macroblock check further down almost never fails. */
-                const uint2 *probe = p.halo + (mb0 - W + min(KF_STAGGER, W - 1)) * 8 + 7;
+                const uint2 *probe = p.halo + (mb0 - W + min(p.stagger, W - 1)) * 8 + 7;
                 KF_STAT(const long long ts = clock64();)
                 while (mvg_ld_relaxed_u64(probe).y != epoch) { __nanosleep(2000); KF_STAT(st[0]++;) }
                 KF_STAT(st[1] += clock64() - ts;)
@@ -408,7 +410,7 @@ kf_recon(KFParams p)
                     /* This row has caught up with the row above.  Do not follow it at the minimum distance: fall back until
                      * the row above is KF_STAGGER macroblocks ahead again, then reload (every word validates itself: the
                      * probe word says nothing about its neighbours). */
-                    const uint2 *probe = p.halo + (mb0 - W + min(g * KF_GROUP + max(KF_STAGGER, KF_GROUP + 1), W - 1)) * 8 + 7;
+                    const uint2 *probe = p.halo + (mb0 - W + min(g * KF_GROUP + max(p.stagger, KF_GROUP + 1), W - 1)) * 8 + 7;
                     KF_STAT(const long long ts = clock64(); st[2]++;)
                     while (mvg_ld_relaxed_u64(probe).y != epoch) { __nanosleep(KF_POLL_NS); KF_STAT(st[3]++;) }
                     KF_STAT(st[4] += clock64() - ts;)
@@ -453,7 +455,7 @@ kf_recon(KFParams p)
                          * lock step find the words they prefetch a group ahead stale every time and pay a round trip to
                          * L2 per macroblock.  Fall back until the row above is KF_STAGGER macroblocks ahead again, then
                          * reload; after that the prefetches hit for the next KF_STAGGER - 8 macroblocks at least. */
-                        const uint2 *probe = p.halo + (mb0 - W + min(mx + max(KF_STAGGER, 2), W - 1)) * 8 + 7;
+                        const uint2 *probe = p.halo + (mb0 - W + min(mx + max(p.stagger, 2), W - 1)) * 8 + 7;
                         KF_STAT(const long long ts = clock64(); st[2]++;)
                         while (mvg_ld_relaxed_u64(probe).y != epoch) { __nanosleep(KF_POLL_NS); KF_STAT(st[3]++;) }
                         KF_STAT(st[4] += clock64() - ts;)
