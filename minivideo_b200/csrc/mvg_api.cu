@@ -50,6 +50,7 @@ struct mvg_ctx {
     int device = -1, sm_count = 0;
     int k1_ctas_per_sm = 1, k2_ctas_per_sm = 1, kf_ctas_per_sm = 1;
     int mode = MVG_PIPELINE_FUSED;   /* mvg_set_pipeline_mode() */
+    int stagger_override = -1;       /* DEV: row distance of the fused kernel from the environment */
     int max_w = 0, max_h = 0, max_pics = 0;
     int w_mbs = 0, h_mbs = 0;
     bool have_sps = false;
@@ -361,6 +362,7 @@ extern "C" int mvg_create(mvg_ctx **out, int device, int max_w_mbs, int max_h_mb
     if (ctx->k1_ctas_per_sm < 1 || ctx->k2_ctas_per_sm < 1 || ctx->kf_ctas_per_sm < 1)
         return bail("kernel does not fit on an SM", cudaErrorLaunchOutOfResources);
     if (const char *m = getenv("MVG_PIPELINE")) ctx->mode = strcmp(m, "split") == 0 ? MVG_PIPELINE_SPLIT : MVG_PIPELINE_FUSED;
+    if (const char *e = getenv("MVG_KF_STAGGER")) ctx->stagger_override = std::min(std::max(atoi(e), 0), 64);
     TRY("stream", cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     TRY("stream", cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     TRY("stream", cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
@@ -702,7 +704,7 @@ static int launch_stages(mvg_ctx *ctx, int first_slot, int n_pics, int rgb_scale
          * starts `stagger` macroblocks behind row r - 1), not by throughput: let its rows follow each other as closely as the
          * group rule allows.  Large launches keep the distance that prevents rows from running in lock step. */
         p.stagger = items < 2LL * ctx->sm_count * KF_WARPS ? KF_GROUP + 1 : KF_STAGGER;
-        if (const char *e = getenv("MVG_KF_STAGGER")) p.stagger = atoi(e);     /* DEV */
+        if (ctx->stagger_override >= 0) p.stagger = ctx->stagger_override;      /* DEV: MVG_KF_STAGGER, read once at mvg_create() */
         /* one CTA per SM; a small batch is spread over as many SMs as it has rows (warps without a row exit at once):
          * a row's warp then has a scheduler to itself instead of sharing it with five others */
         const int grid = (int)std::min<long long>(items, (long long)ctx->sm_count * ctx->kf_ctas_per_sm);
