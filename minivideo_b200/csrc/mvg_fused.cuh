@@ -139,7 +139,8 @@ struct KFWarpSmemT {
 #endif
 };
 
-#define KF_LUT_BYTES  ((sizeof(MvgLuts) + 127) / 128 * 128)
+/* the shuffle-source table lut4s is last in MvgLuts and only staged when the kernel uses it */
+#define KF_LUT_BYTES  (((MVG_L4_SHFL ? sizeof(MvgLuts) : offsetof(MvgLuts, lut4s)) + 127) / 128 * 128)
 #define KF_TAB_BYTES  ((sizeof(MvgXfTables) + 127) / 128 * 128)
 #define KF_SMEM_BYTES(out) (sizeof(KFWarpSmemT<out>) * KF_WARPS_OF(out) + 2048 + KF_LUT_BYTES + KF_TAB_BYTES)
 
@@ -198,7 +199,7 @@ kf_recon(KFParams p)
         wid < n_before ? kf_smem + wid * sizeof(KFWarpSmem)
                        : kf_smem + (lut_addr - base) + KF_LUT_BYTES + KF_TAB_BYTES + (wid - n_before) * sizeof(KFWarpSmem));
 #endif
-    for (int i = threadIdx.x; i < (int)(sizeof(MvgLuts) / 16); i += blockDim.x)
+    for (int i = threadIdx.x; i < (int)(KF_LUT_BYTES / 16); i += blockDim.x)
         reinterpret_cast<uint4 *>(luts)[i] = __ldg(reinterpret_cast<const uint4 *>(p.luts) + i);
     mvg_xf_load_tables(T, p.tab);
     if (lane == 0) mvg_mbar_init(&s.mbar, 1);

@@ -19,6 +19,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "mvg_internal.h"
@@ -706,7 +707,7 @@ struct K2WarpSmem {
 };
 
 /* dynamic shared memory: warp records and the tap tables (2 KB aligned, see the kernel) */
-#define K2_LUT_BYTES  ((sizeof(MvgLuts) + 127) / 128 * 128)
+#define K2_LUT_BYTES  (((MVG_L4_SHFL ? sizeof(MvgLuts) : offsetof(MvgLuts, lut4s)) + 127) / 128 * 128)
 #define K2_SMEM_BYTES (sizeof(K2WarpSmem) * K2_WARPS + 2048 + K2_LUT_BYTES)
 
 /* 16-byte asynchronous copy global -> shared (LDGSTS), completion by per-thread groups */
@@ -1130,7 +1131,7 @@ k2_wavefront(K2Params p)
     K2WarpSmem &s = *reinterpret_cast<K2WarpSmem *>(
         wid < n_before ? k2_smem + wid * sizeof(K2WarpSmem)
                        : k2_smem + (lut_addr - base) + K2_LUT_BYTES + (wid - n_before) * sizeof(K2WarpSmem));
-    for (int i = threadIdx.x; i < (int)(sizeof(MvgLuts) / 16); i += blockDim.x)
+    for (int i = threadIdx.x; i < (int)(K2_LUT_BYTES / 16); i += blockDim.x)
         reinterpret_cast<uint4 *>(luts)[i] = __ldg(reinterpret_cast<const uint4 *>(p.luts) + i);
     __syncthreads();
 
