@@ -835,7 +835,7 @@ extern "C" int mvg_download_yuv420(mvg_ctx *ctx, int slot, uint8_t *y, uint8_t *
 {
     MvgRange nvtx_range("mvg_download_yuv420");
     if (check_ready(ctx, slot, 1, "mvg_download_yuv420") != MVG_SUCCESS) return MVG_FAILURE;
-    if (!ctx->tiles_valid) return fail(ctx, "mvg_download_yuv420: the last run produced RGB24 only (mvg_run_rgb); use mvg_run()");
+    if (!ctx->tiles_valid) return fail(ctx, "mvg_download_yuv420: the last run produced RGB24 only (mvg_run_rgb, mvg_run_thumbs); use mvg_run()");
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t n = ctx->n_mb();
     if (launch_planar(ctx, slot, 1, ctx->stream) != MVG_SUCCESS) return MVG_FAILURE;

@@ -229,6 +229,49 @@ def test_garbage_side_information_terminates_and_leaves_the_context_usable(seed)
     ctx.close()
 
 
+def test_run_thumbs_contract():
+    """mvg_run_thumbs(): scale 1 is the full-size one-kernel path, a divisor that is not 2, 4, 8, 16 falls back to tiles +
+    kernel 3 (planar picture available afterwards), the thumbnail mode leaves no planar picture behind, and a scale that
+    does not divide the picture is refused with a message.  Random garbage through the thumbnail mode terminates."""
+    from minivideo_b200 import api, synth
+    from oracle import cpu
+    _, soa = synth.generate(2, want_stream=False, width_mbs=9, height_mbs=6, profile_idc=100, transform8x8=1, seed=91)
+    want_yuv, _ = cpu.reconstruct(soa)
+    ctx = _ctx_for(soa, soa.n_pics)
+    try:
+        ctx.upload(soa, 0)
+        for scale in (1, 2, 3, 6, 8):                                       # 144 x 96: 3 and 6 divide it, 8 too
+            ctx.run_thumbs(0, soa.n_pics, scale)
+            ctx.sync()
+            want = cpu.yuv_to_rgb(want_yuv, soa.width, soa.height, scale)
+            got = np.stack([ctx.download_rgb(i, scale) for i in range(soa.n_pics)])
+            assert np.array_equal(got, want), scale
+            if scale in (3, 6):
+                assert np.array_equal(ctx.download_yuv420(0), want_yuv[0])
+            else:
+                with pytest.raises(api.MvgError, match="RGB24 only"):
+                    ctx.download_yuv420(0)
+        with pytest.raises(api.MvgError, match="rgb_scale"):
+            ctx.run_thumbs(0, soa.n_pics, 5)
+        with pytest.raises(api.MvgError, match="rgb_scale"):
+            ctx.run_thumbs(0, soa.n_pics, 0)
+        rng = np.random.default_rng(5)
+        bad = synth.generate(2, want_stream=False, width_mbs=9, height_mbs=6, profile_idc=100, transform8x8=1, seed=92)[1]
+        for name in ("mb_kind", "i16_mode", "chroma_mode", "cbp", "luma_modes"):
+            a = getattr(bad, name)
+            a[...] = rng.integers(0, 256, a.shape, dtype=np.uint8)
+        bad.qp_y[...] = rng.integers(-128, 128, bad.qp_y.shape).astype(np.int8)
+        ctx.upload(bad, 0)
+        ctx.run_thumbs(0, bad.n_pics, 4)
+        ctx.sync()                                                          # a fault or a hang would surface here
+        ctx.upload(soa, 0)
+        ctx.run_thumbs(0, soa.n_pics, 4)
+        ctx.sync()
+        assert np.array_equal(ctx.download_rgb(1, 4), cpu.yuv_to_rgb(want_yuv, soa.width, soa.height, 4)[1])
+    finally:
+        ctx.close()
+
+
 def test_async_submissions_two_batches_in_flight():
     """mvg_submit*/mvg_wait (the asynchronous boundary): several submissions in flight through one context -- different
     batches, packed and dense, RGB and YUV, a context smaller than a batch -- complete with the right bytes whatever the
