@@ -259,7 +259,7 @@ def run_ours(args):
             os.dup2(keep, 1)
             os.close(keep)
     # the host cores are shared by the ranks: each takes its share for the bitstream path
-    host_threads = max(1, (len(os.sched_getaffinity(0)) or 1) // world)
+    host_threads = args.stream_threads or max(1, (len(os.sched_getaffinity(0)) or 1) // world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -646,6 +646,7 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=384, help="pictures per end-to-end step per GPU")
     ap.add_argument("--stream-frames", type=int, default=1024, help="pictures per step of the bitstream-to-RGB measurement (0 = skip)")
     ap.add_argument("--stream-batch", type=int, default=128, help="pictures per sub-batch of the bitstream-to-RGB measurement")
+    ap.add_argument("--stream-threads", type=int, default=0, help="parser threads per GPU (0 = this rank's share of the host cores)")
     ap.add_argument("--ref-pics", type=int, default=30, help="pictures each host core decodes in the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs3", dest="configs3", action="store_false", help="skip the configs[3] block (8000 pictures, 1/4-size RGB)")
