@@ -257,15 +257,6 @@ extern "C" void mvg_build_luts(MvgLuts *out)
                     word |= (uint32_t)(off + MVG_LUT4_BIAS) << (8 * k);
                 }
                 out->lut4[row][y * 4 + x] = out->lut4[row][16 + y * 4 + x] = word;
-                /* the same taps as lanes of the neighbour vector a half warp holds (k2_luma4_step, MVG_L4_SHFL) */
-                uint32_t lanes = 0;
-                for (int k = 0; k < 4; k++) {
-                    int i = t.r[k].i;
-                    if (!t.r[k].left && !tr && i > 3) i = 3;
-                    lanes |= (uint32_t)(t.r[k].left ? 9 + i : 1 + i) << (8 * k);
-                }
-                out->lut4s[row][y * 4 + x] = lanes;
-                out->lut4s[row][16 + y * 4 + x] = lanes + 0x10101010u;
             }
     }
     auto line8 = [](Ref r) { return r.left ? MVG_N8_LEFT(r.i) : MVG_N8_TOP(r.i); };

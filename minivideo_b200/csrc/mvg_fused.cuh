@@ -56,9 +56,6 @@
 #define KF_RGBS_PITCH 96     /* staging row of a group in thumbnail mode: at most 4 macroblocks x 8 pixels x 3 bytes (s = 2) */
 /* RGB staging of a PAIR of macroblocks (only with KF_WO_GROUP = 0): 16 rows of 2 x 48 bytes + 16 of padding */
 #define KF_RGB_STRIDE 112
-#ifndef KF_OPAQUE_BASE
-#define KF_OPAQUE_BASE 1
-#endif
 /* KF_WO_GROUP: the RGB24 of a whole group of four macroblocks is staged and written out once per group.  Staging: 16
  * rows of 4 x 48 bytes + 16 of padding = 13 pieces of 16 bytes (odd: eight consecutive rows start in eight different
  * 16-byte bank groups), even picture rows in staging rows 0..7, odd ones in 8..15.  The conversion's lane 4 q + h stores
@@ -67,9 +64,6 @@
  * for the global stores too: a quarter that covers eight picture rows costs eight tag look-ups -- take 4 x 16 bytes of
  * staging row s and of s + 4 (13 s and 13 (s + 4) pieces differ by 4 modulo 8: all eight bank groups), i.e. two picture
  * rows, two 128-byte lines.  Every address is a lane constant plus an immediate. */
-#ifndef KF_LDGSTS
-#define KF_LDGSTS 0         /* 1: levels by per-lane 16-byte asynchronous copies instead of one bulk copy per macroblock + mbarrier (correct, 2 % slower) */
-#endif
 #ifndef KF_WO_GROUP
 #define KF_WO_GROUP (KF_GROUP == 4)
 #endif
@@ -77,12 +71,6 @@
 #ifndef KF_HALO_GROUP
 #define KF_HALO_GROUP (KF_GROUP == 4)   /* the halo words of the row above are validated and parked in shared memory once
                                            per group of four macroblocks (0: checked per macroblock, kept in registers) */
-#endif
-#ifndef KF_HALO_FAST
-#define KF_HALO_FAST 1      /* one comparison per macroblock while the whole group of halo words above is valid */
-#endif
-#ifndef KF_LCOL_COPY
-#define KF_LCOL_COPY 1      /* RGB mode: left-column hand-over as a one-sample-per-lane copy */
 #endif
 
 struct KFParams {
@@ -139,8 +127,7 @@ struct KFWarpSmemT {
 #endif
 };
 
-/* the shuffle-source table lut4s is last in MvgLuts and only staged when the kernel uses it */
-#define KF_LUT_BYTES  (((MVG_L4_SHFL ? sizeof(MvgLuts) : offsetof(MvgLuts, lut4s)) + 127) / 128 * 128)
+#define KF_LUT_BYTES  ((sizeof(MvgLuts) + 127) / 128 * 128)
 #define KF_TAB_BYTES  ((sizeof(MvgXfTables) + 127) / 128 * 128)
 #define KF_SMEM_BYTES(out) (sizeof(KFWarpSmemT<out>) * KF_WARPS_OF(out) + 2048 + KF_LUT_BYTES + KF_TAB_BYTES)
 
@@ -158,7 +145,7 @@ struct KFWarpSmemT {
  *      picture rows per quarter warp.
  * What the kernel runs out of first is the shared-memory/LSU data pipe and instruction issue, both at about 80 % (ncu,
  * profiles/): hence conflict-free layouts everywhere, and nothing in the row loop that the compiler could turn into a
- * special-register read (KF_OPAQUE_BASE).  The body is 49 KB of code, just under what the instruction cache holds for
+ * special-register read (the opaque base addresses below).  The body is 49 KB of code, just under what the instruction cache holds for
  * 25 warps at different places of it: unrolling one 95-instruction loop three times costs 17 % (profiles/r02_notes.md). */
 #ifdef KF_MAXREG
 #define KF_BOUNDS __maxnreg__(KF_MAXREG)        /* explicit register budget (the block size is given at launch) */
@@ -177,7 +164,6 @@ kf_recon(KFParams p)
     /* layout: the tap tables sit on the first 2 KB boundary (so that (mode << 7) can be OR-ed into a lane's
      * table address), the dequantisation tables behind them; warp records fill the space before, the rest follow */
     const unsigned base = mvg_smem_u32(kf_smem);
-#if KF_OPAQUE_BASE
     /* The addresses everything hangs on -- the tables and this warp's record -- as opaque warp-uniform 32-bit shared
      * addresses.  Left to itself the compiler carries them as (shared window base) + (offset) in two uniform registers,
      * spends two instructions per lane-dependent address on adding them up and, worse, re-derives the window base inside
@@ -190,15 +176,6 @@ kf_recon(KFParams p)
                                                : (lut_addr - base) + (unsigned)(KF_LUT_BYTES + KF_TAB_BYTES) + (wid - n_before) * (unsigned)sizeof(KFWarpSmem));
     rec_addr = __shfl_sync(MVG_FULL, mvg_keep(rec_addr), 0);
     KFWarpSmem &s = *reinterpret_cast<KFWarpSmem *>(__cvta_shared_to_generic(rec_addr));
-#else
-    const unsigned lut_addr = (base + 2047u) & ~2047u;
-    const unsigned n_before = (lut_addr - base) / (unsigned)sizeof(KFWarpSmem);
-    MvgLuts *luts = reinterpret_cast<MvgLuts *>(kf_smem + (lut_addr - base));
-    MvgXfTables &T = *reinterpret_cast<MvgXfTables *>(kf_smem + (lut_addr - base) + KF_LUT_BYTES);
-    KFWarpSmem &s = *reinterpret_cast<KFWarpSmem *>(
-        wid < n_before ? kf_smem + wid * sizeof(KFWarpSmem)
-                       : kf_smem + (lut_addr - base) + KF_LUT_BYTES + KF_TAB_BYTES + (wid - n_before) * sizeof(KFWarpSmem));
-#endif
     for (int i = threadIdx.x; i < (int)(KF_LUT_BYTES / 16); i += blockDim.x)
         reinterpret_cast<uint4 *>(luts)[i] = __ldg(reinterpret_cast<const uint4 *>(p.luts) + i);
     mvg_xf_load_tables(T, p.tab);
@@ -225,10 +202,9 @@ kf_recon(KFParams p)
     c.resid = reinterpret_cast<const uint8_t *>(s.tile);
     {
         const int half = lane >> 4, pix = lane & 15, px = pix & 3, py = pix >> 2;
-        c.lut4 = lut_addr + (MVG_L4_SHFL ? (unsigned)offsetof(MvgLuts, lut4s) : 0u) + (unsigned)lane * 4u;
+        c.lut4 = lut_addr + (unsigned)lane * 4u;
         c.h4 = half ? 0u : (unsigned)(4 * MVG_LT_STRIDE - 8);
         c.s4 = py * MVG_LT_STRIDE + px + (int)c.h4;
-        c.nb4 = (int)c.h4 + (pix >= 9 && pix <= 12 ? (pix - 9) * MVG_LT_STRIDE - 1 : pix >= 1 && pix <= 8 ? -MVG_LT_STRIDE + pix - 1 : -MVG_LT_STRIDE - 1);
         c.r4odd = pix * 2 + (half ? 64 : 0);
         c.r4even = pix * 2 + (half ? -64 : 0);
         c.m4c = half ? 0x10100010u : 0x10001000u;
@@ -247,7 +223,7 @@ kf_recon(KFParams p)
         /* the Intra4x4 step constants stay in registers (mvg_keep): without this the compiler re-derives them from the
          * lane index in every one of the ten steps.  6.58 -> 6.41 ms per 1000 pictures; keeping the Intra8x8 and the RGB
          * output offsets as well costs more in register pressure than it saves (6.51 / 7.11 ms) */
-        c.lut4 = mvg_keep(c.lut4); c.h4 = mvg_keep(c.h4); c.s4 = mvg_keep(c.s4); c.nb4 = mvg_keep(c.nb4); c.r4odd = mvg_keep(c.r4odd); c.r4even = mvg_keep(c.r4even);
+        c.lut4 = mvg_keep(c.lut4); c.h4 = mvg_keep(c.h4); c.s4 = mvg_keep(c.s4); c.r4odd = mvg_keep(c.r4odd); c.r4even = mvg_keep(c.r4even);
     }
     /* sample row -1 of the tiles comes from the halo words of the row above: lanes 0..3 luma x = 4*lane,
      * 4,5 Cb, 6,7 Cr of the macroblock above, lanes 8,9 luma x = 16..23 of the macroblock above-right */
@@ -281,12 +257,10 @@ kf_recon(KFParams p)
         wo_csrc = s.ct[0] + K2_CO(2 * h, q);
         lc_dst = s.lt + K2_TO(-1, 2 * q);
         lc_cdst = s.ct[0] + K2_CO(-1, q);
-#if KF_LCOL_COPY
         /* the left neighbour column of the next macroblock by a copy of its own, one sample per lane (rows 0..15 of
          * luma, 0..7 of Cb, 0..7 of Cr): one load and one store instead of four predicated byte stores */
         lc_dst = lane < 16 ? s.lt + K2_TO(-1, lane) : s.ct[(lane >> 3) & 1] + K2_CO(-1, lane & 7);
         lc_src = lc_dst + (lane < 16 ? 16 : 8);
-#endif
         rgb_dst = KF_WO_GROUP ? s.u.rgb + q * KF_RGB_GSTRIDE + 12 * h : s.u.rgb + 2 * q * KF_RGB_STRIDE + 12 * h;
     }
     const unsigned lc_sel = lane < 16 ? 7u : 3u;            /* tiles: byte 3 of the second / first 8-byte piece */
@@ -294,9 +268,7 @@ kf_recon(KFParams p)
 
     MvgSideInfo side;
     side.init(lane, p.mb_kind, p.i16_mode, p.chroma_mode, p.luma_modes, p.qp_y);
-#if !KF_LDGSTS
     unsigned parity = 0;            /* phase parity of the mbarrier: one phase per group */
-#endif
     KF_STAT(unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};)
 
     for (;;) {
@@ -314,22 +286,6 @@ kf_recon(KFParams p)
 
         /* group 0: levels and side information.  The buffer was last touched by this warp's generic-proxy
          * accesses (residual of an earlier group): order them before the asynchronous write. */
-#if KF_LDGSTS
-        /* per-lane 16-byte asynchronous copies (LDGSTS), 48 per macroblock: a full-warp instruction and a half-warp one.
-         * Completion by the lanes' own copy groups + __syncwarp(): no barrier object, no proxy fence, no single-lane
-         * issue sequence -- and six 128-byte shared-memory wavefronts per macroblock, where the bulk copy's writes are
-         * counted as twenty-four of 32 bytes */
-        const uint8_t *lv_lane = reinterpret_cast<const uint8_t *>(lv_row) + lane * 16;
-        uint8_t *const tile_lane = reinterpret_cast<uint8_t *>(s.tile) + lane * 16;
-        {
-            const int n0 = min(KF_GROUP, W);
-            for (int j = 0; j < n0; j++) {
-                mvg_cp_async16(tile_lane + j * (KF_MBS * 2), lv_lane + j * 768);
-                if (lane < 16) mvg_cp_async16(tile_lane + j * (KF_MBS * 2) + 512, lv_lane + j * 768 + 512);
-            }
-            mvg_cp_async_commit();
-        }
-#else
         if (lane == 0) {
             const int n0 = min(KF_GROUP, W);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -337,7 +293,6 @@ kf_recon(KFParams p)
             if (KF_MBS == 384) mvg_bulk_load(s.tile, lv_row, (unsigned)n0 * 768u, &s.mbar);
             else for (int j = 0; j < n0; j++) mvg_bulk_load(s.tile + j * KF_MBS, lv_row + j * 384, 768u, &s.mbar);
         }
-#endif
         unsigned nmeta = side.load(lane, (long long)mb0, min(KF_GROUP, W));
 
         /* thumbnail mode: `per` output pixels per macroblock side, picture rows of W * per * 3 bytes */
@@ -385,15 +340,10 @@ kf_recon(KFParams p)
             const int n_next = min(KF_GROUP, W - (g + 1) * KF_GROUP);       /* macroblocks of the next group (<= 0: none) */
             if (n_next > 0) nmeta = side.load(lane, (long long)mb0 + (g + 1) * KF_GROUP, n_next);
             int16_t *tile = s.tile;
-#if KF_LDGSTS
-            mvg_cp_async_wait<0>();
-            __syncwarp();
-#else
             mvg_mbar_wait(&s.mbar, parity);
             parity ^= 1u;
             /* the next phase collects the next group's copies, which are issued one by one below */
             if (n_next > 0 && lane == 0) mvg_mbar_expect_tx(&s.mbar, (unsigned)n_next * 768u);
-#endif
 
             /* ---- levels -> residual, in place (kernel 1's stage) ---- */
             mvg_xf_group<KF_GROUP, KF_MBS>(tile, s.u.x, T, meta, nmb, lane);
@@ -446,7 +396,7 @@ kf_recon(KFParams p)
                      * two of the next one, which sit in qb when this is the last macroblock of the group */
                     /* the common case first: all 32 words of the group are this launch's (lanes past the end of the row
                      * hold the epoch from their initialisation), and so are the two of the next group where they matter */
-                    bool all_ok = KF_HALO_FAST && okA == MVG_FULL;
+                    bool all_ok = okA == MVG_FULL;
                     if (hj == 3 && availC) all_ok = all_ok && (__ballot_sync(MVG_FULL, qb.y == epoch) & 3u) == 3u;
                     if (!all_ok) {
                       const unsigned need = availC ? 0x3FFu : 0xFFu;
@@ -512,14 +462,7 @@ kf_recon(KFParams p)
                     const unsigned y1 = *reinterpret_cast<const unsigned *>(wo_src + MVG_LT_STRIDE);
                     const unsigned cb2 = mvg_pair_lo(*reinterpret_cast<const uint16_t *>(wo_csrc));
                     const unsigned cr2 = mvg_pair_lo(*reinterpret_cast<const uint16_t *>(wo_csrc + MVG_CT_PLANE));
-#if KF_LCOL_COPY
                     *lc_dst = *lc_src;                                  /* x = 15 / 7 -> x = -1 of my row */
-#else
-                    if ((lane & 3) == 3) {      /* x = 15 of both luma rows, x = 7 of the chroma row: the next macroblock's left column */
-                        lc_dst[0] = (uint8_t)(y0 >> 24); lc_dst[MVG_LT_STRIDE] = (uint8_t)(y1 >> 24);
-                        lc_cdst[0] = (uint8_t)(cb2 >> 16); lc_cdst[MVG_CT_PLANE] = (uint8_t)(cr2 >> 16);
-                    }
-#endif
                     /* the terms that do not depend on Y: pixels x and x + 2 of a row use chroma samples c and c + 1 */
                     const unsigned rC = __vsub2(((cr2 * 204u) >> 7) & 0x01ff01ffu, 0x00de00deu);                   /* - 222 */
                     const unsigned bC = __vsub2(((cb2 * 129u) >> 6) & 0x03ff03ffu, 0x01140114u);                   /* - 276 */
@@ -588,19 +531,10 @@ kf_recon(KFParams p)
                 *cn_dst = *cn_src;
                 __syncwarp();
                 /* this macroblock's residual is spent: its slot takes macroblock j of the next group */
-#if KF_LDGSTS
-                if (j < n_next) {
-                    const uint8_t *src = lv_lane + (size_t)(mx + KF_GROUP) * 768;
-                    mvg_cp_async16(tile_lane + j * (KF_MBS * 2), src);
-                    if (lane < 16) mvg_cp_async16(tile_lane + j * (KF_MBS * 2) + 512, src + 512);
-                    mvg_cp_async_commit();
-                }
-#else
                 if (j < n_next && lane == 0) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mvg_bulk_load(tile + j * KF_MBS, lv_row + (size_t)(mx + KF_GROUP) * 384, 768u, &s.mbar);
                 }
-#endif
                 if (OUT == KF_OUT_RGBS && j == nmb - 1) {
                     /* the group's `per` rows of nmb * per * 3 bytes: 32-bit pieces where rows are whole words (s = 2, 4), bytes
                      * otherwise; piece idx of a full group's geometry, of which a short last group uses the first columns */

@@ -72,8 +72,6 @@ struct MvgMbCtl { uint32_t w0, w1, w2, w3; };
 struct MvgLuts {
     uint32_t lut4[16][32];
     uint32_t lut8[16][32];      /* rows 9..15 are zero: a mode nibble outside 0..8 (malformed input) reads entry 0, never out of bounds */
-    uint32_t lut4s[16][32];     /* lut4 as shuffle sources (MVG_L4_SHFL): byte k = the LANE that holds tap k, lane 16 * half + n holding
-                                   neighbour n of its half's block: 0 p[-1,-1], 1..8 p[0..7,-1], 9..12 p[-1,0..3] */
 };
 
 #ifdef __cplusplus

@@ -188,21 +188,6 @@ __device__ __forceinline__ unsigned mvg_pack_shr6(int hi, int lo)
     return __vsub2(t, 0x02000200u);
 }
 
-#ifndef MVG_CLS_SWAP
-#define MVG_CLS_SWAP 1      /* classification pass of mvg_xf_group: bank-conflict-free half order (0: the plain order, for comparison) */
-#endif
-#ifndef MVG_L4_SHFL
-#define MVG_L4_SHFL 0       /* 1: Intra4x4 taps by shuffles from a per-half neighbour vector instead of four byte loads per sample (correct, 1 % slower: a shuffle costs the pipe as much as the load it replaces) */
-#endif
-#ifndef MVG_DC_WHT
-#define MVG_DC_WHT 0        /* DC transforms as cross-lane butterflies (correct, but 1 % slower than the default: a few lanes per macroblock, through a scratch array -- the shuffles cost more than the divergent code they replace) */
-#endif
-#ifndef MVG_CLS_UNROLL
-#define MVG_CLS_UNROLL 0
-#endif
-#ifndef MVG_GEN_SWAP
-#define MVG_GEN_SWAP 0
-#endif
 #define K1_WARPS 12         /* warps per CTA; two CTAs per SM     */
 #define K1_GROUP 4          /* macroblocks per warp iteration     */
 #define K1_TILE  (K1_GROUP * 384)
@@ -342,43 +327,6 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
     }
 
     /* ---------------- DC transforms ---------------- */
-#if MVG_DC_WHT
-    /* Both DC transforms are Walsh-Hadamard transforms (2x2: natural order; 4x4: the standard's row order 0, 2, 3, 1 of
-     * the natural one), so they run as butterflies ACROSS lanes, one coefficient per lane: a shuffle and an add/subtract
-     * per stage, no scratch array, no lane-divergent code. */
-    {   /* chroma DC (h264_transform.c:827-936): lane = 8 j + 4 plane + k, f = A c A, then scale */
-        const int pl = (lane >> 2) & 1;
-        int v = 0;
-        if (mj < nmb) v = tile[mj * MBS + 256 + (lane & 7) * 16];
-        int t = __shfl_xor_sync(MVG_FULL, v, 1); v = (lane & 1) ? t - v : v + t;
-        t = __shfl_xor_sync(MVG_FULL, v, 2);     v = (lane & 2) ? t - v : v + t;
-        const int qe = T.qpc[pl][qp_j], qpc = qe & 255, qd = qe >> 8;
-        const int ls00 = T.ls4[((pl + 1) * 6 + (qpc - 6 * qd)) * 16];
-        if (mj < nmb) s.dc[mj][16 + (lane & 7)] = (int)((unsigned)(v * ls00) << qd) >> 5;
-    }
-    {   /* Intra16x16 luma DC (h264_transform.c:756-812): two macroblocks per pass, lane = 16 m + 4 y + x holds c[y][x]; after
-         * the four stages it holds the output whose row / column index is the inverse of 0, 2, 3, 1 at y / x */
-        const int x = lane & 3, y = (lane >> 2) & 3;
-        const int src = mvg_blk_of(x, y) * 16, dst = mvg_blk_of((0x9C >> (2 * x)) & 3, (0x9C >> (2 * y)) & 3);
-#pragma unroll 1
-        for (int p = 0; p < (G + 1) / 2; p++) {
-            const int m2 = 2 * p + (lane >> 4);
-            const unsigned kq = __shfl_sync(MVG_FULL, meta, (8 * m2 + 4) & 31), qq = __shfl_sync(MVG_FULL, meta, (8 * m2 + 5) & 31);
-            const bool act = m2 < nmb && (int)kq == MVG_MB_I16x16;
-            if (!__any_sync(MVG_FULL, act)) continue;
-            const int qp = min(max((int)(signed char)qq, 0), 51);
-            int v = act ? (int)tile[m2 * MBS + src] : 0;
-#pragma unroll
-            for (int st = 1; st < 16; st <<= 1) {
-                const int t = __shfl_xor_sync(MVG_FULL, v, st);
-                v = (lane & st) ? t - v : v + t;
-            }
-            const int qd = qp / 6, tt = v * T.ls4[(qp - 6 * qd) * 16];
-            if (act) s.dc[m2][dst] = (qp >= 36) ? (int)((unsigned)tt << (qd - 6)) : ((tt + (1 << (5 - qd))) >> (6 - qd));
-        }
-    }
-    __syncwarp();
-#else
     if (mj < nmb) {
         const int16_t *cf = tile + mj * MBS;
         if (kind_j == MVG_MB_I16x16 && mt < 4) {         /* row mt of c: t = c * H */
@@ -410,15 +358,10 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
         }
     }
     __syncwarp();
-#endif
 
     /* ---------------- classify the 4x4 blocks, compact the general ones ---------------- */
     int n4 = 0, n8 = 0;
-#if MVG_CLS_UNROLL
-#pragma unroll
-#else
 #pragma unroll 1        /* code size: the fused kernel has to fit the instruction cache */
-#endif
     for (int r = 0; r < (G * 24 + 31) / 32; r++) {
         /* u / 24 for u = lane + 32 r < 96: r, and one more from lane 24 - 8 r on */
         const int u = lane + 32 * r, j0 = G <= 4 ? r + (lane >= 24 - 8 * r) : u / 24, b = u - 24 * j0;
@@ -430,7 +373,6 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
         const int kind = mw & 255;
         const bool is8 = kind == MVG_MB_I8x8 && b < 16;
         uint4 *blk = reinterpret_cast<uint4 *>(tile + j * MBS + b * 16);
-#if MVG_CLS_SWAP
         /* a lane's block is two 16-byte halves 32 bytes apart from its neighbour's: read in the same order by all lanes,
          * the eight lanes of a quarter warp touch only four of the eight 16-byte bank groups (two wavefronts per quarter).
          * Lanes 4..7 of every eight take the second half first: 2 l + (l >> 2 & 1) covers all eight groups. */
@@ -438,12 +380,6 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
         const uint4 wa = blk[o], wb = blk[o ^ 1];
         const unsigned x0 = o ? wb.x : wa.x, x4 = o ? wa.x : wb.x;        /* first word of the first / second half */
         const unsigned rest = (x0 & 0xffff0000u) | x4 | wa.y | wa.z | wa.w | wb.y | wb.z | wb.w;
-#else
-        const int o = 0;
-        const uint4 w0 = blk[0], w1 = blk[1];
-        const unsigned x0 = w0.x;
-        const unsigned rest = (w0.x & 0xffff0000u) | w0.y | w0.z | w0.w | w1.x | w1.y | w1.z | w1.w;
-#endif
         const int dcraw = (short)(x0 & 0xffff);
         const bool nz8q = live && is8 && (rest | (x0 & 0xffffu)) != 0;
         const bool general = live && !is8 && rest != 0;
@@ -484,13 +420,7 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
             const int comp = b < 16 ? 0 : (b < 20 ? 1 : 2);
             const int qpb = comp ? (T.qpc[comp - 1][qp] & 255) : qp;
             uint4 *blk = reinterpret_cast<uint4 *>(tile + j * MBS + b * 16);
-#if MVG_GEN_SWAP    /* same half order trick as in the classification pass; the halves are swapped back with selects */
-            const int o = (lane >> 2) & 1;
-            const uint4 h0 = blk[o], h1 = blk[o ^ 1];
-            const uint4 a = o ? h1 : h0, bb = o ? h0 : h1;
-#else
             const uint4 a = blk[0], bb = blk[1];
-#endif
             int c[16];                      /* zig-zag k -> (row,col): utils.h:64 / spec Table 8-13 */
             c[0] = (short)(a.x & 0xffff); c[1] = (int)a.x >> 16; c[4] = (short)(a.y & 0xffff); c[8] = (int)a.y >> 16;
             c[5] = (short)(a.z & 0xffff); c[2] = (int)a.z >> 16; c[3] = (short)(a.w & 0xffff); c[6] = (int)a.w >> 16;
@@ -521,11 +451,7 @@ __device__ __forceinline__ void mvg_xf_group(int16_t *tile, MvgXfScratch<G> &s, 
             o0.z = mvg_pack_shr6(c[5], c[4]);   o0.w = mvg_pack_shr6(c[7], c[6]);
             o1.x = mvg_pack_shr6(c[9], c[8]);   o1.y = mvg_pack_shr6(c[11], c[10]);
             o1.z = mvg_pack_shr6(c[13], c[12]); o1.w = mvg_pack_shr6(c[15], c[14]);
-#if MVG_GEN_SWAP
-            blk[o] = o ? o1 : o0; blk[o ^ 1] = o ? o0 : o1;
-#else
             blk[0] = o0; blk[1] = o1;
-#endif
         }
     }
 
@@ -707,7 +633,7 @@ struct K2WarpSmem {
 };
 
 /* dynamic shared memory: warp records and the tap tables (2 KB aligned, see the kernel) */
-#define K2_LUT_BYTES  (((MVG_L4_SHFL ? sizeof(MvgLuts) : offsetof(MvgLuts, lut4s)) + 127) / 128 * 128)
+#define K2_LUT_BYTES  ((sizeof(MvgLuts) + 127) / 128 * 128)
 #define K2_SMEM_BYTES (sizeof(K2WarpSmem) * K2_WARPS + 2048 + K2_LUT_BYTES)
 
 /* 16-byte asynchronous copy global -> shared (LDGSTS), completion by per-thread groups */
@@ -764,8 +690,7 @@ struct K2Ctx {
     const uint8_t *lut8;        /* MvgLuts::lut8[0][lane] in shared memory */
     int lane;
     /* Intra4x4: lane = 16 * half + 4 * py + px */
-    unsigned lut4;              /* shared-memory address of lut4[0][lane] (lut4s with MVG_L4_SHFL; tables 2 KB aligned) */
-    int nb4;                    /* MVG_L4_SHFL: tile offset of neighbour lane & 15 of my half's block, relative to the half-1 block origin */
+    unsigned lut4;              /* shared-memory address of lut4[0][lane] (table 2 KB aligned) */
     int s4;                     /* tile offset of my sample relative to the origin of the half-1 block */
     int r4odd, r4even;          /* residual byte offset relative to the half-0 block, by0 odd / even */
     unsigned h4;                /* tile offset of my block relative to the half-1 block (0 or 4 rows down, 8 left) */
@@ -849,15 +774,6 @@ __device__ __forceinline__ void k2_luma4_step(const K2Ctx &c, unsigned seq, unsi
     const unsigned m = (sh >= 7 ? (seq >> (sh >= 7 ? sh - 7 : 0)) : (seq << (sh >= 7 ? 0 : 7 - sh))) & 0x780u;
     unsigned e;
     asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(m | c.lut4));
-#if MVG_L4_SHFL
-    /* The 13 neighbours of a block, one per lane of its half warp (one shared-memory wavefront), and the four taps of
-     * every sample by shuffles from the lanes the table names: 4 wavefronts per step instead of 7 (the shared-memory
-     * pipe is what this kernel runs out of first), at the same instruction count. */
-    MVG_ASSERT(c.lt + org1 + c.nb4 >= c.rec_lo && c.lt + org1 + c.nb4 < c.rec_hi, 0);
-    const int nraw = c.lt[org1 + c.nb4];
-    int sum = __shfl_sync(MVG_FULL, nraw, e) + __shfl_sync(MVG_FULL, nraw, e >> 8) +
-              __shfl_sync(MVG_FULL, nraw, e >> 16) + __shfl_sync(MVG_FULL, nraw, e >> 24) + 2;
-#else
     const uint8_t *nb = c.lt + (org1 - MVG_LUT4_BIAS);
 #ifdef MVG_CHECKED
 #pragma unroll
@@ -868,7 +784,6 @@ __device__ __forceinline__ void k2_luma4_step(const K2Ctx &c, unsigned seq, unsi
 #endif
     int sum = (int)nb[__dp4a(e, c.sel[0], c.h4)] + (int)nb[__dp4a(e, c.sel[1], c.h4)] +
               (int)nb[__dp4a(e, c.sel[2], c.h4)] + (int)nb[__dp4a(e, c.sel[3], c.h4)] + 2;
-#endif
 #ifdef MVG_CHECKED
     {
         const uint8_t *a = c.resid + blk0 * 32 + ((by0 & 1) ? c.r4odd : c.r4even);
@@ -1152,10 +1067,9 @@ k2_wavefront(K2Params p)
     c.resid = reinterpret_cast<const uint8_t *>(s.resid[0]);
     {
         const int half = lane >> 4, pix = lane & 15, px = pix & 3, py = pix >> 2;
-        c.lut4 = lut_addr + (MVG_L4_SHFL ? (unsigned)offsetof(MvgLuts, lut4s) : 0u) + (unsigned)lane * 4u;
+        c.lut4 = lut_addr + (unsigned)lane * 4u;
         c.h4 = half ? 0u : (unsigned)(4 * MVG_LT_STRIDE - 8);
         c.s4 = py * MVG_LT_STRIDE + px + (int)c.h4;
-        c.nb4 = (int)c.h4 + (pix >= 9 && pix <= 12 ? (pix - 9) * MVG_LT_STRIDE - 1 : pix >= 1 && pix <= 8 ? -MVG_LT_STRIDE + pix - 1 : -MVG_LT_STRIDE - 1);
         c.r4odd = pix * 2 + (half ? 64 : 0);
         c.r4even = pix * 2 + (half ? -64 : 0);
         c.m4c = half ? 0x10100010u : 0x10001000u;

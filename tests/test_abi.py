@@ -66,7 +66,7 @@ def test_pred_tap_tables_reproduce_the_oracle_predictors():
     from oracle import cpu
 
     class Luts(C.Structure):
-        _fields_ = [("lut4", C.c_uint32 * (16 * 32)), ("lut8", C.c_uint32 * (16 * 32)), ("lut4s", C.c_uint32 * (16 * 32))]
+        _fields_ = [("lut4", C.c_uint32 * (16 * 32)), ("lut8", C.c_uint32 * (16 * 32))]
     lib = api.load_library()
     luts = Luts()
     lib.mvg_build_luts(C.byref(luts))
@@ -84,17 +84,6 @@ def test_pred_tap_tables_reproduce_the_oracle_predictors():
         off = taps4(mode)
         top = (off + 1) // STRIDE == -1
         assert np.array_equal(taps4(row), np.where(top & (off + STRIDE > 3), -STRIDE + 3, off))
-    # lut4s: the same taps named by the lane (of a half warp) that holds the neighbour: 0 p[-1,-1], 1..8 p[0..7,-1],
-    # 9..12 p[-1,0..3]; lanes 16..31 name lanes of their own half
-    lut4s = np.frombuffer(luts.lut4s, np.uint32).reshape(16, 32)
-    nb_off = np.array([-STRIDE - 1] + [-STRIDE + i for i in range(8)] + [i * STRIDE - 1 for i in range(4)], np.int64)
-    for row in range(16):
-        lanes = np.stack([(lut4s[row, :16] >> (8 * k)) & 255 for k in range(4)], -1)
-        if not lut4[row].any():
-            assert not lut4s[row, :16].any()
-            continue
-        assert lanes.max() <= 12 and np.array_equal(nb_off[lanes], taps4(row)), row
-        assert np.array_equal(lut4s[row, 16:], lut4s[row, :16] + 0x10101010)
     rng = np.random.default_rng(1)
 
     # 2x2-MB picture: MBs 0,1,2 are I16x16 with random DC so that MB 3 sees random neighbours;
